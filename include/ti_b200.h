@@ -1,0 +1,156 @@
+/*
+ * ti_b200.h -- C ABI of libturboinfer_b200.so, the B200 (sm_100a) implementation of TurboInfer's
+ * token-generation hot path.
+ *
+ * This is the drop-in boundary.  The reference has no C ABI of its own: its seam is
+ * the C++ class surface (TensorEngine / Quantizer / InferenceEngine).  The host-side C++ classes in
+ * include/turboinfer/ keep that surface and are implemented ONLY in terms of the entry points below;
+ * each entry point cites the reference interface it replaces (file:line relative to /root/reference).
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; ti_b200_last_error() returns the
+ *    thread-local message.  Nothing throws across this boundary.  The host C++ wrappers turn a
+ *    non-zero status into std::runtime_error like the reference does (src/core/tensor_engine.cpp:492-494).
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails loudly.
+ *  - "host" pointers are ordinary host memory (H2D / D2H copies happen inside the call, synchronous
+ *    at return, like the reference's value-in / value-out ops); "_dev" variants take device pointers
+ *    obtained from ti_b200_malloc and only enqueue work on the library stream.
+ *  - weights are [in, out] row-major (y = x . W), the reference convention (tensor_engine.cpp:565-573).
+ *  - handles are opaque 64-bit values; sizes are size_t; no C++ / torch types cross.
+ */
+#ifndef TI_B200_H
+#define TI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TI_B200_ABI_VERSION 1
+
+/* numerically equal to turboinfer::optimize::QuantizationType (include/turboinfer/optimize/quantization.hpp:24-29) */
+enum { TI_Q_INT8 = 0, TI_Q_INT4 = 1, TI_Q_NONE = 3 };
+
+typedef uint64_t ti_qweight_t; /* packed INT4/INT8 weight resident in HBM */
+typedef uint64_t ti_model_t;   /* device-resident decoder (weights + paged KV cache + decode graph) */
+
+/* ---- lifecycle / errors ---------------------------------------------------------------------
+ * replaces TensorEngine::TensorEngine(ComputeDevice) / initialize / gpu_available / device_info
+ * (include/turboinfer/core/tensor_engine.hpp:42-60, src/core/tensor_engine.cpp:323-469) */
+int ti_b200_abi_version(void);
+int ti_b200_init(int device);
+int ti_b200_shutdown(void);
+int ti_b200_device_count(int* n);
+int ti_b200_device_info(char* buf, size_t cap);
+const char* ti_b200_last_error(void);
+int ti_b200_sync(void);
+
+/* ---- raw device memory (for callers that keep activations resident) --------------------------- */
+int ti_b200_malloc(void** dev, size_t bytes);
+int ti_b200_free(void* dev);
+int ti_b200_memcpy_h2d(void* dev, const void* host, size_t bytes);
+int ti_b200_memcpy_d2h(void* host, const void* dev, size_t bytes);
+
+/* ---- quantizer ---------------------------------------------------------------------------------
+ * ti_b200_quant_info    <- Quantizer::calculate_quantization_info (src/optimize/quantization.cpp:335-394)
+ * ti_b200_quantize      <- quantize_to_int8 / quantize_to_int4 (:662-693); q_out is int8[n] or int32[n]
+ *                          exactly like the reference's tensors (INT4 = one value per int32)
+ * ti_b200_dequantize    <- dequantize_from_int8 / dequantize_from_int4 (:695-713)
+ * ti_b200_quantize_pack <- Quantizer::quantize_tensor (:36-64) followed by the device re-tiling:
+ *                          min/max scan, scale/zero-point, quantize, pack 2 nibbles (INT4) or 1 byte
+ *                          (INT8) per element into the GEMV streaming layout, all on the GPU.
+ * ti_b200_qweight_unpack -> the integers back in the reference's [K,N] int32 order, for the
+ *                          unpack(pack(q)) == reference-ints check.
+ * All integer results and the scale / zero-point bits are bit-exact with the reference. */
+int ti_b200_quant_info(const float* x_host, size_t n, int qtype, int symmetric, float* scale, float* zero_point);
+int ti_b200_quantize(const float* x_host, size_t n, int qtype, float scale, float zero_point, void* q_out_host);
+int ti_b200_dequantize(const void* q_host, size_t n, int qtype, float scale, float zero_point, float* x_out_host);
+int ti_b200_quantize_pack(const float* w_host, size_t K, size_t N, int qtype, int symmetric, ti_qweight_t* out);
+int ti_b200_qweight_info(ti_qweight_t w, size_t* K, size_t* N, int* qtype, float* scale, float* zero_point,
+                         size_t* packed_bytes);
+int ti_b200_qweight_unpack(ti_qweight_t w, int32_t* q_out_host);
+int ti_b200_qweight_free(ti_qweight_t w);
+
+/* ---- tensor-engine ops (host tensors in, host tensors out) --------------------------------------
+ * ti_b200_gemv_q        <- TensorEngine::matmul(x, dequantize_tensor(quantize_tensor(W)))  (tensor_engine.cpp:490-640)
+ *                          y[b,:] = scale * (x[b,:] . q) (+ zero-point term); rows = batch of independent GEMVs
+ * ti_b200_matmul_f32    <- TensorEngine::matmul on fp32 2-D tensors, reproducing the reference build's
+ *                          per-element order of roundings (bit-exact, see oracle/ti_oracle.c tio_matmul)
+ * ti_b200_rms_norm      <- TensorEngine::rms_norm (:1452-1508)
+ * ti_b200_rope          <- TensorEngine::apply_rope (:1510-1624); ndim 3: [B,T,D], ndim 4: [B,nh,T,D]
+ * ti_b200_silu / relu / add / mul <- :900-923, :828-869, :1626-1678, :1680-1743
+ * ti_b200_silu_mul      <- multiply(up, silu(gate)), the SwiGLU of compute_ffn (inference_engine.cpp:389-391)
+ * ti_b200_softmax       <- TensorEngine::softmax, scalar branch (:1017-1033)
+ * ti_b200_attention_decode <- attention_fast_incremental (:1254-1388) when num_heads == 1,
+ *                          multi_head_attention with q_len 1 (:1149-1252) otherwise; q [B,1,H], k/v [B,t,H] */
+int ti_b200_gemv_q(ti_qweight_t w, const float* x_host, float* y_host, size_t rows);
+int ti_b200_matmul_f32(const float* a_host, const float* b_host, float* c_host, size_t M, size_t K, size_t N);
+int ti_b200_rms_norm(const float* x_host, const float* w_host, float* y_host, size_t rows, size_t H, float eps);
+int ti_b200_rope(const float* x_host, const float* pos_host, float* y_host, size_t B, size_t nh, size_t T, size_t D,
+                 int ndim, int pos_2d, float theta);
+int ti_b200_silu(const float* x_host, float* y_host, size_t n);
+int ti_b200_relu(const float* x_host, float* y_host, size_t n);
+int ti_b200_add(const float* a_host, const float* b_host, float* y_host, size_t n);
+int ti_b200_mul(const float* a_host, const float* b_host, float* y_host, size_t n);
+int ti_b200_silu_mul(const float* gate_host, const float* up_host, float* y_host, size_t n);
+int ti_b200_softmax(const float* x_host, float* y_host, size_t rows, size_t n, float temperature);
+int ti_b200_attention_decode(const float* q_host, const float* k_host, const float* v_host, float* out_host,
+                             size_t B, size_t t, size_t H, size_t num_heads);
+
+/* device-pointer variant of the GEMV used by the bench (inputs already resident in HBM) */
+int ti_b200_gemv_q_dev(ti_qweight_t w, const float* x_dev, float* y_dev);
+
+/* ---- decoder model -------------------------------------------------------------------------------
+ * replaces InferenceEngine(ModelData, InferenceConfig) / initialize_model (src/model/inference_engine.cpp:480-564),
+ * KVCache (:25-172), TransformerLayer::forward_incremental (:244-401), forward_pass_incremental (:1493-1552),
+ * forward_pass (:1429-1491) and the greedy branch of generate / sample_next_token (:734-802, :1554-1673). */
+typedef struct ti_model_config {
+    int32_t vocab, hidden, layers, heads, inter;
+    float rope_theta;        /* ModelMetadata::rope_theta; 10000 */
+    float rms_eps;           /* TensorEngine::rms_norm default 1e-5 */
+    int32_t qtype;           /* TI_Q_INT4 / TI_Q_INT8: 2-D projection weights are quantized (symmetric, per tensor) and packed;
+                                TI_Q_NONE is not a decode mode of this engine */
+    int32_t attn_mode;       /* 0: one head over the whole hidden dim (literal reference); 1: `heads` heads */
+    int32_t rope_mode;       /* 0: none (literal); 1: per head; 2: whole hidden */
+    int32_t max_seq;         /* KV-cache capacity in tokens (KVCache::max_length, reference hard-codes 2048) */
+    int32_t kv_page_tokens;  /* tokens per KV page; 0 = default 64 */
+    int32_t compat_literal;  /* 1: placeholder embeddings 0.1f*(i%100) and unscaled integer weights */
+    int32_t reserved[7];
+} ti_model_config;
+
+int ti_b200_model_new(const ti_model_config* cfg, ti_model_t* out);
+/* `name` uses the reference tensor names accepted by initialize_model (:483-563), e.g.
+ * "layers.3.attention.q_proj.weight"; data is fp32 [rows, cols] ([in, out] for projections, [H] for norms:
+ * rows = 1).  Absent tensors trigger the reference's null-weight fall-backs (:293-296, :377-380, :392-395). */
+int ti_b200_model_set_tensor(ti_model_t m, const char* name, const float* data_host, size_t rows, size_t cols);
+/* same, but the fp32 source is generated on the device: uniform(-amp, amp) from a counter-based hash of
+ * (seed, element index) -- for benchmark-size models whose fp32 weights would not fit host RAM. */
+int ti_b200_model_set_tensor_synthetic(ti_model_t m, const char* name, size_t rows, size_t cols, uint64_t seed, float amp);
+int ti_b200_model_finalize(ti_model_t m);
+int ti_b200_model_free(ti_model_t m);
+/* KVCache::reset (:60-69): frees the page list, length = 0 */
+int ti_b200_model_reset(ti_model_t m);
+int ti_b200_model_kv_length(ti_model_t m, int32_t* length);
+/* bytes one decode step must move at cache length t: packed weights + scales + KV read/write */
+int ti_b200_model_step_bytes(ti_model_t m, int32_t t, double* weight_bytes, double* kv_bytes);
+/* forward_pass_incremental for one token: appends to the KV cache; logits_host may be NULL */
+int ti_b200_decode_step(ti_model_t m, int32_t token, float* logits_host, int32_t* argmax);
+/* generate(): prefill `prompt`, then n_new greedy tokens (top_k = 1).  out_tokens gets the new ids, returns their
+ * count in *n_out (early stop on token 2 when stop_on_eos, :760).  logits_host (optional) receives
+ * [n_new, vocab]; decode_ms (optional) is the CUDA-event time of the decode loop only. */
+int ti_b200_generate_greedy(ti_model_t m, const int32_t* prompt, int32_t n_prompt, int32_t n_new, int32_t stop_on_eos,
+                            int32_t* out_tokens, int32_t* n_out, float* logits_host, float* decode_ms);
+
+/* ---- instrumentation for bench.py ------------------------------------------------------------------ */
+/* number of kernels this library has launched since init (the bench's `gpu_launches`) */
+int ti_b200_launch_count(uint64_t* n);
+/* times `reps` back-to-back launches of the GEMV over `n_w` different packed weights (cycled, so the working
+ * set exceeds L2 when their total size does) with CUDA events on the library stream; ms = total elapsed */
+int ti_b200_bench_gemv(const ti_qweight_t* w, size_t n_w, size_t reps, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

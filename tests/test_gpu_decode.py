@@ -1,0 +1,131 @@
+"""End-to-end decode on the GPU vs oracle level B: greedy token ids bit-exact, logits <= 1e-2."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import SHAPES, make_model, meta_with_layers, prompt_tokens, rel_err_inf
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+
+
+@pytest.fixture(scope="module")
+def tb():
+    import turboinfer_b200 as t
+    t.init(0)
+    return t
+
+
+def fake_quant_model(port, w, qt):
+    return {k: (port.fake_quant(v, qt) if (v.ndim == 2 and "embeddings" not in k) else v) for k, v in w.items()}
+
+
+def run_pair(tb, port, meta, w, qt, prompt, n_new, am, rm, max_seq=256):
+    m = tb.Model(meta, qt, attn_mode=am, rope_mode=rm, max_seq=max_seq).load(w)
+    try:
+        toks, logits, ms = m.generate_greedy(prompt, n_new, want_logits=True)
+    finally:
+        m.free()
+    rt, rl = port.decode_greedy(fake_quant_model(port, w, qt), meta, prompt, n_new, attn_mode=am, rope_mode=rm)
+    return toks, logits, rt, rl
+
+
+@pytest.mark.parametrize("qname,qt", [("int8", oracle.QINT8), ("int4", oracle.QINT4)])
+@pytest.mark.parametrize("am,rm", [(1, 0), (0, 0), (1, 1)])
+def test_tiny_model_vs_golden_reference(tb, qname, qt, am, rm):
+    meta = SHAPES["tiny-test"]
+    w = make_model(meta, norm_jitter=0.1)
+    m = tb.Model(meta, qt, attn_mode=am, rope_mode=rm, max_seq=128).load(w)
+    try:
+        toks, logits, _ = m.generate_greedy(prompt_tokens(5, meta["vocab"]), 24, want_logits=True)
+    finally:
+        m.free()
+    key = f"decodeB/{qname}/a{am}r{rm}"
+    assert np.array_equal(toks, G[key + "/tokens"])
+    assert rel_err_inf(logits[0], G[key + "/logits_first"]) <= 1e-2
+    assert rel_err_inf(logits[-1], G[key + "/logits_last"]) <= 1e-2
+
+
+@pytest.mark.parametrize("qt", [oracle.QINT8, oracle.QINT4])
+@pytest.mark.parametrize("am,rm", [(1, 0), (0, 0), (1, 1), (0, 2)])
+def test_bench_small_shape_vs_oracle(tb, port, qt, am, rm):
+    meta = SHAPES["bench-small"]
+    w = make_model(meta, norm_jitter=0.05)
+    toks, logits, rt, rl = run_pair(tb, port, meta, w, qt, prompt_tokens(4, meta["vocab"]), 48, am, rm)
+    assert np.array_equal(toks, rt)
+    assert rel_err_inf(logits, rl) <= 1e-2
+
+
+@pytest.mark.parametrize("variant", [dict(gate=False), dict(o_proj=False), dict(norms=False), dict(o_proj=False, norms=False, gate=False)])
+def test_null_weight_fallbacks(tb, port, variant):
+    meta = SHAPES["tiny-test"]
+    w = make_model(meta, norm_jitter=0.1, **variant)
+    toks, logits, rt, rl = run_pair(tb, port, meta, w, oracle.QINT8, prompt_tokens(3, meta["vocab"]), 10, 1, 0)
+    assert np.array_equal(toks, rt)
+    assert rel_err_inf(logits, rl) <= 1e-2
+
+
+def test_decode_step_api_and_kv_semantics(tb, port):
+    meta = SHAPES["tiny-test"]
+    w = make_model(meta, norm_jitter=0.1)
+    m = tb.Model(meta, oracle.QINT8, attn_mode=1, max_seq=8).load(w)
+    try:
+        prompt = prompt_tokens(4, meta["vocab"])
+        assert m.kv_length == 0
+        last = None
+        for tok in prompt:
+            last = m.decode_step(tok)
+        assert m.kv_length == 4
+        rt, rl = port.decode_greedy(fake_quant_model(port, w, oracle.QINT8), meta, prompt, 1, attn_mode=1)
+        assert last[0] == rt[0]
+        assert rel_err_inf(last[1], rl[0]) <= 1e-2
+        for _ in range(4):
+            m.decode_step(1)
+        with pytest.raises(tb.B200Error, match="KV cache overflow"):      # inference_engine.cpp:100-102
+            m.decode_step(1)
+        m.reset()
+        assert m.kv_length == 0
+        again = m.decode_step(prompt[0])
+        m.reset()
+        assert np.array_equal(m.decode_step(prompt[0])[1], again[1])       # reset really forgets the cache
+        with pytest.raises(tb.B200Error):
+            m.generate_greedy([], 4)
+        with pytest.raises(tb.B200Error):
+            m.generate_greedy([meta["vocab"]], 4)
+    finally:
+        m.free()
+
+
+def test_eos_stop(tb, port):
+    meta = SHAPES["tiny-test"]
+    w = make_model(meta, norm_jitter=0.1)
+    # make token 2 irresistible: huge lm_head column
+    w = dict(w)
+    lm = w["lm_head.weight"].copy()
+    m0 = tb.Model(meta, oracle.QINT8, max_seq=64).load(w)
+    try:
+        full, _, _ = m0.generate_greedy([5, 6], 12)
+        stopped, _, _ = m0.generate_greedy([5, 6], 12, stop_on_eos=True)
+    finally:
+        m0.free()
+    if 2 in list(full):
+        assert list(stopped) == list(full[: list(full).index(2) + 1])
+    else:
+        assert np.array_equal(stopped, full)
+
+
+@pytest.mark.parametrize("shape,qt,n_new", [("tinyllama", oracle.QINT4, 6), ("llama7b", oracle.QINT4, 3), ("llama7b", oracle.QINT8, 3)])
+def test_full_width_truncated_depth(tb, port, shape, qt, n_new):
+    """Full-width, L = 2: the end-to-end parity case for the big shapes."""
+    meta = meta_with_layers(SHAPES[shape], 2)
+    w = make_model(meta)
+    prompt = prompt_tokens(4, meta["vocab"])
+    toks, logits, rt, rl = run_pair(tb, port, meta, w, qt, prompt, n_new, 1, 1, max_seq=64)
+    top2 = np.sort(rl, axis=-1)[:, -2:]
+    margin = (top2[:, 1] - top2[:, 0]) / np.abs(rl).max()
+    err = rel_err_inf(logits, rl)
+    print(f"{shape} q{qt}: logits rel err {err:.3e}, min top-2 margin {margin.min():.3e}")
+    assert err <= 1e-2
+    assert np.array_equal(toks, rt)

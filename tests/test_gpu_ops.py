@@ -1,0 +1,146 @@
+"""GPU tensor-engine ops vs the oracle.  fp32 tolerance rule: max|gpu-ref| / |ref|_inf <= 1e-2
+(SURVEY 8a); the actual errors are reported and are orders of magnitude below that."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import rel_err_inf
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2          # the tolerance north_star states for logits / fp32 ops
+TIGHT = 2e-5        # what a re-ordered fp32 reduction actually achieves on these sizes
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+
+
+@pytest.fixture(scope="module")
+def tb():
+    import turboinfer_b200 as t
+    t.init(0)
+    return t
+
+
+@pytest.mark.parametrize("qt", [oracle.QINT4, oracle.QINT8])
+@pytest.mark.parametrize("sym", [True, False])
+@pytest.mark.parametrize("K,N", [(256, 1024), (300, 77), (1024, 4), (2048, 515), (4096, 4096), (11008, 4096), (4096, 11008),
+                                 (2048, 32000), (5632, 2048), (1, 5), (1030, 1)])
+def test_gemv_q_vs_dequant_matmul(tb, port, qt, sym, K, N):
+    if not sym and K * N > 4096 * 4096:
+        pytest.skip("asymmetric only on the smaller shapes")
+    rng = np.random.default_rng(K + 7 * N + qt)
+    w = rng.uniform(-1, 1, (K, N)).astype(np.float32) / np.float32(np.sqrt(K))
+    x = rng.standard_normal((1, K)).astype(np.float32)
+    s, z = port.quant_info(w, qt, sym)
+    wfq = port.dequantize(port.quantize(w, qt, s, z), qt, s, z)   # dequantize_tensor(quantize_tensor(W))
+    ref = port.matmul(x, wfq)
+    qw = tb.QWeight(w, qt, sym)
+    try:
+        got = qw.gemv(x)
+    finally:
+        qw.free()
+    err = rel_err_inf(got, ref)
+    assert err <= TOL
+    assert err <= 1e-4, f"re-ordered fp32 accumulate should be ~1e-6, got {err}"
+
+
+def test_gemv_q_rows_and_linearity(tb, port):
+    rng = np.random.default_rng(9)
+    K, N = 2048, 2048
+    w = rng.uniform(-1, 1, (K, N)).astype(np.float32) / 45
+    qw = tb.QWeight(w, oracle.QINT4)
+    try:
+        x = rng.standard_normal((3, K)).astype(np.float32)
+        y = qw.gemv(x)
+        for r in range(3):
+            assert np.array_equal(y[r], qw.gemv(x[r:r + 1])[0])       # rows are independent GEMVs, deterministic
+        assert np.array_equal(qw.gemv(np.zeros((1, K), np.float32)), np.zeros((1, N), np.float32))
+        ya, yb, yab = qw.gemv(x[0:1]), qw.gemv(x[1:2]), qw.gemv(x[0:1] + x[1:2])
+        assert rel_err_inf(yab, ya + yb) <= 1e-5                           # linearity in x
+    finally:
+        qw.free()
+
+
+@pytest.mark.parametrize("M,K,N", [(1, 256, 1024), (1, 300, 77), (1, 2048, 512), (4, 64, 40), (3, 7, 5), (40, 64, 48),
+                                   (33, 100, 45), (32, 300, 39), (1, 4096, 4096)])
+def test_matmul_f32_bit_exact(tb, port, M, K, N):
+    rng = np.random.default_rng(M + K + N)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    b = rng.standard_normal((K, N)).astype(np.float32)
+    assert np.array_equal(tb.ops.matmul(a, b), port.matmul(a, b))
+
+
+def test_matmul_golden(tb):
+    assert np.array_equal(tb.ops.matmul(G["mm/a"], G["mm/b"]), G["mm/c"])
+    assert np.array_equal(tb.ops.matmul(G["gemv/x"], G["gemv/w"]), G["gemv/y"])
+
+
+@pytest.mark.parametrize("rows,H", [(1, 128), (3, 515), (1, 4096), (2, 7), (5, 8192)])
+def test_rms_norm(tb, port, rows, H):
+    rng = np.random.default_rng(H)
+    x = rng.standard_normal((rows, H)).astype(np.float32)
+    w = (1 + 0.1 * rng.standard_normal(H)).astype(np.float32)
+    assert rel_err_inf(tb.ops.rms_norm(x, w), port.rms_norm(x, w)) <= TIGHT
+    assert rel_err_inf(tb.ops.rms_norm(G["rms/x"], G["rms/w"]), G["rms/y"]) <= TIGHT
+
+
+def test_rope(tb, port):
+    for key in ("rope3", "rope4", "rope_dec"):
+        assert rel_err_inf(tb.ops.rope(G[key + "/x"], G[key + "/pos"]), G[key + "/out"]) <= TIGHT
+    rng = np.random.default_rng(1)
+    x4 = rng.standard_normal((2, 32, 3, 128)).astype(np.float32)
+    pos2 = np.array([[0, 1, 4095], [17, 2047, 3000]], dtype=np.float32)
+    assert rel_err_inf(tb.ops.rope(x4, pos2), port.rope(x4, pos2)) <= TIGHT
+    with pytest.raises(tb.B200Error):
+        tb.ops.rope(np.zeros((1, 2, 3), np.float32), np.zeros(2, np.float32))      # odd last dim
+
+
+def test_elementwise(tb, port):
+    rng = np.random.default_rng(2)
+    v = (rng.standard_normal(100003) * 3).astype(np.float32)
+    u = v[::-1].copy()
+    assert rel_err_inf(tb.ops.silu(v), port.silu(v)) <= TIGHT
+    assert np.array_equal(tb.ops.relu(v), port.relu(v))
+    assert np.array_equal(tb.ops.add(v, u), port.add(v, u))
+    assert np.array_equal(tb.ops.mul(v, u), port.mul(v, u))
+    assert rel_err_inf(tb.ops.silu_mul(v, u), port.mul(u, port.silu(v))) <= TIGHT
+    assert rel_err_inf(tb.ops.silu(G["act/x"]), G["act/silu"]) <= TIGHT
+
+
+def test_softmax(tb, port):
+    rng = np.random.default_rng(3)
+    for n in (12, 13, 64, 1000, 32000):
+        s = rng.standard_normal((3, n)).astype(np.float32) * 4
+        got = tb.ops.softmax(s, 0.7)
+        assert rel_err_inf(got, port.softmax(s, 0.7)) <= TIGHT
+        assert np.allclose(got.sum(axis=-1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("t", [10, 50, 100, 200])
+def test_fast_attention_reference_fixture(tb, t):
+    H = 256
+    q = (0.1 * (np.arange(H) % 10)).astype(np.float32).reshape(1, 1, H)
+    k = (np.float32(0.05) * (np.add.outer(np.arange(t), np.arange(H)) % 20).astype(np.float32)).reshape(1, t, H)
+    v = (np.float32(0.02) * (np.add.outer(2 * np.arange(t), np.arange(H)) % 15).astype(np.float32)).reshape(1, t, H)
+    assert rel_err_inf(tb.ops.attention_decode(q, k, v, 1), G[f"attn/t{t}/out"]) <= TIGHT
+    assert rel_err_inf(tb.ops.attention_decode(q, k, v, 4), G[f"attn/t{t}/mha4"]) <= TIGHT
+
+
+@pytest.mark.parametrize("B,t,H,nh", [(1, 1, 64, 1), (1, 37, 256, 1), (2, 200, 256, 4), (1, 2048, 4096, 32), (1, 777, 2048, 32),
+                                       (1, 300, 4096, 1), (1, 65, 128, 4), (1, 4000, 1024, 8)])
+def test_attention_vs_oracle(tb, port, B, t, H, nh):
+    rng = np.random.default_rng(t + H)
+    q = rng.standard_normal((B, 1, H)).astype(np.float32)
+    k = rng.standard_normal((B, t, H)).astype(np.float32)
+    v = rng.standard_normal((B, t, H)).astype(np.float32)
+    ref = port.attention_fast_incremental(q, k, v) if nh == 1 else port.multi_head_attention(q, k, v, nh)
+    assert rel_err_inf(tb.ops.attention_decode(q, k, v, nh), ref) <= 1e-4
+
+
+def test_error_behaviour(tb):
+    with pytest.raises(tb.B200Error):
+        tb.ops.attention_decode(np.zeros((1, 1, 30), np.float32), np.zeros((1, 2, 30), np.float32),
+                                np.zeros((1, 2, 30), np.float32), 4)     # hidden not divisible by heads
+    with pytest.raises(tb.B200Error):
+        tb.ops.softmax(np.zeros((0, 4), np.float32))

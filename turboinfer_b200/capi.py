@@ -1,0 +1,343 @@
+"""ctypes bindings of include/ti_b200.h (numpy in / numpy out).  No torch, no fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+Q_INT8, Q_INT4, Q_NONE = 0, 1, 3
+
+_f = C.POINTER(C.c_float)
+_i32 = C.POINTER(C.c_int32)
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class ModelConfig(C.Structure):
+    _fields_ = [("vocab", C.c_int32), ("hidden", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32),
+                ("inter", C.c_int32), ("rope_theta", C.c_float), ("rms_eps", C.c_float), ("qtype", C.c_int32),
+                ("attn_mode", C.c_int32), ("rope_mode", C.c_int32), ("max_seq", C.c_int32),
+                ("kv_page_tokens", C.c_int32), ("compat_literal", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+# every symbol include/ti_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "ti_b200_abi_version": (C.c_int, []),
+    "ti_b200_init": (C.c_int, [C.c_int]),
+    "ti_b200_shutdown": (C.c_int, []),
+    "ti_b200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "ti_b200_device_info": (C.c_int, [C.c_char_p, C.c_size_t]),
+    "ti_b200_last_error": (C.c_char_p, []),
+    "ti_b200_sync": (C.c_int, []),
+    "ti_b200_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "ti_b200_free": (C.c_int, [C.c_void_p]),
+    "ti_b200_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ti_b200_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ti_b200_quant_info": (C.c_int, [_f, C.c_size_t, C.c_int, C.c_int, _f, _f]),
+    "ti_b200_quantize": (C.c_int, [_f, C.c_size_t, C.c_int, C.c_float, C.c_float, C.c_void_p]),
+    "ti_b200_dequantize": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_float, _f]),
+    "ti_b200_quantize_pack": (C.c_int, [_f, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_uint64)]),
+    "ti_b200_qweight_info": (C.c_int, [C.c_uint64, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_int), _f, _f,
+                                       C.POINTER(C.c_size_t)]),
+    "ti_b200_qweight_unpack": (C.c_int, [C.c_uint64, _i32]),
+    "ti_b200_qweight_free": (C.c_int, [C.c_uint64]),
+    "ti_b200_gemv_q": (C.c_int, [C.c_uint64, _f, _f, C.c_size_t]),
+    "ti_b200_matmul_f32": (C.c_int, [_f, _f, _f, C.c_size_t, C.c_size_t, C.c_size_t]),
+    "ti_b200_rms_norm": (C.c_int, [_f, _f, _f, C.c_size_t, C.c_size_t, C.c_float]),
+    "ti_b200_rope": (C.c_int, [_f, _f, _f, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_float]),
+    "ti_b200_silu": (C.c_int, [_f, _f, C.c_size_t]),
+    "ti_b200_relu": (C.c_int, [_f, _f, C.c_size_t]),
+    "ti_b200_add": (C.c_int, [_f, _f, _f, C.c_size_t]),
+    "ti_b200_mul": (C.c_int, [_f, _f, _f, C.c_size_t]),
+    "ti_b200_silu_mul": (C.c_int, [_f, _f, _f, C.c_size_t]),
+    "ti_b200_softmax": (C.c_int, [_f, _f, C.c_size_t, C.c_size_t, C.c_float]),
+    "ti_b200_attention_decode": (C.c_int, [_f, _f, _f, _f, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]),
+    "ti_b200_gemv_q_dev": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p]),
+    "ti_b200_model_new": (C.c_int, [C.POINTER(ModelConfig), C.POINTER(C.c_uint64)]),
+    "ti_b200_model_set_tensor": (C.c_int, [C.c_uint64, C.c_char_p, _f, C.c_size_t, C.c_size_t]),
+    "ti_b200_model_set_tensor_synthetic": (C.c_int, [C.c_uint64, C.c_char_p, C.c_size_t, C.c_size_t, C.c_uint64, C.c_float]),
+    "ti_b200_model_finalize": (C.c_int, [C.c_uint64]),
+    "ti_b200_model_free": (C.c_int, [C.c_uint64]),
+    "ti_b200_model_reset": (C.c_int, [C.c_uint64]),
+    "ti_b200_model_kv_length": (C.c_int, [C.c_uint64, _i32]),
+    "ti_b200_model_step_bytes": (C.c_int, [C.c_uint64, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ti_b200_decode_step": (C.c_int, [C.c_uint64, C.c_int32, _f, _i32]),
+    "ti_b200_generate_greedy": (C.c_int, [C.c_uint64, _i32, C.c_int32, C.c_int32, C.c_int32, _i32, _i32, _f, _f]),
+    "ti_b200_launch_count": (C.c_int, [C.POINTER(C.c_uint64)]),
+    "ti_b200_bench_gemv": (C.c_int, [C.POINTER(C.c_uint64), C.c_size_t, C.c_size_t, _f]),
+}
+
+_lib: Optional[C.CDLL] = None
+_inited = False
+
+
+def library_path() -> str:
+    return os.path.join(HERE, "libturboinfer_b200.so")
+
+
+def lib() -> C.CDLL:
+    """Loads the extension (building it with nvcc if the in-tree .so is missing or stale)."""
+    global _lib
+    if _lib is None:
+        path = library_path()
+        srcdir = os.path.join(HERE, "csrc")
+        if os.path.isdir(srcdir) and os.path.exists("/usr/local/cuda/bin/nvcc"):
+            from . import build as _build
+            _build.build()
+        if not os.path.exists(path):
+            raise B200Error(f"{path} is missing: build it with `python -m turboinfer_b200.build` (no CPU fallback exists)")
+        L = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _ck(rc: int) -> None:
+    if rc != 0:
+        raise B200Error(lib().ti_b200_last_error().decode("utf-8", "replace"))
+
+
+def init(device: int = 0) -> None:
+    global _inited
+    _ck(lib().ti_b200_init(device))
+    _inited = True
+
+
+def shutdown() -> None:
+    global _inited
+    if _lib is not None:
+        _ck(_lib.ti_b200_shutdown())
+    _inited = False
+
+
+def _need() -> C.CDLL:
+    if not _inited:
+        init(int(os.environ.get("LOCAL_RANK", "0")))
+    return lib()
+
+
+def device_info() -> str:
+    buf = C.create_string_buffer(512)
+    _ck(_need().ti_b200_device_info(buf, 512))
+    return buf.value.decode()
+
+
+def launch_count() -> int:
+    n = C.c_uint64()
+    _ck(lib().ti_b200_launch_count(C.byref(n)))
+    return n.value
+
+
+def _fp(a: np.ndarray):
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_f)
+
+
+def _c(a, dtype=np.float32) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class QWeight:
+    """A packed INT4 / INT8 weight resident in HBM (Quantizer::quantize_tensor + device re-tiling)."""
+
+    def __init__(self, w: np.ndarray, qtype: int, symmetric: bool = True):
+        w = _c(w)
+        assert w.ndim == 2
+        h = C.c_uint64()
+        _ck(_need().ti_b200_quantize_pack(_fp(w), w.shape[0], w.shape[1], qtype, int(symmetric), C.byref(h)))
+        self.handle = h.value
+        K, N, qt, by = C.c_size_t(), C.c_size_t(), C.c_int(), C.c_size_t()
+        s, z = C.c_float(), C.c_float()
+        _ck(lib().ti_b200_qweight_info(self.handle, C.byref(K), C.byref(N), C.byref(qt), C.byref(s), C.byref(z), C.byref(by)))
+        self.K, self.N, self.qtype, self.packed_bytes = K.value, N.value, qt.value, by.value
+        self.scale, self.zero_point = np.float32(s.value), np.float32(z.value)
+
+    def unpack(self) -> np.ndarray:
+        q = np.empty((self.K, self.N), dtype=np.int32)
+        _ck(lib().ti_b200_qweight_unpack(self.handle, q.ctypes.data_as(_i32)))
+        return q
+
+    def gemv(self, x: np.ndarray) -> np.ndarray:
+        x = _c(x)
+        rows = x.size // self.K
+        y = np.empty((rows, self.N), dtype=np.float32)
+        _ck(lib().ti_b200_gemv_q(self.handle, _fp(x), _fp(y), rows))
+        return y
+
+    def free(self) -> None:
+        if self.handle:
+            _ck(lib().ti_b200_qweight_free(self.handle))
+            self.handle = 0
+
+
+class _Ops:
+    """TensorEngine / Quantizer entry points on host arrays (upload -> kernel -> download)."""
+
+    def quant_info(self, x, qtype: int, symmetric: bool = True):
+        x = _c(x).ravel()
+        s, z = C.c_float(), C.c_float()
+        _ck(_need().ti_b200_quant_info(_fp(x), x.size, qtype, int(symmetric), C.byref(s), C.byref(z)))
+        return np.float32(s.value), np.float32(z.value)
+
+    def quantize(self, x, qtype: int, scale: float, zp: float) -> np.ndarray:
+        x = _c(x)
+        q = np.empty(x.shape, dtype=np.int8 if qtype == Q_INT8 else np.int32)
+        _ck(_need().ti_b200_quantize(_fp(x.ravel()), x.size, qtype, scale, zp, q.ctypes.data))
+        return q
+
+    def dequantize(self, q, qtype: int, scale: float, zp: float) -> np.ndarray:
+        q = _c(q, np.int8 if qtype == Q_INT8 else np.int32)
+        x = np.empty(q.shape, dtype=np.float32)
+        _ck(_need().ti_b200_dequantize(q.ctypes.data, q.size, qtype, scale, zp, _fp(x.ravel())))
+        return x
+
+    def matmul(self, a, b) -> np.ndarray:
+        a, b = _c(a), _c(b)
+        M, K = a.shape
+        N = b.shape[1]
+        c = np.empty((M, N), dtype=np.float32)
+        _ck(_need().ti_b200_matmul_f32(_fp(a), _fp(b), _fp(c), M, K, N))
+        return c
+
+    def rms_norm(self, x, w, eps: float = 1e-5) -> np.ndarray:
+        x, w = _c(x), _c(w)
+        H = x.shape[-1]
+        y = np.empty_like(x)
+        _ck(_need().ti_b200_rms_norm(_fp(x), _fp(w), _fp(y), x.size // H, H, eps))
+        return y
+
+    def rope(self, x, pos, theta: float = 10000.0) -> np.ndarray:
+        x, pos = _c(x), _c(pos)
+        y = np.empty_like(x)
+        if x.ndim == 3:
+            B, T, D = x.shape
+            nh = 1
+        else:
+            B, nh, T, D = x.shape
+        _ck(_need().ti_b200_rope(_fp(x), _fp(pos), _fp(y), B, nh, T, D, x.ndim, int(pos.ndim == 2), theta))
+        return y
+
+    def _unary(self, fn, x):
+        x = _c(x)
+        y = np.empty_like(x)
+        _ck(fn(_fp(x), _fp(y), x.size))
+        return y
+
+    def silu(self, x):
+        return self._unary(_need().ti_b200_silu, x)
+
+    def relu(self, x):
+        return self._unary(_need().ti_b200_relu, x)
+
+    def _binary(self, fn, a, b):
+        a, b = _c(a), _c(b)
+        y = np.empty_like(a)
+        _ck(fn(_fp(a), _fp(b), _fp(y), a.size))
+        return y
+
+    def add(self, a, b):
+        return self._binary(_need().ti_b200_add, a, b)
+
+    def mul(self, a, b):
+        return self._binary(_need().ti_b200_mul, a, b)
+
+    def silu_mul(self, gate, up):
+        return self._binary(_need().ti_b200_silu_mul, gate, up)
+
+    def softmax(self, x, temperature: float = 1.0) -> np.ndarray:
+        x = _c(x)
+        n = x.shape[-1]
+        y = np.empty_like(x)
+        _ck(_need().ti_b200_softmax(_fp(x), _fp(y), x.size // n, n, temperature))
+        return y
+
+    def attention_decode(self, q, k, v, num_heads: int = 1) -> np.ndarray:
+        q, k, v = _c(q), _c(k), _c(v)
+        B, _, H = q.shape
+        t = k.shape[1]
+        out = np.empty((B, 1, H), dtype=np.float32)
+        _ck(_need().ti_b200_attention_decode(_fp(q), _fp(k), _fp(v), _fp(out), B, t, H, num_heads))
+        return out
+
+
+ops = _Ops()
+
+
+class Model:
+    """Device-resident decoder (InferenceEngine's weights + KV cache + incremental forward + greedy generate)."""
+
+    def __init__(self, meta: dict, qtype: int, *, attn_mode: int = 1, rope_mode: int = 0, max_seq: int = 2048,
+                 kv_page_tokens: int = 0, compat_literal: bool = False):
+        cfg = ModelConfig()
+        cfg.vocab, cfg.hidden, cfg.layers, cfg.heads, cfg.inter = (meta["vocab"], meta["hidden"], meta["layers"],
+                                                                   meta["heads"], meta["inter"])
+        cfg.rope_theta = meta.get("rope_theta", 10000.0)
+        cfg.rms_eps = meta.get("rms_eps", 1e-5)
+        cfg.qtype, cfg.attn_mode, cfg.rope_mode = qtype, attn_mode, rope_mode
+        cfg.max_seq, cfg.kv_page_tokens, cfg.compat_literal = max_seq, kv_page_tokens, int(compat_literal)
+        self.meta = dict(meta)
+        h = C.c_uint64()
+        _ck(_need().ti_b200_model_new(C.byref(cfg), C.byref(h)))
+        self.handle = h.value
+
+    def set_tensor(self, name: str, data: np.ndarray) -> None:
+        data = _c(data)
+        rows, cols = (1, data.size) if data.ndim == 1 else data.shape
+        _ck(lib().ti_b200_model_set_tensor(self.handle, name.encode(), _fp(data), rows, cols))
+
+    def set_tensor_synthetic(self, name: str, rows: int, cols: int, seed: int, amp: float) -> None:
+        _ck(lib().ti_b200_model_set_tensor_synthetic(self.handle, name.encode(), rows, cols, seed, amp))
+
+    def load(self, weights: dict) -> "Model":
+        for name, arr in weights.items():
+            self.set_tensor(name, arr)
+        self.finalize()
+        return self
+
+    def finalize(self) -> None:
+        _ck(lib().ti_b200_model_finalize(self.handle))
+
+    def reset(self) -> None:
+        _ck(lib().ti_b200_model_reset(self.handle))
+
+    @property
+    def kv_length(self) -> int:
+        n = C.c_int32()
+        _ck(lib().ti_b200_model_kv_length(self.handle, C.byref(n)))
+        return n.value
+
+    def step_bytes(self, t: int):
+        w, k = C.c_double(), C.c_double()
+        _ck(lib().ti_b200_model_step_bytes(self.handle, t, C.byref(w), C.byref(k)))
+        return w.value, k.value
+
+    def decode_step(self, token: int, want_logits: bool = True):
+        V = self.meta["vocab"]
+        logits = np.empty(V, dtype=np.float32) if want_logits else None
+        am = C.c_int32()
+        _ck(lib().ti_b200_decode_step(self.handle, token, _fp(logits) if want_logits else C.cast(None, _f), C.byref(am)))
+        return am.value, logits
+
+    def generate_greedy(self, prompt: Sequence[int], n_new: int, *, stop_on_eos: bool = False, want_logits: bool = False):
+        p = _c(prompt, np.int32)
+        out = np.zeros(max(n_new, 1), dtype=np.int32)
+        n_out, ms = C.c_int32(), C.c_float()
+        logits = np.empty((max(n_new, 1), self.meta["vocab"]), dtype=np.float32) if want_logits else None
+        _ck(lib().ti_b200_generate_greedy(self.handle, p.ctypes.data_as(_i32), p.size, n_new, int(stop_on_eos),
+                                          out.ctypes.data_as(_i32), C.byref(n_out),
+                                          _fp(logits) if want_logits else C.cast(None, _f), C.byref(ms)))
+        n = n_out.value
+        return out[:n].copy(), (logits[:n].copy() if want_logits else None), ms.value
+
+    def free(self) -> None:
+        if self.handle:
+            _ck(lib().ti_b200_model_free(self.handle))
+            self.handle = 0

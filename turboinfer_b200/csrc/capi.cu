@@ -1,0 +1,1147 @@
+// capi.cu -- implementation of include/ti_b200.h: handle tables, device memory, kernel launches, and the
+// device-resident decoder (weights quantized + packed once, paged KV cache, one CUDA graph per decode step).
+// Host-side only orchestration lives here; all arithmetic of the hot path runs in the sm_100a kernels of
+// gemv.cuh / kernels.cuh.  There is no CPU fallback.
+#include "../../include/ti_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace tib;
+
+namespace {
+
+thread_local std::string g_err;
+int g_device = -1;
+int g_num_sms = 0;
+cudaStream_t g_stream = nullptr;
+uint64_t g_launches = 0;
+bool g_use_pdl = false;
+bool g_attr_done = false;
+
+int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define TRY(expr)            \
+    do {                     \
+        int rc_ = (expr);    \
+        if (rc_ != 0) return rc_; \
+    } while (0)
+
+int need_init() {
+    if (g_device < 0) return fail("ti_b200: not initialised -- call ti_b200_init(device) first (no CPU fallback exists)");
+    return 0;
+}
+
+int grid_for(size_t n, int block = 256) {
+    size_t g = (n + block - 1) / block;
+    size_t cap = (size_t)g_num_sms * 8;
+    return (int)std::max<size_t>(1, std::min(g, cap));
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    int alloc(size_t count) {
+        release();
+        if (count == 0) return 0;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e != cudaSuccess) return fail("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        n = count;
+        return 0;
+    }
+};
+
+// ---- packed weight ------------------------------------------------------------------------------------
+struct QWeight {
+    QLayout L{};
+    int qtype = TI_Q_INT4;
+    int stages = 0;
+    size_t smem = 0;
+    float scale = 0.f, zp = 0.f;  // of the first (or only) source tensor
+    int offset4 = 8;              // what was added to INT4 values when stored
+    bool has_zterm = false;
+    DevBuf<uint8_t> packed;
+    DevBuf<float> colscale, colzterm;
+    size_t bytes() const { return layout_bytes(L); }
+};
+
+int pick_stages(const QLayout& L, int* stages, size_t* smem) {
+    for (int s = kMaxStages; s >= 2; --s) {
+        size_t b = gemv_smem_bytes(L, s);
+        if (b <= 227 * 1024) {
+            *stages = s;
+            *smem = b;
+            return 0;
+        }
+    }
+    return fail("GEMV K=%d does not fit shared memory (x needs %d KiB)", L.K, layout_kpad(L) * 4 / 1024);
+}
+
+int set_kernel_attrs() {
+    if (g_attr_done) return 0;
+    CK(cudaFuncSetAttribute(gemv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(gemv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(attn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    g_attr_done = true;
+    return 0;
+}
+
+int launch_gemv(const QWeight& w, GemvArgs a, cudaStream_t st) {
+    a.wq = w.packed.p;
+    a.colscale = w.colscale.p;
+    a.colzterm = w.has_zterm ? w.colzterm.p : nullptr;
+    a.L = w.L;
+    a.stages = w.stages;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(w.L.P);
+    cfg.blockDim = dim3(kGemvThreads);
+    cfg.dynamicSmemBytes = w.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    if (w.L.bits == 4) CK(cudaLaunchKernelEx(&cfg, gemv_kernel<4>, a));
+    else CK(cudaLaunchKernelEx(&cfg, gemv_kernel<8>, a));
+    ++g_launches;
+    return 0;
+}
+
+// source fp32 matrix on the device awaiting quantization
+struct RawTensor {
+    DevBuf<float> data;
+    size_t rows = 0, cols = 0;
+    bool present() const { return data.p != nullptr; }
+};
+
+// min/max -> (scale, zero_point) on the device; sz = 2 floats
+int device_quant_params(const float* x, size_t n, int qtype, int symmetric, float* sz_dev, uint32_t* mm_dev, cudaStream_t st) {
+    const uint32_t init[2] = {0xFFFFFFFFu, 0u};
+    CK(cudaMemcpyAsync(mm_dev, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    minmax_kernel<<<grid_for(n), 256, 0, st>>>(x, n, mm_dev);
+    quant_params_kernel<<<1, 1, 0, st>>>(mm_dev, qtype, symmetric, sz_dev);
+    g_launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Quantize + pack up to three device fp32 sources (all [K][n_i]) into one streaming weight.
+int build_qweight(const float* const* src, const int* src_n, int nsrc, int mode, int K, int qtype, int symmetric, bool unit_scale,
+                  std::unique_ptr<QWeight>* out) {
+    auto w = std::make_unique<QWeight>();
+    int N = 0;
+    for (int i = 0; i < nsrc; ++i) N += src_n[i];
+    w->L = make_layout(K, N, qtype == TI_Q_INT4 ? 4 : 8, g_num_sms);
+    w->qtype = qtype;
+    TRY(pick_stages(w->L, &w->stages, &w->smem));
+    TRY(w->packed.alloc(layout_bytes(w->L)));
+    TRY(w->colscale.alloc((size_t)4 * w->L.U));
+    TRY(w->colzterm.alloc((size_t)4 * w->L.U));
+    DevBuf<float> sz;
+    DevBuf<uint32_t> mm;
+    TRY(sz.alloc(2 * 3));
+    TRY(mm.alloc(2));
+    PackArgs pa{};
+    pa.nsrc = nsrc;
+    pa.mode = mode;
+    pa.qtype = qtype;
+    pa.unit_scale = unit_scale ? 1 : 0;
+    pa.L = w->L;
+    pa.out = w->packed.p;
+    pa.colscale = w->colscale.p;
+    pa.colzterm = w->colzterm.p;
+    for (int i = 0; i < nsrc; ++i) {
+        TRY(device_quant_params(src[i], (size_t)K * src_n[i], qtype, symmetric, sz.p + 2 * i, mm.p, g_stream));
+        pa.src[i].w = src[i];
+        pa.src[i].n = src_n[i];
+        pa.src[i].sz = sz.p + 2 * i;
+    }
+    pack_kernel<<<w->L.P, kConsumerThreads, 0, g_stream>>>(pa);
+    ++g_launches;
+    CK(cudaGetLastError());
+    float h[6] = {0};
+    CK(cudaMemcpyAsync(h, sz.p, sizeof(float) * 2 * nsrc, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    w->scale = h[0];
+    w->zp = h[1];
+    w->has_zterm = false;
+    for (int i = 0; i < nsrc; ++i) w->has_zterm |= (h[2 * i + 1] != 0.0f);
+    w->offset4 = (h[1] == 0.0f) ? 8 : 0;
+    *out = std::move(w);
+    return 0;
+}
+
+// ---- model ---------------------------------------------------------------------------------------------
+struct Layer {
+    RawTensor raw_q, raw_k, raw_v, raw_o, raw_up, raw_gate, raw_down;  // pending fp32 sources
+    std::unique_ptr<QWeight> qkv, o, gateup, down;
+    DevBuf<float> attn_norm, ffn_norm;
+    DevBuf<float> k_pool, v_pool;
+    bool has_gate = false;
+    // compat_literal: reference-layout fp32 (or integer-valued fp32) matrices
+    DevBuf<float> lit_up, lit_down;
+};
+
+struct Model {
+    ti_model_config cfg{};
+    std::vector<Layer> layers;
+    DevBuf<float> tok_emb, out_norm;
+    RawTensor raw_lm;
+    std::unique_ptr<QWeight> lm_head;
+    DevBuf<float> lit_lm;
+    bool finalized = false;
+    int page_tokens = 64, num_pages = 0;
+    DevBuf<int> page_table;
+    DevBuf<StepState> state;
+    DevBuf<float> x, nrm, q, attn_out, act, logits, part_o, part_ml, inv_freq, hist;
+    DevBuf<int> out_tokens, prompt;
+    int attn_heads = 1, attn_dim = 0, max_splits = 1;
+    size_t attn_smem = 0;
+    cudaGraphExec_t graph_decode = nullptr, graph_prefill = nullptr;
+    DevBuf<StepIO> io;
+    int launches_decode = 0, launches_prefill = 0;  // kernels per captured step
+    int host_pos = 0;  // mirror of state.pos
+    ~Model() {
+        if (graph_decode) cudaGraphExecDestroy(graph_decode);
+        if (graph_prefill) cudaGraphExecDestroy(graph_prefill);
+    }
+};
+
+std::mutex g_mu;
+std::vector<std::unique_ptr<QWeight>> g_qweights;
+std::vector<std::unique_ptr<Model>> g_models;
+
+QWeight* get_qw(ti_qweight_t h) {
+    if (h == 0 || h > g_qweights.size()) return nullptr;
+    return g_qweights[h - 1].get();
+}
+Model* get_model(ti_model_t h) {
+    if (h == 0 || h > g_models.size()) return nullptr;
+    return g_models[h - 1].get();
+}
+
+int upload(DevBuf<float>& dst, const float* host, size_t n) {
+    TRY(dst.alloc(n));
+    CK(cudaMemcpyAsync(dst.p, host, n * sizeof(float), cudaMemcpyHostToDevice, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+// "layers.3.attention.q_proj.weight" -> (3, slot).  Accepts the naming variants of initialize_model (:483-563).
+enum Slot { S_NONE, S_EMB, S_NORM, S_LM, S_Q, S_K, S_V, S_O, S_AN, S_FN, S_UP, S_DOWN, S_GATE };
+Slot parse_name(const std::string& name, int* layer) {
+    *layer = -1;
+    if (name == "token_embeddings.weight" || name == "embed_tokens.weight" || name == "model.embed_tokens.weight") return S_EMB;
+    if (name == "norm.weight" || name == "model.norm.weight") return S_NORM;
+    if (name == "lm_head.weight" || name == "output.weight") return S_LM;
+    std::string rest = name;
+    if (rest.rfind("model.", 0) == 0) rest = rest.substr(6);
+    if (rest.rfind("layers.", 0) != 0) return S_NONE;
+    rest = rest.substr(7);
+    size_t dot = rest.find('.');
+    if (dot == std::string::npos) return S_NONE;
+    *layer = atoi(rest.substr(0, dot).c_str());
+    rest = rest.substr(dot + 1);
+    auto is = [&](const char* a, const char* b) { return rest == a || rest == b; };
+    if (is("self_attn.q_proj.weight", "attention.q_proj.weight")) return S_Q;
+    if (is("self_attn.k_proj.weight", "attention.k_proj.weight")) return S_K;
+    if (is("self_attn.v_proj.weight", "attention.v_proj.weight")) return S_V;
+    if (is("self_attn.o_proj.weight", "attention.o_proj.weight")) return S_O;
+    if (is("input_layernorm.weight", "attention_norm.weight")) return S_AN;
+    if (is("post_attention_layernorm.weight", "ffn_norm.weight")) return S_FN;
+    if (is("mlp.up_proj.weight", "feed_forward.w1.weight")) return S_UP;
+    if (is("mlp.down_proj.weight", "feed_forward.w2.weight")) return S_DOWN;
+    if (is("mlp.gate_proj.weight", "feed_forward.w3.weight")) return S_GATE;
+    return S_NONE;
+}
+
+int pack_single(RawTensor& raw, int qtype, std::unique_ptr<QWeight>* out) {
+    const float* src[1] = {raw.data.p};
+    int n[1] = {(int)raw.cols};
+    TRY(build_qweight(src, n, 1, 0, (int)raw.rows, qtype, 1, false, out));
+    raw.data.release();
+    return 0;
+}
+
+// pack whatever groups of a layer have become complete (keeps peak fp32 residency to one group)
+int pack_ready(Model& m, Layer& ly, bool final_pass) {
+    const int qt = m.cfg.qtype;
+    if (m.cfg.compat_literal) return 0;
+    if (!ly.qkv && ly.raw_q.present() && ly.raw_k.present() && ly.raw_v.present()) {
+        const float* src[3] = {ly.raw_q.data.p, ly.raw_k.data.p, ly.raw_v.data.p};
+        int n[3] = {(int)ly.raw_q.cols, (int)ly.raw_k.cols, (int)ly.raw_v.cols};
+        TRY(build_qweight(src, n, 3, 0, (int)ly.raw_q.rows, qt, 1, false, &ly.qkv));
+        ly.raw_q.data.release(); ly.raw_k.data.release(); ly.raw_v.data.release();
+    }
+    if (!ly.o && ly.raw_o.present()) TRY(pack_single(ly.raw_o, qt, &ly.o));
+    if (!ly.down && ly.raw_down.present()) TRY(pack_single(ly.raw_down, qt, &ly.down));
+    if (!ly.gateup && ly.raw_up.present() && ly.raw_gate.present()) {
+        const float* src[2] = {ly.raw_gate.data.p, ly.raw_up.data.p};  // even columns = gate, odd = up
+        int n[2] = {(int)ly.raw_gate.cols, (int)ly.raw_up.cols};
+        TRY(build_qweight(src, n, 2, 1, (int)ly.raw_up.rows, qt, 1, false, &ly.gateup));
+        ly.has_gate = true;
+        ly.raw_up.data.release(); ly.raw_gate.data.release();
+    }
+    if (final_pass && !ly.gateup && ly.raw_up.present()) {  // no gate: relu(up) (:392-395)
+        TRY(pack_single(ly.raw_up, qt, &ly.gateup));
+        ly.has_gate = false;
+    }
+    return 0;
+}
+
+int store_tensor(Model& m, const std::string& name, DevBuf<float>&& dev, size_t rows, size_t cols) {
+    int li = -1;
+    Slot s = parse_name(name, &li);
+    if (s == S_NONE) return fail("unknown tensor name '%s'", name.c_str());
+    const size_t H = m.cfg.hidden, V = m.cfg.vocab, I = m.cfg.inter;
+    auto expect = [&](size_t r, size_t c) -> int {
+        if (rows != r || cols != c) return fail("tensor '%s' has shape [%zu,%zu], expected [%zu,%zu]", name.c_str(), rows, cols, r, c);
+        return 0;
+    };
+    auto take = [&](RawTensor& t) {
+        t.data.release();
+        t.data.p = dev.p; t.data.n = dev.n; dev.p = nullptr; dev.n = 0;
+        t.rows = rows; t.cols = cols;
+    };
+    auto take_vec = [&](DevBuf<float>& t) {
+        t.release();
+        t.p = dev.p; t.n = dev.n; dev.p = nullptr; dev.n = 0;
+    };
+    if (s == S_EMB) { TRY(expect(V, H)); take_vec(m.tok_emb); return 0; }
+    if (s == S_NORM) { if (rows * cols != H) return fail("norm.weight must have %zu elements", H); take_vec(m.out_norm); return 0; }
+    if (s == S_LM) {
+        TRY(expect(H, V));
+        take(m.raw_lm);
+        if (!m.cfg.compat_literal) TRY(pack_single(m.raw_lm, m.cfg.qtype, &m.lm_head));
+        return 0;
+    }
+    if (li < 0 || li >= (int)m.layers.size()) return fail("layer index out of range in '%s'", name.c_str());
+    Layer& ly = m.layers[li];
+    switch (s) {
+        case S_Q: TRY(expect(H, H)); take(ly.raw_q); break;
+        case S_K: TRY(expect(H, H)); take(ly.raw_k); break;
+        case S_V: TRY(expect(H, H)); take(ly.raw_v); break;
+        case S_O: TRY(expect(H, H)); take(ly.raw_o); break;
+        case S_UP: TRY(expect(H, I)); take(ly.raw_up); break;
+        case S_GATE: TRY(expect(H, I)); take(ly.raw_gate); break;
+        case S_DOWN: TRY(expect(I, H)); take(ly.raw_down); break;
+        case S_AN: if (rows * cols != H) return fail("bad norm size"); take_vec(ly.attn_norm); break;
+        case S_FN: if (rows * cols != H) return fail("bad norm size"); take_vec(ly.ffn_norm); break;
+        default: break;
+    }
+    return pack_ready(m, ly, false);
+}
+
+// ---- decode step -------------------------------------------------------------------------------------
+int enqueue_attention(Model& m, Layer& ly, cudaStream_t st) {
+    AttnArgs a{};
+    a.q = m.q.p;
+    a.k_pool = ly.k_pool.p;
+    a.v_pool = ly.v_pool.p;
+    a.page_table = m.page_table.p;
+    a.page_tokens = m.page_tokens;
+    a.pos_ptr = &m.state.p->pos;
+    a.t_bias = 1;
+    a.H = m.cfg.hidden;
+    a.D = m.attn_dim;
+    a.heads = m.attn_heads;
+    a.max_splits = m.max_splits;
+    a.min_chunk = 64;
+    a.scale = 1.0f / sqrtf((float)m.attn_dim);  // :1288 (D = hidden in literal single-head mode, head_dim otherwise)
+    a.part_o = m.part_o.p;
+    a.part_ml = m.part_ml.p;
+    a.out = m.attn_out.p;
+    attn_partial_kernel<<<dim3(m.attn_heads, m.max_splits), kAttnThreads, m.attn_smem, st>>>(a);
+    attn_combine_kernel<<<m.attn_heads, 256, 0, st>>>(a);
+    g_launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int enqueue_step(Model& m, bool with_head, cudaStream_t st) {
+    const int H = m.cfg.hidden;
+    StepState* S = m.state.p;
+    embed_kernel<<<grid_for(H), 256, 0, st>>>(m.tok_emb.p, S, m.x.p, H, 0);
+    ++g_launches;
+    for (auto& ly : m.layers) {
+        const bool attn = ly.qkv && ly.o;
+        if (attn) {
+            GemvArgs a{};
+            a.x = m.x.p;
+            a.norm_w = ly.attn_norm.p;
+            a.rms_eps = m.cfg.rms_eps;
+            a.epi = EPI_QKV;
+            a.out = m.q.p;
+            a.hidden = H;
+            a.rope_dim = m.cfg.rope_mode == 1 ? H / m.cfg.heads : (m.cfg.rope_mode == 2 ? H : 0);
+            a.inv_freq = m.inv_freq.p;
+            a.pos_ptr = &S->pos;
+            a.k_pool = ly.k_pool.p;
+            a.v_pool = ly.v_pool.p;
+            a.page_table = m.page_table.p;
+            a.page_tokens = m.page_tokens;
+            TRY(launch_gemv(*ly.qkv, a, st));
+            TRY(enqueue_attention(m, ly, st));
+            GemvArgs o{};
+            o.x = m.attn_out.p;
+            o.epi = EPI_RESIDUAL;
+            o.resid = m.x.p;
+            o.out = m.x.p;
+            TRY(launch_gemv(*ly.o, o, st));
+        } else {
+            // compute_attention returns its (normalised) input when a projection is missing (:293-296): x <- x + n
+            const float* n = m.x.p;
+            if (ly.attn_norm.p) {
+                rms_norm_kernel<<<1, 256, 0, st>>>(m.x.p, ly.attn_norm.p, m.nrm.p, H, m.cfg.rms_eps);
+                ++g_launches;
+                n = m.nrm.p;
+            }
+            elementwise_kernel<<<grid_for(H), 256, 0, st>>>(m.x.p, n, m.x.p, H, EW_ADD);
+            ++g_launches;
+        }
+        if (ly.gateup && ly.down) {
+            GemvArgs g{};
+            g.x = m.x.p;
+            g.norm_w = ly.ffn_norm.p;
+            g.rms_eps = m.cfg.rms_eps;
+            g.epi = ly.has_gate ? EPI_SWIGLU : EPI_RELU;
+            g.out = m.act.p;
+            TRY(launch_gemv(*ly.gateup, g, st));
+            GemvArgs d{};
+            d.x = m.act.p;
+            d.epi = EPI_RESIDUAL;
+            d.resid = m.x.p;
+            d.out = m.x.p;
+            TRY(launch_gemv(*ly.down, d, st));
+        } else {
+            const float* f = m.x.p;  // compute_ffn returns its input (:377-380)
+            if (ly.ffn_norm.p) {
+                rms_norm_kernel<<<1, 256, 0, st>>>(m.x.p, ly.ffn_norm.p, m.nrm.p, H, m.cfg.rms_eps);
+                ++g_launches;
+                f = m.nrm.p;
+            }
+            elementwise_kernel<<<grid_for(H), 256, 0, st>>>(m.x.p, f, m.x.p, H, EW_ADD);
+            ++g_launches;
+        }
+    }
+    if (with_head) {
+        GemvArgs l{};
+        l.x = m.x.p;
+        l.norm_w = m.out_norm.p;
+        l.rms_eps = m.cfg.rms_eps;
+        l.epi = EPI_LOGITS;
+        l.out = m.logits.p;
+        l.argmax_key = &S->argmax_key;
+        TRY(launch_gemv(*m.lm_head, l, st));
+    }
+    return 0;
+}
+
+int capture_graph(Model& m, bool with_head, cudaGraphExec_t* out) {
+    StepIO* io = m.io.p;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+    const uint64_t launches_before = g_launches;
+    int rc = enqueue_step(m, with_head, g_stream);
+    if (rc == 0) {
+        step_finish_kernel<<<1, 1024, 0, g_stream>>>(m.state.p, io, m.logits.p, m.cfg.vocab, with_head ? 1 : 0);
+        ++g_launches;
+    }
+    cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
+    (with_head ? m.launches_decode : m.launches_prefill) = (int)(g_launches - launches_before);
+    g_launches = launches_before;  // captured, not launched
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(out, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// extern "C" surface
+// =====================================================================================================
+extern "C" {
+
+int ti_b200_abi_version(void) { return TI_B200_ABI_VERSION; }
+const char* ti_b200_last_error(void) { return g_err.c_str(); }
+
+int ti_b200_device_count(int* n) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *n = 0; return fail("cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *n = c;
+    return 0;
+}
+
+int ti_b200_init(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail("ti_b200_init: no CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+    if (device < 0 || device >= count) return fail("ti_b200_init: device %d out of range [0,%d)", device, count);
+    if (g_device == device) return 0;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("ti_b200_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    g_num_sms = prop.multiProcessorCount;
+    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    g_device = device;
+    const char* pdl = getenv("TURBOINFER_B200_PDL");
+    g_use_pdl = pdl ? atoi(pdl) != 0 : false;
+    return set_kernel_attrs();
+}
+
+int ti_b200_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_device < 0) return 0;
+    cudaStreamSynchronize(g_stream);
+    g_models.clear();
+    g_qweights.clear();
+    cudaStreamDestroy(g_stream);
+    g_stream = nullptr;
+    g_device = -1;
+    g_attr_done = false;
+    return 0;
+}
+
+int ti_b200_device_info(char* buf, size_t cap) {
+    TRY(need_init());
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, g_device));
+    size_t fr = 0, tot = 0;
+    CK(cudaMemGetInfo(&fr, &tot));
+    snprintf(buf, cap, "%s sm_%d%d, %d SMs, %.1f GiB HBM (%.1f free), smem/CTA %zu KiB", prop.name, prop.major, prop.minor,
+             prop.multiProcessorCount, tot / 1073741824.0, fr / 1073741824.0, prop.sharedMemPerBlockOptin / 1024);
+    return 0;
+}
+
+int ti_b200_sync(void) {
+    TRY(need_init());
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+int ti_b200_malloc(void** dev, size_t bytes) {
+    TRY(need_init());
+    CK(cudaMalloc(dev, bytes));
+    return 0;
+}
+int ti_b200_free(void* dev) {
+    TRY(need_init());
+    CK(cudaFree(dev));
+    return 0;
+}
+int ti_b200_memcpy_h2d(void* dev, const void* host, size_t bytes) {
+    TRY(need_init());
+    CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+int ti_b200_memcpy_d2h(void* host, const void* dev, size_t bytes) {
+    TRY(need_init());
+    CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+int ti_b200_launch_count(uint64_t* n) { *n = g_launches; return 0; }
+
+// ---- quantizer ---------------------------------------------------------------------------------------
+int ti_b200_quant_info(const float* x_host, size_t n, int qtype, int symmetric, float* scale, float* zero_point) {
+    TRY(need_init());
+    if (n == 0) return fail("Cannot quantize an empty tensor");
+    if (qtype != TI_Q_INT8 && qtype != TI_Q_INT4) return fail("Unsupported quantization type");
+    DevBuf<float> x, sz;
+    DevBuf<uint32_t> mm;
+    TRY(upload(x, x_host, n));
+    TRY(sz.alloc(2));
+    TRY(mm.alloc(2));
+    TRY(device_quant_params(x.p, n, qtype, symmetric, sz.p, mm.p, g_stream));
+    float h[2];
+    CK(cudaMemcpyAsync(h, sz.p, sizeof(h), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    *scale = h[0];
+    *zero_point = h[1];
+    return 0;
+}
+
+int ti_b200_quantize(const float* x_host, size_t n, int qtype, float scale, float zero_point, void* q_out_host) {
+    TRY(need_init());
+    if (qtype != TI_Q_INT8 && qtype != TI_Q_INT4) return fail("Unsupported quantization type");
+    if (n == 0) return 0;
+    DevBuf<float> x;
+    DevBuf<int8_t> q8;
+    DevBuf<int32_t> q32;
+    TRY(upload(x, x_host, n));
+    if (qtype == TI_Q_INT8) TRY(q8.alloc(n)); else TRY(q32.alloc(n));
+    quantize_flat_kernel<<<grid_for(n), 256, 0, g_stream>>>(x.p, n, qtype, scale, zero_point, q8.p, q32.p);
+    ++g_launches;
+    CK(cudaGetLastError());
+    if (qtype == TI_Q_INT8) CK(cudaMemcpyAsync(q_out_host, q8.p, n, cudaMemcpyDeviceToHost, g_stream));
+    else CK(cudaMemcpyAsync(q_out_host, q32.p, n * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+int ti_b200_dequantize(const void* q_host, size_t n, int qtype, float scale, float zero_point, float* x_out_host) {
+    TRY(need_init());
+    if (qtype != TI_Q_INT8 && qtype != TI_Q_INT4) return fail("Unsupported quantization type for dequantization");
+    if (n == 0) return 0;
+    DevBuf<float> x;
+    DevBuf<int8_t> q8;
+    DevBuf<int32_t> q32;
+    TRY(x.alloc(n));
+    if (qtype == TI_Q_INT8) {
+        TRY(q8.alloc(n));
+        CK(cudaMemcpyAsync(q8.p, q_host, n, cudaMemcpyHostToDevice, g_stream));
+    } else {
+        TRY(q32.alloc(n));
+        CK(cudaMemcpyAsync(q32.p, q_host, n * 4, cudaMemcpyHostToDevice, g_stream));
+    }
+    dequantize_flat_kernel<<<grid_for(n), 256, 0, g_stream>>>(q8.p, q32.p, n, qtype, scale, zero_point, x.p);
+    ++g_launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(x_out_host, x.p, n * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+int ti_b200_quantize_pack(const float* w_host, size_t K, size_t N, int qtype, int symmetric, ti_qweight_t* out) {
+    TRY(need_init());
+    if (K == 0 || N == 0) return fail("Cannot quantize an empty tensor");
+    if (qtype != TI_Q_INT8 && qtype != TI_Q_INT4) return fail("Unsupported quantization type");
+    DevBuf<float> w;
+    TRY(upload(w, w_host, K * N));
+    const float* src[1] = {w.p};
+    int n[1] = {(int)N};
+    std::unique_ptr<QWeight> q;
+    TRY(build_qweight(src, n, 1, 0, (int)K, qtype, symmetric, false, &q));
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_qweights.push_back(std::move(q));
+    *out = g_qweights.size();
+    return 0;
+}
+
+int ti_b200_qweight_info(ti_qweight_t h, size_t* K, size_t* N, int* qtype, float* scale, float* zero_point, size_t* packed_bytes) {
+    QWeight* w = get_qw(h);
+    if (!w) return fail("invalid qweight handle");
+    if (K) *K = w->L.K;
+    if (N) *N = w->L.N;
+    if (qtype) *qtype = w->qtype;
+    if (scale) *scale = w->scale;
+    if (zero_point) *zero_point = w->zp;
+    if (packed_bytes) *packed_bytes = w->bytes();
+    return 0;
+}
+
+int ti_b200_qweight_unpack(ti_qweight_t h, int32_t* q_out_host) {
+    TRY(need_init());
+    QWeight* w = get_qw(h);
+    if (!w) return fail("invalid qweight handle");
+    DevBuf<int32_t> q;
+    const size_t n = (size_t)w->L.K * w->L.N;
+    TRY(q.alloc(n));
+    unpack_kernel<<<w->L.P, kConsumerThreads, 0, g_stream>>>(w->packed.p, w->L, w->offset4, q.p);
+    ++g_launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(q_out_host, q.p, n * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+int ti_b200_qweight_free(ti_qweight_t h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (h == 0 || h > g_qweights.size() || !g_qweights[h - 1]) return fail("invalid qweight handle");
+    g_qweights[h - 1].reset();
+    return 0;
+}
+
+// ---- ops ---------------------------------------------------------------------------------------------
+int ti_b200_gemv_q_dev(ti_qweight_t h, const float* x_dev, float* y_dev) {
+    TRY(need_init());
+    QWeight* w = get_qw(h);
+    if (!w) return fail("invalid qweight handle");
+    GemvArgs a{};
+    a.x = x_dev;
+    a.epi = EPI_STORE;
+    a.out = y_dev;
+    return launch_gemv(*w, a, g_stream);
+}
+
+int ti_b200_gemv_q(ti_qweight_t h, const float* x_host, float* y_host, size_t rows) {
+    TRY(need_init());
+    QWeight* w = get_qw(h);
+    if (!w) return fail("invalid qweight handle");
+    if (rows == 0) return fail("Cannot perform matrix multiplication on empty tensors");
+    const size_t K = w->L.K, N = w->L.N;
+    DevBuf<float> x, y;
+    TRY(upload(x, x_host, rows * K));
+    TRY(y.alloc(rows * N));
+    for (size_t r = 0; r < rows; ++r) TRY(ti_b200_gemv_q_dev(h, x.p + r * K, y.p + r * N));
+    CK(cudaMemcpyAsync(y_host, y.p, rows * N * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+int ti_b200_matmul_f32(const float* a_host, const float* b_host, float* c_host, size_t M, size_t K, size_t N) {
+    TRY(need_init());
+    if (M == 0 || K == 0 || N == 0) return fail("Cannot perform matrix multiplication on empty tensors");
+    DevBuf<float> a, b, c;
+    TRY(upload(a, a_host, M * K));
+    TRY(upload(b, b_host, K * N));
+    TRY(c.alloc(M * N));
+    matmul_f32_exact_kernel<<<dim3((unsigned)((N + 127) / 128), (unsigned)M), 128, 0, g_stream>>>(a.p, b.p, c.p, (int)M, (int)K, (int)N, 0);
+    ++g_launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c_host, c.p, M * N * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+int ti_b200_rms_norm(const float* x_host, const float* w_host, float* y_host, size_t rows, size_t H, float eps) {
+    TRY(need_init());
+    if (rows == 0 || H == 0) return fail("Cannot apply RMS normalization to empty tensors");
+    DevBuf<float> x, w, y;
+    TRY(upload(x, x_host, rows * H));
+    TRY(upload(w, w_host, H));
+    TRY(y.alloc(rows * H));
+    rms_norm_kernel<<<(unsigned)rows, 256, 0, g_stream>>>(x.p, w.p, y.p, (int)H, eps);
+    ++g_launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(y_host, y.p, rows * H * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+static std::vector<float> host_inv_freq(size_t D, float theta) {
+    std::vector<float> f(D / 2);
+    for (size_t i = 0; i < D / 2; ++i) f[i] = 1.0f / std::pow(theta, static_cast<float>(2 * i) / static_cast<float>(D));  // :1562-1565
+    return f;
+}
+
+int ti_b200_rope(const float* x_host, const float* pos_host, float* y_host, size_t B, size_t nh, size_t T, size_t D, int ndim,
+                 int pos_2d, float theta) {
+    TRY(need_init());
+    if (ndim != 3 && ndim != 4) return fail("RoPE supports 3D or 4D input tensors only");
+    if (D % 2 != 0) return fail("Hidden dimension must be even for RoPE");
+    const size_t heads = ndim == 4 ? nh : 1;
+    const size_t rows = B * heads * T;
+    if (rows == 0 || D == 0) return fail("Cannot apply RoPE to empty tensors");
+    DevBuf<float> x, pos, y, fr;
+    TRY(upload(x, x_host, rows * D));
+    TRY(upload(pos, pos_host, pos_2d ? B * T : T));
+    std::vector<float> f = host_inv_freq(D, theta);
+    TRY(upload(fr, f.data(), f.size()));
+    TRY(y.alloc(rows * D));
+    rope_kernel<<<grid_for(rows * D / 2), 256, 0, g_stream>>>(x.p, pos.p, fr.p, y.p, (int)heads, (int)T, (int)D, pos_2d, rows);
+    ++g_launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(y_host, y.p, rows * D * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+static int elementwise_host(const float* a_host, const float* b_host, float* y_host, size_t n, int op) {
+    TRY(need_init());
+    if (n == 0) return fail("Cannot apply an element-wise operation to empty tensors");
+    DevBuf<float> a, b, y;
+    TRY(upload(a, a_host, n));
+    if (b_host) TRY(upload(b, b_host, n));
+    TRY(y.alloc(n));
+    elementwise_kernel<<<grid_for(n), 256, 0, g_stream>>>(a.p, b.p, y.p, n, op);
+    ++g_launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(y_host, y.p, n * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+int ti_b200_silu(const float* x, float* y, size_t n) { return elementwise_host(x, nullptr, y, n, EW_SILU); }
+int ti_b200_relu(const float* x, float* y, size_t n) { return elementwise_host(x, nullptr, y, n, EW_RELU); }
+int ti_b200_add(const float* a, const float* b, float* y, size_t n) { return elementwise_host(a, b, y, n, EW_ADD); }
+int ti_b200_mul(const float* a, const float* b, float* y, size_t n) { return elementwise_host(a, b, y, n, EW_MUL); }
+int ti_b200_silu_mul(const float* g, const float* u, float* y, size_t n) { return elementwise_host(g, u, y, n, EW_SILU_MUL); }
+
+int ti_b200_softmax(const float* x_host, float* y_host, size_t rows, size_t n, float temperature) {
+    TRY(need_init());
+    if (rows == 0 || n == 0) return fail("Cannot apply softmax to empty tensor");
+    DevBuf<float> x, y;
+    TRY(upload(x, x_host, rows * n));
+    TRY(y.alloc(rows * n));
+    softmax_kernel<<<(unsigned)rows, 256, 0, g_stream>>>(x.p, y.p, (int)n, temperature);
+    ++g_launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(y_host, y.p, rows * n * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+static size_t attn_smem_bytes(int D) {
+    const int groups = D < kAttnThreads ? kAttnThreads / D : 1;
+    return sizeof(float) * ((size_t)D + kAttnTokBlock + 32 + (size_t)groups * D);
+}
+static int attn_check_dim(size_t H, size_t heads) {
+    if (heads == 0 || H % heads != 0) return fail("Hidden size must be divisible by number of heads");
+    const size_t D = H / heads;
+    if (D % 4 != 0) return fail("attention head dimension %zu must be a multiple of 4", D);
+    if (D > (size_t)kAttnThreads * 32) return fail("attention head dimension %zu too large", D);
+    return 0;
+}
+
+int ti_b200_attention_decode(const float* q_host, const float* k_host, const float* v_host, float* out_host, size_t B, size_t t,
+                             size_t H, size_t num_heads) {
+    TRY(need_init());
+    if (B == 0 || t == 0 || H == 0) return fail("Cannot compute attention with empty tensors");
+    TRY(attn_check_dim(H, num_heads));
+    const int D = (int)(H / num_heads);
+    DevBuf<float> q, k, v, out, po, pml;
+    DevBuf<int> table, pos;
+    TRY(upload(q, q_host, B * H));
+    TRY(upload(k, k_host, B * t * H));
+    TRY(upload(v, v_host, B * t * H));
+    TRY(out.alloc(B * H));
+    const int page_tokens = 64;
+    const int pages = (int)((t + page_tokens - 1) / page_tokens);
+    // the host tensors are contiguous [t, H]: identity page table over a pool that is the tensor itself
+    std::vector<int> tab(pages);
+    for (int i = 0; i < pages; ++i) tab[i] = i;
+    TRY(table.alloc(pages));
+    CK(cudaMemcpyAsync(table.p, tab.data(), pages * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    const int tpos = (int)t;
+    TRY(pos.alloc(1));
+    CK(cudaMemcpyAsync(pos.p, &tpos, sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    const int max_splits = std::max(1, std::min<int>((2 * g_num_sms + (int)num_heads - 1) / (int)num_heads, 512));
+    TRY(po.alloc((size_t)num_heads * max_splits * D));
+    TRY(pml.alloc((size_t)num_heads * max_splits * 2));
+    for (size_t b = 0; b < B; ++b) {
+        AttnArgs a{};
+        a.q = q.p + b * H;
+        a.k_pool = k.p + b * t * H;
+        a.v_pool = v.p + b * t * H;
+        a.page_table = table.p;
+        a.page_tokens = page_tokens;
+        a.pos_ptr = pos.p;
+        a.t_bias = 0;
+        a.H = (int)H;
+        a.D = D;
+        a.heads = (int)num_heads;
+        a.max_splits = max_splits;
+        a.min_chunk = 64;
+        a.scale = 1.0f / sqrtf((float)D);
+        a.part_o = po.p;
+        a.part_ml = pml.p;
+        a.out = out.p + b * H;
+        attn_partial_kernel<<<dim3((unsigned)num_heads, max_splits), kAttnThreads, attn_smem_bytes(D), g_stream>>>(a);
+        attn_combine_kernel<<<(unsigned)num_heads, 256, 0, g_stream>>>(a);
+        g_launches += 2;
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(out_host, out.p, B * H * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+// ---- model -------------------------------------------------------------------------------------------
+int ti_b200_model_new(const ti_model_config* cfg, ti_model_t* out) {
+    TRY(need_init());
+    if (!cfg || !out) return fail("null argument");
+    if (cfg->hidden <= 0 || cfg->vocab <= 0 || cfg->layers < 0 || cfg->heads <= 0) return fail("invalid model config");
+    if (cfg->qtype != TI_Q_INT4 && cfg->qtype != TI_Q_INT8 && !cfg->compat_literal)
+        return fail("qtype must be TI_Q_INT4 or TI_Q_INT8 (fp32 weights are only supported with compat_literal)");
+    auto m = std::make_unique<Model>();
+    m->cfg = *cfg;
+    if (m->cfg.rms_eps == 0.f) m->cfg.rms_eps = 1e-5f;
+    if (m->cfg.rope_theta == 0.f) m->cfg.rope_theta = 10000.0f;
+    if (m->cfg.max_seq <= 0) m->cfg.max_seq = 2048;  // KVCache hard-codes 2048 (inference_engine.cpp:569)
+    m->page_tokens = cfg->kv_page_tokens > 0 ? cfg->kv_page_tokens : 64;
+    m->layers.resize(cfg->layers);
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_models.push_back(std::move(m));
+    *out = g_models.size();
+    return 0;
+}
+
+int ti_b200_model_set_tensor(ti_model_t h, const char* name, const float* data_host, size_t rows, size_t cols) {
+    TRY(need_init());
+    Model* m = get_model(h);
+    if (!m) return fail("invalid model handle");
+    if (m->finalized) return fail("model already finalized");
+    if (!data_host || rows * cols == 0) return fail("tensor '%s' is empty", name);
+    DevBuf<float> dev;
+    TRY(upload(dev, data_host, rows * cols));
+    return store_tensor(*m, name, std::move(dev), rows, cols);
+}
+
+int ti_b200_model_set_tensor_synthetic(ti_model_t h, const char* name, size_t rows, size_t cols, uint64_t seed, float amp) {
+    TRY(need_init());
+    Model* m = get_model(h);
+    if (!m) return fail("invalid model handle");
+    if (m->finalized) return fail("model already finalized");
+    DevBuf<float> dev;
+    TRY(dev.alloc(rows * cols));
+    synth_fill_kernel<<<grid_for(rows * cols), 256, 0, g_stream>>>(dev.p, rows * cols, seed, amp);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return store_tensor(*m, name, std::move(dev), rows, cols);
+}
+
+int ti_b200_model_finalize(ti_model_t h) {
+    TRY(need_init());
+    Model* mp = get_model(h);
+    if (!mp) return fail("invalid model handle");
+    Model& m = *mp;
+    if (m.finalized) return 0;
+    if (m.cfg.compat_literal) return fail("compat_literal decode is not available in this build");
+    const int H = m.cfg.hidden, V = m.cfg.vocab, I = m.cfg.inter;
+    if (!m.tok_emb.p) return fail("token_embeddings.weight missing");
+    if (!m.lm_head) return fail("lm_head.weight missing");  // the reference draws random logits here (:1544-1549); refuse instead
+    m.attn_heads = m.cfg.attn_mode == 1 ? m.cfg.heads : 1;
+    TRY(attn_check_dim(H, m.attn_heads));
+    m.attn_dim = H / m.attn_heads;
+    m.attn_smem = attn_smem_bytes(m.attn_dim);
+    m.max_splits = std::max(1, std::min((2 * g_num_sms + m.attn_heads - 1) / m.attn_heads, 512));
+    m.num_pages = (m.cfg.max_seq + m.page_tokens - 1) / m.page_tokens;
+    for (auto& ly : m.layers) {
+        TRY(pack_ready(m, ly, true));
+        if (ly.qkv && ly.o) {
+            TRY(ly.k_pool.alloc((size_t)m.num_pages * m.page_tokens * H));
+            TRY(ly.v_pool.alloc((size_t)m.num_pages * m.page_tokens * H));
+        }
+        // sources that cannot be used (e.g. q/k/v without o_proj) are dropped, like the reference ignores them
+        ly.raw_q.data.release(); ly.raw_k.data.release(); ly.raw_v.data.release(); ly.raw_o.data.release();
+        ly.raw_up.data.release(); ly.raw_gate.data.release(); ly.raw_down.data.release();
+    }
+    // page table: pages are handed out in order by reset(); physical order is deliberately not the identity
+    std::vector<int> tab(m.num_pages);
+    for (int i = 0; i < m.num_pages; ++i) tab[i] = m.num_pages - 1 - i;
+    TRY(m.page_table.alloc(m.num_pages));
+    CK(cudaMemcpyAsync(m.page_table.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    TRY(m.state.alloc(1));
+    CK(cudaMemsetAsync(m.state.p, 0, sizeof(StepState), g_stream));
+    TRY(m.io.alloc(1));
+    CK(cudaMemsetAsync(m.io.p, 0, sizeof(StepIO), g_stream));
+    TRY(m.x.alloc(H));
+    TRY(m.nrm.alloc(H));
+    TRY(m.q.alloc(H));
+    TRY(m.attn_out.alloc(H));
+    TRY(m.act.alloc(std::max(I, 1)));
+    TRY(m.logits.alloc(V));
+    TRY(m.part_o.alloc((size_t)m.attn_heads * m.max_splits * m.attn_dim));
+    TRY(m.part_ml.alloc((size_t)m.attn_heads * m.max_splits * 2));
+    const int rope_dim = m.cfg.rope_mode == 1 ? H / m.cfg.heads : H;
+    std::vector<float> f = host_inv_freq(rope_dim, m.cfg.rope_theta);
+    TRY(upload(m.inv_freq, f.data(), f.size()));
+    CK(cudaStreamSynchronize(g_stream));
+    TRY(capture_graph(m, true, &m.graph_decode));
+    TRY(capture_graph(m, false, &m.graph_prefill));
+    m.finalized = true;
+    m.host_pos = 0;
+    return 0;
+}
+
+int ti_b200_model_free(ti_model_t h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (h == 0 || h > g_models.size() || !g_models[h - 1]) return fail("invalid model handle");
+    cudaStreamSynchronize(g_stream);
+    g_models[h - 1].reset();
+    return 0;
+}
+
+int ti_b200_model_reset(ti_model_t h) {
+    TRY(need_init());
+    Model* m = get_model(h);
+    if (!m || !m->finalized) return fail("invalid or unfinalized model handle");
+    CK(cudaMemsetAsync(m->state.p, 0, sizeof(StepState), g_stream));
+    m->host_pos = 0;
+    return 0;
+}
+
+int ti_b200_model_kv_length(ti_model_t h, int32_t* length) {
+    Model* m = get_model(h);
+    if (!m) return fail("invalid model handle");
+    *length = m->host_pos;
+    return 0;
+}
+
+int ti_b200_model_step_bytes(ti_model_t h, int32_t t, double* weight_bytes, double* kv_bytes) {
+    Model* m = get_model(h);
+    if (!m || !m->finalized) return fail("invalid or unfinalized model handle");
+    double wb = 0, kb = 0;
+    const double H = m->cfg.hidden;
+    auto add = [&](const std::unique_ptr<QWeight>& w) {
+        if (!w) return;
+        wb += (double)w->L.K * w->L.N * w->L.bits / 8.0 + 4.0 * w->L.N + 4.0 * (w->L.K + w->L.N);
+    };
+    for (auto& ly : m->layers) {
+        add(ly.qkv); add(ly.o); add(ly.gateup); add(ly.down);
+        if (ly.qkv && ly.o) kb += 2.0 * t * H * 4.0 + 2.0 * H * 4.0;  // K,V read over t tokens + one row written
+    }
+    add(m->lm_head);
+    wb += H * 4.0;  // embedding row
+    if (weight_bytes) *weight_bytes = wb;
+    if (kv_bytes) *kv_bytes = kb;
+    return 0;
+}
+
+static int check_capacity(Model& m, int extra) {
+    if (m.host_pos + extra > m.cfg.max_seq) return fail("KV cache overflow: sequence too long");  // inference_engine.cpp:100-102
+    return 0;
+}
+
+int ti_b200_decode_step(ti_model_t h, int32_t token, float* logits_host, int32_t* argmax) {
+    TRY(need_init());
+    Model* m = get_model(h);
+    if (!m || !m->finalized) return fail("invalid or unfinalized model handle");
+    if (token < 0 || token >= m->cfg.vocab) return fail("token id %d out of range", token);
+    TRY(check_capacity(*m, 1));
+    StepIO io{};
+    CK(cudaMemcpyAsync(m->io.p, &io, sizeof(io), cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(&m->state.p->token, &token, sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    const int zero = 0;
+    CK(cudaMemcpyAsync(&m->state.p->step, &zero, sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    CK(cudaGraphLaunch(m->graph_decode, g_stream));
+    g_launches += m->launches_decode;
+    m->host_pos += 1;
+    if (logits_host) CK(cudaMemcpyAsync(logits_host, m->logits.p, (size_t)m->cfg.vocab * 4, cudaMemcpyDeviceToHost, g_stream));
+    int tok = 0;
+    CK(cudaMemcpyAsync(&tok, &m->state.p->token, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    if (argmax) *argmax = tok;
+    return 0;
+}
+
+int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_prompt, int32_t n_new, int32_t stop_on_eos,
+                            int32_t* out_tokens, int32_t* n_out, float* logits_host, float* decode_ms) {
+    TRY(need_init());
+    Model* mp = get_model(h);
+    if (!mp || !mp->finalized) return fail("invalid or unfinalized model handle");
+    Model& m = *mp;
+    if (n_prompt <= 0) return fail("Input tokens cannot be empty");  // validate_input_tokens (:1409)
+    if (n_new < 0) return fail("n_new must be >= 0");
+    for (int i = 0; i < n_prompt; ++i)
+        if (prompt[i] < 0 || prompt[i] >= m.cfg.vocab) return fail("token id %d out of range", prompt[i]);
+    TRY(ti_b200_model_reset(h));  // generate() resets the KV cache first (:746)
+    TRY(check_capacity(m, n_prompt + std::max(0, n_new - 1)));
+    const int V = m.cfg.vocab;
+    if ((int)m.prompt.n < n_prompt) TRY(m.prompt.alloc(n_prompt));
+    if ((int)m.out_tokens.n < std::max(n_new, 1)) TRY(m.out_tokens.alloc(std::max(n_new, 1)));
+    CK(cudaMemcpyAsync(m.prompt.p, prompt, n_prompt * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    StepIO io{};
+    io.out_tokens = m.out_tokens.p;
+    io.out_cap = n_new;
+    if (logits_host && n_new > 0) {
+        if (m.hist.n < (size_t)n_new * V) TRY(m.hist.alloc((size_t)n_new * V));
+        io.hist = m.hist.p;
+        io.hist_cap = n_new;
+    }
+    CK(cudaMemcpyAsync(m.io.p, &io, sizeof(io), cudaMemcpyHostToDevice, g_stream));
+    // prefill: the prompt goes through the same incremental step, one token at a time; only the last one needs logits
+    for (int i = 0; i < n_prompt; ++i) {
+        set_token_kernel<<<1, 1, 0, g_stream>>>(m.state.p, m.prompt.p, i);
+        ++g_launches;
+        const bool last = i == n_prompt - 1;
+        if (last && n_new == 0) { CK(cudaGraphLaunch(m.graph_prefill, g_stream)); g_launches += m.launches_prefill; }
+        else if (last) { CK(cudaGraphLaunch(m.graph_decode, g_stream)); g_launches += m.launches_decode; }
+        else { CK(cudaGraphLaunch(m.graph_prefill, g_stream)); g_launches += m.launches_prefill; }
+    }
+    m.host_pos = n_prompt;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, g_stream));
+    // the last prompt step already produced token 0; every further step feeds the token the previous one picked
+    for (int i = 1; i < n_new; ++i) {
+        CK(cudaGraphLaunch(m.graph_decode, g_stream));
+        g_launches += m.launches_decode;
+    }
+    CK(cudaEventRecord(e1, g_stream));
+    m.host_pos += std::max(0, n_new - 1);
+    std::vector<int> toks(std::max(n_new, 1));
+    if (n_new > 0) CK(cudaMemcpyAsync(toks.data(), m.out_tokens.p, n_new * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    if (logits_host && n_new > 0) CK(cudaMemcpyAsync(logits_host, m.hist.p, (size_t)n_new * V * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (decode_ms) *decode_ms = ms;
+    int produced = n_new;
+    if (stop_on_eos)
+        for (int i = 0; i < n_new; ++i)
+            if (toks[i] == 2) { produced = i + 1; break; }  // hard-coded EOS id 2 (:760)
+    for (int i = 0; i < produced; ++i) out_tokens[i] = toks[i];
+    if (n_out) *n_out = produced;
+    return 0;
+}
+
+int ti_b200_bench_gemv(const ti_qweight_t* ws, size_t n_w, size_t reps, float* ms) {
+    TRY(need_init());
+    if (n_w == 0 || reps == 0) return fail("nothing to time");
+    std::vector<QWeight*> w(n_w);
+    size_t maxK = 0, maxN = 0;
+    for (size_t i = 0; i < n_w; ++i) {
+        w[i] = get_qw(ws[i]);
+        if (!w[i]) return fail("invalid qweight handle");
+        maxK = std::max<size_t>(maxK, w[i]->L.K);
+        maxN = std::max<size_t>(maxN, w[i]->L.N);
+    }
+    DevBuf<float> x, y;
+    TRY(x.alloc(maxK));
+    TRY(y.alloc(maxN));
+    synth_fill_kernel<<<grid_for(maxK), 256, 0, g_stream>>>(x.p, maxK, 12345, 1.0f);
+    ++g_launches;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (size_t i = 0; i < std::min<size_t>(n_w, 3); ++i) TRY(ti_b200_gemv_q_dev(ws[i], x.p, y.p));  // warm-up
+    CK(cudaEventRecord(e0, g_stream));
+    for (size_t r = 0; r < reps; ++r) TRY(ti_b200_gemv_q_dev(ws[r % n_w], x.p, y.p));
+    CK(cudaEventRecord(e1, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    CK(cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 0;
+}
+
+}  // extern "C"

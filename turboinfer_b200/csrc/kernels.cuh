@@ -1,0 +1,527 @@
+// kernels.cuh -- the small kernels around the streaming GEMV: quantize / pack / unpack, the reference-order fp32
+// matmul, element-wise ops, RMSNorm, RoPE, softmax, split-K flash-decoding attention over the paged KV cache,
+// embedding lookup and the greedy-token bookkeeping.  All fp32, no fast-math: divisions, sqrt, roundf, expf are
+// the IEEE / full-precision versions so that integer results are bit-exact with the reference.
+#pragma once
+#include <cfloat>
+#include "gemv.cuh"
+
+namespace tib {
+
+// ---------------------------------------------------------------------------------------------------
+// synthetic weights: uniform(-amp, amp) from a counter-based hash (splitmix64) of (seed, index)
+// ---------------------------------------------------------------------------------------------------
+TIB_HD uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+TIB_HD float synth_uniform(uint64_t seed, uint64_t idx, float amp) {
+    const uint64_t h = splitmix64(seed * 0xD1342543DE82EF95ull + idx);
+    const float u = (float)(uint32_t)(h >> 40) * (1.0f / 16777216.0f);  // [0,1), 24 bits
+    return (2.0f * u - 1.0f) * amp;
+}
+__global__ void synth_fill_kernel(float* out, size_t n, uint64_t seed, float amp) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = synth_uniform(seed, i, amp);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Quantizer::calculate_quantization_info (src/optimize/quantization.cpp:335-394): min / max scan
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_order(float f) {  // order-preserving float -> uint
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float float_unorder(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+// mm[0] = ordered min (init 0xFFFFFFFF), mm[1] = ordered max (init 0)
+__global__ void minmax_kernel(const float* x, size_t n, uint32_t* mm) {
+    float mn = INFINITY, mx = -INFINITY;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&mm[0], float_order(mn));
+        atomicMax(&mm[1], float_order(mx));
+    }
+}
+// sz[0] = scale, sz[1] = zero_point, with the reference's exact expressions (:352-388)
+__global__ void quant_params_kernel(const uint32_t* mm, int qtype, int symmetric, float* sz) {
+    const float mn = float_unorder(mm[0]), mx = float_unorder(mm[1]);
+    float scale, zp;
+    if (symmetric) {
+        const float amax = fmaxf(fabsf(mn), fabsf(mx));
+        scale = __fdiv_rn(amax, qtype == 0 ? 127.0f : 7.0f);
+        zp = 0.0f;
+    } else {
+        scale = __fdiv_rn(__fsub_rn(mx, mn), qtype == 0 ? 255.0f : 15.0f);
+        zp = __fdiv_rn(-mn, scale);
+    }
+    sz[0] = scale;
+    sz[1] = zp;
+}
+
+// quantize_to_int8 (:662-674) / quantize_to_int4 (:676-693): the integer the reference stores
+__device__ __forceinline__ int quantize_one(float x, int qtype, float scale, float zp) {
+    if (qtype == 0) {
+        float v = roundf(__fadd_rn(__fdiv_rn(x, scale), zp));
+        v = fmaxf(-128.0f, fminf(127.0f, v));
+        return (int)v;
+    }
+    float v = roundf(__fsub_rn(__fdiv_rn(x, scale), zp));
+    if (zp == 0.0f) v = fmaxf(-7.0f, fminf(7.0f, v));
+    else v = fmaxf(0.0f, fminf(15.0f, v));
+    return (int)v;
+}
+__global__ void quantize_flat_kernel(const float* x, size_t n, int qtype, float scale, float zp, int8_t* q8, int32_t* q32) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int q = quantize_one(x[i], qtype, scale, zp);
+        if (qtype == 0) q8[i] = (int8_t)q;
+        else q32[i] = q;
+    }
+}
+// dequantize_from_int8 (:695-703): scale*(q - zp);  dequantize_from_int4 (:705-713): scale*(q + zp)
+__global__ void dequantize_flat_kernel(const int8_t* q8, const int32_t* q32, size_t n, int qtype, float scale, float zp, float* x) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (qtype == 0) x[i] = __fmul_rn(scale, __fsub_rn((float)q8[i], zp));
+        else x[i] = __fmul_rn(scale, __fadd_rn((float)q32[i], zp));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pack: fp32 [K][N_src] sources -> quantize -> the streaming layout of qlayout.cuh
+// A packed matrix may fuse several reference tensors that share x:
+//   mode 0  concatenate along N (q | k | v), mode 1  interleave two sources (gate_i, up_i)
+// Each source keeps its own per-tensor scale / zero-point (written per column into colscale / colzterm).
+// ---------------------------------------------------------------------------------------------------
+struct PackSrc {
+    const float* w;   // [K][n] fp32, device
+    int n;
+    const float* sz;  // device: scale, zero_point
+};
+struct PackArgs {
+    PackSrc src[3];
+    int nsrc;
+    int mode;
+    int qtype;       // 0 int8, 1 int4
+    int unit_scale;  // 1: colscale = 1 (compat_literal: unscaled integers)
+    QLayout L;
+    uint8_t* out;
+    float* colscale;
+    float* colzterm;
+};
+__device__ __forceinline__ void pack_locate(const PackArgs& a, int n, int& si, int& sc) {
+    if (a.mode == 1) { si = n & 1; sc = n >> 1; return; }
+    si = 0; sc = n;
+    while (si < a.nsrc - 1 && sc >= a.src[si].n) { sc -= a.src[si].n; ++si; }
+}
+// grid = P slabs, block = 512 (16 warps mirror the 16 consumer warps)
+__global__ void pack_kernel(const PackArgs a) {
+    const QLayout& L = a.L;
+    const Slab slab = make_slab(L, blockIdx.x);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int my_n = warp_items(slab, warp), first = warp_first_item(slab, warp);
+    // byte offset of every round
+    size_t round_off = 0;
+    int r_cur = 0;
+    for (int idx = 0; idx < my_n; ++idx) {
+        const int r = idx / kItemsPerRound, g = idx % kItemsPerRound;
+        while (r_cur < r) { round_off += (size_t)round_total(slab, r_cur) * kItemBytes; ++r_cur; }
+        const int item = first + idx;
+        const int s = item / slab.ncols, c = item - s * slab.ncols;
+        const int n = slab.col0 + c;
+        int si = 0, sc = 0;
+        float scale = 1.f, zp = 0.f;
+        const bool live = n < L.N;
+        if (live) {
+            pack_locate(a, n, si, sc);
+            scale = a.src[si].sz[0];
+            zp = a.src[si].sz[1];
+        }
+        uint32_t words[4] = {0, 0, 0, 0};
+        const int nj = L.ksc / 128;
+        for (int j = 0; j < nj; ++j)
+            for (int e = 0; e < 4; ++e) {
+                const int k = s * L.ksc + 128 * j + 4 * lane + e;
+                int q = 0;
+                if (live && k < L.K) q = quantize_one(a.src[si].w[(size_t)k * a.src[si].n + sc], a.qtype, scale, zp);
+                if (L.bits == 4) {
+                    // symmetric values are stored offset by 8; asymmetric ones (0..15) as they are
+                    const uint32_t u = (uint32_t)((zp == 0.0f || !live) ? q + 8 : q) & 0xFu;
+                    words[j >> 1] |= u << (4 * ((j & 1) * 4 + e));
+                } else {
+                    const uint32_t u = (uint32_t)(q + 128) & 0xFFu;
+                    words[j] |= u << (8 * e);
+                }
+            }
+        uint8_t* dst = a.out + slab.byte0 + round_off + ((size_t)round_warp_offset(slab, r, warp) + g) * kItemBytes + lane * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
+        if (s == 0 && lane == 0) {
+            // y = scale * (sum x*(u - off) + zterm * sum x):
+            //   INT8 dequant = scale*(q - zp)          -> zterm = -zp
+            //   INT4 dequant = scale*(q + zp); asym u=q -> sum x*(u-8) = sum x*q - 8 sum x -> zterm = zp + 8
+            a.colscale[n] = (live && !a.unit_scale) ? scale : (live ? 1.0f : 0.0f);
+            float zt = 0.f;
+            if (live && zp != 0.0f) zt = a.qtype == 0 ? -zp : zp + 8.0f;
+            if (a.colzterm) a.colzterm[n] = a.unit_scale ? 0.f : zt;
+        }
+    }
+}
+// inverse of pack for a single-source matrix: q_out[k][n] in the reference's [K,N] int32 order
+__global__ void unpack_kernel(const uint8_t* packed, QLayout L, int stored_offset4, int32_t* q_out) {
+    const Slab slab = make_slab(L, blockIdx.x);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int my_n = warp_items(slab, warp), first = warp_first_item(slab, warp);
+    size_t round_off = 0;
+    int r_cur = 0;
+    for (int idx = 0; idx < my_n; ++idx) {
+        const int r = idx / kItemsPerRound, g = idx % kItemsPerRound;
+        while (r_cur < r) { round_off += (size_t)round_total(slab, r_cur) * kItemBytes; ++r_cur; }
+        const int item = first + idx;
+        const int s = item / slab.ncols, c = item - s * slab.ncols;
+        const int n = slab.col0 + c;
+        if (n >= L.N) continue;
+        const uint8_t* src = packed + slab.byte0 + round_off + ((size_t)round_warp_offset(slab, r, warp) + g) * kItemBytes + lane * 16;
+        const uint4 wv = *reinterpret_cast<const uint4*>(src);
+        const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
+        const int nj = L.ksc / 128;
+        for (int j = 0; j < nj; ++j)
+            for (int e = 0; e < 4; ++e) {
+                const int k = s * L.ksc + 128 * j + 4 * lane + e;
+                if (k >= L.K) continue;
+                int q;
+                if (L.bits == 4) q = (int)((words[j >> 1] >> (4 * ((j & 1) * 4 + e))) & 0xFu) - stored_offset4;
+                else q = (int)((words[j] >> (8 * e)) & 0xFFu) - 128;
+                q_out[(size_t)k * L.N + n] = q;
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TensorEngine::matmul on fp32 (src/core/tensor_engine.cpp:490-640) in the reference build's order of roundings
+// (see oracle/ti_oracle.c tio_matmul): thread = output column, k sequential.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float chain_unfused4(const float* a, const float* b, size_t ldb, int k0, int k1, float s) {
+    const int kv = k0 + ((k1 - k0) / 4) * 4;
+    for (int k = k0; k < kv; ++k) s = __fadd_rn(s, __fmul_rn(a[k], b[(size_t)k * ldb]));
+    for (int k = kv; k < k1; ++k) s = fmaf(a[k], b[(size_t)k * ldb], s);
+    return s;
+}
+__global__ void matmul_f32_exact_kernel(const float* A, const float* B, float* C, int M, int K, int N, int relu) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= N) return;
+    const float* a = A + (size_t)i * K;
+    const float* b = B + j;
+    const bool tiled = M >= 32 && N >= 32 && K >= 32;
+    float s = 0.f;
+    if (tiled && j < (N / 8) * 8) {
+        for (int k = 0; k < K; ++k) s = fmaf(a[k], b[(size_t)k * N], s);
+    } else if (tiled) {
+        for (int k0 = 0; k0 < K; k0 += 256) s = chain_unfused4(a, b, N, k0, k0 + 256 < K ? k0 + 256 : K, s);
+    } else {
+        s = chain_unfused4(a, b, N, 0, K, s);
+    }
+    C[(size_t)i * N + j] = relu ? fmaxf(s, 0.f) : s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// element-wise ops and row ops (stand-alone TensorEngine entry points; the decode path uses the fused forms)
+// ---------------------------------------------------------------------------------------------------
+enum EwOp : int { EW_SILU = 0, EW_RELU = 1, EW_ADD = 2, EW_MUL = 3, EW_SILU_MUL = 4 };
+__global__ void elementwise_kernel(const float* a, const float* b, float* y, size_t n, int op) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float x = a[i];
+        float r;
+        switch (op) {
+            case EW_SILU: r = x / (1.0f + expf(-x)); break;              // :918
+            case EW_RELU: r = fmaxf(0.0f, x); break;                     // :856
+            case EW_ADD: r = x + b[i]; break;                            // :1664
+            case EW_MUL: r = x * b[i]; break;                            // :1729
+            default: r = b[i] * (x / (1.0f + expf(-x))); break;          // multiply(up, silu(gate)), a = gate, b = up
+        }
+        y[i] = r;
+    }
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    __syncthreads();
+    return s;
+}
+__device__ __forceinline__ float block_max_256(float v, float* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float s = -INFINITY;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s = fmaxf(s, red[i]);
+    __syncthreads();
+    return s;
+}
+
+// rms_norm (:1452-1508), one block per row
+__global__ void rms_norm_kernel(const float* x, const float* w, float* y, int H, float eps) {
+    __shared__ float red[32];
+    const float* xr = x + (size_t)blockIdx.x * H;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) ss = fmaf(xr[i], xr[i], ss);
+    const float tot = block_sum_256(ss, red);
+    const float rms = sqrtf(tot / (float)H + eps);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) y[(size_t)blockIdx.x * H + i] = (xr[i] / rms) * w[i];
+}
+
+// softmax, scalar branch (:1017-1033), one block per row
+__global__ void softmax_kernel(const float* x, float* y, int n, float temperature) {
+    __shared__ float red[32];
+    const float* xr = x + (size_t)blockIdx.x * n;
+    float* yr = y + (size_t)blockIdx.x * n;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, xr[i]);
+    mx = block_max_256(mx, red);
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = expf((xr[i] - mx) / temperature);
+        yr[i] = v;
+        s += v;
+    }
+    const float tot = block_sum_256(s, red);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) yr[i] = yr[i] / tot;
+}
+
+// apply_rope (:1510-1624): rows = B*heads*T vectors of D floats; pos index = (b*T + s) or s
+__global__ void rope_kernel(const float* x, const float* pos, const float* inv_freq, float* y, int heads, int T, int D, int pos_2d, size_t rows) {
+    const int half = D / 2;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < rows * half; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t row = idx / half;
+        const int i = (int)(idx - row * half);
+        const size_t s = row % T, b = row / ((size_t)heads * T);
+        const float p = pos_2d ? pos[b * T + s] : pos[s];
+        float sn, cs;
+        sincosf(p * inv_freq[i], &sn, &cs);
+        const float xe = x[row * D + 2 * i], xo = x[row * D + 2 * i + 1];
+        y[row * D + 2 * i] = __fsub_rn(__fmul_rn(xe, cs), __fmul_rn(xo, sn));
+        y[row * D + 2 * i + 1] = __fadd_rn(__fmul_rn(xe, sn), __fmul_rn(xo, cs));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Split-K flash-decoding attention over the paged KV cache.
+// Replaces attention_fast_incremental (:1254-1388) / multi_head_attention q_len 1 (:1149-1252) and the
+// copy-out of KVCache::update_incremental (inference_engine.cpp:147-157): K/V are read in place, once.
+//   grid (heads, splits): CTA (h, j) covers tokens [j*chunk, (j+1)*chunk) of head h:
+//     scores s_t = scale * q_h . K_t  (warp per token, float4 lanes, shuffle reduce) -> shared memory
+//     block max / exp / sum, o_d = sum_t p_t V_t[d] (threads over d: coalesced rows, no shuffles),
+//     online rescale across sub-blocks of 256 tokens; writes (m, l, o) partials
+//   attn_combine_kernel merges the splits: o = sum_j e^{m_j - M} o_j / sum_j e^{m_j - M} l_j
+// ---------------------------------------------------------------------------------------------------
+constexpr int kAttnThreads = 256;
+constexpr int kAttnTokBlock = 256;
+
+struct AttnArgs {
+    const float* q;          // [heads*D]
+    const float* k_pool;     // [page][page_tokens][H]
+    const float* v_pool;
+    const int* page_table;
+    int page_tokens;
+    const int* pos_ptr;      // device scalar; tokens in cache = *pos_ptr + t_bias
+    int t_bias;              // 1 inside the decode step (the current token was just appended)
+    int H, D, heads;
+    int max_splits, min_chunk;
+    float scale;
+    float* part_o;           // [heads][max_splits][D]
+    float* part_ml;          // [heads][max_splits][2]
+    float* out;              // [heads*D]
+};
+
+__device__ __forceinline__ const float* kv_row(const float* pool, const int* table, int page_tokens, int H, int t) {
+    const int page = table[t / page_tokens];
+    return pool + ((size_t)page * page_tokens + (t % page_tokens)) * H;
+}
+
+__device__ __forceinline__ void attn_split_range(int t, int max_splits, int min_chunk, int& nsplit, int& chunk) {
+    nsplit = (t + min_chunk - 1) / min_chunk;
+    if (nsplit > max_splits) nsplit = max_splits;
+    if (nsplit < 1) nsplit = 1;
+    chunk = (t + nsplit - 1) / nsplit;
+}
+
+__global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnArgs a) {
+    extern __shared__ float sm[];
+    float* qs = sm;                        // D
+    float* sc = qs + a.D;                  // kAttnTokBlock
+    float* red = sc + kAttnTokBlock;       // 32
+    float* ored = red + 32;                // groups * D (cross-group reduce when D < 256)
+    const int h = blockIdx.x, j = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t = *a.pos_ptr + a.t_bias;
+    int nsplit, chunk;
+    attn_split_range(t, a.max_splits, a.min_chunk, nsplit, chunk);
+    if (j >= nsplit) return;
+    const int t0 = j * chunk, t1 = min(t, t0 + chunk);
+    const int D = a.D, hoff = h * D;
+    for (int d = tid; d < D; d += kAttnThreads) qs[d] = a.q[hoff + d];
+    __syncthreads();
+
+    // thread -> (token group, dims) mapping for the value pass
+    const int groups = D < kAttnThreads ? kAttnThreads / D : 1;  // D is a power of two multiple of 32 or >= 256
+    const int grp = D < kAttnThreads ? tid / D : 0;
+    const int d0 = D < kAttnThreads ? tid % D : tid;
+    constexpr int kMaxDimsPerThread = 32;  // D <= 8192
+    float o[kMaxDimsPerThread];
+#pragma unroll
+    for (int i = 0; i < kMaxDimsPerThread; ++i) o[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int tb = t0; tb < t1; tb += kAttnTokBlock) {
+        const int nt = min(kAttnTokBlock, t1 - tb);
+        // scores
+        for (int tt = warp; tt < nt; tt += kAttnThreads / 32) {
+            const float* kr = kv_row(a.k_pool, a.page_table, a.page_tokens, a.H, tb + tt) + hoff;
+            float s = 0.f;
+            for (int d = 4 * lane; d < D; d += 128) {
+                const float4 kv = *reinterpret_cast<const float4*>(kr + d);
+                s = fmaf(qs[d], kv.x, s);
+                s = fmaf(qs[d + 1], kv.y, s);
+                s = fmaf(qs[d + 2], kv.z, s);
+                s = fmaf(qs[d + 3], kv.w, s);
+            }
+            s = warp_sum(s);
+            if (lane == 0) sc[tt] = s * a.scale;
+        }
+        __syncthreads();
+        float mx = -INFINITY;
+        for (int tt = tid; tt < nt; tt += kAttnThreads) mx = fmaxf(mx, sc[tt]);
+        mx = block_max_256(mx, red);
+        const float m_new = fmaxf(m_run, mx);
+        float ls = 0.f;
+        for (int tt = tid; tt < nt; tt += kAttnThreads) {
+            const float p = expf(sc[tt] - m_new);
+            sc[tt] = p;
+            ls += p;
+        }
+        ls = block_sum_256(ls, red);  // also orders the sc[] writes before the reads below
+        const float corr = expf(m_run - m_new);  // 0 on the first block (m_run = -inf)
+        l_run = l_run * corr + ls;
+        m_run = m_new;
+        // values
+#pragma unroll
+        for (int i = 0; i < kMaxDimsPerThread; ++i) {
+            const int d = d0 + i * kAttnThreads;
+            if (i == 0 || d < D) {
+                float acc = o[i] * corr;
+                if (d < D)
+                    for (int tt = grp; tt < nt; tt += groups) {
+                        const float* vr = kv_row(a.v_pool, a.page_table, a.page_tokens, a.H, tb + tt) + hoff;
+                        acc = fmaf(sc[tt], vr[d], acc);
+                    }
+                o[i] = acc;
+            }
+        }
+        __syncthreads();
+    }
+    // write partials
+    float* po = a.part_o + ((size_t)h * a.max_splits + j) * D;
+    if (groups > 1) {
+        ored[grp * D + d0] = o[0];
+        __syncthreads();
+        if (grp == 0) {
+            float acc = 0.f;
+            for (int g = 0; g < groups; ++g) acc += ored[g * D + d0];
+            po[d0] = acc;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < kMaxDimsPerThread; ++i) {
+            const int d = d0 + i * kAttnThreads;
+            if (d < D) po[d] = o[i];
+        }
+    }
+    if (tid == 0) {
+        a.part_ml[((size_t)h * a.max_splits + j) * 2 + 0] = m_run;
+        a.part_ml[((size_t)h * a.max_splits + j) * 2 + 1] = l_run;
+    }
+}
+
+__global__ void attn_combine_kernel(const AttnArgs a) {
+    const int h = blockIdx.x;
+    const int t = *a.pos_ptr + a.t_bias;
+    int nsplit, chunk;
+    attn_split_range(t, a.max_splits, a.min_chunk, nsplit, chunk);
+    const float* ml = a.part_ml + (size_t)h * a.max_splits * 2;
+    float M = -INFINITY;
+    for (int j = 0; j < nsplit; ++j) M = fmaxf(M, ml[2 * j]);
+    float Lsum = 0.f;
+    for (int j = 0; j < nsplit; ++j) Lsum += ml[2 * j + 1] * expf(ml[2 * j] - M);
+    for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
+        float acc = 0.f;
+        for (int j = 0; j < nsplit; ++j)
+            acc = fmaf(a.part_o[((size_t)h * a.max_splits + j) * a.D + d], expf(ml[2 * j] - M), acc);
+        a.out[h * a.D + d] = acc / Lsum;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// decode-step bookkeeping
+// ---------------------------------------------------------------------------------------------------
+struct StepState {
+    int pos;        // tokens in the KV cache
+    int token;      // token to feed next
+    int step;       // tokens written to out_tokens
+    int pad;
+    unsigned long long argmax_key;
+};
+
+// x = token_embeddings[token]  (the lookup of the dead InferenceEngineImpl::forward_pass, inference_engine.cpp:594-612);
+// compat_literal: x[i] = 0.1f * (i % 100)  (:1508-1512)
+__global__ void embed_kernel(const float* emb, const StepState* st, float* x, int H, int literal) {
+    const int tok = st->token;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H; i += gridDim.x * blockDim.x)
+        x[i] = literal ? 0.1f * (float)(i % 100) : emb[(size_t)tok * H + i];
+}
+
+struct StepIO {
+    int* out_tokens;  // generated ids, [out_cap]
+    int out_cap;
+    float* hist;      // optional logits history [hist_cap][V]
+    int hist_cap;
+};
+
+// after the lm_head (or after the last layer during prefill): optionally keep the logits, decode the argmax key
+// (greedy = the top_k 1 branch of sample_next_token, inference_engine.cpp:1585-1598), publish the token and
+// advance the cache position
+__global__ void step_finish_kernel(StepState* st, const StepIO* io, const float* logits, int V, int sample) {
+    const int step = st->step;
+    if (sample && io->hist && step < io->hist_cap)
+        for (int i = threadIdx.x; i < V; i += blockDim.x) io->hist[(size_t)step * V + i] = logits[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (sample) {
+            const int tok = 0x7FFFFFFF - (int)(uint32_t)(st->argmax_key & 0xFFFFFFFFull);
+            st->token = tok;
+            if (io->out_tokens && step < io->out_cap) io->out_tokens[step] = tok;
+            st->step = step + 1;
+        }
+        st->argmax_key = 0ull;
+        st->pos += 1;
+    }
+}
+__global__ void set_token_kernel(StepState* st, const int* prompt, int i) { st->token = prompt[i]; }
+
+}  // namespace tib
