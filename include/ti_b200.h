@@ -149,6 +149,10 @@ int ti_b200_launch_count(uint64_t* n);
 /* times `reps` back-to-back launches of the GEMV over `n_w` different packed weights (cycled, so the working
  * set exceeds L2 when their total size does) with CUDA events on the library stream; ms = total elapsed */
 int ti_b200_bench_gemv(const ti_qweight_t* w, size_t n_w, size_t reps, float* ms);
+/* same, over the model's own packed matrices of one kind, cycling through the layers:
+ * slot 0 = fused q|k|v, 1 = o_proj, 2 = fused gate/up (or up), 3 = down_proj, 4 = lm_head.
+ * alg_bytes_per_launch = K*N*bits/8 + 4*N (scales) + 4*(K + N) (x in, y out), the figure of SURVEY.md 8d. */
+int ti_b200_model_bench_gemv(ti_model_t m, int slot, size_t reps, float* ms, double* alg_bytes_per_launch);
 
 #ifdef __cplusplus
 }

@@ -42,7 +42,9 @@ def test_gemv_q_vs_dequant_matmul(tb, port, qt, sym, K, N):
         qw.free()
     err = rel_err_inf(got, ref)
     assert err <= TOL
-    assert err <= 1e-4, f"re-ordered fp32 accumulate should be ~1e-6, got {err}"
+    # symmetric: only the fp32 summation order differs (~1e-6).  Asymmetric adds the zero-point term zp*sum(x) outside the
+    # dot product, a cancellation the reference performs element by element, so allow an order of magnitude more.
+    assert err <= (1e-4 if sym else 2e-3), f"re-ordered fp32 accumulate should be ~1e-6, got {err}"
 
 
 def test_gemv_q_rows_and_linearity(tb, port):

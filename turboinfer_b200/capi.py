@@ -70,6 +70,7 @@ SYMBOLS = {
     "ti_b200_generate_greedy": (C.c_int, [C.c_uint64, _i32, C.c_int32, C.c_int32, C.c_int32, _i32, _i32, _f, _f]),
     "ti_b200_launch_count": (C.c_int, [C.POINTER(C.c_uint64)]),
     "ti_b200_bench_gemv": (C.c_int, [C.POINTER(C.c_uint64), C.c_size_t, C.c_size_t, _f]),
+    "ti_b200_model_bench_gemv": (C.c_int, [C.c_uint64, C.c_int, C.c_size_t, _f, C.POINTER(C.c_double)]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -301,6 +302,38 @@ class Model:
             self.set_tensor(name, arr)
         self.finalize()
         return self
+
+    def load_synthetic(self, *, gate: bool = True, norms: bool = True) -> "Model":
+        """Random-init weights generated ON THE DEVICE (uniform, amplitude 1/sqrt(fan_in); norm weights 1.0;
+        seeds per SURVEY.md 8d) -- for benchmark-size models whose fp32 weights would not fit host RAM."""
+        V, H, I, L = (self.meta[k] for k in ("vocab", "hidden", "inter", "layers"))
+        self.set_tensor_synthetic("token_embeddings.weight", V, H, 777, 0.1)
+        self.set_tensor_synthetic("lm_head.weight", H, V, 999, 1.0 / np.sqrt(H))
+        ones = np.ones(H, dtype=np.float32)
+        if norms:
+            self.set_tensor("norm.weight", ones)
+        for l in range(L):
+            p, s = f"layers.{l}.", 1000 * l
+            a_h, a_i = 1.0 / np.sqrt(H), 1.0 / np.sqrt(I)
+            self.set_tensor_synthetic(p + "attention.q_proj.weight", H, H, s + 1, a_h)
+            self.set_tensor_synthetic(p + "attention.k_proj.weight", H, H, s + 2, a_h)
+            self.set_tensor_synthetic(p + "attention.v_proj.weight", H, H, s + 3, a_h)
+            self.set_tensor_synthetic(p + "attention.o_proj.weight", H, H, s + 6, a_h)
+            self.set_tensor_synthetic(p + "mlp.up_proj.weight", H, I, s + 4, a_h)
+            if gate:
+                self.set_tensor_synthetic(p + "mlp.gate_proj.weight", H, I, s + 7, a_h)
+            self.set_tensor_synthetic(p + "mlp.down_proj.weight", I, H, s + 5, a_i)
+            if norms:
+                self.set_tensor(p + "attention_norm.weight", ones)
+                self.set_tensor(p + "ffn_norm.weight", ones)
+        self.finalize()
+        return self
+
+    def bench_gemv(self, slot: int, reps: int):
+        """(avg ms per launch, algorithmic bytes per launch) of the model's own GEMVs of one kind, back to back."""
+        ms, by = C.c_float(), C.c_double()
+        _ck(lib().ti_b200_model_bench_gemv(self.handle, slot, reps, C.byref(ms), C.byref(by)))
+        return ms.value / reps, by.value
 
     def finalize(self) -> None:
         _ck(lib().ti_b200_model_finalize(self.handle))

@@ -1144,4 +1144,46 @@ int ti_b200_bench_gemv(const ti_qweight_t* ws, size_t n_w, size_t reps, float* m
     return 0;
 }
 
+int ti_b200_model_bench_gemv(ti_model_t h, int slot, size_t reps, float* ms, double* alg_bytes_per_launch) {
+    TRY(need_init());
+    Model* m = get_model(h);
+    if (!m || !m->finalized) return fail("invalid or unfinalized model handle");
+    std::vector<QWeight*> ws;
+    if (slot == 4) ws.push_back(m->lm_head.get());
+    else
+        for (auto& ly : m->layers) {
+            QWeight* w = slot == 0 ? ly.qkv.get() : slot == 1 ? ly.o.get() : slot == 2 ? ly.gateup.get() : ly.down.get();
+            if (w) ws.push_back(w);
+        }
+    if (ws.empty() || reps == 0) return fail("nothing to time for slot %d", slot);
+    size_t maxK = 0, maxN = 0;
+    for (auto* w : ws) { maxK = std::max<size_t>(maxK, w->L.K); maxN = std::max<size_t>(maxN, w->L.N); }
+    DevBuf<float> x, y;
+    TRY(x.alloc(maxK));
+    TRY(y.alloc(maxN));
+    synth_fill_kernel<<<grid_for(maxK), 256, 0, g_stream>>>(x.p, maxK, 12345, 1.0f);
+    ++g_launches;
+    auto run = [&](QWeight* w) {
+        GemvArgs a{};
+        a.x = x.p;
+        a.epi = EPI_STORE;
+        a.out = y.p;
+        return launch_gemv(*w, a, g_stream);
+    };
+    for (size_t i = 0; i < std::min<size_t>(ws.size(), 3); ++i) TRY(run(ws[i]));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, g_stream));
+    for (size_t r = 0; r < reps; ++r) TRY(run(ws[r % ws.size()]));
+    CK(cudaEventRecord(e1, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    CK(cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const QWeight& w0 = *ws[0];
+    if (alg_bytes_per_launch) *alg_bytes_per_launch = (double)w0.L.K * w0.L.N * w0.L.bits / 8.0 + 4.0 * w0.L.N + 4.0 * (w0.L.K + w0.L.N);
+    return 0;
+}
+
 }  // extern "C"
