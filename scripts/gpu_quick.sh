@@ -1,0 +1,8 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_decode.py -m gpu -q -x --timeout 600 2>&1 | tail -15
+timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_tinyllama.json 2> gpurun_out/bench_tinyllama.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_tinyllama.json')); print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e'], d['whole_step'], d['tokens_tail'])"; tail -5 gpurun_out/bench_tinyllama.err
+timeout 600 python bench.py --workload llama7b-int4-decode256 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_7b_int4.json 2> gpurun_out/bench_7b_int4.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_7b_int4.json')); print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e'], d['whole_step'], d['tokens_tail'])"; tail -5 gpurun_out/bench_7b_int4.err

@@ -14,7 +14,7 @@
 #include <string>
 #include <vector>
 
-#include "kernels.cuh"
+#include "mega.cuh"
 
 using namespace tib;
 
@@ -119,16 +119,22 @@ int set_kernel_attrs() {
     CK(cudaFuncSetAttribute(gemv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(gemv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(attn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CK(cudaFuncSetAttribute(mega_decode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(mega_decode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_attr_done = true;
     return 0;
 }
 
-int launch_gemv(const QWeight& w, GemvArgs a, cudaStream_t st) {
+void fill_weight(const QWeight& w, GemvArgs& a) {
     a.wq = w.packed.p;
     a.colscale = w.colscale.p;
     a.colzterm = w.has_zterm ? w.colzterm.p : nullptr;
     a.L = w.L;
     a.stages = w.stages;
+}
+
+int launch_gemv(const QWeight& w, GemvArgs a, cudaStream_t st) {
+    fill_weight(w, a);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(w.L.P);
     cfg.blockDim = dim3(kGemvThreads);
@@ -238,6 +244,14 @@ struct Model {
     cudaGraphExec_t graph_decode = nullptr, graph_prefill = nullptr;
     DevBuf<StepIO> io;
     int launches_decode = 0, launches_prefill = 0;  // kernels per captured step
+    // persistent-kernel engine
+    bool use_mega = false;
+    DevBuf<MegaPhase> phases;
+    int nphases = 0;
+    DevBuf<unsigned int> sync_buf;   // [0] grid barrier counter, [2..5] two 64-bit argmax keys
+    DevBuf<unsigned int> head_cnt;
+    int mega_stages = 0, mega_max_kpad = 0, mega_max_items = 0, mega_attn_floats = 0;
+    size_t mega_smem = 0;
     int host_pos = 0;  // mirror of state.pos
     ~Model() {
         if (graph_decode) cudaGraphExecDestroy(graph_decode);
@@ -493,6 +507,146 @@ int capture_graph(Model& m, bool with_head, cudaGraphExec_t* out) {
     e = cudaGraphInstantiate(out, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// ---- persistent-kernel engine ---------------------------------------------------------------------------
+int build_mega(Model& m) {
+    const int H = m.cfg.hidden;
+    std::vector<MegaPhase> ph;
+    int max_kpad = 0, max_items = 0;
+    auto gemv_phase = [&](const QWeight& w, GemvArgs g, int x_src, int resid_src, int is_head) {
+        MegaPhase p{};
+        p.type = PH_GEMV;
+        p.x_src = x_src;
+        p.resid_src = resid_src;
+        p.is_head = is_head;
+        fill_weight(w, g);
+        p.g = g;
+        max_kpad = std::max(max_kpad, layout_kpad(w.L));
+        max_items = std::max(max_items, slab_max_items(w.L));
+        ph.push_back(p);
+    };
+    const int mega_splits = std::max(1, std::min(g_num_sms / m.attn_heads, m.max_splits));
+    for (size_t l = 0; l < m.layers.size(); ++l) {
+        Layer& ly = m.layers[l];
+        const int src0 = l == 0 ? SRC_EMB : SRC_PTR;
+        GemvArgs a{};
+        a.x = m.x.p;
+        a.norm_w = ly.attn_norm.p;
+        a.rms_eps = m.cfg.rms_eps;
+        a.epi = EPI_QKV;
+        a.out = m.q.p;
+        a.hidden = H;
+        a.rope_dim = m.cfg.rope_mode == 1 ? H / m.cfg.heads : (m.cfg.rope_mode == 2 ? H : 0);
+        a.inv_freq = m.inv_freq.p;
+        a.pos_ptr = &m.state.p->pos;
+        a.k_pool = ly.k_pool.p;
+        a.v_pool = ly.v_pool.p;
+        a.page_table = m.page_table.p;
+        a.page_tokens = m.page_tokens;
+        gemv_phase(*ly.qkv, a, src0, SRC_PTR, 0);
+        MegaPhase at{};
+        at.type = PH_ATTN;
+        at.at.q = m.q.p;
+        at.at.k_pool = ly.k_pool.p;
+        at.at.v_pool = ly.v_pool.p;
+        at.at.page_table = m.page_table.p;
+        at.at.page_tokens = m.page_tokens;
+        at.at.pos_ptr = &m.state.p->pos;
+        at.at.t_bias = 1;
+        at.at.H = H;
+        at.at.D = m.attn_dim;
+        at.at.heads = m.attn_heads;
+        at.at.max_splits = mega_splits;
+        at.at.min_chunk = 64;
+        at.at.scale = 1.0f / sqrtf((float)m.attn_dim);
+        at.at.part_o = m.part_o.p;
+        at.at.part_ml = m.part_ml.p;
+        at.at.out = m.attn_out.p;
+        ph.push_back(at);
+        GemvArgs o{};
+        o.x = m.attn_out.p;
+        o.epi = EPI_RESIDUAL;
+        o.resid = m.x.p;
+        o.out = m.x.p;
+        gemv_phase(*ly.o, o, SRC_PTR, src0, 0);
+        GemvArgs g{};
+        g.x = m.x.p;
+        g.norm_w = ly.ffn_norm.p;
+        g.rms_eps = m.cfg.rms_eps;
+        g.epi = ly.has_gate ? EPI_SWIGLU : EPI_RELU;
+        g.out = m.act.p;
+        gemv_phase(*ly.gateup, g, SRC_PTR, SRC_PTR, 0);
+        GemvArgs d{};
+        d.x = m.act.p;
+        d.epi = EPI_RESIDUAL;
+        d.resid = m.x.p;
+        d.out = m.x.p;
+        gemv_phase(*ly.down, d, SRC_PTR, SRC_PTR, 0);
+    }
+    GemvArgs lm{};
+    lm.x = m.x.p;
+    lm.norm_w = m.out_norm.p;
+    lm.rms_eps = m.cfg.rms_eps;
+    lm.epi = EPI_LOGITS;
+    lm.out = m.logits.p;
+    gemv_phase(*m.lm_head, lm, m.layers.empty() ? SRC_EMB : SRC_PTR, SRC_PTR, 1);
+
+    m.mega_max_kpad = max_kpad;
+    m.mega_max_items = max_items;
+    m.mega_attn_floats = attn_scratch_floats(m.attn_dim, kConsumerThreads);
+    m.mega_stages = 0;
+    for (int s = kMaxStages; s >= 2; --s)
+        if (mega_smem_bytes(s, max_kpad, max_items, m.mega_attn_floats) <= 227 * 1024) { m.mega_stages = s; break; }
+    if (m.mega_stages == 0) return fail("persistent kernel does not fit shared memory");
+    m.mega_smem = mega_smem_bytes(m.mega_stages, max_kpad, max_items, m.mega_attn_floats);
+    for (auto& p : ph) p.g.stages = m.mega_stages;
+    m.nphases = (int)ph.size();
+    TRY(m.phases.alloc(ph.size()));
+    CK(cudaMemcpyAsync(m.phases.p, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice, g_stream));
+    TRY(m.sync_buf.alloc(8));
+    TRY(m.head_cnt.alloc(std::max(1, m.attn_heads)));
+    CK(cudaMemsetAsync(m.sync_buf.p, 0, 8 * sizeof(unsigned int), g_stream));
+    CK(cudaMemsetAsync(m.head_cnt.p, 0, std::max(1, m.attn_heads) * sizeof(unsigned int), g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    int bits = m.cfg.qtype == TI_Q_INT4 ? 4 : 8;
+    int per_sm = 0;
+    if (bits == 4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_decode_kernel<4>, kGemvThreads, m.mega_smem));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_decode_kernel<8>, kGemvThreads, m.mega_smem));
+    if (per_sm < 1) return fail("persistent kernel cannot be resident (occupancy 0)");
+    return 0;
+}
+
+// n_steps forward passes in one cooperative launch; steps < n_prompt take their token from m.prompt, later ones from
+// the previous step's argmax; steps >= first_sample run the lm_head and publish a token
+int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
+    if (n_steps <= 0) return 0;
+    CK(cudaMemsetAsync(m.sync_buf.p, 0, 8 * sizeof(unsigned int), g_stream));
+    MegaArgs a{};
+    a.phases = m.phases.p;
+    a.nphases = m.nphases;
+    a.emb = m.tok_emb.p;
+    a.H = m.cfg.hidden;
+    a.V = m.cfg.vocab;
+    a.st = m.state.p;
+    a.io = m.io.p;
+    a.prompt = m.prompt.p;
+    a.n_prompt = n_prompt;
+    a.n_steps = n_steps;
+    a.first_sample = first_sample;
+    a.grid_bar = m.sync_buf.p;
+    a.head_cnt = m.head_cnt.p;
+    a.keys = reinterpret_cast<unsigned long long*>(m.sync_buf.p + 2);
+    a.logits = m.logits.p;
+    a.stages = m.mega_stages;
+    a.max_kpad = m.mega_max_kpad;
+    a.max_items = m.mega_max_items;
+    a.attn_floats = m.mega_attn_floats;
+    void* args[] = {&a};
+    const void* fn = m.cfg.qtype == TI_Q_INT4 ? (const void*)mega_decode_kernel<4> : (const void*)mega_decode_kernel<8>;
+    CK(cudaLaunchCooperativeKernel(fn, dim3(g_num_sms), dim3(kGemvThreads), args, m.mega_smem, g_stream));
+    ++g_launches;
     return 0;
 }
 
@@ -816,10 +970,7 @@ int ti_b200_softmax(const float* x_host, float* y_host, size_t rows, size_t n, f
     return 0;
 }
 
-static size_t attn_smem_bytes(int D) {
-    const int groups = D < kAttnThreads ? kAttnThreads / D : 1;
-    return sizeof(float) * ((size_t)D + kAttnTokBlock + 32 + (size_t)groups * D);
-}
+static size_t attn_smem_bytes(int D) { return sizeof(float) * (size_t)attn_scratch_floats(D, kAttnThreads); }
 static int attn_check_dim(size_t H, size_t heads) {
     if (heads == 0 || H % heads != 0) return fail("Hidden size must be divisible by number of heads");
     const size_t D = H / heads;
@@ -940,6 +1091,7 @@ int ti_b200_model_finalize(ti_model_t h) {
     m.attn_dim = H / m.attn_heads;
     m.attn_smem = attn_smem_bytes(m.attn_dim);
     m.max_splits = std::max(1, std::min((2 * g_num_sms + m.attn_heads - 1) / m.attn_heads, 512));
+    m.max_splits = std::max(m.max_splits, g_num_sms / m.attn_heads);
     m.num_pages = (m.cfg.max_seq + m.page_tokens - 1) / m.page_tokens;
     for (auto& ly : m.layers) {
         TRY(pack_ready(m, ly, true));
@@ -972,6 +1124,13 @@ int ti_b200_model_finalize(ti_model_t h) {
     std::vector<float> f = host_inv_freq(rope_dim, m.cfg.rope_theta);
     TRY(upload(m.inv_freq, f.data(), f.size()));
     CK(cudaStreamSynchronize(g_stream));
+    bool complete = true;
+    for (auto& ly : m.layers) complete &= (ly.qkv && ly.o && ly.gateup && ly.down);
+    const char* eng = getenv("TURBOINFER_B200_ENGINE");
+    const bool want_graph = m.cfg.reserved[0] == 1 || (eng && std::string(eng) == "graph");
+    m.use_mega = complete && !want_graph;
+    TRY(m.prompt.alloc(16));
+    if (m.use_mega) TRY(build_mega(m));
     TRY(capture_graph(m, true, &m.graph_decode));
     TRY(capture_graph(m, false, &m.graph_prefill));
     m.finalized = true;
@@ -1039,8 +1198,12 @@ int ti_b200_decode_step(ti_model_t h, int32_t token, float* logits_host, int32_t
     CK(cudaMemcpyAsync(&m->state.p->token, &token, sizeof(int), cudaMemcpyHostToDevice, g_stream));
     const int zero = 0;
     CK(cudaMemcpyAsync(&m->state.p->step, &zero, sizeof(int), cudaMemcpyHostToDevice, g_stream));
-    CK(cudaGraphLaunch(m->graph_decode, g_stream));
-    g_launches += m->launches_decode;
+    if (m->use_mega) {
+        TRY(run_mega(*m, 0, 1, 0));
+    } else {
+        CK(cudaGraphLaunch(m->graph_decode, g_stream));
+        g_launches += m->launches_decode;
+    }
     m->host_pos += 1;
     if (logits_host) CK(cudaMemcpyAsync(logits_host, m->logits.p, (size_t)m->cfg.vocab * 4, cudaMemcpyDeviceToHost, g_stream));
     int tok = 0;
@@ -1075,6 +1238,16 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
         io.hist_cap = n_new;
     }
     CK(cudaMemcpyAsync(m.io.p, &io, sizeof(io), cudaMemcpyHostToDevice, g_stream));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    if (m.use_mega) {
+        // launch 1: the prompt (its last step picks token 0); launch 2: the decode loop, timed
+        TRY(run_mega(m, n_prompt, n_prompt, n_new > 0 ? n_prompt - 1 : n_prompt));
+        CK(cudaEventRecord(e0, g_stream));
+        TRY(run_mega(m, 0, n_new - 1, 0));
+        CK(cudaEventRecord(e1, g_stream));
+    } else {
     // prefill: the prompt goes through the same incremental step, one token at a time; only the last one needs logits
     for (int i = 0; i < n_prompt; ++i) {
         set_token_kernel<<<1, 1, 0, g_stream>>>(m.state.p, m.prompt.p, i);
@@ -1084,10 +1257,6 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
         else if (last) { CK(cudaGraphLaunch(m.graph_decode, g_stream)); g_launches += m.launches_decode; }
         else { CK(cudaGraphLaunch(m.graph_prefill, g_stream)); g_launches += m.launches_prefill; }
     }
-    m.host_pos = n_prompt;
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, g_stream));
     // the last prompt step already produced token 0; every further step feeds the token the previous one picked
     for (int i = 1; i < n_new; ++i) {
@@ -1095,7 +1264,8 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
         g_launches += m.launches_decode;
     }
     CK(cudaEventRecord(e1, g_stream));
-    m.host_pos += std::max(0, n_new - 1);
+    }
+    m.host_pos = n_prompt + std::max(0, n_new - 1);
     std::vector<int> toks(std::max(n_new, 1));
     if (n_new > 0) CK(cudaMemcpyAsync(toks.data(), m.out_tokens.p, n_new * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
     if (logits_host && n_new > 0) CK(cudaMemcpyAsync(logits_host, m.hist.p, (size_t)n_new * V * 4, cudaMemcpyDeviceToHost, g_stream));

@@ -196,49 +196,41 @@ __device__ __forceinline__ GemvSmem gemv_carve(uint8_t* base, const QLayout& L, 
     return s;
 }
 
-// ---- the kernel body -------------------------------------------------------------------------------
-template <int BITS>
-__device__ __forceinline__ void gemv_body(const GemvArgs& a, uint8_t* smem_raw) {
-    const QLayout& L = a.L;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const Slab slab = make_slab(L, blockIdx.x);
-    GemvSmem sm = gemv_carve(smem_raw, L, a.stages);
+// ---- building blocks shared by the stand-alone GEMV kernel and the persistent decode kernel (mega.cuh) -------
+
+// cross-CTA data (written by another SM earlier in the same launch) must not be served from a stale L1 line
+__device__ __forceinline__ float ld_act(const float* p, bool coherent) { return coherent ? __ldcg(p) : *p; }
+
+struct PhaseCtx {
+    bool coherent;   // activations were produced by other CTAs of the same launch: read them through L2
+    int pos;         // cache position of the current token (EPI_QKV); < 0: read *pos_ptr
+    unsigned long long* key;  // EPI_LOGITS: argmax key to use instead of GemvArgs::argmax_key (nullptr: keep)
+};
+
+// producer: stream this CTA's slab through the ring.  `it` counts stages over the whole launch.
+__device__ __forceinline__ void gemv_produce(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, uint32_t& it) {
     const int S = a.stages;
-
-    if (tid == 0) {
-        for (int i = 0; i < S; ++i) {
-            mbar_init(&sm.full[i], 1);
-            mbar_init(&sm.empty[i], kConsumerWarps);
-        }
-        fence_mbar_init();
+    const uint8_t* src = a.wq + slab.byte0;
+    for (int r = 0; r < slab.rounds; ++r, ++it) {
+        const uint32_t st = it % S, use = it / S;
+        if (use > 0) mbar_wait(&sm.empty[st], (use - 1) & 1);
+        const uint32_t bytes = (uint32_t)round_total(slab, r) * kItemBytes;
+        mbar_arrive_expect_tx(&sm.full[st], bytes);
+        bulk_g2s_evict_first(sm.ring + (size_t)st * kStageBytes, src, bytes, &sm.full[st]);
+        src += bytes;
     }
-    __syncthreads();
+}
 
-    if (warp == kConsumerWarps) {
-        // ===== producer: the weights do not depend on the previous kernel, start streaming at once =====
-        if (lane == 0) {
-            const uint8_t* src = a.wq + slab.byte0;
-            for (int r = 0; r < slab.rounds; ++r) {
-                const int st = r % S;
-                const int use = r / S;
-                if (use > 0) mbar_wait(&sm.empty[st], (use - 1) & 1);
-                const uint32_t bytes = (uint32_t)round_total(slab, r) * kItemBytes;
-                mbar_arrive_expect_tx(&sm.full[st], bytes);
-                bulk_g2s_evict_first(sm.ring + (size_t)st * kStageBytes, src, bytes, &sm.full[st]);
-                src += bytes;
-            }
-        }
-        return;
-    }
-
-    // ===== consumers =====
-    pdl_wait_prior_grid();  // x (and resid / pos) come from the previous kernel in the stream
-
-    // -- prologue: stage x, fused RMSNorm, INT4 nibble-position prescale --------------------------------
+// consumers, prologue: stage x into shared memory (fused RMSNorm, INT4 nibble-position prescale).
+// Returns sum(x') (only meaningful when want_sum).
+template <int BITS>
+__device__ __forceinline__ float gemv_stage_x(const GemvArgs& a, const float* x, const GemvSmem& sm, bool coherent, bool want_sum,
+                                              int tid, int warp, int lane) {
+    const QLayout& L = a.L;
     const int K = L.K, kpad = layout_kpad(L);
     float ss = 0.f;
     for (int k = tid; k < kpad; k += kConsumerThreads) {
-        float v = k < K ? a.x[k] : 0.f;
+        const float v = k < K ? ld_act(x + k, coherent) : 0.f;
         sm.xs[k] = v;
         ss = fmaf(v, v, ss);
     }
@@ -259,23 +251,28 @@ __device__ __forceinline__ void gemv_body(const GemvArgs& a, uint8_t* smem_raw) 
         sm.xs[k] = v;
     }
     float sumx = 0.f;
-    if (a.colzterm != nullptr) sumx = consumer_block_sum(sx, sm.red, warp, lane);
+    if (want_sum) sumx = consumer_block_sum(sx, sm.red, warp, lane);
     bar_sync(1, kConsumerThreads);
+    return sumx;
+}
 
-    // -- main loop -------------------------------------------------------------------------------------
+// consumers, main loop: per ring stage LDS.128 weights, unpack, FFMA2, reduce, partials to shared memory
+template <int BITS>
+__device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, uint32_t& it, int warp, int lane) {
+    const QLayout& L = a.L;
+    const int S = a.stages;
     constexpr int NX = BITS == 4 ? 16 : 8;  // float2 pairs of x per lane per superchunk
     f32x2 xr[NX];
     int cur_s = -1;
     const int my_n = warp_items(slab, warp);
     const int first = warp_first_item(slab, warp);
-    int it_s = first / slab.ncols;       // superchunk of the next item
+    int it_s = first / slab.ncols;  // superchunk of the next item
     int it_c = first - it_s * slab.ncols;
     int item = first;
-
-    for (int r = 0; r < slab.rounds; ++r) {
-        const int st = r % S;
+    for (int r = 0; r < slab.rounds; ++r, ++it) {
+        const uint32_t st = it % S;
         const int g_n = round_items(my_n, r);
-        mbar_wait(&sm.full[st], (r / S) & 1);
+        mbar_wait(&sm.full[st], (it / S) & 1);
         const uint8_t* wbase = sm.ring + (size_t)st * kStageBytes + (size_t)round_warp_offset(slab, r, warp) * kItemBytes + lane * 16;
         float v[kItemsPerRound] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -292,8 +289,8 @@ __device__ __forceinline__ void gemv_body(const GemvArgs& a, uint8_t* smem_raw) 
                     }
                 }
                 const uint4 wv = lds128(wbase + g * kItemBytes);
-                if (BITS == 4) v[g] = dot_q4(wv, reinterpret_cast<const f32x2(&)[16]>(xr[0]));
-                else v[g] = dot_q8(wv, reinterpret_cast<const f32x2(&)[8]>(xr[0]));
+                if constexpr (BITS == 4) v[g] = dot_q4(wv, xr);
+                else v[g] = dot_q8(wv, xr);
                 if (++it_c == slab.ncols) { it_c = 0; ++it_s; }
             }
         }
@@ -305,8 +302,12 @@ __device__ __forceinline__ void gemv_body(const GemvArgs& a, uint8_t* smem_raw) 
         item += g_n;
     }
     bar_sync(1, kConsumerThreads);
+}
 
-    // -- epilogue ----------------------------------------------------------------------------------------
+// consumers, epilogue: fixed-order sum of the superchunk partials, scale, fused tail op
+__device__ __forceinline__ void gemv_epilogue(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, float sumx, const float* resid,
+                                              const PhaseCtx& ctx, int tid, int lane) {
+    const QLayout& L = a.L;
     const int ncols = slab.ncols, nsc = L.nsc;
     auto column = [&](int c) -> float {
         float acc = 0.f;
@@ -315,10 +316,8 @@ __device__ __forceinline__ void gemv_body(const GemvArgs& a, uint8_t* smem_raw) 
         if (a.colzterm != nullptr) acc = fmaf(a.colzterm[n], sumx, acc);
         return a.colscale[n] * acc;
     };
-
     if (a.epi == EPI_SWIGLU || a.epi == EPI_QKV) {
-        // column pairs
-        for (int pc = tid; pc < ncols / 2; pc += kConsumerThreads) {
+        for (int pc = tid; pc < ncols / 2; pc += kConsumerThreads) {  // column pairs
             const int n0 = slab.col0 + 2 * pc;
             if (n0 >= L.N) continue;
             const float y0 = column(2 * pc), y1 = column(2 * pc + 1);
@@ -328,7 +327,7 @@ __device__ __forceinline__ void gemv_body(const GemvArgs& a, uint8_t* smem_raw) 
             } else {
                 const int H = a.hidden;
                 const int seg = n0 / H, d = n0 - seg * H;
-                const int pos = *a.pos_ptr;
+                const int pos = ctx.pos >= 0 ? ctx.pos : *a.pos_ptr;
                 float o0 = y0, o1 = y1;
                 if (seg < 2 && a.rope_dim > 0) {
                     const int i = (d % a.rope_dim) >> 1;
@@ -354,7 +353,7 @@ __device__ __forceinline__ void gemv_body(const GemvArgs& a, uint8_t* smem_raw) 
             const int n = slab.col0 + c;
             if (n >= L.N) continue;
             float y = column(c);
-            if (a.epi == EPI_RESIDUAL) y = a.resid[n] + y;
+            if (a.epi == EPI_RESIDUAL) y = ld_act(resid + n, ctx.coherent) + y;
             else if (a.epi == EPI_RELU) y = fmaxf(y, 0.f);
             a.out[n] = y;
             if (a.epi == EPI_LOGITS && (y > best)) { best = y; besti = n; }
@@ -366,15 +365,39 @@ __device__ __forceinline__ void gemv_body(const GemvArgs& a, uint8_t* smem_raw) 
                 const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
                 key = other > key ? other : key;
             }
-            if (lane == 0 && key != 0ull) atomicMax(a.argmax_key, key);
+            if (lane == 0 && key != 0ull) atomicMax(ctx.key ? ctx.key : a.argmax_key, key);
         }
     }
 }
 
+__device__ __forceinline__ void gemv_init_barriers(const GemvSmem& sm, int stages) {
+    for (int i = 0; i < stages; ++i) {
+        mbar_init(&sm.full[i], 1);
+        mbar_init(&sm.empty[i], kConsumerWarps);
+    }
+    fence_mbar_init();
+}
+
+// ---- the stand-alone kernel: one GEMV per launch -----------------------------------------------------------
 template <int BITS>
 __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const __grid_constant__ GemvArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    gemv_body<BITS>(a, smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const Slab slab = make_slab(a.L, blockIdx.x);
+    const GemvSmem sm = gemv_carve(smem_raw, a.L, a.stages);
+    if (tid == 0) gemv_init_barriers(sm, a.stages);
+    __syncthreads();
+    uint32_t it = 0;
+    if (warp == kConsumerWarps) {
+        // the weights do not depend on the previous kernel: start streaming at once
+        if (lane == 0) gemv_produce(a, slab, sm, it);
+        return;
+    }
+    pdl_wait_prior_grid();  // x (and resid / pos) come from the previous kernel in the stream
+    const PhaseCtx ctx{false, -1, nullptr};
+    const float sumx = gemv_stage_x<BITS>(a, a.x, sm, false, a.colzterm != nullptr, tid, warp, lane);
+    gemv_consume<BITS>(a, slab, sm, it, warp, lane);
+    gemv_epilogue(a, slab, sm, sumx, a.resid, ctx, tid, lane);
 }
 
 }  // namespace tib

@@ -362,120 +362,7 @@ __device__ __forceinline__ void attn_split_range(int t, int max_splits, int min_
     chunk = (t + nsplit - 1) / nsplit;
 }
 
-__global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnArgs a) {
-    extern __shared__ float sm[];
-    float* qs = sm;                        // D
-    float* sc = qs + a.D;                  // kAttnTokBlock
-    float* red = sc + kAttnTokBlock;       // 32
-    float* ored = red + 32;                // groups * D (cross-group reduce when D < 256)
-    const int h = blockIdx.x, j = blockIdx.y;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int t = *a.pos_ptr + a.t_bias;
-    int nsplit, chunk;
-    attn_split_range(t, a.max_splits, a.min_chunk, nsplit, chunk);
-    if (j >= nsplit) return;
-    const int t0 = j * chunk, t1 = min(t, t0 + chunk);
-    const int D = a.D, hoff = h * D;
-    for (int d = tid; d < D; d += kAttnThreads) qs[d] = a.q[hoff + d];
-    __syncthreads();
-
-    // thread -> (token group, dims) mapping for the value pass
-    const int groups = D < kAttnThreads ? kAttnThreads / D : 1;  // D is a power of two multiple of 32 or >= 256
-    const int grp = D < kAttnThreads ? tid / D : 0;
-    const int d0 = D < kAttnThreads ? tid % D : tid;
-    constexpr int kMaxDimsPerThread = 32;  // D <= 8192
-    float o[kMaxDimsPerThread];
-#pragma unroll
-    for (int i = 0; i < kMaxDimsPerThread; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
-
-    for (int tb = t0; tb < t1; tb += kAttnTokBlock) {
-        const int nt = min(kAttnTokBlock, t1 - tb);
-        // scores
-        for (int tt = warp; tt < nt; tt += kAttnThreads / 32) {
-            const float* kr = kv_row(a.k_pool, a.page_table, a.page_tokens, a.H, tb + tt) + hoff;
-            float s = 0.f;
-            for (int d = 4 * lane; d < D; d += 128) {
-                const float4 kv = *reinterpret_cast<const float4*>(kr + d);
-                s = fmaf(qs[d], kv.x, s);
-                s = fmaf(qs[d + 1], kv.y, s);
-                s = fmaf(qs[d + 2], kv.z, s);
-                s = fmaf(qs[d + 3], kv.w, s);
-            }
-            s = warp_sum(s);
-            if (lane == 0) sc[tt] = s * a.scale;
-        }
-        __syncthreads();
-        float mx = -INFINITY;
-        for (int tt = tid; tt < nt; tt += kAttnThreads) mx = fmaxf(mx, sc[tt]);
-        mx = block_max_256(mx, red);
-        const float m_new = fmaxf(m_run, mx);
-        float ls = 0.f;
-        for (int tt = tid; tt < nt; tt += kAttnThreads) {
-            const float p = expf(sc[tt] - m_new);
-            sc[tt] = p;
-            ls += p;
-        }
-        ls = block_sum_256(ls, red);  // also orders the sc[] writes before the reads below
-        const float corr = expf(m_run - m_new);  // 0 on the first block (m_run = -inf)
-        l_run = l_run * corr + ls;
-        m_run = m_new;
-        // values
-#pragma unroll
-        for (int i = 0; i < kMaxDimsPerThread; ++i) {
-            const int d = d0 + i * kAttnThreads;
-            if (i == 0 || d < D) {
-                float acc = o[i] * corr;
-                if (d < D)
-                    for (int tt = grp; tt < nt; tt += groups) {
-                        const float* vr = kv_row(a.v_pool, a.page_table, a.page_tokens, a.H, tb + tt) + hoff;
-                        acc = fmaf(sc[tt], vr[d], acc);
-                    }
-                o[i] = acc;
-            }
-        }
-        __syncthreads();
-    }
-    // write partials
-    float* po = a.part_o + ((size_t)h * a.max_splits + j) * D;
-    if (groups > 1) {
-        ored[grp * D + d0] = o[0];
-        __syncthreads();
-        if (grp == 0) {
-            float acc = 0.f;
-            for (int g = 0; g < groups; ++g) acc += ored[g * D + d0];
-            po[d0] = acc;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < kMaxDimsPerThread; ++i) {
-            const int d = d0 + i * kAttnThreads;
-            if (d < D) po[d] = o[i];
-        }
-    }
-    if (tid == 0) {
-        a.part_ml[((size_t)h * a.max_splits + j) * 2 + 0] = m_run;
-        a.part_ml[((size_t)h * a.max_splits + j) * 2 + 1] = l_run;
-    }
-}
-
-__global__ void attn_combine_kernel(const AttnArgs a) {
-    const int h = blockIdx.x;
-    const int t = *a.pos_ptr + a.t_bias;
-    int nsplit, chunk;
-    attn_split_range(t, a.max_splits, a.min_chunk, nsplit, chunk);
-    const float* ml = a.part_ml + (size_t)h * a.max_splits * 2;
-    float M = -INFINITY;
-    for (int j = 0; j < nsplit; ++j) M = fmaxf(M, ml[2 * j]);
-    float Lsum = 0.f;
-    for (int j = 0; j < nsplit; ++j) Lsum += ml[2 * j + 1] * expf(ml[2 * j] - M);
-    for (int d = threadIdx.x; d < a.D; d += blockDim.x) {
-        float acc = 0.f;
-        for (int j = 0; j < nsplit; ++j)
-            acc = fmaf(a.part_o[((size_t)h * a.max_splits + j) * a.D + d], expf(ml[2 * j] - M), acc);
-        a.out[h * a.D + d] = acc / Lsum;
-    }
-}
+// (attn_partial_kernel / attn_combine_kernel are defined in mega.cuh on top of attn_item / attn_merge_head)
 
 // ---------------------------------------------------------------------------------------------------
 // decode-step bookkeeping
