@@ -154,6 +154,10 @@ int ti_b200_bench_gemv(const ti_qweight_t* w, size_t n_w, size_t reps, float* ms
  * alg_bytes_per_launch = K*N*bits/8 + 4*N (scales) + 4*(K + N) (x in, y out), the figure of SURVEY.md 8d. */
 int ti_b200_model_bench_gemv(ti_model_t m, int slot, size_t reps, float* ms, double* alg_bytes_per_launch);
 
+/* debug: one decode step on the persistent-kernel engine with CTA 0 recording 6 SM-clock stamps per phase
+ * (phase start, barrier passed, x staged, weights consumed, epilogue done, barrier arrived) */
+int ti_b200_debug_timeline(ti_model_t m, int32_t token, int64_t* stamps, size_t cap, size_t* n_phases);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,7 @@ SYMBOLS = {
     "ti_b200_launch_count": (C.c_int, [C.POINTER(C.c_uint64)]),
     "ti_b200_bench_gemv": (C.c_int, [C.POINTER(C.c_uint64), C.c_size_t, C.c_size_t, _f]),
     "ti_b200_model_bench_gemv": (C.c_int, [C.c_uint64, C.c_int, C.c_size_t, _f, C.POINTER(C.c_double)]),
+    "ti_b200_debug_timeline": (C.c_int, [C.c_uint64, C.c_int32, C.POINTER(C.c_int64), C.c_size_t, C.POINTER(C.c_size_t)]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -328,6 +329,13 @@ class Model:
                 self.set_tensor(p + "ffn_norm.weight", ones)
         self.finalize()
         return self
+
+    def debug_timeline(self, token: int = 1) -> np.ndarray:
+        """[phases, 6] SM-clock stamps of CTA 0 for one decode step on the persistent-kernel engine."""
+        buf = np.zeros(6 * 4096, dtype=np.int64)
+        n = C.c_size_t()
+        _ck(lib().ti_b200_debug_timeline(self.handle, token, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size, C.byref(n)))
+        return buf[: 6 * n.value].reshape(n.value, 6).copy()
 
     def bench_gemv(self, slot: int, reps: int):
         """(avg ms per launch, algorithmic bytes per launch) of the model's own GEMVs of one kind, back to back."""

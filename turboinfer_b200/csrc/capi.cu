@@ -251,6 +251,8 @@ struct Model {
     DevBuf<unsigned int> sync_buf;   // [0] grid barrier counter, [2..5] two 64-bit argmax keys
     DevBuf<unsigned int> head_cnt;
     int mega_stages = 0, mega_max_kpad = 0, mega_max_items = 0, mega_attn_floats = 0;
+    DevBuf<long long> dbg;
+    bool dbg_on = false;
     size_t mega_smem = 0;
     int host_pos = 0;  // mirror of state.pos
     ~Model() {
@@ -612,8 +614,8 @@ int build_mega(Model& m) {
     CK(cudaStreamSynchronize(g_stream));
     int bits = m.cfg.qtype == TI_Q_INT4 ? 4 : 8;
     int per_sm = 0;
-    if (bits == 4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_decode_kernel<4>, kGemvThreads, m.mega_smem));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_decode_kernel<8>, kGemvThreads, m.mega_smem));
+    if (bits == 4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_decode_kernel<4>, kMegaThreads, m.mega_smem));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_decode_kernel<8>, kMegaThreads, m.mega_smem));
     if (per_sm < 1) return fail("persistent kernel cannot be resident (occupancy 0)");
     return 0;
 }
@@ -643,9 +645,10 @@ int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
     a.max_kpad = m.mega_max_kpad;
     a.max_items = m.mega_max_items;
     a.attn_floats = m.mega_attn_floats;
+    a.dbg = m.dbg_on ? m.dbg.p : nullptr;
     void* args[] = {&a};
     const void* fn = m.cfg.qtype == TI_Q_INT4 ? (const void*)mega_decode_kernel<4> : (const void*)mega_decode_kernel<8>;
-    CK(cudaLaunchCooperativeKernel(fn, dim3(g_num_sms), dim3(kGemvThreads), args, m.mega_smem, g_stream));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(g_num_sms), dim3(kMegaThreads), args, m.mega_smem, g_stream));
     ++g_launches;
     return 0;
 }
@@ -1281,6 +1284,29 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
             if (toks[i] == 2) { produced = i + 1; break; }  // hard-coded EOS id 2 (:760)
     for (int i = 0; i < produced; ++i) out_tokens[i] = toks[i];
     if (n_out) *n_out = produced;
+    return 0;
+}
+
+int ti_b200_debug_timeline(ti_model_t h, int32_t token, int64_t* stamps, size_t cap, size_t* n_phases) {
+    TRY(need_init());
+    Model* m = get_model(h);
+    if (!m || !m->finalized || !m->use_mega) return fail("timeline needs a finalized model on the persistent-kernel engine");
+    TRY(check_capacity(*m, 1));
+    const size_t n = (size_t)m->nphases * 6;
+    if (cap < n) return fail("stamp buffer too small: need %zu", n);
+    TRY(m->dbg.alloc(n));
+    CK(cudaMemsetAsync(m->dbg.p, 0, n * sizeof(long long), g_stream));
+    StepIO io{};
+    CK(cudaMemcpyAsync(m->io.p, &io, sizeof(io), cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(&m->state.p->token, &token, sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    m->dbg_on = true;
+    int rc = run_mega(*m, 0, 1, 0);
+    m->dbg_on = false;
+    TRY(rc);
+    m->host_pos += 1;
+    CK(cudaMemcpyAsync(stamps, m->dbg.p, n * sizeof(long long), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    *n_phases = m->nphases;
     return 0;
 }
 

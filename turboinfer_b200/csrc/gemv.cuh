@@ -85,12 +85,25 @@ __device__ __forceinline__ float consumer_block_sum(float v, float* red, int war
 // INT4: a lane's 16 B hold 32 nibbles u = q + 8.  (w & (0xF << 4p)) | 0x4B000000 is the float 2^23 + u*16^p;
 // adding -(2^23 + 8*16^p) leaves (u - 8)*16^p exactly, and x was pre-multiplied by 16^-p when it was staged,
 // so one LOP3 + half an FADD2 + half an FFMA2 per weight, all exact until the fp32 accumulate.
-__device__ __forceinline__ float dot_q4(const uint4& wv, const f32x2 (&xr)[16]) {
-    const uint32_t MAGIC = 0x4B000000u;
-    const f32x2 C01 = pack2(-8388616.f, -8388736.f);
-    const f32x2 C23 = pack2(-8390656.f, -8421376.f);
-    const f32x2 C42 = pack2(-8912896.f, -8390656.f);
-    const f32x2 C34 = pack2(-8421376.f, -8912896.f);
+struct Q4Consts {
+    uint32_t magic;
+    f32x2 c01, c23, c42, c34;
+};
+// The constants are made opaque to the compiler once per kernel so they live in registers instead of being
+// re-materialised (UMOV pairs) for every item.
+__device__ __forceinline__ Q4Consts q4_consts() {
+    Q4Consts c;
+    c.magic = 0x4B000000u;
+    c.c01 = pack2(-8388616.f, -8388736.f);
+    c.c23 = pack2(-8390656.f, -8421376.f);
+    c.c42 = pack2(-8912896.f, -8390656.f);
+    c.c34 = pack2(-8421376.f, -8912896.f);
+    asm volatile("" : "+r"(c.magic), "+l"(c.c01), "+l"(c.c23), "+l"(c.c42), "+l"(c.c34));
+    return c;
+}
+__device__ __forceinline__ float dot_q4(const uint4& wv, const f32x2 (&xr)[16], const Q4Consts& k) {
+    const uint32_t MAGIC = k.magic;
+    const f32x2 C01 = k.c01, C23 = k.c23, C42 = k.c42, C34 = k.c34;
     f32x2 acc0 = 0ull, acc1 = 0ull;
     const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
@@ -116,9 +129,9 @@ __device__ __forceinline__ float dot_q4(const uint4& wv, const f32x2 (&xr)[16]) 
 }
 
 // INT8: a lane's 16 B hold 16 bytes q + 128; PRMT drops byte e into the mantissa of 2^23.
-__device__ __forceinline__ float dot_q8(const uint4& wv, const f32x2 (&xr)[8]) {
-    const uint32_t MAGIC = 0x4B000000u;
-    const f32x2 C = pack2(-8388736.f, -8388736.f);
+__device__ __forceinline__ float dot_q8(const uint4& wv, const f32x2 (&xr)[8], const Q4Consts& k) {
+    const uint32_t MAGIC = k.magic;
+    const f32x2 C = k.c01 == 0ull ? 0ull : pack2(-8388736.f, -8388736.f);
     f32x2 acc0 = 0ull, acc1 = 0ull;
     const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
@@ -223,32 +236,106 @@ __device__ __forceinline__ void gemv_produce(const GemvArgs& a, const Slab& slab
 
 // consumers, prologue: stage x into shared memory (fused RMSNorm, INT4 nibble-position prescale).
 // Returns sum(x') (only meaningful when want_sum).
+// Fast path (K % 4 == 0, 16-byte aligned pointers): 128-bit loads, four per thread in flight before first use, so
+// the global-memory latency is paid once per batch instead of once per element.
+__device__ __forceinline__ float4 ld_act4(const float* p, bool coherent) {
+    return coherent ? __ldcg(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p);
+}
+template <int BITS>
+__device__ __forceinline__ float4 q4_prescale4(float4 v, int k0) {
+    if (BITS == 4) {
+        // element e of the float4 at k0 sits at nibble position p(j, e), j = (k0 % 1024) / 128  (qlayout.cuh q4_pos)
+        if (((k0 & 1023) >> 7) & 1) { v.x *= 1.0f / 65536.0f; v.y *= 1.0f / 256.0f; v.z *= 1.0f / 4096.0f; v.w *= 1.0f / 65536.0f; }
+        else { v.y *= 1.0f / 16.0f; v.z *= 1.0f / 256.0f; v.w *= 1.0f / 4096.0f; }
+    }
+    return v;
+}
+
 template <int BITS>
 __device__ __forceinline__ float gemv_stage_x(const GemvArgs& a, const float* x, const GemvSmem& sm, bool coherent, bool want_sum,
                                               int tid, int warp, int lane) {
     const QLayout& L = a.L;
     const int K = L.K, kpad = layout_kpad(L);
-    float ss = 0.f;
-    for (int k = tid; k < kpad; k += kConsumerThreads) {
-        const float v = k < K ? ld_act(x + k, coherent) : 0.f;
-        sm.xs[k] = v;
-        ss = fmaf(v, v, ss);
-    }
-    float rms = 1.f;
-    if (a.norm_w != nullptr) {
-        const float tot = consumer_block_sum(ss, sm.red, warp, lane);
-        rms = sqrtf(tot / (float)K + a.rms_eps);  // :1501
-    }
-    float sx = 0.f;
-    for (int k = tid; k < kpad; k += kConsumerThreads) {
-        float v = sm.xs[k];
-        if (a.norm_w != nullptr && k < K) v = (v / rms) * a.norm_w[k];  // :1504-1506, same two roundings
-        sx += v;
-        if (BITS == 4) {
-            const int p = q4_pos((k & 1023) >> 7, k & 3);
-            v *= __uint_as_float((uint32_t)(127 - 4 * p) << 23);  // 16^-p, exact
+    const float* nw = a.norm_w;
+    const bool vec = (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(nw)) & 15) == 0;
+    float ss = 0.f, sx = 0.f, rms = 1.f;
+    if (vec) {
+        constexpr int B = 4;  // float4 loads in flight per thread
+        const int nvec = kpad >> 2, kvec = K >> 2;
+        for (int v0 = tid; v0 < nvec; v0 += B * kConsumerThreads) {
+            float4 xv[B];
+#pragma unroll
+            for (int i = 0; i < B; ++i) {
+                const int v = v0 + i * kConsumerThreads;
+                xv[i] = v < kvec ? ld_act4(x + 4 * v, coherent) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < B; ++i) {
+                const int v = v0 + i * kConsumerThreads;
+                if (v < nvec) {
+                    ss = fmaf(xv[i].x, xv[i].x, ss); ss = fmaf(xv[i].y, xv[i].y, ss);
+                    ss = fmaf(xv[i].z, xv[i].z, ss); ss = fmaf(xv[i].w, xv[i].w, ss);
+                    if (nw == nullptr) {  // no second pass needed: finish now
+                        sx += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+                        xv[i] = q4_prescale4<BITS>(xv[i], 4 * v);
+                    }
+                    *reinterpret_cast<float4*>(sm.xs + 4 * v) = xv[i];
+                }
+            }
         }
-        sm.xs[k] = v;
+        if (nw != nullptr) {
+            // the norm weights do not depend on the reduction: get the first batch moving before the barriers
+            float4 wv[B];
+#pragma unroll
+            for (int i = 0; i < B; ++i) {
+                const int v = tid + i * kConsumerThreads;
+                wv[i] = v < kvec ? *reinterpret_cast<const float4*>(nw + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const float tot = consumer_block_sum(ss, sm.red, warp, lane);
+            rms = sqrtf(tot / (float)K + a.rms_eps);  // :1501
+            for (int v0 = tid; v0 < kvec; v0 += B * kConsumerThreads) {
+                if (v0 != tid) {
+#pragma unroll
+                    for (int i = 0; i < B; ++i) {
+                        const int v = v0 + i * kConsumerThreads;
+                        wv[i] = v < kvec ? *reinterpret_cast<const float4*>(nw + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < B; ++i) {
+                    const int v = v0 + i * kConsumerThreads;
+                    if (v < kvec) {
+                        float4 t = *reinterpret_cast<const float4*>(sm.xs + 4 * v);
+                        t.x = (t.x / rms) * wv[i].x;  // :1504-1506, same two roundings
+                        t.y = (t.y / rms) * wv[i].y;
+                        t.z = (t.z / rms) * wv[i].z;
+                        t.w = (t.w / rms) * wv[i].w;
+                        sx += (t.x + t.y) + (t.z + t.w);
+                        *reinterpret_cast<float4*>(sm.xs + 4 * v) = q4_prescale4<BITS>(t, 4 * v);
+                    }
+                }
+            }
+        }
+    } else {
+        for (int k = tid; k < kpad; k += kConsumerThreads) {
+            const float v = k < K ? ld_act(x + k, coherent) : 0.f;
+            sm.xs[k] = v;
+            ss = fmaf(v, v, ss);
+        }
+        if (nw != nullptr) {
+            const float tot = consumer_block_sum(ss, sm.red, warp, lane);
+            rms = sqrtf(tot / (float)K + a.rms_eps);
+        }
+        for (int k = tid; k < kpad; k += kConsumerThreads) {
+            float v = sm.xs[k];
+            if (nw != nullptr && k < K) v = (v / rms) * nw[k];
+            sx += v;
+            if (BITS == 4) {
+                const int p = q4_pos((k & 1023) >> 7, k & 3);
+                v *= __uint_as_float((uint32_t)(127 - 4 * p) << 23);  // 16^-p, exact
+            }
+            sm.xs[k] = v;
+        }
     }
     float sumx = 0.f;
     if (want_sum) sumx = consumer_block_sum(sx, sm.red, warp, lane);
@@ -256,71 +343,143 @@ __device__ __forceinline__ float gemv_stage_x(const GemvArgs& a, const float* x,
     return sumx;
 }
 
-// consumers, main loop: per ring stage LDS.128 weights, unpack, FFMA2, reduce, partials to shared memory
-template <int BITS>
+// consumers, main loop: per ring stage LDS.128 weights, unpack, FFMA2, reduce, partials to shared memory.
+// A round hands each warp up to 4 items.  The common case -- 4 items of the same k-superchunk -- is straight-line
+// code, so the four unpack / FMA chains interleave (ILP 4); rounds that end the warp's range or straddle a
+// superchunk boundary take the per-item path.  The warp reduction of round r is issued after round r+1's
+// shared-memory loads, hiding the shuffle latency behind them.
+template <int BITS, int DBG = 0>
 __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, uint32_t& it, int warp, int lane) {
     const QLayout& L = a.L;
     const int S = a.stages;
+    const int ksc = L.ksc, ncols = slab.ncols, nrounds = slab.rounds;
     constexpr int NX = BITS == 4 ? 16 : 8;  // float2 pairs of x per lane per superchunk
+    const Q4Consts kc = q4_consts();
     f32x2 xr[NX];
     int cur_s = -1;
     const int my_n = warp_items(slab, warp);
     const int first = warp_first_item(slab, warp);
-    int it_s = first / slab.ncols;  // superchunk of the next item
-    int it_c = first - it_s * slab.ncols;
+    int it_s = first / ncols;  // superchunk / column of the next item
+    int it_c = first - it_s * ncols;
     int item = first;
-    for (int r = 0; r < slab.rounds; ++r, ++it) {
+    const int w_lo = warp < slab.m ? warp : slab.m, w_hi = warp - w_lo;  // warps before this one with b+1 / b items
+    const float* xlane = sm.xs + 4 * lane;
+    auto load_x = [&](int s) {
+        cur_s = s;
+        const float* xp = xlane + (size_t)s * ksc;
+#pragma unroll
+        for (int j = 0; j < NX / 2; ++j) {
+            const uint4 q = lds128(xp + 128 * j);
+            xr[2 * j] = pack2u(q.x, q.y);
+            xr[2 * j + 1] = pack2u(q.z, q.w);
+        }
+    };
+    auto dot = [&](const uint4& wv) -> float {
+        if constexpr (DBG == 1) return __uint_as_float(wv.x ^ wv.y ^ wv.z ^ wv.w);
+        else if constexpr (BITS == 4) return dot_q4(wv, xr, kc);
+        else return dot_q8(wv, xr, kc);
+    };
+    float pv0 = 0.f, pv1 = 0.f, pv2 = 0.f, pv3 = 0.f;  // previous round's per-lane sums, reduced one round late
+    int p_item = 0, p_n = 0;
+    auto flush_prev = [&]() {
+        if (p_n > 0) {
+            const float tot = reduce4(pv0, pv1, pv2, pv3, lane);
+            const int gi = lane >> 3;
+            if ((lane & 7) == 0 && gi < p_n) sm.part[p_item + gi] = tot;  // part[s*ncols + c]
+        }
+    };
+    for (int r = 0; r < nrounds; ++r, ++it) {
         const uint32_t st = it % S;
         const int g_n = round_items(my_n, r);
+        const int woff = w_lo * round_items(slab.b + 1, r) + w_hi * round_items(slab.b, r);
         mbar_wait(&sm.full[st], (it / S) & 1);
-        const uint8_t* wbase = sm.ring + (size_t)st * kStageBytes + (size_t)round_warp_offset(slab, r, warp) * kItemBytes + lane * 16;
-        float v[kItemsPerRound] = {0.f, 0.f, 0.f, 0.f};
+        const uint8_t* wbase = sm.ring + (size_t)st * kStageBytes + (size_t)woff * kItemBytes + lane * 16;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+        if (DBG == 2) {
+            flush_prev();
+        } else if (g_n == kItemsPerRound && it_c + kItemsPerRound <= ncols) {
+            const uint4 w0 = lds128(wbase), w1 = lds128(wbase + kItemBytes), w2 = lds128(wbase + 2 * kItemBytes),
+                        w3 = lds128(wbase + 3 * kItemBytes);
+            if (it_s != cur_s) load_x(it_s);
+            flush_prev();
+            v0 = dot(w0); v1 = dot(w1); v2 = dot(w2); v3 = dot(w3);
+            it_c += kItemsPerRound;
+            if (it_c == ncols) { it_c = 0; ++it_s; }
+        } else {
+            flush_prev();
+            float v[kItemsPerRound] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int g = 0; g < kItemsPerRound; ++g) {
-            if (g < g_n) {
-                if (it_s != cur_s) {
-                    cur_s = it_s;
-                    const float* xp = sm.xs + (size_t)cur_s * L.ksc + 4 * lane;
-#pragma unroll
-                    for (int j = 0; j < NX / 2; ++j) {
-                        const uint4 q = lds128(xp + 128 * j);
-                        xr[2 * j] = pack2u(q.x, q.y);
-                        xr[2 * j + 1] = pack2u(q.z, q.w);
-                    }
+            for (int g = 0; g < kItemsPerRound; ++g) {
+                if (g < g_n) {
+                    if (it_s != cur_s) load_x(it_s);
+                    v[g] = dot(lds128(wbase + g * kItemBytes));
+                    if (++it_c == ncols) { it_c = 0; ++it_s; }
                 }
-                const uint4 wv = lds128(wbase + g * kItemBytes);
-                if constexpr (BITS == 4) v[g] = dot_q4(wv, xr);
-                else v[g] = dot_q8(wv, xr);
-                if (++it_c == slab.ncols) { it_c = 0; ++it_s; }
             }
+            v0 = v[0]; v1 = v[1]; v2 = v[2]; v3 = v[3];
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[st]);  // this warp is done reading the stage
-        const float tot = reduce4(v[0], v[1], v[2], v[3], lane);
-        const int gi = lane >> 3;
-        if ((lane & 7) == 0 && gi < g_n) sm.part[item + gi] = tot;  // part[s*ncols + c]
+        pv0 = v0; pv1 = v1; pv2 = v2; pv3 = v3;
+        p_item = item; p_n = g_n;
         item += g_n;
     }
+    flush_prev();
     bar_sync(1, kConsumerThreads);
+}
+
+// Values the epilogue needs that do not depend on this phase's arithmetic; loaded early (before the grid barrier
+// in the persistent kernel) so their latency is off the critical path.  They cover the thread's first column
+// (or column pair); further columns, if a slab has more than 512, load theirs in place.
+struct EpiPre {
+    float cs0, cs1;   // colscale
+    float zt0, zt1;   // colzterm (0 when absent)
+    float r0;         // residual input (EPI_RESIDUAL)
+    float invf;       // inv_freq entry (EPI_QKV with RoPE)
+    int page;         // physical KV page of the current position (EPI_QKV)
+};
+
+__device__ __forceinline__ EpiPre gemv_epilogue_prefetch(const GemvArgs& a, const Slab& slab, const float* resid, const PhaseCtx& ctx, int tid) {
+    EpiPre p{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0};
+    const bool pairs = a.epi == EPI_SWIGLU || a.epi == EPI_QKV;
+    const int c = pairs ? 2 * tid : tid;
+    const int n = slab.col0 + c;
+    if (c < slab.ncols && n < a.L.N) {
+        p.cs0 = a.colscale[n];
+        if (a.colzterm) p.zt0 = a.colzterm[n];
+        if (pairs) {
+            p.cs1 = a.colscale[n + 1];
+            if (a.colzterm) p.zt1 = a.colzterm[n + 1];
+        }
+        if (a.epi == EPI_RESIDUAL) p.r0 = ld_act(resid + n, ctx.coherent);
+        if (a.epi == EPI_QKV) {
+            const int pos = ctx.pos >= 0 ? ctx.pos : *a.pos_ptr;
+            p.page = a.page_table[pos / a.page_tokens];
+            if (a.rope_dim > 0) p.invf = a.inv_freq[((n % a.hidden) % a.rope_dim) >> 1];
+        }
+    }
+    return p;
 }
 
 // consumers, epilogue: fixed-order sum of the superchunk partials, scale, fused tail op
 __device__ __forceinline__ void gemv_epilogue(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, float sumx, const float* resid,
-                                              const PhaseCtx& ctx, int tid, int lane) {
+                                              const PhaseCtx& ctx, const EpiPre& pre, int tid, int lane) {
     const QLayout& L = a.L;
     const int ncols = slab.ncols, nsc = L.nsc;
-    auto column = [&](int c) -> float {
+    auto colsum = [&](int c) -> float {
         float acc = 0.f;
         for (int s = 0; s < nsc; ++s) acc += sm.part[s * ncols + c];
-        const int n = slab.col0 + c;
-        if (a.colzterm != nullptr) acc = fmaf(a.colzterm[n], sumx, acc);
-        return a.colscale[n] * acc;
+        return acc;
     };
     if (a.epi == EPI_SWIGLU || a.epi == EPI_QKV) {
         for (int pc = tid; pc < ncols / 2; pc += kConsumerThreads) {  // column pairs
             const int n0 = slab.col0 + 2 * pc;
             if (n0 >= L.N) continue;
-            const float y0 = column(2 * pc), y1 = column(2 * pc + 1);
+            const bool first = pc == tid;
+            const float cs0 = first ? pre.cs0 : a.colscale[n0], cs1 = first ? pre.cs1 : a.colscale[n0 + 1];
+            const float zt0 = first ? pre.zt0 : (a.colzterm ? a.colzterm[n0] : 0.f);
+            const float zt1 = first ? pre.zt1 : (a.colzterm ? a.colzterm[n0 + 1] : 0.f);
+            const float y0 = cs0 * fmaf(zt0, sumx, colsum(2 * pc)), y1 = cs1 * fmaf(zt1, sumx, colsum(2 * pc + 1));
             if (a.epi == EPI_SWIGLU) {
                 const float sg = y0 / (1.0f + expf(-y0));  // silu(gate), :918
                 a.out[n0 >> 1] = y1 * sg;                   // multiply(up, silu(gate))
@@ -330,19 +489,19 @@ __device__ __forceinline__ void gemv_epilogue(const GemvArgs& a, const Slab& sla
                 const int pos = ctx.pos >= 0 ? ctx.pos : *a.pos_ptr;
                 float o0 = y0, o1 = y1;
                 if (seg < 2 && a.rope_dim > 0) {
-                    const int i = (d % a.rope_dim) >> 1;
+                    const float invf = first ? pre.invf : a.inv_freq[(d % a.rope_dim) >> 1];
                     float sn, cs;
-                    sincosf((float)pos * a.inv_freq[i], &sn, &cs);
+                    sincosf((float)pos * invf, &sn, &cs);
                     o0 = __fsub_rn(__fmul_rn(y0, cs), __fmul_rn(y1, sn));  // :1584-1585, un-fused like the build
                     o1 = __fadd_rn(__fmul_rn(y0, sn), __fmul_rn(y1, cs));
                 }
                 if (seg == 0) {
-                    a.out[d] = o0; a.out[d + 1] = o1;
+                    *reinterpret_cast<float2*>(a.out + d) = make_float2(o0, o1);
                 } else {
-                    const int page = a.page_table[pos / a.page_tokens];
+                    const int page = first ? pre.page : a.page_table[pos / a.page_tokens];
                     const size_t off = ((size_t)page * a.page_tokens + (pos % a.page_tokens)) * H + d;
                     float* dst = seg == 1 ? a.k_pool : a.v_pool;
-                    dst[off] = o0; dst[off + 1] = o1;
+                    *reinterpret_cast<float2*>(dst + off) = make_float2(o0, o1);
                 }
             }
         }
@@ -352,8 +511,11 @@ __device__ __forceinline__ void gemv_epilogue(const GemvArgs& a, const Slab& sla
         for (int c = tid; c < ncols; c += kConsumerThreads) {
             const int n = slab.col0 + c;
             if (n >= L.N) continue;
-            float y = column(c);
-            if (a.epi == EPI_RESIDUAL) y = ld_act(resid + n, ctx.coherent) + y;
+            const bool first = c == tid;
+            const float cs = first ? pre.cs0 : a.colscale[n];
+            const float zt = first ? pre.zt0 : (a.colzterm ? a.colzterm[n] : 0.f);
+            float y = cs * fmaf(zt, sumx, colsum(c));
+            if (a.epi == EPI_RESIDUAL) y = (first ? pre.r0 : ld_act(resid + n, ctx.coherent)) + y;
             else if (a.epi == EPI_RELU) y = fmaxf(y, 0.f);
             a.out[n] = y;
             if (a.epi == EPI_LOGITS && (y > best)) { best = y; besti = n; }
@@ -379,7 +541,7 @@ __device__ __forceinline__ void gemv_init_barriers(const GemvSmem& sm, int stage
 }
 
 // ---- the stand-alone kernel: one GEMV per launch -----------------------------------------------------------
-template <int BITS>
+template <int BITS, int DBG = 0>
 __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const __grid_constant__ GemvArgs a) {
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -396,8 +558,9 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const __grid_cons
     pdl_wait_prior_grid();  // x (and resid / pos) come from the previous kernel in the stream
     const PhaseCtx ctx{false, -1, nullptr};
     const float sumx = gemv_stage_x<BITS>(a, a.x, sm, false, a.colzterm != nullptr, tid, warp, lane);
-    gemv_consume<BITS>(a, slab, sm, it, warp, lane);
-    gemv_epilogue(a, slab, sm, sumx, a.resid, ctx, tid, lane);
+    const EpiPre pre = gemv_epilogue_prefetch(a, slab, a.resid, ctx, tid);
+    gemv_consume<BITS, DBG>(a, slab, sm, it, warp, lane);
+    gemv_epilogue(a, slab, sm, sumx, a.resid, ctx, pre, tid, lane);
 }
 
 }  // namespace tib

@@ -47,11 +47,12 @@ struct MegaArgs {
     float* logits;
     int stages;
     int max_kpad, max_items, attn_floats;
+    long long* dbg;   // optional: CTA 0 writes 6 clock64 stamps per phase of step 0 (debug timeline)
 };
 
 TIB_HD size_t mega_smem_bytes(int stages, int max_kpad, int max_items, int attn_floats) {
     return (size_t)stages * kStageBytes + (size_t)max_kpad * 4 + (size_t)max_items * 4 + 32 * 4 + (size_t)attn_floats * 4 +
-           (size_t)2 * kMaxStages * 8 + 16 + 128;
+           (size_t)2 * kMaxStages * 8 + 16 + 128 + ((sizeof(MegaPhase) + 15) & ~size_t(15));
 }
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -97,7 +98,7 @@ TIB_HD int attn_scratch_floats(int D, int nt) {
 
 // Computes the (m, l, o) partial of head h over tokens [t0, t1) and stores it.  q / K / V are read through L2.
 template <int NT>
-__device__ __forceinline__ void attn_item(const AttnArgs& a, int h, int j, int t0, int t1, float* sm) {
+__device__ __forceinline__ void attn_item(const AttnArgs& a, int h, int j, int t0, int t1, float* sm, bool direct = false) {
     float* qs = sm;
     float* sc = qs + a.D;
     float* red = sc + kAttnTokBlock;
@@ -160,7 +161,13 @@ __device__ __forceinline__ void attn_item(const AttnArgs& a, int h, int j, int t
         }
         bar_sync(1, NT);
     }
-    float* po = a.part_o + ((size_t)h * a.max_splits + j) * D;
+    // direct: this item covers the whole context of the head -> normalise and write the output, no partials
+    float* po = direct ? a.out + hoff : a.part_o + ((size_t)h * a.max_splits + j) * D;
+    const float onorm = direct ? 1.0f / l_run : 1.0f;
+    if (direct) {
+#pragma unroll
+        for (int i = 0; i < kMaxDims; ++i) o[i] *= onorm;
+    }
     if (groups > 1) {
         if (active) ored[grp * D + d0] = o[0];
         bar_sync(1, NT);
@@ -176,7 +183,7 @@ __device__ __forceinline__ void attn_item(const AttnArgs& a, int h, int j, int t
             if (d < D) po[d] = o[i];
         }
     }
-    if (tid == 0) {
+    if (tid == 0 && !direct) {
         a.part_ml[((size_t)h * a.max_splits + j) * 2 + 0] = m_run;
         a.part_ml[((size_t)h * a.max_splits + j) * 2 + 1] = l_run;
     }
@@ -206,12 +213,13 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnAr
     attn_split_range(t, a.max_splits, a.min_chunk, nsplit, chunk);
     const int j = blockIdx.y;
     if (j >= nsplit) return;
-    attn_item<kAttnThreads>(a, blockIdx.x, j, j * chunk, min(t, (j + 1) * chunk), attn_dyn_smem);
+    attn_item<kAttnThreads>(a, blockIdx.x, j, j * chunk, min(t, (j + 1) * chunk), attn_dyn_smem, nsplit == 1);
 }
 __global__ void __launch_bounds__(kAttnThreads) attn_combine_kernel(const AttnArgs a) {
     const int t = *a.pos_ptr + a.t_bias;
     int nsplit, chunk;
     attn_split_range(t, a.max_splits, a.min_chunk, nsplit, chunk);
+    if (nsplit == 1) return;  // attn_partial_kernel wrote the output directly
     attn_merge_head<kAttnThreads>(a, blockIdx.x, nsplit);
 }
 
@@ -226,6 +234,11 @@ __device__ __forceinline__ void mega_attention(const AttnArgs& a, int t, unsigne
     for (int i = blockIdx.x; i < items; i += gridDim.x) {
         const int h = i / nsplit, j = i - h * nsplit;
         const int t0 = j * chunk, t1 = min(t, t0 + chunk);
+        if (nsplit == 1) {  // short context: one CTA per head does everything, no partials / counters / merge
+            attn_item<NT>(a, h, 0, 0, t, sm, true);
+            bar_sync(1, NT);
+            continue;
+        }
         attn_item<NT>(a, h, j, t0, t1, sm);
         __threadfence();
         bar_sync(1, NT);
@@ -241,8 +254,14 @@ __device__ __forceinline__ void mega_attention(const AttnArgs& a, int t, unsigne
     }
 }
 
+// Registers: more than 16 warps put 5 on an SM sub-partition, which caps a uniform allocation at 96 per thread.  The
+// kernel is compiled for 96 (__maxnreg__); the producer warpgroup then shrinks to 24 and the four consumer warpgroups
+// grow to 112 (the pool is the CTA's launch allocation: 640 x 96 >= 512 x 112 + 128 x 24).  setmaxnreg is a
+// warpgroup-wide instruction, so the producer warp comes with three idle siblings (warps 17..19) that only execute
+// the shrink and exit: the CTA has 20 warps.
+constexpr int kMegaThreads = (kConsumerWarps + 4) * 32;  // 640
 template <int BITS>
-__global__ void __launch_bounds__(kGemvThreads, 1) mega_decode_kernel(const __grid_constant__ MegaArgs m) {
+__global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaArgs m) {
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // carve: ring | xs | part | red | attention scratch | mbarriers
@@ -261,15 +280,18 @@ __global__ void __launch_bounds__(kGemvThreads, 1) mega_decode_kernel(const __gr
     p = (p + 15) & ~uintptr_t(15);
     sm.full = reinterpret_cast<uint64_t*>(p);
     sm.empty = sm.full + kMaxStages;
+    p += (size_t)2 * kMaxStages * 8;
+    MegaPhase* sph = reinterpret_cast<MegaPhase*>(p);  // this phase's descriptor, staged by the consumers
     if (tid == 0) gemv_init_barriers(sm, m.stages);
     __syncthreads();
 
     const int pos0 = m.st->pos;
     uint32_t it = 0;
 
-    if (warp == kConsumerWarps) {
-        // ===== producer: every GEMV phase of every step, back to back =====
-        if (lane == 0) {
+    if (warp >= kConsumerWarps) {
+        // ===== producer warpgroup: warp 16 streams every GEMV phase of every step, back to back =====
+        reg_dealloc<24>();
+        if (warp == kConsumerWarps && lane == 0) {
             for (int s = 0; s < m.n_steps; ++s) {
                 const bool sample = s >= m.first_sample;
                 for (int ph = 0; ph < m.nphases; ++ph) {
@@ -285,6 +307,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) mega_decode_kernel(const __gr
     }
 
     // ===== consumers =====
+    reg_alloc<112>();
     unsigned int bar_target = 0;
     bool need_wait = false;
     auto grid_arrive = [&]() {
@@ -331,24 +354,48 @@ __global__ void __launch_bounds__(kGemvThreads, 1) mega_decode_kernel(const __gr
         }
         if (s < m.n_prompt) token = m.prompt[s];
         for (int ph = 0; ph < m.nphases; ++ph) {
-            const MegaPhase& P = m.phases[ph];
-            if (P.is_head && !sample) continue;
-            grid_wait();
+            const bool is_head = ph == m.nphases - 1;  // the lm_head is always the last phase
+            if (is_head && !sample) continue;
+            const bool stamp = m.dbg != nullptr && s == 0 && blockIdx.x == 0 && tid == 0;
+            long long* ts = m.dbg + (size_t)ph * 6;
+            if (stamp) ts[0] = clock64();
+            // Everything that does not depend on the previous phase's output happens BEFORE the grid barrier:
+            // stage the phase descriptor in shared memory, fetch the epilogue's per-column constants.
+            const MegaPhase& PG = m.phases[ph];
+            {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(&PG);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(sph);
+                for (int i = tid; i < (int)(sizeof(MegaPhase) / 4); i += kConsumerThreads) dst[i] = src[i];
+            }
+            const bool gemv_here = PG.type == PH_GEMV && (int)blockIdx.x < PG.g.L.P;
+            const PhaseCtx ctx{true, pos, is_head ? &m.keys[s & 1] : nullptr};
+            Slab slab{};
+            EpiPre pre{};
+            const float* resid = nullptr;
+            if (gemv_here) {
+                slab = make_slab(PG.g.L, blockIdx.x);
+                resid = PG.resid_src == SRC_EMB ? m.emb + (size_t)token * m.H : PG.g.resid;
+                pre = gemv_epilogue_prefetch(PG.g, slab, resid, ctx, tid);
+            }
+            if (need_wait) grid_wait(); else bar_sync(1, kConsumerThreads);
+            const MegaPhase& P = *sph;
+            if (stamp) { ts[1] = clock64(); ts[2] = ts[1]; ts[3] = ts[1]; }
             if (P.type == PH_GEMV) {
-                if ((int)blockIdx.x < P.g.L.P) {
-                    const Slab slab = make_slab(P.g.L, blockIdx.x);
+                if (gemv_here) {
                     const float* x = P.x_src == SRC_EMB ? m.emb + (size_t)token * m.H : P.g.x;
-                    const float* resid = P.resid_src == SRC_EMB ? m.emb + (size_t)token * m.H : P.g.resid;
                     const GemvArgs& g = P.g;
-                    const PhaseCtx ctx{true, pos, P.is_head ? &m.keys[s & 1] : nullptr};
                     const float sumx = gemv_stage_x<BITS>(g, x, sm, P.x_src != SRC_EMB, g.colzterm != nullptr, tid, warp, lane);
+                    if (stamp) ts[2] = clock64();
                     gemv_consume<BITS>(g, slab, sm, it, warp, lane);
-                    gemv_epilogue(g, slab, sm, sumx, resid, ctx, tid, lane);
+                    if (stamp) ts[3] = clock64();
+                    gemv_epilogue(g, slab, sm, sumx, resid, ctx, pre, tid, lane);
                 }
             } else {
                 mega_attention(P.at, pos + 1, m.head_cnt, attn_sm);
             }
+            if (stamp) ts[4] = clock64();
             grid_arrive();
+            if (stamp) ts[5] = clock64();
         }
     }
     // tail: the last step's token, and the state the host reads back
