@@ -1,0 +1,103 @@
+// microbench3.cu -- where the streaming GEMV's time goes on a B200: the bulk-copy ring alone (no math), the integer
+// main loop on top of it, and the main loop alone out of a pre-filled ring, on matrices far larger than L2.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o scripts/microbench3 scripts/microbench3.cu
+#include <cstdio>
+#include <vector>
+#include "../turboinfer_b200/csrc/gemv.cuh"
+using namespace tib;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+// consumers only: the ring is filled once with garbage, full barriers are never waited on
+template <int BITS>
+__global__ void __launch_bounds__(kGemvThreads, 1) k_consume_only(const __grid_constant__ GemvArgs a, long long* cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const Slab slab = make_slab(a.L, blockIdx.x);
+    const GemvSmem sm = gemv_carve(smem_raw, a.L, a.stages);
+    if (warp == kConsumerWarps) return;
+    for (int i = tid; i < a.stages * kStageBytes / 4; i += kConsumerThreads) reinterpret_cast<uint32_t*>(sm.ring)[i] = i * 2654435761u;
+    const float s_x = gemv_stage_x<BITS>(a, a.x, sm, slab, false, tid, warp, lane);
+    const long long t0 = clock64();
+    uint32_t it = 0;
+    gemv_consume<BITS, 2>(a, slab, sm, it, warp, lane);   // DBG 2: no mbarrier traffic, ring pre-filled
+    const long long t1 = clock64();
+    if (lane == 0) atomicMax((unsigned long long*)cycles, (unsigned long long)(t1 - t0));
+    if (sm.acc[tid % 12] == 12345 && s_x == 1.f) a.out[0] = 1.f;
+}
+
+template <int BITS, int DBG>
+static int run_real(const char* label, int K, int N, int sms, int reps, int force_stages = 0) {
+    QLayout L = make_layout(K, N, BITS, sms);
+    int stages = 0; size_t smem = 0;
+    for (int s = kMaxStages; s >= 2; --s) if (gemv_smem_bytes(L, s) <= 227 * 1024) { stages = s; smem = gemv_smem_bytes(L, s); break; }
+    if (force_stages) { stages = force_stages; smem = gemv_smem_bytes(L, stages); }
+    const size_t bytes = layout_bytes(L);
+    const int copies = bytes > (300u << 20) ? 2 : 4;   // cycle through several matrices so the working set exceeds L2
+    uint8_t* w; float *cs, *x, *y;
+    CK(cudaMalloc(&w, bytes * copies)); CK(cudaMemset(w, 0x5A, bytes * copies));
+    CK(cudaMalloc(&cs, 4 * (size_t)4 * L.U)); CK(cudaMalloc(&x, 4 * (size_t)K)); CK(cudaMalloc(&y, 4 * (size_t)4 * L.U));
+    CK(cudaMemset(cs, 0, 4 * (size_t)4 * L.U)); CK(cudaMemset(x, 0, 4 * (size_t)K));
+    CK(cudaFuncSetAttribute(gemv_kernel<BITS, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GemvArgs a{};
+    a.colscale = cs; a.L = L; a.stages = stages; a.x = x; a.epi = EPI_STORE; a.out = y; a.woff = 8;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int r = 0; r < 3; ++r) { a.wq = w + (size_t)(r % copies) * bytes; gemv_kernel<BITS, DBG><<<L.P, kGemvThreads, smem>>>(a); }
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    cudaEventRecord(e0);
+    for (int r = 0; r < reps; ++r) { a.wq = w + (size_t)(r % copies) * bytes; gemv_kernel<BITS, DBG><<<L.P, kGemvThreads, smem>>>(a); }
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("gemv_kernel<%d> %-18s K=%5d N=%6d stages %d: %8.2f us/launch, %6.0f GB/s\n", BITS, label, K, N, stages, ms * 1e3 / reps, bytes / (ms * 1e-3 / reps) / 1e9);
+    cudaFree(w); cudaFree(cs); cudaFree(x); cudaFree(y);
+    return 0;
+}
+
+template <int BITS>
+static int run_consume(int K, int N, int sms) {
+    QLayout L = make_layout(K, N, BITS, sms);
+    int stages = 4; size_t smem = gemv_smem_bytes(L, stages);
+    float *cs, *x, *y; long long* cyc; long long h;
+    CK(cudaMalloc(&cs, 4 * (size_t)4 * L.U)); CK(cudaMalloc(&x, 4 * (size_t)K)); CK(cudaMalloc(&y, 4 * (size_t)4 * L.U)); CK(cudaMalloc(&cyc, 8));
+    CK(cudaMemset(x, 0, 4 * (size_t)K)); CK(cudaMemset(cyc, 0, 8));
+    CK(cudaFuncSetAttribute(k_consume_only<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GemvArgs a{};
+    a.colscale = cs; a.L = L; a.stages = stages; a.x = x; a.epi = EPI_STORE; a.out = y; a.woff = 8;
+    k_consume_only<BITS><<<L.P, kGemvThreads, smem>>>(a, cyc);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemset(cyc, 0, 8));
+    k_consume_only<BITS><<<L.P, kGemvThreads, smem>>>(a, cyc);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost));
+    const Slab s0 = make_slab(L, 0);
+    const int T = s0.nunits * L.nchunks;
+    printf("consume only <%d> K=%5d N=%6d: %lld cycles for %d items per CTA -> %.2f cycles/item/SM -> %.0f GB/s at 1.9 GHz\n", BITS, K, N, h, T,
+           (double)h / T, 512.0 / ((double)h / T) * 1.9 * sms);
+    cudaFree(cs); cudaFree(x); cudaFree(y); cudaFree(cyc);
+    return 0;
+}
+
+int main() {
+    CK(cudaSetDevice(0));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    const int sms = prop.multiProcessorCount;
+    printf("%s, %d SMs\n", prop.name, sms);
+    run_consume<4>(4096, 148 * 4 * 40, sms);
+    run_consume<4>(11008, 148 * 4 * 12, sms);
+    run_consume<8>(4096, 148 * 4 * 20, sms);
+    // 8192 x 65536 INT4 = 268 MB per matrix
+    run_real<4, 1>("stream only", 8192, 65536, sms, 20);
+    run_real<4, 1>("stream only", 8192, 65536, sms, 20, 4);
+    run_real<4, 1>("stream only", 8192, 65536, sms, 20, 3);
+    run_real<4, 1>("stream only", 8192, 65536, sms, 20, 2);
+    run_real<4, 0>("full", 8192, 65536, sms, 20);
+    run_real<8, 1>("stream only", 8192, 32768, sms, 20);
+    run_real<8, 0>("full", 8192, 32768, sms, 20);
+    run_real<4, 0>("full", 4096, 22016, sms, 50);
+    run_real<4, 1>("stream only", 4096, 22016, sms, 50);
+    return 0;
+}

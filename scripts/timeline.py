@@ -22,6 +22,11 @@ print(f"{shape} L={layers} t={ctx}: phase  wait  stage_x  consume  epilogue  arr
 f = 1 / 1965.0
 for i, r in enumerate(ts):
     nm = names[i % 5] if i < len(ts) - 1 else "lm_head"
-    d = np.diff(r) * f
-    print(f"{i:3d} {nm:7s} " + " ".join(f"{x:8.2f}" for x in d) + f"  {(r[5]-r[0])*f:8.2f}")
+    d = np.diff(r[:6]) * f
+    sub = ""
+    if r[6] > 0:
+        pts = [r[1], r[6], r[7], r[8], r[9], r[10]]
+        sub = "   | prologue: " + " ".join(f"{(b - a) * f:5.2f}" for a, b in zip(pts[:-1], pts[1:])) + f" | ready stages {r[11]}"
+    print(f"{i:3d} {nm:7s} " + " ".join(f"{x:8.2f}" for x in d) + f"  {(r[5]-r[0])*f:8.2f}" + sub)
+print("prologue columns: stats gathered | rms+scale | x,w loads issued..arrived | (gap) | digits stored | final barrier")
 print("step total us:", (ts[-1, 5] - ts[0, 0]) * f)

@@ -331,11 +331,12 @@ class Model:
         return self
 
     def debug_timeline(self, token: int = 1) -> np.ndarray:
-        """[phases, 6] SM-clock stamps of CTA 0 for one decode step on the persistent-kernel engine."""
-        buf = np.zeros(6 * 4096, dtype=np.int64)
+        """[phases, 12] SM-clock stamps of CTA 0 for one decode step on the persistent-kernel engine: 6 phase-level
+        stamps (start, barrier passed, x staged, weights consumed, epilogue done, arrived) + 6 inside the prologue."""
+        buf = np.zeros(12 * 4096, dtype=np.int64)
         n = C.c_size_t()
         _ck(lib().ti_b200_debug_timeline(self.handle, token, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size, C.byref(n)))
-        return buf[: 6 * n.value].reshape(n.value, 6).copy()
+        return buf[: 12 * n.value].reshape(n.value, 12).copy()
 
     def bench_gemv(self, slot: int, reps: int):
         """(avg ms per launch, algorithmic bytes per launch) of the model's own GEMVs of one kind, back to back."""

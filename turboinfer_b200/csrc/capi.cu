@@ -111,7 +111,7 @@ int pick_stages(const QLayout& L, int* stages, size_t* smem) {
             return 0;
         }
     }
-    return fail("GEMV K=%d does not fit shared memory (x needs %d KiB)", L.K, layout_kpad(L) * 4 / 1024);
+    return fail("GEMV K=%d does not fit shared memory (x digits need %d KiB)", L.K, layout_kpad(L) * 3 / 1024);
 }
 
 int set_kernel_attrs() {
@@ -131,6 +131,7 @@ void fill_weight(const QWeight& w, GemvArgs& a) {
     a.colzterm = w.has_zterm ? w.colzterm.p : nullptr;
     a.L = w.L;
     a.stages = w.stages;
+    a.woff = w.L.bits == 4 ? w.offset4 : 0;
 }
 
 int launch_gemv(const QWeight& w, GemvArgs a, cudaStream_t st) {
@@ -189,6 +190,7 @@ int build_qweight(const float* const* src, const int* src_n, int nsrc, int mode,
     pa.nsrc = nsrc;
     pa.mode = mode;
     pa.qtype = qtype;
+    pa.off4 = symmetric ? 8 : 0;
     pa.unit_scale = unit_scale ? 1 : 0;
     pa.L = w->L;
     pa.out = w->packed.p;
@@ -210,7 +212,7 @@ int build_qweight(const float* const* src, const int* src_n, int nsrc, int mode,
     w->zp = h[1];
     w->has_zterm = false;
     for (int i = 0; i < nsrc; ++i) w->has_zterm |= (h[2 * i + 1] != 0.0f);
-    w->offset4 = (h[1] == 0.0f) ? 8 : 0;
+    w->offset4 = symmetric ? 8 : 0;
     *out = std::move(w);
     return 0;
 }
@@ -247,12 +249,15 @@ struct Model {
     // persistent-kernel engine
     bool use_mega = false;
     DevBuf<MegaPhase> phases;
+    DevBuf<ProdRec> prod;
     int nphases = 0;
     DevBuf<unsigned int> sync_buf;   // [0] grid barrier counter, [2..5] two 64-bit argmax keys
     DevBuf<unsigned int> head_cnt;
-    int mega_stages = 0, mega_max_kpad = 0, mega_max_items = 0, mega_attn_floats = 0;
+    int mega_stages = 0, mega_max_kpad = 0, mega_max_units = 0, mega_attn_floats = 0;
     DevBuf<long long> dbg;
     bool dbg_on = false;
+    DevBuf<float4> stats;
+    DevBuf<XStats> emb_stats;
     size_t mega_smem = 0;
     int host_pos = 0;  // mirror of state.pos
     ~Model() {
@@ -516,7 +521,7 @@ int capture_graph(Model& m, bool with_head, cudaGraphExec_t* out) {
 int build_mega(Model& m) {
     const int H = m.cfg.hidden;
     std::vector<MegaPhase> ph;
-    int max_kpad = 0, max_items = 0;
+    int max_kpad = 0, max_units = 0;
     auto gemv_phase = [&](const QWeight& w, GemvArgs g, int x_src, int resid_src, int is_head) {
         MegaPhase p{};
         p.type = PH_GEMV;
@@ -526,7 +531,7 @@ int build_mega(Model& m) {
         fill_weight(w, g);
         p.g = g;
         max_kpad = std::max(max_kpad, layout_kpad(w.L));
-        max_items = std::max(max_items, slab_max_items(w.L));
+        max_units = std::max(max_units, slab_max_units(w.L));
         ph.push_back(p);
     };
     const int mega_splits = std::max(1, std::min(g_num_sms / m.attn_heads, m.max_splits));
@@ -572,6 +577,7 @@ int build_mega(Model& m) {
         o.epi = EPI_RESIDUAL;
         o.resid = m.x.p;
         o.out = m.x.p;
+        o.next_norm_w = ly.ffn_norm.p;
         gemv_phase(*ly.o, o, SRC_PTR, src0, 0);
         GemvArgs g{};
         g.x = m.x.p;
@@ -585,6 +591,7 @@ int build_mega(Model& m) {
         d.epi = EPI_RESIDUAL;
         d.resid = m.x.p;
         d.out = m.x.p;
+        d.next_norm_w = l + 1 < m.layers.size() ? m.layers[l + 1].attn_norm.p : m.out_norm.p;
         gemv_phase(*ly.down, d, SRC_PTR, SRC_PTR, 0);
     }
     GemvArgs lm{};
@@ -596,17 +603,33 @@ int build_mega(Model& m) {
     gemv_phase(*m.lm_head, lm, m.layers.empty() ? SRC_EMB : SRC_PTR, SRC_PTR, 1);
 
     m.mega_max_kpad = max_kpad;
-    m.mega_max_items = max_items;
+    m.mega_max_units = max_units;
     m.mega_attn_floats = attn_scratch_floats(m.attn_dim, kConsumerThreads);
     m.mega_stages = 0;
     for (int s = kMaxStages; s >= 2; --s)
-        if (mega_smem_bytes(s, max_kpad, max_items, m.mega_attn_floats) <= 227 * 1024) { m.mega_stages = s; break; }
+        if (mega_smem_bytes(s, max_kpad, max_units, m.mega_attn_floats) <= 227 * 1024) { m.mega_stages = s; break; }
     if (m.mega_stages == 0) return fail("persistent kernel does not fit shared memory");
-    m.mega_smem = mega_smem_bytes(m.mega_stages, max_kpad, max_items, m.mega_attn_floats);
+    m.mega_smem = mega_smem_bytes(m.mega_stages, max_kpad, max_units, m.mega_attn_floats);
     for (auto& p : ph) p.g.stages = m.mega_stages;
     m.nphases = (int)ph.size();
     TRY(m.phases.alloc(ph.size()));
     CK(cudaMemcpyAsync(m.phases.p, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice, g_stream));
+    std::vector<ProdRec> prod(ph.size());
+    for (size_t i = 0; i < ph.size(); ++i) {
+        prod[i].wq = (unsigned long long)(uintptr_t)ph[i].g.wq;
+        prod[i].L = ph[i].g.L;
+        prod[i].flags = (ph[i].type == PH_GEMV ? 1 : 0) | (ph[i].is_head ? 2 : 0);
+    }
+    TRY(m.prod.alloc(prod.size()));
+    CK(cudaMemcpyAsync(m.prod.p, prod.data(), prod.size() * sizeof(ProdRec), cudaMemcpyHostToDevice, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    TRY(m.stats.alloc((size_t)2 * g_num_sms * 2));
+    CK(cudaMemsetAsync(m.stats.p, 0, (size_t)2 * g_num_sms * 2 * sizeof(float4), g_stream));
+    TRY(m.emb_stats.alloc(m.cfg.vocab));
+    emb_stats_kernel<<<m.cfg.vocab, 256, 0, g_stream>>>(m.tok_emb.p, m.layers.empty() ? m.out_norm.p : m.layers[0].attn_norm.p,
+                                                        m.emb_stats.p, H);
+    ++g_launches;
+    CK(cudaGetLastError());
     TRY(m.sync_buf.alloc(8));
     TRY(m.head_cnt.alloc(std::max(1, m.attn_heads)));
     CK(cudaMemsetAsync(m.sync_buf.p, 0, 8 * sizeof(unsigned int), g_stream));
@@ -627,6 +650,7 @@ int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
     CK(cudaMemsetAsync(m.sync_buf.p, 0, 8 * sizeof(unsigned int), g_stream));
     MegaArgs a{};
     a.phases = m.phases.p;
+    a.prod = m.prod.p;
     a.nphases = m.nphases;
     a.emb = m.tok_emb.p;
     a.H = m.cfg.hidden;
@@ -643,9 +667,11 @@ int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
     a.logits = m.logits.p;
     a.stages = m.mega_stages;
     a.max_kpad = m.mega_max_kpad;
-    a.max_items = m.mega_max_items;
+    a.max_units = m.mega_max_units;
     a.attn_floats = m.mega_attn_floats;
     a.dbg = m.dbg_on ? m.dbg.p : nullptr;
+    a.stats = m.stats.p;
+    a.emb_stats = m.emb_stats.p;
     void* args[] = {&a};
     const void* fn = m.cfg.qtype == TI_Q_INT4 ? (const void*)mega_decode_kernel<4> : (const void*)mega_decode_kernel<8>;
     CK(cudaLaunchCooperativeKernel(fn, dim3(g_num_sms), dim3(kMegaThreads), args, m.mega_smem, g_stream));
@@ -1292,7 +1318,7 @@ int ti_b200_debug_timeline(ti_model_t h, int32_t token, int64_t* stamps, size_t 
     Model* m = get_model(h);
     if (!m || !m->finalized || !m->use_mega) return fail("timeline needs a finalized model on the persistent-kernel engine");
     TRY(check_capacity(*m, 1));
-    const size_t n = (size_t)m->nphases * 6;
+    const size_t n = (size_t)m->nphases * kStampsPerPhase;
     if (cap < n) return fail("stamp buffer too small: need %zu", n);
     TRY(m->dbg.alloc(n));
     CK(cudaMemsetAsync(m->dbg.p, 0, n * sizeof(long long), g_stream));

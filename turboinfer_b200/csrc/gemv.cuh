@@ -9,12 +9,25 @@
 //   warp 16 (one elected lane)  producer: streams the CTA's contiguous slab of packed weights HBM -> shared memory
 //                               with 1-D bulk async copies (TMA engine, cp.async.bulk + mbarrier complete_tx),
 //                               <= 32 KiB per stage, kStages deep, weights marked L2 evict-first
-//   warps 0..15                 consumers: stage x into shared memory (fused RMSNorm, nibble-position prescale),
-//                               then per stage: LDS.128 weights, unpack in registers (LOP3 magic-number trick, no
-//                               int->float converts), FADD2 / FFMA2 fp32 accumulate, 6-shuffle transposed warp
-//                               reduction of 4 items, partial sums to shared memory
-//   epilogue                    per column: fixed-order sum of the k-superchunk partials, * scale (+ zero-point
-//                               term), then the fused residual / SwiGLU / ReLU / RoPE+KV-append / logits+argmax
+//   warps 0..15                 consumers
+//     prologue   x (fp32, optionally RMS-normalised with the reference's roundings) is converted ONCE per GEMV to
+//                24-bit block fixed point, x_k ~= s_x * xf_k with |xf_k| < 2^23, and stored in shared memory as three
+//                8-bit digit planes (xf = d2*65536 + d1*256 + d0; d0, d1 unsigned, d2 signed)
+//     main loop  per 512-byte item (4 columns x 256 k INT4 / 128 k INT8): one LDS.128 of weights, nibbles unpacked in
+//                registers with LOP3 / SHF, products accumulated with IDP4A (4 MACs per instruction) into three int32
+//                accumulators per lane, one per digit.  Integer accumulation is exact and order-independent, so the
+//                result does not depend on how k is split over lanes, warps or (tensor-parallel) GPUs.
+//                B200 measurement (scripts/microbench2.cu): IDP4A issues every 2 cycles per SM sub-partition, which
+//                bounds this loop at 12 cycles per item per SM = 1.8x the HBM rate; the fp32 magic-number unpack it
+//                replaces was bound by the ALU pipe at 18+ cycles per item per SM (below the HBM rate in practice).
+//     reduction  lanes (column c, k-slice s): 3 shuffle steps over s per run of items of one unit, then one shared-
+//                memory integer atomic per (column, digit)
+//   epilogue                    per column: y = colscale * s_x * (A2*65536 + A1*256 + A0 - off*sum(xf) [+ zero-point
+//                               term]) evaluated in int64 / fp64 and rounded once, then the fused residual / SwiGLU /
+//                               ReLU / RoPE+KV-append / logits+argmax
+// Accuracy: the only approximation is the 24-bit quantisation of x relative to max|x| (absolute error <= 2^-24 max|x|
+// per element, i.e. what an fp32 mantissa holds for the largest elements); products and sums are exact.  Measured
+// error against the fp64 dot product is below that of the reference's own sequential fp32 accumulation.
 // HBM-bound by design: algorithmic bytes = K*N*bits/8 + O(K + N) floats; every packed byte is read exactly once.
 #pragma once
 #include "ptx.cuh"
@@ -25,6 +38,8 @@ namespace tib {
 constexpr int kGemvThreads = (kConsumerWarps + 1) * 32;  // 544
 constexpr int kConsumerThreads = kConsumerWarps * 32;    // 512
 constexpr int kMaxStages = 6;
+constexpr float kXQMax = 8388000.0f;   // bound of |xf|: below 2^23 - 256 so that rounding can never reach 2^23
+constexpr int kXCache = 8;             // float4 vectors of x a thread keeps in registers between the two prologue passes
 
 enum GemvEpilogue : int {
     EPI_STORE = 0,    // out[n] = y
@@ -42,6 +57,7 @@ struct GemvArgs {
     const float* colzterm;  // [4*U] zero-point term per column (y += scale*zterm*sum(x)), or nullptr
     QLayout L;
     int stages;
+    int woff;               // offset added to the stored INT4 values (8 symmetric, 0 asymmetric); INT8 is stored signed
     // prologue
     const float* x;        // [K]
     const float* norm_w;   // RMSNorm weight [K] or nullptr
@@ -61,6 +77,16 @@ struct GemvArgs {
     int page_tokens;
     // EPI_LOGITS
     unsigned long long* argmax_key;
+    // persistent kernel: the RMSNorm weight the NEXT GEMV applies to this one's output (nullptr: none); used to hand
+    // the next prologue its sum of squares and max|x * w| bound (see XStats)
+    const float* next_norm_w;
+};
+
+// What a GEMV prologue needs to know about its input before it can convert it to fixed point in ONE pass: the sum of
+// squares (RMSNorm) and a bound of max|x_k * w_k| (w = 1 without norm).  In the persistent kernel the phase that
+// PRODUCES x leaves one partial per CTA in global memory; the consumers combine them in CTA order (deterministic).
+struct XStats {
+    float ss, am;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -68,103 +94,79 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-
-// sum over the 512 consumer threads, identical (and identically ordered) in every thread
-__device__ __forceinline__ float consumer_block_sum(float v, float* red, int warp, int lane) {
-    v = warp_sum(v);
-    if (lane == 0) red[warp] = v;
-    bar_sync(1, kConsumerThreads);
-    float s = 0.f;
+__device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
-    for (int i = 0; i < kConsumerWarps; ++i) s += red[i];
-    bar_sync(1, kConsumerThreads);
-    return s;
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
 }
 
-// ---- per-item dot products -------------------------------------------------------------------------
-// INT4: a lane's 16 B hold 32 nibbles u = q + 8.  (w & (0xF << 4p)) | 0x4B000000 is the float 2^23 + u*16^p;
-// adding -(2^23 + 8*16^p) leaves (u - 8)*16^p exactly, and x was pre-multiplied by 16^-p when it was staged,
-// so one LOP3 + half an FADD2 + half an FFMA2 per weight, all exact until the fp32 accumulate.
-struct Q4Consts {
-    uint32_t magic;
-    f32x2 c01, c23, c42, c34;
+// ---- integer dot products ----------------------------------------------------------------------------
+__device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c) {  // a, b unsigned bytes
+    int d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {  // a unsigned, b signed
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp4a_su(uint32_t a, uint32_t b, int c) {  // a signed, b unsigned
+    int d;
+    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp4a_ss(uint32_t a, uint32_t b, int c) {  // a, b signed
+    int d;
+    asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// The digits of one (chunk, k-slice) held in registers: INT4 [digit][half] / INT8 [digit] vectors of 4 words,
+// 128 B apart in shared memory (qlayout.cuh xdigit_word_offset).
+template <int BITS>
+struct XDigits {
+    uint4 v[BITS == 4 ? 6 : 3];
 };
-// The constants are made opaque to the compiler once per kernel so they live in registers instead of being
-// re-materialised (UMOV pairs) for every item.
-__device__ __forceinline__ Q4Consts q4_consts() {
-    Q4Consts c;
-    c.magic = 0x4B000000u;
-    c.c01 = pack2(-8388616.f, -8388736.f);
-    c.c23 = pack2(-8390656.f, -8421376.f);
-    c.c42 = pack2(-8912896.f, -8390656.f);
-    c.c34 = pack2(-8421376.f, -8912896.f);
-    asm volatile("" : "+r"(c.magic), "+l"(c.c01), "+l"(c.c23), "+l"(c.c42), "+l"(c.c34));
-    return c;
-}
-__device__ __forceinline__ float dot_q4(const uint4& wv, const f32x2 (&xr)[16], const Q4Consts& k) {
-    const uint32_t MAGIC = k.magic;
-    const f32x2 C01 = k.c01, C23 = k.c23, C42 = k.c42, C34 = k.c34;
-    f32x2 acc0 = 0ull, acc1 = 0ull;
-    const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
+template <int BITS>
+__device__ __forceinline__ XDigits<BITS> load_xdigits(uint32_t xs) {
+    XDigits<BITS> x;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t w = words[i];
-        const uint32_t wh = w >> 12;
-        const uint32_t m0 = and_or(w, 0x0000000Fu, MAGIC);
-        const uint32_t m1 = and_or(w, 0x000000F0u, MAGIC);
-        const uint32_t m2 = and_or(w, 0x00000F00u, MAGIC);
-        const uint32_t m3 = and_or(w, 0x0000F000u, MAGIC);
-        const uint32_t m4 = and_or(w, 0x000F0000u, MAGIC);
-        const uint32_t m5 = and_or(wh, 0x00000F00u, MAGIC);
-        const uint32_t m6 = and_or(wh, 0x0000F000u, MAGIC);
-        const uint32_t m7 = and_or(wh, 0x000F0000u, MAGIC);
-        acc0 = fma2(add2(pack2u(m0, m1), C01), xr[4 * i + 0], acc0);
-        acc1 = fma2(add2(pack2u(m2, m3), C23), xr[4 * i + 1], acc1);
-        acc0 = fma2(add2(pack2u(m4, m5), C42), xr[4 * i + 2], acc0);
-        acc1 = fma2(add2(pack2u(m6, m7), C34), xr[4 * i + 3], acc1);
-    }
-    float a, b;
-    unpack2(add2(acc0, acc1), a, b);
-    return a + b;
+    for (int i = 0; i < (BITS == 4 ? 6 : 3); ++i) x.v[i] = lds128s(xs + 128 * i);
+    return x;
 }
+constexpr int kAccPerUnit = 3;  // one int32 accumulator per digit
 
-// INT8: a lane's 16 B hold 16 bytes q + 128; PRMT drops byte e into the mantissa of 2^23.
-__device__ __forceinline__ float dot_q8(const uint4& wv, const f32x2 (&xr)[8], const Q4Consts& k) {
-    const uint32_t MAGIC = k.magic;
-    const f32x2 C = k.c01 == 0ull ? 0ull : pack2(-8388736.f, -8388736.f);
-    f32x2 acc0 = 0ull, acc1 = 0ull;
-    const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
+// One item for one lane: 16 bytes of weights of column c against the digits of k-slice s of the item's chunk.
+// acc: one accumulator per digit; a quad keeps 12 of them busy, so no IDP4A waits on the one before it
+template <int BITS>
+__device__ __forceinline__ void item_dot(const uint4& wv, const XDigits<BITS>& x, int (&acc)[kAccPerUnit]) {
+    const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+    if constexpr (BITS == 4) {
+        const uint32_t d0a[4] = {x.v[0].x, x.v[0].y, x.v[0].z, x.v[0].w}, d0b[4] = {x.v[1].x, x.v[1].y, x.v[1].z, x.v[1].w};
+        const uint32_t d1a[4] = {x.v[2].x, x.v[2].y, x.v[2].z, x.v[2].w}, d1b[4] = {x.v[3].x, x.v[3].y, x.v[3].z, x.v[3].w};
+        const uint32_t d2a[4] = {x.v[4].x, x.v[4].y, x.v[4].z, x.v[4].w}, d2b[4] = {x.v[5].x, x.v[5].y, x.v[5].z, x.v[5].w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t w = words[i];
-        const uint32_t m0 = prmt(w, MAGIC, 0x7650u);
-        const uint32_t m1 = prmt(w, MAGIC, 0x7651u);
-        const uint32_t m2 = prmt(w, MAGIC, 0x7652u);
-        const uint32_t m3 = prmt(w, MAGIC, 0x7653u);
-        acc0 = fma2(add2(pack2u(m0, m1), C), xr[2 * i + 0], acc0);
-        acc1 = fma2(add2(pack2u(m2, m3), C), xr[2 * i + 1], acc1);
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t lo = w[j] & 0x0F0F0F0Fu;
+            const uint32_t hi = (w[j] >> 4) & 0x0F0F0F0Fu;
+            acc[0] = dp4a_uu(lo, d0a[j], acc[0]);
+            acc[1] = dp4a_uu(lo, d1a[j], acc[1]);
+            acc[2] = dp4a_us(lo, d2a[j], acc[2]);
+            acc[0] = dp4a_uu(hi, d0b[j], acc[0]);
+            acc[1] = dp4a_uu(hi, d1b[j], acc[1]);
+            acc[2] = dp4a_us(hi, d2b[j], acc[2]);
+        }
+    } else {
+        const uint32_t d0[4] = {x.v[0].x, x.v[0].y, x.v[0].z, x.v[0].w}, d1[4] = {x.v[1].x, x.v[1].y, x.v[1].z, x.v[1].w};
+        const uint32_t d2[4] = {x.v[2].x, x.v[2].y, x.v[2].z, x.v[2].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc[0] = dp4a_su(w[j], d0[j], acc[0]);
+            acc[1] = dp4a_su(w[j], d1[j], acc[1]);
+            acc[2] = dp4a_ss(w[j], d2[j], acc[2]);
+        }
     }
-    float a, b;
-    unpack2(add2(acc0, acc1), a, b);
-    return a + b;
-}
-
-// Reduce four per-lane values over the warp with 6 shuffles; afterwards lane 8*i (i < 4) holds the full
-// sum of v[i].  Every v[i] goes through the same addition tree, so equal inputs give bit-equal sums.
-__device__ __forceinline__ float reduce4(float v0, float v1, float v2, float v3, int lane) {
-    const bool hi16 = lane & 16;
-    float keep0 = hi16 ? v2 : v0, keep1 = hi16 ? v3 : v1;
-    float send0 = hi16 ? v0 : v2, send1 = hi16 ? v1 : v3;
-    keep0 += __shfl_xor_sync(0xffffffffu, send0, 16);
-    keep1 += __shfl_xor_sync(0xffffffffu, send1, 16);
-    const bool hi8 = lane & 8;
-    float keep = hi8 ? keep1 : keep0;
-    float send = hi8 ? keep0 : keep1;
-    keep += __shfl_xor_sync(0xffffffffu, send, 8);
-    keep += __shfl_xor_sync(0xffffffffu, keep, 4);
-    keep += __shfl_xor_sync(0xffffffffu, keep, 2);
-    keep += __shfl_xor_sync(0xffffffffu, keep, 1);
-    return keep;
 }
 
 __device__ __forceinline__ unsigned long long argmax_pack(float v, int idx) {
@@ -177,36 +179,45 @@ __device__ __forceinline__ unsigned long long argmax_pack(float v, int idx) {
 // ---- shared-memory carve-up ------------------------------------------------------------------------
 struct GemvSmem {
     uint8_t* ring;      // stages * 32 KiB
-    float* xs;          // kpad floats
-    float* part;        // max items floats
-    float* red;         // 32 floats
+    uint8_t* xd;        // digit planes of x: 3 * kpad bytes
+    int* acc;           // [ncols][3] integer column sums
+    float* red;         // 64 floats of reduction scratch
+    long long* sxf;     // [16] per-warp partial sums of xf over k
     uint64_t* full;     // [stages]
     uint64_t* empty;    // [stages]
 };
 
-TIB_HD size_t gemv_smem_bytes(const QLayout& L, int stages) {
+TIB_HD size_t gemv_smem_bytes_for(int stages, int kpad, int max_units) {
     size_t b = (size_t)stages * kStageBytes;
-    b += (size_t)layout_kpad(L) * 4;
-    b += (size_t)slab_max_items(L) * 4;
-    b += 32 * 4;
+    b += (size_t)3 * kpad;
+    b += (size_t)max_units * 4 * 3 * 4;
+    b += 64 * 4 + 16 * 8;
     b += (size_t)2 * kMaxStages * 8;
     return b + 128;
 }
+TIB_HD size_t gemv_smem_bytes(const QLayout& L, int stages) { return gemv_smem_bytes_for(stages, layout_kpad(L), slab_max_units(L)); }
 
-__device__ __forceinline__ GemvSmem gemv_carve(uint8_t* base, const QLayout& L, int stages) {
+__device__ __forceinline__ GemvSmem gemv_carve_for(uint8_t* base, int stages, int kpad, int max_units, uint8_t** end = nullptr) {
     GemvSmem s;
     uintptr_t p = (reinterpret_cast<uintptr_t>(base) + 127) & ~uintptr_t(127);
     s.ring = reinterpret_cast<uint8_t*>(p);
     p += (size_t)stages * kStageBytes;
-    s.xs = reinterpret_cast<float*>(p);
-    p += (size_t)layout_kpad(L) * 4;
-    s.part = reinterpret_cast<float*>(p);
-    p += (size_t)slab_max_items(L) * 4;
+    s.xd = reinterpret_cast<uint8_t*>(p);
+    p += (size_t)3 * kpad;   // kpad is a multiple of 128: stays 16-byte aligned
+    s.acc = reinterpret_cast<int*>(p);
+    p += (size_t)max_units * 4 * 3 * 4;
     s.red = reinterpret_cast<float*>(p);
-    p += 32 * 4;
+    p += 64 * 4;
+    s.sxf = reinterpret_cast<long long*>(p);
+    p += 16 * 8;
     s.full = reinterpret_cast<uint64_t*>(p);
     s.empty = s.full + kMaxStages;
+    p += (size_t)2 * kMaxStages * 8;
+    if (end) *end = reinterpret_cast<uint8_t*>(p);
     return s;
+}
+__device__ __forceinline__ GemvSmem gemv_carve(uint8_t* base, const QLayout& L, int stages) {
+    return gemv_carve_for(base, stages, layout_kpad(L), slab_max_units(L));
 }
 
 // ---- building blocks shared by the stand-alone GEMV kernel and the persistent decode kernel (mega.cuh) -------
@@ -220,211 +231,285 @@ struct PhaseCtx {
     unsigned long long* key;  // EPI_LOGITS: argmax key to use instead of GemvArgs::argmax_key (nullptr: keep)
 };
 
-// producer: stream this CTA's slab through the ring.  `it` counts stages over the whole launch.
-__device__ __forceinline__ void gemv_produce(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, uint32_t& it) {
+// producer (the whole warp): stream this CTA's slab through the ring.  `it` counts stages over the whole launch.
+// Lane w < 16 computes how many items consumer warp w takes from the stage, one REDUX sums them, lane 0 drives the
+// mbarriers and the bulk copy -- the per-stage bookkeeping must stay far below the ~0.7 us a stage lasts at HBM rate.
+__device__ __forceinline__ void gemv_produce(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, uint32_t& it, int lane) {
     const int S = a.stages;
     const uint8_t* src = a.wq + slab.byte0;
+    const int l_nq = warp_quads(slab, lane & 15), l_fq = warp_first_quad(slab, lane & 15);
     for (int r = 0; r < slab.rounds; ++r, ++it) {
-        const uint32_t st = it % S, use = it / S;
-        if (use > 0) mbar_wait(&sm.empty[st], (use - 1) & 1);
-        const uint32_t bytes = (uint32_t)round_total(slab, r) * kItemBytes;
-        mbar_arrive_expect_tx(&sm.full[st], bytes);
-        bulk_g2s_evict_first(sm.ring + (size_t)st * kStageBytes, src, bytes, &sm.full[st]);
+        const int l_items = (lane < kConsumerWarps && r < l_nq) ? (l_fq + r >= slab.qfull ? slab.nlast : 4) : 0;
+        const uint32_t bytes = (uint32_t)__reduce_add_sync(0xffffffffu, l_items) * kItemBytes;
+        if (lane == 0) {
+            const uint32_t st = it % S, use = it / S;
+            if (use > 0) mbar_wait(&sm.empty[st], (use - 1) & 1);
+            mbar_arrive_expect_tx(&sm.full[st], bytes);
+            bulk_g2s_evict_first(sm.ring + (size_t)st * kStageBytes, src, bytes, &sm.full[st]);
+        }
         src += bytes;
     }
+    __syncwarp();
 }
 
-// consumers, prologue: stage x into shared memory (fused RMSNorm, INT4 nibble-position prescale).
-// Returns sum(x') (only meaningful when want_sum).
-// Fast path (K % 4 == 0, 16-byte aligned pointers): 128-bit loads, four per thread in flight before first use, so
-// the global-memory latency is paid once per batch instead of once per element.
-__device__ __forceinline__ float4 ld_act4(const float* p, bool coherent) {
-    return coherent ? __ldcg(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p);
-}
-template <int BITS>
-__device__ __forceinline__ float4 q4_prescale4(float4 v, int k0) {
-    if (BITS == 4) {
-        // element e of the float4 at k0 sits at nibble position p(j, e), j = (k0 % 1024) / 128  (qlayout.cuh q4_pos)
-        if (((k0 & 1023) >> 7) & 1) { v.x *= 1.0f / 65536.0f; v.y *= 1.0f / 256.0f; v.z *= 1.0f / 4096.0f; v.w *= 1.0f / 65536.0f; }
-        else { v.y *= 1.0f / 16.0f; v.z *= 1.0f / 256.0f; v.w *= 1.0f / 4096.0f; }
+// ---- prologue: x -> (optional RMSNorm) -> 24-bit block fixed point -> digit planes in shared memory -----------
+__device__ __forceinline__ float4 ld_x4(const float* x, int v, int K, bool vec, bool coherent) {
+    const int k = 4 * v;
+    if (vec) {
+        if (k >= K) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return coherent ? __ldcg(reinterpret_cast<const float4*>(x + k)) : *reinterpret_cast<const float4*>(x + k);
     }
-    return v;
+    float4 r;
+    r.x = k + 0 < K ? ld_act(x + k + 0, coherent) : 0.f;
+    r.y = k + 1 < K ? ld_act(x + k + 1, coherent) : 0.f;
+    r.z = k + 2 < K ? ld_act(x + k + 2, coherent) : 0.f;
+    r.w = k + 3 < K ? ld_act(x + k + 3, coherent) : 0.f;
+    return r;
+}
+
+// two block-wide reductions at once (sum of a, max of b) over the 512 consumer threads; every thread gets the same,
+// identically ordered result.  Uses red[slot*32 .. slot*32+31]; callers alternate slots instead of a trailing barrier.
+__device__ __forceinline__ void consumer_sum_max(float& a, float& b, float* red, int warp, int lane) {
+    a = warp_sum(a);
+    b = warp_max(b);
+    if (lane == 0) { red[warp] = a; red[16 + warp] = b; }
+    bar_sync(1, kConsumerThreads);
+    float s = 0.f, m = 0.f;
+#pragma unroll
+    for (int i = 0; i < kConsumerWarps; ++i) { s += red[i]; m = fmaxf(m, red[16 + i]); }
+    a = s;
+    b = m;
 }
 
 template <int BITS>
-__device__ __forceinline__ float gemv_stage_x(const GemvArgs& a, const float* x, const GemvSmem& sm, bool coherent, bool want_sum,
+__device__ __forceinline__ void x_store_digits(uint8_t* xd, int v, float4 y, float inv_s, long long& sxf) {
+    const int f0 = __float2int_rn(y.x * inv_s), f1 = __float2int_rn(y.y * inv_s), f2 = __float2int_rn(y.z * inv_s),
+              f3 = __float2int_rn(y.w * inv_s);
+    sxf += (long long)((f0 + f1) + (f2 + f3));
+    // byte b of each of the four values -> one word per digit
+    const uint32_t lo01 = __byte_perm(f0, f1, 0x5140), lo23 = __byte_perm(f2, f3, 0x5140);  // [f0.b0 f1.b0 f0.b1 f1.b1]
+    const uint32_t d0 = __byte_perm(lo01, lo23, 0x5410);
+    const uint32_t d1 = __byte_perm(lo01, lo23, 0x7632);
+    const uint32_t hi01 = __byte_perm(f0, f1, 0x0062), hi23 = __byte_perm(f2, f3, 0x0062);  // [f0.b2 f1.b2 . .]
+    const uint32_t d2 = __byte_perm(hi01, hi23, 0x5410);
+    const int k = 4 * v;
+    *reinterpret_cast<uint32_t*>(xd + xdigit_word_offset(BITS, k, 0)) = d0;
+    *reinterpret_cast<uint32_t*>(xd + xdigit_word_offset(BITS, k, 1)) = d1;
+    *reinterpret_cast<uint32_t*>(xd + xdigit_word_offset(BITS, k, 2)) = d2;
+}
+
+// Returns s_x (x_k ~= s_x * xf_k).  Also zeroes the column accumulators of this phase and leaves sum(xf) in *sm.sxf.
+template <int BITS>
+__device__ __forceinline__ float gemv_stage_x(const GemvArgs& a, const float* x, const GemvSmem& sm, const Slab& slab, bool coherent,
                                               int tid, int warp, int lane) {
     const QLayout& L = a.L;
     const int K = L.K, kpad = layout_kpad(L);
     const float* nw = a.norm_w;
     const bool vec = (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(nw)) & 15) == 0;
-    float ss = 0.f, sx = 0.f, rms = 1.f;
-    if (vec) {
-        constexpr int B = 4;  // float4 loads in flight per thread
-        const int nvec = kpad >> 2, kvec = K >> 2;
-        for (int v0 = tid; v0 < nvec; v0 += B * kConsumerThreads) {
-            float4 xv[B];
+    const int nvec = kpad >> 2;
+    const bool cached = nvec <= kXCache * kConsumerThreads;
+    for (int i = tid; i < slab.ncols * 3; i += kConsumerThreads) sm.acc[i] = 0;
+    float ss = 0.f, amax = 0.f;
+    float4 xv[kXCache];
+    // pass 1: sum of squares (RMSNorm) and a tight bound of max|y|, y = (x / rms) * w
+    if (cached) {
 #pragma unroll
-            for (int i = 0; i < B; ++i) {
-                const int v = v0 + i * kConsumerThreads;
-                xv[i] = v < kvec ? ld_act4(x + 4 * v, coherent) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int i = 0; i < B; ++i) {
-                const int v = v0 + i * kConsumerThreads;
-                if (v < nvec) {
-                    ss = fmaf(xv[i].x, xv[i].x, ss); ss = fmaf(xv[i].y, xv[i].y, ss);
-                    ss = fmaf(xv[i].z, xv[i].z, ss); ss = fmaf(xv[i].w, xv[i].w, ss);
-                    if (nw == nullptr) {  // no second pass needed: finish now
-                        sx += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
-                        xv[i] = q4_prescale4<BITS>(xv[i], 4 * v);
-                    }
-                    *reinterpret_cast<float4*>(sm.xs + 4 * v) = xv[i];
-                }
-            }
+        for (int i = 0; i < kXCache; ++i) {
+            const int v = tid + i * kConsumerThreads;
+            xv[i] = v < nvec ? ld_x4(x, v, K, vec, coherent) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (nw != nullptr) {
-            // the norm weights do not depend on the reduction: get the first batch moving before the barriers
-            float4 wv[B];
 #pragma unroll
-            for (int i = 0; i < B; ++i) {
-                const int v = tid + i * kConsumerThreads;
-                wv[i] = v < kvec ? *reinterpret_cast<const float4*>(nw + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            const float tot = consumer_block_sum(ss, sm.red, warp, lane);
-            rms = sqrtf(tot / (float)K + a.rms_eps);  // :1501
-            for (int v0 = tid; v0 < kvec; v0 += B * kConsumerThreads) {
-                if (v0 != tid) {
-#pragma unroll
-                    for (int i = 0; i < B; ++i) {
-                        const int v = v0 + i * kConsumerThreads;
-                        wv[i] = v < kvec ? *reinterpret_cast<const float4*>(nw + 4 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < B; ++i) {
-                    const int v = v0 + i * kConsumerThreads;
-                    if (v < kvec) {
-                        float4 t = *reinterpret_cast<const float4*>(sm.xs + 4 * v);
-                        t.x = (t.x / rms) * wv[i].x;  // :1504-1506, same two roundings
-                        t.y = (t.y / rms) * wv[i].y;
-                        t.z = (t.z / rms) * wv[i].z;
-                        t.w = (t.w / rms) * wv[i].w;
-                        sx += (t.x + t.y) + (t.z + t.w);
-                        *reinterpret_cast<float4*>(sm.xs + 4 * v) = q4_prescale4<BITS>(t, 4 * v);
-                    }
-                }
+        for (int i = 0; i < kXCache; ++i) {
+            const int v = tid + i * kConsumerThreads;
+            if (v < nvec) {
+                const float4 t = xv[i];
+                ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
+                float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (nw != nullptr) w = ld_x4(nw, v, K, vec, false);
+                amax = fmaxf(fmaxf(amax, fabsf(t.x * w.x)), fmaxf(fabsf(t.y * w.y), fmaxf(fabsf(t.z * w.z), fabsf(t.w * w.w))));
             }
         }
     } else {
-        for (int k = tid; k < kpad; k += kConsumerThreads) {
-            const float v = k < K ? ld_act(x + k, coherent) : 0.f;
-            sm.xs[k] = v;
-            ss = fmaf(v, v, ss);
-        }
-        if (nw != nullptr) {
-            const float tot = consumer_block_sum(ss, sm.red, warp, lane);
-            rms = sqrtf(tot / (float)K + a.rms_eps);
-        }
-        for (int k = tid; k < kpad; k += kConsumerThreads) {
-            float v = sm.xs[k];
-            if (nw != nullptr && k < K) v = (v / rms) * nw[k];
-            sx += v;
-            if (BITS == 4) {
-                const int p = q4_pos((k & 1023) >> 7, k & 3);
-                v *= __uint_as_float((uint32_t)(127 - 4 * p) << 23);  // 16^-p, exact
-            }
-            sm.xs[k] = v;
+        for (int v = tid; v < nvec; v += kConsumerThreads) {
+            const float4 t = ld_x4(x, v, K, vec, coherent);
+            ss = fmaf(t.x, t.x, ss); ss = fmaf(t.y, t.y, ss); ss = fmaf(t.z, t.z, ss); ss = fmaf(t.w, t.w, ss);
+            float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (nw != nullptr) w = ld_x4(nw, v, K, vec, false);
+            amax = fmaxf(fmaxf(amax, fabsf(t.x * w.x)), fmaxf(fabsf(t.y * w.y), fmaxf(fabsf(t.z * w.z), fabsf(t.w * w.w))));
         }
     }
-    float sumx = 0.f;
-    if (want_sum) sumx = consumer_block_sum(sx, sm.red, warp, lane);
+    consumer_sum_max(ss, amax, sm.red, warp, lane);
+    float rms = 1.f;
+    if (nw != nullptr) {
+        rms = sqrtf(ss / (float)K + a.rms_eps);  // :1501
+        amax = (amax / rms) * 1.000001f;          // covers the two roundings of (x / rms) * w
+    }
+    const bool finite = amax > 0.f && amax < INFINITY;
+    const float inv_s = finite ? kXQMax / amax : 0.f;
+    const float s_x = finite ? amax / kXQMax : 0.f;
+    // pass 2: y, fixed point, digit planes
+    long long sxf = 0;
+    auto emit = [&](int v, float4 t) {
+        if (nw != nullptr) {
+            const float4 w = ld_x4(nw, v, K, vec, false);
+            t.x = (t.x / rms) * w.x;  // :1504-1506, same two roundings
+            t.y = (t.y / rms) * w.y;
+            t.z = (t.z / rms) * w.z;
+            t.w = (t.w / rms) * w.w;
+        }
+        x_store_digits<BITS>(sm.xd, v, t, inv_s, sxf);
+    };
+    if (cached) {
+#pragma unroll
+        for (int i = 0; i < kXCache; ++i) {
+            const int v = tid + i * kConsumerThreads;
+            if (v < nvec) emit(v, xv[i]);
+        }
+    } else {
+        for (int v = tid; v < nvec; v += kConsumerThreads) emit(v, ld_x4(x, v, K, vec, coherent));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sxf += __shfl_xor_sync(0xffffffffu, sxf, o);
+    if (lane == 0) sm.sxf[tid >> 5] = sxf;
     bar_sync(1, kConsumerThreads);
-    return sumx;
+    return s_x;
 }
 
-// consumers, main loop: per ring stage LDS.128 weights, unpack, FFMA2, reduce, partials to shared memory.
-// A round hands each warp up to 4 items.  The common case -- 4 items of the same k-superchunk -- is straight-line
-// code, so the four unpack / FMA chains interleave (ILP 4); rounds that end the warp's range or straddle a
-// superchunk boundary take the per-item path.  The warp reduction of round r is issued after round r+1's
-// shared-memory loads, hiding the shuffle latency behind them.
+// Single-pass prologue for callers that already know sum(x^2) and the bound of max|x*w| (persistent kernel).
+template <int BITS>
+__device__ __forceinline__ float gemv_stage_x_known(const GemvArgs& a, const float* x, const GemvSmem& sm, const Slab& slab, bool coherent,
+                                                    XStats st, int tid, int lane, long long* dbg = nullptr) {
+    const QLayout& L = a.L;
+    const int K = L.K, kpad = layout_kpad(L);
+    const float* nw = a.norm_w;
+    const bool vec = (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(nw)) & 15) == 0;
+    const int nvec = kpad >> 2;
+    for (int i = tid; i < slab.ncols * 3; i += kConsumerThreads) sm.acc[i] = 0;
+    float rms = 1.f, amax = st.am;
+    if (nw != nullptr) {
+        rms = sqrtf(st.ss / (float)K + a.rms_eps);  // :1501
+        amax = __fdividef(amax, rms) * 1.00001f;     // a bound, not a result: the fast division is fine
+    }
+    const bool finite = amax > 0.f && amax < INFINITY;
+    const float inv_s = finite ? __fdividef(kXQMax, amax) : 0.f;  // |y * inv_s| <= kXQMax * (1 + 1e-6) either way
+    const float s_x = finite ? amax * (1.0f / kXQMax) : 0.f;
+    if (dbg) dbg[0] = clock64();
+    long long sxf = 0;
+    constexpr int B = 4;  // float4 loads in flight per thread
+    for (int v0 = tid; v0 < nvec; v0 += B * kConsumerThreads) {
+        float4 xv[B], wv[B];
+#pragma unroll
+        for (int i = 0; i < B; ++i) {
+            const int v = v0 + i * kConsumerThreads;
+            xv[i] = v < nvec ? ld_x4(x, v, K, vec, coherent) : make_float4(0.f, 0.f, 0.f, 0.f);
+            wv[i] = (nw != nullptr && v < nvec) ? ld_x4(nw, v, K, vec, false) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+        if (dbg) { dbg[1] = clock64(); if (xv[0].x == 1.2345e-30f) dbg[2] = 1; dbg[2] = clock64(); }
+#pragma unroll
+        for (int i = 0; i < B; ++i) {
+            const int v = v0 + i * kConsumerThreads;
+            if (v < nvec) {
+                float4 t = xv[i];
+                if (nw != nullptr) {
+                    t.x = (t.x / rms) * wv[i].x;  // :1504-1506, same two roundings
+                    t.y = (t.y / rms) * wv[i].y;
+                    t.z = (t.z / rms) * wv[i].z;
+                    t.w = (t.w / rms) * wv[i].w;
+                }
+                x_store_digits<BITS>(sm.xd, v, t, inv_s, sxf);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sxf += __shfl_xor_sync(0xffffffffu, sxf, o);
+    if (lane == 0) sm.sxf[tid >> 5] = sxf;
+    if (dbg) dbg[3] = clock64();
+    bar_sync(1, kConsumerThreads);
+    if (dbg) dbg[4] = clock64();
+    return s_x;
+}
+
+// consumers, main loop: one quad per warp per ring stage -- LDS the chunk's digits once, LDS.128 the <= 4 items,
+// IDP4A them into per-unit accumulators; when the warp's run over a group ends, reduce the digit sums over the 8
+// k-slices (3 shuffle steps) and add them to the column sums in shared memory.
 template <int BITS, int DBG = 0>
 __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, uint32_t& it, int warp, int lane) {
     const QLayout& L = a.L;
     const int S = a.stages;
-    const int ksc = L.ksc, ncols = slab.ncols, nrounds = slab.rounds;
-    constexpr int NX = BITS == 4 ? 16 : 8;  // float2 pairs of x per lane per superchunk
-    const Q4Consts kc = q4_consts();
-    f32x2 xr[NX];
-    int cur_s = -1;
-    const int my_n = warp_items(slab, warp);
-    const int first = warp_first_item(slab, warp);
-    int it_s = first / ncols;  // superchunk / column of the next item
-    int it_c = first - it_s * ncols;
-    int item = first;
-    const int w_lo = warp < slab.m ? warp : slab.m, w_hi = warp - w_lo;  // warps before this one with b+1 / b items
-    const float* xlane = sm.xs + 4 * lane;
-    auto load_x = [&](int s) {
-        cur_s = s;
-        const float* xp = xlane + (size_t)s * ksc;
+    const int C = L.nchunks, nrounds = slab.rounds;
+    constexpr int kChunkBytes = BITS == 4 ? 768 : 384;
+    const int my_nq = warp_quads(slab, warp);
+    const int fq = warp_first_quad(slab, warp);
+    int grp = fq / C;          // group / chunk of the warp's next quad
+    int chunk = fq - grp * C;
+    const int c = lane & 3, s = lane >> 2;
+    const uint32_t xlane = smem_u32(sm.xd) + s * 16;
+    const uint32_t ring_lane = smem_u32(sm.ring) + lane * 16;
+    // lane l < 16 stands for warp l when the stage offsets are summed with one REDUX per round
+    const int l_nq = warp_quads(slab, lane & 15), l_fq = warp_first_quad(slab, lane & 15);
+    const bool l_before = lane < warp;  // warp < 16
+    int acc[4][kAccPerUnit];
 #pragma unroll
-        for (int j = 0; j < NX / 2; ++j) {
-            const uint4 q = lds128(xp + 128 * j);
-            xr[2 * j] = pack2u(q.x, q.y);
-            xr[2 * j + 1] = pack2u(q.z, q.w);
-        }
-    };
-    auto dot = [&](const uint4& wv) -> float {
-        if constexpr (DBG == 1) return __uint_as_float(wv.x ^ wv.y ^ wv.z ^ wv.w);
-        else if constexpr (BITS == 4) return dot_q4(wv, xr, kc);
-        else return dot_q8(wv, xr, kc);
-    };
-    float pv0 = 0.f, pv1 = 0.f, pv2 = 0.f, pv3 = 0.f;  // previous round's per-lane sums, reduced one round late
-    int p_item = 0, p_n = 0;
-    auto flush_prev = [&]() {
-        if (p_n > 0) {
-            const float tot = reduce4(pv0, pv1, pv2, pv3, lane);
-            const int gi = lane >> 3;
-            if ((lane & 7) == 0 && gi < p_n) sm.part[p_item + gi] = tot;  // part[s*ncols + c]
-        }
-    };
-    for (int r = 0; r < nrounds; ++r, ++it) {
-        const uint32_t st = it % S;
-        const int g_n = round_items(my_n, r);
-        const int woff = w_lo * round_items(slab.b + 1, r) + w_hi * round_items(slab.b, r);
-        mbar_wait(&sm.full[st], (it / S) & 1);
-        const uint8_t* wbase = sm.ring + (size_t)st * kStageBytes + (size_t)woff * kItemBytes + lane * 16;
-        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-        if (DBG == 2) {
-            flush_prev();
-        } else if (g_n == kItemsPerRound && it_c + kItemsPerRound <= ncols) {
-            const uint4 w0 = lds128(wbase), w1 = lds128(wbase + kItemBytes), w2 = lds128(wbase + 2 * kItemBytes),
-                        w3 = lds128(wbase + 3 * kItemBytes);
-            if (it_s != cur_s) load_x(it_s);
-            flush_prev();
-            v0 = dot(w0); v1 = dot(w1); v2 = dot(w2); v3 = dot(w3);
-            it_c += kItemsPerRound;
-            if (it_c == ncols) { it_c = 0; ++it_s; }
-        } else {
-            flush_prev();
-            float v[kItemsPerRound] = {0.f, 0.f, 0.f, 0.f};
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int g = 0; g < kItemsPerRound; ++g) {
-                if (g < g_n) {
-                    if (it_s != cur_s) load_x(it_s);
-                    v[g] = dot(lds128(wbase + g * kItemBytes));
-                    if (++it_c == ncols) { it_c = 0; ++it_s; }
-                }
+        for (int i = 0; i < kAccPerUnit; ++i) acc[u][i] = 0;
+    bool dirty = false;
+    auto flush = [&]() {
+        const int live = grp == slab.ngroups - 1 ? slab.nlast : 4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int v0 = acc[u][0], v1 = acc[u][1], v2 = acc[u][2];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                v2 += __shfl_xor_sync(0xffffffffu, v2, o);
             }
-            v0 = v[0]; v1 = v[1]; v2 = v[2]; v3 = v[3];
+            if (lane < 4 && u < live) {
+                int* dst = sm.acc + ((grp * 4 + u) * 4 + c) * 3;
+                atomicAdd(dst + 0, v0);
+                atomicAdd(dst + 1, v1);
+                atomicAdd(dst + 2, v2);
+            }
+#pragma unroll
+            for (int i = 0; i < kAccPerUnit; ++i) acc[u][i] = 0;
+        }
+        dirty = false;
+    };
+    uint32_t st = it % S, par = (it / S) & 1;
+    it += nrounds;
+    for (int r = 0; r < nrounds; ++r) {
+        if (r > 0 && ++st == (uint32_t)S) { st = 0; par ^= 1; }
+        const bool have = r < my_nq;
+        // items of the warps before this one in the stage
+        const int l_items = (l_before && r < l_nq) ? (l_fq + r >= slab.qfull ? slab.nlast : 4) : 0;
+        const int woff = __reduce_add_sync(0xffffffffu, l_items);
+        XDigits<BITS> xd;
+        if (have) xd = load_xdigits<BITS>(xlane + chunk * kChunkBytes);  // does not depend on the stage: before the wait
+        if (DBG != 2) mbar_wait(&sm.full[st], par);
+        if (have) {
+            const int live = grp == slab.ngroups - 1 ? slab.nlast : 4;
+            const uint32_t wbase = ring_lane + st * kStageBytes + woff * kItemBytes;
+            auto one = [&](const uint4& wv, int (&ac)[kAccPerUnit]) {
+                if (DBG != 1) item_dot<BITS>(wv, xd, ac);
+                else ac[0] += (int)(wv.x ^ wv.y ^ wv.z ^ wv.w);
+            };
+            if (live == 4) {  // the common case, straight-line: four loads in flight, 12 independent IDP4A chains
+                const uint4 w0 = lds128s(wbase), w1 = lds128s(wbase + kItemBytes), w2 = lds128s(wbase + 2 * kItemBytes),
+                            w3 = lds128s(wbase + 3 * kItemBytes);
+                one(w0, acc[0]); one(w1, acc[1]); one(w2, acc[2]); one(w3, acc[3]);
+            } else {          // ragged last group of the slab: 1..3 items
+                { const uint4 w0 = lds128s(wbase); one(w0, acc[0]); }
+                if (live > 1) { const uint4 w1 = lds128s(wbase + kItemBytes); one(w1, acc[1]); }
+                if (live > 2) { const uint4 w2 = lds128s(wbase + 2 * kItemBytes); one(w2, acc[2]); }
+            }
+            dirty = true;
+            if (++chunk == C) { flush(); chunk = 0; ++grp; }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[st]);  // this warp is done reading the stage
-        pv0 = v0; pv1 = v1; pv2 = v2; pv3 = v3;
-        p_item = item; p_n = g_n;
-        item += g_n;
+        if (DBG != 2 && lane == 0) mbar_arrive(&sm.empty[st]);  // this warp is done reading the stage
     }
-    flush_prev();
+    if (dirty) flush();
     bar_sync(1, kConsumerThreads);
 }
 
@@ -461,15 +546,23 @@ __device__ __forceinline__ EpiPre gemv_epilogue_prefetch(const GemvArgs& a, cons
     return p;
 }
 
-// consumers, epilogue: fixed-order sum of the superchunk partials, scale, fused tail op
-__device__ __forceinline__ void gemv_epilogue(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, float sumx, const float* resid,
-                                              const PhaseCtx& ctx, const EpiPre& pre, int tid, int lane) {
+// consumers, epilogue: combine the digit sums exactly, scale once, fused tail op
+// Returns this thread's contribution to the XStats of the output (EPI_RESIDUAL / EPI_SWIGLU / EPI_RELU / EPI_STORE).
+__device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, float s_x, const float* resid,
+                                                const PhaseCtx& ctx, const EpiPre& pre, int tid, int lane) {
+    XStats out_st{0.f, 0.f};
     const QLayout& L = a.L;
-    const int ncols = slab.ncols, nsc = L.nsc;
-    auto colsum = [&](int c) -> float {
-        float acc = 0.f;
-        for (int s = 0; s < nsc; ++s) acc += sm.part[s * ncols + c];
-        return acc;
+    const int ncols = slab.ncols;
+    long long sxf = 0;
+#pragma unroll
+    for (int i = 0; i < kConsumerWarps; ++i) sxf += sm.sxf[i];
+    const long long offterm = (long long)a.woff * sxf;
+    const double sx = (double)s_x, dsxf = (double)sxf;
+    // y = cs * s_x * (sum_k u_k xf_k - off * sum xf + zt * sum xf)
+    auto colval = [&](int c, float cs, float zt) -> float {
+        const int* p = sm.acc + c * 3;
+        const long long t = ((long long)p[2] << 16) + ((long long)p[1] << 8) + (long long)p[0] - offterm;
+        return (float)(((double)t + (double)zt * dsxf) * (sx * (double)cs));
     };
     if (a.epi == EPI_SWIGLU || a.epi == EPI_QKV) {
         for (int pc = tid; pc < ncols / 2; pc += kConsumerThreads) {  // column pairs
@@ -479,10 +572,12 @@ __device__ __forceinline__ void gemv_epilogue(const GemvArgs& a, const Slab& sla
             const float cs0 = first ? pre.cs0 : a.colscale[n0], cs1 = first ? pre.cs1 : a.colscale[n0 + 1];
             const float zt0 = first ? pre.zt0 : (a.colzterm ? a.colzterm[n0] : 0.f);
             const float zt1 = first ? pre.zt1 : (a.colzterm ? a.colzterm[n0 + 1] : 0.f);
-            const float y0 = cs0 * fmaf(zt0, sumx, colsum(2 * pc)), y1 = cs1 * fmaf(zt1, sumx, colsum(2 * pc + 1));
+            const float y0 = colval(2 * pc, cs0, zt0), y1 = colval(2 * pc + 1, cs1, zt1);
             if (a.epi == EPI_SWIGLU) {
                 const float sg = y0 / (1.0f + expf(-y0));  // silu(gate), :918
-                a.out[n0 >> 1] = y1 * sg;                   // multiply(up, silu(gate))
+                const float o = y1 * sg;                    // multiply(up, silu(gate))
+                a.out[n0 >> 1] = o;
+                out_st.am = fmaxf(out_st.am, fabsf(o));
             } else {
                 const int H = a.hidden;
                 const int seg = n0 / H, d = n0 - seg * H;
@@ -514,11 +609,16 @@ __device__ __forceinline__ void gemv_epilogue(const GemvArgs& a, const Slab& sla
             const bool first = c == tid;
             const float cs = first ? pre.cs0 : a.colscale[n];
             const float zt = first ? pre.zt0 : (a.colzterm ? a.colzterm[n] : 0.f);
-            float y = cs * fmaf(zt, sumx, colsum(c));
+            float y = colval(c, cs, zt);
             if (a.epi == EPI_RESIDUAL) y = (first ? pre.r0 : ld_act(resid + n, ctx.coherent)) + y;
             else if (a.epi == EPI_RELU) y = fmaxf(y, 0.f);
             a.out[n] = y;
-            if (a.epi == EPI_LOGITS && (y > best)) { best = y; besti = n; }
+            if (a.epi == EPI_LOGITS) {
+                if (y > best) { best = y; besti = n; }
+            } else {
+                out_st.ss = fmaf(y, y, out_st.ss);
+                out_st.am = fmaxf(out_st.am, fabsf(a.next_norm_w ? y * a.next_norm_w[n] : y));
+            }
         }
         if (a.epi == EPI_LOGITS) {
             unsigned long long key = besti == 0x7FFFFFFF ? 0ull : argmax_pack(best, besti);
@@ -530,6 +630,7 @@ __device__ __forceinline__ void gemv_epilogue(const GemvArgs& a, const Slab& sla
             if (lane == 0 && key != 0ull) atomicMax(ctx.key ? ctx.key : a.argmax_key, key);
         }
     }
+    return out_st;
 }
 
 __device__ __forceinline__ void gemv_init_barriers(const GemvSmem& sm, int stages) {
@@ -552,15 +653,15 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const __grid_cons
     uint32_t it = 0;
     if (warp == kConsumerWarps) {
         // the weights do not depend on the previous kernel: start streaming at once
-        if (lane == 0) gemv_produce(a, slab, sm, it);
+        gemv_produce(a, slab, sm, it, lane);
         return;
     }
     pdl_wait_prior_grid();  // x (and resid / pos) come from the previous kernel in the stream
     const PhaseCtx ctx{false, -1, nullptr};
-    const float sumx = gemv_stage_x<BITS>(a, a.x, sm, false, a.colzterm != nullptr, tid, warp, lane);
     const EpiPre pre = gemv_epilogue_prefetch(a, slab, a.resid, ctx, tid);
+    const float s_x = gemv_stage_x<BITS>(a, a.x, sm, slab, false, tid, warp, lane);
     gemv_consume<BITS, DBG>(a, slab, sm, it, warp, lane);
-    gemv_epilogue(a, slab, sm, sumx, a.resid, ctx, pre, tid, lane);
+    (void)gemv_epilogue(a, slab, sm, s_x, a.resid, ctx, pre, tid, lane);
 }
 
 }  // namespace tib

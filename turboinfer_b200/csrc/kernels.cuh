@@ -114,6 +114,7 @@ struct PackArgs {
     int nsrc;
     int mode;
     int qtype;       // 0 int8, 1 int4
+    int off4;        // INT4: value added before storing the nibble (8 symmetric, 0 asymmetric)
     int unit_scale;  // 1: colscale = 1 (compat_literal: unscaled integers)
     QLayout L;
     uint8_t* out;
@@ -125,85 +126,91 @@ __device__ __forceinline__ void pack_locate(const PackArgs& a, int n, int& si, i
     si = 0; sc = n;
     while (si < a.nsrc - 1 && sc >= a.src[si].n) { sc -= a.src[si].n; ++si; }
 }
-// grid = P slabs, block = 512 (16 warps mirror the 16 consumer warps)
+// grid = P slabs, block = 512 (16 warps mirror the 16 consumer warps); lane = (column c, k-slice s) like the GEMV
 __global__ void pack_kernel(const PackArgs a) {
     const QLayout& L = a.L;
     const Slab slab = make_slab(L, blockIdx.x);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int my_n = warp_items(slab, warp), first = warp_first_item(slab, warp);
-    // byte offset of every round
-    size_t round_off = 0;
-    int r_cur = 0;
-    for (int idx = 0; idx < my_n; ++idx) {
-        const int r = idx / kItemsPerRound, g = idx % kItemsPerRound;
-        while (r_cur < r) { round_off += (size_t)round_total(slab, r_cur) * kItemBytes; ++r_cur; }
-        const int item = first + idx;
-        const int s = item / slab.ncols, c = item - s * slab.ncols;
-        const int n = slab.col0 + c;
-        int si = 0, sc = 0;
-        float scale = 1.f, zp = 0.f;
-        const bool live = n < L.N;
-        if (live) {
-            pack_locate(a, n, si, sc);
-            scale = a.src[si].sz[0];
-            zp = a.src[si].sz[1];
-        }
-        uint32_t words[4] = {0, 0, 0, 0};
-        const int nj = L.ksc / 128;
-        for (int j = 0; j < nj; ++j)
-            for (int e = 0; e < 4; ++e) {
-                const int k = s * L.ksc + 128 * j + 4 * lane + e;
-                int q = 0;
-                if (live && k < L.K) q = quantize_one(a.src[si].w[(size_t)k * a.src[si].n + sc], a.qtype, scale, zp);
+    const int c = lane & 3, s = lane >> 2;
+    const int nq = warp_quads(slab, warp), fq = warp_first_quad(slab, warp);
+    const int kl = L.kc / 8;  // k per lane per item
+    size_t stage_base = 0;    // byte offset of round r inside the slab
+    for (int r = 0; r < nq; ++r) {
+        const int q = fq + r;
+        const int grp = q / L.nchunks, chunk = q - grp * L.nchunks;
+        const int live = q >= slab.qfull ? slab.nlast : 4;
+        const size_t qoff = stage_base + (size_t)round_warp_offset(slab, r, warp) * kItemBytes;
+        stage_base += (size_t)round_total(slab, r) * kItemBytes;
+        for (int u = 0; u < live; ++u) {
+            const int n = slab.col0 + 4 * (4 * grp + u) + c;
+            int si = 0, sc = 0;
+            float scale = 1.f, zp = 0.f;
+            const bool col_live = n < L.N;
+            if (col_live) {
+                pack_locate(a, n, si, sc);
+                scale = a.src[si].sz[0];
+                zp = a.src[si].sz[1];
+            }
+            uint32_t words[4] = {0, 0, 0, 0};
+            for (int e = 0; e < kl; ++e) {
+                const int k = chunk * L.kc + s * kl + e;
+                int qv = 0;
+                const bool el_live = col_live && k < L.K;
+                if (el_live) qv = quantize_one(a.src[si].w[(size_t)k * a.src[si].n + sc], a.qtype, scale, zp);
+                int word, shift;
+                lane_elem_pos(L.bits, e, word, shift);
                 if (L.bits == 4) {
-                    // symmetric values are stored offset by 8; asymmetric ones (0..15) as they are
-                    const uint32_t u = (uint32_t)((zp == 0.0f || !live) ? q + 8 : q) & 0xFu;
-                    words[j >> 1] |= u << (4 * ((j & 1) * 4 + e));
+                    const int uval = el_live ? qv + a.off4 : a.off4;  // padding stores q = 0
+                    words[word] |= ((uint32_t)uval & 0xFu) << shift;
                 } else {
-                    const uint32_t u = (uint32_t)(q + 128) & 0xFFu;
-                    words[j] |= u << (8 * e);
+                    words[word] |= ((uint32_t)qv & 0xFFu) << shift;
                 }
             }
-        uint8_t* dst = a.out + slab.byte0 + round_off + ((size_t)round_warp_offset(slab, r, warp) + g) * kItemBytes + lane * 16;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
-        if (s == 0 && lane == 0) {
-            // y = scale * (sum x*(u - off) + zterm * sum x):
-            //   INT8 dequant = scale*(q - zp)          -> zterm = -zp
-            //   INT4 dequant = scale*(q + zp); asym u=q -> sum x*(u-8) = sum x*q - 8 sum x -> zterm = zp + 8
-            a.colscale[n] = (live && !a.unit_scale) ? scale : (live ? 1.0f : 0.0f);
-            float zt = 0.f;
-            if (live && zp != 0.0f) zt = a.qtype == 0 ? -zp : zp + 8.0f;
-            if (a.colzterm) a.colzterm[n] = a.unit_scale ? 0.f : zt;
+            uint8_t* dst = a.out + slab.byte0 + qoff + (size_t)u * kItemBytes + lane * 16;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
+            if (chunk == 0 && s == 0) {
+                // y = scale * (sum x*(u - off) + zterm * sum x):
+                //   INT8 dequant = scale*(q - zp), stored q          -> zterm = -zp
+                //   INT4 dequant = scale*(q + zp), stored u = q + off -> zterm = +zp
+                a.colscale[n] = (col_live && !a.unit_scale) ? scale : (col_live ? 1.0f : 0.0f);
+                float zt = 0.f;
+                if (col_live && zp != 0.0f) zt = a.qtype == 0 ? -zp : zp;
+                if (a.colzterm) a.colzterm[n] = a.unit_scale ? 0.f : zt;
+            }
         }
     }
 }
 // inverse of pack for a single-source matrix: q_out[k][n] in the reference's [K,N] int32 order
-__global__ void unpack_kernel(const uint8_t* packed, QLayout L, int stored_offset4, int32_t* q_out) {
+__global__ void unpack_kernel(const uint8_t* packed, QLayout L, int off4, int32_t* q_out) {
     const Slab slab = make_slab(L, blockIdx.x);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int my_n = warp_items(slab, warp), first = warp_first_item(slab, warp);
-    size_t round_off = 0;
-    int r_cur = 0;
-    for (int idx = 0; idx < my_n; ++idx) {
-        const int r = idx / kItemsPerRound, g = idx % kItemsPerRound;
-        while (r_cur < r) { round_off += (size_t)round_total(slab, r_cur) * kItemBytes; ++r_cur; }
-        const int item = first + idx;
-        const int s = item / slab.ncols, c = item - s * slab.ncols;
-        const int n = slab.col0 + c;
-        if (n >= L.N) continue;
-        const uint8_t* src = packed + slab.byte0 + round_off + ((size_t)round_warp_offset(slab, r, warp) + g) * kItemBytes + lane * 16;
-        const uint4 wv = *reinterpret_cast<const uint4*>(src);
-        const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
-        const int nj = L.ksc / 128;
-        for (int j = 0; j < nj; ++j)
-            for (int e = 0; e < 4; ++e) {
-                const int k = s * L.ksc + 128 * j + 4 * lane + e;
+    const int c = lane & 3, s = lane >> 2;
+    const int nq = warp_quads(slab, warp), fq = warp_first_quad(slab, warp);
+    const int kl = L.kc / 8;
+    size_t stage_base = 0;
+    for (int r = 0; r < nq; ++r) {
+        const int q = fq + r;
+        const int grp = q / L.nchunks, chunk = q - grp * L.nchunks;
+        const int live = q >= slab.qfull ? slab.nlast : 4;
+        const size_t qoff = stage_base + (size_t)round_warp_offset(slab, r, warp) * kItemBytes;
+        stage_base += (size_t)round_total(slab, r) * kItemBytes;
+        for (int u = 0; u < live; ++u) {
+            const int n = slab.col0 + 4 * (4 * grp + u) + c;
+            if (n >= L.N) continue;
+            const uint8_t* src = packed + slab.byte0 + qoff + (size_t)u * kItemBytes + lane * 16;
+            const uint4 wv = *reinterpret_cast<const uint4*>(src);
+            const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
+            for (int e = 0; e < kl; ++e) {
+                const int k = chunk * L.kc + s * kl + e;
                 if (k >= L.K) continue;
-                int q;
-                if (L.bits == 4) q = (int)((words[j >> 1] >> (4 * ((j & 1) * 4 + e))) & 0xFu) - stored_offset4;
-                else q = (int)((words[j] >> (8 * e)) & 0xFFu) - 128;
-                q_out[(size_t)k * L.N + n] = q;
+                int word, shift;
+                lane_elem_pos(L.bits, e, word, shift);
+                int qv;
+                if (L.bits == 4) qv = (int)((words[word] >> shift) & 0xFu) - off4;
+                else qv = (int)(int8_t)((words[word] >> shift) & 0xFFu);
+                q_out[(size_t)k * L.N + n] = qv;
             }
+        }
     }
 }
 
@@ -381,6 +388,28 @@ __global__ void embed_kernel(const float* emb, const StepState* st, float* x, in
     const int tok = st->token;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H; i += gridDim.x * blockDim.x)
         x[i] = literal ? 0.1f * (float)(i % 100) : emb[(size_t)tok * H + i];
+}
+
+// XStats of every embedding row against the norm weight of the first GEMV (gemv.cuh XStats): one block per row
+__global__ void emb_stats_kernel(const float* emb, const float* norm_w, XStats* out, int H) {
+    __shared__ float red[64];
+    const float* e = emb + (size_t)blockIdx.x * H;
+    float ss = 0.f, am = 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        const float v = e[i];
+        ss = fmaf(v, v, ss);
+        am = fmaxf(am, fabsf(norm_w ? v * norm_w[i] : v));
+    }
+    ss = warp_sum(ss);
+    am = warp_max(am);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[warp] = ss; red[32 + warp] = am; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f, a = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s += red[i]; a = fmaxf(a, red[32 + i]); }
+        out[blockIdx.x] = XStats{s, a};
+    }
 }
 
 struct StepIO {

@@ -18,6 +18,7 @@
 namespace tib {
 
 enum MegaPhaseType : int { PH_GEMV = 0, PH_ATTN = 1 };
+constexpr int kStampsPerPhase = 12;  // debug timeline: 6 phase-level stamps + 6 inside the prologue
 enum MegaSrc : int { SRC_PTR = 0, SRC_EMB = 1 };
 
 struct MegaPhase {
@@ -29,8 +30,18 @@ struct MegaPhase {
     AttnArgs at;
 };
 
+// What the producer warp needs of a phase, compact enough for a lane to hold a whole record in registers: the
+// producer runs AHEAD of the consumers, so it must never wait on a chain of dependent global loads per phase.
+struct ProdRec {
+    unsigned long long wq;   // packed weights
+    QLayout L;
+    int flags;               // bit 0: GEMV phase, bit 1: lm_head (only on sampling steps)
+};
+static_assert(sizeof(ProdRec) == 40, "ProdRec is shuffled as 10 words");
+
 struct MegaArgs {
     const MegaPhase* __restrict__ phases;
+    const ProdRec* __restrict__ prod;   // [nphases]
     int nphases;
     const float* emb;     // [V][H]
     int H, V;
@@ -46,13 +57,14 @@ struct MegaArgs {
     unsigned long long* keys;     // [2] argmax keys, zeroed by the host before every launch
     float* logits;
     int stages;
-    int max_kpad, max_items, attn_floats;
+    int max_kpad, max_units, attn_floats;
     long long* dbg;   // optional: CTA 0 writes 6 clock64 stamps per phase of step 0 (debug timeline)
+    float4* stats;            // [2][gridDim.x][2]: per-CTA partial statistics (32-byte slots) of the phase's output, by phase parity
+    const XStats* emb_stats;  // [V]: statistics of every embedding row (against the first norm weight)
 };
 
-TIB_HD size_t mega_smem_bytes(int stages, int max_kpad, int max_items, int attn_floats) {
-    return (size_t)stages * kStageBytes + (size_t)max_kpad * 4 + (size_t)max_items * 4 + 32 * 4 + (size_t)attn_floats * 4 +
-           (size_t)2 * kMaxStages * 8 + 16 + 128 + ((sizeof(MegaPhase) + 15) & ~size_t(15));
+TIB_HD size_t mega_smem_bytes(int stages, int max_kpad, int max_units, int attn_floats) {
+    return gemv_smem_bytes_for(stages, max_kpad, max_units) + 16 + (size_t)attn_floats * 4 + 16 + ((sizeof(MegaPhase) + 15) & ~size_t(15));
 }
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -97,8 +109,10 @@ TIB_HD int attn_scratch_floats(int D, int nt) {
 }
 
 // Computes the (m, l, o) partial of head h over tokens [t0, t1) and stores it.  q / K / V are read through L2.
+// Returns the thread's max |value written to a.out| (direct items only).
 template <int NT>
-__device__ __forceinline__ void attn_item(const AttnArgs& a, int h, int j, int t0, int t1, float* sm, bool direct = false) {
+__device__ __forceinline__ float attn_item(const AttnArgs& a, int h, int j, int t0, int t1, float* sm, bool direct = false) {
+    float out_am = 0.f;
     float* qs = sm;
     float* sc = qs + a.D;
     float* red = sc + kAttnTokBlock;
@@ -175,23 +189,29 @@ __device__ __forceinline__ void attn_item(const AttnArgs& a, int h, int j, int t
             float acc = 0.f;
             for (int g = 0; g < groups; ++g) acc += ored[g * D + d0];
             po[d0] = acc;
+            if (direct) out_am = fabsf(acc);
         }
     } else {
 #pragma unroll
         for (int i = 0; i < kMaxDims; ++i) {
             const int d = d0 + i * NT;
-            if (d < D) po[d] = o[i];
+            if (d < D) {
+                po[d] = o[i];
+                if (direct) out_am = fmaxf(out_am, fabsf(o[i]));
+            }
         }
     }
     if (tid == 0 && !direct) {
         a.part_ml[((size_t)h * a.max_splits + j) * 2 + 0] = m_run;
         a.part_ml[((size_t)h * a.max_splits + j) * 2 + 1] = l_run;
     }
+    return out_am;
 }
 
 // merge the nsplit partials of head h (fixed order, independent of which CTA does it)
 template <int NT>
-__device__ __forceinline__ void attn_merge_head(const AttnArgs& a, int h, int nsplit) {
+__device__ __forceinline__ float attn_merge_head(const AttnArgs& a, int h, int nsplit) {
+    float out_am = 0.f;
     const float* ml = a.part_ml + (size_t)h * a.max_splits * 2;
     float M = -INFINITY;
     for (int j = 0; j < nsplit; ++j) M = fmaxf(M, __ldcg(ml + 2 * j));
@@ -201,8 +221,11 @@ __device__ __forceinline__ void attn_merge_head(const AttnArgs& a, int h, int ns
         float acc = 0.f;
         for (int j = 0; j < nsplit; ++j)
             acc = fmaf(__ldcg(a.part_o + ((size_t)h * a.max_splits + j) * a.D + d), expf(__ldcg(ml + 2 * j) - M), acc);
-        a.out[h * a.D + d] = acc / Lsum;
+        const float o = acc / Lsum;
+        a.out[h * a.D + d] = o;
+        out_am = fmaxf(out_am, fabsf(o));
     }
+    return out_am;
 }
 
 // stand-alone launches (TensorEngine::attention_fast_incremental / multi_head_attention entry points, per-op engine)
@@ -213,20 +236,21 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnAr
     attn_split_range(t, a.max_splits, a.min_chunk, nsplit, chunk);
     const int j = blockIdx.y;
     if (j >= nsplit) return;
-    attn_item<kAttnThreads>(a, blockIdx.x, j, j * chunk, min(t, (j + 1) * chunk), attn_dyn_smem, nsplit == 1);
+    (void)attn_item<kAttnThreads>(a, blockIdx.x, j, j * chunk, min(t, (j + 1) * chunk), attn_dyn_smem, nsplit == 1);
 }
 __global__ void __launch_bounds__(kAttnThreads) attn_combine_kernel(const AttnArgs a) {
     const int t = *a.pos_ptr + a.t_bias;
     int nsplit, chunk;
     attn_split_range(t, a.max_splits, a.min_chunk, nsplit, chunk);
     if (nsplit == 1) return;  // attn_partial_kernel wrote the output directly
-    attn_merge_head<kAttnThreads>(a, blockIdx.x, nsplit);
+    (void)attn_merge_head<kAttnThreads>(a, blockIdx.x, nsplit);
 }
 
 // the attention phase of the persistent kernel: (head, split) items dealt round-robin to the CTAs; the CTA that
 // completes the last split of a head merges that head's partials (no extra grid barrier, deterministic result)
-__device__ __forceinline__ void mega_attention(const AttnArgs& a, int t, unsigned int* head_cnt, float* sm) {
+__device__ __forceinline__ float mega_attention(const AttnArgs& a, int t, unsigned int* head_cnt, float* sm) {
     constexpr int NT = kConsumerThreads;
+    float out_am = 0.f;
     int nsplit, chunk;
     attn_split_range(t, a.max_splits, a.min_chunk, nsplit, chunk);
     const int items = a.heads * nsplit;
@@ -235,11 +259,11 @@ __device__ __forceinline__ void mega_attention(const AttnArgs& a, int t, unsigne
         const int h = i / nsplit, j = i - h * nsplit;
         const int t0 = j * chunk, t1 = min(t, t0 + chunk);
         if (nsplit == 1) {  // short context: one CTA per head does everything, no partials / counters / merge
-            attn_item<NT>(a, h, 0, 0, t, sm, true);
+            out_am = fmaxf(out_am, attn_item<NT>(a, h, 0, 0, t, sm, true));
             bar_sync(1, NT);
             continue;
         }
-        attn_item<NT>(a, h, j, t0, t1, sm);
+        (void)attn_item<NT>(a, h, j, t0, t1, sm);
         __threadfence();
         bar_sync(1, NT);
         if (threadIdx.x == 0) {
@@ -249,14 +273,15 @@ __device__ __forceinline__ void mega_attention(const AttnArgs& a, int t, unsigne
             __threadfence();
         }
         bar_sync(1, NT);
-        if (*flag) attn_merge_head<NT>(a, h, nsplit);
+        if (*flag) out_am = fmaxf(out_am, attn_merge_head<NT>(a, h, nsplit));
         bar_sync(1, NT);
     }
+    return out_am;
 }
 
 // Registers: more than 16 warps put 5 on an SM sub-partition, which caps a uniform allocation at 96 per thread.  The
-// kernel is compiled for 96 (__maxnreg__); the producer warpgroup then shrinks to 24 and the four consumer warpgroups
-// grow to 112 (the pool is the CTA's launch allocation: 640 x 96 >= 512 x 112 + 128 x 24).  setmaxnreg is a
+// kernel is compiled for 96 (__maxnreg__); the producer warpgroup then shrinks to 56 and the four consumer warpgroups
+// grow to 104 (the pool is the CTA's launch allocation: 640 x 96 >= 512 x 104 + 128 x 56).  setmaxnreg is a
 // warpgroup-wide instruction, so the producer warp comes with three idle siblings (warps 17..19) that only execute
 // the shrink and exit: the CTA has 20 warps.
 constexpr int kMegaThreads = (kConsumerWarps + 4) * 32;  // 640
@@ -264,23 +289,13 @@ template <int BITS>
 __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaArgs m) {
     extern __shared__ uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // carve: ring | xs | part | red | attention scratch | mbarriers
-    GemvSmem sm;
-    uintptr_t p = (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127);
-    sm.ring = reinterpret_cast<uint8_t*>(p);
-    p += (size_t)m.stages * kStageBytes;
-    sm.xs = reinterpret_cast<float*>(p);
-    p += (size_t)m.max_kpad * 4;
-    sm.part = reinterpret_cast<float*>(p);
-    p += (size_t)m.max_items * 4;
-    sm.red = reinterpret_cast<float*>(p);
-    p += 32 * 4;
+    // carve: ring | x digits | column sums | reduction scratch | mbarriers | attention scratch | phase descriptor
+    uint8_t* tail = nullptr;
+    const GemvSmem sm = gemv_carve_for(smem_raw, m.stages, m.max_kpad, m.max_units, &tail);
+    uintptr_t p = (reinterpret_cast<uintptr_t>(tail) + 15) & ~uintptr_t(15);
     float* attn_sm = reinterpret_cast<float*>(p);
     p += (size_t)m.attn_floats * 4;
     p = (p + 15) & ~uintptr_t(15);
-    sm.full = reinterpret_cast<uint64_t*>(p);
-    sm.empty = sm.full + kMaxStages;
-    p += (size_t)2 * kMaxStages * 8;
     MegaPhase* sph = reinterpret_cast<MegaPhase*>(p);  // this phase's descriptor, staged by the consumers
     if (tid == 0) gemv_init_barriers(sm, m.stages);
     __syncthreads();
@@ -290,16 +305,42 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
 
     if (warp >= kConsumerWarps) {
         // ===== producer warpgroup: warp 16 streams every GEMV phase of every step, back to back =====
-        reg_dealloc<24>();
-        if (warp == kConsumerWarps && lane == 0) {
+        reg_dealloc<56>();
+        if (warp == kConsumerWarps) {
+            // lane l holds the record of phase base + l; the next block of 32 is fetched while this one is streamed
+            auto fetch = [&](int base, uint32_t (&r)[10]) {
+                const int ph = base + lane;
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(m.prod + (ph < m.nphases ? ph : 0));
+#pragma unroll
+                for (int i = 0; i < 10; ++i) r[i] = __ldg(src + i);
+                if (ph >= m.nphases) r[9] = 0;
+            };
+            uint32_t cur[10], nxt[10];
+            fetch(0, cur);
             for (int s = 0; s < m.n_steps; ++s) {
                 const bool sample = s >= m.first_sample;
-                for (int ph = 0; ph < m.nphases; ++ph) {
-                    const MegaPhase& P = m.phases[ph];
-                    if (P.type != PH_GEMV || (P.is_head && !sample)) continue;
-                    if ((int)blockIdx.x >= P.g.L.P) continue;
-                    const Slab slab = make_slab(P.g.L, blockIdx.x);
-                    gemv_produce(P.g, slab, sm, it);
+                for (int base = 0; base < m.nphases; base += 32) {
+                    const int nb = base + 32 < m.nphases ? base + 32 : 0;  // wraps to the next step's first block
+                    fetch(nb, nxt);
+                    const int cnt = min(32, m.nphases - base);
+                    for (int j = 0; j < cnt; ++j) {
+                        uint32_t f[10];
+#pragma unroll
+                        for (int i = 0; i < 10; ++i) f[i] = __shfl_sync(0xffffffffu, cur[i], j);
+                        const int flags = (int)f[9];
+                        if (!(flags & 1) || ((flags & 2) && !sample)) continue;
+                        QLayout L;
+                        L.K = (int)f[2]; L.N = (int)f[3]; L.bits = (int)f[4]; L.kc = (int)f[5]; L.nchunks = (int)f[6]; L.U = (int)f[7]; L.P = (int)f[8];
+                        if ((int)blockIdx.x >= L.P) continue;
+                        GemvArgs g;
+                        g.wq = reinterpret_cast<const uint8_t*>(((unsigned long long)f[1] << 32) | f[0]);
+                        g.L = L;
+                        g.stages = m.stages;
+                        const Slab slab = make_slab(L, blockIdx.x);
+                        gemv_produce(g, slab, sm, it, lane);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) cur[i] = nxt[i];
                 }
             }
         }
@@ -307,14 +348,51 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
     }
 
     // ===== consumers =====
-    reg_alloc<112>();
+    reg_alloc<104>();
     unsigned int bar_target = 0;
     bool need_wait = false;
-    auto grid_arrive = [&]() {
+    // ends a phase: publishes this CTA's partial statistics of the phase's output, then arrives on the grid barrier
+    auto grid_arrive = [&](int ph, XStats st) {
+        st.ss = warp_sum(st.ss);
+        st.am = warp_max(st.am);
+        if (lane == 0) { sm.red[32 + warp] = st.ss; sm.red[48 + warp] = st.am; }
         bar_sync(1, kConsumerThreads);  // every consumer thread's stores are ordered before thread 0's release
-        if (tid == 0) red_release_add(m.grid_bar, 1u);
+        if (warp == 0) {
+            // a whole 32-byte sector per CTA (a partial-sector write would have L2 fetch the rest from HBM first), in a
+            // buffer small enough to stay L2-resident: two copies, alternating with the phase
+            float ss = 0.f, am = 0.f;
+#pragma unroll
+            for (int i = 0; i < kConsumerWarps; ++i) { ss += sm.red[32 + i]; am = fmaxf(am, sm.red[48 + i]); }
+            float* slot = reinterpret_cast<float*>(m.stats + ((size_t)(ph & 1) * gridDim.x + blockIdx.x) * 2);
+            if (lane < 8) slot[lane] = lane == 0 ? ss : (lane == 1 ? am : 0.f);
+            __syncwarp();
+            if (lane == 0) red_release_add(m.grid_bar, 1u);
+        }
         bar_target += gridDim.x;
         need_wait = true;
+    };
+    // combines the per-CTA partials of phase `ph` in CTA order.  ONE warp per CTA reads them (thousands of warps asking
+    // for the same ten cache lines at once serialise in the L2 slice: measured 2 us) and hands the result to the
+    // others through shared memory; same loads and same addition tree in every CTA, so the bits are identical.
+    auto gather_stats = [&](int ph) -> XStats {
+        if (warp == 0) {
+            const float4* p = m.stats + (size_t)(ph & 1) * gridDim.x * 2;
+            constexpr int kMaxPer = 8;  // grids up to 256 CTAs
+            float2 v[kMaxPer];
+#pragma unroll
+            for (int j = 0; j < kMaxPer; ++j) {  // all loads in flight before the first use
+                const int i = lane + 32 * j;
+                v[j] = i < (int)gridDim.x ? __ldcg(reinterpret_cast<const float2*>(p + 2 * i)) : make_float2(0.f, 0.f);
+            }
+            float ss = 0.f, am = 0.f;
+#pragma unroll
+            for (int j = 0; j < kMaxPer; ++j) { ss += v[j].x; am = fmaxf(am, v[j].y); }
+            ss = warp_sum(ss);
+            am = warp_max(am);
+            if (lane == 0) { sm.red[0] = ss; sm.red[1] = am; }
+        }
+        bar_sync(1, kConsumerThreads);
+        return XStats{sm.red[0], sm.red[1]};
     };
     auto grid_wait = [&]() {
         if (!need_wait) return;
@@ -357,7 +435,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
             const bool is_head = ph == m.nphases - 1;  // the lm_head is always the last phase
             if (is_head && !sample) continue;
             const bool stamp = m.dbg != nullptr && s == 0 && blockIdx.x == 0 && tid == 0;
-            long long* ts = m.dbg + (size_t)ph * 6;
+            long long* ts = m.dbg + (size_t)ph * kStampsPerPhase;
             if (stamp) ts[0] = clock64();
             // Everything that does not depend on the previous phase's output happens BEFORE the grid barrier:
             // stage the phase descriptor in shared memory, fetch the epilogue's per-column constants.
@@ -380,21 +458,33 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
             if (need_wait) grid_wait(); else bar_sync(1, kConsumerThreads);
             const MegaPhase& P = *sph;
             if (stamp) { ts[1] = clock64(); ts[2] = ts[1]; ts[3] = ts[1]; }
+            XStats out_st{0.f, 0.f};
             if (P.type == PH_GEMV) {
                 if (gemv_here) {
-                    const float* x = P.x_src == SRC_EMB ? m.emb + (size_t)token * m.H : P.g.x;
+                    const bool from_emb = P.x_src == SRC_EMB;
+                    const float* x = from_emb ? m.emb + (size_t)token * m.H : P.g.x;
                     const GemvArgs& g = P.g;
-                    const float sumx = gemv_stage_x<BITS>(g, x, sm, P.x_src != SRC_EMB, g.colzterm != nullptr, tid, warp, lane);
-                    if (stamp) ts[2] = clock64();
+                    const XStats in_st = from_emb ? m.emb_stats[token] : gather_stats(ph - 1);
+                    if (stamp) ts[6] = clock64();
+                    const float s_x = gemv_stage_x_known<BITS>(g, x, sm, slab, !from_emb, in_st, tid, lane, stamp ? ts + 7 : nullptr);
+                    if (stamp) {
+                        ts[2] = clock64();
+                        int ready = 0;  // stages of this phase already in shared memory when its main loop starts
+                        for (int i = 0; i < m.stages && i < slab.rounds; ++i) {
+                            const uint32_t ii = it + i;
+                            ready += mbar_try_wait(&sm.full[ii % m.stages], (ii / m.stages) & 1) ? 1 : 0;
+                        }
+                        ts[11] = ready;
+                    }
                     gemv_consume<BITS>(g, slab, sm, it, warp, lane);
                     if (stamp) ts[3] = clock64();
-                    gemv_epilogue(g, slab, sm, sumx, resid, ctx, pre, tid, lane);
+                    out_st = gemv_epilogue(g, slab, sm, s_x, resid, ctx, pre, tid, lane);
                 }
             } else {
-                mega_attention(P.at, pos + 1, m.head_cnt, attn_sm);
+                out_st.am = mega_attention(P.at, pos + 1, m.head_cnt, attn_sm);
             }
             if (stamp) ts[4] = clock64();
-            grid_arrive();
+            grid_arrive(ph, out_st);
             if (stamp) ts[5] = clock64();
         }
     }

@@ -122,4 +122,11 @@ __device__ __forceinline__ uint4 lds128(const void* p) {
     return v;
 }
 
+// same, from a 32-bit shared-window address computed once (saves the generic->shared conversion per load)
+__device__ __forceinline__ uint4 lds128s(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+
 }  // namespace tib
