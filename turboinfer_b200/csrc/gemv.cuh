@@ -23,7 +23,7 @@
 //     reduction  lanes (column c, k-slice s): 3 shuffle steps over s per run of items of one unit, then one shared-
 //                memory integer atomic per (column, digit)
 //   epilogue                    per column: y = colscale * s_x * (A2*65536 + A1*256 + A0 - off*sum(xf) [+ zero-point
-//                               term]) evaluated in int64 / fp64 and rounded once, then the fused residual / SwiGLU /
+//                               term]); the integer part is exact (int64), then three fp32 roundings; fused residual / SwiGLU /
 //                               ReLU / RoPE+KV-append / logits+argmax
 // Accuracy: the only approximation is the 24-bit quantisation of x relative to max|x| (absolute error <= 2^-24 max|x|
 // per element, i.e. what an fp32 mantissa holds for the largest elements); products and sums are exact.  Measured
@@ -38,7 +38,7 @@ namespace tib {
 constexpr int kGemvThreads = (kConsumerWarps + 1) * 32;  // 544
 constexpr int kConsumerThreads = kConsumerWarps * 32;    // 512
 constexpr int kMaxStages = 6;
-constexpr float kXQMax = 8388000.0f;   // bound of |xf|: below 2^23 - 256 so that rounding can never reach 2^23
+constexpr float kXQMax = 8388000.0f;   // bound of |xf|: (1 + 2e-5) * 8388000 + 0.5 < 2^23, so rounding never reaches 2^23
 constexpr int kXCache = 8;             // float4 vectors of x a thread keeps in registers between the two prologue passes
 
 enum GemvEpilogue : int {
@@ -181,8 +181,9 @@ struct GemvSmem {
     uint8_t* ring;      // stages * 32 KiB
     uint8_t* xd;        // digit planes of x: 3 * kpad bytes
     int* acc;           // [ncols][3] integer column sums
-    float* red;         // 64 floats of reduction scratch
+    float* red;         // 128 floats of reduction scratch
     long long* sxf;     // [16] per-warp partial sums of xf over k
+    unsigned long long* keyred;  // [16] per-warp argmax keys (dataflow engine)
     uint64_t* full;     // [stages]
     uint64_t* empty;    // [stages]
 };
@@ -191,7 +192,7 @@ TIB_HD size_t gemv_smem_bytes_for(int stages, int kpad, int max_units) {
     size_t b = (size_t)stages * kStageBytes;
     b += (size_t)3 * kpad;
     b += (size_t)max_units * 4 * 3 * 4;
-    b += 64 * 4 + 16 * 8;
+    b += 128 * 4 + 32 * 8;
     b += (size_t)2 * kMaxStages * 8;
     return b + 128;
 }
@@ -207,8 +208,10 @@ __device__ __forceinline__ GemvSmem gemv_carve_for(uint8_t* base, int stages, in
     s.acc = reinterpret_cast<int*>(p);
     p += (size_t)max_units * 4 * 3 * 4;
     s.red = reinterpret_cast<float*>(p);
-    p += 64 * 4;
+    p += 128 * 4;
     s.sxf = reinterpret_cast<long long*>(p);
+    p += 16 * 8;
+    s.keyred = reinterpret_cast<unsigned long long*>(p);
     p += 16 * 8;
     s.full = reinterpret_cast<uint64_t*>(p);
     s.empty = s.full + kMaxStages;
@@ -229,6 +232,12 @@ struct PhaseCtx {
     bool coherent;   // activations were produced by other CTAs of the same launch: read them through L2
     int pos;         // cache position of the current token (EPI_QKV); < 0: read *pos_ptr
     unsigned long long* key;  // EPI_LOGITS: argmax key to use instead of GemvArgs::argmax_key (nullptr: keep)
+    // dataflow engine (mega_ll.cuh): activations travel as LL words (ptx.cuh); 0 = plain floats
+    uint32_t ll_epoch;        // epoch to stamp on this phase's outputs; `out` / `resid` then point at llword arrays
+    llword* knew_ll;          // EPI_QKV: the current token's K and V rows, for the attention phase that follows
+    llword* vnew_ll;
+    unsigned long long* keyred;  // EPI_LOGITS: per-warp best keys go to this shared-memory array instead of an atomic
+    bool resid_plain;         // the residual input is plain floats (embedding row) even though the output is LL
 };
 
 // producer (the whole warp): stream this CTA's slab through the ring.  `it` counts stages over the whole launch.
@@ -375,46 +384,66 @@ __device__ __forceinline__ float gemv_stage_x(const GemvArgs& a, const float* x,
     return s_x;
 }
 
-// Single-pass prologue for callers that already know sum(x^2) and the bound of max|x*w| (persistent kernel).
-template <int BITS>
+// Single-pass prologue for callers that can obtain sum(x^2) and the bound of max|x*w| without reading x (persistent
+// kernel: the phase that produced x left per-CTA partials).  The first batch of x / norm-weight loads is issued BEFORE
+// get_stats() is called, so the statistics' round trip to L2 overlaps the data's.
+// x_ll != nullptr (dataflow engine): x arrives as LL words stamped `ep`; each load is verified and re-tried.
+template <int BITS, typename StatsFn>
 __device__ __forceinline__ float gemv_stage_x_known(const GemvArgs& a, const float* x, const GemvSmem& sm, const Slab& slab, bool coherent,
-                                                    XStats st, int tid, int lane, long long* dbg = nullptr) {
+                                                    StatsFn&& get_stats, int tid, int lane, long long* dbg = nullptr,
+                                                    const llword* x_ll = nullptr, uint32_t ep = 0) {
     const QLayout& L = a.L;
     const int K = L.K, kpad = layout_kpad(L);
     const float* nw = a.norm_w;
     const bool vec = (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(nw)) & 15) == 0;
-    const int nvec = kpad >> 2;
+    const int nvec = kpad >> 2, kvec = K >> 2;
     for (int i = tid; i < slab.ncols * 3; i += kConsumerThreads) sm.acc[i] = 0;
-    float rms = 1.f, amax = st.am;
-    if (nw != nullptr) {
-        rms = sqrtf(st.ss / (float)K + a.rms_eps);  // :1501
-        amax = __fdividef(amax, rms) * 1.00001f;     // a bound, not a result: the fast division is fine
-    }
-    const bool finite = amax > 0.f && amax < INFINITY;
-    const float inv_s = finite ? __fdividef(kXQMax, amax) : 0.f;  // |y * inv_s| <= kXQMax * (1 + 1e-6) either way
-    const float s_x = finite ? amax * (1.0f / kXQMax) : 0.f;
-    if (dbg) dbg[0] = clock64();
-    long long sxf = 0;
     constexpr int B = 4;  // float4 loads in flight per thread
-    for (int v0 = tid; v0 < nvec; v0 += B * kConsumerThreads) {
-        float4 xv[B], wv[B];
+    float4 xv[B], wv[B];
+    bool okv[B] = {true, true, true, true};
+    auto issue = [&](int v0) {
 #pragma unroll
         for (int i = 0; i < B; ++i) {
             const int v = v0 + i * kConsumerThreads;
-            xv[i] = v < nvec ? ld_x4(x, v, K, vec, coherent) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (x_ll != nullptr) xv[i] = v < kvec ? ll_try4(x_ll + 4 * v, ep, okv[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            else xv[i] = v < nvec ? ld_x4(x, v, K, vec, coherent) : make_float4(0.f, 0.f, 0.f, 0.f);
             wv[i] = (nw != nullptr && v < nvec) ? ld_x4(nw, v, K, vec, false) : make_float4(1.f, 1.f, 1.f, 1.f);
         }
-        if (dbg) { dbg[1] = clock64(); if (xv[0].x == 1.2345e-30f) dbg[2] = 1; dbg[2] = clock64(); }
+    };
+    issue(tid);
+    if (dbg) dbg[0] = clock64();
+    const XStats st = get_stats();
+    if (dbg) dbg[1] = clock64();
+    float inv_rms = 1.f, amax = st.am;
+    if (nw != nullptr) {
+        inv_rms = rsqrtf(st.ss / (float)K + a.rms_eps);  // :1501
+        amax = amax * inv_rms * 1.00001f;                 // a bound of max|y|, y = x * inv_rms * w
+    }
+    const bool finite = amax > 0.f && amax < INFINITY;
+    const float inv_s = finite ? __fdividef(kXQMax, amax) : 0.f;  // |y * inv_s| <= kXQMax * (1 + 2e-5) < 2^23
+    const float s_x = finite ? amax * (1.0f / kXQMax) : 0.f;
+    long long sxf = 0;
+    for (int v0 = tid; v0 < nvec; v0 += B * kConsumerThreads) {
+        if (v0 != tid) issue(v0);
+        if (x_ll != nullptr) {   // all loads of the batch were issued before this first check; stragglers spin
+#pragma unroll
+            for (int i = 0; i < B; ++i) {
+                const int v = v0 + i * kConsumerThreads;
+                if (v < kvec && !okv[i]) xv[i] = ll_wait4(x_ll + 4 * v, ep);
+            }
+        }
 #pragma unroll
         for (int i = 0; i < B; ++i) {
             const int v = v0 + i * kConsumerThreads;
             if (v < nvec) {
                 float4 t = xv[i];
                 if (nw != nullptr) {
-                    t.x = (t.x / rms) * wv[i].x;  // :1504-1506, same two roundings
-                    t.y = (t.y / rms) * wv[i].y;
-                    t.z = (t.z / rms) * wv[i].z;
-                    t.w = (t.w / rms) * wv[i].w;
+                    // the reference divides by rms (:1504-1506); multiplying by the reciprocal differs by ~1 ulp, far
+                    // below the 2^-24 max|y| granularity of the fixed-point conversion that follows
+                    t.x = (t.x * inv_rms) * wv[i].x;
+                    t.y = (t.y * inv_rms) * wv[i].y;
+                    t.z = (t.z * inv_rms) * wv[i].z;
+                    t.w = (t.w * inv_rms) * wv[i].w;
                 }
                 x_store_digits<BITS>(sm.xd, v, t, inv_s, sxf);
             }
@@ -423,9 +452,9 @@ __device__ __forceinline__ float gemv_stage_x_known(const GemvArgs& a, const flo
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sxf += __shfl_xor_sync(0xffffffffu, sxf, o);
     if (lane == 0) sm.sxf[tid >> 5] = sxf;
-    if (dbg) dbg[3] = clock64();
+    if (dbg) dbg[2] = clock64();
     bar_sync(1, kConsumerThreads);
-    if (dbg) dbg[4] = clock64();
+    if (dbg) dbg[3] = clock64();
     return s_x;
 }
 
@@ -536,7 +565,8 @@ __device__ __forceinline__ EpiPre gemv_epilogue_prefetch(const GemvArgs& a, cons
             p.cs1 = a.colscale[n + 1];
             if (a.colzterm) p.zt1 = a.colzterm[n + 1];
         }
-        if (a.epi == EPI_RESIDUAL) p.r0 = ld_act(resid + n, ctx.coherent);
+        if (a.epi == EPI_RESIDUAL)
+            p.r0 = (ctx.ll_epoch && !ctx.resid_plain) ? ll_value(ll_load(reinterpret_cast<const llword*>(resid) + n)) : ld_act(resid + n, ctx.coherent);
         if (a.epi == EPI_QKV) {
             const int pos = ctx.pos >= 0 ? ctx.pos : *a.pos_ptr;
             p.page = a.page_table[pos / a.page_tokens];
@@ -557,12 +587,18 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
 #pragma unroll
     for (int i = 0; i < kConsumerWarps; ++i) sxf += sm.sxf[i];
     const long long offterm = (long long)a.woff * sxf;
-    const double sx = (double)s_x, dsxf = (double)sxf;
+    const float fsxf = (float)sxf;
+    const uint32_t ep = ctx.ll_epoch;
+    llword* const out_ll = reinterpret_cast<llword*>(a.out);
+    const llword* const resid_ll = reinterpret_cast<const llword*>(resid);
     // y = cs * s_x * (sum_k u_k xf_k - off * sum xf + zt * sum xf)
     auto colval = [&](int c, float cs, float zt) -> float {
         const int* p = sm.acc + c * 3;
         const long long t = ((long long)p[2] << 16) + ((long long)p[1] << 8) + (long long)p[0] - offterm;
-        return (float)(((double)t + (double)zt * dsxf) * (sx * (double)cs));
+        // |t| < 2^47: hi * 2^23 + lo with both parts exact in fp32, so tf is the correctly rounded t (no fp64 needed)
+        const int hi = (int)(t >> 23), lo = (int)(t & 0x7FFFFF);
+        const float tf = fmaf((float)hi, 8388608.0f, (float)lo);
+        return (fmaf(zt, fsxf, tf) * s_x) * cs;
     };
     if (a.epi == EPI_SWIGLU || a.epi == EPI_QKV) {
         for (int pc = tid; pc < ncols / 2; pc += kConsumerThreads) {  // column pairs
@@ -576,7 +612,8 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
             if (a.epi == EPI_SWIGLU) {
                 const float sg = y0 / (1.0f + expf(-y0));  // silu(gate), :918
                 const float o = y1 * sg;                    // multiply(up, silu(gate))
-                a.out[n0 >> 1] = o;
+                if (ep) ll_store_f(out_ll + (n0 >> 1), o, ep);
+                else a.out[n0 >> 1] = o;
                 out_st.am = fmaxf(out_st.am, fabsf(o));
             } else {
                 const int H = a.hidden;
@@ -591,12 +628,18 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
                     o1 = __fadd_rn(__fmul_rn(y0, sn), __fmul_rn(y1, cs));
                 }
                 if (seg == 0) {
-                    *reinterpret_cast<float2*>(a.out + d) = make_float2(o0, o1);
+                    if (ep) { ll_store_f(out_ll + d, o0, ep); ll_store_f(out_ll + d + 1, o1, ep); }
+                    else *reinterpret_cast<float2*>(a.out + d) = make_float2(o0, o1);
                 } else {
                     const int page = first ? pre.page : a.page_table[pos / a.page_tokens];
                     const size_t off = ((size_t)page * a.page_tokens + (pos % a.page_tokens)) * H + d;
                     float* dst = seg == 1 ? a.k_pool : a.v_pool;
                     *reinterpret_cast<float2*>(dst + off) = make_float2(o0, o1);
+                    if (ep) {  // this step's attention reads the new row from here, later steps from the cache
+                        llword* nl = (seg == 1 ? ctx.knew_ll : ctx.vnew_ll) + d;
+                        ll_store_f(nl, o0, ep);
+                        ll_store_f(nl + 1, o1, ep);
+                    }
                 }
             }
         }
@@ -610,9 +653,10 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
             const float cs = first ? pre.cs0 : a.colscale[n];
             const float zt = first ? pre.zt0 : (a.colzterm ? a.colzterm[n] : 0.f);
             float y = colval(c, cs, zt);
-            if (a.epi == EPI_RESIDUAL) y = (first ? pre.r0 : ld_act(resid + n, ctx.coherent)) + y;
+            if (a.epi == EPI_RESIDUAL) y = (first ? pre.r0 : ((ep && !ctx.resid_plain) ? ll_value(ll_load(resid_ll + n)) : ld_act(resid + n, ctx.coherent))) + y;
             else if (a.epi == EPI_RELU) y = fmaxf(y, 0.f);
-            a.out[n] = y;
+            if (ep && a.epi != EPI_LOGITS) ll_store_f(out_ll + n, y, ep);
+            else a.out[n] = y;
             if (a.epi == EPI_LOGITS) {
                 if (y > best) { best = y; besti = n; }
             } else {
@@ -627,7 +671,8 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
                 const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
                 key = other > key ? other : key;
             }
-            if (lane == 0 && key != 0ull) atomicMax(ctx.key ? ctx.key : a.argmax_key, key);
+            if (ctx.keyred) { if (lane == 0) ctx.keyred[tid >> 5] = key; }
+            else if (lane == 0 && key != 0ull) atomicMax(ctx.key ? ctx.key : a.argmax_key, key);
         }
     }
     return out_st;
@@ -657,7 +702,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const __grid_cons
         return;
     }
     pdl_wait_prior_grid();  // x (and resid / pos) come from the previous kernel in the stream
-    const PhaseCtx ctx{false, -1, nullptr};
+    const PhaseCtx ctx{false, -1, nullptr, 0u, nullptr, nullptr, nullptr, false};
     const EpiPre pre = gemv_epilogue_prefetch(a, slab, a.resid, ctx, tid);
     const float s_x = gemv_stage_x<BITS>(a, a.x, sm, slab, false, tid, warp, lane);
     gemv_consume<BITS, DBG>(a, slab, sm, it, warp, lane);

@@ -103,9 +103,12 @@ __device__ __forceinline__ float nt_max(float v, float* red) {
     return s;
 }
 
+TIB_HD int attn_fast_scratch_floats(int nt);
 TIB_HD int attn_scratch_floats(int D, int nt) {
     const int groups = D < nt ? nt / D : 1;
-    return D + kAttnTokBlock + 32 + groups * D + 4;
+    const int generic = D + kAttnTokBlock + 32 + groups * D + 4;
+    const int fast = D <= 128 ? attn_fast_scratch_floats(nt) + 4 : 0;   // + the merge flag of mega_attention
+    return generic > fast ? generic : fast;
 }
 
 // Computes the (m, l, o) partial of head h over tokens [t0, t1) and stores it.  q / K / V are read through L2.
@@ -208,6 +211,110 @@ __device__ __forceinline__ float attn_item(const AttnArgs& a, int h, int j, int 
     return out_am;
 }
 
+// Low-latency item for head dims <= 128 (every Llama-family shape): a warp owns whole tokens, a lane owns 4 dims.
+// Each warp issues the K AND V row loads of 4 tokens at once (they do not depend on q or on the scores), so a short
+// context costs one memory round trip; scores are warp-shuffle dot products, the softmax is "online" per warp, and the
+// 16 warps' (m, l, o) are merged through shared memory in warp order (deterministic).  Same arithmetic as
+// attention_fast_incremental (:1254-1388) up to the order of the fp32 sums; expf is the full-precision one.
+TIB_HD int attn_fast_scratch_floats(int nt) { return (nt / 32) * (128 + 2); }
+template <int NT>
+__device__ __forceinline__ float attn_item_fast(const AttnArgs& a, int h, int j, int t0, int t1, float* sm, bool direct) {
+    constexpr int NW = NT / 32, G = 4;
+    float* wm = sm;                 // [NW]
+    float* wl = wm + NW;            // [NW]
+    float* wo = wl + NW;            // [NW][128]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int D = a.D, hoff = h * D;
+    const bool lane_on = 4 * lane < D;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // the first group's K / V loads go out before q is needed
+    float4 kv[G], vv[G];
+    auto issue = [&](int tbase) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int t = tbase + g * NW;
+            if (t < t1 && lane_on) {
+                const size_t row = (size_t)hoff + 4 * lane;
+                kv[g] = __ldcg(reinterpret_cast<const float4*>(kv_row(a.k_pool, a.page_table, a.page_tokens, a.H, t) + row));
+                vv[g] = __ldcg(reinterpret_cast<const float4*>(kv_row(a.v_pool, a.page_table, a.page_tokens, a.H, t) + row));
+            } else {
+                kv[g] = zero4;
+                vv[g] = zero4;
+            }
+        }
+    };
+    issue(t0 + warp);
+    const float4 q = lane_on ? __ldcg(reinterpret_cast<const float4*>(a.q + hoff + 4 * lane)) : zero4;
+    float m_run = -INFINITY, l_run = 0.f;
+    float4 o = zero4;
+    for (int tbase = t0 + warp; tbase < t1; tbase += G * NW) {
+        if (tbase != t0 + warp) issue(tbase);
+        float s[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            float d = q.x * kv[g].x;
+            d = fmaf(q.y, kv[g].y, d);
+            d = fmaf(q.z, kv[g].z, d);
+            d = fmaf(q.w, kv[g].w, d);
+            s[g] = d;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) s[g] += __shfl_xor_sync(0xffffffffu, s[g], off);
+        }
+        float mx = m_run;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            s[g] = tbase + g * NW < t1 ? s[g] * a.scale : -INFINITY;
+            mx = fmaxf(mx, s[g]);
+        }
+        const float corr = expf(m_run - mx);   // first group: exp(-inf) = 0
+        l_run *= corr;
+        o.x *= corr; o.y *= corr; o.z *= corr; o.w *= corr;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const float p = expf(s[g] - mx);     // masked tokens: exp(-inf) = 0
+            l_run += p;
+            o.x = fmaf(p, vv[g].x, o.x);
+            o.y = fmaf(p, vv[g].y, o.y);
+            o.z = fmaf(p, vv[g].z, o.z);
+            o.w = fmaf(p, vv[g].w, o.w);
+        }
+        m_run = mx;
+    }
+    // merge the warps (a warp without tokens has m = -inf, l = 0, o = 0)
+    if (lane == 0) { wm[warp] = m_run; wl[warp] = l_run; }
+    *reinterpret_cast<float4*>(wo + warp * 128 + 4 * lane) = o;
+    bar_sync(1, NT);
+    float out_am = 0.f;
+    if (tid < D) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) M = fmaxf(M, wm[w]);
+        float Lsum = 0.f, acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const float f = wm[w] == -INFINITY ? 0.f : expf(wm[w] - M);
+            Lsum = fmaf(wl[w], f, Lsum);
+            acc = fmaf(wo[w * 128 + tid], f, acc);
+        }
+        if (direct) {
+            const float r = acc / Lsum;
+            a.out[hoff + tid] = r;
+            out_am = fabsf(r);
+        } else {
+            a.part_o[((size_t)h * a.max_splits + j) * D + tid] = acc;
+            if (tid == 0) {
+                a.part_ml[((size_t)h * a.max_splits + j) * 2 + 0] = M;
+                a.part_ml[((size_t)h * a.max_splits + j) * 2 + 1] = Lsum;
+            }
+        }
+    }
+    bar_sync(1, NT);   // the scratch is reused by the next item
+    return out_am;
+}
+
 // merge the nsplit partials of head h (fixed order, independent of which CTA does it)
 template <int NT>
 __device__ __forceinline__ float attn_merge_head(const AttnArgs& a, int h, int nsplit) {
@@ -236,7 +343,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnAr
     attn_split_range(t, a.max_splits, a.min_chunk, nsplit, chunk);
     const int j = blockIdx.y;
     if (j >= nsplit) return;
-    (void)attn_item<kAttnThreads>(a, blockIdx.x, j, j * chunk, min(t, (j + 1) * chunk), attn_dyn_smem, nsplit == 1);
+    if (a.D <= 128) (void)attn_item_fast<kAttnThreads>(a, blockIdx.x, j, j * chunk, min(t, (j + 1) * chunk), attn_dyn_smem, nsplit == 1);
+    else (void)attn_item<kAttnThreads>(a, blockIdx.x, j, j * chunk, min(t, (j + 1) * chunk), attn_dyn_smem, nsplit == 1);
 }
 __global__ void __launch_bounds__(kAttnThreads) attn_combine_kernel(const AttnArgs a) {
     const int t = *a.pos_ptr + a.t_bias;
@@ -258,12 +366,14 @@ __device__ __forceinline__ float mega_attention(const AttnArgs& a, int t, unsign
     for (int i = blockIdx.x; i < items; i += gridDim.x) {
         const int h = i / nsplit, j = i - h * nsplit;
         const int t0 = j * chunk, t1 = min(t, t0 + chunk);
+        const bool fast = a.D <= 128;
         if (nsplit == 1) {  // short context: one CTA per head does everything, no partials / counters / merge
-            out_am = fmaxf(out_am, attn_item<NT>(a, h, 0, 0, t, sm, true));
+            out_am = fmaxf(out_am, fast ? attn_item_fast<NT>(a, h, 0, 0, t, sm, true) : attn_item<NT>(a, h, 0, 0, t, sm, true));
             bar_sync(1, NT);
             continue;
         }
-        (void)attn_item<NT>(a, h, j, t0, t1, sm);
+        if (fast) (void)attn_item_fast<NT>(a, h, j, t0, t1, sm, false);
+        else (void)attn_item<NT>(a, h, j, t0, t1, sm);
         __threadfence();
         bar_sync(1, NT);
         if (threadIdx.x == 0) {
@@ -446,7 +556,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                 for (int i = tid; i < (int)(sizeof(MegaPhase) / 4); i += kConsumerThreads) dst[i] = src[i];
             }
             const bool gemv_here = PG.type == PH_GEMV && (int)blockIdx.x < PG.g.L.P;
-            const PhaseCtx ctx{true, pos, is_head ? &m.keys[s & 1] : nullptr};
+            const PhaseCtx ctx{true, pos, is_head ? &m.keys[s & 1] : nullptr, 0u, nullptr, nullptr, nullptr, false};
             Slab slab{};
             EpiPre pre{};
             const float* resid = nullptr;
@@ -464,9 +574,9 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                     const bool from_emb = P.x_src == SRC_EMB;
                     const float* x = from_emb ? m.emb + (size_t)token * m.H : P.g.x;
                     const GemvArgs& g = P.g;
-                    const XStats in_st = from_emb ? m.emb_stats[token] : gather_stats(ph - 1);
                     if (stamp) ts[6] = clock64();
-                    const float s_x = gemv_stage_x_known<BITS>(g, x, sm, slab, !from_emb, in_st, tid, lane, stamp ? ts + 7 : nullptr);
+                    auto stats_fn = [&]() -> XStats { return from_emb ? m.emb_stats[token] : gather_stats(ph - 1); };
+                    const float s_x = gemv_stage_x_known<BITS>(g, x, sm, slab, !from_emb, stats_fn, tid, lane, stamp ? ts + 7 : nullptr);
                     if (stamp) {
                         ts[2] = clock64();
                         int ready = 0;  // stages of this phase already in shared memory when its main loop starts
