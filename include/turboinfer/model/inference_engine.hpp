@@ -1,0 +1,73 @@
+// turboinfer/model/inference_engine.hpp -- InferenceEngine of the B200 build (reference include/turboinfer/model/
+// inference_engine.hpp:25-372): weights are quantized, packed and uploaded once at construction; generate() runs the
+// persistent decode kernel.  Greedy (top_k = 1) is sampled on the device; other settings sample on the host from
+// downloaded logits (temperature -> top-k -> softmax -> top-p -> inverse CDF, like sample_next_token :1554-1673).
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../core/tensor_engine.hpp"
+#include "model_loader.hpp"
+
+namespace turboinfer {
+namespace model {
+
+struct InferenceConfig {
+    size_t max_sequence_length = 2048;
+    size_t max_batch_size = 32;
+    float temperature = 1.0f;
+    float top_p = 0.9f;
+    size_t top_k = 50;
+    float length_penalty = 1.0f;
+    int eos_token_id = 2;          // generate() stops on token 2 regardless, like the reference (:760)
+    bool use_cache = true;
+    core::ComputeDevice device = core::ComputeDevice::kAuto;
+};
+
+struct GenerationResult {
+    std::vector<int> tokens;
+    std::vector<float> logprobs;
+    float total_time_ms = 0.f;
+    float tokens_per_second = 0.f;
+    bool finished = false;
+    std::string stop_reason;
+};
+
+class InferenceEngine {
+public:
+    explicit InferenceEngine(const ModelData& model_data, const InferenceConfig& config = InferenceConfig{});
+    ~InferenceEngine();
+    InferenceEngine(const InferenceEngine&) = delete;
+    InferenceEngine& operator=(const InferenceEngine&) = delete;
+    InferenceEngine(InferenceEngine&&) noexcept;
+    InferenceEngine& operator=(InferenceEngine&&) noexcept;
+
+    const ModelMetadata& model_metadata() const noexcept { return model_metadata_; }
+    const InferenceConfig& config() const noexcept { return config_; }
+    void set_config(const InferenceConfig& config) { config_ = config; }
+
+    GenerationResult generate(const std::vector<int>& input_tokens, size_t max_new_tokens, bool include_logprobs = false);
+    std::vector<GenerationResult> generate_batch(const std::vector<std::vector<int>>& input_tokens_batch, size_t max_new_tokens,
+                                                 bool include_logprobs = false);
+    void reset_state();
+    size_t memory_usage() const;
+    std::string performance_stats() const;
+
+    // exposed for tests (private in the reference, :248-255): one incremental forward pass, logits [1, 1, vocab]
+    core::Tensor forward_pass_incremental(const std::vector<int>& tokens);
+
+private:
+    void validate_input_tokens(const std::vector<int>& tokens) const;
+    int sample_next_token(const float* logits, std::vector<float>* logprobs);
+
+    ModelMetadata model_metadata_;
+    InferenceConfig config_;
+    uint64_t handle_ = 0;
+    struct Stats;
+    std::unique_ptr<Stats> stats_;
+};
+
+}  // namespace model
+}  // namespace turboinfer

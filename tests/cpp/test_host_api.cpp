@@ -1,0 +1,248 @@
+// test_host_api.cpp -- the C++ class surface of the B200 build, written the way the reference's own tests are
+// (stand-alone main(), hand-rolled checks; tests/test_tensor.cpp, tests/test_quantization_complete.cpp,
+// tests/test_inference_engine.cpp of the reference).  `cpu` mode needs no GPU: host value types and the loud failure
+// of every device entry point.  `gpu` mode runs the ops, the quantizer fixtures and a small decoder on cuda:0.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "turboinfer/core/tensor_engine.hpp"
+#include "turboinfer/model/inference_engine.hpp"
+#include "turboinfer/optimize/quantization.hpp"
+
+using namespace turboinfer;
+using core::DataType;
+using core::Tensor;
+using core::TensorShape;
+
+static int g_failed = 0;
+#define CHECK(cond) do { if (!(cond)) { std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); ++g_failed; } } while (0)
+#define CHECK_THROWS(expr, type) do { bool ok_ = false; try { (void)(expr); } catch (const type&) { ok_ = true; } catch (...) {} \
+    if (!ok_) { std::printf("FAIL %s:%d  %s did not throw %s\n", __FILE__, __LINE__, #expr, #type); ++g_failed; } } while (0)
+
+static Tensor ramp(std::initializer_list<size_t> dims, float a, float b) {
+    Tensor t{TensorShape(dims)};
+    float* p = t.data_ptr<float>();
+    for (size_t i = 0; i < t.shape().total_size(); ++i) p[i] = a * (float)(i % 97) + b;
+    return t;
+}
+
+static void test_host_types() {
+    Tensor t{TensorShape({2, 3, 4})};
+    CHECK(t.shape().ndim() == 3 && t.shape().total_size() == 24 && t.byte_size() == 96 && !t.empty());
+    for (size_t i = 0; i < 24; ++i) CHECK(t.data_ptr<float>()[i] == 0.0f);            // zero-initialised
+    CHECK_THROWS(t.shape().size(3), std::out_of_range);
+    CHECK_THROWS(t.data_ptr<int8_t>(), std::runtime_error);                             // sizeof check only
+    (void)t.data_ptr<int32_t>();                                                        // same size: allowed, like the reference
+    for (size_t i = 0; i < 24; ++i) t.data_ptr<float>()[i] = (float)i;
+    Tensor r = t.reshape(TensorShape({6, 4}));
+    r.data_ptr<float>()[0] = 99.f;
+    CHECK(t.data_ptr<float>()[0] == 0.f);                                               // deep copy
+    CHECK_THROWS(t.reshape(TensorShape({5, 5})), std::runtime_error);
+    Tensor s = t.slice({0, 1, 1}, {2, 3, 3});
+    CHECK(s.shape().dimensions() == (std::vector<size_t>{2, 2, 2}));
+    CHECK(s.data_ptr<float>()[0] == 5.f && s.data_ptr<float>()[1] == 6.f && s.data_ptr<float>()[2] == 9.f && s.data_ptr<float>()[7] == 22.f);
+    Tensor c = t;
+    c.fill<float>(1.f);
+    CHECK(t.data_ptr<float>()[5] == 5.f && c.data_ptr<float>()[5] == 1.f);
+    CHECK(core::get_dtype_size(DataType::kInt8) == 1 && std::string(core::dtype_to_string(DataType::kInt32)) == "int32");
+    Tensor q{TensorShape({4}), DataType::kInt8};
+    CHECK(q.byte_size() == 4);
+    CHECK(optimize::get_quantization_bits(optimize::QuantizationType::kInt4) == 4);
+}
+
+static void test_no_cpu_fallback(bool have_gpu) {
+    CHECK_THROWS(core::TensorEngine(core::ComputeDevice::kCPU), std::runtime_error);
+    if (!have_gpu) {
+        CHECK_THROWS(core::TensorEngine(core::ComputeDevice::kAuto), std::runtime_error);  // no device: fail loudly
+        optimize::Quantizer qz;
+        CHECK_THROWS(qz.quantize_tensor(ramp({4, 4}, 0.1f, -1.f)), std::runtime_error);
+        model::ModelData md;
+        md.metadata().vocab_size = 8; md.metadata().hidden_size = 8; md.metadata().num_layers = 0; md.metadata().num_heads = 1;
+        CHECK_THROWS(model::InferenceEngine(md), std::runtime_error);
+    }
+}
+
+static void test_ops_gpu() {
+    core::TensorEngine eng(core::ComputeDevice::kGPU);
+    CHECK(eng.gpu_available());
+    CHECK(eng.device_info().find("B200") != std::string::npos || !eng.device_info().empty());
+    Tensor a = ramp({3, 40}, 0.01f, -0.3f), b = ramp({3, 40}, -0.02f, 0.5f);
+    Tensor s = eng.add(a, b), m = eng.multiply(a, b), r = eng.relu(a), si = eng.silu(a), sc = eng.scale(a, 2.5f);
+    for (size_t i = 0; i < 120; ++i) {
+        const float x = a.data_ptr<float>()[i], y = b.data_ptr<float>()[i];
+        CHECK(s.data_ptr<float>()[i] == x + y);
+        CHECK(m.data_ptr<float>()[i] == x * y);
+        CHECK(r.data_ptr<float>()[i] == std::fmax(0.f, x));
+        CHECK(std::fabs(si.data_ptr<float>()[i] - x / (1.0f + std::exp(-x))) <= 1e-6f);
+        CHECK(sc.data_ptr<float>()[i] == x * 2.5f);
+    }
+    CHECK_THROWS(eng.add(a, ramp({2, 40}, 1.f, 0.f)), std::runtime_error);
+    // matmul [M,K].[K,N] and [B,T,K].[K,N]; integer weights are promoted without scale
+    Tensor x = ramp({2, 3, 64}, 0.01f, -0.2f), w = ramp({64, 48}, -0.003f, 0.1f);
+    Tensor y = eng.matmul(x, w);
+    CHECK(y.shape().dimensions() == (std::vector<size_t>{2, 3, 48}));
+    double worst = 0, scale = 0;
+    for (size_t i = 0; i < 6; ++i)
+        for (size_t n = 0; n < 48; ++n) {
+            double acc = 0;
+            for (size_t k = 0; k < 64; ++k) acc += (double)x.data_ptr<float>()[i * 64 + k] * w.data_ptr<float>()[k * 48 + n];
+            worst = std::fmax(worst, std::fabs(acc - y.data_ptr<float>()[i * 48 + n]));
+            scale = std::fmax(scale, std::fabs(acc));
+        }
+    CHECK(worst <= 1e-5 * scale);
+    Tensor wi{TensorShape({64, 48}), DataType::kInt8};
+    for (size_t i = 0; i < 64 * 48; ++i) wi.data_ptr<int8_t>()[i] = (int8_t)((int)(i % 15) - 7);
+    Tensor yi = eng.matmul(x.reshape(TensorShape({6, 64})), wi);
+    double acc0 = 0;
+    for (size_t k = 0; k < 64; ++k) acc0 += (double)x.data_ptr<float>()[k] * (double)((int)((k * 48) % 15) - 7);
+    CHECK(std::fabs(acc0 - yi.data_ptr<float>()[0]) <= 1e-4 * (1.0 + std::fabs(acc0)));
+    CHECK_THROWS(eng.matmul(x, ramp({63, 48}, 1.f, 0.f)), std::runtime_error);
+    // softmax rows sum to one; rms_norm of a constant row
+    Tensor p = eng.softmax(ramp({4, 10}, 0.3f, -1.f));
+    for (size_t rr = 0; rr < 4; ++rr) {
+        float sum = 0;
+        for (size_t i = 0; i < 10; ++i) sum += p.data_ptr<float>()[rr * 10 + i];
+        CHECK(std::fabs(sum - 1.0f) <= 1e-5f);
+    }
+    Tensor ones{TensorShape({32})};
+    ones.fill<float>(1.f);
+    Tensor cst{TensorShape({2, 32})};
+    cst.fill<float>(3.f);
+    Tensor nrm = eng.rms_norm(cst, ones);
+    CHECK(std::fabs(nrm.data_ptr<float>()[5] - 3.f / std::sqrt(9.f + 1e-5f)) <= 1e-6f);
+    // attention over t identical keys: the output is the mean of the values = the value
+    Tensor q = ramp({1, 1, 64}, 0.01f, 0.f), kk{TensorShape({1, 5, 64})}, vv{TensorShape({1, 5, 64})};
+    for (size_t t = 0; t < 5; ++t)
+        for (size_t h = 0; h < 64; ++h) { kk.data_ptr<float>()[t * 64 + h] = 0.1f; vv.data_ptr<float>()[t * 64 + h] = (float)h; }
+    Tensor o1 = eng.attention_fast_incremental(q, kk, vv), o4 = eng.multi_head_attention(q, kk, vv, 4);
+    for (size_t h = 0; h < 64; ++h) { CHECK(std::fabs(o1.data_ptr<float>()[h] - (float)h) <= 1e-4f); CHECK(std::fabs(o4.data_ptr<float>()[h] - (float)h) <= 1e-4f); }
+    // RoPE at position 0 is the identity; pairs keep their norm at other positions
+    Tensor xr = ramp({1, 2, 8}, 0.1f, 0.05f), pos{TensorShape({2})};
+    pos.data_ptr<float>()[0] = 0.f; pos.data_ptr<float>()[1] = 3.f;
+    Tensor ro = eng.apply_rope(xr, pos);
+    for (size_t i = 0; i < 8; ++i) CHECK(std::fabs(ro.data_ptr<float>()[i] - xr.data_ptr<float>()[i]) <= 1e-6f);
+    for (size_t i = 0; i < 4; ++i) {
+        const float* a0 = xr.data_ptr<float>() + 8 + 2 * i; const float* b0 = ro.data_ptr<float>() + 8 + 2 * i;
+        CHECK(std::fabs((a0[0] * a0[0] + a0[1] * a0[1]) - (b0[0] * b0[0] + b0[1] * b0[1])) <= 1e-5f);
+    }
+    CHECK_THROWS(eng.gelu(a), std::runtime_error);
+}
+
+static void test_quantizer_gpu() {
+    // the reference's own fixtures (tests/test_quantization_complete.cpp:26-29, :88-91, :141-144): round trip error < scale
+    struct Fx { optimize::QuantizationType type; bool sym; float lo, hi; int n; };
+    const Fx fx[] = {{optimize::QuantizationType::kInt8, true, -10.f, 10.f, 16}, {optimize::QuantizationType::kInt4, true, -2.f, 2.f, 9},
+                     {optimize::QuantizationType::kInt8, false, 1.f, 6.f, 6}};
+    for (const Fx& f : fx) {
+        Tensor x{TensorShape({(size_t)f.n})};
+        for (int i = 0; i < f.n; ++i) x.data_ptr<float>()[i] = f.lo + (f.hi - f.lo) * (float)i / (float)(f.n - 1);
+        optimize::QuantizationConfig cfg;
+        cfg.type = f.type;
+        cfg.symmetric = f.sym;
+        optimize::Quantizer qz(cfg);
+        optimize::QuantizationInfo info = qz.calculate_quantization_info(x);
+        CHECK(info.scales.size() == 1 && info.scales[0] > 0.f);
+        if (f.sym) CHECK(info.zero_points[0] == 0.f);
+        Tensor q = qz.quantize_tensor(x);
+        CHECK(q.dtype() == (f.type == optimize::QuantizationType::kInt8 ? DataType::kInt8 : DataType::kInt32));
+        Tensor d = qz.dequantize_tensor(q, info);
+        for (int i = 0; i < f.n; ++i) CHECK(std::fabs(d.data_ptr<float>()[i] - x.data_ptr<float>()[i]) <= info.scales[0]);
+        if (f.type == optimize::QuantizationType::kInt4 && f.sym) {   // scale = max|x| / 7, q = round-half-away(x / scale)
+            CHECK(info.scales[0] == 2.0f / 7.0f);
+            CHECK(q.data_ptr<int32_t>()[0] == -7 && q.data_ptr<int32_t>()[8] == 7 && q.data_ptr<int32_t>()[4] == 0);
+        }
+    }
+}
+
+static model::ModelData small_model(const char* quant) {
+    model::ModelData md;
+    auto& m = md.metadata();
+    m.name = "cpp-test"; m.architecture = "llama"; m.vocab_size = 96; m.hidden_size = 64; m.num_layers = 2; m.num_heads = 4;
+    m.intermediate_size = 128; m.rope_theta = 10000.f;
+    m.extra_params["b200.quantization"] = quant;
+    uint32_t st = 12345u;
+    auto rnd = [&](float amp) { st = st * 1664525u + 1013904223u; return ((float)(st >> 8) / 8388608.0f - 1.0f) * amp; };
+    auto mat = [&](size_t r, size_t c, float amp) {
+        Tensor t{TensorShape({r, c})};
+        for (size_t i = 0; i < r * c; ++i) t.data_ptr<float>()[i] = rnd(amp);
+        return t;
+    };
+    auto vec1 = [&](size_t n) {
+        Tensor t{TensorShape({n})};
+        for (size_t i = 0; i < n; ++i) t.data_ptr<float>()[i] = 1.0f + rnd(0.1f);
+        return t;
+    };
+    md.add_tensor("token_embeddings.weight", mat(96, 64, 0.1f));
+    md.add_tensor("lm_head.weight", mat(64, 96, 0.125f));
+    md.add_tensor("norm.weight", vec1(64));
+    for (int l = 0; l < 2; ++l) {
+        const std::string p = "layers." + std::to_string(l) + ".";
+        for (const char* n : {"attention.q_proj.weight", "attention.k_proj.weight", "attention.v_proj.weight", "attention.o_proj.weight"})
+            md.add_tensor(p + n, mat(64, 64, 0.125f));
+        md.add_tensor(p + "feed_forward.w1.weight", mat(64, 128, 0.125f));
+        md.add_tensor(p + "feed_forward.w3.weight", mat(64, 128, 0.125f));
+        md.add_tensor(p + "feed_forward.w2.weight", mat(128, 64, 0.09f));
+        md.add_tensor(p + "attention_norm.weight", vec1(64));
+        md.add_tensor(p + "ffn_norm.weight", vec1(64));
+    }
+    md.add_tensor("some.unrelated.tensor", mat(2, 2, 1.f));   // ignored, like the reference ignores unknown names
+    return md;
+}
+
+static void test_engine_gpu() {
+    for (const char* quant : {"int8", "int4"}) {
+        model::InferenceConfig cfg;
+        cfg.top_k = 1;   // greedy
+        cfg.max_sequence_length = 64;
+        model::InferenceEngine eng(small_model(quant), cfg);
+        const std::vector<int> prompt = {1, 15, 25, 35};   // benchmark_inference.cpp:331
+        model::GenerationResult a = eng.generate(prompt, 12), b = eng.generate(prompt, 12, true);
+        CHECK(a.tokens.size() <= prompt.size() + 12 && a.tokens.size() > prompt.size());
+        CHECK(a.tokens == b.tokens);                                       // deterministic
+        CHECK(b.logprobs.size() == b.tokens.size() - prompt.size());
+        for (float lp : b.logprobs) CHECK(lp <= 0.f);
+        CHECK(a.stop_reason == "max_new_tokens" || a.stop_reason == "eos_token");
+        // the one-call device loop and the step-by-step path agree token for token
+        eng.reset_state();
+        std::vector<int> seq = prompt;
+        Tensor lg = eng.forward_pass_incremental(prompt);
+        for (size_t i = prompt.size(); i < a.tokens.size(); ++i) {
+            const float* row = lg.data_ptr<float>() + (lg.shape().size(1) - 1) * 96;
+            int best = 0;
+            for (int v = 1; v < 96; ++v) if (row[v] > row[best]) best = v;
+            CHECK(best == a.tokens[i]);
+            seq.push_back(best);
+            if (i + 1 < a.tokens.size()) lg = eng.forward_pass_incremental({best});
+        }
+        CHECK_THROWS(eng.generate({}, 4), std::runtime_error);
+        CHECK_THROWS(eng.generate(std::vector<int>(65, 1), 4), std::runtime_error);
+        model::GenerationResult longrun = eng.generate(prompt, 1000);      // stops at max_sequence_length (or EOS)
+        CHECK(longrun.tokens.size() <= 64 && longrun.finished);
+        cfg.top_k = 5;
+        cfg.temperature = 0.8f;
+        eng.set_config(cfg);
+        model::GenerationResult smp = eng.generate(prompt, 6, true);       // host-side sampling path
+        CHECK(smp.tokens.size() > prompt.size() && smp.logprobs.size() == smp.tokens.size() - prompt.size());
+        auto batch = eng.generate_batch({prompt, {3, 4}}, 3);
+        CHECK(batch.size() == 2);
+        CHECK(eng.memory_usage() > 0 && !eng.performance_stats().empty());
+    }
+    model::ModelData bad = small_model("int8");
+    bad.add_tensor("layers.0.attention.q_proj.weight", Tensor{TensorShape({64, 64}), DataType::kInt8});
+    CHECK_THROWS(model::InferenceEngine(bad), std::runtime_error);
+}
+
+int main(int argc, char** argv) {
+    const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
+    test_host_types();
+    test_no_cpu_fallback(gpu);
+    if (gpu) {
+        test_ops_gpu();
+        test_quantizer_gpu();
+        test_engine_gpu();
+    }
+    std::printf("%s: %d check(s) failed\n", gpu ? "gpu" : "cpu", g_failed);
+    return g_failed == 0 ? 0 : 1;
+}

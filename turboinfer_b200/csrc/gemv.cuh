@@ -388,10 +388,31 @@ __device__ __forceinline__ float gemv_stage_x(const GemvArgs& a, const float* x,
 // kernel: the phase that produced x left per-CTA partials).  The first batch of x / norm-weight loads is issued BEFORE
 // get_stats() is called, so the statistics' round trip to L2 overlaps the data's.
 // x_ll != nullptr (dataflow engine): x arrives as LL words stamped `ep`; each load is verified and re-tried.
+// The RMSNorm weights of a phase are static: the persistent kernel fetches the thread's first batch BEFORE the grid
+// barrier (they usually come from HBM, not L2) and hands them in.
+struct NormPre {
+    float4 w[4];
+    bool valid;
+};
+__device__ __forceinline__ NormPre gemv_norm_prefetch(const GemvArgs& a, int tid) {
+    NormPre p;
+    p.valid = false;
+    const float* nw = a.norm_w;
+    if (nw == nullptr || (a.L.K & 3) != 0 || (reinterpret_cast<uintptr_t>(nw) & 15) != 0) return p;
+    const int kvec = a.L.K >> 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int v = tid + i * kConsumerThreads;
+        p.w[i] = v < kvec ? __ldg(reinterpret_cast<const float4*>(nw) + v) : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+    p.valid = true;
+    return p;
+}
+
 template <int BITS, typename StatsFn>
 __device__ __forceinline__ float gemv_stage_x_known(const GemvArgs& a, const float* x, const GemvSmem& sm, const Slab& slab, bool coherent,
                                                     StatsFn&& get_stats, int tid, int lane, long long* dbg = nullptr,
-                                                    const llword* x_ll = nullptr, uint32_t ep = 0) {
+                                                    const llword* x_ll = nullptr, uint32_t ep = 0, const NormPre* npre = nullptr) {
     const QLayout& L = a.L;
     const int K = L.K, kpad = layout_kpad(L);
     const float* nw = a.norm_w;
@@ -401,16 +422,17 @@ __device__ __forceinline__ float gemv_stage_x_known(const GemvArgs& a, const flo
     constexpr int B = 4;  // float4 loads in flight per thread
     float4 xv[B], wv[B];
     bool okv[B] = {true, true, true, true};
-    auto issue = [&](int v0) {
+    auto issue = [&](int v0, bool use_pre) {
 #pragma unroll
         for (int i = 0; i < B; ++i) {
             const int v = v0 + i * kConsumerThreads;
             if (x_ll != nullptr) xv[i] = v < kvec ? ll_try4(x_ll + 4 * v, ep, okv[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
             else xv[i] = v < nvec ? ld_x4(x, v, K, vec, coherent) : make_float4(0.f, 0.f, 0.f, 0.f);
-            wv[i] = (nw != nullptr && v < nvec) ? ld_x4(nw, v, K, vec, false) : make_float4(1.f, 1.f, 1.f, 1.f);
+            if (use_pre) wv[i] = npre->w[i];
+            else wv[i] = (nw != nullptr && v < nvec) ? ld_x4(nw, v, K, vec, false) : make_float4(1.f, 1.f, 1.f, 1.f);
         }
     };
-    issue(tid);
+    issue(tid, npre != nullptr && npre->valid);
     if (dbg) dbg[0] = clock64();
     const XStats st = get_stats();
     if (dbg) dbg[1] = clock64();
@@ -424,7 +446,7 @@ __device__ __forceinline__ float gemv_stage_x_known(const GemvArgs& a, const flo
     const float s_x = finite ? amax * (1.0f / kXQMax) : 0.f;
     long long sxf = 0;
     for (int v0 = tid; v0 < nvec; v0 += B * kConsumerThreads) {
-        if (v0 != tid) issue(v0);
+        if (v0 != tid) issue(v0, false);
         if (x_ll != nullptr) {   // all loads of the batch were issued before this first check; stragglers spin
 #pragma unroll
             for (int i = 0; i < B; ++i) {

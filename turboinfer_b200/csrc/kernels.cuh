@@ -216,7 +216,7 @@ __global__ void unpack_kernel(const uint8_t* packed, QLayout L, int off4, int32_
 
 // ---------------------------------------------------------------------------------------------------
 // TensorEngine::matmul on fp32 (src/core/tensor_engine.cpp:490-640) in the reference build's order of roundings
-// (see oracle/ti_oracle.c tio_matmul): thread = output column, k sequential.
+// (its order is pinned by the test-side restatement, function tio_matmul): thread = output column, k sequential.
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float chain_unfused4(const float* a, const float* b, size_t ldb, int k0, int k1, float s) {
     const int kv = k0 + ((k1 - k0) / 4) * 4;

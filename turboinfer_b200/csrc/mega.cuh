@@ -415,42 +415,40 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
 
     if (warp >= kConsumerWarps) {
         // ===== producer warpgroup: warp 16 streams every GEMV phase of every step, back to back =====
-        reg_dealloc<56>();
+        reg_dealloc<40>();
         if (warp == kConsumerWarps) {
-            // lane l holds the record of phase base + l; the next block of 32 is fetched while this one is streamed
-            auto fetch = [&](int base, uint32_t (&r)[10]) {
-                const int ph = base + lane;
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(m.prod + (ph < m.nphases ? ph : 0));
-#pragma unroll
-                for (int i = 0; i < 10; ++i) r[i] = __ldg(src + i);
-                if (ph >= m.nphases) r[9] = 0;
-            };
-            uint32_t cur[10], nxt[10];
-            fetch(0, cur);
+            // lane l holds the record of phase base + l: one latency per 32 phases, then register shuffles only
             for (int s = 0; s < m.n_steps; ++s) {
                 const bool sample = s >= m.first_sample;
                 for (int base = 0; base < m.nphases; base += 32) {
-                    const int nb = base + 32 < m.nphases ? base + 32 : 0;  // wraps to the next step's first block
-                    fetch(nb, nxt);
+                    const int lph = base + lane;
+                    uint32_t cur[10];
+                    {
+                        const uint32_t* src = reinterpret_cast<const uint32_t*>(m.prod + (lph < m.nphases ? lph : 0));
+#pragma unroll
+                        for (int i = 0; i < 10; ++i) cur[i] = __ldg(src + i);
+                        if (lph >= m.nphases) cur[9] = 0;
+                    }
                     const int cnt = min(32, m.nphases - base);
                     for (int j = 0; j < cnt; ++j) {
-                        uint32_t f[10];
-#pragma unroll
-                        for (int i = 0; i < 10; ++i) f[i] = __shfl_sync(0xffffffffu, cur[i], j);
-                        const int flags = (int)f[9];
+                        const int flags = (int)__shfl_sync(0xffffffffu, cur[9], j);
                         if (!(flags & 1) || ((flags & 2) && !sample)) continue;
-                        QLayout L;
-                        L.K = (int)f[2]; L.N = (int)f[3]; L.bits = (int)f[4]; L.kc = (int)f[5]; L.nchunks = (int)f[6]; L.U = (int)f[7]; L.P = (int)f[8];
-                        if ((int)blockIdx.x >= L.P) continue;
                         GemvArgs g;
-                        g.wq = reinterpret_cast<const uint8_t*>(((unsigned long long)f[1] << 32) | f[0]);
-                        g.L = L;
+                        QLayout& L = g.L;
+                        L.K = (int)__shfl_sync(0xffffffffu, cur[2], j);
+                        L.N = (int)__shfl_sync(0xffffffffu, cur[3], j);
+                        L.bits = (int)__shfl_sync(0xffffffffu, cur[4], j);
+                        L.kc = (int)__shfl_sync(0xffffffffu, cur[5], j);
+                        L.nchunks = (int)__shfl_sync(0xffffffffu, cur[6], j);
+                        L.U = (int)__shfl_sync(0xffffffffu, cur[7], j);
+                        L.P = (int)__shfl_sync(0xffffffffu, cur[8], j);
+                        if ((int)blockIdx.x >= L.P) continue;
+                        const uint32_t lo = __shfl_sync(0xffffffffu, cur[0], j), hi = __shfl_sync(0xffffffffu, cur[1], j);
+                        g.wq = reinterpret_cast<const uint8_t*>(((unsigned long long)hi << 32) | lo);
                         g.stages = m.stages;
                         const Slab slab = make_slab(L, blockIdx.x);
                         gemv_produce(g, slab, sm, it, lane);
                     }
-#pragma unroll
-                    for (int i = 0; i < 10; ++i) cur[i] = nxt[i];
                 }
             }
         }
@@ -559,11 +557,14 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
             const PhaseCtx ctx{true, pos, is_head ? &m.keys[s & 1] : nullptr, 0u, nullptr, nullptr, nullptr, false};
             Slab slab{};
             EpiPre pre{};
+            NormPre npre;
+            npre.valid = false;
             const float* resid = nullptr;
             if (gemv_here) {
                 slab = make_slab(PG.g.L, blockIdx.x);
                 resid = PG.resid_src == SRC_EMB ? m.emb + (size_t)token * m.H : PG.g.resid;
                 pre = gemv_epilogue_prefetch(PG.g, slab, resid, ctx, tid);
+                npre = gemv_norm_prefetch(PG.g, tid);
             }
             if (need_wait) grid_wait(); else bar_sync(1, kConsumerThreads);
             const MegaPhase& P = *sph;
@@ -576,7 +577,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                     const GemvArgs& g = P.g;
                     if (stamp) ts[6] = clock64();
                     auto stats_fn = [&]() -> XStats { return from_emb ? m.emb_stats[token] : gather_stats(ph - 1); };
-                    const float s_x = gemv_stage_x_known<BITS>(g, x, sm, slab, !from_emb, stats_fn, tid, lane, stamp ? ts + 7 : nullptr);
+                    const float s_x = gemv_stage_x_known<BITS>(g, x, sm, slab, !from_emb, stats_fn, tid, lane, stamp ? ts + 7 : nullptr, nullptr, 0u, &npre);
                     if (stamp) {
                         ts[2] = clock64();
                         int ready = 0;  // stages of this phase already in shared memory when its main loop starts
