@@ -148,7 +148,18 @@ static void test_quantizer_gpu() {
         Tensor q = qz.quantize_tensor(x);
         CHECK(q.dtype() == (f.type == optimize::QuantizationType::kInt8 ? DataType::kInt8 : DataType::kInt32));
         Tensor d = qz.dequantize_tensor(q, info);
-        for (int i = 0; i < f.n; ++i) CHECK(std::fabs(d.data_ptr<float>()[i] - x.data_ptr<float>()[i]) <= info.scales[0]);
+        if (f.sym) {
+            for (int i = 0; i < f.n; ++i) CHECK(std::fabs(d.data_ptr<float>()[i] - x.data_ptr<float>()[i]) <= info.scales[0]);
+        } else {
+            // the reference's asymmetric INT8 maps [min, max] onto zp .. zp + 255 and then clamps to int8 (:662-674), so the
+            // upper part of the range saturates at 127; the contract here is the reference's formula, not a small error
+            const float sc = info.scales[0], zp = info.zero_points[0];
+            for (int i = 0; i < f.n; ++i) {
+                const float qe = std::fmax(-128.f, std::fmin(127.f, std::round(x.data_ptr<float>()[i] / sc + zp)));
+                CHECK(q.data_ptr<int8_t>()[i] == (int8_t)qe);
+                CHECK(d.data_ptr<float>()[i] == sc * (qe - zp));
+            }
+        }
         if (f.type == optimize::QuantizationType::kInt4 && f.sym) {   // scale = max|x| / 7, q = round-half-away(x / scale)
             CHECK(info.scales[0] == 2.0f / 7.0f);
             CHECK(q.data_ptr<int32_t>()[0] == -7 && q.data_ptr<int32_t>()[8] == 7 && q.data_ptr<int32_t>()[4] == 0);

@@ -564,7 +564,6 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                 slab = make_slab(PG.g.L, blockIdx.x);
                 resid = PG.resid_src == SRC_EMB ? m.emb + (size_t)token * m.H : PG.g.resid;
                 pre = gemv_epilogue_prefetch(PG.g, slab, resid, ctx, tid);
-                npre = gemv_norm_prefetch(PG.g, tid);
             }
             if (need_wait) grid_wait(); else bar_sync(1, kConsumerThreads);
             const MegaPhase& P = *sph;
