@@ -86,6 +86,11 @@ int ti_b200_qweight_free(ti_qweight_t w);
  * ti_b200_attention_decode <- attention_fast_incremental (:1254-1388) when num_heads == 1,
  *                          multi_head_attention with q_len 1 (:1149-1252) otherwise; q [B,1,H], k/v [B,t,H] */
 int ti_b200_gemv_q(ti_qweight_t w, const float* x_host, float* y_host, size_t rows);
+/* ti_b200_gemm_q        <- TensorEngine::matmul with M >= 32 rows, i.e. simd_gemm_float (tensor_engine.cpp:191-255), on the
+ *                          same quantized weight: the prefill / batched-decode contraction on the tcgen05 tensor cores
+ *                          (INT8 digit planes x INT8 / unpacked INT4, exact int32 accumulation in TMEM).  Every output row
+ *                          is bit-identical to ti_b200_gemv_q of that row. */
+int ti_b200_gemm_q(ti_qweight_t w, const float* x_host, float* y_host, size_t rows);
 int ti_b200_matmul_f32(const float* a_host, const float* b_host, float* c_host, size_t M, size_t K, size_t N);
 int ti_b200_rms_norm(const float* x_host, const float* w_host, float* y_host, size_t rows, size_t H, float eps);
 int ti_b200_rope(const float* x_host, const float* pos_host, float* y_host, size_t B, size_t nh, size_t T, size_t D,
@@ -153,6 +158,9 @@ int ti_b200_bench_gemv(const ti_qweight_t* w, size_t n_w, size_t reps, float* ms
  * slot 0 = fused q|k|v, 1 = o_proj, 2 = fused gate/up (or up), 3 = down_proj, 4 = lm_head.
  * alg_bytes_per_launch = K*N*bits/8 + 4*N (scales) + 4*(K + N) (x in, y out), the figure of SURVEY.md 8d. */
 int ti_b200_model_bench_gemv(ti_model_t m, int slot, size_t reps, float* ms, double* alg_bytes_per_launch);
+/* times `reps` launches of the tensor-core GEMM kernel alone (activations already converted and resident);
+ * ms = average per launch, ops_per_launch = 2 * 3 * rows * K * N integer operations (three INT8 digit planes) */
+int ti_b200_bench_gemm(ti_qweight_t w, size_t rows, size_t reps, float* ms, double* ops_per_launch);
 
 /* debug: one decode step on the persistent-kernel engine with CTA 0 recording 6 SM-clock stamps per phase
  * (phase start, barrier passed, x staged, weights consumed, epilogue done, barrier arrived) */

@@ -47,6 +47,8 @@ SYMBOLS = {
     "ti_b200_qweight_unpack": (C.c_int, [C.c_uint64, _i32]),
     "ti_b200_qweight_free": (C.c_int, [C.c_uint64]),
     "ti_b200_gemv_q": (C.c_int, [C.c_uint64, _f, _f, C.c_size_t]),
+    "ti_b200_gemm_q": (C.c_int, [C.c_uint64, _f, _f, C.c_size_t]),
+    "ti_b200_bench_gemm": (C.c_int, [C.c_uint64, C.c_size_t, C.c_size_t, _f, C.POINTER(C.c_double)]),
     "ti_b200_matmul_f32": (C.c_int, [_f, _f, _f, C.c_size_t, C.c_size_t, C.c_size_t]),
     "ti_b200_rms_norm": (C.c_int, [_f, _f, _f, C.c_size_t, C.c_size_t, C.c_float]),
     "ti_b200_rope": (C.c_int, [_f, _f, _f, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_float]),
@@ -173,6 +175,20 @@ class QWeight:
         y = np.empty((rows, self.N), dtype=np.float32)
         _ck(lib().ti_b200_gemv_q(self.handle, _fp(x), _fp(y), rows))
         return y
+
+    def gemm(self, x: np.ndarray) -> np.ndarray:
+        """Y[rows, N] on the tcgen05 tensor cores (prefill / batched decode); rows are bit-identical to gemv()."""
+        x = _c(x)
+        rows = x.size // self.K
+        y = np.empty((rows, self.N), dtype=np.float32)
+        _ck(lib().ti_b200_gemm_q(self.handle, _fp(x), _fp(y), rows))
+        return y
+
+    def bench_gemm(self, rows: int, reps: int):
+        """(avg ms per launch of the GEMM kernel alone, integer ops per launch)."""
+        ms, ops = C.c_float(), C.c_double()
+        _ck(lib().ti_b200_bench_gemm(self.handle, rows, reps, C.byref(ms), C.byref(ops)))
+        return ms.value, ops.value
 
     def free(self) -> None:
         if self.handle:

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "mega_ll.cuh"
+#include "gemm_tc.cuh"
 
 using namespace tib;
 
@@ -99,6 +100,9 @@ struct QWeight {
     bool has_zterm = false;
     DevBuf<uint8_t> packed;
     DevBuf<float> colscale, colzterm;
+    // K-major byte copy for the tensor-core GEMM (built on first use): Wk[n_pad][k_pad]
+    DevBuf<uint8_t> kmajor;
+    int k_pad = 0, n_pad = 0;
     size_t bytes() const { return layout_bytes(L); }
 };
 
@@ -861,6 +865,90 @@ int run_mega_ll(Model& m, int n_prompt, int n_steps, int first_sample) {
     return 0;
 }
 
+// ---- tensor-core GEMM (prefill / batched decode) ---------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_tmap_u8_2d(CUtensorMap* map, void* base, uint64_t cols, uint64_t rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+        if (!p || qr != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled is not available in this driver");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols};          // bytes between rows
+    const cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)kGemmBM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+int ensure_kmajor(QWeight& w) {
+    if (w.kmajor.p) return 0;
+    w.k_pad = (layout_kpad(w.L) + kGemmBK - 1) / kGemmBK * kGemmBK;
+    w.n_pad = (4 * w.L.U + kGemmBN - 1) / kGemmBN * kGemmBN;
+    TRY(w.kmajor.alloc((size_t)w.n_pad * w.k_pad));
+    CK(cudaMemsetAsync(w.kmajor.p, 0, (size_t)w.n_pad * w.k_pad, g_stream));
+    unpack_kmajor_kernel<<<w.L.P, kConsumerThreads, 0, g_stream>>>(w.packed.p, w.L, w.k_pad, w.kmajor.p);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// x_dev [M][K] fp32 -> y_dev [M][N] fp32; scratch buffers are allocated per call (this entry point is not the decode path)
+int gemm_q_dev(QWeight& w, const float* x_dev, float* y_dev, int M, float* kernel_ms, int reps) {
+    static bool attr = false;
+    if (!attr) {
+        CK(cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+        attr = true;
+    }
+    TRY(ensure_kmajor(w));
+    const int K = w.L.K, N = w.L.N;
+    const int m_pad = (M + kGemmBM - 1) / kGemmBM * kGemmBM;
+    DevBuf<int8_t> planes;
+    DevBuf<float> sx;
+    DevBuf<long long> sxf;
+    TRY(planes.alloc((size_t)3 * m_pad * w.k_pad));
+    TRY(sx.alloc(M));
+    TRY(sxf.alloc(M));
+    CK(cudaMemsetAsync(planes.p, 0, (size_t)3 * m_pad * w.k_pad, g_stream));
+    gemm_digits_kernel<<<M, 256, 0, g_stream>>>(x_dev, M, K, m_pad, w.k_pad, planes.p, sx.p, sxf.p);
+    ++g_launches;
+    CK(cudaGetLastError());
+    CUtensorMap map_a, map_b;
+    TRY(make_tmap_u8_2d(&map_a, planes.p, (uint64_t)w.k_pad, (uint64_t)3 * m_pad));
+    TRY(make_tmap_u8_2d(&map_b, w.kmajor.p, (uint64_t)w.k_pad, (uint64_t)w.n_pad));
+    GemmArgs g{};
+    g.M = M; g.N = N; g.K = K;
+    g.m_pad = m_pad; g.k_pad = w.k_pad;
+    g.a_signed_b = w.L.bits == 8 ? 1 : 0;
+    g.woff = w.L.bits == 4 ? w.offset4 : 0;
+    g.sx = sx.p; g.sxf = sxf.p;
+    g.colscale = w.colscale.p;
+    g.colzterm = w.has_zterm ? w.colzterm.p : nullptr;
+    g.y = y_dev;
+    const dim3 grid((N + kGemmBN - 1) / kGemmBN, m_pad / kGemmBM);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (kernel_ms) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventRecord(e0, g_stream)); }
+    for (int r = 0; r < std::max(reps, 1); ++r) {
+        gemm_i8_tc_kernel<<<grid, kGemmThreads, kGemmSmemBytes, g_stream>>>(map_a, map_b, g);
+        ++g_launches;
+    }
+    CK(cudaGetLastError());
+    if (kernel_ms) CK(cudaEventRecord(e1, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    if (kernel_ms) {
+        CK(cudaEventElapsedTime(kernel_ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    return 0;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -1086,6 +1174,38 @@ int ti_b200_gemv_q(ti_qweight_t h, const float* x_host, float* y_host, size_t ro
     for (size_t r = 0; r < rows; ++r) TRY(ti_b200_gemv_q_dev(h, x.p + r * K, y.p + r * N));
     CK(cudaMemcpyAsync(y_host, y.p, rows * N * 4, cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+int ti_b200_gemm_q(ti_qweight_t h, const float* x_host, float* y_host, size_t rows) {
+    TRY(need_init());
+    QWeight* w = get_qw(h);
+    if (!w) return fail("invalid qweight handle");
+    if (rows == 0) return fail("Cannot perform matrix multiplication on empty tensors");
+    DevBuf<float> x, y;
+    TRY(upload(x, x_host, rows * w->L.K));
+    TRY(y.alloc(rows * w->L.N));
+    TRY(gemm_q_dev(*w, x.p, y.p, (int)rows, nullptr, 1));
+    CK(cudaMemcpyAsync(y_host, y.p, rows * w->L.N * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+int ti_b200_bench_gemm(ti_qweight_t h, size_t rows, size_t reps, float* ms, double* ops_per_launch) {
+    TRY(need_init());
+    QWeight* w = get_qw(h);
+    if (!w) return fail("invalid qweight handle");
+    if (rows == 0 || reps == 0) return fail("nothing to time");
+    DevBuf<float> x, y;
+    TRY(x.alloc(rows * w->L.K));
+    TRY(y.alloc(rows * w->L.N));
+    synth_fill_kernel<<<grid_for(rows * w->L.K), 256, 0, g_stream>>>(x.p, rows * w->L.K, 4242, 1.0f);
+    ++g_launches;
+    TRY(gemm_q_dev(*w, x.p, y.p, (int)rows, nullptr, 2));   // warm-up (also builds the K-major copy)
+    float total = 0.f;
+    TRY(gemm_q_dev(*w, x.p, y.p, (int)rows, &total, (int)reps));
+    *ms = total / (float)reps;
+    if (ops_per_launch) *ops_per_launch = 2.0 * 3.0 * (double)rows * w->L.K * w->L.N;   // three INT8 digit planes
     return 0;
 }
 

@@ -1,0 +1,250 @@
+// gemm_tc.cuh -- tcgen05 tensor-core GEMM for the batched side of the hot path (prefill / batched decode), where the
+// work really is a dense contraction:  Y[M,N] = X[M,K] . dequant(Wq[K,N]).
+//
+// Replaces simd_gemm_float (src/core/tensor_engine.cpp:191-255, the M,N,K >= 32 branch of TensorEngine::matmul) on
+// quantized weights.  Same arithmetic contract as the streaming GEMV (gemv.cuh), so a row of the GEMM is bit-identical
+// to the GEMV of that row: each activation row is converted to 24-bit block fixed point and split into three 8-bit
+// digit planes; the tensor cores multiply the INT8 planes with the INT8 / unpacked-INT4 weights (kind::i8, exact
+// int32 accumulation in TMEM, one accumulator per digit); the epilogue recombines the digits in int64 and scales once.
+//
+//   CTA tile      128 tokens x 128 columns, K in steps of 128 bytes; 3 accumulators x 128 columns of TMEM
+//   warp 0        TMA producer: per stage 3 digit tiles of A (128 x 128 B) + 1 tile of B (128 x 128 B), SWIZZLE_128B
+//   warp 1        TMEM allocation; one elected lane issues tcgen05.mma (M 128, N 128, K 32): 4 k-steps x 3 digits per stage,
+//                 tcgen05.commit releases the stage / publishes the accumulators
+//   warps 2..5    epilogue: tcgen05.ld 32x32b (lane = token row), digit recombination, scale, store
+// Operands are K-major in shared memory; descriptors follow the sm_100 layout (start address, SBO = 1024 B between 8-row
+// groups, version 1, layout type SWIZZLE_128B); the k-step inside the 128-byte swizzle atom advances the start address.
+#pragma once
+#include <cuda.h>
+
+#include "gemv.cuh"
+
+namespace tib {
+
+constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 128;   // BK in bytes = int8 elements
+constexpr int kGemmStages = 3;
+constexpr int kGemmThreads = 192;
+constexpr int kGemmTileBytes = kGemmBM * kGemmBK;              // 16 KiB
+constexpr int kGemmStageBytes = 4 * kGemmTileBytes;            // 3 A digit tiles + 1 B tile
+constexpr size_t kGemmSmemBytes = (size_t)kGemmStages * kGemmStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GemmArgs {
+    int M, N, K;            // logical sizes
+    int m_pad, k_pad;       // padded to 128
+    int a_signed_b;         // 1: weights are signed bytes (INT8), 0: unsigned (INT4 nibbles stored as q + woff)
+    int woff;
+    const float* sx;        // [M] s_x of each row
+    const long long* sxf;   // [M] sum of xf of each row
+    const float* colscale;  // [N]
+    const float* colzterm;  // [N] or nullptr
+    float* y;               // [M][N]
+};
+
+// ---- activations -> digit planes [3][m_pad][k_pad] (K-major rows), one block per row ------------------------
+__global__ void gemm_digits_kernel(const float* x, int M, int K, int m_pad, int k_pad, int8_t* planes, float* sx_out, long long* sxf_out) {
+    __shared__ float red[32];
+    __shared__ long long redl[32];
+    const int row = blockIdx.x;
+    const float* xr = x + (size_t)row * K;
+    float amax = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) amax = fmaxf(amax, fabsf(xr[k]));
+    amax = warp_max(amax);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    amax = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) amax = fmaxf(amax, red[i]);
+    const bool finite = amax > 0.f && amax < INFINITY;
+    const float inv_s = finite ? kXQMax / amax : 0.f;   // the expressions of gemv_stage_x, so rows match the GEMV bit for bit
+    const float s_x = finite ? amax / kXQMax : 0.f;
+    long long sxf = 0;
+    for (int k = threadIdx.x; k < k_pad; k += blockDim.x) {
+        const int f = k < K ? __float2int_rn(xr[k] * inv_s) : 0;
+        sxf += f;
+        planes[((size_t)0 * m_pad + row) * k_pad + k] = (int8_t)(f & 0xFF);
+        planes[((size_t)1 * m_pad + row) * k_pad + k] = (int8_t)((f >> 8) & 0xFF);
+        planes[((size_t)2 * m_pad + row) * k_pad + k] = (int8_t)((f >> 16) & 0xFF);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sxf += __shfl_xor_sync(0xffffffffu, sxf, o);
+    if ((threadIdx.x & 31) == 0) redl[threadIdx.x >> 5] = sxf;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += redl[i];
+        sx_out[row] = s_x;
+        sxf_out[row] = t;
+    }
+}
+
+// ---- packed streaming layout -> K-major bytes Wk[n_pad][k_pad] (the B operand), same thread mapping as unpack_kernel ----
+__global__ void unpack_kmajor_kernel(const uint8_t* packed, QLayout L, int k_pad, uint8_t* wk) {
+    const Slab slab = make_slab(L, blockIdx.x);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = lane & 3, s = lane >> 2;
+    const int nq = warp_quads(slab, warp), fq = warp_first_quad(slab, warp);
+    const int kl = L.kc / 8;
+    size_t stage_base = 0;
+    for (int r = 0; r < nq; ++r) {
+        const int q = fq + r;
+        const int grp = q / L.nchunks, chunk = q - grp * L.nchunks;
+        const int live = q >= slab.qfull ? slab.nlast : 4;
+        const size_t qoff = stage_base + (size_t)round_warp_offset(slab, r, warp) * kItemBytes;
+        stage_base += (size_t)round_total(slab, r) * kItemBytes;
+        for (int u = 0; u < live; ++u) {
+            const int n = slab.col0 + 4 * (4 * grp + u) + c;
+            const uint4 wv = *reinterpret_cast<const uint4*>(packed + slab.byte0 + qoff + (size_t)u * kItemBytes + lane * 16);
+            const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
+            for (int e = 0; e < kl; ++e) {
+                const int k = chunk * L.kc + s * kl + e;
+                if (k >= k_pad) continue;
+                int word, shift;
+                lane_elem_pos(L.bits, e, word, shift);
+                const uint32_t v = L.bits == 4 ? (words[word] >> shift) & 0xFu : (words[word] >> shift) & 0xFFu;
+                wk[(size_t)n * k_pad + k] = (uint8_t)v;   // INT4: u = q + woff (0..15); INT8: two's complement q
+            }
+        }
+    }
+}
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, SWIZZLE_128B, tile rows 128 B apart inside 1024-byte 8-row groups
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address
+    d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int a_signed, int b_signed) {
+    return (2u << 4)                        // D format S32
+           | ((uint32_t)a_signed << 7)      // A: 0 unsigned / 1 signed 8-bit
+           | ((uint32_t)b_signed << 10)     // B
+           | ((uint32_t)(kGemmBN >> 3) << 17) | ((uint32_t)(kGemmBM >> 4) << 24);   // K-major A and B (bits 15, 16 = 0)
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+    extern __shared__ uint8_t gsm_raw[];
+    const uint32_t base = (smem_u32(gsm_raw) + 1023u) & ~1023u;
+    uint8_t* tiles = gsm_raw + (base - smem_u32(gsm_raw));
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)kGemmStages * kGemmStageBytes);
+    uint64_t* empty = full + kGemmStages;
+    uint64_t* tmem_full = empty + kGemmStages;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nb = blockIdx.x, mb = blockIdx.y;
+    const int KB = g.k_pad / kGemmBK;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kGemmStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int st = kb % kGemmStages, use = kb / kGemmStages;
+                if (use > 0) mbar_wait(&empty[st], (use - 1) & 1);
+                mbar_arrive_expect_tx(&full[st], kGemmStageBytes);
+                uint8_t* sbase = tiles + (size_t)st * kGemmStageBytes;
+                for (int d = 0; d < 3; ++d) tma_load_2d(sbase + d * kGemmTileBytes, &map_a, kb * kGemmBK, d * g.m_pad + mb * kGemmBM, &full[st]);
+                tma_load_2d(sbase + 3 * kGemmTileBytes, &map_b, kb * kGemmBK, nb * kGemmBN, &full[st]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t id_u = umma_idesc_i8(0, g.a_signed_b), id_s = umma_idesc_i8(1, g.a_signed_b);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int st = kb % kGemmStages, use = kb / kGemmStages;
+                mbar_wait(&full[st], use & 1);
+                tc_fence_after();
+                const uint32_t sbase = base + st * kGemmStageBytes;
+#pragma unroll
+                for (int k4 = 0; k4 < kGemmBK / 32; ++k4) {
+                    const uint64_t bdesc = umma_desc_sw128(sbase + 3 * kGemmTileBytes + k4 * 32);
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const uint64_t adesc = umma_desc_sw128(sbase + d * kGemmTileBytes + k4 * 32);
+                        tc_mma_i8(tmem + d * kGemmBN, adesc, bdesc, d == 2 ? id_s : id_u, (kb | k4) != 0 ? 1u : 0u);
+                    }
+                }
+                tc_commit(&empty[st]);   // the stage may be refilled once these MMAs have read it
+            }
+            tc_commit(tmem_full);
+        }
+    } else {
+        // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; lane = token row of the tile
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int row = mb * kGemmBM + q * 32 + lane;
+        const bool row_ok = row < g.M;
+        const float sx = row_ok ? g.sx[row] : 0.f;
+        const long long sxf = row_ok ? g.sxf[row] : 0;
+        const long long offterm = (long long)g.woff * sxf;
+        const float fsxf = (float)sxf;
+        for (int c0 = 0; c0 < kGemmBN; c0 += 16) {
+            uint32_t a[3][16];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * kGemmBN + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(a[d][0]), "=r"(a[d][1]), "=r"(a[d][2]), "=r"(a[d][3]), "=r"(a[d][4]), "=r"(a[d][5]), "=r"(a[d][6]), "=r"(a[d][7]),
+                      "=r"(a[d][8]), "=r"(a[d][9]), "=r"(a[d][10]), "=r"(a[d][11]), "=r"(a[d][12]), "=r"(a[d][13]), "=r"(a[d][14]), "=r"(a[d][15])
+                    : "r"(taddr));
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row_ok) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int n = nb * kGemmBN + c0 + i;
+                    if (n < g.N) {
+                        const long long t = ((long long)(int)a[2][i] << 16) + ((long long)(int)a[1][i] << 8) + (long long)(int)a[0][i] - offterm;
+                        const int hi = (int)(t >> 23), lo = (int)(t & 0x7FFFFF);
+                        const float tf = fmaf((float)hi, 8388608.0f, (float)lo);
+                        const float zt = g.colzterm ? g.colzterm[n] : 0.f;
+                        g.y[(size_t)row * g.N + n] = (fmaf(zt, fsxf, tf) * sx) * g.colscale[n];   // the GEMV epilogue's expression
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+}  // namespace tib
