@@ -1,2 +1,2 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests/test_gpu_gemm.py tests/test_host_cpp.py -m gpu -q -x --timeout 300 2>&1 | tail -15
+TURBOINFER_B200_DBG_NOMATH=2 timeout 250 python scripts/timeline.py llama7b 2 16 2>&1 | tail -15

@@ -529,6 +529,7 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
     };
     uint32_t st = it % S, par = (it / S) & 1;
     it += nrounds;
+    bool ready = false;   // the NEXT stage's barrier is probed while this stage is being multiplied
     for (int r = 0; r < nrounds; ++r) {
         if (r > 0 && ++st == (uint32_t)S) { st = 0; par ^= 1; }
         const bool have = r < my_nq;
@@ -537,7 +538,9 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
         const int woff = __reduce_add_sync(0xffffffffu, l_items);
         XDigits<BITS> xd;
         if (have) xd = load_xdigits<BITS>(xlane + chunk * kChunkBytes);  // does not depend on the stage: before the wait
-        if (DBG != 2) mbar_wait(&sm.full[st], par);
+        if (DBG != 2 && !ready) mbar_wait(&sm.full[st], par);
+        ready = false;
+        const uint32_t st_n = st + 1 == (uint32_t)S ? 0u : st + 1, par_n = st + 1 == (uint32_t)S ? par ^ 1u : par;
         if (have) {
             const int live = grp == slab.ngroups - 1 ? slab.nlast : 4;
             const uint32_t wbase = ring_lane + st * kStageBytes + woff * kItemBytes;
@@ -548,6 +551,7 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
             if (live == 4) {  // the common case, straight-line: four loads in flight, 12 independent IDP4A chains
                 const uint4 w0 = lds128s(wbase), w1 = lds128s(wbase + kItemBytes), w2 = lds128s(wbase + 2 * kItemBytes),
                             w3 = lds128s(wbase + 3 * kItemBytes);
+                if (DBG != 2 && r + 1 < nrounds) ready = mbar_test_wait(&sm.full[st_n], par_n);
                 one(w0, acc[0]); one(w1, acc[1]); one(w2, acc[2]); one(w3, acc[3]);
             } else {          // ragged last group of the slab: 1..3 items
                 { const uint4 w0 = lds128s(wbase); one(w0, acc[0]); }

@@ -59,6 +59,7 @@ struct MegaArgs {
     int stages;
     int max_kpad, max_units, attn_floats;
     long long* dbg;   // optional: CTA 0 writes 6 clock64 stamps per phase of step 0 (debug timeline)
+    int dbg_nomath;   // debug: the main loop only XORs the weights (what the ring alone can deliver)
     float4* stats;            // [2][gridDim.x][2]: per-CTA partial statistics (32-byte slots) of the phase's output, by phase parity
     const XStats* emb_stats;  // [V]: statistics of every embedding row (against the first norm weight)
 };
@@ -416,7 +417,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
     if (warp >= kConsumerWarps) {
         // ===== producer warpgroup: warp 16 streams every GEMV phase of every step, back to back =====
         reg_dealloc<40>();
-        if (warp == kConsumerWarps) {
+        if (warp == kConsumerWarps && m.dbg_nomath != 2) {
             // lane l holds the record of phase base + l: one latency per 32 phases, then register shuffles only
             for (int s = 0; s < m.n_steps; ++s) {
                 const bool sample = s >= m.first_sample;
@@ -586,7 +587,9 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                         }
                         ts[11] = ready;
                     }
-                    gemv_consume<BITS>(g, slab, sm, it, warp, lane);
+                    if (m.dbg_nomath == 2) gemv_consume<BITS, 2>(g, slab, sm, it, warp, lane);
+                    else if (m.dbg_nomath) gemv_consume<BITS, 1>(g, slab, sm, it, warp, lane);
+                    else gemv_consume<BITS>(g, slab, sm, it, warp, lane);
                     if (stamp) ts[3] = clock64();
                     out_st = gemv_epilogue(g, slab, sm, s_x, resid, ctx, pre, tid, lane);
                 }
