@@ -47,6 +47,16 @@ int ti_b200_device_info(char* buf, size_t cap);
 const char* ti_b200_last_error(void);
 int ti_b200_sync(void);
 
+/* ---- tensor parallelism (the reference has none) --------------------------------------------------
+ * One process per GPU.  Rank 0 obtains an id with ti_b200_tp_unique_id and hands it to the other ranks by any means
+ * (the tests and the bench use torch.distributed); every rank then calls ti_b200_tp_init.  A model created with
+ * cfg.reserved[1] = nranks is sharded: column-parallel q/k/v (whole heads per rank) and gate/up, row-parallel o and
+ * down, one NCCL all-reduce (fp32 sum over NVLink) after each row-parallel GEMV; embeddings, norms and lm_head are
+ * replicated.  Every rank is given the WHOLE fp32 tensors: quantization parameters come from the whole tensor
+ * (quantize first, then shard), so the integers are the reference's. */
+int ti_b200_tp_unique_id(uint8_t* out, size_t cap);   /* cap >= 128 */
+int ti_b200_tp_init(int nranks, int rank, const uint8_t* unique_id, size_t id_bytes);
+
 /* ---- raw device memory (for callers that keep activations resident) --------------------------- */
 int ti_b200_malloc(void** dev, size_t bytes);
 int ti_b200_free(void* dev);
@@ -122,7 +132,7 @@ typedef struct ti_model_config {
     int32_t max_seq;         /* KV-cache capacity in tokens (KVCache::max_length, reference hard-codes 2048) */
     int32_t kv_page_tokens;  /* tokens per KV page; 0 = default 64 */
     int32_t compat_literal;  /* 1: placeholder embeddings 0.1f*(i%100) and unscaled integer weights */
-    int32_t reserved[7];
+    int32_t reserved[7];     /* [0] = 1: per-op graph engine instead of the persistent kernel; [1] = tensor parallel degree (0/1: none) */
 } ti_model_config;
 
 int ti_b200_model_new(const ti_model_config* cfg, ti_model_t* out);

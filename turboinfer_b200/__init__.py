@@ -8,7 +8,7 @@ There is no CPU fallback: importing works anywhere (so the symbol table can be c
 entry point raises unless a CUDA device is present and the extension is built.
 """
 from .capi import (Q_INT4, Q_INT8, Q_NONE, B200Error, Model, QWeight, lib, library_path, init, shutdown,  # noqa: F401
-                   device_info, launch_count, ops)
+                   device_info, launch_count, ops, tp_init, tp_unique_id)
 
 __all__ = ["Q_INT4", "Q_INT8", "Q_NONE", "B200Error", "Model", "QWeight", "lib", "library_path", "init", "shutdown",
-           "device_info", "launch_count", "ops"]
+           "device_info", "launch_count", "ops", "tp_init", "tp_unique_id"]

@@ -34,6 +34,8 @@ SYMBOLS = {
     "ti_b200_device_info": (C.c_int, [C.c_char_p, C.c_size_t]),
     "ti_b200_last_error": (C.c_char_p, []),
     "ti_b200_sync": (C.c_int, []),
+    "ti_b200_tp_unique_id": (C.c_int, [C.c_char_p, C.c_size_t]),
+    "ti_b200_tp_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
     "ti_b200_malloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "ti_b200_free": (C.c_int, [C.c_void_p]),
     "ti_b200_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -126,6 +128,17 @@ def _need() -> C.CDLL:
     if not _inited:
         init(int(os.environ.get("LOCAL_RANK", "0")))
     return lib()
+
+
+def tp_unique_id() -> bytes:
+    """Rank 0: the NCCL id of a new tensor-parallel group; hand it to the other ranks, then tp_init() everywhere."""
+    buf = C.create_string_buffer(128)
+    _ck(_need().ti_b200_tp_unique_id(buf, 128))
+    return buf.raw
+
+
+def tp_init(nranks: int, rank: int, unique_id: bytes) -> None:
+    _ck(_need().ti_b200_tp_init(nranks, rank, unique_id, len(unique_id)))
 
 
 def device_info() -> str:
@@ -293,7 +306,7 @@ class Model:
     """Device-resident decoder (InferenceEngine's weights + KV cache + incremental forward + greedy generate)."""
 
     def __init__(self, meta: dict, qtype: int, *, attn_mode: int = 1, rope_mode: int = 0, max_seq: int = 2048,
-                 kv_page_tokens: int = 0, compat_literal: bool = False):
+                 kv_page_tokens: int = 0, compat_literal: bool = False, tp: int = 1, per_op_engine: bool = False):
         cfg = ModelConfig()
         cfg.vocab, cfg.hidden, cfg.layers, cfg.heads, cfg.inter = (meta["vocab"], meta["hidden"], meta["layers"],
                                                                    meta["heads"], meta["inter"])
@@ -301,6 +314,8 @@ class Model:
         cfg.rms_eps = meta.get("rms_eps", 1e-5)
         cfg.qtype, cfg.attn_mode, cfg.rope_mode = qtype, attn_mode, rope_mode
         cfg.max_seq, cfg.kv_page_tokens, cfg.compat_literal = max_seq, kv_page_tokens, int(compat_literal)
+        cfg.reserved[0] = 1 if per_op_engine else 0
+        cfg.reserved[1] = tp if tp > 1 else 0   # tensor-parallel degree: needs tp_init() on every rank first
         self.meta = dict(meta)
         h = C.c_uint64()
         _ck(_need().ti_b200_model_new(C.byref(cfg), C.byref(h)))

@@ -14,6 +14,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include "mega_ll.cuh"
 #include "gemm_tc.cuh"
 
@@ -28,6 +31,18 @@ cudaStream_t g_stream = nullptr;
 uint64_t g_launches = 0;
 bool g_use_pdl = false;
 bool g_attr_done = false;
+
+// ---- tensor parallelism: NCCL is loaded at run time (dlopen), so the library has no link-time dependency on it ----
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+} g_nccl;
+ncclComm_t g_comm = nullptr;
+int g_tp_size = 1, g_tp_rank = 0;
 
 int fail(const char* fmt, ...) {
     char buf[1024];
@@ -176,9 +191,29 @@ int device_quant_params(const float* x, size_t n, int qtype, int symmetric, floa
     return 0;
 }
 
+// A source of a packed weight: a view (rows [row0, row0 + K), columns [col0, col0 + n)) of a whole fp32 tensor
+// [rows][cols] on the device.  The quantization parameters always come from the WHOLE tensor.
+struct SrcView {
+    const float* full;
+    size_t rows, cols;
+    size_t row0, col0;
+    int n;
+};
+
+int build_qweight_views(const SrcView* v, int nsrc, int mode, int K, int qtype, int symmetric, bool unit_scale, std::unique_ptr<QWeight>* out);
+
 // Quantize + pack up to three device fp32 sources (all [K][n_i]) into one streaming weight.
 int build_qweight(const float* const* src, const int* src_n, int nsrc, int mode, int K, int qtype, int symmetric, bool unit_scale,
                   std::unique_ptr<QWeight>* out) {
+    SrcView v[3];
+    for (int i = 0; i < nsrc; ++i) v[i] = SrcView{src[i], (size_t)K, (size_t)src_n[i], 0, 0, src_n[i]};
+    return build_qweight_views(v, nsrc, mode, K, qtype, symmetric, unit_scale, out);
+}
+
+int build_qweight_views(const SrcView* v, int nsrc, int mode, int K, int qtype, int symmetric, bool unit_scale, std::unique_ptr<QWeight>* out) {
+    const float* src[3];
+    int src_n[3];
+    for (int i = 0; i < nsrc; ++i) { src[i] = v[i].full + v[i].row0 * v[i].cols + v[i].col0; src_n[i] = v[i].n; }
     auto w = std::make_unique<QWeight>();
     int N = 0;
     for (int i = 0; i < nsrc; ++i) N += src_n[i];
@@ -203,9 +238,10 @@ int build_qweight(const float* const* src, const int* src_n, int nsrc, int mode,
     pa.colscale = w->colscale.p;
     pa.colzterm = w->colzterm.p;
     for (int i = 0; i < nsrc; ++i) {
-        TRY(device_quant_params(src[i], (size_t)K * src_n[i], qtype, symmetric, sz.p + 2 * i, mm.p, g_stream));
+        TRY(device_quant_params(v[i].full, v[i].rows * v[i].cols, qtype, symmetric, sz.p + 2 * i, mm.p, g_stream));
         pa.src[i].w = src[i];
         pa.src[i].n = src_n[i];
+        pa.src[i].ld = (int)v[i].cols;
         pa.src[i].sz = sz.p + 2 * i;
     }
     pack_kernel<<<w->L.P, kConsumerThreads, 0, g_stream>>>(pa);
@@ -254,6 +290,8 @@ struct Model {
     int launches_decode = 0, launches_prefill = 0;  // kernels per captured step
     // persistent-kernel engine
     bool use_mega = false;
+    int tp = 1, tp_rank = 0;   // tensor-parallel degree / rank of this model
+    DevBuf<float> ar_tmp;      // [H] partial output of a row-parallel GEMV, all-reduced in place
     bool use_ll = false;   // dataflow (LL) variant of the persistent kernel
     DevBuf<MegaLLPhase> ll_phases;
     DevBuf<llword> ll_xres, ll_act, ll_attn, ll_q, ll_knew, ll_vnew, ll_part, ll_keys, ll_stats;
@@ -327,10 +365,17 @@ Slot parse_name(const std::string& name, int* layer) {
     return S_NONE;
 }
 
-int pack_single(RawTensor& raw, int qtype, std::unique_ptr<QWeight>* out) {
-    const float* src[1] = {raw.data.p};
-    int n[1] = {(int)raw.cols};
-    TRY(build_qweight(src, n, 1, 0, (int)raw.rows, qtype, 1, false, out));
+enum ShardKind { SH_NONE, SH_COLS, SH_ROWS };   // column-parallel (split N) / row-parallel (split K)
+SrcView shard_view(const RawTensor& raw, ShardKind kind, int tp, int rank) {
+    SrcView v{raw.data.p, raw.rows, raw.cols, 0, 0, (int)raw.cols};
+    if (tp > 1 && kind == SH_COLS) { v.n = (int)(raw.cols / tp); v.col0 = (size_t)rank * v.n; }
+    if (tp > 1 && kind == SH_ROWS) v.row0 = (size_t)rank * (raw.rows / tp);
+    return v;
+}
+int pack_single(RawTensor& raw, int qtype, std::unique_ptr<QWeight>* out, ShardKind kind = SH_NONE, int tp = 1, int rank = 0) {
+    const SrcView v = shard_view(raw, kind, tp, rank);
+    const int K = (tp > 1 && kind == SH_ROWS) ? (int)(raw.rows / tp) : (int)raw.rows;
+    TRY(build_qweight_views(&v, 1, 0, K, qtype, 1, false, out));
     raw.data.release();
     return 0;
 }
@@ -340,22 +385,22 @@ int pack_ready(Model& m, Layer& ly, bool final_pass) {
     const int qt = m.cfg.qtype;
     if (m.cfg.compat_literal) return 0;
     if (!ly.qkv && ly.raw_q.present() && ly.raw_k.present() && ly.raw_v.present()) {
-        const float* src[3] = {ly.raw_q.data.p, ly.raw_k.data.p, ly.raw_v.data.p};
-        int n[3] = {(int)ly.raw_q.cols, (int)ly.raw_k.cols, (int)ly.raw_v.cols};
-        TRY(build_qweight(src, n, 3, 0, (int)ly.raw_q.rows, qt, 1, false, &ly.qkv));
+        // tensor parallel: each rank keeps the columns of its own heads of q, k and v (column-parallel)
+        const SrcView v[3] = {shard_view(ly.raw_q, SH_COLS, m.tp, m.tp_rank), shard_view(ly.raw_k, SH_COLS, m.tp, m.tp_rank),
+                              shard_view(ly.raw_v, SH_COLS, m.tp, m.tp_rank)};
+        TRY(build_qweight_views(v, 3, 0, (int)ly.raw_q.rows, qt, 1, false, &ly.qkv));
         ly.raw_q.data.release(); ly.raw_k.data.release(); ly.raw_v.data.release();
     }
-    if (!ly.o && ly.raw_o.present()) TRY(pack_single(ly.raw_o, qt, &ly.o));
-    if (!ly.down && ly.raw_down.present()) TRY(pack_single(ly.raw_down, qt, &ly.down));
+    if (!ly.o && ly.raw_o.present()) TRY(pack_single(ly.raw_o, qt, &ly.o, SH_ROWS, m.tp, m.tp_rank));          // row-parallel
+    if (!ly.down && ly.raw_down.present()) TRY(pack_single(ly.raw_down, qt, &ly.down, SH_ROWS, m.tp, m.tp_rank));
     if (!ly.gateup && ly.raw_up.present() && ly.raw_gate.present()) {
-        const float* src[2] = {ly.raw_gate.data.p, ly.raw_up.data.p};  // even columns = gate, odd = up
-        int n[2] = {(int)ly.raw_gate.cols, (int)ly.raw_up.cols};
-        TRY(build_qweight(src, n, 2, 1, (int)ly.raw_up.rows, qt, 1, false, &ly.gateup));
+        const SrcView v[2] = {shard_view(ly.raw_gate, SH_COLS, m.tp, m.tp_rank), shard_view(ly.raw_up, SH_COLS, m.tp, m.tp_rank)};  // even columns = gate, odd = up
+        TRY(build_qweight_views(v, 2, 1, (int)ly.raw_up.rows, qt, 1, false, &ly.gateup));
         ly.has_gate = true;
         ly.raw_up.data.release(); ly.raw_gate.data.release();
     }
     if (final_pass && !ly.gateup && ly.raw_up.present()) {  // no gate: relu(up) (:392-395)
-        TRY(pack_single(ly.raw_up, qt, &ly.gateup));
+        TRY(pack_single(ly.raw_up, qt, &ly.gateup, SH_COLS, m.tp, m.tp_rank));
         ly.has_gate = false;
     }
     return 0;
@@ -414,7 +459,7 @@ int enqueue_attention(Model& m, Layer& ly, cudaStream_t st) {
     a.page_tokens = m.page_tokens;
     a.pos_ptr = &m.state.p->pos;
     a.t_bias = 1;
-    a.H = m.cfg.hidden;
+    a.H = m.cfg.hidden / m.tp;
     a.D = m.attn_dim;
     a.heads = m.attn_heads;
     a.max_splits = m.max_splits;
@@ -430,8 +475,20 @@ int enqueue_attention(Model& m, Layer& ly, cudaStream_t st) {
     return 0;
 }
 
+// row-parallel GEMV output under tensor parallelism: partial [H] -> NCCL all-reduce (sum) -> x += partial
+int tp_allreduce_add(Model& m, cudaStream_t st) {
+    const int H = m.cfg.hidden;
+    const ncclResult_t r = g_nccl.AllReduce(m.ar_tmp.p, m.ar_tmp.p, (size_t)H, ncclFloat32, ncclSum, g_comm, st);
+    if (r != ncclSuccess) return fail("ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+    elementwise_kernel<<<grid_for(H), 256, 0, st>>>(m.x.p, m.ar_tmp.p, m.x.p, H, EW_ADD);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int enqueue_step(Model& m, bool with_head, cudaStream_t st) {
     const int H = m.cfg.hidden;
+    const int Hl = H / m.tp;   // this rank's share of the attention width (its heads)
     StepState* S = m.state.p;
     embed_kernel<<<grid_for(H), 256, 0, st>>>(m.tok_emb.p, S, m.x.p, H, 0);
     ++g_launches;
@@ -444,7 +501,7 @@ int enqueue_step(Model& m, bool with_head, cudaStream_t st) {
             a.rms_eps = m.cfg.rms_eps;
             a.epi = EPI_QKV;
             a.out = m.q.p;
-            a.hidden = H;
+            a.hidden = Hl;
             a.rope_dim = m.cfg.rope_mode == 1 ? H / m.cfg.heads : (m.cfg.rope_mode == 2 ? H : 0);
             a.inv_freq = m.inv_freq.p;
             a.pos_ptr = &S->pos;
@@ -456,10 +513,17 @@ int enqueue_step(Model& m, bool with_head, cudaStream_t st) {
             TRY(enqueue_attention(m, ly, st));
             GemvArgs o{};
             o.x = m.attn_out.p;
-            o.epi = EPI_RESIDUAL;
-            o.resid = m.x.p;
-            o.out = m.x.p;
-            TRY(launch_gemv(*ly.o, o, st));
+            if (m.tp > 1) {
+                o.epi = EPI_STORE;
+                o.out = m.ar_tmp.p;
+                TRY(launch_gemv(*ly.o, o, st));
+                TRY(tp_allreduce_add(m, st));
+            } else {
+                o.epi = EPI_RESIDUAL;
+                o.resid = m.x.p;
+                o.out = m.x.p;
+                TRY(launch_gemv(*ly.o, o, st));
+            }
         } else {
             // compute_attention returns its (normalised) input when a projection is missing (:293-296): x <- x + n
             const float* n = m.x.p;
@@ -481,10 +545,17 @@ int enqueue_step(Model& m, bool with_head, cudaStream_t st) {
             TRY(launch_gemv(*ly.gateup, g, st));
             GemvArgs d{};
             d.x = m.act.p;
-            d.epi = EPI_RESIDUAL;
-            d.resid = m.x.p;
-            d.out = m.x.p;
-            TRY(launch_gemv(*ly.down, d, st));
+            if (m.tp > 1) {
+                d.epi = EPI_STORE;
+                d.out = m.ar_tmp.p;
+                TRY(launch_gemv(*ly.down, d, st));
+                TRY(tp_allreduce_add(m, st));
+            } else {
+                d.epi = EPI_RESIDUAL;
+                d.resid = m.x.p;
+                d.out = m.x.p;
+                TRY(launch_gemv(*ly.down, d, st));
+            }
         } else {
             const float* f = m.x.p;  // compute_ffn returns its input (:377-380)
             if (ly.ffn_norm.p) {
@@ -527,6 +598,20 @@ int capture_graph(Model& m, bool with_head, cudaGraphExec_t* out) {
     e = cudaGraphInstantiate(out, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// one forward pass on the per-op engine: replay the captured graph, or (tensor parallel) enqueue the kernels directly
+int run_step(Model& m, bool with_head) {
+    if (m.tp == 1) {
+        CK(cudaGraphLaunch(with_head ? m.graph_decode : m.graph_prefill, g_stream));
+        g_launches += with_head ? m.launches_decode : m.launches_prefill;
+        return 0;
+    }
+    TRY(enqueue_step(m, with_head, g_stream));
+    step_finish_kernel<<<1, 1024, 0, g_stream>>>(m.state.p, m.io.p, m.logits.p, m.cfg.vocab, with_head ? 1 : 0);
+    ++g_launches;
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -1012,6 +1097,48 @@ int ti_b200_device_info(char* buf, size_t cap) {
     return 0;
 }
 
+static int nccl_load() {
+    if (g_nccl.lib) return 0;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail("tensor parallelism needs NCCL: %s", dlerror());
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+    g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GetErrorString)
+        return fail("the NCCL library lacks a required symbol");
+    g_nccl.lib = lib;
+    return 0;
+}
+
+int ti_b200_tp_unique_id(uint8_t* out, size_t cap) {
+    TRY(need_init());
+    TRY(nccl_load());
+    if (cap < sizeof(ncclUniqueId)) return fail("unique id buffer too small: need %zu bytes", sizeof(ncclUniqueId));
+    ncclUniqueId id;
+    const ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail("ncclGetUniqueId failed: %s", g_nccl.GetErrorString(r));
+    memcpy(out, &id, sizeof(id));
+    return 0;
+}
+
+int ti_b200_tp_init(int nranks, int rank, const uint8_t* unique_id, size_t id_bytes) {
+    TRY(need_init());
+    TRY(nccl_load());
+    if (nranks < 2 || rank < 0 || rank >= nranks) return fail("invalid tensor parallel geometry (%d ranks, rank %d)", nranks, rank);
+    if (id_bytes < sizeof(ncclUniqueId)) return fail("unique id too short");
+    if (g_comm) return fail("tensor parallel group already initialised");
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof(id));
+    const ncclResult_t r = g_nccl.CommInitRank(&g_comm, nranks, id, rank);
+    if (r != ncclSuccess) { g_comm = nullptr; return fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r)); }
+    g_tp_size = nranks;
+    g_tp_rank = rank;
+    return 0;
+}
+
 int ti_b200_sync(void) {
     TRY(need_init());
     CK(cudaStreamSynchronize(g_stream));
@@ -1377,6 +1504,13 @@ int ti_b200_model_new(const ti_model_config* cfg, ti_model_t* out) {
     if (m->cfg.rope_theta == 0.f) m->cfg.rope_theta = 10000.0f;
     if (m->cfg.max_seq <= 0) m->cfg.max_seq = 2048;  // KVCache hard-codes 2048 (inference_engine.cpp:569)
     m->page_tokens = cfg->kv_page_tokens > 0 ? cfg->kv_page_tokens : 64;
+    if (cfg->reserved[1] > 1) {   // tensor-parallel model: every rank creates it with the same config after ti_b200_tp_init
+        if (g_comm == nullptr || cfg->reserved[1] != g_tp_size) return fail("tensor parallel degree %d needs ti_b200_tp_init with as many ranks first", cfg->reserved[1]);
+        if (cfg->attn_mode != 1 || cfg->rope_mode == 2) return fail("tensor parallelism shards attention heads: attn_mode 1 and per-head RoPE only");
+        if (cfg->heads % g_tp_size || cfg->inter % g_tp_size || cfg->hidden % (4 * g_tp_size)) return fail("heads, inter and hidden must be divisible by the tensor parallel degree");
+        m->tp = g_tp_size;
+        m->tp_rank = g_tp_rank;
+    }
     m->layers.resize(cfg->layers);
     std::lock_guard<std::mutex> lk(g_mu);
     g_models.push_back(std::move(m));
@@ -1418,9 +1552,10 @@ int ti_b200_model_finalize(ti_model_t h) {
     const int H = m.cfg.hidden, V = m.cfg.vocab, I = m.cfg.inter;
     if (!m.tok_emb.p) return fail("token_embeddings.weight missing");
     if (!m.lm_head) return fail("lm_head.weight missing");  // the reference draws random logits here (:1544-1549); refuse instead
-    m.attn_heads = m.cfg.attn_mode == 1 ? m.cfg.heads : 1;
-    TRY(attn_check_dim(H, m.attn_heads));
-    m.attn_dim = H / m.attn_heads;
+    const int Hl = H / m.tp;   // attention width owned by this rank
+    m.attn_heads = m.cfg.attn_mode == 1 ? m.cfg.heads / m.tp : 1;
+    TRY(attn_check_dim(Hl, m.attn_heads));
+    m.attn_dim = Hl / m.attn_heads;
     m.attn_smem = attn_smem_bytes(m.attn_dim);
     m.max_splits = std::max(1, std::min((2 * g_num_sms + m.attn_heads - 1) / m.attn_heads, 512));
     m.max_splits = std::max(m.max_splits, g_num_sms / m.attn_heads);
@@ -1428,8 +1563,8 @@ int ti_b200_model_finalize(ti_model_t h) {
     for (auto& ly : m.layers) {
         TRY(pack_ready(m, ly, true));
         if (ly.qkv && ly.o) {
-            TRY(ly.k_pool.alloc((size_t)m.num_pages * m.page_tokens * H));
-            TRY(ly.v_pool.alloc((size_t)m.num_pages * m.page_tokens * H));
+            TRY(ly.k_pool.alloc((size_t)m.num_pages * m.page_tokens * Hl));
+            TRY(ly.v_pool.alloc((size_t)m.num_pages * m.page_tokens * Hl));
         }
         // sources that cannot be used (e.g. q/k/v without o_proj) are dropped, like the reference ignores them
         ly.raw_q.data.release(); ly.raw_k.data.release(); ly.raw_v.data.release(); ly.raw_o.data.release();
@@ -1460,13 +1595,16 @@ int ti_b200_model_finalize(ti_model_t h) {
     for (auto& ly : m.layers) complete &= (ly.qkv && ly.o && ly.gateup && ly.down);
     const char* eng = getenv("TURBOINFER_B200_ENGINE");
     const bool want_graph = m.cfg.reserved[0] == 1 || (eng && std::string(eng) == "graph");
-    m.use_mega = complete && !want_graph;
+    m.use_mega = complete && !want_graph && m.tp == 1;
+    if (m.tp > 1) TRY(m.ar_tmp.alloc(H));
     TRY(m.prompt.alloc(16));
     if (m.use_mega) TRY(build_mega(m));
     m.use_ll = m.use_mega && eng && std::string(eng) == "ll";   // experimental dataflow variant, off by default
     if (m.use_ll) TRY(build_mega_ll(m));
-    TRY(capture_graph(m, true, &m.graph_decode));
-    TRY(capture_graph(m, false, &m.graph_prefill));
+    if (m.tp == 1) {   // tensor-parallel steps hold NCCL calls: they are enqueued directly, not replayed from a graph
+        TRY(capture_graph(m, true, &m.graph_decode));
+        TRY(capture_graph(m, false, &m.graph_prefill));
+    }
     m.finalized = true;
     m.host_pos = 0;
     return 0;
@@ -1535,8 +1673,7 @@ int ti_b200_decode_step(ti_model_t h, int32_t token, float* logits_host, int32_t
     if (m->use_mega) {
         TRY(run_mega(*m, 0, 1, 0));
     } else {
-        CK(cudaGraphLaunch(m->graph_decode, g_stream));
-        g_launches += m->launches_decode;
+        TRY(run_step(*m, true));
     }
     m->host_pos += 1;
     if (logits_host) CK(cudaMemcpyAsync(logits_host, m->logits.p, (size_t)m->cfg.vocab * 4, cudaMemcpyDeviceToHost, g_stream));
@@ -1587,16 +1724,11 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
         set_token_kernel<<<1, 1, 0, g_stream>>>(m.state.p, m.prompt.p, i);
         ++g_launches;
         const bool last = i == n_prompt - 1;
-        if (last && n_new == 0) { CK(cudaGraphLaunch(m.graph_prefill, g_stream)); g_launches += m.launches_prefill; }
-        else if (last) { CK(cudaGraphLaunch(m.graph_decode, g_stream)); g_launches += m.launches_decode; }
-        else { CK(cudaGraphLaunch(m.graph_prefill, g_stream)); g_launches += m.launches_prefill; }
+        TRY(run_step(m, last && n_new > 0));
     }
     CK(cudaEventRecord(e0, g_stream));
     // the last prompt step already produced token 0; every further step feeds the token the previous one picked
-    for (int i = 1; i < n_new; ++i) {
-        CK(cudaGraphLaunch(m.graph_decode, g_stream));
-        g_launches += m.launches_decode;
-    }
+    for (int i = 1; i < n_new; ++i) TRY(run_step(m, true));
     CK(cudaEventRecord(e1, g_stream));
     }
     m.host_pos = n_prompt + std::max(0, n_new - 1);

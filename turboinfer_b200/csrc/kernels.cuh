@@ -105,9 +105,10 @@ __global__ void dequantize_flat_kernel(const int8_t* q8, const int32_t* q32, siz
 // Each source keeps its own per-tensor scale / zero-point (written per column into colscale / colzterm).
 // ---------------------------------------------------------------------------------------------------
 struct PackSrc {
-    const float* w;   // [K][n] fp32, device
-    int n;
-    const float* sz;  // device: scale, zero_point
+    const float* w;   // fp32 on the device: element (k, c) at w[k * ld + c] -- a whole tensor or a tensor-parallel shard view
+    int n;            // columns of the view
+    int ld;           // row stride of the underlying tensor (= n when the view is the whole tensor)
+    const float* sz;  // device: scale, zero_point (of the WHOLE tensor: quantize first, then shard -- SURVEY.md 8e)
 };
 struct PackArgs {
     PackSrc src[3];
@@ -156,7 +157,7 @@ __global__ void pack_kernel(const PackArgs a) {
                 const int k = chunk * L.kc + s * kl + e;
                 int qv = 0;
                 const bool el_live = col_live && k < L.K;
-                if (el_live) qv = quantize_one(a.src[si].w[(size_t)k * a.src[si].n + sc], a.qtype, scale, zp);
+                if (el_live) qv = quantize_one(a.src[si].w[(size_t)k * a.src[si].ld + sc], a.qtype, scale, zp);
                 int word, shift;
                 lane_elem_pos(L.bits, e, word, shift);
                 if (L.bits == 4) {
