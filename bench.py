@@ -43,6 +43,9 @@ WORKLOADS = {
     "llama7b-int4-decode256": ("llama7b", "int4", 4, 256, 1024),
     "llama7b-int8-decode256": ("llama7b", "int8", 4, 256, 1024),
     "bench-small-int8-decode128": ("bench-small", "int8", 4, 128, 256),
+    # tensor-parallel parity / scaling cases of BASELINE.json (run with --tp under torchrun)
+    "llama13b-int8-decode128": ("llama13b", "int8", 4, 128, 512),
+    "llama70b-int4-decode64": ("llama70b", "int4", 4, 64, 512),
 }
 QT = {"int8": 0, "int4": 1}
 
@@ -147,6 +150,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="tinyllama-int4-decode512", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tp", action="store_true", help="the N ranks form ONE tensor-parallel group decoding one sequence (strong scaling) "
+                                                      "instead of N data-parallel replicas")
     ap.add_argument("--layers", type=int, default=0, help="debug: truncate depth (the number is then NOT a bench value)")
     args = ap.parse_args()
 
@@ -156,7 +161,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": args.workload, "shape": dict(SHAPES[shape]), "weights": qname + " symmetric per-tensor (reference default)",
               "batch": 1, "prompt_tokens": n_prompt, "new_tokens": n_new, "kv_cache": "fp32 paged, 64 tokens/page",
-              "attention": "multi-head (mode B), RoPE per head", "parallelism": f"dp{world}" if world > 1 else "single",
+              "attention": "multi-head (mode B), RoPE per head",
+              "parallelism": (f"tp{world}" if args.tp else f"dp{world}") if world > 1 else "single",
               "l2": "weights 598 MB > 126 MB L2: every decode step streams them from HBM"}
 
     if args.impl == "reference":
@@ -187,12 +193,19 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl")
     tb.init(local_rank)
+    tp = world if (args.tp and world > 1) else 1
+    if tp > 1:
+        # the NCCL id of the tensor-parallel group travels over a gloo side channel
+        side = dist.new_group(backend="gloo")
+        box = [tb.tp_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=side)
+        tb.tp_init(world, rank, box[0])
     meta = dict(SHAPES[shape])
     if args.layers:
         meta = meta_with_layers(meta, args.layers)
-    model = tb.Model(meta, QT[qname], attn_mode=1, rope_mode=1, max_seq=max_seq)
+    model = tb.Model(meta, QT[qname], attn_mode=1, rope_mode=1, max_seq=max_seq, tp=tp)
     model.load_synthetic()
-    prompt = prompt_tokens(n_prompt, meta["vocab"], offset=rank)
+    prompt = prompt_tokens(n_prompt, meta["vocab"], offset=0 if tp > 1 else rank)
 
     def barrier():
         tb.lib().ti_b200_sync()
@@ -229,8 +242,9 @@ def main():
         t = torch.tensor([dev_total_ms, wall_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_total_ms, wall_total = float(t[0]), float(t[1])
-    tokens_dev = world * args.steps * (n_new - 1)
-    tokens_e2e = world * args.steps * n_new
+    seqs = 1 if tp > 1 else world   # tensor parallel: the ranks share one sequence
+    tokens_dev = seqs * args.steps * (n_new - 1)
+    tokens_e2e = seqs * args.steps * n_new
     value = tokens_dev / (dev_total_ms / 1e3)
     e2e = tokens_e2e / wall_total
 
@@ -250,7 +264,7 @@ def main():
         launch_us = 1e3 * dev_total_ms / args.steps
         launch_gbs = launch_bytes / (launch_us * 1e-6) / 1e9
         wb, kb = model.step_bytes(n_prompt + n_new // 2)
-        step_gbs = (wb + kb) * value / world / 1e9
+        step_gbs = (wb + kb) * value / seqs / 1e9   # per GPU (step_bytes counts this rank's shards)
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "r01_ncu_decode_kernel_summary.json")) as f:
@@ -259,19 +273,20 @@ def main():
             traffic = None
         out = {
             "metric": "decode_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak",
             "vs_baseline": None, "dtype": "int32 accumulate (dp4a) of " + qname + " weights x 24-bit fixed-point activations, f32 elsewhere",
             "data": "synthetic", "config": config,
             "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 4 * n_prompt, "d2h_bytes_per_step": 4 * n_new},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "mega_decode_kernel<%d> (persistent: one launch decodes %d tokens)" % (4 if qname == "int4" else 8, n_new - 1),
+            "roofline": {"bound": "hbm", "kernel": ("gemv_kernel<%d> + NCCL all-reduce per layer (per-op engine, tensor parallel; per-GPU bytes)" % (4 if qname == "int4" else 8)) if tp > 1 else
+                         "mega_decode_kernel<%d> (persistent: one launch decodes %d tokens)" % (4 if qname == "int4" else 8, n_new - 1),
                          "achieved": launch_gbs, "peak": peak, "unit": "GB/s", "frac": launch_gbs / peak,
                          "traffic": traffic, "peak_source": peak_src + ", sustained (the launch lasts hundreds of ms)",
                          "frac_of_8TBps_spec": launch_gbs / 8000.0, "alg_bytes_per_launch": launch_bytes, "us_per_launch": launch_us},
             "per_kernel": per_kernel,
             "whole_step": {"alg_bytes_per_token": wb + kb, "weight_bytes": wb, "kv_bytes_mid_run": kb, "GBps": step_gbs,
                            "frac_of_measured_peak": step_gbs / peak, "frac_of_8TBps_spec": step_gbs / 8000.0,
-                           "us_per_token": 1e6 / (value / world)},
+                           "us_per_token": 1e6 / (value / seqs)},
             "clocks": clocks, "tokens_tail": [int(x) for x in toks[-4:]], "wall_s_timed_region": t_all,
             "device": tb.device_info(),
         }

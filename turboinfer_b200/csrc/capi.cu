@@ -603,7 +603,7 @@ int capture_graph(Model& m, bool with_head, cudaGraphExec_t* out) {
 
 // one forward pass on the per-op engine: replay the captured graph, or (tensor parallel) enqueue the kernels directly
 int run_step(Model& m, bool with_head) {
-    if (m.tp == 1) {
+    if (m.graph_decode != nullptr) {
         CK(cudaGraphLaunch(with_head ? m.graph_decode : m.graph_prefill, g_stream));
         g_launches += with_head ? m.launches_decode : m.launches_prefill;
         return 0;
@@ -1601,7 +1601,10 @@ int ti_b200_model_finalize(ti_model_t h) {
     if (m.use_mega) TRY(build_mega(m));
     m.use_ll = m.use_mega && eng && std::string(eng) == "ll";   // experimental dataflow variant, off by default
     if (m.use_ll) TRY(build_mega_ll(m));
-    if (m.tp == 1) {   // tensor-parallel steps hold NCCL calls: they are enqueued directly, not replayed from a graph
+    // tensor-parallel steps hold NCCL all-reduces: NCCL supports stream capture, so they are replayed from a graph as
+    // well (TURBOINFER_B200_TP_GRAPH=0 enqueues them directly instead)
+    const char* tpg = getenv("TURBOINFER_B200_TP_GRAPH");
+    if (m.tp == 1 || !(tpg && atoi(tpg) == 0)) {
         TRY(capture_graph(m, true, &m.graph_decode));
         TRY(capture_graph(m, false, &m.graph_prefill));
     }
@@ -1638,7 +1641,7 @@ int ti_b200_model_step_bytes(ti_model_t h, int32_t t, double* weight_bytes, doub
     Model* m = get_model(h);
     if (!m || !m->finalized) return fail("invalid or unfinalized model handle");
     double wb = 0, kb = 0;
-    const double H = m->cfg.hidden;
+    const double H = m->cfg.hidden / m->tp;   // KV rows are as wide as this rank's heads
     auto add = [&](const std::unique_ptr<QWeight>& w) {
         if (!w) return;
         wb += (double)w->L.K * w->L.N * w->L.bits / 8.0 + 4.0 * w->L.N + 4.0 * (w->L.K + w->L.N);
