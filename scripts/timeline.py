@@ -26,7 +26,10 @@ for i, r in enumerate(ts):
     sub = ""
     if r[6] > 0:
         pts = [r[1], r[6], r[7], r[8], r[9], r[10]]
-        sub = "   | prologue: " + " ".join(f"{(b - a) * f:5.2f}" for a, b in zip(pts[:-1], pts[1:])) + f" | ready stages {r[11]}"
+        cons = os.environ.get("TURBOINFER_B200_DBG_NOMATH") == "3"
+        if cons:
+            pts = [r[2], r[8], r[9], r[10], r[3]]
+        sub = "   | prologue: " + " ".join(f"{(b - a) * f:5.2f}" for a, b in zip(pts[:-1], pts[1:])) + ("" if cons else f" | ready stages {r[11]}")
     print(f"{i:3d} {nm:7s} " + " ".join(f"{x:8.2f}" for x in d) + f"  {(r[5]-r[0])*f:8.2f}" + sub)
 print("prologue columns: stats gathered | rms+scale | x,w loads issued..arrived | (gap) | digits stored | final barrier")
 print("step total us:", (ts[-1, 5] - ts[0, 0]) * f)

@@ -19,6 +19,7 @@
 
 #include "mega_ll.cuh"
 #include "gemm_tc.cuh"
+#include "prefill.cuh"
 
 using namespace tib;
 
@@ -290,6 +291,12 @@ struct Model {
     int launches_decode = 0, launches_prefill = 0;  // kernels per captured step
     // persistent-kernel engine
     bool use_mega = false;
+    // batched prefill (tensor-core GEMM path): scratch sized for pf_cap prompt rows
+    int pf_cap = 0;
+    DevBuf<float> pf_x, pf_qkv, pf_attn, pf_gu, pf_act, pf_sx;
+    DevBuf<int8_t> pf_planes;
+    DevBuf<long long> pf_sxf;
+    DevBuf<int> pf_tokens;
     int tp = 1, tp_rank = 0;   // tensor-parallel degree / rank of this model
     DevBuf<float> ar_tmp;      // [H] partial output of a row-parallel GEMV, all-reduced in place
     bool use_ll = false;   // dataflow (LL) variant of the persistent kernel
@@ -704,7 +711,9 @@ int build_mega(Model& m) {
     m.mega_max_units = max_units;
     m.mega_attn_floats = attn_scratch_floats(m.attn_dim, kConsumerThreads);
     m.mega_stages = 0;
-    for (int s = kMaxStages; s >= 2; --s)
+    int max_stages = kMaxStages;
+    if (const char* e = getenv("TURBOINFER_B200_STAGES")) max_stages = std::max(2, std::min(kMaxStages, atoi(e)));   // experiments
+    for (int s = max_stages; s >= 2; --s)
         if (mega_smem_bytes(s, max_kpad, max_units, m.mega_attn_floats) <= 227 * 1024) { m.mega_stages = s; break; }
     if (m.mega_stages == 0) return fail("persistent kernel does not fit shared memory");
     m.mega_smem = mega_smem_bytes(m.mega_stages, max_kpad, max_units, m.mega_attn_floats);
@@ -1032,6 +1041,101 @@ int gemm_q_dev(QWeight& w, const float* x_dev, float* y_dev, int M, float* kerne
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
     }
+    return 0;
+}
+
+// ---- batched prefill on the tensor cores --------------------------------------------------------------------------
+// One GEMM of the prefill path: activations are already digit planes; no host synchronisation.
+int pf_gemm(Model& m, QWeight& w, int M, int m_pad, float* y, const float* resid) {
+    TRY(ensure_kmajor(w));
+    if (w.k_pad != (layout_kpad(w.L) + kGemmBK - 1) / kGemmBK * kGemmBK) return fail("internal: k_pad mismatch");
+    CUtensorMap map_a, map_b;
+    TRY(make_tmap_u8_2d(&map_a, m.pf_planes.p, (uint64_t)w.k_pad, (uint64_t)3 * m_pad));
+    TRY(make_tmap_u8_2d(&map_b, w.kmajor.p, (uint64_t)w.k_pad, (uint64_t)w.n_pad));
+    GemmArgs g{};
+    g.M = M; g.N = w.L.N; g.K = w.L.K;
+    g.m_pad = m_pad; g.k_pad = w.k_pad;
+    g.a_signed_b = w.L.bits == 8 ? 1 : 0;
+    g.woff = w.L.bits == 4 ? w.offset4 : 0;
+    g.sx = m.pf_sx.p; g.sxf = m.pf_sxf.p;
+    g.colscale = w.colscale.p;
+    g.colzterm = w.has_zterm ? w.colzterm.p : nullptr;
+    g.y = y;
+    g.resid = resid;
+    const dim3 grid((w.L.N + kGemmBN - 1) / kGemmBN, m_pad / kGemmBM);
+    gemm_i8_tc_kernel<<<grid, kGemmThreads, kGemmSmemBytes, g_stream>>>(map_a, map_b, g);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+int pf_digits(Model& m, const float* x, const float* norm_w, int M, int K, int m_pad, int k_pad) {
+    // planes of rows >= M and columns >= K stay zero: the buffer is cleared when it is (re)allocated and only rows < M,
+    // columns < k_pad are written -- k_pad differs per weight, so clear the tail columns explicitly
+    CK(cudaMemsetAsync(m.pf_planes.p, 0, (size_t)3 * m_pad * k_pad, g_stream));
+    rmsnorm_digits_kernel<<<M, 256, (size_t)K * sizeof(float), g_stream>>>(x, norm_w, m.cfg.rms_eps, M, K, m_pad, k_pad, m.pf_planes.p, m.pf_sx.p, m.pf_sxf.p);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+bool prefill_gemm_eligible(const Model& m, int M) {
+    if (M < 32 || m.tp != 1 || m.cfg.attn_mode != 1 || m.cfg.rope_mode == 2 || m.attn_dim > 128 || (m.attn_dim & 3)) return false;
+    if (const char* e = getenv("TURBOINFER_B200_PREFILL")) if (std::string(e) == "decode") return false;
+    for (auto& ly : m.layers) if (!(ly.qkv && ly.o && ly.gateup && ly.down)) return false;
+    return true;
+}
+
+// forward_pass over prompt[0 .. M): fills the KV cache for positions pos0 .. pos0 + M - 1 (pos0 = 0 after reset()).
+// The hidden states stay in pf_x; the caller runs the last prompt token through the decode engine for the logits.
+int prefill_gemm(Model& m, const int* prompt_dev, int M) {
+    static bool attr = false;
+    if (!attr) {
+        CK(cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+        CK(cudaFuncSetAttribute(rmsnorm_digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr = true;
+    }
+    const int H = m.cfg.hidden, I = std::max(m.cfg.inter, 1);
+    const int m_pad = (M + kGemmBM - 1) / kGemmBM * kGemmBM;
+    int kmax = 0;
+    for (auto& ly : m.layers)
+        for (QWeight* w : {ly.qkv.get(), ly.o.get(), ly.gateup.get(), ly.down.get()}) kmax = std::max(kmax, (layout_kpad(w->L) + kGemmBK - 1) / kGemmBK * kGemmBK);
+    if (M > m.pf_cap) {
+        TRY(m.pf_x.alloc((size_t)M * H));
+        TRY(m.pf_qkv.alloc((size_t)M * 3 * H));
+        TRY(m.pf_attn.alloc((size_t)M * H));
+        TRY(m.pf_gu.alloc((size_t)M * 2 * I));
+        TRY(m.pf_act.alloc((size_t)M * I));
+        TRY(m.pf_sx.alloc(M));
+        TRY(m.pf_sxf.alloc(M));
+        TRY(m.pf_planes.alloc((size_t)3 * m_pad * kmax));
+        m.pf_cap = M;
+    }
+    const int pos0 = 0;
+    const int rope_dim = m.cfg.rope_mode == 1 ? H / m.cfg.heads : 0;
+    embed_rows_kernel<<<M, 256, 0, g_stream>>>(m.tok_emb.p, prompt_dev, m.pf_x.p, H);
+    ++g_launches;
+    for (auto& ly : m.layers) {
+        TRY(ensure_kmajor(*ly.qkv));
+        TRY(pf_digits(m, m.pf_x.p, ly.attn_norm.p, M, H, m_pad, ly.qkv->k_pad));
+        TRY(pf_gemm(m, *ly.qkv, M, m_pad, m.pf_qkv.p, nullptr));
+        rope_kv_kernel<<<M, 256, 0, g_stream>>>(m.pf_qkv.p, M, H, rope_dim, m.inv_freq.p, pos0, ly.k_pool.p, ly.v_pool.p, m.page_table.p, m.page_tokens);
+        causal_attention_kernel<<<dim3(m.attn_heads, (M + kPfQ - 1) / kPfQ), kPfThreads, 0, g_stream>>>(
+            m.pf_qkv.p, M, H, m.attn_dim, 1.0f / sqrtf((float)m.attn_dim), pos0, ly.k_pool.p, ly.v_pool.p, m.page_table.p, m.page_tokens, m.pf_attn.p);
+        g_launches += 2;
+        TRY(ensure_kmajor(*ly.o));
+        TRY(pf_digits(m, m.pf_attn.p, nullptr, M, H, m_pad, ly.o->k_pad));
+        TRY(pf_gemm(m, *ly.o, M, m_pad, m.pf_x.p, m.pf_x.p));
+        TRY(ensure_kmajor(*ly.gateup));
+        TRY(pf_digits(m, m.pf_x.p, ly.ffn_norm.p, M, H, m_pad, ly.gateup->k_pad));
+        TRY(pf_gemm(m, *ly.gateup, M, m_pad, m.pf_gu.p, nullptr));
+        if (ly.has_gate) swiglu_rows_kernel<<<grid_for((size_t)M * I), 256, 0, g_stream>>>(m.pf_gu.p, m.pf_act.p, (size_t)M, (size_t)I);
+        else relu_rows_kernel<<<grid_for((size_t)M * I), 256, 0, g_stream>>>(m.pf_gu.p, m.pf_act.p, (size_t)M * I);
+        ++g_launches;
+        TRY(ensure_kmajor(*ly.down));
+        TRY(pf_digits(m, m.pf_act.p, nullptr, M, I, m_pad, ly.down->k_pad));
+        TRY(pf_gemm(m, *ly.down, M, m_pad, m.pf_x.p, m.pf_x.p));
+    }
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -1716,8 +1820,19 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     if (m.use_mega) {
-        // launch 1: the prompt (its last step picks token 0); launch 2: the decode loop, timed
-        TRY(run_mega(m, n_prompt, n_prompt, n_new > 0 ? n_prompt - 1 : n_prompt));
+        // launch 1: the prompt (its last step picks token 0); launch 2: the decode loop, timed.
+        // Long prompts (>= 32 tokens besides the last one, the reference's own GEMM threshold, tensor_engine.cpp:561) go
+        // through the tensor-core GEMM path: all tokens but the last fill the KV cache in one batched forward pass, the
+        // last one runs through the decode engine and yields the first logits.
+        if (prefill_gemm_eligible(m, n_prompt - 1)) {
+            const int M = n_prompt - 1;
+            TRY(prefill_gemm(m, m.prompt.p, M));
+            CK(cudaMemcpyAsync(&m.state.p->pos, &M, sizeof(int), cudaMemcpyHostToDevice, g_stream));
+            CK(cudaMemcpyAsync(m.prompt.p, prompt + M, sizeof(int), cudaMemcpyHostToDevice, g_stream));
+            TRY(run_mega(m, 1, 1, n_new > 0 ? 0 : 1));
+        } else {
+            TRY(run_mega(m, n_prompt, n_prompt, n_new > 0 ? n_prompt - 1 : n_prompt));
+        }
         CK(cudaEventRecord(e0, g_stream));
         TRY(run_mega(m, 0, n_new - 1, 0));
         CK(cudaEventRecord(e1, g_stream));

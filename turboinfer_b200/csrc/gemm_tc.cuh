@@ -38,6 +38,7 @@ struct GemmArgs {
     const float* colscale;  // [N]
     const float* colzterm;  // [N] or nullptr
     float* y;               // [M][N]
+    const float* resid;     // optional [M][N] added to the result (may alias y): the residual connections of the decoder
 };
 
 // ---- activations -> digit planes [3][m_pad][k_pad] (K-major rows), one block per row ------------------------
@@ -233,7 +234,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         const int hi = (int)(t >> 23), lo = (int)(t & 0x7FFFFF);
                         const float tf = fmaf((float)hi, 8388608.0f, (float)lo);
                         const float zt = g.colzterm ? g.colzterm[n] : 0.f;
-                        g.y[(size_t)row * g.N + n] = (fmaf(zt, fsxf, tf) * sx) * g.colscale[n];   // the GEMV epilogue's expression
+                        float yv = (fmaf(zt, fsxf, tf) * sx) * g.colscale[n];   // the GEMV epilogue's expression
+                        if (g.resid) yv = g.resid[(size_t)row * g.N + n] + yv;
+                        g.y[(size_t)row * g.N + n] = yv;
                     }
                 }
             }

@@ -484,7 +484,8 @@ __device__ __forceinline__ float gemv_stage_x_known(const GemvArgs& a, const flo
 // IDP4A them into per-unit accumulators; when the warp's run over a group ends, reduce the digit sums over the 8
 // k-slices (3 shuffle steps) and add them to the column sums in shared memory.
 template <int BITS, int DBG = 0>
-__device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, uint32_t& it, int warp, int lane) {
+__device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, uint32_t& it, int warp, int lane,
+                                             long long* dbg = nullptr) {
     const QLayout& L = a.L;
     const int S = a.stages;
     const int C = L.nchunks, nrounds = slab.rounds;
@@ -539,6 +540,7 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
         XDigits<BITS> xd;
         if (have) xd = load_xdigits<BITS>(xlane + chunk * kChunkBytes);  // does not depend on the stage: before the wait
         if (DBG != 2 && !ready) mbar_wait(&sm.full[st], par);
+        if (dbg && r == 0) dbg[0] = clock64();
         ready = false;
         const uint32_t st_n = st + 1 == (uint32_t)S ? 0u : st + 1, par_n = st + 1 == (uint32_t)S ? par ^ 1u : par;
         if (have) {
@@ -564,8 +566,11 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
         __syncwarp();
         if (DBG != 2 && lane == 0) mbar_arrive(&sm.empty[st]);  // this warp is done reading the stage
     }
+    if (dbg) dbg[1] = clock64();
     if (dirty) flush();
+    if (dbg) dbg[2] = clock64();
     bar_sync(1, kConsumerThreads);
+    if (dbg) dbg[3] = clock64();
 }
 
 // Values the epilogue needs that do not depend on this phase's arithmetic; loaded early (before the grid barrier

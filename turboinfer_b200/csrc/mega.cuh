@@ -18,6 +18,8 @@
 namespace tib {
 
 enum MegaPhaseType : int { PH_GEMV = 0, PH_ATTN = 1 };
+struct MegaArgs;
+__device__ __forceinline__ bool getenv_dbg_consume(const MegaArgs& m);
 constexpr int kStampsPerPhase = 12;  // debug timeline: 6 phase-level stamps + 6 inside the prologue
 enum MegaSrc : int { SRC_PTR = 0, SRC_EMB = 1 };
 
@@ -64,6 +66,7 @@ struct MegaArgs {
     const XStats* emb_stats;  // [V]: statistics of every embedding row (against the first norm weight)
 };
 
+__device__ __forceinline__ bool getenv_dbg_consume(const MegaArgs& m) { return m.dbg_nomath == 3; }
 TIB_HD size_t mega_smem_bytes(int stages, int max_kpad, int max_units, int attn_floats) {
     return gemv_smem_bytes_for(stages, max_kpad, max_units) + 16 + (size_t)attn_floats * 4 + 16 + ((sizeof(MegaPhase) + 15) & ~size_t(15));
 }
@@ -583,13 +586,16 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                         int ready = 0;  // stages of this phase already in shared memory when its main loop starts
                         for (int i = 0; i < m.stages && i < slab.rounds; ++i) {
                             const uint32_t ii = it + i;
-                            ready += mbar_try_wait(&sm.full[ii % m.stages], (ii / m.stages) & 1) ? 1 : 0;
+                            ready += mbar_test_wait(&sm.full[ii % m.stages], (ii / m.stages) & 1) ? 1 : 0;   // non-blocking probe
                         }
                         ts[11] = ready;
                     }
+#ifdef TIB_MEGA_DEBUG_VARIANTS
                     if (m.dbg_nomath == 2) gemv_consume<BITS, 2>(g, slab, sm, it, warp, lane);
-                    else if (m.dbg_nomath) gemv_consume<BITS, 1>(g, slab, sm, it, warp, lane);
-                    else gemv_consume<BITS>(g, slab, sm, it, warp, lane);
+                    else if (m.dbg_nomath == 1) gemv_consume<BITS, 1>(g, slab, sm, it, warp, lane);
+                    else
+#endif
+                    gemv_consume<BITS>(g, slab, sm, it, warp, lane, (stamp && getenv_dbg_consume(m)) ? ts + 8 : nullptr);
                     if (stamp) ts[3] = clock64();
                     out_st = gemv_epilogue(g, slab, sm, s_x, resid, ctx, pre, tid, lane);
                 }
