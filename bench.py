@@ -42,6 +42,8 @@ WORKLOADS = {
     "tinyllama-int4-decode512": ("tinyllama", "int4", 4, 512, 1024),
     "llama7b-int4-decode256": ("llama7b", "int4", 4, 256, 1024),
     "llama7b-int8-decode256": ("llama7b", "int8", 4, 256, 1024),
+    # BASELINE.json configs[2]: prefill 2048 (tcgen05 GEMM path) + decode 256
+    "llama7b-int4-prefill2048-decode256": ("llama7b", "int4", 2048, 256, 2560),
     "bench-small-int8-decode128": ("bench-small", "int8", 4, 128, 256),
     # tensor-parallel parity / scaling cases of BASELINE.json (run with --tp under torchrun)
     "llama13b-int8-decode128": ("llama13b", "int8", 4, 128, 512),
@@ -221,7 +223,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = tb.launch_count()
-    dev_ms, wall = [], []
+    dev_ms, wall, prefill_ms = [], [], []
     toks = None
     t_all0 = time.perf_counter()
     for _ in range(args.steps):
@@ -229,6 +231,7 @@ def main():
         toks, _, ms = model.generate_greedy(prompt, n_new)      # host prompt in, host tokens out
         wall.append(time.perf_counter() - t0)
         dev_ms.append(ms)
+        prefill_ms.append(model.last_prefill_ms())
     barrier()
     t_all = time.perf_counter() - t_all0
     launches = tb.launch_count() - launches0
@@ -287,6 +290,8 @@ def main():
             "whole_step": {"alg_bytes_per_token": wb + kb, "weight_bytes": wb, "kv_bytes_mid_run": kb, "GBps": step_gbs,
                            "frac_of_measured_peak": step_gbs / peak, "frac_of_8TBps_spec": step_gbs / 8000.0,
                            "us_per_token": 1e6 / (value / seqs)},
+            "prefill": {"prompt_tokens": n_prompt, "ms": statistics.median(prefill_ms), "tokens_per_s": n_prompt / (statistics.median(prefill_ms) * 1e-3),
+                        "path": "tcgen05 INT8 GEMM, batched" if n_prompt > 32 else "decode engine, token by token"},
             "clocks": clocks, "tokens_tail": [int(x) for x in toks[-4:]], "wall_s_timed_region": t_all,
             "device": tb.device_info(),
         }

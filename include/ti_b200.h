@@ -158,6 +158,9 @@ int ti_b200_decode_step(ti_model_t m, int32_t token, float* logits_host, int32_t
 int ti_b200_generate_greedy(ti_model_t m, const int32_t* prompt, int32_t n_prompt, int32_t n_new, int32_t stop_on_eos,
                             int32_t* out_tokens, int32_t* n_out, float* logits_host, float* decode_ms);
 
+/* CUDA-event time of the prompt phase (prefill) of the last ti_b200_generate_greedy call on this model, in ms */
+int ti_b200_model_last_prefill_ms(ti_model_t m, float* ms);
+
 /* ---- instrumentation for bench.py ------------------------------------------------------------------ */
 /* number of kernels this library has launched since init (the bench's `gpu_launches`) */
 int ti_b200_launch_count(uint64_t* n);

@@ -72,6 +72,7 @@ SYMBOLS = {
     "ti_b200_model_step_bytes": (C.c_int, [C.c_uint64, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ti_b200_decode_step": (C.c_int, [C.c_uint64, C.c_int32, _f, _i32]),
     "ti_b200_generate_greedy": (C.c_int, [C.c_uint64, _i32, C.c_int32, C.c_int32, C.c_int32, _i32, _i32, _f, _f]),
+    "ti_b200_model_last_prefill_ms": (C.c_int, [C.c_uint64, _f]),
     "ti_b200_launch_count": (C.c_int, [C.POINTER(C.c_uint64)]),
     "ti_b200_bench_gemv": (C.c_int, [C.POINTER(C.c_uint64), C.c_size_t, C.c_size_t, _f]),
     "ti_b200_model_bench_gemv": (C.c_int, [C.c_uint64, C.c_int, C.c_size_t, _f, C.POINTER(C.c_double)]),
@@ -368,6 +369,11 @@ class Model:
         n = C.c_size_t()
         _ck(lib().ti_b200_debug_timeline(self.handle, token, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size, C.byref(n)))
         return buf[: 12 * n.value].reshape(n.value, 12).copy()
+
+    def last_prefill_ms(self) -> float:
+        ms = C.c_float()
+        _ck(lib().ti_b200_model_last_prefill_ms(self.handle, C.byref(ms)))
+        return ms.value
 
     def bench_gemv(self, slot: int, reps: int):
         """(avg ms per launch, algorithmic bytes per launch) of the model's own GEMVs of one kind, back to back."""

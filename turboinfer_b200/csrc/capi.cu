@@ -293,6 +293,7 @@ struct Model {
     bool use_mega = false;
     // batched prefill (tensor-core GEMM path): scratch sized for pf_cap prompt rows
     int pf_cap = 0;
+    float last_prefill_ms = 0.f;   // CUDA-event time of the prompt phase of the last generate call
     DevBuf<float> pf_x, pf_qkv, pf_attn, pf_gu, pf_act, pf_sx;
     DevBuf<int8_t> pf_planes;
     DevBuf<long long> pf_sxf;
@@ -1816,9 +1817,11 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
         io.hist_cap = n_new;
     }
     CK(cudaMemcpyAsync(m.io.p, &io, sizeof(io), cudaMemcpyHostToDevice, g_stream));
-    cudaEvent_t e0, e1;
+    cudaEvent_t e0, e1, ep;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
+    CK(cudaEventCreate(&ep));
+    CK(cudaEventRecord(ep, g_stream));
     if (m.use_mega) {
         // launch 1: the prompt (its last step picks token 0); launch 2: the decode loop, timed.
         // Long prompts (>= 32 tokens besides the last one, the reference's own GEMM threshold, tensor_engine.cpp:561) go
@@ -1856,8 +1859,10 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
     CK(cudaStreamSynchronize(g_stream));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, e0, e1));
+    CK(cudaEventElapsedTime(&m.last_prefill_ms, ep, e0));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    cudaEventDestroy(ep);
     if (decode_ms) *decode_ms = ms;
     int produced = n_new;
     if (stop_on_eos)
@@ -1865,6 +1870,13 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
             if (toks[i] == 2) { produced = i + 1; break; }  // hard-coded EOS id 2 (:760)
     for (int i = 0; i < produced; ++i) out_tokens[i] = toks[i];
     if (n_out) *n_out = produced;
+    return 0;
+}
+
+int ti_b200_model_last_prefill_ms(ti_model_t h, float* ms) {
+    Model* m = get_model(h);
+    if (!m || !m->finalized) return fail("invalid or unfinalized model handle");
+    *ms = m->last_prefill_ms;
     return 0;
 }
 
