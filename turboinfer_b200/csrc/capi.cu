@@ -1700,7 +1700,11 @@ int ti_b200_model_finalize(ti_model_t h) {
     for (auto& ly : m.layers) complete &= (ly.qkv && ly.o && ly.gateup && ly.down);
     const char* eng = getenv("TURBOINFER_B200_ENGINE");
     const bool want_graph = m.cfg.reserved[0] == 1 || (eng && std::string(eng) == "graph");
-    m.use_mega = complete && !want_graph && m.tp == 1;
+    bool vec_ok = complete && H % 4 == 0;
+    if (complete)
+        for (auto& ly : m.layers)
+            for (QWeight* w : {ly.qkv.get(), ly.o.get(), ly.gateup.get(), ly.down.get()}) vec_ok &= w->L.K % 4 == 0;
+    m.use_mega = complete && !want_graph && m.tp == 1 && vec_ok;   // the persistent kernel's prologue uses 128-bit loads only
     if (m.tp > 1) TRY(m.ar_tmp.alloc(H));
     TRY(m.prompt.alloc(16));
     if (m.use_mega) TRY(build_mega(m));

@@ -81,30 +81,18 @@ __global__ void gemm_digits_kernel(const float* x, int M, int K, int m_pad, int 
 __global__ void unpack_kmajor_kernel(const uint8_t* packed, QLayout L, int k_pad, uint8_t* wk) {
     const Slab slab = make_slab(L, blockIdx.x);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = lane & 3, s = lane >> 2;
-    const int nq = warp_quads(slab, warp), fq = warp_first_quad(slab, warp);
-    const int kl = L.kc / 8;
-    size_t stage_base = 0;
-    for (int r = 0; r < nq; ++r) {
-        const int q = fq + r;
-        const int grp = q / L.nchunks, chunk = q - grp * L.nchunks;
-        const int live = q >= slab.qfull ? slab.nlast : 4;
-        const size_t qoff = stage_base + (size_t)round_warp_offset(slab, r, warp) * kItemBytes;
-        stage_base += (size_t)round_total(slab, r) * kItemBytes;
-        for (int u = 0; u < live; ++u) {
-            const int n = slab.col0 + 4 * (4 * grp + u) + c;
-            const uint4 wv = *reinterpret_cast<const uint4*>(packed + slab.byte0 + qoff + (size_t)u * kItemBytes + lane * 16);
-            const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
-            for (int e = 0; e < kl; ++e) {
-                const int k = chunk * L.kc + s * kl + e;
-                if (k >= k_pad) continue;
-                int word, shift;
-                lane_elem_pos(L.bits, e, word, shift);
-                const uint32_t v = L.bits == 4 ? (words[word] >> shift) & 0xFu : (words[word] >> shift) & 0xFFu;
-                wk[(size_t)n * k_pad + k] = (uint8_t)v;   // INT4: u = q + woff (0..15); INT8: two's complement q
-            }
+    const int kik = kitem_k(L.bits), nel = L.bits == 4 ? 8 : 4;
+    for_each_quad_word(L, slab, warp, lane, [&](size_t off, int nl, int grp, int chunk, int ki, int widx) {
+        const uint32_t word = *reinterpret_cast<const uint32_t*>(packed + off);
+        for (int i = 0; i < nel; ++i) {
+            int row, kk;
+            kitem_word_elem(L.bits, nl, widx, i, row, kk);
+            const int n = slab.col0 + 16 * grp + row, k = chunk * L.kc + ki * kik + kk;
+            if (k >= k_pad) continue;
+            // INT4: u = q + woff (0..15); INT8: two's complement q
+            wk[(size_t)n * k_pad + k] = (uint8_t)(L.bits == 4 ? (word >> (4 * i)) & 0xFu : (word >> (8 * i)) & 0xFFu);
         }
-    }
+    });
 }
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------

@@ -12,16 +12,18 @@
 //   warps 0..15                 consumers
 //     prologue   x (fp32, optionally RMS-normalised with the reference's roundings) is converted ONCE per GEMV to
 //                24-bit block fixed point, x_k ~= s_x * xf_k with |xf_k| < 2^23, and stored in shared memory as three
-//                8-bit digit planes (xf = d2*65536 + d1*256 + d0; d0, d1 unsigned, d2 signed)
-//     main loop  per 512-byte item (4 columns x 256 k INT4 / 128 k INT8): one LDS.128 of weights, nibbles unpacked in
-//                registers with LOP3 / SHF, products accumulated with IDP4A (4 MACs per instruction) into three int32
-//                accumulators per lane, one per digit.  Integer accumulation is exact and order-independent, so the
-//                result does not depend on how k is split over lanes, warps or (tensor-parallel) GPUs.
-//                B200 measurement (scripts/microbench2.cu): IDP4A issues every 2 cycles per SM sub-partition, which
-//                bounds this loop at 12 cycles per item per SM = 1.8x the HBM rate; the fp32 magic-number unpack it
-//                replaces was bound by the ALU pipe at 18+ cycles per item per SM (below the HBM rate in practice).
-//     reduction  lanes (column c, k-slice s): 3 shuffle steps over s per run of items of one unit, then one shared-
-//                memory integer atomic per (column, digit)
+//                signed 8-bit digit planes (xf = d2*65536 + d1*256 + d0, every digit in [-128, 127])
+//     main loop  warp-level integer MMAs (mma.sync.m16n8k32 u8/s8 x s8 -> s32, SASS IMMA.16832): the A operand is 16
+//                weight columns x 32 k, stored in HBM in fragment order so that one LDS.128 per lane is the fragment (INT4:
+//                of two MMAs -- `w & 0x0F0F0F0F` is the first, `w & 0xF0F0F0F0` the second, 16x too large, which a
+//                shift of its own accumulator undoes exactly); the B operand's 8 columns carry the three digit planes
+//                (5 columns idle: the tensor pipe has >10x headroom here).  Integer accumulation is exact and order-
+//                independent, so the result does not depend on how k is split over warps or (tensor-parallel) GPUs.
+//                B200 measurement (scripts/microbench5.cu): IMMA.16832 issues every ~2-3 cycles per SM; the loop runs at
+//                9 cycles per 512-byte item per SM out of shared memory (bound by the LDS wavefronts) = 2.4x the HBM
+//                rate.  The IDP4A loop it replaces needed 19-27 (scripts/microbench2/3.cu), the fp32 unpack before 18+.
+//     reduction  none across lanes: the C fragment of lane (g, t) already holds the sums of columns g, g+8 for digit
+//                planes 2t, 2t+1; one shared-memory integer atomic per (column, digit) when a warp leaves a group
 //   epilogue                    per column: y = colscale * s_x * (A2*65536 + A1*256 + A0 - off*sum(xf) [+ zero-point
 //                               term]); the integer part is exact (int64), then three fp32 roundings; fused residual / SwiGLU /
 //                               ReLU / RoPE+KV-append / logits+argmax
@@ -38,7 +40,7 @@ namespace tib {
 constexpr int kGemvThreads = (kConsumerWarps + 1) * 32;  // 544
 constexpr int kConsumerThreads = kConsumerWarps * 32;    // 512
 constexpr int kMaxStages = 6;
-constexpr float kXQMax = 8388000.0f;   // bound of |xf|: (1 + 2e-5) * 8388000 + 0.5 < 2^23, so rounding never reaches 2^23
+constexpr float kXQMax = 8355000.0f;   // bound of |xf|: (1 + 2e-5) * 8355000 + 0.5 < 127*65536 + 127*256 + 127, the largest value three signed digits hold
 constexpr int kXCache = 8;             // float4 vectors of x a thread keeps in registers between the two prologue passes
 
 enum GemvEpilogue : int {
@@ -100,73 +102,55 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// ---- integer dot products ----------------------------------------------------------------------------
-__device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c) {  // a, b unsigned bytes
-    int d;
-    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
+// ---- warp-level integer MMA ----------------------------------------------------------------------------
+// D[16 x 8] += A[16 x 32] * B[32 x 8], A = weights (unsigned nibbles-in-bytes for INT4, signed bytes for INT8), B = digits
+__device__ __forceinline__ void imma_u8s8(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {  // a unsigned, b signed
-    int d;
-    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ int dp4a_su(uint32_t a, uint32_t b, int c) {  // a signed, b unsigned
-    int d;
-    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ int dp4a_ss(uint32_t a, uint32_t b, int c) {  // a, b signed
-    int d;
-    asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
+__device__ __forceinline__ void imma_s8s8(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// The digits of one (chunk, k-slice) held in registers: INT4 [digit][half] / INT8 [digit] vectors of 4 words,
-// 128 B apart in shared memory (qlayout.cuh xdigit_word_offset).
+// Accumulators of one warp for the group it is working on.  INT4: lo[] collects the low-nibble MMAs, hi[] the
+// high-nibble ones (operands 16x too large: total = lo + (hi >> 4), exact); two sets each so that consecutive
+// k-items do not wait on one another.  INT8: lo[] only.
 template <int BITS>
-struct XDigits {
-    uint4 v[BITS == 4 ? 6 : 3];
-};
-template <int BITS>
-__device__ __forceinline__ XDigits<BITS> load_xdigits(uint32_t xs) {
-    XDigits<BITS> x;
+struct QuadAcc {
+    int lo[2][4];
+    int hi[BITS == 4 ? 2 : 1][4];
+    __device__ __forceinline__ void clear() {
 #pragma unroll
-    for (int i = 0; i < (BITS == 4 ? 6 : 3); ++i) x.v[i] = lds128s(xs + 128 * i);
-    return x;
-}
-constexpr int kAccPerUnit = 3;  // one int32 accumulator per digit
-
-// One item for one lane: 16 bytes of weights of column c against the digits of k-slice s of the item's chunk.
-// acc: one accumulator per digit; a quad keeps 12 of them busy, so no IDP4A waits on the one before it
-template <int BITS>
-__device__ __forceinline__ void item_dot(const uint4& wv, const XDigits<BITS>& x, int (&acc)[kAccPerUnit]) {
-    const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
-    if constexpr (BITS == 4) {
-        const uint32_t d0a[4] = {x.v[0].x, x.v[0].y, x.v[0].z, x.v[0].w}, d0b[4] = {x.v[1].x, x.v[1].y, x.v[1].z, x.v[1].w};
-        const uint32_t d1a[4] = {x.v[2].x, x.v[2].y, x.v[2].z, x.v[2].w}, d1b[4] = {x.v[3].x, x.v[3].y, x.v[3].z, x.v[3].w};
-        const uint32_t d2a[4] = {x.v[4].x, x.v[4].y, x.v[4].z, x.v[4].w}, d2b[4] = {x.v[5].x, x.v[5].y, x.v[5].z, x.v[5].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t lo = w[j] & 0x0F0F0F0Fu;
-            const uint32_t hi = (w[j] >> 4) & 0x0F0F0F0Fu;
-            acc[0] = dp4a_uu(lo, d0a[j], acc[0]);
-            acc[1] = dp4a_uu(lo, d1a[j], acc[1]);
-            acc[2] = dp4a_us(lo, d2a[j], acc[2]);
-            acc[0] = dp4a_uu(hi, d0b[j], acc[0]);
-            acc[1] = dp4a_uu(hi, d1b[j], acc[1]);
-            acc[2] = dp4a_us(hi, d2b[j], acc[2]);
-        }
-    } else {
-        const uint32_t d0[4] = {x.v[0].x, x.v[0].y, x.v[0].z, x.v[0].w}, d1[4] = {x.v[1].x, x.v[1].y, x.v[1].z, x.v[1].w};
-        const uint32_t d2[4] = {x.v[2].x, x.v[2].y, x.v[2].z, x.v[2].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            acc[0] = dp4a_su(w[j], d0[j], acc[0]);
-            acc[1] = dp4a_su(w[j], d1[j], acc[1]);
-            acc[2] = dp4a_ss(w[j], d2[j], acc[2]);
+        for (int i = 0; i < 4; ++i) {
+            lo[0][i] = lo[1][i] = 0;
+            hi[0][i] = 0;
+            if (BITS == 4) hi[BITS == 4 ? 1 : 0][i] = 0;
         }
     }
+    __device__ __forceinline__ int total(int i) const {
+        if constexpr (BITS == 4) return (lo[0][i] + lo[1][i]) + ((hi[0][i] + hi[1][i]) >> 4);
+        else return lo[0][i] + lo[1][i];
+    }
+};
+
+// One k-item: the lane's A fragment registers (w.x .. w.w = registers 0..3) against the digits of the item's k range
+// (INT4: xv = {b0, b1 of the first 32 k, b0, b1 of the next 32 k}; INT8: xv.x, xv.y).
+template <int BITS>
+__device__ __forceinline__ void kitem_mma(QuadAcc<BITS>& acc, int par, const uint4& w, const uint4& xv) {
+    if constexpr (BITS == 4) {
+        imma_u8s8(acc.lo[par], w.x & 0x0F0F0F0Fu, w.y & 0x0F0F0F0Fu, w.z & 0x0F0F0F0Fu, w.w & 0x0F0F0F0Fu, xv.x, xv.y);
+        imma_u8s8(acc.hi[par], w.x & 0xF0F0F0F0u, w.y & 0xF0F0F0F0u, w.z & 0xF0F0F0F0u, w.w & 0xF0F0F0F0u, xv.z, xv.w);
+    } else {
+        imma_s8s8(acc.lo[par], w.x, w.y, w.z, w.w, xv.x, xv.y);
+    }
+}
+template <int BITS>
+__device__ __forceinline__ uint4 load_xfrag(uint32_t addr) {
+    if constexpr (BITS == 4) return lds128s(addr);
+    else { const uint2 v = lds64s(addr); return make_uint4(v.x, v.y, 0u, 0u); }
 }
 
 __device__ __forceinline__ unsigned long long argmax_pack(float v, int idx) {
@@ -295,12 +279,14 @@ __device__ __forceinline__ void x_store_digits(uint8_t* xd, int v, float4 y, flo
     const int f0 = __float2int_rn(y.x * inv_s), f1 = __float2int_rn(y.y * inv_s), f2 = __float2int_rn(y.z * inv_s),
               f3 = __float2int_rn(y.w * inv_s);
     sxf += (long long)((f0 + f1) + (f2 + f3));
+    // signed digits: the bytes of u = f + 0x808080 are d + 128 (no carries to track), so digit = byte ^ 0x80
+    const int u0 = f0 + 0x808080, u1 = f1 + 0x808080, u2 = f2 + 0x808080, u3 = f3 + 0x808080;
     // byte b of each of the four values -> one word per digit
-    const uint32_t lo01 = __byte_perm(f0, f1, 0x5140), lo23 = __byte_perm(f2, f3, 0x5140);  // [f0.b0 f1.b0 f0.b1 f1.b1]
-    const uint32_t d0 = __byte_perm(lo01, lo23, 0x5410);
-    const uint32_t d1 = __byte_perm(lo01, lo23, 0x7632);
-    const uint32_t hi01 = __byte_perm(f0, f1, 0x0062), hi23 = __byte_perm(f2, f3, 0x0062);  // [f0.b2 f1.b2 . .]
-    const uint32_t d2 = __byte_perm(hi01, hi23, 0x5410);
+    const uint32_t lo01 = __byte_perm(u0, u1, 0x5140), lo23 = __byte_perm(u2, u3, 0x5140);  // [u0.b0 u1.b0 u0.b1 u1.b1]
+    const uint32_t d0 = __byte_perm(lo01, lo23, 0x5410) ^ 0x80808080u;
+    const uint32_t d1 = __byte_perm(lo01, lo23, 0x7632) ^ 0x80808080u;
+    const uint32_t hi01 = __byte_perm(u0, u1, 0x0062), hi23 = __byte_perm(u2, u3, 0x0062);  // [u0.b2 u1.b2 . .]
+    const uint32_t d2 = __byte_perm(hi01, hi23, 0x5410) ^ 0x80808080u;
     const int k = 4 * v;
     *reinterpret_cast<uint32_t*>(xd + xdigit_word_offset(BITS, k, 0)) = d0;
     *reinterpret_cast<uint32_t*>(xd + xdigit_word_offset(BITS, k, 1)) = d1;
@@ -480,52 +466,102 @@ __device__ __forceinline__ float gemv_stage_x_known(const GemvArgs& a, const flo
     return s_x;
 }
 
-// consumers, main loop: one quad per warp per ring stage -- LDS the chunk's digits once, LDS.128 the <= 4 items,
-// IDP4A them into per-unit accumulators; when the warp's run over a group ends, reduce the digit sums over the 8
-// k-slices (3 shuffle steps) and add them to the column sums in shared memory.
+// The same prologue, written for the persistent kernel's instruction footprint (every phase re-enters this code, and
+// the kernel is far larger than the 32 KiB instruction cache): 128-bit loads only -- the host checks K % 4 == 0 and the
+// 16-byte alignment once -- and a single copy of the conversion body.
+template <int BITS, typename StatsFn>
+__device__ __forceinline__ float gemv_stage_x_lean(const GemvArgs& a, const float* x, const GemvSmem& sm, const Slab& slab, bool coherent,
+                                                   StatsFn&& get_stats, int tid, int lane) {
+    const int K = a.L.K, nvec = layout_kpad(a.L) >> 2, kvec = K >> 2;
+    const float4* nw4 = reinterpret_cast<const float4*>(a.norm_w);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (int i = tid; i < slab.ncols * 3; i += kConsumerThreads) sm.acc[i] = 0;
+    constexpr int B = 4;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f), one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 xv[B], wv[B];
+    auto issue = [&](int v0) {
+#pragma unroll
+        for (int i = 0; i < B; ++i) {
+            const int v = v0 + i * kConsumerThreads;
+            xv[i] = v < kvec ? (coherent ? __ldcg(x4 + v) : x4[v]) : zero4;
+            wv[i] = (nw4 != nullptr && v < kvec) ? __ldg(nw4 + v) : one4;
+        }
+    };
+    issue(tid);
+    const XStats st = get_stats();
+    float inv_rms = 1.f, amax = st.am;
+    if (nw4 != nullptr) {
+        inv_rms = rsqrtf(st.ss / (float)K + a.rms_eps);  // :1501
+        amax = amax * inv_rms * 1.00001f;
+    }
+    const bool finite = amax > 0.f && amax < INFINITY;
+    const float inv_s = finite ? __fdividef(kXQMax, amax) : 0.f;
+    const float s_x = finite ? amax * (1.0f / kXQMax) : 0.f;
+    long long sxf = 0;
+    int v0 = tid;
+    while (true) {
+#pragma unroll
+        for (int i = 0; i < B; ++i) {
+            const int v = v0 + i * kConsumerThreads;
+            if (v < nvec) {
+                float4 t = xv[i];
+                t.x = (t.x * inv_rms) * wv[i].x;   // reciprocal instead of the reference's division: ~1 ulp, see above
+                t.y = (t.y * inv_rms) * wv[i].y;
+                t.z = (t.z * inv_rms) * wv[i].z;
+                t.w = (t.w * inv_rms) * wv[i].w;
+                x_store_digits<BITS>(sm.xd, v, t, inv_s, sxf);
+            }
+        }
+        v0 += B * kConsumerThreads;
+        if (v0 >= nvec) break;
+        issue(v0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sxf += __shfl_xor_sync(0xffffffffu, sxf, o);
+    if (lane == 0) sm.sxf[tid >> 5] = sxf;
+    bar_sync(1, kConsumerThreads);
+    return s_x;
+}
+
+// consumers, main loop: one quad per warp per ring stage -- 4 k-items, each one LDS.128 of weights (the A fragments),
+// one LDS of digits (the B fragments) and 2 (INT4) / 1 (INT8) IMMA; when the warp's run over a group ends, the C
+// fragments are added to the column sums in shared memory (no cross-lane reduction needed).
 template <int BITS, int DBG = 0>
 __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, uint32_t& it, int warp, int lane,
                                              long long* dbg = nullptr) {
     const QLayout& L = a.L;
     const int S = a.stages;
     const int C = L.nchunks, nrounds = slab.rounds;
-    constexpr int kChunkBytes = BITS == 4 ? 768 : 384;
+    constexpr int kChunkBytes = BITS == 4 ? 768 : 384;   // digits of one chunk: 4 k-items x 3 planes x 4 t x 16 / 8 B
+    constexpr int kXItem = kChunkBytes / 4;
     const int my_nq = warp_quads(slab, warp);
     const int fq = warp_first_quad(slab, warp);
     int grp = fq / C;          // group / chunk of the warp's next quad
     int chunk = fq - grp * C;
-    const int c = lane & 3, s = lane >> 2;
-    const uint32_t xlane = smem_u32(sm.xd) + s * 16;
-    const uint32_t ring_lane = smem_u32(sm.ring) + lane * 16;
+    const int g = lane >> 2, t = lane & 3;
+    const uint32_t xlane = smem_u32(sm.xd) + ((g < 3 ? g : 0) * 4 + t) * (BITS == 4 ? 16 : 8);   // B column g = digit plane g
+    const uint32_t ring_base = smem_u32(sm.ring);
     // lane l < 16 stands for warp l when the stage offsets are summed with one REDUX per round
     const int l_nq = warp_quads(slab, lane & 15), l_fq = warp_first_quad(slab, lane & 15);
     const bool l_before = lane < warp;  // warp < 16
-    int acc[4][kAccPerUnit];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int i = 0; i < kAccPerUnit; ++i) acc[u][i] = 0;
+    QuadAcc<BITS> acc;
+    acc.clear();
     bool dirty = false;
     auto flush = [&]() {
-        const int live = grp == slab.ngroups - 1 ? slab.nlast : 4;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            int v0 = acc[u][0], v1 = acc[u][1], v2 = acc[u][2];
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-                v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-                v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-                v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        // C fragment: c0, c1 = (row g, B columns 2t, 2t+1), c2, c3 = (row g + 8, same columns); B column = digit plane
+        const int rows = grp == slab.ngroups - 1 ? 4 * slab.nlast : 16;
+        if (t < 2) {
+            int* dst = sm.acc + (grp * 16 + g) * 3 + 2 * t;
+            if (g < rows) {
+                atomicAdd(dst, acc.total(0));
+                if (t == 0) atomicAdd(dst + 1, acc.total(1));
             }
-            if (lane < 4 && u < live) {
-                int* dst = sm.acc + ((grp * 4 + u) * 4 + c) * 3;
-                atomicAdd(dst + 0, v0);
-                atomicAdd(dst + 1, v1);
-                atomicAdd(dst + 2, v2);
+            if (g + 8 < rows) {
+                atomicAdd(dst + 24, acc.total(2));
+                if (t == 0) atomicAdd(dst + 25, acc.total(3));
             }
-#pragma unroll
-            for (int i = 0; i < kAccPerUnit; ++i) acc[u][i] = 0;
         }
+        acc.clear();
         dirty = false;
     };
     uint32_t st = it % S, par = (it / S) & 1;
@@ -534,31 +570,40 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
     for (int r = 0; r < nrounds; ++r) {
         if (r > 0 && ++st == (uint32_t)S) { st = 0; par ^= 1; }
         const bool have = r < my_nq;
-        // items of the warps before this one in the stage
+        // 512-byte items of the warps before this one in the stage
         const int l_items = (l_before && r < l_nq) ? (l_fq + r >= slab.qfull ? slab.nlast : 4) : 0;
         const int woff = __reduce_add_sync(0xffffffffu, l_items);
-        XDigits<BITS> xd;
-        if (have) xd = load_xdigits<BITS>(xlane + chunk * kChunkBytes);  // does not depend on the stage: before the wait
+        uint4 xv[4];
+        if (have) {   // does not depend on the stage: before the wait
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[i] = load_xfrag<BITS>(xlane + chunk * kChunkBytes + i * kXItem);
+        }
         if (DBG != 2 && !ready) mbar_wait(&sm.full[st], par);
         if (dbg && r == 0) dbg[0] = clock64();
         ready = false;
         const uint32_t st_n = st + 1 == (uint32_t)S ? 0u : st + 1, par_n = st + 1 == (uint32_t)S ? par ^ 1u : par;
         if (have) {
-            const int live = grp == slab.ngroups - 1 ? slab.nlast : 4;
-            const uint32_t wbase = ring_lane + st * kStageBytes + woff * kItemBytes;
-            auto one = [&](const uint4& wv, int (&ac)[kAccPerUnit]) {
-                if (DBG != 1) item_dot<BITS>(wv, xd, ac);
-                else ac[0] += (int)(wv.x ^ wv.y ^ wv.z ^ wv.w);
+            const int nl = grp == slab.ngroups - 1 ? slab.nlast : 4;
+            const uint32_t qbase = ring_base + st * kStageBytes + woff * kItemBytes;
+            auto one = [&](int i, const uint4& wv) {
+                if (DBG != 1) kitem_mma<BITS>(acc, i & 1, wv, xv[i]);
+                else acc.lo[0][0] += (int)(wv.x ^ wv.y ^ wv.z ^ wv.w);
             };
-            if (live == 4) {  // the common case, straight-line: four loads in flight, 12 independent IDP4A chains
-                const uint4 w0 = lds128s(wbase), w1 = lds128s(wbase + kItemBytes), w2 = lds128s(wbase + 2 * kItemBytes),
-                            w3 = lds128s(wbase + 3 * kItemBytes);
+            if (nl == 4) {  // the common case, straight-line: four loads in flight
+                const uint32_t wbase = qbase + lane * 16;
+                const uint4 w0 = lds128s(wbase), w1 = lds128s(wbase + 512), w2 = lds128s(wbase + 1024), w3 = lds128s(wbase + 1536);
                 if (DBG != 2 && r + 1 < nrounds) ready = mbar_test_wait(&sm.full[st_n], par_n);
-                one(w0, acc[0]); one(w1, acc[1]); one(w2, acc[2]); one(w3, acc[3]);
-            } else {          // ragged last group of the slab: 1..3 items
-                { const uint4 w0 = lds128s(wbase); one(w0, acc[0]); }
-                if (live > 1) { const uint4 w1 = lds128s(wbase + kItemBytes); one(w1, acc[1]); }
-                if (live > 2) { const uint4 w2 = lds128s(wbase + 2 * kItemBytes); one(w2, acc[2]); }
+                one(0, w0); one(1, w1); one(2, w2); one(3, w3);
+            } else {        // ragged last group of the slab: rows 0..7 in part A, rows 8..11 (nl = 3) in part B
+                const bool in_a = nl > 1 || lane < 16, in_b = nl == 3 && lane < 16;
+                const uint32_t wbase = qbase + lane * 8;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint2 pa = make_uint2(0u, 0u), pb = make_uint2(0u, 0u);
+                    if (in_a) pa = lds64s(wbase + i * nl * 128);
+                    if (in_b) pb = lds64s(wbase + i * nl * 128 + 256);
+                    one(i, make_uint4(pa.x, pb.x, pa.y, pb.y));
+                }
             }
             dirty = true;
             if (++chunk == C) { flush(); chunk = 0; ++grp; }

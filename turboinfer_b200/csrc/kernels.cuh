@@ -127,92 +127,64 @@ __device__ __forceinline__ void pack_locate(const PackArgs& a, int n, int& si, i
     si = 0; sc = n;
     while (si < a.nsrc - 1 && sc >= a.src[si].n) { sc -= a.src[si].n; ++si; }
 }
-// grid = P slabs, block = 512 (16 warps mirror the 16 consumer warps); lane = (column c, k-slice s) like the GEMV
+// grid = P slabs, block = 512
 __global__ void pack_kernel(const PackArgs a) {
     const QLayout& L = a.L;
     const Slab slab = make_slab(L, blockIdx.x);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = lane & 3, s = lane >> 2;
-    const int nq = warp_quads(slab, warp), fq = warp_first_quad(slab, warp);
-    const int kl = L.kc / 8;  // k per lane per item
-    size_t stage_base = 0;    // byte offset of round r inside the slab
-    for (int r = 0; r < nq; ++r) {
-        const int q = fq + r;
-        const int grp = q / L.nchunks, chunk = q - grp * L.nchunks;
-        const int live = q >= slab.qfull ? slab.nlast : 4;
-        const size_t qoff = stage_base + (size_t)round_warp_offset(slab, r, warp) * kItemBytes;
-        stage_base += (size_t)round_total(slab, r) * kItemBytes;
-        for (int u = 0; u < live; ++u) {
-            const int n = slab.col0 + 4 * (4 * grp + u) + c;
-            int si = 0, sc = 0;
-            float scale = 1.f, zp = 0.f;
-            const bool col_live = n < L.N;
-            if (col_live) {
+    const int kik = kitem_k(L.bits), nel = L.bits == 4 ? 8 : 4;
+    for_each_quad_word(L, slab, warp, lane, [&](size_t off, int nl, int grp, int chunk, int ki, int widx) {
+        uint32_t word = 0;
+        for (int i = 0; i < nel; ++i) {
+            int row, kk;
+            kitem_word_elem(L.bits, nl, widx, i, row, kk);
+            const int n = slab.col0 + 16 * grp + row, k = chunk * L.kc + ki * kik + kk;
+            int qv = 0;
+            const bool live = n < L.N && k < L.K;
+            if (live) {
+                int si, sc;
                 pack_locate(a, n, si, sc);
-                scale = a.src[si].sz[0];
-                zp = a.src[si].sz[1];
+                qv = quantize_one(a.src[si].w[(size_t)k * a.src[si].ld + sc], a.qtype, a.src[si].sz[0], a.src[si].sz[1]);
             }
-            uint32_t words[4] = {0, 0, 0, 0};
-            for (int e = 0; e < kl; ++e) {
-                const int k = chunk * L.kc + s * kl + e;
-                int qv = 0;
-                const bool el_live = col_live && k < L.K;
-                if (el_live) qv = quantize_one(a.src[si].w[(size_t)k * a.src[si].ld + sc], a.qtype, scale, zp);
-                int word, shift;
-                lane_elem_pos(L.bits, e, word, shift);
-                if (L.bits == 4) {
-                    const int uval = el_live ? qv + a.off4 : a.off4;  // padding stores q = 0
-                    words[word] |= ((uint32_t)uval & 0xFu) << shift;
-                } else {
-                    words[word] |= ((uint32_t)qv & 0xFFu) << shift;
-                }
-            }
-            uint8_t* dst = a.out + slab.byte0 + qoff + (size_t)u * kItemBytes + lane * 16;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(words[0], words[1], words[2], words[3]);
-            if (chunk == 0 && s == 0) {
-                // y = scale * (sum x*(u - off) + zterm * sum x):
-                //   INT8 dequant = scale*(q - zp), stored q          -> zterm = -zp
-                //   INT4 dequant = scale*(q + zp), stored u = q + off -> zterm = +zp
-                a.colscale[n] = (col_live && !a.unit_scale) ? scale : (col_live ? 1.0f : 0.0f);
-                float zt = 0.f;
-                if (col_live && zp != 0.0f) zt = a.qtype == 0 ? -zp : zp;
-                if (a.colzterm) a.colzterm[n] = a.unit_scale ? 0.f : zt;
-            }
+            if (L.bits == 4) word |= ((uint32_t)(live ? qv + a.off4 : a.off4) & 0xFu) << (4 * i);   // padding stores q = 0
+            else word |= ((uint32_t)qv & 0xFFu) << (8 * i);
         }
+        *reinterpret_cast<uint32_t*>(a.out + off) = word;
+    });
+    // per-column scale and zero-point term:  y = scale * (sum x*(u - off) + zterm * sum x)
+    //   INT8 dequant = scale*(q - zp), stored q          -> zterm = -zp
+    //   INT4 dequant = scale*(q + zp), stored u = q + off -> zterm = +zp
+    for (int c = threadIdx.x; c < slab.ncols; c += blockDim.x) {
+        const int n = slab.col0 + c;
+        const bool col_live = n < L.N;
+        float scale = 1.f, zp = 0.f;
+        if (col_live) {
+            int si, sc;
+            pack_locate(a, n, si, sc);
+            scale = a.src[si].sz[0];
+            zp = a.src[si].sz[1];
+        }
+        a.colscale[n] = (col_live && !a.unit_scale) ? scale : (col_live ? 1.0f : 0.0f);
+        float zt = 0.f;
+        if (col_live && zp != 0.0f) zt = a.qtype == 0 ? -zp : zp;
+        if (a.colzterm) a.colzterm[n] = a.unit_scale ? 0.f : zt;
     }
 }
 // inverse of pack for a single-source matrix: q_out[k][n] in the reference's [K,N] int32 order
 __global__ void unpack_kernel(const uint8_t* packed, QLayout L, int off4, int32_t* q_out) {
     const Slab slab = make_slab(L, blockIdx.x);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int c = lane & 3, s = lane >> 2;
-    const int nq = warp_quads(slab, warp), fq = warp_first_quad(slab, warp);
-    const int kl = L.kc / 8;
-    size_t stage_base = 0;
-    for (int r = 0; r < nq; ++r) {
-        const int q = fq + r;
-        const int grp = q / L.nchunks, chunk = q - grp * L.nchunks;
-        const int live = q >= slab.qfull ? slab.nlast : 4;
-        const size_t qoff = stage_base + (size_t)round_warp_offset(slab, r, warp) * kItemBytes;
-        stage_base += (size_t)round_total(slab, r) * kItemBytes;
-        for (int u = 0; u < live; ++u) {
-            const int n = slab.col0 + 4 * (4 * grp + u) + c;
-            if (n >= L.N) continue;
-            const uint8_t* src = packed + slab.byte0 + qoff + (size_t)u * kItemBytes + lane * 16;
-            const uint4 wv = *reinterpret_cast<const uint4*>(src);
-            const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
-            for (int e = 0; e < kl; ++e) {
-                const int k = chunk * L.kc + s * kl + e;
-                if (k >= L.K) continue;
-                int word, shift;
-                lane_elem_pos(L.bits, e, word, shift);
-                int qv;
-                if (L.bits == 4) qv = (int)((words[word] >> shift) & 0xFu) - off4;
-                else qv = (int)(int8_t)((words[word] >> shift) & 0xFFu);
-                q_out[(size_t)k * L.N + n] = qv;
-            }
+    const int kik = kitem_k(L.bits), nel = L.bits == 4 ? 8 : 4;
+    for_each_quad_word(L, slab, warp, lane, [&](size_t off, int nl, int grp, int chunk, int ki, int widx) {
+        const uint32_t word = *reinterpret_cast<const uint32_t*>(packed + off);
+        for (int i = 0; i < nel; ++i) {
+            int row, kk;
+            kitem_word_elem(L.bits, nl, widx, i, row, kk);
+            const int n = slab.col0 + 16 * grp + row, k = chunk * L.kc + ki * kik + kk;
+            if (n >= L.N || k >= L.K) continue;
+            q_out[(size_t)k * L.N + n] = L.bits == 4 ? (int)((word >> (4 * i)) & 0xFu) - off4 : (int)(int8_t)((word >> (8 * i)) & 0xFFu);
         }
-    }
+    });
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -580,7 +580,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                     const GemvArgs& g = P.g;
                     if (stamp) ts[6] = clock64();
                     auto stats_fn = [&]() -> XStats { return from_emb ? m.emb_stats[token] : gather_stats(ph - 1); };
-                    const float s_x = gemv_stage_x_known<BITS>(g, x, sm, slab, !from_emb, stats_fn, tid, lane, stamp ? ts + 7 : nullptr, nullptr, 0u, &npre);
+                    const float s_x = gemv_stage_x_lean<BITS>(g, x, sm, slab, !from_emb, stats_fn, tid, lane);
                     if (stamp) {
                         ts[2] = clock64();
                         int ready = 0;  // stages of this phase already in shared memory when its main loop starts

@@ -141,6 +141,12 @@ __device__ __forceinline__ uint4 lds128s(uint32_t saddr) {
     return v;
 }
 
+__device__ __forceinline__ uint2 lds64s(uint32_t saddr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
+}
+
 // ---- "LL" words: a value and an epoch in ONE naturally aligned 64-bit word (single-copy atomic), so data can be handed
 // from one SM to others without a fence, a flag or a barrier: the consumer just re-reads until the epoch matches.
 typedef unsigned long long llword;

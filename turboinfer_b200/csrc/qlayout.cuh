@@ -6,19 +6,14 @@
 // Terms
 //   unit        4 consecutive output columns
 //   chunk       kc consecutive k: 256 (INT4) / 128 (INT8)
-//   item        one unit x one chunk = 32 lanes x 16 B = 512 B.  Lane l = (c = l & 3, s = l >> 2) holds, for column
-//               4*unit + c, the kc/8 values k = chunk*kc + s*(kc/8) + [0, kc/8):
-//               INT4: 32 nibbles u = q + off; word j (0..3), nibble 2i   -> k_local = 8j + i       (i < 4)
-//                                                        nibble 2i+1 -> k_local = 8j + 4 + i
-//                     so (w & 0x0F0F0F0F) and ((w >> 4) & 0x0F0F0F0F) are two dp4a operands of 4 consecutive k each
-//               INT8: 16 bytes q (two's complement); word j (0..3), byte i -> k_local = 4j + i
-//   group       4 consecutive units of a slab (16 columns); the last group of a slab may have 1..3 units
-//   quad        the <= 4 items of one group at one chunk: they share their activations, which a warp therefore loads
-//               from shared memory once per quad
+//   group       4 consecutive units of a slab (16 columns); the last group of a slab may have nl = 1..3 units
+//   quad        one group x one chunk: nl * 512 B, stored as 4 k-items in warp-MMA fragment order (see kitem_word_elem
+//               below): a k-item is the A operand of mma.sync.m16n8k32 (rows = the group's columns), INT4 two of them
+//               (low / high nibbles).  "item" below is the byte-accounting unit of 512 B: a quad counts nl items.
 //   CTA slab    the matrix is cut by columns into P slabs (whole units, P = #SMs when N allows); slab p is one
 //               contiguous byte range.  Inside it, quads are numbered group-major (q = group*nchunks + chunk), dealt
 //               to the 16 consumer warps as contiguous ranges, and laid out round by round:
-//               [round][warp][<= 4 items of the warp's quad][lane][16 B], a round being what the 16 warps consume
+//               [round][warp][the warp's quad: 4 k-items], a round being what the 16 warps consume
 //               from one pipeline stage (<= 32 KiB, one bulk async copy).  No padding items are stored.
 // K is padded to whole chunks with zeros (q = 0); every Llama-family K is a multiple of 256, so no padding bytes
 // are streamed for the benchmark shapes.
@@ -77,8 +72,9 @@ struct Slab {
 
 TIB_HD Slab make_slab(const QLayout& L, int p) {
     Slab s;
-    const int u0 = (int)((long long)p * L.U / L.P);
-    const int u1 = (int)((long long)(p + 1) * L.U / L.P);
+    // 32-bit arithmetic: p * U < 2^31 for every supported shape (U < 2^22 units, p < 512)
+    const int u0 = (int)((unsigned)p * (unsigned)L.U / (unsigned)L.P);
+    const int u1 = (int)((unsigned)(p + 1) * (unsigned)L.U / (unsigned)L.P);
     s.unit0 = u0;
     s.nunits = u1 - u0;
     s.col0 = 4 * u0;
@@ -111,30 +107,66 @@ TIB_HD int round_warp_offset(const Slab& s, int r, int w) {
 }
 TIB_HD int round_total(const Slab& s, int r) { return round_warp_offset(s, r, kConsumerWarps); }
 
-// position of element k_local (0 .. kc/8) of a lane inside its 16 bytes: word index and bit shift
-TIB_HD void lane_elem_pos(int bits, int k_local, int& word, int& shift) {
-    if (bits == 4) {
-        word = k_local >> 3;
-        const int r = k_local & 7;
-        shift = r < 4 ? 8 * r : 8 * (r - 4) + 4;
-    } else {
-        word = k_local >> 2;
-        shift = 8 * (k_local & 3);
+// ---- inside a quad: the warp-MMA fragment order ---------------------------------------------------------------
+// A quad (16 columns x one chunk; the slab's last group may have nl = 1..3 units = 4*nl columns) is stored as 4
+// consecutive k-items.  A k-item covers 64 k (INT4) / 32 k (INT8) of the group's columns and is exactly the A operand
+// of mma.sync.m16n8k32 (rows = the group's columns, 32 k per instruction; INT4: the low nibbles of a word are the
+// fragment of the first 32 k, the high nibbles that of the next 32 k):
+//   lane = (g = lane >> 2, t = lane & 3); fragment register j (0..3), byte b (0..3):
+//       row (column in the group) = g + 8 * (j & 1),   k in the 32-k block = 4*t + b + 16 * (j >> 1)
+//   full group (nl = 4):  512 B, lane l holds registers j = 0..3 at bytes [16 l, 16 l + 16)          (one LDS.128)
+//   ragged group:         rows 0..7 first ("part A": registers j = 0, 2 of lanes g < min(8, 4 nl), 8 B per lane), then
+//                         rows 8..11 for nl = 3 ("part B": registers j = 1, 3 of lanes g < 4) -- nl * 128 B, no padding
+// so a quad occupies nl * 512 B whatever nl is, as many bytes as its elements need.
+TIB_HD int kitem_bytes(int nl) { return nl * 128; }
+TIB_HD int kitem_k(int bits) { return bits == 4 ? 64 : 32; }
+
+// Inverse map used by the pack / unpack kernels: 32-bit word `widx` of a k-item of a group with nl units, element i of
+// the word (INT4: nibble i, bits [4i, 4i+4); INT8: byte i) -> row (column in the group) and k offset inside the k-item.
+TIB_HD void kitem_word_elem(int bits, int nl, int widx, int i, int& row, int& kk) {
+    int lane, j;
+    if (nl == 4) { lane = widx >> 2; j = widx & 3; }
+    else {
+        const int na = nl == 1 ? 32 : 64;           // words of part A
+        if (widx < na) { lane = widx >> 1; j = 2 * (widx & 1); }
+        else { lane = (widx - na) >> 1; j = 2 * ((widx - na) & 1) + 1; }
     }
+    const int g = lane >> 2, t = lane & 3;
+    row = g + 8 * (j & 1);
+    if (bits == 4) kk = 4 * t + (i >> 1) + 16 * (j >> 1) + 32 * (i & 1);
+    else kk = 4 * t + i + 16 * (j >> 1);
 }
 
-// The activation vector is staged in shared memory as three 8-bit digit planes of a 24-bit fixed-point value
-// (gemv.cuh).  Byte address of the 32-bit word holding digit d of the four values k .. k+3 (k % 4 == 0), laid out so
-// that the 8 k-slices of a chunk are contiguous 16-byte vectors (conflict-free LDS.128 from lanes (c, s)):
-//   INT4: [chunk][digit][half h][slice s][word j]   k = chunk*256 + s*32 + j*8 + h*4
-//   INT8: [chunk][digit][slice s][word j]           k = chunk*128 + s*16 + j*4
-TIB_HD int xdigit_word_offset(int bits, int k, int d) {
-    if (bits == 4) {
-        const int chunk = k >> 8, s = (k >> 5) & 7, j = (k >> 3) & 3, h = (k >> 2) & 1;
-        return ((((chunk * 3 + d) * 2 + h) * 8 + s) * 4 + j) * 4;
+#ifdef __CUDACC__
+// Walks the 32-bit words of the quads that consumer warp `warp` of slab `slab` owns (the pack / unpack kernels mirror
+// the GEMV's 16 consumer warps): f(byte offset of the word in the packed buffer, nl, group, chunk, k-item, word in k-item)
+template <typename F>
+__device__ __forceinline__ void for_each_quad_word(const QLayout& L, const Slab& slab, int warp, int lane, F&& f) {
+    const int nq = warp_quads(slab, warp), fq = warp_first_quad(slab, warp);
+    size_t stage_base = 0;    // byte offset of round r inside the slab
+    for (int r = 0; r < nq; ++r) {
+        const int q = fq + r;
+        const int grp = q / L.nchunks, chunk = q - grp * L.nchunks;
+        const int nl = q >= slab.qfull ? slab.nlast : 4;
+        const size_t qoff = slab.byte0 + stage_base + (size_t)round_warp_offset(slab, r, warp) * kItemBytes;
+        stage_base += (size_t)round_total(slab, r) * kItemBytes;
+        const int wpk = nl * 32;   // words per k-item
+        for (int wq = lane; wq < 4 * wpk; wq += 32) f(qoff + (size_t)wq * 4, nl, grp, chunk, wq / wpk, wq % wpk);
     }
-    const int chunk = k >> 7, s = (k >> 4) & 7, j = (k >> 2) & 3;
-    return (((chunk * 3 + d) * 8 + s) * 4 + j) * 4;
+}
+#endif
+
+// The activation vector is staged in shared memory as three SIGNED 8-bit digit planes of a 24-bit fixed-point value,
+// xf = d2*65536 + d1*256 + d0 with every digit in [-128, 127] (gemv.cuh), in the order the B fragments of the MMAs want:
+// lane (g, t) multiplies digit plane g (columns g >= 3 of the product are unused) and needs, per 32-k block, the words
+// k = 4t .. 4t+3 and k = 16+4t .. 16+4t+3.
+//   INT4: [k / 64][digit][t][4 words: k%64 = 4t, 16+4t, 32+4t, 48+4t]     one LDS.128 per k-item (two MMAs)
+//   INT8: [k / 32][digit][t][2 words: k%32 = 4t, 16+4t]                   one LDS.64 per k-item (one MMA)
+// Byte address of the word holding digit d of the four values k .. k+3 (k % 4 == 0):
+TIB_HD int xdigit_word_offset(int bits, int k, int d) {
+    const int t = (k >> 2) & 3, q = k >> 4;
+    if (bits == 4) return (((q >> 2) * 3 + d) * 4 + t) * 16 + (q & 3) * 4;
+    return (((q >> 1) * 3 + d) * 4 + t) * 8 + (q & 1) * 4;
 }
 TIB_HD size_t xdigit_bytes(const QLayout& L) { return (size_t)3 * layout_kpad(L); }
 
