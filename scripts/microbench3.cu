@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) k_consume_only(const __grid_c
     for (int i = tid; i < a.stages * kStageBytes / 4; i += kConsumerThreads) reinterpret_cast<uint32_t*>(sm.ring)[i] = i * 2654435761u;
     const float s_x = gemv_stage_x<BITS>(a, a.x, sm, slab, false, tid, warp, lane);
     const long long t0 = clock64();
-    uint32_t it = 0;
+    RingPos it;
     gemv_consume<BITS, 2>(a, slab, sm, it, warp, lane);   // DBG 2: no mbarrier traffic, ring pre-filled
     const long long t1 = clock64();
     if (lane == 0) atomicMax((unsigned long long*)cycles, (unsigned long long)(t1 - t0));
@@ -27,13 +27,13 @@ __global__ void __launch_bounds__(kGemvThreads, 1) k_consume_only(const __grid_c
 }
 
 template <int BITS, int DBG>
-static int run_real(const char* label, int K, int N, int sms, int reps, int force_stages = 0) {
+static int run_real(const char* label, int K, int N, int sms, int reps, int force_stages = 0, int force_copies = 0) {
     QLayout L = make_layout(K, N, BITS, sms);
     int stages = 0; size_t smem = 0;
     for (int s = kMaxStages; s >= 2; --s) if (gemv_smem_bytes(L, s) <= 227 * 1024) { stages = s; smem = gemv_smem_bytes(L, s); break; }
     if (force_stages) { stages = force_stages; smem = gemv_smem_bytes(L, stages); }
     const size_t bytes = layout_bytes(L);
-    const int copies = bytes > (300u << 20) ? 2 : 4;   // cycle through several matrices so the working set exceeds L2
+    const int copies = force_copies ? force_copies : (bytes > (300u << 20) ? 2 : 4);   // cycle through several matrices so the working set exceeds L2
     uint8_t* w; float *cs, *x, *y;
     CK(cudaMalloc(&w, bytes * copies)); CK(cudaMemset(w, 0x5A, bytes * copies));
     CK(cudaMalloc(&cs, 4 * (size_t)4 * L.U)); CK(cudaMalloc(&x, 4 * (size_t)K)); CK(cudaMalloc(&y, 4 * (size_t)4 * L.U));
@@ -97,6 +97,11 @@ int main() {
     run_real<4, 0>("full", 8192, 65536, sms, 20);
     run_real<8, 1>("stream only", 8192, 32768, sms, 20);
     run_real<8, 0>("full", 8192, 32768, sms, 20);
+    // one L2-resident matrix, streamed again and again: what the ring delivers when HBM is out of the picture
+    run_real<4, 1>("stream only, L2", 8192, 16384, sms, 50, 0, 1);
+    run_real<4, 0>("full, L2", 8192, 16384, sms, 50, 0, 1);
+    run_real<4, 1>("stream only, HBM", 8192, 16384, sms, 50, 0, 4);
+    run_real<4, 0>("full, HBM", 8192, 16384, sms, 50, 0, 4);
     run_real<4, 0>("full", 4096, 22016, sms, 50);
     run_real<4, 1>("stream only", 4096, 22016, sms, 50);
     return 0;

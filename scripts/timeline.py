@@ -18,18 +18,17 @@ for t in range(ctx):
 for rep in range(2):
     ts = m.debug_timeline(5)
 names = ["qkv", "attn", "o", "gateup", "down"]
-print(f"{shape} L={layers} t={ctx}: phase  wait  stage_x  consume  epilogue  arrive  total (us @1.965GHz)")
+print(f"{shape} L={layers} t={ctx}: us @1.965GHz, CTA 0 thread 0")
+print("phase        | hdr   wait | issue stats conv  bar  =stage | 1stw  loop flush  bar =consume | epi  | bar  slot  red =arrive | total  ready")
 f = 1 / 1965.0
+tot = {}
 for i, r in enumerate(ts):
     nm = names[i % 5] if i < len(ts) - 1 else "lm_head"
-    d = np.diff(r[:6]) * f
-    sub = ""
-    if r[6] > 0:
-        pts = [r[1], r[6], r[7], r[8], r[9], r[10]]
-        cons = os.environ.get("TURBOINFER_B200_DBG_NOMATH") == "3"
-        if cons:
-            pts = [r[2], r[8], r[9], r[10], r[3]]
-        sub = "   | prologue: " + " ".join(f"{(b - a) * f:5.2f}" for a, b in zip(pts[:-1], pts[1:])) + ("" if cons else f" | ready stages {r[11]}")
-    print(f"{i:3d} {nm:7s} " + " ".join(f"{x:8.2f}" for x in d) + f"  {(r[5]-r[0])*f:8.2f}" + sub)
-print("prologue columns: stats gathered | rms+scale | x,w loads issued..arrived | (gap) | digits stored | final barrier")
+    u = lambda a, b: (r[b] - r[a]) * f if r[a] > 0 and r[b] > 0 else 0.0
+    if nm == "attn":
+        line = f"{i:3d} {nm:7s} | {u(0,12):5.2f} {u(12,1):5.2f} | {'':29s} | {'':29s} | {u(1,4):4.2f} | {u(4,21):4.2f} {u(21,22):5.2f} {u(22,5):4.2f} ={u(4,5):5.2f} | {u(0,5):6.2f}"
+    else:
+        line = (f"{i:3d} {nm:7s} | {u(0,12):5.2f} {u(12,1):5.2f} | {u(6,13):5.2f} {u(13,14):5.2f} {u(14,15):4.2f} {u(15,2):4.2f} ={u(1,2):5.2f} | "
+                f"{u(2,17):4.2f} {u(17,18):5.2f} {u(18,19):5.2f} {u(19,3):4.2f} ={u(2,3):6.2f} | {u(3,4):4.2f} | {u(4,21):4.2f} {u(21,22):5.2f} {u(22,5):4.2f} ={u(4,5):5.2f} | {u(0,5):6.2f}  {r[11]}")
+    print(line)
 print("step total us:", (ts[-1, 5] - ts[0, 0]) * f)

@@ -363,12 +363,12 @@ class Model:
         return self
 
     def debug_timeline(self, token: int = 1) -> np.ndarray:
-        """[phases, 12] SM-clock stamps of CTA 0 for one decode step on the persistent-kernel engine: 6 phase-level
+        """[phases, 32] SM-clock stamps of CTA 0 for one decode step on the persistent-kernel engine: 6 phase-level
         stamps (start, barrier passed, x staged, weights consumed, epilogue done, arrived) + 6 inside the prologue."""
-        buf = np.zeros(12 * 4096, dtype=np.int64)
+        buf = np.zeros(32 * 4096, dtype=np.int64)
         n = C.c_size_t()
         _ck(lib().ti_b200_debug_timeline(self.handle, token, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size, C.byref(n)))
-        return buf[: 12 * n.value].reshape(n.value, 12).copy()
+        return buf[: 32 * n.value].reshape(n.value, 32).copy()
 
     def last_prefill_ms(self) -> float:
         ms = C.c_float()

@@ -17,7 +17,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
-#include "mega_ll.cuh"
+#include "mega.cuh"
 #include "gemm_tc.cuh"
 #include "prefill.cuh"
 
@@ -141,8 +141,6 @@ int set_kernel_attrs() {
     CK(cudaFuncSetAttribute(attn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CK(cudaFuncSetAttribute(mega_decode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(mega_decode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(mega_ll_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CK(cudaFuncSetAttribute(mega_ll_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_attr_done = true;
     return 0;
 }
@@ -300,22 +298,14 @@ struct Model {
     DevBuf<int> pf_tokens;
     int tp = 1, tp_rank = 0;   // tensor-parallel degree / rank of this model
     DevBuf<float> ar_tmp;      // [H] partial output of a row-parallel GEMV, all-reduced in place
-    bool use_ll = false;   // dataflow (LL) variant of the persistent kernel
-    DevBuf<MegaLLPhase> ll_phases;
-    DevBuf<llword> ll_xres, ll_act, ll_attn, ll_q, ll_knew, ll_vnew, ll_part, ll_keys, ll_stats;
-    uint32_t host_epoch = 0;
-    DevBuf<unsigned int> ll_cnt;
-    int ll_attn_floats = 0, ll_stages = 0;
-    size_t ll_smem = 0;
     DevBuf<MegaPhase> phases;
     DevBuf<ProdRec> prod;
     int nphases = 0;
-    DevBuf<unsigned int> sync_buf;   // [0] grid barrier counter, [2..5] two 64-bit argmax keys
+    DevBuf<unsigned int> sync_buf;   // kBarWords barrier words (128 B apart), then two 64-bit argmax keys
     DevBuf<unsigned int> head_cnt;
     int mega_stages = 0, mega_max_kpad = 0, mega_max_units = 0, mega_attn_floats = 0;
     DevBuf<long long> dbg;
     bool dbg_on = false;
-    DevBuf<float4> stats;
     DevBuf<XStats> emb_stats;
     size_t mega_smem = 0;
     int host_pos = 0;  // mirror of state.pos
@@ -731,16 +721,14 @@ int build_mega(Model& m) {
     TRY(m.prod.alloc(prod.size()));
     CK(cudaMemcpyAsync(m.prod.p, prod.data(), prod.size() * sizeof(ProdRec), cudaMemcpyHostToDevice, g_stream));
     CK(cudaStreamSynchronize(g_stream));
-    TRY(m.stats.alloc((size_t)2 * g_num_sms * 2));
-    CK(cudaMemsetAsync(m.stats.p, 0, (size_t)2 * g_num_sms * 2 * sizeof(float4), g_stream));
     TRY(m.emb_stats.alloc(m.cfg.vocab));
     emb_stats_kernel<<<m.cfg.vocab, 256, 0, g_stream>>>(m.tok_emb.p, m.layers.empty() ? m.out_norm.p : m.layers[0].attn_norm.p,
                                                         m.emb_stats.p, H);
     ++g_launches;
     CK(cudaGetLastError());
-    TRY(m.sync_buf.alloc(8));
+    TRY(m.sync_buf.alloc(kBarWords * kBarStride + 8));
     TRY(m.head_cnt.alloc(std::max(1, m.attn_heads)));
-    CK(cudaMemsetAsync(m.sync_buf.p, 0, 8 * sizeof(unsigned int), g_stream));
+    CK(cudaMemsetAsync(m.sync_buf.p, 0, (kBarWords * kBarStride + 8) * sizeof(unsigned int), g_stream));
     CK(cudaMemsetAsync(m.head_cnt.p, 0, std::max(1, m.attn_heads) * sizeof(unsigned int), g_stream));
     CK(cudaStreamSynchronize(g_stream));
     int bits = m.cfg.qtype == TI_Q_INT4 ? 4 : 8;
@@ -753,11 +741,9 @@ int build_mega(Model& m) {
 
 // n_steps forward passes in one cooperative launch; steps < n_prompt take their token from m.prompt, later ones from
 // the previous step's argmax; steps >= first_sample run the lm_head and publish a token
-int run_mega_ll(Model& m, int n_prompt, int n_steps, int first_sample);
 int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
     if (n_steps <= 0) return 0;
-    if (m.use_ll) return run_mega_ll(m, n_prompt, n_steps, first_sample);
-    CK(cudaMemsetAsync(m.sync_buf.p, 0, 8 * sizeof(unsigned int), g_stream));
+    CK(cudaMemsetAsync(m.sync_buf.p, 0, (kBarWords * kBarStride + 8) * sizeof(unsigned int), g_stream));
     MegaArgs a{};
     a.phases = m.phases.p;
     a.prod = m.prod.p;
@@ -773,7 +759,7 @@ int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
     a.first_sample = first_sample;
     a.grid_bar = m.sync_buf.p;
     a.head_cnt = m.head_cnt.p;
-    a.keys = reinterpret_cast<unsigned long long*>(m.sync_buf.p + 2);
+    a.keys = reinterpret_cast<unsigned long long*>(m.sync_buf.p + kBarWords * kBarStride);
     a.logits = m.logits.p;
     a.stages = m.mega_stages;
     a.max_kpad = m.mega_max_kpad;
@@ -781,182 +767,11 @@ int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
     a.attn_floats = m.mega_attn_floats;
     a.dbg = m.dbg_on ? m.dbg.p : nullptr;
     a.dbg_nomath = (m.dbg_on && getenv("TURBOINFER_B200_DBG_NOMATH")) ? atoi(getenv("TURBOINFER_B200_DBG_NOMATH")) : 0;
-    a.stats = m.stats.p;
     a.emb_stats = m.emb_stats.p;
+    a.dbg_flags = getenv("TURBOINFER_B200_DBG_FLAGS") ? atoi(getenv("TURBOINFER_B200_DBG_FLAGS")) : 0;
     void* args[] = {&a};
     const void* fn = m.cfg.qtype == TI_Q_INT4 ? (const void*)mega_decode_kernel<4> : (const void*)mega_decode_kernel<8>;
     CK(cudaLaunchCooperativeKernel(fn, dim3(g_num_sms), dim3(kMegaThreads), args, m.mega_smem, g_stream));
-    ++g_launches;
-    return 0;
-}
-
-// ---- dataflow (LL) engine: same phases as build_mega, activations exchanged as LL words -----------------------
-int build_mega_ll(Model& m) {
-    const int H = m.cfg.hidden, I = std::max(m.cfg.inter, 1);
-    for (auto& ly : m.layers)
-        for (QWeight* w : {ly.qkv.get(), ly.o.get(), ly.gateup.get(), ly.down.get()})
-            if (w->L.K % 4 != 0) return fail("the dataflow engine needs K %% 4 == 0 (K = %d)", w->L.K);
-    if (H % 4 != 0) return fail("the dataflow engine needs hidden %% 4 == 0");
-    const int splits = std::max(1, std::min(g_num_sms / m.attn_heads, m.max_splits));
-    auto alloc0 = [&](DevBuf<llword>& b, size_t n) -> int {
-        TRY(b.alloc(n));
-        CK(cudaMemsetAsync(b.p, 0, n * sizeof(llword), g_stream));
-        return 0;
-    };
-    TRY(alloc0(m.ll_xres, H));
-    TRY(alloc0(m.ll_act, I));
-    TRY(alloc0(m.ll_attn, H));
-    TRY(alloc0(m.ll_q, H));
-    TRY(alloc0(m.ll_knew, H));
-    TRY(alloc0(m.ll_vnew, H));
-    TRY(alloc0(m.ll_part, (size_t)m.attn_heads * splits * (m.attn_dim + 2)));
-    TRY(alloc0(m.ll_keys, (size_t)2 * g_num_sms));
-    TRY(alloc0(m.ll_stats, (size_t)2 * g_num_sms * 2));
-    TRY(m.ll_cnt.alloc(96));
-    m.host_epoch = 0;
-    std::vector<MegaLLPhase> ph;
-    auto as_f = [](llword* p) { return reinterpret_cast<float*>(p); };
-    auto gemv_phase = [&](const QWeight& w, GemvArgs g, const llword* x_ll, int x_src, int resid_src, int is_head) {
-        MegaLLPhase p{};
-        p.type = PH_GEMV;
-        p.x_src = x_src;
-        p.resid_src = resid_src;
-        p.is_head = is_head;
-        fill_weight(w, g);
-        g.stages = m.mega_stages;
-        p.g = g;
-        p.x_ll = x_ll;
-        p.knew_ll = m.ll_knew.p;
-        p.vnew_ll = m.ll_vnew.p;
-        ph.push_back(p);
-    };
-    for (size_t l = 0; l < m.layers.size(); ++l) {
-        Layer& ly = m.layers[l];
-        const int src0 = l == 0 ? SRC_EMB : SRC_PTR;
-        GemvArgs a{};
-        a.norm_w = ly.attn_norm.p;
-        a.rms_eps = m.cfg.rms_eps;
-        a.epi = EPI_QKV;
-        a.out = as_f(m.ll_q.p);
-        a.hidden = H;
-        a.rope_dim = m.cfg.rope_mode == 1 ? H / m.cfg.heads : (m.cfg.rope_mode == 2 ? H : 0);
-        a.inv_freq = m.inv_freq.p;
-        a.pos_ptr = &m.state.p->pos;
-        a.k_pool = ly.k_pool.p;
-        a.v_pool = ly.v_pool.p;
-        a.page_table = m.page_table.p;
-        a.page_tokens = m.page_tokens;
-        gemv_phase(*ly.qkv, a, m.ll_xres.p, src0, SRC_PTR, 0);
-        MegaLLPhase at{};
-        at.type = PH_ATTN;
-        at.at.k_pool = ly.k_pool.p;
-        at.at.v_pool = ly.v_pool.p;
-        at.at.page_table = m.page_table.p;
-        at.at.page_tokens = m.page_tokens;
-        at.at.pos_ptr = &m.state.p->pos;
-        at.at.t_bias = 1;
-        at.at.H = H;
-        at.at.D = m.attn_dim;
-        at.at.heads = m.attn_heads;
-        at.at.max_splits = splits;
-        at.at.min_chunk = 64;
-        at.at.scale = 1.0f / sqrtf((float)m.attn_dim);
-        at.at.q_ll = m.ll_q.p;
-        at.at.knew_ll = m.ll_knew.p;
-        at.at.vnew_ll = m.ll_vnew.p;
-        at.at.out_ll = m.ll_attn.p;
-        at.at.part_ll = m.ll_part.p;
-        ph.push_back(at);
-        GemvArgs o{};
-        o.epi = EPI_RESIDUAL;
-        o.resid = as_f(m.ll_xres.p);
-        o.out = as_f(m.ll_xres.p);
-        gemv_phase(*ly.o, o, m.ll_attn.p, SRC_PTR, src0, 0);
-        GemvArgs g{};
-        g.norm_w = ly.ffn_norm.p;
-        g.rms_eps = m.cfg.rms_eps;
-        g.epi = ly.has_gate ? EPI_SWIGLU : EPI_RELU;
-        g.out = as_f(m.ll_act.p);
-        gemv_phase(*ly.gateup, g, m.ll_xres.p, SRC_PTR, SRC_PTR, 0);
-        GemvArgs d{};
-        d.epi = EPI_RESIDUAL;
-        d.resid = as_f(m.ll_xres.p);
-        d.out = as_f(m.ll_xres.p);
-        gemv_phase(*ly.down, d, m.ll_act.p, SRC_PTR, SRC_PTR, 0);
-    }
-    GemvArgs lm{};
-    lm.norm_w = m.out_norm.p;
-    lm.rms_eps = m.cfg.rms_eps;
-    lm.epi = EPI_LOGITS;
-    lm.out = m.logits.p;
-    gemv_phase(*m.lm_head, lm, m.ll_xres.p, m.layers.empty() ? SRC_EMB : SRC_PTR, SRC_PTR, 1);
-    if ((int)ph.size() != m.nphases) return fail("internal: phase lists differ");
-    for (size_t i = 1; i < ph.size(); ++i) {
-        if (ph[i - 1].type == PH_GEMV) {
-            ph[i].prod_kind = 0;
-            ph[i].prod_P = ph[i - 1].g.L.P;
-        } else {
-            ph[i].prod_kind = 1;
-            ph[i].prod_heads = ph[i - 1].at.heads;
-            ph[i].prod_splits = ph[i - 1].at.max_splits;
-            ph[i].prod_minchunk = ph[i - 1].at.min_chunk;
-        }
-    }
-    m.ll_attn_floats = attn_ll_scratch_floats(m.attn_dim, kConsumerThreads);
-    m.ll_stages = 0;
-    for (int s = kMaxStages; s >= 2; --s)
-        if (mega_ll_smem_bytes(s, m.mega_max_kpad, m.mega_max_units, m.ll_attn_floats) <= 227 * 1024) { m.ll_stages = s; break; }
-    if (m.ll_stages == 0) return fail("dataflow kernel does not fit shared memory");
-    m.ll_smem = mega_ll_smem_bytes(m.ll_stages, m.mega_max_kpad, m.mega_max_units, m.ll_attn_floats);
-    for (auto& p : ph) p.g.stages = m.ll_stages;
-    TRY(m.ll_phases.alloc(ph.size()));
-    CK(cudaMemcpyAsync(m.ll_phases.p, ph.data(), ph.size() * sizeof(MegaLLPhase), cudaMemcpyHostToDevice, g_stream));
-    CK(cudaStreamSynchronize(g_stream));
-    int per_sm = 0;
-    if (m.cfg.qtype == TI_Q_INT4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_ll_kernel<4>, kMegaThreads, m.ll_smem));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_ll_kernel<8>, kMegaThreads, m.ll_smem));
-    if (per_sm < 1) return fail("dataflow kernel cannot be resident (occupancy 0)");
-    return 0;
-}
-
-int run_mega_ll(Model& m, int n_prompt, int n_steps, int first_sample) {
-    if (n_steps <= 0) return 0;
-    const uint64_t need = (uint64_t)n_steps * (uint64_t)(m.nphases + 1);
-    if ((uint64_t)m.host_epoch + need >= 0xFFFFFFF0ull) {
-        // epochs would wrap: clear every LL buffer and start over (once per ~26 million tokens)
-        for (DevBuf<llword>* b : {&m.ll_xres, &m.ll_act, &m.ll_attn, &m.ll_q, &m.ll_knew, &m.ll_vnew, &m.ll_part, &m.ll_keys, &m.ll_stats})
-            CK(cudaMemsetAsync(b->p, 0, b->n * sizeof(llword), g_stream));
-        m.host_epoch = 0;
-    }
-    CK(cudaMemsetAsync(m.ll_cnt.p, 0, 96 * sizeof(unsigned int), g_stream));
-    MegaLLArgs a{};
-    a.phases = m.ll_phases.p;
-    a.cnt = m.ll_cnt.p;
-    a.prod = m.prod.p;
-    a.nphases = m.nphases;
-    a.emb = m.tok_emb.p;
-    a.H = m.cfg.hidden;
-    a.V = m.cfg.vocab;
-    a.st = m.state.p;
-    a.io = m.io.p;
-    a.prompt = m.prompt.p;
-    a.n_prompt = n_prompt;
-    a.n_steps = n_steps;
-    a.first_sample = first_sample;
-    a.keys_ll = m.ll_keys.p;
-    a.stats_ll = m.ll_stats.p;
-    a.emb_stats = m.emb_stats.p;
-    a.logits = m.logits.p;
-    a.stages = m.ll_stages;
-    a.max_kpad = m.mega_max_kpad;
-    a.max_units = m.mega_max_units;
-    a.attn_floats = m.ll_attn_floats;
-    a.dbg = m.dbg_on ? m.dbg.p : nullptr;
-    a.ep0 = m.host_epoch;
-    m.host_epoch += (uint32_t)need;
-    void* args[] = {&a};
-    const void* fn = m.cfg.qtype == TI_Q_INT4 ? (const void*)mega_ll_kernel<4> : (const void*)mega_ll_kernel<8>;
-    CK(cudaLaunchCooperativeKernel(fn, dim3(g_num_sms), dim3(kMegaThreads), args, m.ll_smem, g_stream));
     ++g_launches;
     return 0;
 }
@@ -1708,8 +1523,6 @@ int ti_b200_model_finalize(ti_model_t h) {
     if (m.tp > 1) TRY(m.ar_tmp.alloc(H));
     TRY(m.prompt.alloc(16));
     if (m.use_mega) TRY(build_mega(m));
-    m.use_ll = m.use_mega && eng && std::string(eng) == "ll";   // experimental dataflow variant, off by default
-    if (m.use_ll) TRY(build_mega_ll(m));
     // tensor-parallel steps hold NCCL all-reduces: NCCL supports stream capture, so they are replayed from a graph as
     // well (TURBOINFER_B200_TP_GRAPH=0 enqueues them directly instead)
     const char* tpg = getenv("TURBOINFER_B200_TP_GRAPH");

@@ -167,7 +167,7 @@ struct GemvSmem {
     int* acc;           // [ncols][3] integer column sums
     float* red;         // 128 floats of reduction scratch
     long long* sxf;     // [16] per-warp partial sums of xf over k
-    unsigned long long* keyred;  // [16] per-warp argmax keys (dataflow engine)
+    unsigned int* spare;         // 128 spare bytes
     uint64_t* full;     // [stages]
     uint64_t* empty;    // [stages]
 };
@@ -195,7 +195,7 @@ __device__ __forceinline__ GemvSmem gemv_carve_for(uint8_t* base, int stages, in
     p += 128 * 4;
     s.sxf = reinterpret_cast<long long*>(p);
     p += 16 * 8;
-    s.keyred = reinterpret_cast<unsigned long long*>(p);
+    s.spare = reinterpret_cast<unsigned int*>(p);
     p += 16 * 8;
     s.full = reinterpret_cast<uint64_t*>(p);
     s.empty = s.full + kMaxStages;
@@ -216,27 +216,27 @@ struct PhaseCtx {
     bool coherent;   // activations were produced by other CTAs of the same launch: read them through L2
     int pos;         // cache position of the current token (EPI_QKV); < 0: read *pos_ptr
     unsigned long long* key;  // EPI_LOGITS: argmax key to use instead of GemvArgs::argmax_key (nullptr: keep)
-    // dataflow engine (mega_ll.cuh): activations travel as LL words (ptx.cuh); 0 = plain floats
-    uint32_t ll_epoch;        // epoch to stamp on this phase's outputs; `out` / `resid` then point at llword arrays
-    llword* knew_ll;          // EPI_QKV: the current token's K and V rows, for the attention phase that follows
-    llword* vnew_ll;
-    unsigned long long* keyred;  // EPI_LOGITS: per-warp best keys go to this shared-memory array instead of an atomic
-    bool resid_plain;         // the residual input is plain floats (embedding row) even though the output is LL
+};
+
+// Position in the ring, carried across the GEMVs of a launch (no divisions per phase): stage and the parity of its use.
+struct RingPos {
+    uint32_t st = 0, par = 0;
+    __device__ __forceinline__ void advance(uint32_t S) { if (++st == S) { st = 0; par ^= 1u; } }
 };
 
 // producer (the whole warp): stream this CTA's slab through the ring.  `it` counts stages over the whole launch.
 // Lane w < 16 computes how many items consumer warp w takes from the stage, one REDUX sums them, lane 0 drives the
 // mbarriers and the bulk copy -- the per-stage bookkeeping must stay far below the ~0.7 us a stage lasts at HBM rate.
-__device__ __forceinline__ void gemv_produce(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, uint32_t& it, int lane) {
+__device__ __forceinline__ void gemv_produce(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, RingPos& it, int lane) {
     const int S = a.stages;
     const uint8_t* src = a.wq + slab.byte0;
     const int l_nq = warp_quads(slab, lane & 15), l_fq = warp_first_quad(slab, lane & 15);
-    for (int r = 0; r < slab.rounds; ++r, ++it) {
+    for (int r = 0; r < slab.rounds; ++r, it.advance(S)) {
         const int l_items = (lane < kConsumerWarps && r < l_nq) ? (l_fq + r >= slab.qfull ? slab.nlast : 4) : 0;
         const uint32_t bytes = (uint32_t)__reduce_add_sync(0xffffffffu, l_items) * kItemBytes;
         if (lane == 0) {
-            const uint32_t st = it % S, use = it / S;
-            if (use > 0) mbar_wait(&sm.empty[st], (use - 1) & 1);
+            const uint32_t st = it.st;
+            mbar_wait(&sm.empty[st], it.par ^ 1u);   // a fresh mbarrier counts its "previous" phase as complete
             mbar_arrive_expect_tx(&sm.full[st], bytes);
             bulk_g2s_evict_first(sm.ring + (size_t)st * kStageBytes, src, bytes, &sm.full[st]);
         }
@@ -370,133 +370,53 @@ __device__ __forceinline__ float gemv_stage_x(const GemvArgs& a, const float* x,
     return s_x;
 }
 
-// Single-pass prologue for callers that can obtain sum(x^2) and the bound of max|x*w| without reading x (persistent
-// kernel: the phase that produced x left per-CTA partials).  The first batch of x / norm-weight loads is issued BEFORE
-// get_stats() is called, so the statistics' round trip to L2 overlaps the data's.
-// x_ll != nullptr (dataflow engine): x arrives as LL words stamped `ep`; each load is verified and re-tried.
-// The RMSNorm weights of a phase are static: the persistent kernel fetches the thread's first batch BEFORE the grid
-// barrier (they usually come from HBM, not L2) and hands them in.
-struct NormPre {
-    float4 w[4];
-    bool valid;
+// Single-pass prologue of the persistent kernel: sum(x^2) and the bound of max|x*w| arrive with the grid barrier (the
+// phase that produced x reduced them into the barrier word), so x is read once.  Written for the persistent kernel's
+// latency: 128-bit loads only (the host checks K % 4 == 0 and the alignment once); the RMSNorm weights of a phase are
+// static and usually come from HBM, not L2, so the thread's share is fetched BEFORE the grid barrier (XPre) and the x
+// loads are issued the moment the barrier opens.
+constexpr int kXBatch = 6;   // float4 vectors per thread per batch: K <= 12288 converts in one batch
+struct XPre {
+    float4 w[kXBatch];
 };
-__device__ __forceinline__ NormPre gemv_norm_prefetch(const GemvArgs& a, int tid) {
-    NormPre p;
-    p.valid = false;
-    const float* nw = a.norm_w;
-    if (nw == nullptr || (a.L.K & 3) != 0 || (reinterpret_cast<uintptr_t>(nw) & 15) != 0) return p;
+__device__ __forceinline__ void gemv_x_prefetch(const GemvArgs& a, int tid, XPre& p) {
+    const float4* nw4 = reinterpret_cast<const float4*>(a.norm_w);
     const int kvec = a.L.K >> 2;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < kXBatch; ++i) {
         const int v = tid + i * kConsumerThreads;
-        p.w[i] = v < kvec ? __ldg(reinterpret_cast<const float4*>(nw) + v) : make_float4(1.f, 1.f, 1.f, 1.f);
+        p.w[i] = (nw4 != nullptr && v < kvec) ? ldg_stream4(nw4 + v) : make_float4(1.f, 1.f, 1.f, 1.f);
     }
-    p.valid = true;
-    return p;
 }
-
-template <int BITS, typename StatsFn>
-__device__ __forceinline__ float gemv_stage_x_known(const GemvArgs& a, const float* x, const GemvSmem& sm, const Slab& slab, bool coherent,
-                                                    StatsFn&& get_stats, int tid, int lane, long long* dbg = nullptr,
-                                                    const llword* x_ll = nullptr, uint32_t ep = 0, const NormPre* npre = nullptr) {
-    const QLayout& L = a.L;
-    const int K = L.K, kpad = layout_kpad(L);
-    const float* nw = a.norm_w;
-    const bool vec = (K & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(nw)) & 15) == 0;
-    const int nvec = kpad >> 2, kvec = K >> 2;
-    for (int i = tid; i < slab.ncols * 3; i += kConsumerThreads) sm.acc[i] = 0;
-    constexpr int B = 4;  // float4 loads in flight per thread
-    float4 xv[B], wv[B];
-    bool okv[B] = {true, true, true, true};
-    auto issue = [&](int v0, bool use_pre) {
-#pragma unroll
-        for (int i = 0; i < B; ++i) {
-            const int v = v0 + i * kConsumerThreads;
-            if (x_ll != nullptr) xv[i] = v < kvec ? ll_try4(x_ll + 4 * v, ep, okv[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            else xv[i] = v < nvec ? ld_x4(x, v, K, vec, coherent) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (use_pre) wv[i] = npre->w[i];
-            else wv[i] = (nw != nullptr && v < nvec) ? ld_x4(nw, v, K, vec, false) : make_float4(1.f, 1.f, 1.f, 1.f);
-        }
-    };
-    issue(tid, npre != nullptr && npre->valid);
-    if (dbg) dbg[0] = clock64();
-    const XStats st = get_stats();
-    if (dbg) dbg[1] = clock64();
-    float inv_rms = 1.f, amax = st.am;
-    if (nw != nullptr) {
-        inv_rms = rsqrtf(st.ss / (float)K + a.rms_eps);  // :1501
-        amax = amax * inv_rms * 1.00001f;                 // a bound of max|y|, y = x * inv_rms * w
-    }
-    const bool finite = amax > 0.f && amax < INFINITY;
-    const float inv_s = finite ? __fdividef(kXQMax, amax) : 0.f;  // |y * inv_s| <= kXQMax * (1 + 2e-5) < 2^23
-    const float s_x = finite ? amax * (1.0f / kXQMax) : 0.f;
-    long long sxf = 0;
-    for (int v0 = tid; v0 < nvec; v0 += B * kConsumerThreads) {
-        if (v0 != tid) issue(v0, false);
-        if (x_ll != nullptr) {   // all loads of the batch were issued before this first check; stragglers spin
-#pragma unroll
-            for (int i = 0; i < B; ++i) {
-                const int v = v0 + i * kConsumerThreads;
-                if (v < kvec && !okv[i]) xv[i] = ll_wait4(x_ll + 4 * v, ep);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < B; ++i) {
-            const int v = v0 + i * kConsumerThreads;
-            if (v < nvec) {
-                float4 t = xv[i];
-                if (nw != nullptr) {
-                    // the reference divides by rms (:1504-1506); multiplying by the reciprocal differs by ~1 ulp, far
-                    // below the 2^-24 max|y| granularity of the fixed-point conversion that follows
-                    t.x = (t.x * inv_rms) * wv[i].x;
-                    t.y = (t.y * inv_rms) * wv[i].y;
-                    t.z = (t.z * inv_rms) * wv[i].z;
-                    t.w = (t.w * inv_rms) * wv[i].w;
-                }
-                x_store_digits<BITS>(sm.xd, v, t, inv_s, sxf);
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sxf += __shfl_xor_sync(0xffffffffu, sxf, o);
-    if (lane == 0) sm.sxf[tid >> 5] = sxf;
-    if (dbg) dbg[2] = clock64();
-    bar_sync(1, kConsumerThreads);
-    if (dbg) dbg[3] = clock64();
-    return s_x;
-}
-
-// The same prologue, written for the persistent kernel's instruction footprint (every phase re-enters this code, and
-// the kernel is far larger than the 32 KiB instruction cache): 128-bit loads only -- the host checks K % 4 == 0 and the
-// 16-byte alignment once -- and a single copy of the conversion body.
-template <int BITS, typename StatsFn>
+template <int BITS>
 __device__ __forceinline__ float gemv_stage_x_lean(const GemvArgs& a, const float* x, const GemvSmem& sm, const Slab& slab, bool coherent,
-                                                   StatsFn&& get_stats, int tid, int lane) {
+                                                   XStats st, XPre& pre, bool load_w, int tid, int lane, long long* ts = nullptr) {
     const int K = a.L.K, nvec = layout_kpad(a.L) >> 2, kvec = K >> 2;
     const float4* nw4 = reinterpret_cast<const float4*>(a.norm_w);
     const float4* x4 = reinterpret_cast<const float4*>(x);
-    for (int i = tid; i < slab.ncols * 3; i += kConsumerThreads) sm.acc[i] = 0;
-    constexpr int B = 4;
+    constexpr int B = kXBatch;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f), one4 = make_float4(1.f, 1.f, 1.f, 1.f);
-    float4 xv[B], wv[B];
-    auto issue = [&](int v0) {
+    float4 xv[B];
+    auto issue = [&](int v0, bool with_w) {
 #pragma unroll
         for (int i = 0; i < B; ++i) {
             const int v = v0 + i * kConsumerThreads;
             xv[i] = v < kvec ? (coherent ? __ldcg(x4 + v) : x4[v]) : zero4;
-            wv[i] = (nw4 != nullptr && v < kvec) ? __ldg(nw4 + v) : one4;
+            if (with_w) pre.w[i] = (nw4 != nullptr && v < kvec) ? ldg_stream4(nw4 + v) : one4;
         }
     };
-    issue(tid);
-    const XStats st = get_stats();
+    issue(tid, load_w);
+    if (ts) ts[0] = clock64();
+    for (int i = tid; i < slab.ncols * 3; i += kConsumerThreads) sm.acc[i] = 0;
     float inv_rms = 1.f, amax = st.am;
     if (nw4 != nullptr) {
         inv_rms = rsqrtf(st.ss / (float)K + a.rms_eps);  // :1501
-        amax = amax * inv_rms * 1.00001f;
+        amax = amax * inv_rms * 1.00001f;                 // a bound of max|y|, y = x * inv_rms * w
     }
     const bool finite = amax > 0.f && amax < INFINITY;
-    const float inv_s = finite ? __fdividef(kXQMax, amax) : 0.f;
+    const float inv_s = finite ? __fdividef(kXQMax, amax) : 0.f;   // |y * inv_s| <= kXQMax * (1 + 2e-5)
     const float s_x = finite ? amax * (1.0f / kXQMax) : 0.f;
+    if (ts) ts[1] = clock64();
     long long sxf = 0;
     int v0 = tid;
     while (true) {
@@ -505,17 +425,20 @@ __device__ __forceinline__ float gemv_stage_x_lean(const GemvArgs& a, const floa
             const int v = v0 + i * kConsumerThreads;
             if (v < nvec) {
                 float4 t = xv[i];
-                t.x = (t.x * inv_rms) * wv[i].x;   // reciprocal instead of the reference's division: ~1 ulp, see above
-                t.y = (t.y * inv_rms) * wv[i].y;
-                t.z = (t.z * inv_rms) * wv[i].z;
-                t.w = (t.w * inv_rms) * wv[i].w;
+                // the reference divides by rms (:1504-1506); multiplying by the reciprocal differs by ~1 ulp, far below
+                // the 2^-24 max|y| granularity of the fixed-point conversion that follows
+                t.x = (t.x * inv_rms) * pre.w[i].x;
+                t.y = (t.y * inv_rms) * pre.w[i].y;
+                t.z = (t.z * inv_rms) * pre.w[i].z;
+                t.w = (t.w * inv_rms) * pre.w[i].w;
                 x_store_digits<BITS>(sm.xd, v, t, inv_s, sxf);
             }
         }
         v0 += B * kConsumerThreads;
         if (v0 >= nvec) break;
-        issue(v0);
+        issue(v0, true);
     }
+    if (ts) ts[2] = clock64();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sxf += __shfl_xor_sync(0xffffffffu, sxf, o);
     if (lane == 0) sm.sxf[tid >> 5] = sxf;
@@ -527,7 +450,7 @@ __device__ __forceinline__ float gemv_stage_x_lean(const GemvArgs& a, const floa
 // one LDS of digits (the B fragments) and 2 (INT4) / 1 (INT8) IMMA; when the warp's run over a group ends, the C
 // fragments are added to the column sums in shared memory (no cross-lane reduction needed).
 template <int BITS, int DBG = 0>
-__device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, uint32_t& it, int warp, int lane,
+__device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, RingPos& it, int warp, int lane,
                                              long long* dbg = nullptr) {
     const QLayout& L = a.L;
     const int S = a.stages;
@@ -564,36 +487,40 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
         acc.clear();
         dirty = false;
     };
-    uint32_t st = it % S, par = (it / S) & 1;
-    it += nrounds;
     bool ready = false;   // the NEXT stage's barrier is probed while this stage is being multiplied
-    for (int r = 0; r < nrounds; ++r) {
-        if (r > 0 && ++st == (uint32_t)S) { st = 0; par ^= 1; }
+    for (int r = 0; r < nrounds; ++r, it.advance(S)) {
+        const uint32_t st = it.st, par = it.par;
         const bool have = r < my_nq;
         // 512-byte items of the warps before this one in the stage
         const int l_items = (l_before && r < l_nq) ? (l_fq + r >= slab.qfull ? slab.nlast : 4) : 0;
         const int woff = __reduce_add_sync(0xffffffffu, l_items);
-        uint4 xv[4];
-        if (have) {   // does not depend on the stage: before the wait
-#pragma unroll
-            for (int i = 0; i < 4; ++i) xv[i] = load_xfrag<BITS>(xlane + chunk * kChunkBytes + i * kXItem);
+        const uint32_t xq = xlane + chunk * kChunkBytes;
+        uint4 xa, xb;
+        if (have) {   // digits of the first two k-items: they do not depend on the stage, so before the wait
+            xa = load_xfrag<BITS>(xq);
+            xb = load_xfrag<BITS>(xq + kXItem);
         }
         if (DBG != 2 && !ready) mbar_wait(&sm.full[st], par);
         if (dbg && r == 0) dbg[0] = clock64();
         ready = false;
-        const uint32_t st_n = st + 1 == (uint32_t)S ? 0u : st + 1, par_n = st + 1 == (uint32_t)S ? par ^ 1u : par;
+        RingPos nx = it;
+        nx.advance(S);
         if (have) {
             const int nl = grp == slab.ngroups - 1 ? slab.nlast : 4;
             const uint32_t qbase = ring_base + st * kStageBytes + woff * kItemBytes;
-            auto one = [&](int i, const uint4& wv) {
-                if (DBG != 1) kitem_mma<BITS>(acc, i & 1, wv, xv[i]);
+            auto one = [&](int i, const uint4& wv, const uint4& xv) {
+                if (DBG != 1) kitem_mma<BITS>(acc, i & 1, wv, xv);
                 else acc.lo[0][0] += (int)(wv.x ^ wv.y ^ wv.z ^ wv.w);
             };
-            if (nl == 4) {  // the common case, straight-line: four loads in flight
+            if (nl == 4) {  // the common case, straight-line, two k-items at a time (register budget)
                 const uint32_t wbase = qbase + lane * 16;
-                const uint4 w0 = lds128s(wbase), w1 = lds128s(wbase + 512), w2 = lds128s(wbase + 1024), w3 = lds128s(wbase + 1536);
-                if (DBG != 2 && r + 1 < nrounds) ready = mbar_test_wait(&sm.full[st_n], par_n);
-                one(0, w0); one(1, w1); one(2, w2); one(3, w3);
+                const uint4 w0 = lds128s(wbase), w1 = lds128s(wbase + 512);
+                one(0, w0, xa); one(1, w1, xb);
+                const uint4 w2 = lds128s(wbase + 1024), w3 = lds128s(wbase + 1536);
+                xa = load_xfrag<BITS>(xq + 2 * kXItem);
+                xb = load_xfrag<BITS>(xq + 3 * kXItem);
+                if (DBG != 2 && r + 1 < nrounds) ready = mbar_test_wait(&sm.full[nx.st], nx.par);
+                one(2, w2, xa); one(3, w3, xb);
             } else {        // ragged last group of the slab: rows 0..7 in part A, rows 8..11 (nl = 3) in part B
                 const bool in_a = nl > 1 || lane < 16, in_b = nl == 3 && lane < 16;
                 const uint32_t wbase = qbase + lane * 8;
@@ -602,7 +529,9 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
                     uint2 pa = make_uint2(0u, 0u), pb = make_uint2(0u, 0u);
                     if (in_a) pa = lds64s(wbase + i * nl * 128);
                     if (in_b) pb = lds64s(wbase + i * nl * 128 + 256);
-                    one(i, make_uint4(pa.x, pb.x, pa.y, pb.y));
+                    if (i == 2) xa = load_xfrag<BITS>(xq + 2 * kXItem);
+                    if (i == 3) xb = load_xfrag<BITS>(xq + 3 * kXItem);
+                    one(i, make_uint4(pa.x, pb.x, pa.y, pb.y), (i & 1) ? xb : xa);
                 }
             }
             dirty = true;
@@ -625,12 +554,13 @@ struct EpiPre {
     float cs0, cs1;   // colscale
     float zt0, zt1;   // colzterm (0 when absent)
     float r0;         // residual input (EPI_RESIDUAL)
+    float nw0;        // RMSNorm weight the next GEMV applies to this column (1 when none): for the output statistics
     float invf;       // inv_freq entry (EPI_QKV with RoPE)
     int page;         // physical KV page of the current position (EPI_QKV)
 };
 
 __device__ __forceinline__ EpiPre gemv_epilogue_prefetch(const GemvArgs& a, const Slab& slab, const float* resid, const PhaseCtx& ctx, int tid) {
-    EpiPre p{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0};
+    EpiPre p{0.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0};
     const bool pairs = a.epi == EPI_SWIGLU || a.epi == EPI_QKV;
     const int c = pairs ? 2 * tid : tid;
     const int n = slab.col0 + c;
@@ -642,7 +572,8 @@ __device__ __forceinline__ EpiPre gemv_epilogue_prefetch(const GemvArgs& a, cons
             if (a.colzterm) p.zt1 = a.colzterm[n + 1];
         }
         if (a.epi == EPI_RESIDUAL)
-            p.r0 = (ctx.ll_epoch && !ctx.resid_plain) ? ll_value(ll_load(reinterpret_cast<const llword*>(resid) + n)) : ld_act(resid + n, ctx.coherent);
+            p.r0 = ld_act(resid + n, ctx.coherent);
+        if (!pairs && a.next_norm_w) p.nw0 = a.next_norm_w[n];
         if (a.epi == EPI_QKV) {
             const int pos = ctx.pos >= 0 ? ctx.pos : *a.pos_ptr;
             p.page = a.page_table[pos / a.page_tokens];
@@ -664,9 +595,6 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
     for (int i = 0; i < kConsumerWarps; ++i) sxf += sm.sxf[i];
     const long long offterm = (long long)a.woff * sxf;
     const float fsxf = (float)sxf;
-    const uint32_t ep = ctx.ll_epoch;
-    llword* const out_ll = reinterpret_cast<llword*>(a.out);
-    const llword* const resid_ll = reinterpret_cast<const llword*>(resid);
     // y = cs * s_x * (sum_k u_k xf_k - off * sum xf + zt * sum xf)
     auto colval = [&](int c, float cs, float zt) -> float {
         const int* p = sm.acc + c * 3;
@@ -688,8 +616,7 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
             if (a.epi == EPI_SWIGLU) {
                 const float sg = y0 / (1.0f + expf(-y0));  // silu(gate), :918
                 const float o = y1 * sg;                    // multiply(up, silu(gate))
-                if (ep) ll_store_f(out_ll + (n0 >> 1), o, ep);
-                else a.out[n0 >> 1] = o;
+                a.out[n0 >> 1] = o;
                 out_st.am = fmaxf(out_st.am, fabsf(o));
             } else {
                 const int H = a.hidden;
@@ -704,18 +631,12 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
                     o1 = __fadd_rn(__fmul_rn(y0, sn), __fmul_rn(y1, cs));
                 }
                 if (seg == 0) {
-                    if (ep) { ll_store_f(out_ll + d, o0, ep); ll_store_f(out_ll + d + 1, o1, ep); }
-                    else *reinterpret_cast<float2*>(a.out + d) = make_float2(o0, o1);
+                    *reinterpret_cast<float2*>(a.out + d) = make_float2(o0, o1);
                 } else {
                     const int page = first ? pre.page : a.page_table[pos / a.page_tokens];
                     const size_t off = ((size_t)page * a.page_tokens + (pos % a.page_tokens)) * H + d;
                     float* dst = seg == 1 ? a.k_pool : a.v_pool;
                     *reinterpret_cast<float2*>(dst + off) = make_float2(o0, o1);
-                    if (ep) {  // this step's attention reads the new row from here, later steps from the cache
-                        llword* nl = (seg == 1 ? ctx.knew_ll : ctx.vnew_ll) + d;
-                        ll_store_f(nl, o0, ep);
-                        ll_store_f(nl + 1, o1, ep);
-                    }
                 }
             }
         }
@@ -729,15 +650,14 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
             const float cs = first ? pre.cs0 : a.colscale[n];
             const float zt = first ? pre.zt0 : (a.colzterm ? a.colzterm[n] : 0.f);
             float y = colval(c, cs, zt);
-            if (a.epi == EPI_RESIDUAL) y = (first ? pre.r0 : ((ep && !ctx.resid_plain) ? ll_value(ll_load(resid_ll + n)) : ld_act(resid + n, ctx.coherent))) + y;
+            if (a.epi == EPI_RESIDUAL) y = (first ? pre.r0 : ld_act(resid + n, ctx.coherent)) + y;
             else if (a.epi == EPI_RELU) y = fmaxf(y, 0.f);
-            if (ep && a.epi != EPI_LOGITS) ll_store_f(out_ll + n, y, ep);
-            else a.out[n] = y;
+            a.out[n] = y;
             if (a.epi == EPI_LOGITS) {
                 if (y > best) { best = y; besti = n; }
             } else {
                 out_st.ss = fmaf(y, y, out_st.ss);
-                out_st.am = fmaxf(out_st.am, fabsf(a.next_norm_w ? y * a.next_norm_w[n] : y));
+                out_st.am = fmaxf(out_st.am, fabsf(y * (first ? pre.nw0 : (a.next_norm_w ? a.next_norm_w[n] : 1.f))));
             }
         }
         if (a.epi == EPI_LOGITS) {
@@ -747,8 +667,7 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
                 const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
                 key = other > key ? other : key;
             }
-            if (ctx.keyred) { if (lane == 0) ctx.keyred[tid >> 5] = key; }
-            else if (lane == 0 && key != 0ull) atomicMax(ctx.key ? ctx.key : a.argmax_key, key);
+            if (lane == 0 && key != 0ull) atomicMax(ctx.key ? ctx.key : a.argmax_key, key);
         }
     }
     return out_st;
@@ -771,14 +690,14 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const __grid_cons
     const GemvSmem sm = gemv_carve(smem_raw, a.L, a.stages);
     if (tid == 0) gemv_init_barriers(sm, a.stages);
     __syncthreads();
-    uint32_t it = 0;
+    RingPos it;
     if (warp == kConsumerWarps) {
         // the weights do not depend on the previous kernel: start streaming at once
         gemv_produce(a, slab, sm, it, lane);
         return;
     }
     pdl_wait_prior_grid();  // x (and resid / pos) come from the previous kernel in the stream
-    const PhaseCtx ctx{false, -1, nullptr, 0u, nullptr, nullptr, nullptr, false};
+    const PhaseCtx ctx{false, -1, nullptr};
     const EpiPre pre = gemv_epilogue_prefetch(a, slab, a.resid, ctx, tid);
     const float s_x = gemv_stage_x<BITS>(a, a.x, sm, slab, false, tid, warp, lane);
     gemv_consume<BITS, DBG>(a, slab, sm, it, warp, lane);

@@ -328,12 +328,6 @@ struct AttnArgs {
     float* part_o;           // [heads][max_splits][D]
     float* part_ml;          // [heads][max_splits][2]
     float* out;              // [heads*D]
-    // dataflow engine (mega_ll.cuh): inputs / outputs as LL words
-    const llword* q_ll;      // [H]
-    const llword* knew_ll;   // [H] K row of the current token
-    const llword* vnew_ll;   // [H]
-    llword* out_ll;          // [H]
-    llword* part_ll;         // [heads][max_splits][D + 2]: o, then m, l
 };
 
 __device__ __forceinline__ const float* kv_row(const float* pool, const int* table, int page_tokens, int H, int t) {

@@ -20,7 +20,7 @@ namespace tib {
 enum MegaPhaseType : int { PH_GEMV = 0, PH_ATTN = 1 };
 struct MegaArgs;
 __device__ __forceinline__ bool getenv_dbg_consume(const MegaArgs& m);
-constexpr int kStampsPerPhase = 12;  // debug timeline: 6 phase-level stamps + 6 inside the prologue
+constexpr int kStampsPerPhase = 32;  // debug timeline: 6 phase-level stamps, [11] ring stages ready, [12..] finer stamps
 enum MegaSrc : int { SRC_PTR = 0, SRC_EMB = 1 };
 
 struct MegaPhase {
@@ -54,7 +54,7 @@ struct MegaArgs {
     int n_prompt;
     int n_steps;          // forward passes in this launch
     int first_sample;     // steps >= first_sample run the lm_head and pick a token
-    unsigned int* grid_bar;       // zeroed by the host before every launch
+    unsigned int* grid_bar;       // kBarWords barrier words, 128 bytes apart; zeroed by the host before every launch
     unsigned int* head_cnt;       // [heads]; zero between phases by construction
     unsigned long long* keys;     // [2] argmax keys, zeroed by the host before every launch
     float* logits;
@@ -62,13 +62,13 @@ struct MegaArgs {
     int max_kpad, max_units, attn_floats;
     long long* dbg;   // optional: CTA 0 writes 6 clock64 stamps per phase of step 0 (debug timeline)
     int dbg_nomath;   // debug: the main loop only XORs the weights (what the ring alone can deliver)
-    float4* stats;            // [2][gridDim.x][2]: per-CTA partial statistics (32-byte slots) of the phase's output, by phase parity
+    int dbg_flags;    // A/B switches (debug): 1 = norm weights loaded after the barrier, 2 = no L1 prefetch of the next descriptor
     const XStats* emb_stats;  // [V]: statistics of every embedding row (against the first norm weight)
 };
 
 __device__ __forceinline__ bool getenv_dbg_consume(const MegaArgs& m) { return m.dbg_nomath == 3; }
 TIB_HD size_t mega_smem_bytes(int stages, int max_kpad, int max_units, int attn_floats) {
-    return gemv_smem_bytes_for(stages, max_kpad, max_units) + 16 + (size_t)attn_floats * 4 + 16 + ((sizeof(MegaPhase) + 15) & ~size_t(15));
+    return gemv_smem_bytes_for(stages, max_kpad, max_units) + 16 + (size_t)attn_floats * 4 + 16 + 2 * ((sizeof(MegaPhase) + 15) & ~size_t(15));
 }
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -78,6 +78,28 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 }
 __device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- the grid barrier -------------------------------------------------------------------------------------------
+// One 16-byte word per barrier instance, {arrivals, max|y*w| as float bits, sum(y^2) in 2^-28 fixed point (64 bits)}:
+// every CTA reduces its partial statistics of the phase's output into the word (integer atomics: exact, so the
+// result does not depend on the arrival order) BEFORE its release-increment of the arrival count, and the one polling
+// thread per CTA reads count and statistics with a single 16-byte load -- the next phase's prologue needs no second
+// round trip to L2 (measured: gathering 148 per-CTA slots after the barrier cost 1.2-1.9 us per phase).  Four words in
+// rotation, each in its own 128-byte line; CTA 0 clears word (k-1) & 3 after passing barrier k (every CTA arrived at
+// k, so every CTA has finished reading k-1), three barriers before its next use.
+constexpr int kBarWords = 4, kBarStride = 32;   // in 32-bit units
+constexpr float kSsScale = 268435456.0f;         // 2^28: resolution 3.7e-9, range 6.9e10
+__device__ __forceinline__ void bar_arrive_stats(unsigned int* w, float ss, float am) {
+    const unsigned long long q = __float2ull_rn(fminf(ss, 6.0e10f) * kSsScale);
+    asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(w + 1), "r"(__float_as_uint(am)) : "memory");
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(w + 2), "l"(q) : "memory");
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(w) : "memory");
+}
+__device__ __forceinline__ uint4 bar_poll(const unsigned int* w) {
+    uint4 v;
+    asm volatile("ld.acquire.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(w) : "memory");
+    return v;
 }
 
 // ---- attention work item (head h, split j) for NT cooperating threads -----------------------------------
@@ -410,12 +432,15 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
     float* attn_sm = reinterpret_cast<float*>(p);
     p += (size_t)m.attn_floats * 4;
     p = (p + 15) & ~uintptr_t(15);
-    MegaPhase* sph = reinterpret_cast<MegaPhase*>(p);  // this phase's descriptor, staged by the consumers
+    // the phase descriptors, staged by the consumers; two slots: a warp may already stage the next phase's while another
+    // still reads this phase's in its epilogue (nobody is more than one barrier ahead)
+    MegaPhase* const sph0 = reinterpret_cast<MegaPhase*>(p);
+    MegaPhase* const sph1 = reinterpret_cast<MegaPhase*>(p + ((sizeof(MegaPhase) + 15) & ~size_t(15)));
     if (tid == 0) gemv_init_barriers(sm, m.stages);
     __syncthreads();
 
     const int pos0 = m.st->pos;
-    uint32_t it = 0;
+    RingPos it;
 
     if (warp >= kConsumerWarps) {
         // ===== producer warpgroup: warp 16 streams every GEMV phase of every step, back to back =====
@@ -456,65 +481,60 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                 }
             }
         }
+        // ===== warp 17: the grid barrier =====
+        // Arriving (a gpu-scope release = MEMBAR, ~0.6 us) and polling are a serial chain of L2 round trips.  A consumer
+        // thread doing them would hold its warp's share of the next phase's pre-barrier work behind that chain; this
+        // warp has nothing else to do.  Consumers signal "phase done" with bar.arrive 2 and pick the statistics of the
+        // phase's output up from shared memory after bar.sync 3.
+        if (warp == kConsumerWarps + 1) {
+            unsigned int k = 0;
+            for (int s = 0; s < m.n_steps; ++s) {
+                const int nph = m.nphases - (s >= m.first_sample ? 0 : 1);   // the lm_head runs on sampling steps only
+                for (int ph = 0; ph < nph; ++ph, ++k) {
+                    bar_sync(2, kConsumerThreads + 32);   // every consumer thread has stored its outputs and partials
+                    if (lane == 0) {
+                        float ss = 0.f, am = 0.f;
+#pragma unroll
+                        for (int i = 0; i < kConsumerWarps; ++i) { ss += sm.red[32 + i]; am = fmaxf(am, sm.red[48 + i]); }
+                        unsigned int* w = m.grid_bar + (k & (kBarWords - 1)) * kBarStride;
+                        bar_arrive_stats(w, ss, am);
+                        const long long t0 = clock64();
+                        uint4 v = bar_poll(w);
+                        while (v.x < gridDim.x) {
+                            if (clock64() - t0 > 8000000000LL) __trap();
+                            v = bar_poll(w);
+                        }
+                        sm.red[0] = __ull2float_rn(((unsigned long long)v.w << 32) | v.z) * (1.0f / kSsScale);
+                        sm.red[1] = __uint_as_float(v.y);
+                        if (blockIdx.x == 0)
+                            *reinterpret_cast<uint4*>(m.grid_bar + ((k + kBarWords - 1) & (kBarWords - 1)) * kBarStride) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    __syncwarp();
+                    bar_arrive(3, kConsumerThreads + 32);  // barrier passed, statistics in sm.red[0..1]
+                }
+            }
+        }
         return;
     }
 
     // ===== consumers =====
     reg_alloc<104>();
-    unsigned int bar_target = 0;
-    bool need_wait = false;
     // ends a phase: publishes this CTA's partial statistics of the phase's output, then arrives on the grid barrier
-    auto grid_arrive = [&](int ph, XStats st) {
+    bool need_wait = false;
+    // ends a phase: leaves this CTA's partial statistics of the phase's output for the barrier warp and signals it
+    auto grid_arrive = [&](XStats st, long long* ts) {
         st.ss = warp_sum(st.ss);
         st.am = warp_max(st.am);
         if (lane == 0) { sm.red[32 + warp] = st.ss; sm.red[48 + warp] = st.am; }
-        bar_sync(1, kConsumerThreads);  // every consumer thread's stores are ordered before thread 0's release
-        if (warp == 0) {
-            // a whole 32-byte sector per CTA (a partial-sector write would have L2 fetch the rest from HBM first), in a
-            // buffer small enough to stay L2-resident: two copies, alternating with the phase
-            float ss = 0.f, am = 0.f;
-#pragma unroll
-            for (int i = 0; i < kConsumerWarps; ++i) { ss += sm.red[32 + i]; am = fmaxf(am, sm.red[48 + i]); }
-            float* slot = reinterpret_cast<float*>(m.stats + ((size_t)(ph & 1) * gridDim.x + blockIdx.x) * 2);
-            if (lane < 8) slot[lane] = lane == 0 ? ss : (lane == 1 ? am : 0.f);
-            __syncwarp();
-            if (lane == 0) red_release_add(m.grid_bar, 1u);
-        }
-        bar_target += gridDim.x;
+        __syncwarp();
+        bar_arrive(2, kConsumerThreads + 32);   // does not wait: on to the next phase's pre-barrier work
+        if (ts) ts[21] = clock64();
         need_wait = true;
     };
-    // combines the per-CTA partials of phase `ph` in CTA order.  ONE warp per CTA reads them (thousands of warps asking
-    // for the same ten cache lines at once serialise in the L2 slice: measured 2 us) and hands the result to the
-    // others through shared memory; same loads and same addition tree in every CTA, so the bits are identical.
-    auto gather_stats = [&](int ph) -> XStats {
-        if (warp == 0) {
-            const float4* p = m.stats + (size_t)(ph & 1) * gridDim.x * 2;
-            constexpr int kMaxPer = 8;  // grids up to 256 CTAs
-            float2 v[kMaxPer];
-#pragma unroll
-            for (int j = 0; j < kMaxPer; ++j) {  // all loads in flight before the first use
-                const int i = lane + 32 * j;
-                v[j] = i < (int)gridDim.x ? __ldcg(reinterpret_cast<const float2*>(p + 2 * i)) : make_float2(0.f, 0.f);
-            }
-            float ss = 0.f, am = 0.f;
-#pragma unroll
-            for (int j = 0; j < kMaxPer; ++j) { ss += v[j].x; am = fmaxf(am, v[j].y); }
-            ss = warp_sum(ss);
-            am = warp_max(am);
-            if (lane == 0) { sm.red[0] = ss; sm.red[1] = am; }
-        }
-        bar_sync(1, kConsumerThreads);
-        return XStats{sm.red[0], sm.red[1]};
-    };
+    // waits until every CTA has finished the phase last arrived on; its output statistics are then in sm.red[0..1]
     auto grid_wait = [&]() {
         if (!need_wait) return;
-        if (tid == 0) {
-            const long long t0 = clock64();
-            while (ld_acquire_u32(m.grid_bar) < bar_target) {
-                if (clock64() - t0 > 8000000000LL) __trap();
-            }
-        }
-        bar_sync(1, kConsumerThreads);
+        bar_sync(3, kConsumerThreads + 32);
         need_wait = false;
     };
     auto decode_key = [&](int s) -> int {
@@ -533,6 +553,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
         }
     };
 
+    unsigned int phase_seq = 0;   // phases executed so far: selects the descriptor slot
     int token = m.st->token;  // decode-only launches continue from the token the previous launch picked
     for (int s = 0; s < m.n_steps; ++s) {
         const bool sample = s >= m.first_sample;
@@ -552,23 +573,30 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
             // Everything that does not depend on the previous phase's output happens BEFORE the grid barrier:
             // stage the phase descriptor in shared memory, fetch the epilogue's per-column constants.
             const MegaPhase& PG = m.phases[ph];
+            // the NEXT phase's descriptor: pull it into L1 now, so that its header does not start with a round trip to L2
+            if (tid * 128 < (int)sizeof(MegaPhase) && !(m.dbg_flags & 2)) {
+                const int nx = ph + 1 < m.nphases ? ph + 1 : 0;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(m.phases + nx) + tid * 128));
+            }
+            MegaPhase* const sph = (phase_seq++ & 1u) ? sph1 : sph0;
             {
                 const uint32_t* src = reinterpret_cast<const uint32_t*>(&PG);
                 uint32_t* dst = reinterpret_cast<uint32_t*>(sph);
                 for (int i = tid; i < (int)(sizeof(MegaPhase) / 4); i += kConsumerThreads) dst[i] = src[i];
             }
             const bool gemv_here = PG.type == PH_GEMV && (int)blockIdx.x < PG.g.L.P;
-            const PhaseCtx ctx{true, pos, is_head ? &m.keys[s & 1] : nullptr, 0u, nullptr, nullptr, nullptr, false};
+            const PhaseCtx ctx{true, pos, is_head ? &m.keys[s & 1] : nullptr};
             Slab slab{};
             EpiPre pre{};
-            NormPre npre;
-            npre.valid = false;
+            XPre xpre;
             const float* resid = nullptr;
             if (gemv_here) {
                 slab = make_slab(PG.g.L, blockIdx.x);
                 resid = PG.resid_src == SRC_EMB ? m.emb + (size_t)token * m.H : PG.g.resid;
                 pre = gemv_epilogue_prefetch(PG.g, slab, resid, ctx, tid);
+                if (!(m.dbg_flags & 1)) gemv_x_prefetch(PG.g, tid, xpre);
             }
+            if (stamp) ts[12] = clock64();
             if (need_wait) grid_wait(); else bar_sync(1, kConsumerThreads);
             const MegaPhase& P = *sph;
             if (stamp) { ts[1] = clock64(); ts[2] = ts[1]; ts[3] = ts[1]; }
@@ -579,23 +607,16 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                     const float* x = from_emb ? m.emb + (size_t)token * m.H : P.g.x;
                     const GemvArgs& g = P.g;
                     if (stamp) ts[6] = clock64();
-                    auto stats_fn = [&]() -> XStats { return from_emb ? m.emb_stats[token] : gather_stats(ph - 1); };
-                    const float s_x = gemv_stage_x_lean<BITS>(g, x, sm, slab, !from_emb, stats_fn, tid, lane);
-                    if (stamp) {
-                        ts[2] = clock64();
-                        int ready = 0;  // stages of this phase already in shared memory when its main loop starts
-                        for (int i = 0; i < m.stages && i < slab.rounds; ++i) {
-                            const uint32_t ii = it + i;
-                            ready += mbar_test_wait(&sm.full[ii % m.stages], (ii / m.stages) & 1) ? 1 : 0;   // non-blocking probe
-                        }
-                        ts[11] = ready;
-                    }
+                    // statistics of x: left in shared memory by grid_wait (reduced into the barrier word by the phase that produced x)
+                    const XStats xst = from_emb ? m.emb_stats[token] : XStats{sm.red[0], sm.red[1]};
+                    const float s_x = gemv_stage_x_lean<BITS>(g, x, sm, slab, !from_emb, xst, xpre, (m.dbg_flags & 1) != 0, tid, lane, stamp ? ts + 13 : nullptr);
+                    if (stamp) ts[2] = clock64();
 #ifdef TIB_MEGA_DEBUG_VARIANTS
                     if (m.dbg_nomath == 2) gemv_consume<BITS, 2>(g, slab, sm, it, warp, lane);
                     else if (m.dbg_nomath == 1) gemv_consume<BITS, 1>(g, slab, sm, it, warp, lane);
                     else
 #endif
-                    gemv_consume<BITS>(g, slab, sm, it, warp, lane, (stamp && getenv_dbg_consume(m)) ? ts + 8 : nullptr);
+                    gemv_consume<BITS>(g, slab, sm, it, warp, lane, stamp ? ts + 17 : nullptr);
                     if (stamp) ts[3] = clock64();
                     out_st = gemv_epilogue(g, slab, sm, s_x, resid, ctx, pre, tid, lane);
                 }
@@ -603,7 +624,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                 out_st.am = mega_attention(P.at, pos + 1, m.head_cnt, attn_sm);
             }
             if (stamp) ts[4] = clock64();
-            grid_arrive(ph, out_st);
+            grid_arrive(out_st, stamp ? ts : nullptr);
             if (stamp) ts[5] = clock64();
         }
     }

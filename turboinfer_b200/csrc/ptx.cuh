@@ -82,6 +82,12 @@ __device__ __forceinline__ void bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// producer side of a named barrier: counts this warp in and returns at once; memory accesses before it are visible
+// to the threads that bar.sync on the same barrier (the PTX producer/consumer pattern)
+__device__ __forceinline__ void bar_arrive(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- register re-allocation between warp roles (setmaxnreg; the kernel must carry __maxnreg__) ----------------
 template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -141,66 +147,18 @@ __device__ __forceinline__ uint4 lds128s(uint32_t saddr) {
     return v;
 }
 
+// read-only data used once per token (norm weights): do not let it push the phase descriptors out of the small L1
+__device__ __forceinline__ float4 ldg_stream4(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ uint2 lds64s(uint32_t saddr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
     return v;
 }
 
-// ---- "LL" words: a value and an epoch in ONE naturally aligned 64-bit word (single-copy atomic), so data can be handed
-// from one SM to others without a fence, a flag or a barrier: the consumer just re-reads until the epoch matches.
-typedef unsigned long long llword;
-__device__ __forceinline__ void ll_store(llword* p, uint32_t bits, uint32_t epoch) {
-    const llword w = ((llword)epoch << 32) | bits;
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
-__device__ __forceinline__ void ll_store_f(llword* p, float v, uint32_t epoch) { ll_store(p, __float_as_uint(v), epoch); }
-__device__ __forceinline__ llword ll_load(const llword* p) {
-    llword w;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
-    return w;
-}
-__device__ __forceinline__ void ll_load2(const llword* p, llword& a, llword& b) {  // 16-byte aligned pair, each word atomic
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-}
-__device__ __forceinline__ bool ll_ready(llword w, uint32_t epoch) { return (uint32_t)(w >> 32) == epoch; }
-__device__ __forceinline__ float ll_value(llword w) { return __uint_as_float((uint32_t)w); }
-// spin until the word carries `epoch`; a protocol bug traps instead of hanging the GPU
-__device__ __forceinline__ uint32_t ll_wait(const llword* p, uint32_t epoch) {
-    llword w = ll_load(p);
-    if (!ll_ready(w, epoch)) {
-        const long long t0 = clock64();
-        do {
-            w = ll_load(p);
-            if (clock64() - t0 > 8000000000LL) __trap();
-        } while (!ll_ready(w, epoch));
-    }
-    return (uint32_t)w;
-}
-__device__ __forceinline__ float ll_wait_f(const llword* p, uint32_t epoch) { return __uint_as_float(ll_wait(p, epoch)); }
-// four consecutive words (32-byte aligned) -> float4
-__device__ __forceinline__ float4 ll_wait4(const llword* p, uint32_t epoch) {
-    llword a, b, c, d;
-    ll_load2(p, a, b);
-    ll_load2(p + 2, c, d);
-    if (!(ll_ready(a, epoch) && ll_ready(b, epoch) && ll_ready(c, epoch) && ll_ready(d, epoch))) {
-        const long long t0 = clock64();
-        do {
-            ll_load2(p, a, b);
-            ll_load2(p + 2, c, d);
-            if (clock64() - t0 > 8000000000LL) __trap();
-        } while (!(ll_ready(a, epoch) && ll_ready(b, epoch) && ll_ready(c, epoch) && ll_ready(d, epoch)));
-    }
-    return make_float4(ll_value(a), ll_value(b), ll_value(c), ll_value(d));
-}
-// one attempt, no branch between the loads: callers issue several of these back to back and check afterwards
-__device__ __forceinline__ float4 ll_try4(const llword* p, uint32_t epoch, bool& ok) {
-    llword a, b, c, d;
-    ll_load2(p, a, b);
-    ll_load2(p + 2, c, d);
-    ok = ll_ready(a, epoch) && ll_ready(b, epoch) && ll_ready(c, epoch) && ll_ready(d, epoch);
-    return make_float4(ll_value(a), ll_value(b), ll_value(c), ll_value(d));
-}
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
 }  // namespace tib
