@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) k_consume_only(const __grid_c
     const float s_x = gemv_stage_x<BITS>(a, a.x, sm, slab, false, tid, warp, lane);
     const long long t0 = clock64();
     RingPos it;
-    gemv_consume<BITS, 2>(a, slab, sm, it, warp, lane);   // DBG 2: no mbarrier traffic, ring pre-filled
+    gemv_consume<BITS, 2>(a, slab, sm, it, make_consume_plan(a.L, slab, warp, lane), warp, lane);   // DBG 2: no mbarrier traffic, ring pre-filled
     const long long t1 = clock64();
     if (lane == 0) atomicMax((unsigned long long*)cycles, (unsigned long long)(t1 - t0));
     if (sm.acc[tid % 12] == 12345 && s_x == 1.f) a.out[0] = 1.f;

@@ -376,6 +376,23 @@ __device__ __forceinline__ float gemv_stage_x(const GemvArgs& a, const float* x,
 // static and usually come from HBM, not L2, so the thread's share is fetched BEFORE the grid barrier (XPre) and the x
 // loads are issued the moment the barrier opens.
 constexpr int kXBatch = 6;   // float4 vectors per thread per batch: K <= 12288 converts in one batch
+// The three scalars the conversion needs, from the statistics of x: y = (x * inv_rms) * w, xf = round(y * inv_s), y ~= s_x * xf
+struct XScale {
+    float inv_rms, inv_s, s_x;
+};
+__device__ __forceinline__ XScale make_xscale(XStats st, bool has_norm, int K, float rms_eps) {
+    XScale sc;
+    sc.inv_rms = 1.f;
+    float amax = st.am;
+    if (has_norm) {
+        sc.inv_rms = rsqrtf(st.ss / (float)K + rms_eps);  // :1501
+        amax = amax * sc.inv_rms * 1.00001f;                 // a bound of max|y|, y = x * inv_rms * w
+    }
+    const bool finite = amax > 0.f && amax < INFINITY;
+    sc.inv_s = finite ? __fdividef(kXQMax, amax) : 0.f;   // |y * inv_s| <= kXQMax * (1 + 2e-5)
+    sc.s_x = finite ? amax * (1.0f / kXQMax) : 0.f;
+    return sc;
+}
 struct XPre {
     float4 w[kXBatch];
 };
@@ -390,7 +407,7 @@ __device__ __forceinline__ void gemv_x_prefetch(const GemvArgs& a, int tid, XPre
 }
 template <int BITS>
 __device__ __forceinline__ float gemv_stage_x_lean(const GemvArgs& a, const float* x, const GemvSmem& sm, const Slab& slab, bool coherent,
-                                                   XStats st, XPre& pre, bool load_w, int tid, int lane, long long* ts = nullptr) {
+                                                   XScale sc, XPre& pre, bool load_w, int tid, int lane, long long* ts = nullptr) {
     const int K = a.L.K, nvec = layout_kpad(a.L) >> 2, kvec = K >> 2;
     const float4* nw4 = reinterpret_cast<const float4*>(a.norm_w);
     const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -408,14 +425,7 @@ __device__ __forceinline__ float gemv_stage_x_lean(const GemvArgs& a, const floa
     issue(tid, load_w);
     if (ts) ts[0] = clock64();
     for (int i = tid; i < slab.ncols * 3; i += kConsumerThreads) sm.acc[i] = 0;
-    float inv_rms = 1.f, amax = st.am;
-    if (nw4 != nullptr) {
-        inv_rms = rsqrtf(st.ss / (float)K + a.rms_eps);  // :1501
-        amax = amax * inv_rms * 1.00001f;                 // a bound of max|y|, y = x * inv_rms * w
-    }
-    const bool finite = amax > 0.f && amax < INFINITY;
-    const float inv_s = finite ? __fdividef(kXQMax, amax) : 0.f;   // |y * inv_s| <= kXQMax * (1 + 2e-5)
-    const float s_x = finite ? amax * (1.0f / kXQMax) : 0.f;
+    const float inv_rms = sc.inv_rms, inv_s = sc.inv_s, s_x = sc.s_x;
     if (ts) ts[1] = clock64();
     long long sxf = 0;
     int v0 = tid;
@@ -449,23 +459,38 @@ __device__ __forceinline__ float gemv_stage_x_lean(const GemvArgs& a, const floa
 // consumers, main loop: one quad per warp per ring stage -- 4 k-items, each one LDS.128 of weights (the A fragments),
 // one LDS of digits (the B fragments) and 2 (INT4) / 1 (INT8) IMMA; when the warp's run over a group ends, the C
 // fragments are added to the column sums in shared memory (no cross-lane reduction needed).
+// Where a warp starts in its slab: depends on the slab's geometry only, so the persistent kernel computes it BEFORE the
+// grid barrier (it holds an integer division).
+struct ConsumePlan {
+    int my_nq;        // quads of this warp
+    int grp, chunk;   // group / chunk of its first quad
+    int l_nq, l_fq;   // quads / first quad of warp (lane & 15): lanes stand for warps when stage offsets are summed
+};
+__device__ __forceinline__ ConsumePlan make_consume_plan(const QLayout& L, const Slab& slab, int warp, int lane) {
+    ConsumePlan p;
+    p.my_nq = warp_quads(slab, warp);
+    const int fq = warp_first_quad(slab, warp);
+    p.grp = fq / L.nchunks;
+    p.chunk = fq - p.grp * L.nchunks;
+    p.l_nq = warp_quads(slab, lane & 15);
+    p.l_fq = warp_first_quad(slab, lane & 15);
+    return p;
+}
 template <int BITS, int DBG = 0>
-__device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, RingPos& it, int warp, int lane,
-                                             long long* dbg = nullptr) {
+__device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, RingPos& it, const ConsumePlan& pl,
+                                             int warp, int lane, long long* dbg = nullptr) {
     const QLayout& L = a.L;
     const int S = a.stages;
     const int C = L.nchunks, nrounds = slab.rounds;
     constexpr int kChunkBytes = BITS == 4 ? 768 : 384;   // digits of one chunk: 4 k-items x 3 planes x 4 t x 16 / 8 B
     constexpr int kXItem = kChunkBytes / 4;
-    const int my_nq = warp_quads(slab, warp);
-    const int fq = warp_first_quad(slab, warp);
-    int grp = fq / C;          // group / chunk of the warp's next quad
-    int chunk = fq - grp * C;
+    const int my_nq = pl.my_nq;
+    int grp = pl.grp, chunk = pl.chunk;   // group / chunk of the warp's next quad
     const int g = lane >> 2, t = lane & 3;
     const uint32_t xlane = smem_u32(sm.xd) + ((g < 3 ? g : 0) * 4 + t) * (BITS == 4 ? 16 : 8);   // B column g = digit plane g
     const uint32_t ring_base = smem_u32(sm.ring);
     // lane l < 16 stands for warp l when the stage offsets are summed with one REDUX per round
-    const int l_nq = warp_quads(slab, lane & 15), l_fq = warp_first_quad(slab, lane & 15);
+    const int l_nq = pl.l_nq, l_fq = pl.l_fq;
     const bool l_before = lane < warp;  // warp < 16
     QuadAcc<BITS> acc;
     acc.clear();
@@ -700,7 +725,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const __grid_cons
     const PhaseCtx ctx{false, -1, nullptr};
     const EpiPre pre = gemv_epilogue_prefetch(a, slab, a.resid, ctx, tid);
     const float s_x = gemv_stage_x<BITS>(a, a.x, sm, slab, false, tid, warp, lane);
-    gemv_consume<BITS, DBG>(a, slab, sm, it, warp, lane);
+    gemv_consume<BITS, DBG>(a, slab, sm, it, make_consume_plan(a.L, slab, warp, lane), warp, lane);
     (void)gemv_epilogue(a, slab, sm, s_x, a.resid, ctx, pre, tid, lane);
 }
 

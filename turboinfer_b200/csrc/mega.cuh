@@ -484,13 +484,24 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
         // ===== warp 17: the grid barrier =====
         // Arriving (a gpu-scope release = MEMBAR, ~0.6 us) and polling are a serial chain of L2 round trips.  A consumer
         // thread doing them would hold its warp's share of the next phase's pre-barrier work behind that chain; this
-        // warp has nothing else to do.  Consumers signal "phase done" with bar.arrive 2 and pick the statistics of the
-        // phase's output up from shared memory after bar.sync 3.
+        // warp has nothing else to do.  Consumers signal "phase done" with bar.arrive 2 and, after bar.sync 3, pick up from
+        // shared memory the conversion scalars this warp derived from the statistics of the phase's output.
         if (warp == kConsumerWarps + 1) {
             unsigned int k = 0;
             for (int s = 0; s < m.n_steps; ++s) {
                 const int nph = m.nphases - (s >= m.first_sample ? 0 : 1);   // the lm_head runs on sampling steps only
                 for (int ph = 0; ph < nph; ++ph, ++k) {
+                    // what the NEXT phase's prologue needs to turn the statistics into its conversion scalars (fetched
+                    // while the consumers are still working on this phase)
+                    int nK = 0;
+                    bool nnorm = false;
+                    float neps = 0.f;
+                    if (lane == 0 && ph + 1 < nph) {
+                        const MegaPhase* np = m.phases + ph + 1;
+                        nK = __ldg(&np->g.L.K);
+                        nnorm = __ldg(reinterpret_cast<const unsigned long long*>(&np->g.norm_w)) != 0ull;
+                        neps = __ldg(&np->g.rms_eps);
+                    }
                     bar_sync(2, kConsumerThreads + 32);   // every consumer thread has stored its outputs and partials
                     if (lane == 0) {
                         float ss = 0.f, am = 0.f;
@@ -504,13 +515,18 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                             if (clock64() - t0 > 8000000000LL) __trap();
                             v = bar_poll(w);
                         }
-                        sm.red[0] = __ull2float_rn(((unsigned long long)v.w << 32) | v.z) * (1.0f / kSsScale);
-                        sm.red[1] = __uint_as_float(v.y);
+                        XStats st;
+                        st.ss = __ull2float_rn(((unsigned long long)v.w << 32) | v.z) * (1.0f / kSsScale);
+                        st.am = __uint_as_float(v.y);
+                        const XScale sc = make_xscale(st, nnorm, nK > 0 ? nK : 1, neps);
+                        sm.red[0] = sc.inv_rms;
+                        sm.red[1] = sc.inv_s;
+                        sm.red[2] = sc.s_x;
                         if (blockIdx.x == 0)
                             *reinterpret_cast<uint4*>(m.grid_bar + ((k + kBarWords - 1) & (kBarWords - 1)) * kBarStride) = make_uint4(0u, 0u, 0u, 0u);
                     }
                     __syncwarp();
-                    bar_arrive(3, kConsumerThreads + 32);  // barrier passed, statistics in sm.red[0..1]
+                    bar_arrive(3, kConsumerThreads + 32);  // barrier passed, scalars in sm.red[0..2]
                 }
             }
         }
@@ -531,7 +547,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
         if (ts) ts[21] = clock64();
         need_wait = true;
     };
-    // waits until every CTA has finished the phase last arrived on; its output statistics are then in sm.red[0..1]
+    // waits until every CTA has finished the phase last arrived on; the next prologue's scalars are then in sm.red[0..2]
     auto grid_wait = [&]() {
         if (!need_wait) return;
         bar_sync(3, kConsumerThreads + 32);
@@ -589,12 +605,14 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
             Slab slab{};
             EpiPre pre{};
             XPre xpre;
+            ConsumePlan plan{};
             const float* resid = nullptr;
             if (gemv_here) {
                 slab = make_slab(PG.g.L, blockIdx.x);
                 resid = PG.resid_src == SRC_EMB ? m.emb + (size_t)token * m.H : PG.g.resid;
                 pre = gemv_epilogue_prefetch(PG.g, slab, resid, ctx, tid);
                 if (!(m.dbg_flags & 1)) gemv_x_prefetch(PG.g, tid, xpre);
+                plan = make_consume_plan(PG.g.L, slab, warp, lane);
             }
             if (stamp) ts[12] = clock64();
             if (need_wait) grid_wait(); else bar_sync(1, kConsumerThreads);
@@ -607,16 +625,18 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                     const float* x = from_emb ? m.emb + (size_t)token * m.H : P.g.x;
                     const GemvArgs& g = P.g;
                     if (stamp) ts[6] = clock64();
-                    // statistics of x: left in shared memory by grid_wait (reduced into the barrier word by the phase that produced x)
-                    const XStats xst = from_emb ? m.emb_stats[token] : XStats{sm.red[0], sm.red[1]};
-                    const float s_x = gemv_stage_x_lean<BITS>(g, x, sm, slab, !from_emb, xst, xpre, (m.dbg_flags & 1) != 0, tid, lane, stamp ? ts + 13 : nullptr);
+                    // conversion scalars: from the barrier warp (it derived them from the statistics of the phase that
+                    // produced x), or from the precomputed statistics of the embedding row
+                    const XScale xsc = from_emb ? make_xscale(m.emb_stats[token], g.norm_w != nullptr, g.L.K, g.rms_eps)
+                                                : XScale{sm.red[0], sm.red[1], sm.red[2]};
+                    const float s_x = gemv_stage_x_lean<BITS>(g, x, sm, slab, !from_emb, xsc, xpre, (m.dbg_flags & 1) != 0, tid, lane, stamp ? ts + 13 : nullptr);
                     if (stamp) ts[2] = clock64();
 #ifdef TIB_MEGA_DEBUG_VARIANTS
-                    if (m.dbg_nomath == 2) gemv_consume<BITS, 2>(g, slab, sm, it, warp, lane);
-                    else if (m.dbg_nomath == 1) gemv_consume<BITS, 1>(g, slab, sm, it, warp, lane);
+                    if (m.dbg_nomath == 2) gemv_consume<BITS, 2>(g, slab, sm, it, plan, warp, lane);
+                    else if (m.dbg_nomath == 1) gemv_consume<BITS, 1>(g, slab, sm, it, plan, warp, lane);
                     else
 #endif
-                    gemv_consume<BITS>(g, slab, sm, it, warp, lane, stamp ? ts + 17 : nullptr);
+                    gemv_consume<BITS>(g, slab, sm, it, plan, warp, lane, stamp ? ts + 17 : nullptr);
                     if (stamp) ts[3] = clock64();
                     out_st = gemv_epilogue(g, slab, sm, s_x, resid, ctx, pre, tid, lane);
                 }
