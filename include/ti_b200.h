@@ -158,6 +158,14 @@ int ti_b200_decode_step(ti_model_t m, int32_t token, float* logits_host, int32_t
 int ti_b200_generate_greedy(ti_model_t m, const int32_t* prompt, int32_t n_prompt, int32_t n_new, int32_t stop_on_eos,
                             int32_t* out_tokens, int32_t* n_out, float* logits_host, float* decode_ms);
 
+/* generate_batch() (src/model/inference_engine.cpp:804-828, a sequential loop of generate() in the reference): `batch`
+ * prompts of equal length n_prompt ([batch][n_prompt]), n_new >= 1 greedy tokens each, advanced in lockstep so that the
+ * weights are read once per step for all sequences (tensor-core GEMM path, one KV cache per sequence).  out_tokens:
+ * [batch][n_new]; logits_last (optional): [batch][vocab] of the last step; decode_ms (optional): CUDA-event time of the
+ * n_new - 1 steps after the prompt.  Single-GPU models with every projection present only. */
+int ti_b200_generate_batch_greedy(ti_model_t m, const int32_t* prompts, int32_t batch, int32_t n_prompt, int32_t n_new,
+                                  int32_t* out_tokens, float* logits_last, float* decode_ms);
+
 /* CUDA-event time of the prompt phase (prefill) of the last ti_b200_generate_greedy call on this model, in ms */
 int ti_b200_model_last_prefill_ms(ti_model_t m, float* ms);
 

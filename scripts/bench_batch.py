@@ -1,0 +1,49 @@
+"""Batched decode (BASELINE.json configs[2], batch 32): B sequences in lockstep through the tcgen05 GEMM path.
+Prints one JSON line: aggregate decode tokens/s (CUDA-event time of the decode steps), e2e wall-clock rate, and the HBM
+bytes a step has to move (the GEMM reads the weights as one byte per element -- INT4 is stored unpacked for the tensor
+cores -- plus every sequence's fp32 KV cache)."""
+import argparse, json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import turboinfer_b200 as tb
+from helpers import SHAPES, meta_with_layers, prompt_tokens
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--shape", default="llama7b")
+ap.add_argument("--qtype", default="int4", choices=["int4", "int8"])
+ap.add_argument("--batch", type=int, default=32)
+ap.add_argument("--prompt", type=int, default=4)
+ap.add_argument("--new", type=int, default=256)
+ap.add_argument("--layers", type=int, default=0)
+ap.add_argument("--reps", type=int, default=3)
+args = ap.parse_args()
+tb.init(0)
+meta = SHAPES[args.shape] if not args.layers else meta_with_layers(SHAPES[args.shape], args.layers)
+m = tb.Model(meta, tb.Q_INT4 if args.qtype == "int4" else tb.Q_INT8, attn_mode=1, rope_mode=1, max_seq=args.prompt + args.new + 64)
+m.load_synthetic()
+prompts = np.array([prompt_tokens(args.prompt, meta["vocab"], offset=b) for b in range(args.batch)], dtype=np.int32)
+l0 = tb.launch_count()
+m.generate_batch_greedy(prompts, args.new)      # warm-up: builds the K-major weight copies and the step graphs
+dev, wall = [], []
+for _ in range(args.reps):
+    t0 = time.perf_counter()
+    toks, _, ms = m.generate_batch_greedy(prompts, args.new)
+    wall.append(time.perf_counter() - t0)
+    dev.append(ms)
+single, _, _ = m.generate_greedy(prompts[0], min(args.new, 16))
+H, L, I, V = meta["hidden"], meta["layers"], meta["inter"], meta["vocab"]
+w_elems = L * (4 * H * H + 3 * H * I) + H * V
+t_mid = args.prompt + args.new // 2
+kv = 2 * L * args.batch * t_mid * H * 4
+ms = float(np.median(dev))
+steps = args.new - 1
+out = {"metric": "decode_tokens_per_s", "value": args.batch * steps / (ms * 1e-3), "unit": "tokens/s", "n_gpus": 1,
+       "config": {"workload": f"{args.shape}-{args.qtype}-batch{args.batch}-decode{args.new}", "batch": args.batch, "prompt_tokens": args.prompt,
+                  "new_tokens": args.new, "path": "tcgen05 INT8 GEMM (three digit planes) + flash-decoding attention per sequence, CUDA graph per step"},
+       "ms_per_step": ms / steps, "e2e": {"value": args.batch * args.new / float(np.median(wall)), "unit": "tokens/s"},
+       "step_bytes": {"weights_as_read_by_the_gemm": w_elems, "kv_mid_run": kv, "GBps": (w_elems + kv) / (ms / steps * 1e-3) / 1e9},
+       "row0_equals_single_sequence_engine": bool(np.array_equal(toks[0][: len(single)], single)),
+       "gpu_launches": tb.launch_count() - l0, "tokens_tail_row0": [int(x) for x in toks[0][-4:]]}
+print(json.dumps(out))
+m.free()

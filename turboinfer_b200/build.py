@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libturboinfer_b200.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["ptx.cuh", "qlayout.cuh", "gemv.cuh", "kernels.cuh", "mega.cuh", "gemm_tc.cuh", "prefill.cuh"]
+HEADERS = ["ptx.cuh", "qlayout.cuh", "gemv.cuh", "kernels.cuh", "mega.cuh", "gemm_tc.cuh", "prefill.cuh", "batch.cuh"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
          "-shared", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -72,6 +72,7 @@ SYMBOLS = {
     "ti_b200_model_step_bytes": (C.c_int, [C.c_uint64, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ti_b200_decode_step": (C.c_int, [C.c_uint64, C.c_int32, _f, _i32]),
     "ti_b200_generate_greedy": (C.c_int, [C.c_uint64, _i32, C.c_int32, C.c_int32, C.c_int32, _i32, _i32, _f, _f]),
+    "ti_b200_generate_batch_greedy": (C.c_int, [C.c_uint64, _i32, C.c_int32, C.c_int32, C.c_int32, _i32, _f, _f]),
     "ti_b200_model_last_prefill_ms": (C.c_int, [C.c_uint64, _f]),
     "ti_b200_launch_count": (C.c_int, [C.POINTER(C.c_uint64)]),
     "ti_b200_bench_gemv": (C.c_int, [C.POINTER(C.c_uint64), C.c_size_t, C.c_size_t, _f]),
@@ -415,6 +416,18 @@ class Model:
                                           _fp(logits) if want_logits else C.cast(None, _f), C.byref(ms)))
         n = n_out.value
         return out[:n].copy(), (logits[:n].copy() if want_logits else None), ms.value
+
+    def generate_batch_greedy(self, prompts, n_new: int, *, want_logits: bool = False):
+        """generate_batch: prompts [B][n_prompt] (equal lengths) -> tokens [B][n_new], logits of the last step, decode ms."""
+        p = np.ascontiguousarray(np.asarray(prompts, dtype=np.int32))
+        assert p.ndim == 2
+        B, n_prompt = p.shape
+        out = np.zeros((B, n_new), dtype=np.int32)
+        logits = np.empty((B, self.meta["vocab"]), dtype=np.float32) if want_logits else None
+        ms = C.c_float()
+        _ck(lib().ti_b200_generate_batch_greedy(self.handle, p.ctypes.data_as(_i32), B, n_prompt, n_new, out.ctypes.data_as(_i32),
+                                                _fp(logits) if want_logits else C.cast(None, _f), C.byref(ms)))
+        return out, logits, ms.value
 
     def free(self) -> None:
         if self.handle:

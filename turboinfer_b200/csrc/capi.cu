@@ -20,6 +20,7 @@
 #include "mega.cuh"
 #include "gemm_tc.cuh"
 #include "prefill.cuh"
+#include "batch.cuh"
 
 using namespace tib;
 
@@ -269,6 +270,23 @@ struct Layer {
     DevBuf<float> lit_up, lit_down;
 };
 
+// Batched decode: B sequences in lockstep, each with its own pages of every layer's KV pools.
+struct BatchState {
+    int B = 0, pages_per_seq = 0, max_splits = 1;
+    std::vector<DevBuf<float>> k, v;     // per layer: [B * pages_per_seq][page_tokens][H]
+    DevBuf<int> tables;                  // [B][pages_per_seq] physical page of each logical page
+    DevBuf<int> tokens;                  // [B] tokens of the current step
+    DevBuf<int> prompts;                 // [n_prompt][B] (column p = the tokens of prompt step p)
+    DevBuf<int> out;                     // [B][n_new]
+    DevBuf<int> pos_step;                // [0] tokens in every cache, [1] output column
+    DevBuf<float> part_o, part_ml, logits;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};   // [0] step without sampling, [1] with lm_head + argmax
+    const void* cap_scratch = nullptr;               // what the captured graphs were built against: the scratch buffers
+    int cap_stride = 0;                              // ... and the row stride of `out`
+    void drop_graphs() { for (auto& g : graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; } }
+    ~BatchState() { drop_graphs(); }
+};
+
 struct Model {
     ti_model_config cfg{};
     std::vector<Layer> layers;
@@ -296,6 +314,7 @@ struct Model {
     DevBuf<int8_t> pf_planes;
     DevBuf<long long> pf_sxf;
     DevBuf<int> pf_tokens;
+    std::unique_ptr<struct BatchState> batch;   // batched decode (generate_batch): per-sequence KV pages, step graphs
     int tp = 1, tp_rank = 0;   // tensor-parallel degree / rank of this model
     DevBuf<float> ar_tmp;      // [H] partial output of a row-parallel GEMV, all-reduced in place
     DevBuf<MegaPhase> phases;
@@ -951,6 +970,95 @@ int prefill_gemm(Model& m, const int* prompt_dev, int M) {
         TRY(pf_digits(m, m.pf_act.p, nullptr, M, I, m_pad, ly.down->k_pad));
         TRY(pf_gemm(m, *ly.down, M, m_pad, m.pf_x.p, m.pf_x.p));
     }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- batched decode on the tensor cores (generate_batch, SURVEY.md 8 a5 / 8e "DP: batched-sequence path") ------------
+int ensure_pf_scratch(Model& m, int M) {
+    const int H = m.cfg.hidden, I = std::max(m.cfg.inter, 1);
+    const int m_pad = (M + kGemmBM - 1) / kGemmBM * kGemmBM;
+    int kmax = 0;
+    auto upd = [&](QWeight* w) { if (w) kmax = std::max(kmax, (layout_kpad(w->L) + kGemmBK - 1) / kGemmBK * kGemmBK); };
+    for (auto& ly : m.layers)
+        for (QWeight* w : {ly.qkv.get(), ly.o.get(), ly.gateup.get(), ly.down.get()}) upd(w);
+    upd(m.lm_head.get());
+    if (M > m.pf_cap || m.pf_planes.n < (size_t)3 * m_pad * kmax) {
+        TRY(m.pf_x.alloc((size_t)M * H));
+        TRY(m.pf_qkv.alloc((size_t)M * 3 * H));
+        TRY(m.pf_attn.alloc((size_t)M * H));
+        TRY(m.pf_gu.alloc((size_t)M * 2 * I));
+        TRY(m.pf_act.alloc((size_t)M * I));
+        TRY(m.pf_sx.alloc(M));
+        TRY(m.pf_sxf.alloc(M));
+        TRY(m.pf_planes.alloc((size_t)3 * m_pad * kmax));
+        m.pf_cap = M;
+    }
+    return 0;
+}
+
+bool batch_eligible(const Model& m) {
+    if (m.tp != 1 || m.cfg.compat_literal || m.cfg.rope_mode == 2 || !m.lm_head) return false;
+    for (auto& ly : m.layers) if (!(ly.qkv && ly.o && ly.gateup && ly.down)) return false;
+    return true;
+}
+
+// one lockstep step of all B sequences: tokens[b] -> KV append at *pos -> (sample: logits, argmax -> tokens[b], out)
+int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
+    const int B = bs.B, H = m.cfg.hidden, I = std::max(m.cfg.inter, 1), V = m.cfg.vocab;
+    const int m_pad = (B + kGemmBM - 1) / kGemmBM * kGemmBM;
+    const int rope_dim = m.cfg.rope_mode == 1 ? H / m.cfg.heads : 0;
+    embed_rows_kernel<<<B, 256, 0, g_stream>>>(m.tok_emb.p, bs.tokens.p, m.pf_x.p, H);
+    ++g_launches;
+    for (size_t l = 0; l < m.layers.size(); ++l) {
+        Layer& ly = m.layers[l];
+        TRY(pf_digits(m, m.pf_x.p, ly.attn_norm.p, B, H, m_pad, ly.qkv->k_pad));
+        TRY(pf_gemm(m, *ly.qkv, B, m_pad, m.pf_qkv.p, nullptr));
+        rope_kv_batch_kernel<<<B, 256, 0, g_stream>>>(m.pf_qkv.p, H, rope_dim, m.inv_freq.p, bs.pos_step.p, bs.k[l].p, bs.v[l].p, bs.tables.p,
+                                                       bs.pages_per_seq, m.page_tokens);
+        AttnArgs a{};
+        a.q = m.pf_qkv.p;
+        a.k_pool = bs.k[l].p;
+        a.v_pool = bs.v[l].p;
+        a.page_table = bs.tables.p;
+        a.page_tokens = m.page_tokens;
+        a.pos_ptr = bs.pos_step.p;
+        a.t_bias = 1;
+        a.H = H;
+        a.D = m.attn_dim;
+        a.heads = m.attn_heads;
+        a.max_splits = bs.max_splits;
+        a.min_chunk = 64;
+        a.scale = 1.0f / sqrtf((float)m.attn_dim);
+        a.part_o = bs.part_o.p;
+        a.part_ml = bs.part_ml.p;
+        a.out = m.pf_attn.p;
+        a.zq = 3 * H;
+        a.zout = H;
+        a.ztable = bs.pages_per_seq;
+        a.zpart_o = (size_t)m.attn_heads * bs.max_splits * m.attn_dim;
+        a.zpart_ml = (size_t)m.attn_heads * bs.max_splits * 2;
+        attn_partial_kernel<<<dim3(m.attn_heads, bs.max_splits, B), kAttnThreads, m.attn_smem, g_stream>>>(a);
+        attn_combine_kernel<<<dim3(m.attn_heads, 1, B), 256, 0, g_stream>>>(a);
+        g_launches += 3;
+        TRY(pf_digits(m, m.pf_attn.p, nullptr, B, H, m_pad, ly.o->k_pad));
+        TRY(pf_gemm(m, *ly.o, B, m_pad, m.pf_x.p, m.pf_x.p));
+        TRY(pf_digits(m, m.pf_x.p, ly.ffn_norm.p, B, H, m_pad, ly.gateup->k_pad));
+        TRY(pf_gemm(m, *ly.gateup, B, m_pad, m.pf_gu.p, nullptr));
+        if (ly.has_gate) swiglu_rows_kernel<<<grid_for((size_t)B * I), 256, 0, g_stream>>>(m.pf_gu.p, m.pf_act.p, (size_t)B, (size_t)I);
+        else relu_rows_kernel<<<grid_for((size_t)B * I), 256, 0, g_stream>>>(m.pf_gu.p, m.pf_act.p, (size_t)B * I);
+        ++g_launches;
+        TRY(pf_digits(m, m.pf_act.p, nullptr, B, I, m_pad, ly.down->k_pad));
+        TRY(pf_gemm(m, *ly.down, B, m_pad, m.pf_x.p, m.pf_x.p));
+    }
+    if (sample) {
+        TRY(pf_digits(m, m.pf_x.p, m.out_norm.p, B, H, m_pad, m.lm_head->k_pad));
+        TRY(pf_gemm(m, *m.lm_head, B, m_pad, bs.logits.p, nullptr));
+        argmax_rows_kernel<<<B, 256, 0, g_stream>>>(bs.logits.p, V, bs.tokens.p, bs.out.p, out_stride, bs.pos_step.p + 1);
+        ++g_launches;
+    }
+    batch_advance_kernel<<<1, 1, 0, g_stream>>>(bs.pos_step.p, sample ? 1 : 0);
+    ++g_launches;
     CK(cudaGetLastError());
     return 0;
 }
@@ -1687,6 +1795,111 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
             if (toks[i] == 2) { produced = i + 1; break; }  // hard-coded EOS id 2 (:760)
     for (int i = 0; i < produced; ++i) out_tokens[i] = toks[i];
     if (n_out) *n_out = produced;
+    return 0;
+}
+
+// InferenceEngine::generate_batch (src/model/inference_engine.cpp:804-828): `batch` prompts of equal length, n_new greedy
+// tokens each.  The reference loops over generate(); here the sequences advance in lockstep so that the weights are read
+// once per step for all of them (tensor-core GEMM path).  out_tokens: [batch][n_new]; logits_last (optional): [batch][vocab]
+// of the last step; decode_ms (optional): CUDA-event time of the n_new - 1 decode steps after the prompt.
+int ti_b200_generate_batch_greedy(ti_model_t h, const int32_t* prompts, int32_t batch, int32_t n_prompt, int32_t n_new, int32_t* out_tokens,
+                                  float* logits_last, float* decode_ms) {
+    TRY(need_init());
+    Model* mp = get_model(h);
+    if (!mp || !mp->finalized) return fail("invalid or unfinalized model handle");
+    Model& m = *mp;
+    if (batch <= 0) return fail("batch must be >= 1");
+    if (n_prompt <= 0) return fail("Input tokens cannot be empty");  // validate_input_tokens (:1409)
+    if (n_new <= 0) return fail("n_new must be >= 1");
+    if (!batch_eligible(m)) return fail("generate_batch needs a complete, non-literal, single-GPU model (q/k/v/o, up/down, lm_head; rope per head or off)");
+    const int B = batch, V = m.cfg.vocab, H = m.cfg.hidden;
+    for (int i = 0; i < B * n_prompt; ++i)
+        if (prompts[i] < 0 || prompts[i] >= V) return fail("token id %d out of range", prompts[i]);
+    const int total = n_prompt + n_new - 1;
+    if (total > m.cfg.max_seq) return fail("KV cache overflow: sequence too long");  // :100-102
+    static bool attr = false;
+    if (!attr) {
+        CK(cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+        CK(cudaFuncSetAttribute(rmsnorm_digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr = true;
+    }
+    // everything that allocates or launches set-up kernels happens before the step graphs are captured
+    for (auto& ly : m.layers)
+        for (QWeight* w : {ly.qkv.get(), ly.o.get(), ly.gateup.get(), ly.down.get()}) TRY(ensure_kmajor(*w));
+    TRY(ensure_kmajor(*m.lm_head));
+    TRY(ensure_pf_scratch(m, B));
+    const int pages = (total + m.page_tokens - 1) / m.page_tokens;
+    if (!m.batch || m.batch->B != B || m.batch->pages_per_seq < pages) {
+        m.batch.reset(new BatchState());
+        BatchState& bs = *m.batch;
+        bs.B = B;
+        bs.pages_per_seq = pages;
+        bs.max_splits = std::max(1, std::min(m.max_splits, (2 * g_num_sms) / std::max(1, B * m.attn_heads)));
+        bs.k.resize(m.layers.size());
+        bs.v.resize(m.layers.size());
+        const size_t pool = (size_t)B * pages * m.page_tokens * H;
+        for (size_t l = 0; l < m.layers.size(); ++l) { TRY(bs.k[l].alloc(pool)); TRY(bs.v[l].alloc(pool)); }
+        std::vector<int> tab((size_t)B * pages);
+        for (int b = 0; b < B; ++b)
+            for (int p = 0; p < pages; ++p) tab[(size_t)b * pages + p] = b * pages + (pages - 1 - p);   // deliberately not the identity
+        TRY(bs.tables.alloc(tab.size()));
+        CK(cudaMemcpyAsync(bs.tables.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        TRY(bs.tokens.alloc(B));
+        TRY(bs.pos_step.alloc(2));
+        TRY(bs.part_o.alloc((size_t)B * m.attn_heads * bs.max_splits * m.attn_dim));
+        TRY(bs.part_ml.alloc((size_t)B * m.attn_heads * bs.max_splits * 2));
+        TRY(bs.logits.alloc((size_t)B * V));
+    }
+    BatchState& bs = *m.batch;
+    if (bs.out.n < (size_t)B * n_new) {
+        TRY(bs.out.alloc((size_t)B * n_new));
+        bs.drop_graphs();   // the graphs hold the old pointer
+    }
+    if (bs.cap_scratch != m.pf_planes.p || bs.cap_stride != n_new) {   // kernel parameters of the captured graphs
+        bs.drop_graphs();
+        bs.cap_scratch = m.pf_planes.p;
+        bs.cap_stride = n_new;
+    }
+    std::vector<int> cols((size_t)n_prompt * B);
+    for (int b = 0; b < B; ++b)
+        for (int p = 0; p < n_prompt; ++p) cols[(size_t)p * B + b] = prompts[(size_t)b * n_prompt + p];
+    if (bs.prompts.n < cols.size()) TRY(bs.prompts.alloc(cols.size()));
+    CK(cudaMemcpyAsync(bs.prompts.p, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemsetAsync(bs.pos_step.p, 0, 2 * sizeof(int), g_stream));   // reset(): every cache is empty again
+    auto run = [&](bool sample) -> int {
+        cudaGraphExec_t& ge = bs.graph[sample ? 1 : 0];
+        if (!ge) {
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = batch_step(m, bs, sample, n_new);
+            const cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
+            if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return fail("cudaStreamEndCapture: %s", cudaGetErrorString(e));
+            CK(cudaGraphInstantiate(&ge, graph, 0));
+            cudaGraphDestroy(graph);
+        }
+        CK(cudaGraphLaunch(ge, g_stream));
+        return 0;
+    };
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int p = 0; p < n_prompt; ++p) {
+        CK(cudaMemcpyAsync(bs.tokens.p, bs.prompts.p + (size_t)p * B, B * sizeof(int), cudaMemcpyDeviceToDevice, g_stream));
+        TRY(run(p == n_prompt - 1));
+    }
+    CK(cudaEventRecord(e0, g_stream));
+    for (int i = 1; i < n_new; ++i) TRY(run(true));
+    CK(cudaEventRecord(e1, g_stream));
+    CK(cudaMemcpyAsync(out_tokens, bs.out.p, (size_t)B * n_new * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    if (logits_last) CK(cudaMemcpyAsync(logits_last, bs.logits.p, (size_t)B * V * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (decode_ms) *decode_ms = ms;
     return 0;
 }
 

@@ -328,6 +328,10 @@ struct AttnArgs {
     float* part_o;           // [heads][max_splits][D]
     float* part_ml;          // [heads][max_splits][2]
     float* out;              // [heads*D]
+    // batched decode (stand-alone kernels only): blockIdx.z = sequence; element strides per sequence of q / out / the page
+    // table / the partial buffers (0 for a single sequence)
+    int zq, zout, ztable;
+    size_t zpart_o, zpart_ml;
 };
 
 __device__ __forceinline__ const float* kv_row(const float* pool, const int* table, int page_tokens, int H, int t) {

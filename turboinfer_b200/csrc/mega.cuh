@@ -362,8 +362,17 @@ __device__ __forceinline__ float attn_merge_head(const AttnArgs& a, int h, int n
 }
 
 // stand-alone launches (TensorEngine::attention_fast_incremental / multi_head_attention entry points, per-op engine)
-__global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnArgs a) {
+__device__ __forceinline__ AttnArgs attn_for_sequence(AttnArgs a, int z) {
+    a.q += (size_t)z * a.zq;
+    a.out += (size_t)z * a.zout;
+    a.page_table += (size_t)z * a.ztable;
+    a.part_o += z * a.zpart_o;
+    a.part_ml += z * a.zpart_ml;
+    return a;
+}
+__global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnArgs a0) {
     extern __shared__ float attn_dyn_smem[];
+    const AttnArgs a = attn_for_sequence(a0, blockIdx.z);
     const int t = *a.pos_ptr + a.t_bias;
     int nsplit, chunk;
     attn_split_range(t, a.max_splits, a.min_chunk, nsplit, chunk);
@@ -372,7 +381,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnAr
     if (a.D <= 128) (void)attn_item_fast<kAttnThreads>(a, blockIdx.x, j, j * chunk, min(t, (j + 1) * chunk), attn_dyn_smem, nsplit == 1);
     else (void)attn_item<kAttnThreads>(a, blockIdx.x, j, j * chunk, min(t, (j + 1) * chunk), attn_dyn_smem, nsplit == 1);
 }
-__global__ void __launch_bounds__(kAttnThreads) attn_combine_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(kAttnThreads) attn_combine_kernel(const AttnArgs a0) {
+    const AttnArgs a = attn_for_sequence(a0, blockIdx.z);
     const int t = *a.pos_ptr + a.t_bias;
     int nsplit, chunk;
     attn_split_range(t, a.max_splits, a.min_chunk, nsplit, chunk);
