@@ -277,7 +277,7 @@ def main():
         out = {
             "metric": "decode_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak",
-            "vs_baseline": None, "dtype": "int32 accumulate (dp4a) of " + qname + " weights x 24-bit fixed-point activations, f32 elsewhere",
+            "vs_baseline": None, "dtype": "int32 accumulate (IMMA.16832 warp MMAs) of " + qname + " weights x 24-bit fixed-point activations, f32 elsewhere",
             "data": "synthetic", "config": config,
             "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 4 * n_prompt, "d2h_bytes_per_step": 4 * n_new},
             "gpu_launches": launches,

@@ -231,6 +231,13 @@ static void test_engine_gpu() {
         CHECK_THROWS(eng.generate(std::vector<int>(65, 1), 4), std::runtime_error);
         model::GenerationResult longrun = eng.generate(prompt, 1000);      // stops at max_sequence_length (or EOS)
         CHECK(longrun.tokens.size() <= 64 && longrun.finished);
+        {   // greedy batches of equal-length prompts advance in lockstep on the device: same tokens as one by one
+            std::vector<std::vector<int>> prompts = {prompt, prompt, prompt};
+            for (size_t b = 0; b < prompts.size(); ++b) for (int& t : prompts[b]) t = (t + 7 * (int)b) % 96;
+            auto lock = eng.generate_batch(prompts, 5);
+            CHECK(lock.size() == 3);
+            for (size_t b = 0; b < prompts.size(); ++b) CHECK(lock[b].tokens == eng.generate(prompts[b], 5).tokens);
+        }
         cfg.top_k = 5;
         cfg.temperature = 0.8f;
         eng.set_config(cfg);

@@ -537,8 +537,47 @@ std::vector<GenerationResult> InferenceEngine::generate_batch(const std::vector<
                                                               bool include_logprobs) {
     if (batch.empty()) throw std::runtime_error("Batch size cannot be zero");
     if (batch.size() > config_.max_batch_size) throw std::runtime_error("Batch size exceeds maximum allowed batch size");
-    std::vector<GenerationResult> out;   // the reference runs the sequences one after the other too (:804-828)
-    for (const auto& tokens : batch) out.push_back(generate(tokens, max_new_tokens, include_logprobs));
+    std::vector<GenerationResult> out;
+    // Greedy, equal-length prompts, no log-probabilities: the sequences advance in lockstep on the device, the weights
+    // are read once per step for the whole batch (ti_b200_generate_batch_greedy).  Tokens after a sequence's first EOS
+    // are dropped here, which is where the reference's per-sequence loop would have stopped (:760).
+    bool lockstep = config_.top_k == 1 && !include_logprobs && batch.size() > 1 && max_new_tokens > 0;
+    for (const auto& tokens : batch) {
+        validate_input_tokens(tokens);
+        lockstep = lockstep && tokens.size() == batch[0].size();
+    }
+    lockstep = lockstep && batch[0].size() + max_new_tokens - 1 <= config_.max_sequence_length;
+    if (lockstep) {
+        const auto t0 = std::chrono::high_resolution_clock::now();
+        const size_t B = batch.size(), P = batch[0].size();
+        std::vector<int32_t> prompts(B * P), toks(B * max_new_tokens);
+        for (size_t b = 0; b < B; ++b) std::copy(batch[b].begin(), batch[b].end(), prompts.begin() + b * P);
+        const int rc = ti_b200_generate_batch_greedy(handle_, prompts.data(), (int32_t)B, (int32_t)P, (int32_t)max_new_tokens, toks.data(), nullptr, nullptr);
+        if (rc == 0) {
+            const auto t1 = std::chrono::high_resolution_clock::now();
+            const float ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
+            for (size_t b = 0; b < B; ++b) {
+                GenerationResult r;
+                r.tokens = batch[b];
+                for (size_t i = 0; i < max_new_tokens; ++i) {
+                    r.tokens.push_back(toks[b * max_new_tokens + i]);
+                    if (toks[b * max_new_tokens + i] == 2) { r.finished = true; r.stop_reason = "eos_token"; break; }
+                }
+                if (!r.finished && r.tokens.size() >= config_.max_sequence_length) { r.finished = true; r.stop_reason = "max_length"; }
+                if (!r.finished) r.stop_reason = "max_new_tokens";
+                r.total_time_ms = ms;
+                const size_t generated = r.tokens.size() - P;
+                r.tokens_per_second = ms > 0.f ? generated / (ms / 1000.0f) : 0.f;
+                stats_->generations++;
+                stats_->tokens += generated;
+                out.push_back(std::move(r));
+            }
+            stats_->time_ms += ms;
+            return out;
+        }
+        // models the lockstep path does not cover (missing projections, literal mode, tensor parallel): one by one
+    }
+    for (const auto& tokens : batch) out.push_back(generate(tokens, max_new_tokens, include_logprobs));   // :804-828
     return out;
 }
 
