@@ -36,6 +36,89 @@ __global__ void rope_kv_batch_kernel(float* qkv, int H, int rope_dim, const floa
     }
 }
 
+// rmsnorm_digits_kernel for the batched decode: one block of 1024 threads per row, the row stays in registers between the
+// passes (K <= 16384), the digit planes are written four bytes at a time.  gu != nullptr: the row is not read from x but
+// computed on the fly as up * silu(gate) from the interleaved (gate_i, up_i) columns of gu[M][2K] (SwiGLU fused in front
+// of the down projection, :918, :1729).  Same expressions as rmsnorm_digits_kernel (prefill.cuh).
+constexpr int kDigitsThreads = 1024, kDigitsVecs = 4;   // 4 float4 per thread
+__global__ void __launch_bounds__(kDigitsThreads) rmsnorm_digits_small_kernel(const float* x, const float* gu, const float* w, float eps, int K,
+                                                                               int m_pad, int k_pad, int8_t* planes, float* sx_out, long long* sxf_out) {
+    __shared__ float red[32];
+    __shared__ long long redl[32];
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float4 v[kDigitsVecs];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kDigitsVecs; ++i) {
+        const int k = 4 * (tid + i * kDigitsThreads);
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K) {
+            if (gu) {
+                const float4 a = *reinterpret_cast<const float4*>(gu + (size_t)row * 2 * K + 2 * k);
+                const float4 b = *reinterpret_cast<const float4*>(gu + (size_t)row * 2 * K + 2 * k + 4);
+                v[i] = make_float4(a.y * (a.x / (1.0f + expf(-a.x))), a.w * (a.z / (1.0f + expf(-a.z))), b.y * (b.x / (1.0f + expf(-b.x))),
+                                   b.w * (b.z / (1.0f + expf(-b.z))));
+            } else {
+                v[i] = *reinterpret_cast<const float4*>(x + (size_t)row * K + k);
+            }
+        }
+        ss = fmaf(v[i].x, v[i].x, ss); ss = fmaf(v[i].y, v[i].y, ss); ss = fmaf(v[i].z, v[i].z, ss); ss = fmaf(v[i].w, v[i].w, ss);
+    }
+    float amax = 0.f;
+    if (w) {
+        ss = warp_sum(ss);
+        if (lane == 0) red[wid] = ss;
+        __syncthreads();
+        float tot = 0.f;
+        for (int i = 0; i < kDigitsThreads / 32; ++i) tot += red[i];
+        __syncthreads();
+        const float rms = sqrtf(tot / (float)K + eps);   // :1501
+#pragma unroll
+        for (int i = 0; i < kDigitsVecs; ++i) {
+            const int k = 4 * (tid + i * kDigitsThreads);
+            if (k < K) {
+                const float4 ww = *reinterpret_cast<const float4*>(w + k);
+                v[i] = make_float4((v[i].x / rms) * ww.x, (v[i].y / rms) * ww.y, (v[i].z / rms) * ww.z, (v[i].w / rms) * ww.w);   // :1504-1506
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kDigitsVecs; ++i) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+    amax = warp_max(amax);
+    if (lane == 0) red[wid] = amax;
+    __syncthreads();
+    amax = 0.f;
+    for (int i = 0; i < kDigitsThreads / 32; ++i) amax = fmaxf(amax, red[i]);
+    const bool finite = amax > 0.f && amax < INFINITY;
+    const float inv_s = finite ? kXQMax / amax : 0.f;
+    const float s_x = finite ? amax / kXQMax : 0.f;
+    long long sxf = 0;
+#pragma unroll
+    for (int i = 0; i < kDigitsVecs; ++i) {
+        const int k = 4 * (tid + i * kDigitsThreads);
+        if (k < k_pad) {   // columns K .. k_pad - 1 are zero
+            const int f0 = __float2int_rn(v[i].x * inv_s), f1 = __float2int_rn(v[i].y * inv_s), f2 = __float2int_rn(v[i].z * inv_s),
+                      f3 = __float2int_rn(v[i].w * inv_s);
+            sxf += (long long)((f0 + f1) + (f2 + f3));
+            const uint32_t lo01 = __byte_perm(f0, f1, 0x5140), lo23 = __byte_perm(f2, f3, 0x5140);
+            const uint32_t hi01 = __byte_perm(f0, f1, 0x0062), hi23 = __byte_perm(f2, f3, 0x0062);
+            *reinterpret_cast<uint32_t*>(planes + ((size_t)0 * m_pad + row) * k_pad + k) = __byte_perm(lo01, lo23, 0x5410);
+            *reinterpret_cast<uint32_t*>(planes + ((size_t)1 * m_pad + row) * k_pad + k) = __byte_perm(lo01, lo23, 0x7632);
+            *reinterpret_cast<uint32_t*>(planes + ((size_t)2 * m_pad + row) * k_pad + k) = __byte_perm(hi01, hi23, 0x5410);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sxf += __shfl_xor_sync(0xffffffffu, sxf, o);
+    if (lane == 0) redl[wid] = sxf;
+    __syncthreads();
+    if (tid == 0) {
+        long long t = 0;
+        for (int i = 0; i < kDigitsThreads / 32; ++i) t += redl[i];
+        sx_out[row] = s_x;
+        sxf_out[row] = t;
+    }
+}
+
 // One block per row: the FIRST maximum of logits[b][0..V) (std::sort descending + [0] of the reference keeps the first of
 // equal values only by accident of its sort; the oracle and every engine here define greedy as "first maximum").
 // tokens[b] feeds the next step's embedding lookup; out[b * out_stride + *step_ptr] is the history the host reads.

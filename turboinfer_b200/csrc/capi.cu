@@ -313,6 +313,8 @@ struct Model {
     DevBuf<float> pf_x, pf_qkv, pf_attn, pf_gu, pf_act, pf_sx;
     DevBuf<int8_t> pf_planes;
     DevBuf<long long> pf_sxf;
+    DevBuf<unsigned long long> pf_ws;   // split-K workspace of the 32-row GEMM: [n_pad][32] integer partial sums, zero between GEMMs
+    DevBuf<unsigned int> pf_cnt;        // ... and its per-tile arrival counters
     DevBuf<int> pf_tokens;
     std::unique_ptr<struct BatchState> batch;   // batched decode (generate_batch): per-sequence KV pages, step graphs
     int tp = 1, tp_rank = 0;   // tensor-parallel degree / rank of this model
@@ -798,7 +800,7 @@ int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
 // ---- tensor-core GEMM (prefill / batched decode) ---------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int make_tmap_u8_2d(CUtensorMap* map, void* base, uint64_t cols, uint64_t rows) {
+int make_tmap_u8_2d(CUtensorMap* map, void* base, uint64_t cols, uint64_t rows, int box_rows = kGemmBM) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -809,7 +811,7 @@ int make_tmap_u8_2d(CUtensorMap* map, void* base, uint64_t cols, uint64_t rows) 
     }
     const cuuint64_t dims[2] = {cols, rows};
     const cuuint64_t strides[1] = {cols};          // bytes between rows
-    const cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)kGemmBM};
+    const cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -881,12 +883,37 @@ int gemm_q_dev(QWeight& w, const float* x_dev, float* y_dev, int M, float* kerne
 
 // ---- batched prefill on the tensor cores --------------------------------------------------------------------------
 // One GEMM of the prefill path: activations are already digit planes; no host synchronisation.
+// split factor of the 32-row GEMM: (N / 128) * S CTAs should fill the SMs in whole waves, with >= 6 k-steps per CTA
+int small_gemm_splits(int tiles, int ksteps) {
+    if (tiles * 10 >= g_num_sms * 6) return 1;   // >= 0.6 CTAs per SM already (two fit): splitting only adds atomics
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= 8 && ksteps / s >= 6; ++s) {
+        const double waves = (double)tiles * s / (2 * g_num_sms);   // two CTAs per SM
+        const double eff = waves / std::ceil(waves);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    }
+    return best;
+}
+int launch_small_gemm(Model& m, QWeight& w, int m_pad, const GemmArgs& g) {
+    static bool attr = false;
+    if (!attr) {
+        CK(cudaFuncSetAttribute(gemm_i8_tc_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmemBytes));
+        attr = true;
+    }
+    const int tiles = (w.L.N + kGemmBN - 1) / kGemmBN;
+    if (m.pf_ws.n < (size_t)w.n_pad * kSmallRows || m.pf_cnt.n < (size_t)tiles) return fail("internal: split-K workspace too small");
+    CUtensorMap map_a, map_b;
+    TRY(make_tmap_u8_2d(&map_a, m.pf_planes.p, (uint64_t)w.k_pad, (uint64_t)3 * m_pad, kSmallRows));
+    TRY(make_tmap_u8_2d(&map_b, w.kmajor.p, (uint64_t)w.k_pad, (uint64_t)w.n_pad));
+    SplitKArgs sk{m.pf_ws.p, m.pf_cnt.p, w.n_pad};
+    const int S = small_gemm_splits(tiles, w.k_pad / kGemmBK);
+    gemm_i8_tc_small_kernel<<<dim3(tiles, S), kSmallThreads, kSmallSmemBytes, g_stream>>>(map_a, map_b, g, sk);
+    return 0;
+}
 int pf_gemm(Model& m, QWeight& w, int M, int m_pad, float* y, const float* resid) {
     TRY(ensure_kmajor(w));
     if (w.k_pad != (layout_kpad(w.L) + kGemmBK - 1) / kGemmBK * kGemmBK) return fail("internal: k_pad mismatch");
-    CUtensorMap map_a, map_b;
-    TRY(make_tmap_u8_2d(&map_a, m.pf_planes.p, (uint64_t)w.k_pad, (uint64_t)3 * m_pad));
-    TRY(make_tmap_u8_2d(&map_b, w.kmajor.p, (uint64_t)w.k_pad, (uint64_t)w.n_pad));
     GemmArgs g{};
     g.M = M; g.N = w.L.N; g.K = w.L.K;
     g.m_pad = m_pad; g.k_pad = w.k_pad;
@@ -897,6 +924,15 @@ int pf_gemm(Model& m, QWeight& w, int M, int m_pad, float* y, const float* resid
     g.colzterm = w.has_zterm ? w.colzterm.p : nullptr;
     g.y = y;
     g.resid = resid;
+    if (M <= kSmallRows && !getenv("TURBOINFER_B200_NO_SMALL_GEMM")) {   // batched decode: 32-row tiles, every SM streams weights
+        TRY(launch_small_gemm(m, w, m_pad, g));
+        ++g_launches;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    CUtensorMap map_a, map_b;
+    TRY(make_tmap_u8_2d(&map_a, m.pf_planes.p, (uint64_t)w.k_pad, (uint64_t)3 * m_pad));
+    TRY(make_tmap_u8_2d(&map_b, w.kmajor.p, (uint64_t)w.k_pad, (uint64_t)w.n_pad));
     const dim3 grid((w.L.N + kGemmBN - 1) / kGemmBN, m_pad / kGemmBM);
     gemm_i8_tc_kernel<<<grid, kGemmThreads, kGemmSmemBytes, g_stream>>>(map_a, map_b, g);
     ++g_launches;
@@ -906,8 +942,9 @@ int pf_gemm(Model& m, QWeight& w, int M, int m_pad, float* y, const float* resid
 int pf_digits(Model& m, const float* x, const float* norm_w, int M, int K, int m_pad, int k_pad) {
     // planes of rows >= M and columns >= K stay zero: the buffer is cleared when it is (re)allocated and only rows < M,
     // columns < k_pad are written -- k_pad differs per weight, so clear the tail columns explicitly
-    CK(cudaMemsetAsync(m.pf_planes.p, 0, (size_t)3 * m_pad * k_pad, g_stream));
-    rmsnorm_digits_kernel<<<M, 256, (size_t)K * sizeof(float), g_stream>>>(x, norm_w, m.cfg.rms_eps, M, K, m_pad, k_pad, m.pf_planes.p, m.pf_sx.p, m.pf_sxf.p);
+    // (the 32-row GEMM of the batched decode never reads rows it does not also ignore: nothing to clear there)
+    if (M > kSmallRows) CK(cudaMemsetAsync(m.pf_planes.p, 0, (size_t)3 * m_pad * k_pad, g_stream));
+    rmsnorm_digits_kernel<<<M, M > kSmallRows ? 256 : 1024, (size_t)K * sizeof(float), g_stream>>>(x, norm_w, m.cfg.rms_eps, M, K, m_pad, k_pad, m.pf_planes.p, m.pf_sx.p, m.pf_sxf.p);
     ++g_launches;
     CK(cudaGetLastError());
     return 0;
@@ -922,6 +959,7 @@ bool prefill_gemm_eligible(const Model& m, int M) {
 
 // forward_pass over prompt[0 .. M): fills the KV cache for positions pos0 .. pos0 + M - 1 (pos0 = 0 after reset()).
 // The hidden states stay in pf_x; the caller runs the last prompt token through the decode engine for the logits.
+int ensure_pf_scratch(Model& m, int M);
 int prefill_gemm(Model& m, const int* prompt_dev, int M) {
     static bool attr = false;
     if (!attr) {
@@ -931,20 +969,7 @@ int prefill_gemm(Model& m, const int* prompt_dev, int M) {
     }
     const int H = m.cfg.hidden, I = std::max(m.cfg.inter, 1);
     const int m_pad = (M + kGemmBM - 1) / kGemmBM * kGemmBM;
-    int kmax = 0;
-    for (auto& ly : m.layers)
-        for (QWeight* w : {ly.qkv.get(), ly.o.get(), ly.gateup.get(), ly.down.get()}) kmax = std::max(kmax, (layout_kpad(w->L) + kGemmBK - 1) / kGemmBK * kGemmBK);
-    if (M > m.pf_cap) {
-        TRY(m.pf_x.alloc((size_t)M * H));
-        TRY(m.pf_qkv.alloc((size_t)M * 3 * H));
-        TRY(m.pf_attn.alloc((size_t)M * H));
-        TRY(m.pf_gu.alloc((size_t)M * 2 * I));
-        TRY(m.pf_act.alloc((size_t)M * I));
-        TRY(m.pf_sx.alloc(M));
-        TRY(m.pf_sxf.alloc(M));
-        TRY(m.pf_planes.alloc((size_t)3 * m_pad * kmax));
-        m.pf_cap = M;
-    }
+    TRY(ensure_pf_scratch(m, M));
     const int pos0 = 0;
     const int rope_dim = m.cfg.rope_mode == 1 ? H / m.cfg.heads : 0;
     embed_rows_kernel<<<M, 256, 0, g_stream>>>(m.tok_emb.p, prompt_dev, m.pf_x.p, H);
@@ -994,6 +1019,17 @@ int ensure_pf_scratch(Model& m, int M) {
         TRY(m.pf_planes.alloc((size_t)3 * m_pad * kmax));
         m.pf_cap = M;
     }
+    size_t nmax = 0;
+    auto updn = [&](QWeight* w) { if (w) nmax = std::max(nmax, (size_t)(4 * w->L.U + kGemmBN - 1) / kGemmBN * kGemmBN); };
+    for (auto& ly : m.layers)
+        for (QWeight* w : {ly.qkv.get(), ly.o.get(), ly.gateup.get(), ly.down.get()}) updn(w);
+    updn(m.lm_head.get());
+    if (m.pf_ws.n < nmax * kSmallRows) {
+        TRY(m.pf_ws.alloc(nmax * kSmallRows));
+        TRY(m.pf_cnt.alloc(nmax / kGemmBN));
+        CK(cudaMemsetAsync(m.pf_ws.p, 0, nmax * kSmallRows * sizeof(unsigned long long), g_stream));
+        CK(cudaMemsetAsync(m.pf_cnt.p, 0, nmax / kGemmBN * sizeof(unsigned int), g_stream));
+    }
     return 0;
 }
 
@@ -1001,6 +1037,23 @@ bool batch_eligible(const Model& m) {
     if (m.tp != 1 || m.cfg.compat_literal || m.cfg.rope_mode == 2 || !m.lm_head) return false;
     for (auto& ly : m.layers) if (!(ly.qkv && ly.o && ly.gateup && ly.down)) return false;
     return true;
+}
+
+// digit planes for the batched decode step (M <= 32 rows read by the GEMM): gu != nullptr fuses SwiGLU in front
+int batch_digits(Model& m, const float* x, const float* gu, const float* norm_w, int B, int K, int m_pad, int k_pad) {
+    const bool small = K % 4 == 0 && k_pad <= 4 * kDigitsThreads * kDigitsVecs;
+    if (small && B <= kSmallRows) {
+        rmsnorm_digits_small_kernel<<<B, kDigitsThreads, 0, g_stream>>>(x, gu, norm_w, m.cfg.rms_eps, K, m_pad, k_pad, m.pf_planes.p, m.pf_sx.p, m.pf_sxf.p);
+        ++g_launches;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    if (gu) {
+        swiglu_rows_kernel<<<grid_for((size_t)B * K), 256, 0, g_stream>>>(gu, m.pf_act.p, (size_t)B, (size_t)K);
+        ++g_launches;
+        x = m.pf_act.p;
+    }
+    return pf_digits(m, x, norm_w, B, K, m_pad, k_pad);
 }
 
 // one lockstep step of all B sequences: tokens[b] -> KV append at *pos -> (sample: logits, argmax -> tokens[b], out)
@@ -1012,7 +1065,7 @@ int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
     ++g_launches;
     for (size_t l = 0; l < m.layers.size(); ++l) {
         Layer& ly = m.layers[l];
-        TRY(pf_digits(m, m.pf_x.p, ly.attn_norm.p, B, H, m_pad, ly.qkv->k_pad));
+        TRY(batch_digits(m, m.pf_x.p, nullptr, ly.attn_norm.p, B, H, m_pad, ly.qkv->k_pad));
         TRY(pf_gemm(m, *ly.qkv, B, m_pad, m.pf_qkv.p, nullptr));
         rope_kv_batch_kernel<<<B, 256, 0, g_stream>>>(m.pf_qkv.p, H, rope_dim, m.inv_freq.p, bs.pos_step.p, bs.k[l].p, bs.v[l].p, bs.tables.p,
                                                        bs.pages_per_seq, m.page_tokens);
@@ -1041,18 +1094,21 @@ int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
         attn_partial_kernel<<<dim3(m.attn_heads, bs.max_splits, B), kAttnThreads, m.attn_smem, g_stream>>>(a);
         attn_combine_kernel<<<dim3(m.attn_heads, 1, B), 256, 0, g_stream>>>(a);
         g_launches += 3;
-        TRY(pf_digits(m, m.pf_attn.p, nullptr, B, H, m_pad, ly.o->k_pad));
+        TRY(batch_digits(m, m.pf_attn.p, nullptr, nullptr, B, H, m_pad, ly.o->k_pad));
         TRY(pf_gemm(m, *ly.o, B, m_pad, m.pf_x.p, m.pf_x.p));
-        TRY(pf_digits(m, m.pf_x.p, ly.ffn_norm.p, B, H, m_pad, ly.gateup->k_pad));
+        TRY(batch_digits(m, m.pf_x.p, nullptr, ly.ffn_norm.p, B, H, m_pad, ly.gateup->k_pad));
         TRY(pf_gemm(m, *ly.gateup, B, m_pad, m.pf_gu.p, nullptr));
-        if (ly.has_gate) swiglu_rows_kernel<<<grid_for((size_t)B * I), 256, 0, g_stream>>>(m.pf_gu.p, m.pf_act.p, (size_t)B, (size_t)I);
-        else relu_rows_kernel<<<grid_for((size_t)B * I), 256, 0, g_stream>>>(m.pf_gu.p, m.pf_act.p, (size_t)B * I);
-        ++g_launches;
-        TRY(pf_digits(m, m.pf_act.p, nullptr, B, I, m_pad, ly.down->k_pad));
+        if (ly.has_gate) {
+            TRY(batch_digits(m, nullptr, m.pf_gu.p, nullptr, B, I, m_pad, ly.down->k_pad));   // SwiGLU fused into the conversion
+        } else {
+            relu_rows_kernel<<<grid_for((size_t)B * I), 256, 0, g_stream>>>(m.pf_gu.p, m.pf_act.p, (size_t)B * I);
+            ++g_launches;
+            TRY(batch_digits(m, m.pf_act.p, nullptr, nullptr, B, I, m_pad, ly.down->k_pad));
+        }
         TRY(pf_gemm(m, *ly.down, B, m_pad, m.pf_x.p, m.pf_x.p));
     }
     if (sample) {
-        TRY(pf_digits(m, m.pf_x.p, m.out_norm.p, B, H, m_pad, m.lm_head->k_pad));
+        TRY(batch_digits(m, m.pf_x.p, nullptr, m.out_norm.p, B, H, m_pad, m.lm_head->k_pad));
         TRY(pf_gemm(m, *m.lm_head, B, m_pad, bs.logits.p, nullptr));
         argmax_rows_kernel<<<B, 256, 0, g_stream>>>(bs.logits.p, V, bs.tokens.p, bs.out.p, out_stride, bs.pos_step.p + 1);
         ++g_launches;

@@ -124,11 +124,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
     return d;
 }
-__host__ __device__ constexpr uint32_t umma_idesc_i8(int a_signed, int b_signed) {
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int a_signed, int b_signed, int bn = kGemmBN) {
     return (2u << 4)                        // D format S32
            | ((uint32_t)a_signed << 7)      // A: 0 unsigned / 1 signed 8-bit
            | ((uint32_t)b_signed << 10)     // B
-           | ((uint32_t)(kGemmBN >> 3) << 17) | ((uint32_t)(kGemmBM >> 4) << 24);   // K-major A and B (bits 15, 16 = 0)
+           | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kGemmBM >> 4) << 24);   // K-major A and B (bits 15, 16 = 0)
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -235,6 +235,179 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+
+// ---- the same GEMM for M <= 32 rows (batched decode), operands swapped ---------------------------------------------
+// With a handful of rows the kernel above would spend 128-row MMAs and 48 KiB of (mostly zero) activation tiles on 32 live
+// rows.  Here the roles are swapped: the MMA's M side (128 rows) are 128 WEIGHT COLUMNS, its N side (32) are the batch
+// rows, D[128 x 32] per digit plane (96 TMEM columns):
+//   * per k-step a CTA loads 16 KiB of weights and the 32 live rows of each digit plane (3 x 4 KiB -- the same bytes for
+//     every CTA, an L2 broadcast);
+//   * the tensor work is 4x smaller than with padded rows, and the epilogue has all four warps busy with coalesced stores
+//     (lane = weight column);
+//   * split-K: grid (N / 128, S); CTA (n, s) multiplies k-steps [s KB / S, (s + 1) KB / S).  The partial sums are exact
+//     integers, so they are combined with 64-bit integer atomics in a workspace (order-independent: bit-identical to
+//     S = 1); the CTA that arrives last on the tile's counter applies offset, scales and residual, stores the tile and
+//     leaves workspace and counter zeroed for the next GEMM.  S is chosen on the host for GEMMs with few column tiles.
+// warps 0..3: epilogue (TMEM lanes 32w.. = weight columns), warp 4: TMEM allocation + MMA issue, warp 5: TMA producer.
+constexpr int kSmallRows = 32, kSmallThreads = 192, kSmallStages = 3;   // 3 stages = 84 KiB: two CTAs per SM
+constexpr int kSmallPlaneBytes = kSmallRows * kGemmBK;                       // 4 KiB
+constexpr int kSmallStageBytes = kGemmTileBytes + 3 * kSmallPlaneBytes;      // weights 16 KiB + digits 12 KiB
+constexpr int kSmallTmemCols = 128;                                          // >= 3 x 32, power of two
+constexpr size_t kSmallSmemBytes = (size_t)kSmallStages * kSmallStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * kSmallRows * 8;
+
+struct SplitKArgs {
+    unsigned long long* ws;   // [32][n_pad] partial integer sums
+    unsigned int* cnt;        // [N / 128] arrivals per tile
+    int n_pad;
+};
+
+__host__ __device__ constexpr uint32_t umma_idesc_i8_mn(int a_signed, int b_signed, int m, int n) {
+    return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kSmallThreads, 2)
+gemm_i8_tc_small_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const GemmArgs g, const SplitKArgs sk) {
+    extern __shared__ uint8_t gsm_raw[];
+    const uint32_t base = (smem_u32(gsm_raw) + 1023u) & ~1023u;
+    uint8_t* tiles = gsm_raw + (base - smem_u32(gsm_raw));
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)kSmallStages * kSmallStageBytes);
+    uint64_t* empty = full + kSmallStages;
+    uint64_t* tmem_full = empty + kSmallStages;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    int* flag = reinterpret_cast<int*>(tmem_ptr + 1);
+    float* s_sx = reinterpret_cast<float*>(tiles + (size_t)kSmallStages * kSmallStageBytes + 256);
+    long long* s_off = reinterpret_cast<long long*>(s_sx + kSmallRows);   // woff * sum(xf) per row; sum(xf) itself after it
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nb = blockIdx.x, S = gridDim.y;
+    const int KB = g.k_pad / kGemmBK;
+    const int kb0 = (int)((long long)blockIdx.y * KB / S), kb1 = (int)((long long)(blockIdx.y + 1) * KB / S);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kSmallStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (threadIdx.x < kSmallRows) {
+        const bool ok = (int)threadIdx.x < g.M;
+        s_sx[threadIdx.x] = ok ? g.sx[threadIdx.x] : 0.f;
+        s_off[threadIdx.x] = ok ? g.sxf[threadIdx.x] : 0;
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(kSmallTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+
+    if (warp == 5) {
+        if (lane == 0) {
+            int st = 0, par = 1;   // a fresh mbarrier counts its "previous" phase as complete
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty[st], par);
+                mbar_arrive_expect_tx(&full[st], kSmallStageBytes);
+                uint8_t* sbase = tiles + (size_t)st * kSmallStageBytes;
+                tma_load_2d(sbase, &map_w, kb * kGemmBK, nb * kGemmBN, &full[st]);
+                for (int d = 0; d < 3; ++d) tma_load_2d(sbase + kGemmTileBytes + d * kSmallPlaneBytes, &map_x, kb * kGemmBK, d * g.m_pad, &full[st]);
+                if (++st == kSmallStages) { st = 0; par ^= 1; }
+            }
+        }
+    } else if (warp == 4) {
+        if (lane == 0) {
+            // A = weights (unsigned nibbles-in-bytes for INT4, signed for INT8), B = digit plane (0, 1 unsigned; 2 signed)
+            const uint32_t id_u = umma_idesc_i8_mn(g.a_signed_b, 0, kGemmBN, kSmallRows), id_s = umma_idesc_i8_mn(g.a_signed_b, 1, kGemmBN, kSmallRows);
+            int st = 0, par = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full[st], par);
+                tc_fence_after();
+                const uint32_t sbase = base + st * kSmallStageBytes;
+#pragma unroll
+                for (int k4 = 0; k4 < kGemmBK / 32; ++k4) {
+                    const uint64_t wdesc = umma_desc_sw128(sbase + k4 * 32);
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const uint64_t xdesc = umma_desc_sw128(sbase + kGemmTileBytes + d * kSmallPlaneBytes + k4 * 32);
+                        tc_mma_i8(tmem + d * kSmallRows, wdesc, xdesc, d == 2 ? id_s : id_u, (kb != kb0 || k4 != 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(&empty[st]);
+                if (++st == kSmallStages) { st = 0; par ^= 1; }
+            }
+            tc_commit(tmem_full);
+        }
+    } else {
+        // epilogue, warps 0..3: TMEM lane = weight column of the tile, TMEM column = batch row (per digit plane)
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int n = nb * kGemmBN + warp * 32 + lane;
+        const bool n_ok = n < g.N;
+        const float cs = n_ok ? g.colscale[n] : 0.f;
+        const float zt = (n_ok && g.colzterm) ? g.colzterm[n] : 0.f;
+        auto finish = [&](int m, long long t) {   // t = sum over all k of u * xf for (row m, column n)
+            const long long sxf = s_off[m];
+            t -= (long long)g.woff * sxf;
+            const int hi = (int)(t >> 23), lo = (int)(t & 0x7FFFFF);
+            const float tf = fmaf((float)hi, 8388608.0f, (float)lo);
+            float yv = (fmaf(zt, (float)sxf, tf) * s_sx[m]) * cs;   // the GEMV epilogue's expression
+            if (g.resid) yv = g.resid[(size_t)m * g.N + n] + yv;
+            g.y[(size_t)m * g.N + n] = yv;
+        };
+        for (int m0 = 0; m0 < kSmallRows; m0 += 16) {
+            uint32_t a[3][16];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(d * kSmallRows + m0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(a[d][0]), "=r"(a[d][1]), "=r"(a[d][2]), "=r"(a[d][3]), "=r"(a[d][4]), "=r"(a[d][5]), "=r"(a[d][6]), "=r"(a[d][7]),
+                      "=r"(a[d][8]), "=r"(a[d][9]), "=r"(a[d][10]), "=r"(a[d][11]), "=r"(a[d][12]), "=r"(a[d][13]), "=r"(a[d][14]), "=r"(a[d][15])
+                    : "r"(taddr));
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int m = m0 + i;
+                const long long t = ((long long)(int)a[2][i] << 16) + ((long long)(int)a[1][i] << 8) + (long long)(int)a[0][i];
+                if (m < g.M && n_ok) {
+                    if (S == 1) finish(m, t);
+                    else atomicAdd(sk.ws + (size_t)m * sk.n_pad + n, (unsigned long long)t);
+                }
+            }
+        }
+        if (S > 1) {
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 0) {
+                const unsigned int prev = atomicAdd(sk.cnt + nb, 1u);
+                *flag = prev == (unsigned int)(S - 1) ? 1 : 0;
+                if (*flag) sk.cnt[nb] = 0u;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (*flag) {   // every split of this tile has added its partial sums
+                __threadfence();
+                for (int m0 = 0; m0 < g.M; m0 += 16) {   // 16 loads in flight, then their 16 rows
+                    unsigned long long v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = (m0 + i < g.M && n_ok) ? __ldcg(sk.ws + (size_t)(m0 + i) * sk.n_pad + n) : 0ull;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (m0 + i < g.M && n_ok) {
+                            finish(m0 + i, (long long)v[i]);
+                            sk.ws[(size_t)(m0 + i) * sk.n_pad + n] = 0ull;
+                        }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kSmallTmemCols) : "memory");
     }
 }
 
