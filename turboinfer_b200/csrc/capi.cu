@@ -40,6 +40,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 } g_nccl;
@@ -319,6 +320,12 @@ struct Model {
     std::unique_ptr<struct BatchState> batch;   // batched decode (generate_batch): per-sequence KV pages, step graphs
     int tp = 1, tp_rank = 0;   // tensor-parallel degree / rank of this model
     DevBuf<float> ar_tmp;      // [H] partial output of a row-parallel GEMV, all-reduced in place
+    // fused tensor-parallel engine: this rank's exchange block {barrier words, partial buffers 0 / 1 [tp][H]} and the
+    // CUDA IPC mappings of every rank's block (own rank: the block itself)
+    bool tp_fused = false;
+    void* xchg = nullptr;
+    void* peer_base[kMaxTp] = {};
+    size_t xchg_part_off = 0, xchg_part_bytes = 0;
     DevBuf<MegaPhase> phases;
     DevBuf<ProdRec> prod;
     int nphases = 0;
@@ -331,6 +338,9 @@ struct Model {
     size_t mega_smem = 0;
     int host_pos = 0;  // mirror of state.pos
     ~Model() {
+        for (int r = 0; r < kMaxTp; ++r)
+            if (peer_base[r] && peer_base[r] != xchg) cudaIpcCloseMemHandle(peer_base[r]);
+        if (xchg) cudaFree(xchg);
         if (graph_decode) cudaGraphExecDestroy(graph_decode);
         if (graph_prefill) cudaGraphExecDestroy(graph_prefill);
     }
@@ -634,6 +644,43 @@ int run_step(Model& m, bool with_head) {
     return 0;
 }
 
+// ---- fused tensor parallelism: peer memory over NVLink ---------------------------------------------------------
+// Every rank allocates one exchange block and maps the other ranks' blocks with CUDA IPC (the handles travel through an
+// NCCL all-gather, the only collective left on this path).  Inside the persistent kernel a row-parallel GEMV stores its
+// partial output straight into every rank's partial buffer and the ranks meet at a barrier of system-scope atomics; no
+// NCCL call, no extra launch per layer.
+int tp_exchange_setup(Model& m) {
+    const int H = m.cfg.hidden, P = m.tp;
+    if (P > kMaxTp) return fail("fused tensor parallelism supports up to %d ranks", kMaxTp);
+    const size_t bar_bytes = (size_t)kBarWords * kBarStride * sizeof(unsigned int) + 256;   // + the barrier sequence number
+    m.xchg_part_off = (bar_bytes + 255) & ~size_t(255);
+    m.xchg_part_bytes = ((size_t)P * H * sizeof(float) + 255) & ~size_t(255);
+    const size_t total = m.xchg_part_off + 2 * m.xchg_part_bytes;
+    CK(cudaMalloc(&m.xchg, total));
+    CK(cudaMemset(m.xchg, 0, total));
+    cudaIpcMemHandle_t mine;
+    CK(cudaIpcGetMemHandle(&mine, m.xchg));
+    DevBuf<uint8_t> hsend, hrecv;
+    TRY(hsend.alloc(sizeof(mine)));
+    TRY(hrecv.alloc(sizeof(mine) * P));
+    CK(cudaMemcpyAsync(hsend.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, g_stream));
+    const ncclResult_t r = g_nccl.AllGather(hsend.p, hrecv.p, sizeof(mine), ncclUint8, g_comm, g_stream);
+    if (r != ncclSuccess) return fail("ncclAllGather (IPC handles) failed: %s", g_nccl.GetErrorString(r));
+    std::vector<cudaIpcMemHandle_t> all(P);
+    CK(cudaMemcpyAsync(all.data(), hrecv.p, sizeof(mine) * P, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    for (int q = 0; q < P; ++q) {
+        if (q == m.tp_rank) { m.peer_base[q] = m.xchg; continue; }
+        const cudaError_t e = cudaIpcOpenMemHandle(&m.peer_base[q], all[q], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { m.peer_base[q] = nullptr; return fail("cudaIpcOpenMemHandle(rank %d) failed: %s", q, cudaGetErrorString(e)); }
+    }
+    // nobody may signal a block that its owner has not zeroed yet: one more collective as a barrier
+    const ncclResult_t r2 = g_nccl.AllGather(hsend.p, hrecv.p, sizeof(mine), ncclUint8, g_comm, g_stream);
+    if (r2 != ncclSuccess) return fail("ncclAllGather (barrier) failed: %s", g_nccl.GetErrorString(r2));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
 // ---- persistent-kernel engine ---------------------------------------------------------------------------
 int build_mega(Model& m) {
     const int H = m.cfg.hidden;
@@ -652,6 +699,25 @@ int build_mega(Model& m) {
         ph.push_back(p);
     };
     const int mega_splits = std::max(1, std::min(g_num_sms / m.attn_heads, m.max_splits));
+    const bool tp = m.tp > 1;
+    const int Hl = H / m.tp;   // this rank's share of the attention width (its heads)
+    float* part[2] = {nullptr, nullptr};
+    if (tp) {
+        part[0] = reinterpret_cast<float*>(static_cast<uint8_t*>(m.xchg) + m.xchg_part_off);
+        part[1] = reinterpret_cast<float*>(static_cast<uint8_t*>(m.xchg) + m.xchg_part_off + m.xchg_part_bytes);
+    }
+    // second half of the all-reduce after a row-parallel GEMV: x <- residual + the partials of all ranks
+    auto reduce_phase = [&](int sel, int resid_src, const float* next_norm_w) {
+        MegaPhase p{};
+        p.type = PH_REDUCE;
+        p.resid_src = resid_src;
+        p.g.x = part[sel];
+        p.g.resid = m.x.p;
+        p.g.out = m.x.p;
+        p.g.next_norm_w = next_norm_w;
+        p.g.L.N = H;
+        ph.push_back(p);
+    };
     for (size_t l = 0; l < m.layers.size(); ++l) {
         Layer& ly = m.layers[l];
         const int src0 = l == 0 ? SRC_EMB : SRC_PTR;
@@ -661,7 +727,7 @@ int build_mega(Model& m) {
         a.rms_eps = m.cfg.rms_eps;
         a.epi = EPI_QKV;
         a.out = m.q.p;
-        a.hidden = H;
+        a.hidden = Hl;
         a.rope_dim = m.cfg.rope_mode == 1 ? H / m.cfg.heads : (m.cfg.rope_mode == 2 ? H : 0);
         a.inv_freq = m.inv_freq.p;
         a.pos_ptr = &m.state.p->pos;
@@ -679,7 +745,7 @@ int build_mega(Model& m) {
         at.at.page_tokens = m.page_tokens;
         at.at.pos_ptr = &m.state.p->pos;
         at.at.t_bias = 1;
-        at.at.H = H;
+        at.at.H = Hl;
         at.at.D = m.attn_dim;
         at.at.heads = m.attn_heads;
         at.at.max_splits = mega_splits;
@@ -691,11 +757,20 @@ int build_mega(Model& m) {
         ph.push_back(at);
         GemvArgs o{};
         o.x = m.attn_out.p;
-        o.epi = EPI_RESIDUAL;
-        o.resid = m.x.p;
-        o.out = m.x.p;
-        o.next_norm_w = ly.ffn_norm.p;
-        gemv_phase(*ly.o, o, SRC_PTR, src0, 0);
+        if (tp) {   // row-parallel: partial output to every rank, barrier across the GPUs, then the reduce phase
+            o.epi = EPI_STORE;
+            o.out = part[0];
+            gemv_phase(*ly.o, o, SRC_PTR, SRC_PTR, 0);
+            ph.back().mgpu = 1;
+            ph.back().part_sel = 0;
+            reduce_phase(0, src0, ly.ffn_norm.p);
+        } else {
+            o.epi = EPI_RESIDUAL;
+            o.resid = m.x.p;
+            o.out = m.x.p;
+            o.next_norm_w = ly.ffn_norm.p;
+            gemv_phase(*ly.o, o, SRC_PTR, src0, 0);
+        }
         GemvArgs g{};
         g.x = m.x.p;
         g.norm_w = ly.ffn_norm.p;
@@ -705,11 +780,21 @@ int build_mega(Model& m) {
         gemv_phase(*ly.gateup, g, SRC_PTR, SRC_PTR, 0);
         GemvArgs d{};
         d.x = m.act.p;
-        d.epi = EPI_RESIDUAL;
-        d.resid = m.x.p;
-        d.out = m.x.p;
-        d.next_norm_w = l + 1 < m.layers.size() ? m.layers[l + 1].attn_norm.p : m.out_norm.p;
-        gemv_phase(*ly.down, d, SRC_PTR, SRC_PTR, 0);
+        const float* norm_after = l + 1 < m.layers.size() ? m.layers[l + 1].attn_norm.p : m.out_norm.p;
+        if (tp) {
+            d.epi = EPI_STORE;
+            d.out = part[1];
+            gemv_phase(*ly.down, d, SRC_PTR, SRC_PTR, 0);
+            ph.back().mgpu = 1;
+            ph.back().part_sel = 1;
+            reduce_phase(1, SRC_PTR, norm_after);
+        } else {
+            d.epi = EPI_RESIDUAL;
+            d.resid = m.x.p;
+            d.out = m.x.p;
+            d.next_norm_w = norm_after;
+            gemv_phase(*ly.down, d, SRC_PTR, SRC_PTR, 0);
+        }
     }
     GemvArgs lm{};
     lm.x = m.x.p;
@@ -790,6 +875,17 @@ int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
     a.dbg_nomath = (m.dbg_on && getenv("TURBOINFER_B200_DBG_NOMATH")) ? atoi(getenv("TURBOINFER_B200_DBG_NOMATH")) : 0;
     a.emb_stats = m.emb_stats.p;
     a.dbg_flags = getenv("TURBOINFER_B200_DBG_FLAGS") ? atoi(getenv("TURBOINFER_B200_DBG_FLAGS")) : 0;
+    a.tp = m.tp_fused ? m.tp : 1;
+    a.tp_rank = m.tp_rank;
+    if (m.tp_fused) {
+        for (int r = 0; r < m.tp; ++r) {
+            uint8_t* b = static_cast<uint8_t*>(m.peer_base[r]);
+            a.peer_bar[r] = reinterpret_cast<unsigned int*>(b);
+            a.peer_part[0][r] = reinterpret_cast<float*>(b + m.xchg_part_off);
+            a.peer_part[1][r] = reinterpret_cast<float*>(b + m.xchg_part_off + m.xchg_part_bytes);
+        }
+        a.mg_seq = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(m.xchg) + (size_t)kBarWords * kBarStride * sizeof(unsigned int));
+    }
     void* args[] = {&a};
     const void* fn = m.cfg.qtype == TI_Q_INT4 ? (const void*)mega_decode_kernel<4> : (const void*)mega_decode_kernel<8>;
     CK(cudaLaunchCooperativeKernel(fn, dim3(g_num_sms), dim3(kMegaThreads), args, m.mega_smem, g_stream));
@@ -1189,9 +1285,10 @@ static int nccl_load() {
     g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
     g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
     g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+    g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(lib, "ncclAllGather"));
     g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
     g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GetErrorString)
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.AllGather || !g_nccl.CommDestroy || !g_nccl.GetErrorString)
         return fail("the NCCL library lacks a required symbol");
     g_nccl.lib = lib;
     return 0;
@@ -1683,8 +1780,14 @@ int ti_b200_model_finalize(ti_model_t h) {
     if (complete)
         for (auto& ly : m.layers)
             for (QWeight* w : {ly.qkv.get(), ly.o.get(), ly.gateup.get(), ly.down.get()}) vec_ok &= w->L.K % 4 == 0;
-    m.use_mega = complete && !want_graph && m.tp == 1 && vec_ok;   // the persistent kernel's prologue uses 128-bit loads only
+    // tensor parallel: the persistent kernel with the all-reduce fused in (peer memory over NVLink) unless the NCCL
+    // baseline of the per-op engine is asked for (TURBOINFER_B200_TP_ENGINE=nccl)
+    const char* tpe = getenv("TURBOINFER_B200_TP_ENGINE");
+    m.tp_fused = m.tp > 1 && complete && vec_ok && !want_graph && !(tpe && std::string(tpe) == "nccl") && m.cfg.attn_mode == 1 &&
+                 H <= kConsumerThreads * g_num_sms;
+    m.use_mega = complete && !want_graph && vec_ok && (m.tp == 1 || m.tp_fused);   // the persistent kernel's prologue uses 128-bit loads only
     if (m.tp > 1) TRY(m.ar_tmp.alloc(H));
+    if (m.tp_fused) TRY(tp_exchange_setup(m));
     TRY(m.prompt.alloc(16));
     if (m.use_mega) TRY(build_mega(m));
     // tensor-parallel steps hold NCCL all-reduces: NCCL supports stream capture, so they are replayed from a graph as

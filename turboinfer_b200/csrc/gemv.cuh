@@ -216,6 +216,11 @@ struct PhaseCtx {
     bool coherent;   // activations were produced by other CTAs of the same launch: read them through L2
     int pos;         // cache position of the current token (EPI_QKV); < 0: read *pos_ptr
     unsigned long long* key;  // EPI_LOGITS: argmax key to use instead of GemvArgs::argmax_key (nullptr: keep)
+    // tensor parallel, row-parallel GEMV (EPI_STORE): the partial output goes to every rank's partial buffer instead of
+    // a.out -- peers[r][peer_off + n], r < npeers (0: single GPU)
+    float* const* peers;
+    int npeers;
+    size_t peer_off;
 };
 
 // Position in the ring, carried across the GEMVs of a launch (no divisions per phase): stage and the parity of its use.
@@ -677,7 +682,11 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
             float y = colval(c, cs, zt);
             if (a.epi == EPI_RESIDUAL) y = (first ? pre.r0 : ld_act(resid + n, ctx.coherent)) + y;
             else if (a.epi == EPI_RELU) y = fmaxf(y, 0.f);
-            a.out[n] = y;
+            if (ctx.npeers > 0) {
+                for (int r = 0; r < ctx.npeers; ++r) ctx.peers[r][ctx.peer_off + n] = y;   // NVLink stores (one local)
+            } else {
+                a.out[n] = y;
+            }
             if (a.epi == EPI_LOGITS) {
                 if (y > best) { best = y; besti = n; }
             } else {
@@ -722,7 +731,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const __grid_cons
         return;
     }
     pdl_wait_prior_grid();  // x (and resid / pos) come from the previous kernel in the stream
-    const PhaseCtx ctx{false, -1, nullptr};
+    const PhaseCtx ctx{false, -1, nullptr, nullptr, 0, 0};
     const EpiPre pre = gemv_epilogue_prefetch(a, slab, a.resid, ctx, tid);
     const float s_x = gemv_stage_x<BITS>(a, a.x, sm, slab, false, tid, warp, lane);
     gemv_consume<BITS, DBG>(a, slab, sm, it, make_consume_plan(a.L, slab, warp, lane), warp, lane);

@@ -17,7 +17,8 @@
 
 namespace tib {
 
-enum MegaPhaseType : int { PH_GEMV = 0, PH_ATTN = 1 };
+enum MegaPhaseType : int { PH_GEMV = 0, PH_ATTN = 1, PH_REDUCE = 2 };
+constexpr int kMaxTp = 8;
 struct MegaArgs;
 __device__ __forceinline__ bool getenv_dbg_consume(const MegaArgs& m);
 constexpr int kStampsPerPhase = 32;  // debug timeline: 6 phase-level stamps, [11] ring stages ready, [12..] finer stamps
@@ -28,6 +29,11 @@ struct MegaPhase {
     int x_src;      // PH_GEMV: where x comes from (pointer in g.x, or the embedding row of the current token)
     int resid_src;  // PH_GEMV + EPI_RESIDUAL: same for the residual input
     int is_head;    // lm_head phase: only run on steps that sample
+    // tensor parallel: a row-parallel GEMV phase (mgpu = 1) stores its partial output into EVERY rank's
+    // partial buffer `part_sel` and ends with a barrier across all GPUs; the PH_REDUCE phase after it sums the partials in
+    // rank order on top of the residual (g.x = this rank's partial buffer [tp][H], g.resid / g.out = the residual stream,
+    // g.L.N = H, g.next_norm_w as in a residual epilogue)
+    int mgpu, part_sel;
     GemvArgs g;
     AttnArgs at;
 };
@@ -63,6 +69,11 @@ struct MegaArgs {
     long long* dbg;   // optional: CTA 0 writes 6 clock64 stamps per phase of step 0 (debug timeline)
     int dbg_nomath;   // debug: the main loop only XORs the weights (what the ring alone can deliver)
     int dbg_flags;    // A/B switches (debug): 1 = norm weights loaded after the barrier, 2 = no L1 prefetch of the next descriptor
+    // tensor parallel: peer pointers (CUDA IPC mappings of every rank's exchange block, own rank included)
+    int tp, tp_rank;
+    float* peer_part[2][kMaxTp];       // [buffer][rank] -> that rank's partial buffer, layout [source rank][H]
+    unsigned int* peer_bar[kMaxTp];    // [rank] -> that rank's multi-GPU barrier words (kBarWords x kBarStride)
+    unsigned int* mg_seq;              // device scalar: multi-GPU barriers passed so far (carried across launches)
     const XStats* emb_stats;  // [V]: statistics of every embedding row (against the first norm weight)
 };
 
@@ -95,6 +106,15 @@ __device__ __forceinline__ void bar_arrive_stats(unsigned int* w, float ss, floa
     asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(w + 1), "r"(__float_as_uint(am)) : "memory");
     asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(w + 2), "l"(q) : "memory");
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(w) : "memory");
+}
+// the same across GPUs: arrivals are system-scope atomics on every rank's word (NVLink), the poll is on the local one
+__device__ __forceinline__ void bar_arrive_sys(unsigned int* w) {
+    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned int bar_poll_sys(const unsigned int* w) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
+    return v;
 }
 __device__ __forceinline__ uint4 bar_poll(const unsigned int* w) {
     uint4 v;
@@ -497,10 +517,11 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
         // warp has nothing else to do.  Consumers signal "phase done" with bar.arrive 2 and, after bar.sync 3, pick up from
         // shared memory the conversion scalars this warp derived from the statistics of the phase's output.
         if (warp == kConsumerWarps + 1) {
-            unsigned int k = 0;
+            unsigned int k = 0;                                  // local barriers of this launch
+            unsigned int kk = m.tp > 1 ? *m.mg_seq : 0u;         // multi-GPU barriers since the group was formed
             for (int s = 0; s < m.n_steps; ++s) {
                 const int nph = m.nphases - (s >= m.first_sample ? 0 : 1);   // the lm_head runs on sampling steps only
-                for (int ph = 0; ph < nph; ++ph, ++k) {
+                for (int ph = 0; ph < nph; ++ph) {
                     // what the NEXT phase's prologue needs to turn the statistics into its conversion scalars (fetched
                     // while the consumers are still working on this phase)
                     int nK = 0;
@@ -512,7 +533,26 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                         nnorm = __ldg(reinterpret_cast<const unsigned long long*>(&np->g.norm_w)) != 0ull;
                         neps = __ldg(&np->g.rms_eps);
                     }
+                    const bool mgpu = m.tp > 1 && __ldg(&m.phases[ph].mgpu) != 0;
                     bar_sync(2, kConsumerThreads + 32);   // every consumer thread has stored its outputs and partials
+                    if (mgpu) {
+                        // barrier across all GPUs: the partial outputs this CTA wrote into the peers' buffers become visible
+                        // (system-scope release) before its arrival is counted on every rank's word
+                        unsigned int* wl = m.peer_bar[m.tp_rank] + (kk & (kBarWords - 1)) * kBarStride;
+                        if (lane < m.tp) bar_arrive_sys(m.peer_bar[lane] + (kk & (kBarWords - 1)) * kBarStride);
+                        if (lane == 0) {
+                            const long long t0 = clock64();
+                            const unsigned int target = gridDim.x * (unsigned int)m.tp;
+                            while (bar_poll_sys(wl) < target) {
+                                if (clock64() - t0 > 120000000000LL) __trap();   // ~60 s: ranks may start a launch at different times
+                            }
+                            if (blockIdx.x == 0) m.peer_bar[m.tp_rank][((kk + kBarWords - 1) & (kBarWords - 1)) * kBarStride] = 0u;
+                        }
+                        ++kk;
+                        __syncwarp();
+                        bar_arrive(3, kConsumerThreads + 32);
+                        continue;
+                    }
                     if (lane == 0) {
                         float ss = 0.f, am = 0.f;
 #pragma unroll
@@ -535,10 +575,12 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                         if (blockIdx.x == 0)
                             *reinterpret_cast<uint4*>(m.grid_bar + ((k + kBarWords - 1) & (kBarWords - 1)) * kBarStride) = make_uint4(0u, 0u, 0u, 0u);
                     }
+                    ++k;
                     __syncwarp();
                     bar_arrive(3, kConsumerThreads + 32);  // barrier passed, scalars in sm.red[0..2]
                 }
             }
+            if (m.tp > 1 && blockIdx.x == 0 && lane == 0) *m.mg_seq = kk;
         }
         return;
     }
@@ -611,7 +653,9 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                 for (int i = tid; i < (int)(sizeof(MegaPhase) / 4); i += kConsumerThreads) dst[i] = src[i];
             }
             const bool gemv_here = PG.type == PH_GEMV && (int)blockIdx.x < PG.g.L.P;
-            const PhaseCtx ctx{true, pos, is_head ? &m.keys[s & 1] : nullptr};
+            const bool to_peers = m.tp > 1 && PG.type == PH_GEMV && PG.mgpu != 0;
+            const PhaseCtx ctx{true, pos, is_head ? &m.keys[s & 1] : nullptr, to_peers ? m.peer_part[PG.part_sel] : nullptr, to_peers ? m.tp : 0,
+                               (size_t)m.tp_rank * (size_t)m.H};
             Slab slab{};
             EpiPre pre{};
             XPre xpre;
@@ -649,6 +693,21 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                     gemv_consume<BITS>(g, slab, sm, it, plan, warp, lane, stamp ? ts + 17 : nullptr);
                     if (stamp) ts[3] = clock64();
                     out_st = gemv_epilogue(g, slab, sm, s_x, resid, ctx, pre, tid, lane);
+                }
+            } else if (P.type == PH_REDUCE) {
+                // all-reduce, second half: every rank's partial of the row-parallel GEMV is in this rank's buffer (the
+                // barrier across the GPUs has been passed); x <- residual + partials in rank order -- the same sums on
+                // every rank, so the replicated residual stream stays bit-identical across the group
+                const int n = P.g.L.N;
+                const int per = ((n + (int)gridDim.x - 1) / (int)gridDim.x + 3) & ~3;
+                const int i = (int)blockIdx.x * per + tid;
+                if (tid < per && i < n) {
+                    const float* rsd = P.resid_src == SRC_EMB ? m.emb + (size_t)token * m.H : P.g.resid;
+                    float v = P.resid_src == SRC_EMB ? rsd[i] : __ldcg(rsd + i);
+                    for (int r = 0; r < m.tp; ++r) v += __ldcg(P.g.x + (size_t)r * n + i);
+                    P.g.out[i] = v;
+                    out_st.ss = v * v;
+                    out_st.am = fabsf(P.g.next_norm_w ? v * P.g.next_norm_w[i] : v);
                 }
             } else {
                 out_st.am = mega_attention(P.at, pos + 1, m.head_cnt, attn_sm);
