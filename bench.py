@@ -281,7 +281,8 @@ def main():
             "data": "synthetic", "config": config,
             "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 4 * n_prompt, "d2h_bytes_per_step": 4 * n_new},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": ("gemv_kernel<%d> + NCCL all-reduce per layer (per-op engine, tensor parallel; per-GPU bytes)" % (4 if qname == "int4" else 8)) if tp > 1 else
+            "roofline": {"bound": "hbm", "kernel": (("gemv_kernel<%d> + NCCL all-reduce per layer (per-op engine, tensor parallel; per-GPU bytes)" if os.environ.get("TURBOINFER_B200_TP_ENGINE") == "nccl"
+                                                     else "mega_decode_kernel<%d> with the all-reduce fused in (peer stores over NVLink + barrier across the GPUs; per-GPU bytes)") % (4 if qname == "int4" else 8)) if tp > 1 else
                          "mega_decode_kernel<%d> (persistent: one launch decodes %d tokens)" % (4 if qname == "int4" else 8, n_new - 1),
                          "achieved": launch_gbs, "peak": peak, "unit": "GB/s", "frac": launch_gbs / peak,
                          "traffic": traffic, "peak_source": peak_src + ", sustained (the launch lasts hundreds of ms)",
