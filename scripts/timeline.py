@@ -19,7 +19,7 @@ for rep in range(2):
     ts = m.debug_timeline(5)
 names = ["qkv", "attn", "o", "gateup", "down"]
 print(f"{shape} L={layers} t={ctx}: us @1.965GHz, CTA 0 thread 0")
-print("phase        | hdr   wait | issue stats conv  bar  =stage | 1stw  loop flush  bar =consume | epi  | bar  slot  red =arrive | total  ready")
+print("phase        | hdr   wait | issue stats conv  bar  =stage | setup+lds+wait   loop flush  bar =consume | epi  | bar  slot  red =arrive | total  ready")
 f = 1 / 1965.0
 tot = {}
 for i, r in enumerate(ts):
@@ -29,6 +29,6 @@ for i, r in enumerate(ts):
         line = f"{i:3d} {nm:7s} | {u(0,12):5.2f} {u(12,1):5.2f} | {'':29s} | {'':29s} | {u(1,4):4.2f} | {u(4,21):4.2f} {u(21,22):5.2f} {u(22,5):4.2f} ={u(4,5):5.2f} | {u(0,5):6.2f}"
     else:
         line = (f"{i:3d} {nm:7s} | {u(0,12):5.2f} {u(12,1):5.2f} | {u(6,13):5.2f} {u(13,14):5.2f} {u(14,15):4.2f} {u(15,2):4.2f} ={u(1,2):5.2f} | "
-                f"{u(2,17):4.2f} {u(17,18):5.2f} {u(18,19):5.2f} {u(19,3):4.2f} ={u(2,3):6.2f} | {u(3,4):4.2f} | {u(4,21):4.2f} {u(21,22):5.2f} {u(22,5):4.2f} ={u(4,5):5.2f} | {u(0,5):6.2f}  {r[11]}")
+                f"{u(2,23):4.2f}+{u(23,24):4.2f}+{u(24,17):4.2f} {u(17,18):5.2f} {u(18,19):5.2f} {u(19,3):4.2f} ={u(2,3):6.2f} | {u(3,4):4.2f} | {u(4,21):4.2f} {u(21,22):5.2f} {u(22,5):4.2f} ={u(4,5):5.2f} | {u(0,5):6.2f}  {r[11]}")
     print(line)
 print("step total us:", (ts[-1, 5] - ts[0, 0]) * f)

@@ -500,6 +500,7 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
     QuadAcc<BITS> acc;
     acc.clear();
     bool dirty = false;
+    if (dbg) dbg[6] = clock64();
     auto flush = [&]() {
         // C fragment: c0, c1 = (row g, B columns 2t, 2t+1), c2, c3 = (row g + 8, same columns); B column = digit plane
         const int rows = grp == slab.ngroups - 1 ? 4 * slab.nlast : 16;
@@ -530,6 +531,7 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
             xa = load_xfrag<BITS>(xq);
             xb = load_xfrag<BITS>(xq + kXItem);
         }
+        if (dbg && r == 0) dbg[7] = clock64();
         if (DBG != 2 && !ready) mbar_wait(&sm.full[st], par);
         if (dbg && r == 0) dbg[0] = clock64();
         ready = false;
