@@ -26,3 +26,14 @@ def test_host_api_without_gpu(exe):
 def test_host_api_on_gpu(exe):
     r = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_packed_layout_host_logic(tmp_path):
+    """qlayout.cuh compiled for the host: slab partition, stage bookkeeping and the fragment-order map (bijection, no
+    padding bytes) for full and ragged groups -- the logic pack / unpack kernels, producer and consumers share."""
+    exe = str(tmp_path / "test_layout")
+    src = os.path.join(ROOT, "tests", "cpp", "test_layout.cpp")
+    r = subprocess.run([os.environ.get("TI_HOST_CXX", "/usr/bin/g++"), "-std=c++17", "-O1", "-o", exe, src], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "layout test: ok" in r.stdout, r.stdout + r.stderr
