@@ -872,7 +872,6 @@ int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
     a.max_units = m.mega_max_units;
     a.attn_floats = m.mega_attn_floats;
     a.dbg = m.dbg_on ? m.dbg.p : nullptr;
-    a.dbg_nomath = (m.dbg_on && getenv("TURBOINFER_B200_DBG_NOMATH")) ? atoi(getenv("TURBOINFER_B200_DBG_NOMATH")) : 0;
     a.emb_stats = m.emb_stats.p;
     a.dbg_flags = getenv("TURBOINFER_B200_DBG_FLAGS") ? atoi(getenv("TURBOINFER_B200_DBG_FLAGS")) : 0;
     a.tp = m.tp_fused ? m.tp : 1;

@@ -20,7 +20,6 @@ namespace tib {
 enum MegaPhaseType : int { PH_GEMV = 0, PH_ATTN = 1, PH_REDUCE = 2 };
 constexpr int kMaxTp = 8;
 struct MegaArgs;
-__device__ __forceinline__ bool getenv_dbg_consume(const MegaArgs& m);
 constexpr int kStampsPerPhase = 32;  // debug timeline: 6 phase-level stamps, [11] ring stages ready, [12..] finer stamps
 enum MegaSrc : int { SRC_PTR = 0, SRC_EMB = 1 };
 
@@ -67,7 +66,6 @@ struct MegaArgs {
     int stages;
     int max_kpad, max_units, attn_floats;
     long long* dbg;   // optional: CTA 0 writes 6 clock64 stamps per phase of step 0 (debug timeline)
-    int dbg_nomath;   // debug: the main loop only XORs the weights (what the ring alone can deliver)
     int dbg_flags;    // A/B switches (debug): 1 = norm weights loaded after the barrier, 2 = no L1 prefetch of the next descriptor
     // tensor parallel: peer pointers (CUDA IPC mappings of every rank's exchange block, own rank included)
     int tp, tp_rank;
@@ -77,7 +75,6 @@ struct MegaArgs {
     const XStats* emb_stats;  // [V]: statistics of every embedding row (against the first norm weight)
 };
 
-__device__ __forceinline__ bool getenv_dbg_consume(const MegaArgs& m) { return m.dbg_nomath == 3; }
 TIB_HD size_t mega_smem_bytes(int stages, int max_kpad, int max_units, int attn_floats) {
     return gemv_smem_bytes_for(stages, max_kpad, max_units) + 16 + (size_t)attn_floats * 4 + 16 + 2 * ((sizeof(MegaPhase) + 15) & ~size_t(15));
 }
@@ -475,7 +472,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
     if (warp >= kConsumerWarps) {
         // ===== producer warpgroup: warp 16 streams every GEMV phase of every step, back to back =====
         reg_dealloc<40>();
-        if (warp == kConsumerWarps && m.dbg_nomath != 2) {
+        if (warp == kConsumerWarps) {
             // lane l holds the record of phase base + l: one latency per 32 phases, then register shuffles only
             for (int s = 0; s < m.n_steps; ++s) {
                 const bool sample = s >= m.first_sample;
@@ -685,11 +682,6 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                                                 : XScale{sm.red[0], sm.red[1], sm.red[2]};
                     const float s_x = gemv_stage_x_lean<BITS>(g, x, sm, slab, !from_emb, xsc, xpre, (m.dbg_flags & 1) != 0, tid, lane, stamp ? ts + 13 : nullptr);
                     if (stamp) ts[2] = clock64();
-#ifdef TIB_MEGA_DEBUG_VARIANTS
-                    if (m.dbg_nomath == 2) gemv_consume<BITS, 2>(g, slab, sm, it, plan, warp, lane);
-                    else if (m.dbg_nomath == 1) gemv_consume<BITS, 1>(g, slab, sm, it, plan, warp, lane);
-                    else
-#endif
                     gemv_consume<BITS>(g, slab, sm, it, plan, warp, lane, stamp ? ts + 17 : nullptr);
                     if (stamp) ts[3] = clock64();
                     out_st = gemv_epilogue(g, slab, sm, s_x, resid, ctx, pre, tid, lane);
