@@ -1060,6 +1060,7 @@ int prefill_gemm(Model& m, const int* prompt_dev, int M) {
     if (!attr) {
         CK(cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
         CK(cudaFuncSetAttribute(rmsnorm_digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        CK(cudaFuncSetAttribute(causal_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPfSmemBytes));
         attr = true;
     }
     const int H = m.cfg.hidden, I = std::max(m.cfg.inter, 1);
@@ -1074,7 +1075,7 @@ int prefill_gemm(Model& m, const int* prompt_dev, int M) {
         TRY(pf_digits(m, m.pf_x.p, ly.attn_norm.p, M, H, m_pad, ly.qkv->k_pad));
         TRY(pf_gemm(m, *ly.qkv, M, m_pad, m.pf_qkv.p, nullptr));
         rope_kv_kernel<<<M, 256, 0, g_stream>>>(m.pf_qkv.p, M, H, rope_dim, m.inv_freq.p, pos0, ly.k_pool.p, ly.v_pool.p, m.page_table.p, m.page_tokens);
-        causal_attention_kernel<<<dim3(m.attn_heads, (M + kPfQ - 1) / kPfQ), kPfThreads, 0, g_stream>>>(
+        causal_attention_kernel<<<dim3(m.attn_heads, (M + kPfQ - 1) / kPfQ), kPfThreads, kPfSmemBytes, g_stream>>>(
             m.pf_qkv.p, M, H, m.attn_dim, 1.0f / sqrtf((float)m.attn_dim), pos0, ly.k_pool.p, ly.v_pool.p, m.page_table.p, m.page_tokens, m.pf_attn.p);
         g_launches += 2;
         TRY(ensure_kmajor(*ly.o));

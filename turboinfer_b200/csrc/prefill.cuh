@@ -94,76 +94,129 @@ __global__ void rope_kv_kernel(float* qkv, int M, int H, int rope_dim, const flo
 }
 
 // Causal multi-head attention for M queries at positions pos0 .. pos0 + M - 1 over the paged cache (which already holds
-// their own K / V rows).  grid (heads, ceil(M / 32)); 8 warps, 4 queries per warp; a lane owns 4 dims (D <= 128).
-// Key tiles of 32 tokens are staged in shared memory once per CTA and shared by its 32 queries; the softmax is online
-// (max-subtracted, expf), one key at a time per query, sums in key order -- the order of attention_fast_incremental.
-constexpr int kPfQ = 32, kPfKT = 32, kPfThreads = 256;
-__global__ void __launch_bounds__(kPfThreads) causal_attention_kernel(const float* qkv, int M, int H, int D, float scale, int pos0,
-                                                                        const float* k_pool, const float* v_pool, const int* page_table,
-                                                                        int page_tokens, float* out) {
-    __shared__ __align__(16) float ks[kPfKT][128];
-    __shared__ __align__(16) float vs[kPfKT][128];
-    const int h = blockIdx.x, qb = blockIdx.y * kPfQ;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// their own K / V rows).  fp32 on the CUDA cores, organised as two register-tiled GEMMs per key tile (no per-pair
+// shuffles): a CTA owns 128 queries of one head; per tile of 64 keys
+//   S[128 x 64] = Q K^T   thread (ty, tx) computes 8 queries x 4 keys, reading Q and K TRANSPOSED from shared memory
+//                         ([d][query], [d][key]: two broadcast LDS.128 + one LDS.128 per 32 FMAs)
+//   online softmax        per query row over the tile (max-subtracted, expf), row statistics shared by the 16 threads of a
+//                         row with shuffles once per tile; O and the running sum are rescaled by exp(m_old - m_new)
+//   O[128 x 128] += P V   the same thread owns the same 8 query rows x 8 dims (64 accumulators), P read transposed
+// Keys in a query's future get probability 0; tiles entirely in the future are skipped.  D <= 128 (padded with zeros).
+constexpr int kPfQ = 128, kPfKT = 64, kPfThreads = 256, kPfD = 128;
+constexpr size_t kPfSmemBytes = ((size_t)kPfD * kPfQ + (size_t)kPfD * kPfKT + (size_t)kPfKT * kPfD + (size_t)kPfKT * kPfQ) * sizeof(float);   // 160 KiB
+__global__ void __launch_bounds__(kPfThreads, 1) causal_attention_kernel(const float* qkv, int M, int H, int D, float scale, int pos0,
+                                                                           const float* k_pool, const float* v_pool, const int* page_table,
+                                                                           int page_tokens, float* out) {
+    extern __shared__ __align__(16) float pf_smem[];
+    float* Qt = pf_smem;                       // [128 d][128 q]
+    float* Kt = Qt + kPfD * kPfQ;              // [128 d][64 k]
+    float* Vs = Kt + kPfD * kPfKT;             // [64 k][128 d]
+    float* Pt = Vs + kPfKT * kPfD;             // [64 k][128 q]
+    const int h = blockIdx.x, qb = (int)(gridDim.y - 1 - blockIdx.y) * kPfQ;   // latest queries (most key tiles) first: no long tail
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int hoff = h * D;
-    const bool lane_on = 4 * lane < D;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 q[4], o[4];
-    float mrun[4], lrun[4];
-    int qpos[4];
+    const int nq = min(kPfQ, M - qb);          // live queries of this CTA
+    // Q tile, transposed.  Consecutive lanes take consecutive queries, so the four scattered stores of a float4 are
+    // conflict-free (the 16-byte global reads of neighbouring d meet again in L1).
+    for (int i = tid; i < kPfQ * (kPfD / 4); i += kPfThreads) {
+        const int q = i & (kPfQ - 1), d4 = (i >> 7) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < nq && d4 < D) v = *reinterpret_cast<const float4*>(qkv + (size_t)(qb + q) * 3 * H + hoff + d4);
+        Qt[(d4 + 0) * kPfQ + q] = v.x; Qt[(d4 + 1) * kPfQ + q] = v.y; Qt[(d4 + 2) * kPfQ + q] = v.z; Qt[(d4 + 3) * kPfQ + q] = v.w;
+    }
+    float o[8][8], mrun[8], lrun[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = qb + warp * 4 + i;
-        qpos[i] = m < M ? pos0 + m : -1;
-        q[i] = (m < M && lane_on) ? *reinterpret_cast<const float4*>(qkv + (size_t)m * 3 * H + hoff + 4 * lane) : zero4;
-        o[i] = zero4;
+    for (int i = 0; i < 8; ++i) {
         mrun[i] = -INFINITY;
         lrun[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[i][j] = 0.f;
     }
-    const int last_pos = pos0 + min(M, qb + kPfQ) - 1;   // keys 0 .. last_pos can matter to this CTA
+    const int last_pos = pos0 + qb + nq - 1;   // keys 0 .. last_pos can matter to this CTA
     for (int t0 = 0; t0 <= last_pos; t0 += kPfKT) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < kPfKT * 32; i += kPfThreads) {
-            const int tt = i >> 5, l = i & 31, t = t0 + tt;
-            float4 kv = zero4, vv = zero4;
-            if (t <= last_pos && 4 * l < D) {
-                const size_t off = ((size_t)page_table[t / page_tokens] * page_tokens + (t % page_tokens)) * H + hoff + 4 * l;
-                kv = *reinterpret_cast<const float4*>(k_pool + off);
-                vv = *reinterpret_cast<const float4*>(v_pool + off);
-            }
-            *reinterpret_cast<float4*>(&ks[tt][4 * l]) = kv;
-            *reinterpret_cast<float4*>(&vs[tt][4 * l]) = vv;
+        __syncthreads();                       // the previous tile's Kt / Vs / Pt are no longer read
+        for (int i = tid; i < kPfKT * (kPfD / 4); i += kPfThreads) {   // K transposed: consecutive lanes = consecutive keys
+            const int kk = i & (kPfKT - 1), d4 = (i >> 6) * 4, t = t0 + kk;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t <= last_pos && d4 < D)
+                kv = *reinterpret_cast<const float4*>(k_pool + ((size_t)page_table[t / page_tokens] * page_tokens + (t % page_tokens)) * H + hoff + d4);
+            Kt[(d4 + 0) * kPfKT + kk] = kv.x; Kt[(d4 + 1) * kPfKT + kk] = kv.y; Kt[(d4 + 2) * kPfKT + kk] = kv.z; Kt[(d4 + 3) * kPfKT + kk] = kv.w;
+        }
+        for (int i = tid; i < kPfKT * (kPfD / 4); i += kPfThreads) {   // V as it is: consecutive lanes = consecutive dims
+            const int kk = i >> 5, d4 = (i & 31) * 4, t = t0 + kk;
+            float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t <= last_pos && d4 < D)
+                vv = *reinterpret_cast<const float4*>(v_pool + ((size_t)page_table[t / page_tokens] * page_tokens + (t % page_tokens)) * H + hoff + d4);
+            *reinterpret_cast<float4*>(Vs + kk * kPfD + d4) = vv;
         }
         __syncthreads();
-        const int nt = min(kPfKT, last_pos - t0 + 1);
+        // S = Q K^T for 8 queries x 4 keys
+        float sacc[8][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (qpos[i] < t0) continue;   // warp-uniform: every key of the tile is in this query's future (or the query is padding)
-            for (int tt = 0; tt < nt && t0 + tt <= qpos[i]; ++tt) {
-                const float4 kv = *reinterpret_cast<const float4*>(&ks[tt][4 * lane]);
-                float s = q[i].x * kv.x;
-                s = fmaf(q[i].y, kv.y, s);
-                s = fmaf(q[i].z, kv.z, s);
-                s = fmaf(q[i].w, kv.w, s);
-                s = warp_sum(s) * scale;
-                const float mn = fmaxf(mrun[i], s);
-                const float corr = expf(mrun[i] - mn), p = expf(s - mn);
-                const float4 vv = *reinterpret_cast<const float4*>(&vs[tt][4 * lane]);
-                lrun[i] = lrun[i] * corr + p;
-                o[i].x = fmaf(p, vv.x, o[i].x * corr);
-                o[i].y = fmaf(p, vv.y, o[i].y * corr);
-                o[i].z = fmaf(p, vv.z, o[i].z * corr);
-                o[i].w = fmaf(p, vv.w, o[i].w * corr);
-                mrun[i] = mn;
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sacc[i][j] = 0.f;
+#pragma unroll 4
+        for (int d = 0; d < kPfD; ++d) {
+            const float4 qa = *reinterpret_cast<const float4*>(Qt + d * kPfQ + 8 * ty), qb4 = *reinterpret_cast<const float4*>(Qt + d * kPfQ + 8 * ty + 4);
+            const float4 kb = *reinterpret_cast<const float4*>(Kt + d * kPfKT + 4 * tx);
+            const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb4.x, qb4.y, qb4.z, qb4.w}, kv[4] = {kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sacc[i][j] = fmaf(qv[i], kv[j], sacc[i][j]);
+        }
+        // online softmax per query row; the 16 threads tx = 0..15 of a row are the 16 lanes of a half-warp
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int qpos = pos0 + qb + 8 * ty + i;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int t = t0 + 4 * tx + j;
+                sacc[i][j] = (t <= qpos && 8 * ty + i < nq) ? sacc[i][j] * scale : -INFINITY;
+                mx = fmaxf(mx, sacc[i][j]);
             }
+#pragma unroll
+            for (int o2 = 8; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
+            const float mn = fmaxf(mrun[i], mx);
+            float rs = 0.f, p[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                p[j] = mn == -INFINITY ? 0.f : expf(sacc[i][j] - mn);   // expf(-inf) = 0 for masked keys
+                rs += p[j];
+            }
+#pragma unroll
+            for (int o2 = 8; o2 > 0; o2 >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o2);
+            const float corr = mn == -INFINITY ? 1.f : expf(mrun[i] - mn);
+            lrun[i] = lrun[i] * corr + rs;
+            mrun[i] = mn;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[i][j] *= corr;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Pt[(4 * tx + j) * kPfQ + 8 * ty + i] = p[j];
+        }
+        __syncthreads();
+        // O += P V for the same 8 queries x dims 8 tx .. 8 tx + 7
+        const int nk = min(kPfKT, last_pos - t0 + 1);
+        for (int kk = 0; kk < nk; ++kk) {
+            const float4 pa = *reinterpret_cast<const float4*>(Pt + kk * kPfQ + 8 * ty), pb = *reinterpret_cast<const float4*>(Pt + kk * kPfQ + 8 * ty + 4);
+            const float4 va = *reinterpret_cast<const float4*>(Vs + kk * kPfD + 8 * tx), vb = *reinterpret_cast<const float4*>(Vs + kk * kPfD + 8 * tx + 4);
+            const float pv[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w}, vv[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[i][j] = fmaf(pv[i], vv[j], o[i][j]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = qb + warp * 4 + i;
-        if (m < M && lane_on) {
+    for (int i = 0; i < 8; ++i) {
+        const int q = 8 * ty + i;
+        if (q < nq && 8 * tx < D) {
             const float inv = 1.0f / lrun[i];
-            *reinterpret_cast<float4*>(out + (size_t)m * H + hoff + 4 * lane) = make_float4(o[i].x * inv, o[i].y * inv, o[i].z * inv, o[i].w * inv);
+            float* dst = out + (size_t)(qb + q) * H + hoff + 8 * tx;
+            *reinterpret_cast<float4*>(dst) = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
+            if (8 * tx + 4 < D) *reinterpret_cast<float4*>(dst + 4) = make_float4(o[i][4] * inv, o[i][5] * inv, o[i][6] * inv, o[i][7] * inv);
         }
     }
 }
