@@ -214,17 +214,35 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (row_ok) {
+                auto val = [&](int i, int n) -> float {
+                    const long long t = ((long long)(int)a[2][i] << 16) + ((long long)(int)a[1][i] << 8) + (long long)(int)a[0][i] - offterm;
+                    const int hi = (int)(t >> 23), lo = (int)(t & 0x7FFFFF);
+                    const float tf = fmaf((float)hi, 8388608.0f, (float)lo);
+                    const float zt = g.colzterm ? g.colzterm[n] : 0.f;
+                    return (fmaf(zt, fsxf, tf) * sx) * g.colscale[n];   // the GEMV epilogue's expression
+                };
+                const int nbase = nb * kGemmBN + c0;
+                float* yrow = g.y + (size_t)row * g.N;
+                const float* rrow = g.resid ? g.resid + (size_t)row * g.N : nullptr;
+                if ((g.N & 3) == 0 && nbase + 16 <= g.N) {   // 64 contiguous bytes per lane: four 16-byte stores
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int n = nb * kGemmBN + c0 + i;
-                    if (n < g.N) {
-                        const long long t = ((long long)(int)a[2][i] << 16) + ((long long)(int)a[1][i] << 8) + (long long)(int)a[0][i] - offterm;
-                        const int hi = (int)(t >> 23), lo = (int)(t & 0x7FFFFF);
-                        const float tf = fmaf((float)hi, 8388608.0f, (float)lo);
-                        const float zt = g.colzterm ? g.colzterm[n] : 0.f;
-                        float yv = (fmaf(zt, fsxf, tf) * sx) * g.colscale[n];   // the GEMV epilogue's expression
-                        if (g.resid) yv = g.resid[(size_t)row * g.N + n] + yv;
-                        g.y[(size_t)row * g.N + n] = yv;
+                    for (int i = 0; i < 16; i += 4) {
+                        float4 v = make_float4(val(i, nbase + i), val(i + 1, nbase + i + 1), val(i + 2, nbase + i + 2), val(i + 3, nbase + i + 3));
+                        if (rrow) {
+                            const float4 r = *reinterpret_cast<const float4*>(rrow + nbase + i);
+                            v.x = r.x + v.x; v.y = r.y + v.y; v.z = r.z + v.z; v.w = r.w + v.w;
+                        }
+                        *reinterpret_cast<float4*>(yrow + nbase + i) = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int n = nbase + i;
+                        if (n < g.N) {
+                            float yv = val(i, n);
+                            if (rrow) yv = rrow[n] + yv;
+                            yrow[n] = yv;
+                        }
                     }
                 }
             }
