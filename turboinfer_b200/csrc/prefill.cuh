@@ -124,13 +124,14 @@ __global__ void __launch_bounds__(kPfThreads, 1) causal_attention_kernel(const f
         if (q < nq && d4 < D) v = *reinterpret_cast<const float4*>(qkv + (size_t)(qb + q) * 3 * H + hoff + d4);
         Qt[(d4 + 0) * kPfQ + q] = v.x; Qt[(d4 + 1) * kPfQ + q] = v.y; Qt[(d4 + 2) * kPfQ + q] = v.z; Qt[(d4 + 3) * kPfQ + q] = v.w;
     }
-    float o[8][8], mrun[8], lrun[8];
+    f32x2 o2[8][4];   // 8 queries x 8 dims, as pairs of dims
+    float mrun[8], lrun[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         mrun[i] = -INFINITY;
         lrun[i] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) o2[i][j] = pack2(0.f, 0.f);
     }
     const int last_pos = pos0 + qb + nq - 1;   // keys 0 .. last_pos can matter to this CTA
     for (int t0 = 0; t0 <= last_pos; t0 += kPfKT) {
@@ -151,21 +152,26 @@ __global__ void __launch_bounds__(kPfThreads, 1) causal_attention_kernel(const f
         }
         __syncthreads();
         // S = Q K^T for 8 queries x 4 keys
-        float sacc[8][4];
+        // (packed fp32x2 FMAs, SASS FFMA2: two fma.rn per instruction, bit-identical to the scalar form)
+        f32x2 sacc2[8][2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) sacc[i][j] = 0.f;
+        for (int i = 0; i < 8; ++i) sacc2[i][0] = sacc2[i][1] = pack2(0.f, 0.f);
 #pragma unroll 4
         for (int d = 0; d < kPfD; ++d) {
             const float4 qa = *reinterpret_cast<const float4*>(Qt + d * kPfQ + 8 * ty), qb4 = *reinterpret_cast<const float4*>(Qt + d * kPfQ + 8 * ty + 4);
             const float4 kb = *reinterpret_cast<const float4*>(Kt + d * kPfKT + 4 * tx);
-            const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb4.x, qb4.y, qb4.z, qb4.w}, kv[4] = {kb.x, kb.y, kb.z, kb.w};
+            const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb4.x, qb4.y, qb4.z, qb4.w};
+            const f32x2 k01 = pack2(kb.x, kb.y), k23 = pack2(kb.z, kb.w);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) sacc[i][j] = fmaf(qv[i], kv[j], sacc[i][j]);
+            for (int i = 0; i < 8; ++i) {
+                const f32x2 qq = pack2(qv[i], qv[i]);
+                sacc2[i][0] = fma2(qq, k01, sacc2[i][0]);
+                sacc2[i][1] = fma2(qq, k23, sacc2[i][1]);
+            }
         }
+        float sacc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { unpack2(sacc2[i][0], sacc[i][0], sacc[i][1]); unpack2(sacc2[i][1], sacc[i][2], sacc[i][3]); }
         // online softmax per query row; the 16 threads tx = 0..15 of a row are the 16 lanes of a half-warp
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -191,8 +197,9 @@ __global__ void __launch_bounds__(kPfThreads, 1) causal_attention_kernel(const f
             const float corr = mn == -INFINITY ? 1.f : expf(mrun[i] - mn);
             lrun[i] = lrun[i] * corr + rs;
             mrun[i] = mn;
+            const f32x2 cc = pack2(corr, corr);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[i][j] *= corr;
+            for (int j = 0; j < 4; ++j) o2[i][j] = mul2(o2[i][j], cc);
 #pragma unroll
             for (int j = 0; j < 4; ++j) Pt[(4 * tx + j) * kPfQ + 8 * ty + i] = p[j];
         }
@@ -202,11 +209,14 @@ __global__ void __launch_bounds__(kPfThreads, 1) causal_attention_kernel(const f
         for (int kk = 0; kk < nk; ++kk) {
             const float4 pa = *reinterpret_cast<const float4*>(Pt + kk * kPfQ + 8 * ty), pb = *reinterpret_cast<const float4*>(Pt + kk * kPfQ + 8 * ty + 4);
             const float4 va = *reinterpret_cast<const float4*>(Vs + kk * kPfD + 8 * tx), vb = *reinterpret_cast<const float4*>(Vs + kk * kPfD + 8 * tx + 4);
-            const float pv[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w}, vv[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+            const float pv[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+            const f32x2 v2[4] = {pack2(va.x, va.y), pack2(va.z, va.w), pack2(vb.x, vb.y), pack2(vb.z, vb.w)};
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 8; ++i) {
+                const f32x2 pp = pack2(pv[i], pv[i]);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[i][j] = fmaf(pv[i], vv[j], o[i][j]);
+                for (int j = 0; j < 4; ++j) o2[i][j] = fma2(pp, v2[j], o2[i][j]);
+            }
         }
     }
 #pragma unroll
@@ -214,9 +224,12 @@ __global__ void __launch_bounds__(kPfThreads, 1) causal_attention_kernel(const f
         const int q = 8 * ty + i;
         if (q < nq && 8 * tx < D) {
             const float inv = 1.0f / lrun[i];
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) unpack2(o2[i][j], o[2 * j], o[2 * j + 1]);
             float* dst = out + (size_t)(qb + q) * H + hoff + 8 * tx;
-            *reinterpret_cast<float4*>(dst) = make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv);
-            if (8 * tx + 4 < D) *reinterpret_cast<float4*>(dst + 4) = make_float4(o[i][4] * inv, o[i][5] * inv, o[i][6] * inv, o[i][7] * inv);
+            *reinterpret_cast<float4*>(dst) = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
+            if (8 * tx + 4 < D) *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
         }
     }
 }
