@@ -100,11 +100,14 @@ __global__ void __launch_bounds__(kDigitsThreads) rmsnorm_digits_small_kernel(co
             const int f0 = __float2int_rn(v[i].x * inv_s), f1 = __float2int_rn(v[i].y * inv_s), f2 = __float2int_rn(v[i].z * inv_s),
                       f3 = __float2int_rn(v[i].w * inv_s);
             sxf += (long long)((f0 + f1) + (f2 + f3));
-            const uint32_t lo01 = __byte_perm(f0, f1, 0x5140), lo23 = __byte_perm(f2, f3, 0x5140);
-            const uint32_t hi01 = __byte_perm(f0, f1, 0x0062), hi23 = __byte_perm(f2, f3, 0x0062);
-            *reinterpret_cast<uint32_t*>(planes + ((size_t)0 * m_pad + row) * k_pad + k) = __byte_perm(lo01, lo23, 0x5410);
-            *reinterpret_cast<uint32_t*>(planes + ((size_t)1 * m_pad + row) * k_pad + k) = __byte_perm(lo01, lo23, 0x7632);
-            *reinterpret_cast<uint32_t*>(planes + ((size_t)2 * m_pad + row) * k_pad + k) = __byte_perm(hi01, hi23, 0x5410);
+            // signed digits: the bytes of f + 0x808080, xor 0x80 (every digit in [-128, 127])
+            const int u0 = f0 + 0x808080, u1 = f1 + 0x808080, u2 = f2 + 0x808080, u3 = f3 + 0x808080;
+            const uint32_t lo01 = __byte_perm(u0, u1, 0x5140), lo23 = __byte_perm(u2, u3, 0x5140);
+            const uint32_t hi01 = __byte_perm(u0, u1, 0x0062), hi23 = __byte_perm(u2, u3, 0x0062);
+            // stored as the swizzled tile images the 32-row GEMM copies in bulk (gemm_tc.cuh xtile_offset)
+            *reinterpret_cast<uint32_t*>(planes + xtile_offset(0, row, k)) = __byte_perm(lo01, lo23, 0x5410) ^ 0x80808080u;
+            *reinterpret_cast<uint32_t*>(planes + xtile_offset(1, row, k)) = __byte_perm(lo01, lo23, 0x7632) ^ 0x80808080u;
+            *reinterpret_cast<uint32_t*>(planes + xtile_offset(2, row, k)) = __byte_perm(hi01, hi23, 0x5410) ^ 0x80808080u;
         }
     }
 #pragma unroll

@@ -118,7 +118,7 @@ struct QWeight {
     bool has_zterm = false;
     DevBuf<uint8_t> packed;
     DevBuf<float> colscale, colzterm;
-    // K-major byte copy for the tensor-core GEMM (built on first use): Wk[n_pad][k_pad]
+    // byte copy for the tensor-core GEMMs (built on first use): tile-major, pre-swizzled (gemm_tc.cuh wtile_offset)
     DevBuf<uint8_t> kmajor;
     int k_pad = 0, n_pad = 0;
     size_t bytes() const { return layout_bytes(L); }
@@ -316,6 +316,7 @@ struct Model {
     DevBuf<long long> pf_sxf;
     DevBuf<unsigned long long> pf_ws;   // split-K workspace of the 32-row GEMM: [n_pad][32] integer partial sums, zero between GEMMs
     DevBuf<unsigned int> pf_cnt;        // ... and its per-tile arrival counters
+    bool pf_small_layout = false;       // pf_planes currently holds the 32-row GEMM's tile images (batch.cuh) rather than [3][m_pad][k_pad]
     DevBuf<int> pf_tokens;
     std::unique_ptr<struct BatchState> batch;   // batched decode (generate_batch): per-sequence KV pages, step graphs
     int tp = 1, tp_rank = 0;   // tensor-parallel degree / rank of this model
@@ -946,9 +947,8 @@ int gemm_q_dev(QWeight& w, const float* x_dev, float* y_dev, int M, float* kerne
     gemm_digits_kernel<<<M, 256, 0, g_stream>>>(x_dev, M, K, m_pad, w.k_pad, planes.p, sx.p, sxf.p);
     ++g_launches;
     CK(cudaGetLastError());
-    CUtensorMap map_a, map_b;
+    CUtensorMap map_a;
     TRY(make_tmap_u8_2d(&map_a, planes.p, (uint64_t)w.k_pad, (uint64_t)3 * m_pad));
-    TRY(make_tmap_u8_2d(&map_b, w.kmajor.p, (uint64_t)w.k_pad, (uint64_t)w.n_pad));
     GemmArgs g{};
     g.M = M; g.N = N; g.K = K;
     g.m_pad = m_pad; g.k_pad = w.k_pad;
@@ -958,11 +958,12 @@ int gemm_q_dev(QWeight& w, const float* x_dev, float* y_dev, int M, float* kerne
     g.colscale = w.colscale.p;
     g.colzterm = w.has_zterm ? w.colzterm.p : nullptr;
     g.y = y_dev;
+    g.wt = w.kmajor.p;
     const dim3 grid((N + kGemmBN - 1) / kGemmBN, m_pad / kGemmBM);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (kernel_ms) { CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventRecord(e0, g_stream)); }
     for (int r = 0; r < std::max(reps, 1); ++r) {
-        gemm_i8_tc_kernel<<<grid, kGemmThreads, kGemmSmemBytes, g_stream>>>(map_a, map_b, g);
+        gemm_i8_tc_kernel<<<grid, kGemmThreads, kGemmSmemBytes, g_stream>>>(map_a, g);
         ++g_launches;
     }
     CK(cudaGetLastError());
@@ -980,15 +981,11 @@ int gemm_q_dev(QWeight& w, const float* x_dev, float* y_dev, int M, float* kerne
 // One GEMM of the prefill path: activations are already digit planes; no host synchronisation.
 // split factor of the 32-row GEMM: (N / 128) * S CTAs should fill the SMs in whole waves, with >= 6 k-steps per CTA
 int small_gemm_splits(int tiles, int ksteps) {
-    if (tiles * 10 >= g_num_sms * 6) return 1;   // >= 0.6 CTAs per SM already (two fit): splitting only adds atomics
-    int best = 1;
-    double best_eff = 0.0;
-    for (int s = 1; s <= 8 && ksteps / s >= 6; ++s) {
-        const double waves = (double)tiles * s / (2 * g_num_sms);   // two CTAs per SM
-        const double eff = waves / std::ceil(waves);
-        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
-    }
-    return best;
+    // One CTA per SM, and a CTA's time is its k-loop (a serial chain of TMA round trips) plus, when split, ~10 us of
+    // atomics + fix-up: splitting pays only for long k-loops on few tiles (the down projection).
+    if (ksteps <= 48 || tiles * 2 > g_num_sms) return 1;
+    int s = std::min(g_num_sms / tiles, ksteps / 24);
+    return std::max(1, std::min(s, 8));
 }
 int launch_small_gemm(Model& m, QWeight& w, int m_pad, const GemmArgs& g) {
     static bool attr = false;
@@ -998,12 +995,9 @@ int launch_small_gemm(Model& m, QWeight& w, int m_pad, const GemmArgs& g) {
     }
     const int tiles = (w.L.N + kGemmBN - 1) / kGemmBN;
     if (m.pf_ws.n < (size_t)w.n_pad * kSmallRows || m.pf_cnt.n < (size_t)tiles) return fail("internal: split-K workspace too small");
-    CUtensorMap map_a, map_b;
-    TRY(make_tmap_u8_2d(&map_a, m.pf_planes.p, (uint64_t)w.k_pad, (uint64_t)3 * m_pad, kSmallRows));
-    TRY(make_tmap_u8_2d(&map_b, w.kmajor.p, (uint64_t)w.k_pad, (uint64_t)w.n_pad));
-    SplitKArgs sk{m.pf_ws.p, m.pf_cnt.p, w.n_pad};
+    SplitKArgs sk{reinterpret_cast<const uint8_t*>(m.pf_planes.p), m.pf_ws.p, m.pf_cnt.p, w.n_pad};
     const int S = small_gemm_splits(tiles, w.k_pad / kGemmBK);
-    gemm_i8_tc_small_kernel<<<dim3(tiles, S), kSmallThreads, kSmallSmemBytes, g_stream>>>(map_a, map_b, g, sk);
+    gemm_i8_tc_small_kernel<<<dim3(tiles, S), kSmallThreads, kSmallSmemBytes, g_stream>>>(g, sk);
     return 0;
 }
 int pf_gemm(Model& m, QWeight& w, int M, int m_pad, float* y, const float* resid) {
@@ -1019,17 +1013,17 @@ int pf_gemm(Model& m, QWeight& w, int M, int m_pad, float* y, const float* resid
     g.colzterm = w.has_zterm ? w.colzterm.p : nullptr;
     g.y = y;
     g.resid = resid;
-    if (M <= kSmallRows && !getenv("TURBOINFER_B200_NO_SMALL_GEMM")) {   // batched decode: 32-row tiles, every SM streams weights
+    g.wt = w.kmajor.p;
+    if (M <= kSmallRows && m.pf_small_layout) {   // batched decode: 32-row tiles, every SM streams weights
         TRY(launch_small_gemm(m, w, m_pad, g));
         ++g_launches;
         CK(cudaGetLastError());
         return 0;
     }
-    CUtensorMap map_a, map_b;
+    CUtensorMap map_a;
     TRY(make_tmap_u8_2d(&map_a, m.pf_planes.p, (uint64_t)w.k_pad, (uint64_t)3 * m_pad));
-    TRY(make_tmap_u8_2d(&map_b, w.kmajor.p, (uint64_t)w.k_pad, (uint64_t)w.n_pad));
     const dim3 grid((w.L.N + kGemmBN - 1) / kGemmBN, m_pad / kGemmBM);
-    gemm_i8_tc_kernel<<<grid, kGemmThreads, kGemmSmemBytes, g_stream>>>(map_a, map_b, g);
+    gemm_i8_tc_kernel<<<grid, kGemmThreads, kGemmSmemBytes, g_stream>>>(map_a, g);
     ++g_launches;
     CK(cudaGetLastError());
     return 0;
@@ -1038,8 +1032,9 @@ int pf_digits(Model& m, const float* x, const float* norm_w, int M, int K, int m
     // planes of rows >= M and columns >= K stay zero: the buffer is cleared when it is (re)allocated and only rows < M,
     // columns < k_pad are written -- k_pad differs per weight, so clear the tail columns explicitly
     // (the 32-row GEMM of the batched decode never reads rows it does not also ignore: nothing to clear there)
-    if (M > kSmallRows) CK(cudaMemsetAsync(m.pf_planes.p, 0, (size_t)3 * m_pad * k_pad, g_stream));
-    rmsnorm_digits_kernel<<<M, M > kSmallRows ? 256 : 1024, (size_t)K * sizeof(float), g_stream>>>(x, norm_w, m.cfg.rms_eps, M, K, m_pad, k_pad, m.pf_planes.p, m.pf_sx.p, m.pf_sxf.p);
+    m.pf_small_layout = false;
+    CK(cudaMemsetAsync(m.pf_planes.p, 0, (size_t)3 * m_pad * k_pad, g_stream));
+    rmsnorm_digits_kernel<<<M, 256, (size_t)K * sizeof(float), g_stream>>>(x, norm_w, m.cfg.rms_eps, M, K, m_pad, k_pad, m.pf_planes.p, m.pf_sx.p, m.pf_sxf.p);
     ++g_launches;
     CK(cudaGetLastError());
     return 0;
@@ -1140,6 +1135,7 @@ int batch_digits(Model& m, const float* x, const float* gu, const float* norm_w,
     const bool small = K % 4 == 0 && k_pad <= 4 * kDigitsThreads * kDigitsVecs;
     if (small && B <= kSmallRows) {
         rmsnorm_digits_small_kernel<<<B, kDigitsThreads, 0, g_stream>>>(x, gu, norm_w, m.cfg.rms_eps, K, m_pad, k_pad, m.pf_planes.p, m.pf_sx.p, m.pf_sxf.p);
+        m.pf_small_layout = true;
         ++g_launches;
         CK(cudaGetLastError());
         return 0;

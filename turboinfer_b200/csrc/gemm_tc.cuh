@@ -39,6 +39,7 @@ struct GemmArgs {
     const float* colzterm;  // [N] or nullptr
     float* y;               // [M][N]
     const float* resid;     // optional [M][N] added to the result (may alias y): the residual connections of the decoder
+    const uint8_t* wt;      // weights, tile-major pre-swizzled (wtile_offset)
 };
 
 // ---- activations -> digit planes [3][m_pad][k_pad] (K-major rows), one block per row ------------------------
@@ -61,9 +62,11 @@ __global__ void gemm_digits_kernel(const float* x, int M, int K, int m_pad, int 
     for (int k = threadIdx.x; k < k_pad; k += blockDim.x) {
         const int f = k < K ? __float2int_rn(xr[k] * inv_s) : 0;
         sxf += f;
-        planes[((size_t)0 * m_pad + row) * k_pad + k] = (int8_t)(f & 0xFF);
-        planes[((size_t)1 * m_pad + row) * k_pad + k] = (int8_t)((f >> 8) & 0xFF);
-        planes[((size_t)2 * m_pad + row) * k_pad + k] = (int8_t)((f >> 16) & 0xFF);
+        // signed digits, f = d2*65536 + d1*256 + d0 with every digit in [-128, 127]: the bytes of f + 0x808080, xor 0x80
+        const int u = f + 0x808080;
+        planes[((size_t)0 * m_pad + row) * k_pad + k] = (int8_t)((u & 0xFF) ^ 0x80);
+        planes[((size_t)1 * m_pad + row) * k_pad + k] = (int8_t)(((u >> 8) & 0xFF) ^ 0x80);
+        planes[((size_t)2 * m_pad + row) * k_pad + k] = (int8_t)(((u >> 16) & 0xFF) ^ 0x80);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sxf += __shfl_xor_sync(0xffffffffu, sxf, o);
@@ -77,7 +80,19 @@ __global__ void gemm_digits_kernel(const float* x, int M, int K, int m_pad, int 
     }
 }
 
-// ---- packed streaming layout -> K-major bytes Wk[n_pad][k_pad] (the B operand), same thread mapping as unpack_kernel ----
+// ---- the B operand in HBM: tile-major, pre-swizzled ---------------------------------------------------------------
+// A weight tile of a k-step (128 columns x 128 B of k) is stored as the exact 16 KiB SWIZZLE_128B image the MMA reads from
+// shared memory, tiles ordered [column tile][k-step]: one 1-D bulk copy per tile and k-step.  (A TMA box over a row-major
+// [N][K] copy fetches 128 separate 128-byte rows 4 KiB apart; streamed once from HBM that was bound by the TMA request
+// rate at ~30 GB/s per SM -- measured, ~1 us per k-step whatever the pipeline depth.)
+// SWIZZLE_128B: inside every 8-row x 128-byte atom the 16-byte chunk c of row r sits at chunk position c ^ (r & 7).
+TIB_HD size_t sw128_offset(int row, int byte) {   // inside a tile whose rows are 128 B
+    return (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128 + (size_t)(((byte >> 4) ^ (row & 7)) << 4) + (byte & 15);
+}
+TIB_HD size_t wtile_offset(int n, int k, int k_pad) {
+    return ((size_t)(n / kGemmBN) * (k_pad / kGemmBK) + k / kGemmBK) * kGemmTileBytes + sw128_offset(n % kGemmBN, k % kGemmBK);
+}
+// packed streaming layout -> tile-major bytes, same thread mapping as unpack_kernel
 __global__ void unpack_kmajor_kernel(const uint8_t* packed, QLayout L, int k_pad, uint8_t* wk) {
     const Slab slab = make_slab(L, blockIdx.x);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -90,7 +105,7 @@ __global__ void unpack_kmajor_kernel(const uint8_t* packed, QLayout L, int k_pad
             const int n = slab.col0 + 16 * grp + row, k = chunk * L.kc + ki * kik + kk;
             if (k >= k_pad) continue;
             // INT4: u = q + woff (0..15); INT8: two's complement q
-            wk[(size_t)n * k_pad + k] = (uint8_t)(L.bits == 4 ? (word >> (4 * i)) & 0xFu : (word >> (8 * i)) & 0xFFu);
+            wk[wtile_offset(n, k, k_pad)] = (uint8_t)(L.bits == 4 ? (word >> (4 * i)) & 0xFu : (word >> (8 * i)) & 0xFFu);
         }
     });
 }
@@ -132,7 +147,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int a_signed, int b_signed,
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GemmArgs g) {
+gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const GemmArgs g) {
     extern __shared__ uint8_t gsm_raw[];
     const uint32_t base = (smem_u32(gsm_raw) + 1023u) & ~1023u;
     uint8_t* tiles = gsm_raw + (base - smem_u32(gsm_raw));
@@ -166,12 +181,12 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 mbar_arrive_expect_tx(&full[st], kGemmStageBytes);
                 uint8_t* sbase = tiles + (size_t)st * kGemmStageBytes;
                 for (int d = 0; d < 3; ++d) tma_load_2d(sbase + d * kGemmTileBytes, &map_a, kb * kGemmBK, d * g.m_pad + mb * kGemmBM, &full[st]);
-                tma_load_2d(sbase + 3 * kGemmTileBytes, &map_b, kb * kGemmBK, nb * kGemmBN, &full[st]);
+                bulk_g2s(sbase + 3 * kGemmTileBytes, g.wt + ((size_t)nb * KB + kb) * kGemmTileBytes, kGemmTileBytes, &full[st]);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t id_u = umma_idesc_i8(0, g.a_signed_b), id_s = umma_idesc_i8(1, g.a_signed_b);
+            const uint32_t id_s = umma_idesc_i8(1, g.a_signed_b);   // A = signed digit plane
             for (int kb = 0; kb < KB; ++kb) {
                 const int st = kb % kGemmStages, use = kb / kGemmStages;
                 mbar_wait(&full[st], use & 1);
@@ -183,7 +198,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
                         const uint64_t adesc = umma_desc_sw128(sbase + d * kGemmTileBytes + k4 * 32);
-                        tc_mma_i8(tmem + d * kGemmBN, adesc, bdesc, d == 2 ? id_s : id_u, (kb | k4) != 0 ? 1u : 0u);
+                        tc_mma_i8(tmem + d * kGemmBN, adesc, bdesc, id_s, (kb | k4) != 0 ? 1u : 0u);
                     }
                 }
                 tc_commit(&empty[st]);   // the stage may be refilled once these MMAs have read it
@@ -261,22 +276,30 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 // With a handful of rows the kernel above would spend 128-row MMAs and 48 KiB of (mostly zero) activation tiles on 32 live
 // rows.  Here the roles are swapped: the MMA's M side (128 rows) are 128 WEIGHT COLUMNS, its N side (32) are the batch
 // rows, D[128 x 32] per digit plane (96 TMEM columns):
-//   * per k-step a CTA loads 16 KiB of weights and the 32 live rows of each digit plane (3 x 4 KiB -- the same bytes for
-//     every CTA, an L2 broadcast);
+//   * per k-step a CTA loads 16 KiB of weights and the 32 live rows of each digit plane (12 KiB -- the same bytes for
+//     every CTA, an L2 broadcast), both stored as ready-made swizzled tile images and fetched with 1-D bulk copies;
 //   * the tensor work is 4x smaller than with padded rows, and the epilogue has all four warps busy with coalesced stores
 //     (lane = weight column);
+//   * 7 stages of 28 KiB: what bounds a CTA is the chain of TMA round trips of its k-loop (measured: with 3 stages a
+//     32-step loop took 21 us whatever else the chip was doing), so the ring is as deep as shared memory allows;
 //   * split-K: grid (N / 128, S); CTA (n, s) multiplies k-steps [s KB / S, (s + 1) KB / S).  The partial sums are exact
 //     integers, so they are combined with 64-bit integer atomics in a workspace (order-independent: bit-identical to
 //     S = 1); the CTA that arrives last on the tile's counter applies offset, scales and residual, stores the tile and
 //     leaves workspace and counter zeroed for the next GEMM.  S is chosen on the host for GEMMs with few column tiles.
 // warps 0..3: epilogue (TMEM lanes 32w.. = weight columns), warp 4: TMEM allocation + MMA issue, warp 5: TMA producer.
-constexpr int kSmallRows = 32, kSmallThreads = 192, kSmallStages = 3;   // 3 stages = 84 KiB: two CTAs per SM
+constexpr int kSmallRows = 32, kSmallThreads = 192, kSmallStages = 7;   // 196 KiB in flight per CTA: a CTA's k-loop is a serial chain of TMA round trips
 constexpr int kSmallPlaneBytes = kSmallRows * kGemmBK;                       // 4 KiB
 constexpr int kSmallStageBytes = kGemmTileBytes + 3 * kSmallPlaneBytes;      // weights 16 KiB + digits 12 KiB
 constexpr int kSmallTmemCols = 128;                                          // >= 3 x 32, power of two
 constexpr size_t kSmallSmemBytes = (size_t)kSmallStages * kSmallStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * kSmallRows * 8;
 
+// The digit planes of the 32 rows for this kernel: [k-step][96 rows = 32 d + m][128 B], each k-step's 12 KiB the exact
+// SWIZZLE_128B image of the three plane tiles (one bulk copy per k-step)
+TIB_HD size_t xtile_offset(int d, int m, int k) {
+    return (size_t)(k / kGemmBK) * 3 * 4096 + sw128_offset(d * 32 + m, k % kGemmBK);
+}
 struct SplitKArgs {
+    const uint8_t* xt;        // digit planes in xtile_offset order
     unsigned long long* ws;   // [32][n_pad] partial integer sums
     unsigned int* cnt;        // [N / 128] arrivals per tile
     int n_pad;
@@ -286,8 +309,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8_mn(int a_signed, int b_sign
     return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(kSmallThreads, 2)
-gemm_i8_tc_small_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const GemmArgs g, const SplitKArgs sk) {
+__global__ void __launch_bounds__(kSmallThreads, 1)
+gemm_i8_tc_small_kernel(const GemmArgs g, const SplitKArgs sk) {
     extern __shared__ uint8_t gsm_raw[];
     const uint32_t base = (smem_u32(gsm_raw) + 1023u) & ~1023u;
     uint8_t* tiles = gsm_raw + (base - smem_u32(gsm_raw));
@@ -302,6 +325,10 @@ gemm_i8_tc_small_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     const int nb = blockIdx.x, S = gridDim.y;
     const int KB = g.k_pad / kGemmBK;
     const int kb0 = (int)((long long)blockIdx.y * KB / S), kb1 = (int)((long long)(blockIdx.y + 1) * KB / S);
+    // Every CTA reads the SAME digit-plane tiles; marching through k in lockstep would make all of them hit the same L2
+    // lines at the same moment (measured: ~1.2 us per k-step whatever the pipeline depth).  Each column tile therefore
+    // starts its k-loop at a different offset and wraps around -- integer sums do not care about the order.
+    const int nk = kb1 - kb0, rot = nk > 0 ? (int)((blockIdx.x * 7u) % (unsigned)nk) : 0;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kSmallStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -325,32 +352,33 @@ gemm_i8_tc_small_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
     if (warp == 5) {
         if (lane == 0) {
             int st = 0, par = 1;   // a fresh mbarrier counts its "previous" phase as complete
-            for (int kb = kb0; kb < kb1; ++kb) {
+            for (int i = 0; i < nk; ++i) {
+                const int kb = kb0 + (i + rot < nk ? i + rot : i + rot - nk);
                 mbar_wait(&empty[st], par);
                 mbar_arrive_expect_tx(&full[st], kSmallStageBytes);
                 uint8_t* sbase = tiles + (size_t)st * kSmallStageBytes;
-                tma_load_2d(sbase, &map_w, kb * kGemmBK, nb * kGemmBN, &full[st]);
-                for (int d = 0; d < 3; ++d) tma_load_2d(sbase + kGemmTileBytes + d * kSmallPlaneBytes, &map_x, kb * kGemmBK, d * g.m_pad, &full[st]);
+                bulk_g2s(sbase, g.wt + ((size_t)nb * KB + kb) * kGemmTileBytes, kGemmTileBytes, &full[st]);
+                bulk_g2s(sbase + kGemmTileBytes, sk.xt + (size_t)kb * 3 * kSmallPlaneBytes, 3 * kSmallPlaneBytes, &full[st]);
                 if (++st == kSmallStages) { st = 0; par ^= 1; }
             }
         }
     } else if (warp == 4) {
         if (lane == 0) {
-            // A = weights (unsigned nibbles-in-bytes for INT4, signed for INT8), B = digit plane (0, 1 unsigned; 2 signed)
-            const uint32_t id_u = umma_idesc_i8_mn(g.a_signed_b, 0, kGemmBN, kSmallRows), id_s = umma_idesc_i8_mn(g.a_signed_b, 1, kGemmBN, kSmallRows);
+            // A = weights (unsigned nibbles-in-bytes for INT4, signed for INT8); B = ALL THREE signed digit planes at once:
+            // their 32-row tiles are contiguous in the stage, so one MMA with N = 96 fills the three accumulators
+            // (columns 32 d + m).  A tcgen05.mma this small is latency-bound (~0.1 us each, measured): three per k32
+            // step made a k-step cost 1.2 us.
+            const uint32_t id = umma_idesc_i8_mn(g.a_signed_b, 1, kGemmBN, 3 * kSmallRows);
             int st = 0, par = 0;
-            for (int kb = kb0; kb < kb1; ++kb) {
+            for (int i = 0; i < nk; ++i) {
                 mbar_wait(&full[st], par);
                 tc_fence_after();
                 const uint32_t sbase = base + st * kSmallStageBytes;
 #pragma unroll
                 for (int k4 = 0; k4 < kGemmBK / 32; ++k4) {
                     const uint64_t wdesc = umma_desc_sw128(sbase + k4 * 32);
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        const uint64_t xdesc = umma_desc_sw128(sbase + kGemmTileBytes + d * kSmallPlaneBytes + k4 * 32);
-                        tc_mma_i8(tmem + d * kSmallRows, wdesc, xdesc, d == 2 ? id_s : id_u, (kb != kb0 || k4 != 0) ? 1u : 0u);
-                    }
+                    const uint64_t xdesc = umma_desc_sw128(sbase + kGemmTileBytes + k4 * 32);
+                    tc_mma_i8(tmem, wdesc, xdesc, id, (i != 0 || k4 != 0) ? 1u : 0u);
                 }
                 tc_commit(&empty[st]);
                 if (++st == kSmallStages) { st = 0; par ^= 1; }

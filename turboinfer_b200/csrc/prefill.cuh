@@ -52,9 +52,11 @@ __global__ void rmsnorm_digits_kernel(const float* x, const float* w, float eps,
     for (int k = tid; k < k_pad; k += blockDim.x) {
         const int f = k < K ? __float2int_rn(rowbuf[k] * inv_s) : 0;
         sxf += f;
-        planes[((size_t)0 * m_pad + row) * k_pad + k] = (int8_t)(f & 0xFF);
-        planes[((size_t)1 * m_pad + row) * k_pad + k] = (int8_t)((f >> 8) & 0xFF);
-        planes[((size_t)2 * m_pad + row) * k_pad + k] = (int8_t)((f >> 16) & 0xFF);
+        // signed digits, f = d2*65536 + d1*256 + d0 with every digit in [-128, 127]: the bytes of f + 0x808080, xor 0x80
+        const int u = f + 0x808080;
+        planes[((size_t)0 * m_pad + row) * k_pad + k] = (int8_t)((u & 0xFF) ^ 0x80);
+        planes[((size_t)1 * m_pad + row) * k_pad + k] = (int8_t)(((u >> 8) & 0xFF) ^ 0x80);
+        planes[((size_t)2 * m_pad + row) * k_pad + k] = (int8_t)(((u >> 16) & 0xFF) ^ 0x80);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sxf += __shfl_xor_sync(0xffffffffu, sxf, o);
