@@ -995,7 +995,7 @@ int launch_small_gemm(Model& m, QWeight& w, int m_pad, const GemmArgs& g) {
     }
     const int tiles = (w.L.N + kGemmBN - 1) / kGemmBN;
     if (m.pf_ws.n < (size_t)w.n_pad * kSmallRows || m.pf_cnt.n < (size_t)tiles) return fail("internal: split-K workspace too small");
-    SplitKArgs sk{reinterpret_cast<const uint8_t*>(m.pf_planes.p), m.pf_ws.p, m.pf_cnt.p, w.n_pad};
+    SplitKArgs sk{reinterpret_cast<const uint8_t*>(m.pf_planes.p), m.pf_ws.p, m.pf_cnt.p, w.n_pad, nullptr};
     const int S = small_gemm_splits(tiles, w.k_pad / kGemmBK);
     gemm_i8_tc_small_kernel<<<dim3(tiles, S), kSmallThreads, kSmallSmemBytes, g_stream>>>(g, sk);
     return 0;
@@ -1976,6 +1976,13 @@ int ti_b200_generate_batch_greedy(ti_model_t h, const int32_t* prompts, int32_t 
     if (!attr) {
         CK(cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
         CK(cudaFuncSetAttribute(rmsnorm_digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        // every kernel of the step asks for the same L1 / shared-memory split as the GEMM (which needs nearly all of it):
+        // a kernel that wants a different carve-out than its predecessor makes the SMs reconfigure before it can start
+        const void* fns[] = {(const void*)gemm_i8_tc_small_kernel, (const void*)gemm_i8_tc_kernel, (const void*)rmsnorm_digits_small_kernel,
+                             (const void*)rmsnorm_digits_kernel, (const void*)rope_kv_batch_kernel, (const void*)attn_partial_kernel,
+                             (const void*)attn_combine_kernel, (const void*)argmax_rows_kernel, (const void*)batch_advance_kernel,
+                             (const void*)embed_rows_kernel, (const void*)swiglu_rows_kernel, (const void*)relu_rows_kernel};
+        for (const void* f : fns) CK(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
     // everything that allocates or launches set-up kernels happens before the step graphs are captured

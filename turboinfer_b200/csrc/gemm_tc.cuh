@@ -290,7 +290,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const GemmArgs g) {
 constexpr int kSmallRows = 32, kSmallThreads = 192, kSmallStages = 7;   // 196 KiB in flight per CTA: a CTA's k-loop is a serial chain of TMA round trips
 constexpr int kSmallPlaneBytes = kSmallRows * kGemmBK;                       // 4 KiB
 constexpr int kSmallStageBytes = kGemmTileBytes + 3 * kSmallPlaneBytes;      // weights 16 KiB + digits 12 KiB
-constexpr int kSmallTmemCols = 128;                                          // >= 3 x 32, power of two
+constexpr int kSmallTmemCols = 512;                                          // four accumulator sets of 3 x 32 columns
 constexpr size_t kSmallSmemBytes = (size_t)kSmallStages * kSmallStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * kSmallRows * 8;
 
 // The digit planes of the 32 rows for this kernel: [k-step][96 rows = 32 d + m][128 B], each k-step's 12 KiB the exact
@@ -303,6 +303,7 @@ struct SplitKArgs {
     unsigned long long* ws;   // [32][n_pad] partial integer sums
     unsigned int* cnt;        // [N / 128] arrivals per tile
     int n_pad;
+    long long* dbg;           // optional (microbenchmark): SM-clock stamps of CTA (0, 0)
 };
 
 __host__ __device__ constexpr uint32_t umma_idesc_i8_mn(int a_signed, int b_signed, int m, int n) {
@@ -349,46 +350,72 @@ gemm_i8_tc_small_kernel(const GemmArgs g, const SplitKArgs sk) {
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
 
+    // Both pipeline loops poll mbarriers, and a poll costs ~0.1-0.2 us even when the phase is long complete (measured,
+    // scripts/microbench7.cu) -- as much as a whole 28 KiB k-step should take.  So four lanes probe the next four stages
+    // at once (lane 0 blocking, the others non-blocking) and lane 0 then handles every consecutive stage that is ready.
+    auto probe4 = [&](uint64_t* bars, int i, int phase_flip) -> int {
+        const int j = i + lane;
+        bool ok = false;
+        if (lane < 4 && j < nk) {
+            const int stj = j % kSmallStages;
+            const uint32_t parj = (uint32_t)((j / kSmallStages) & 1) ^ (uint32_t)phase_flip;
+            ok = lane == 0 ? mbar_try_wait(&bars[stj], parj) : mbar_test_wait(&bars[stj], parj);
+        }
+        const unsigned int mask = __ballot_sync(0xffffffffu, ok) & 0xFu;
+        return __ffs(~mask) - 1;   // consecutive ready stages from i on (0..4)
+    };
     if (warp == 5) {
-        if (lane == 0) {
-            int st = 0, par = 1;   // a fresh mbarrier counts its "previous" phase as complete
-            for (int i = 0; i < nk; ++i) {
-                const int kb = kb0 + (i + rot < nk ? i + rot : i + rot - nk);
-                mbar_wait(&empty[st], par);
-                mbar_arrive_expect_tx(&full[st], kSmallStageBytes);
-                uint8_t* sbase = tiles + (size_t)st * kSmallStageBytes;
-                bulk_g2s(sbase, g.wt + ((size_t)nb * KB + kb) * kGemmTileBytes, kGemmTileBytes, &full[st]);
-                bulk_g2s(sbase + kGemmTileBytes, sk.xt + (size_t)kb * 3 * kSmallPlaneBytes, 3 * kSmallPlaneBytes, &full[st]);
-                if (++st == kSmallStages) { st = 0; par ^= 1; }
+        int i = 0;
+        while (i < nk) {
+            const int nready = probe4(empty, i, 1);   // a fresh mbarrier counts its "previous" phase as complete
+            if (lane == 0) {
+                for (int q = 0; q < nready; ++q) {
+                    const int ii = i + q, st = ii % kSmallStages;
+                    const int kb = kb0 + (ii + rot < nk ? ii + rot : ii + rot - nk);
+                    if (sk.dbg && blockIdx.x == 0 && blockIdx.y == 0 && ii < 40) sk.dbg[64 + ii] = clock64();
+                    mbar_arrive_expect_tx(&full[st], kSmallStageBytes);
+                    uint8_t* sbase = tiles + (size_t)st * kSmallStageBytes;
+                    bulk_g2s(sbase, g.wt + ((size_t)nb * KB + kb) * kGemmTileBytes, kGemmTileBytes, &full[st]);
+                    bulk_g2s(sbase + kGemmTileBytes, sk.xt + (size_t)kb * 3 * kSmallPlaneBytes, 3 * kSmallPlaneBytes, &full[st]);
+                }
             }
+            __syncwarp();
+            i += nready;
         }
     } else if (warp == 4) {
-        if (lane == 0) {
-            // A = weights (unsigned nibbles-in-bytes for INT4, signed for INT8); B = ALL THREE signed digit planes at once:
-            // their 32-row tiles are contiguous in the stage, so one MMA with N = 96 fills the three accumulators
-            // (columns 32 d + m).  A tcgen05.mma this small is latency-bound (~0.1 us each, measured): three per k32
-            // step made a k-step cost 1.2 us.
-            const uint32_t id = umma_idesc_i8_mn(g.a_signed_b, 1, kGemmBN, 3 * kSmallRows);
-            int st = 0, par = 0;
-            for (int i = 0; i < nk; ++i) {
-                mbar_wait(&full[st], par);
+        // A = weights (unsigned nibbles-in-bytes for INT4, signed for INT8); B = ALL THREE signed digit planes at once:
+        // their 32-row tiles are contiguous in the stage, so one MMA with N = 96 fills the three accumulators
+        // (columns 32 d + m) of the k4 step's accumulator set.
+        const uint32_t id = umma_idesc_i8_mn(g.a_signed_b, 1, kGemmBN, 3 * kSmallRows);
+        int i = 0;
+        while (i < nk) {
+            const int nready = probe4(full, i, 0);
+            if (lane == 0 && nready > 0) {
                 tc_fence_after();
-                const uint32_t sbase = base + st * kSmallStageBytes;
+                for (int q = 0; q < nready; ++q) {
+                    const int ii = i + q, st = ii % kSmallStages;
+                    if (sk.dbg && blockIdx.x == 0 && blockIdx.y == 0 && ii < 40) sk.dbg[128 + ii] = clock64();
+                    const uint32_t sbase = base + st * kSmallStageBytes;
 #pragma unroll
-                for (int k4 = 0; k4 < kGemmBK / 32; ++k4) {
-                    const uint64_t wdesc = umma_desc_sw128(sbase + k4 * 32);
-                    const uint64_t xdesc = umma_desc_sw128(sbase + kGemmTileBytes + k4 * 32);
-                    tc_mma_i8(tmem, wdesc, xdesc, id, (i != 0 || k4 != 0) ? 1u : 0u);
+                    for (int k4 = 0; k4 < kGemmBK / 32; ++k4) {
+                        const uint64_t wdesc = umma_desc_sw128(sbase + k4 * 32);
+                        const uint64_t xdesc = umma_desc_sw128(sbase + kGemmTileBytes + k4 * 32);
+                        // one accumulator set per k4: four independent accumulation chains; the epilogue adds the sets
+                        tc_mma_i8(tmem + k4 * 3 * kSmallRows, wdesc, xdesc, id, ii != 0 ? 1u : 0u);
+                    }
+                    tc_commit(&empty[st]);   // the stage may be refilled once these MMAs have read it
                 }
-                tc_commit(&empty[st]);
-                if (++st == kSmallStages) { st = 0; par ^= 1; }
             }
-            tc_commit(tmem_full);
+            __syncwarp();
+            i += nready;
         }
+        if (lane == 0) tc_commit(tmem_full);
     } else {
         // epilogue, warps 0..3: TMEM lane = weight column of the tile, TMEM column = batch row (per digit plane)
+        if (sk.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) sk.dbg[0] = clock64();
         mbar_wait(tmem_full, 0);
         tc_fence_after();
+        if (sk.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) sk.dbg[1] = clock64();
         const int n = nb * kGemmBN + warp * 32 + lane;
         const bool n_ok = n < g.N;
         const float cs = n_ok ? g.colscale[n] : 0.f;
@@ -406,14 +433,22 @@ gemm_i8_tc_small_kernel(const GemmArgs g, const SplitKArgs sk) {
             uint32_t a[3][16];
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(d * kSmallRows + m0);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                    : "=r"(a[d][0]), "=r"(a[d][1]), "=r"(a[d][2]), "=r"(a[d][3]), "=r"(a[d][4]), "=r"(a[d][5]), "=r"(a[d][6]), "=r"(a[d][7]),
-                      "=r"(a[d][8]), "=r"(a[d][9]), "=r"(a[d][10]), "=r"(a[d][11]), "=r"(a[d][12]), "=r"(a[d][13]), "=r"(a[d][14]), "=r"(a[d][15])
-                    : "r"(taddr));
+#pragma unroll
+                for (int i = 0; i < 16; ++i) a[d][i] = 0u;
+#pragma unroll
+                for (int set = 0; set < kGemmBK / 32; ++set) {
+                    uint32_t b[16];
+                    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(set * 3 * kSmallRows + d * kSmallRows + m0);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]),
+                          "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) a[d][i] += b[i];   // the four k4 chains of this digit plane
+                }
             }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int m = m0 + i;
@@ -448,6 +483,7 @@ gemm_i8_tc_small_kernel(const GemmArgs g, const SplitKArgs sk) {
                 }
             }
         }
+        if (sk.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) sk.dbg[2] = clock64();
         tc_fence_before();
     }
     __syncthreads();
