@@ -483,7 +483,7 @@ __device__ __forceinline__ ConsumePlan make_consume_plan(const QLayout& L, const
 }
 template <int BITS, int DBG = 0>
 __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, RingPos& it, const ConsumePlan& pl,
-                                             int warp, int lane, long long* dbg = nullptr) {
+                                             int warp, int lane, long long* dbg = nullptr, bool ready0 = false) {
     const QLayout& L = a.L;
     const int S = a.stages;
     const int C = L.nchunks, nrounds = slab.rounds;
@@ -518,7 +518,9 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
         acc.clear();
         dirty = false;
     };
-    bool ready = false;   // the NEXT stage's barrier is probed while this stage is being multiplied
+    // the NEXT stage's barrier is probed while this stage is being multiplied; the first one may have been probed by the
+    // caller during its prologue (polling an mbarrier costs 0.1-0.2 us even when its phase is long complete)
+    bool ready = ready0;
     for (int r = 0; r < nrounds; ++r, it.advance(S)) {
         const uint32_t st = it.st, par = it.par;
         const bool have = r < my_nq;

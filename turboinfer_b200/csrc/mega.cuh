@@ -680,9 +680,12 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                     // produced x), or from the precomputed statistics of the embedding row
                     const XScale xsc = from_emb ? make_xscale(m.emb_stats[token], g.norm_w != nullptr, g.L.K, g.rms_eps)
                                                 : XScale{sm.red[0], sm.red[1], sm.red[2]};
+                    // the first ring stage of this phase has usually landed long ago: probe its barrier now, so that the
+                    // poll's latency hides behind the conversion instead of opening the main loop
+                    const bool ready0 = slab.rounds > 0 && mbar_test_wait(&sm.full[it.st], it.par);
                     const float s_x = gemv_stage_x_lean<BITS>(g, x, sm, slab, !from_emb, xsc, xpre, (m.dbg_flags & 1) != 0, tid, lane, stamp ? ts + 13 : nullptr);
                     if (stamp) ts[2] = clock64();
-                    gemv_consume<BITS>(g, slab, sm, it, plan, warp, lane, stamp ? ts + 17 : nullptr);
+                    gemv_consume<BITS>(g, slab, sm, it, plan, warp, lane, stamp ? ts + 17 : nullptr, ready0);
                     if (stamp) ts[3] = clock64();
                     out_st = gemv_epilogue(g, slab, sm, s_x, resid, ctx, pre, tid, lane);
                 }
