@@ -17,10 +17,19 @@ ap.add_argument("--prompt", type=int, default=4)
 ap.add_argument("--new", type=int, default=256)
 ap.add_argument("--layers", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--tp", action="store_true", help="under torchrun: the ranks form one tensor-parallel group (NCCL all-reduce after o / down)")
 args = ap.parse_args()
-tb.init(0)
+rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+tp = world if (args.tp and world > 1) else 1
+tb.init(int(os.environ.get("LOCAL_RANK", "0")))
+if tp > 1:
+    import torch.distributed as dist
+    dist.init_process_group("gloo")
+    box = [tb.tp_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    tb.tp_init(world, rank, box[0])
 meta = SHAPES[args.shape] if not args.layers else meta_with_layers(SHAPES[args.shape], args.layers)
-m = tb.Model(meta, tb.Q_INT4 if args.qtype == "int4" else tb.Q_INT8, attn_mode=1, rope_mode=1, max_seq=args.prompt + args.new + 64)
+m = tb.Model(meta, tb.Q_INT4 if args.qtype == "int4" else tb.Q_INT8, attn_mode=1, rope_mode=1, max_seq=args.prompt + args.new + 64, tp=tp)
 m.load_synthetic()
 prompts = np.array([prompt_tokens(args.prompt, meta["vocab"], offset=b) for b in range(args.batch)], dtype=np.int32)
 l0 = tb.launch_count()
@@ -38,12 +47,16 @@ t_mid = args.prompt + args.new // 2
 kv = 2 * L * args.batch * t_mid * H * 4
 ms = float(np.median(dev))
 steps = args.new - 1
-out = {"metric": "decode_tokens_per_s", "value": args.batch * steps / (ms * 1e-3), "unit": "tokens/s", "n_gpus": 1,
+out = {"metric": "decode_tokens_per_s", "value": args.batch * steps / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world, "parallelism": f"tp{tp}" if tp > 1 else "single",
        "config": {"workload": f"{args.shape}-{args.qtype}-batch{args.batch}-decode{args.new}", "batch": args.batch, "prompt_tokens": args.prompt,
                   "new_tokens": args.new, "path": "tcgen05 INT8 GEMM (three digit planes) + flash-decoding attention per sequence, CUDA graph per step"},
        "ms_per_step": ms / steps, "e2e": {"value": args.batch * args.new / float(np.median(wall)), "unit": "tokens/s"},
        "step_bytes": {"weights_as_read_by_the_gemm": w_elems, "kv_mid_run": kv, "GBps": (w_elems + kv) / (ms / steps * 1e-3) / 1e9},
        "row0_equals_single_sequence_engine": bool(np.array_equal(toks[0][: len(single)], single)),
        "gpu_launches": tb.launch_count() - l0, "tokens_tail_row0": [int(x) for x in toks[0][-4:]]}
-print(json.dumps(out))
+if rank == 0:
+    print(json.dumps(out))
 m.free()
+if tp > 1:
+    dist.barrier()
+    dist.destroy_process_group()

@@ -24,16 +24,19 @@ for shape, layers, qt, n_new in cases:
         continue
     w = make_model(meta, norm_jitter=0.1)
     prompt = prompt_tokens(4, meta["vocab"])
+    prompts = np.array([prompt_tokens(4, meta["vocab"], offset=b) for b in range(5)], dtype=np.int32)   # batched decode, B = 5
     ref = tb.Model(meta, qt, attn_mode=1, rope_mode=1, max_seq=128).load(w)
     rt, rl, _ = ref.generate_greedy(prompt, n_new, want_logits=True)
+    rbt, rbl, _ = ref.generate_batch_greedy(prompts, 6, want_logits=True)
     ref.free()
     m = tb.Model(meta, qt, attn_mode=1, rope_mode=1, max_seq=128, tp=world).load(w)
     t0 = time.perf_counter()
     tt, tl, ms = m.generate_greedy(prompt, n_new, want_logits=True)
     dt = time.perf_counter() - t0
+    tbt, tbl, _ = m.generate_batch_greedy(prompts, 6, want_logits=True)
     m.free()
-    same = bool(np.array_equal(rt, tt))
-    err = float(rel_err_inf(tl, rl))
+    same = bool(np.array_equal(rt, tt)) and bool(np.array_equal(rbt, tbt))
+    err = max(float(rel_err_inf(tl, rl)), float(rel_err_inf(tbl, rbl)))
     ok &= same and err <= 1e-4
     print(json.dumps({"rank": rank, "case": f"{shape}/L{meta['layers']}/q{qt}", "tokens_equal": same, "logits_rel_err": err,
                       "tp_decode_ms_per_token": ms / max(1, n_new - 1)}), flush=True)

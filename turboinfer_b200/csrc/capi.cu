@@ -281,6 +281,7 @@ struct BatchState {
     DevBuf<int> out;                     // [B][n_new]
     DevBuf<int> pos_step;                // [0] tokens in every cache, [1] output column
     DevBuf<float> part_o, part_ml, logits;
+    DevBuf<float> ar;                    // tensor parallel: [B][H] partial output of a row-parallel GEMM, all-reduced in place
     cudaGraphExec_t graph[2] = {nullptr, nullptr};   // [0] step without sampling, [1] with lm_head + argmax
     const void* cap_scratch = nullptr;               // what the captured graphs were built against: the scratch buffers
     int cap_stride = 0;                              // ... and the row stride of `out`
@@ -1125,7 +1126,7 @@ int ensure_pf_scratch(Model& m, int M) {
 }
 
 bool batch_eligible(const Model& m) {
-    if (m.tp != 1 || m.cfg.compat_literal || m.cfg.rope_mode == 2 || !m.lm_head) return false;
+    if (m.cfg.compat_literal || m.cfg.rope_mode == 2 || !m.lm_head || (m.tp > 1 && (!g_comm || m.cfg.attn_mode != 1))) return false;
     for (auto& ly : m.layers) if (!(ly.qkv && ly.o && ly.gateup && ly.down)) return false;
     return true;
 }
@@ -1149,17 +1150,31 @@ int batch_digits(Model& m, const float* x, const float* gu, const float* norm_w,
 }
 
 // one lockstep step of all B sequences: tokens[b] -> KV append at *pos -> (sample: logits, argmax -> tokens[b], out)
+// row-parallel GEMM output of the batched step under tensor parallelism: partial [B][H] -> all-reduce (sum) -> x += partial
+int batch_allreduce_add(Model& m, BatchState& bs, int B) {
+    const size_t n = (size_t)B * m.cfg.hidden;
+    const ncclResult_t r = g_nccl.AllReduce(bs.ar.p, bs.ar.p, n, ncclFloat32, ncclSum, g_comm, g_stream);
+    if (r != ncclSuccess) return fail("ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+    elementwise_kernel<<<grid_for(n), 256, 0, g_stream>>>(m.pf_x.p, bs.ar.p, m.pf_x.p, n, EW_ADD);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
-    const int B = bs.B, H = m.cfg.hidden, I = std::max(m.cfg.inter, 1), V = m.cfg.vocab;
+    const int B = bs.B, H = m.cfg.hidden, V = m.cfg.vocab;
+    const int Hl = H / m.tp;   // tensor parallel: this rank's heads (q / k / v / attention width) -- SURVEY.md 8e
     const int m_pad = (B + kGemmBM - 1) / kGemmBM * kGemmBM;
     const int rope_dim = m.cfg.rope_mode == 1 ? H / m.cfg.heads : 0;
+    const bool tp = m.tp > 1;
     embed_rows_kernel<<<B, 256, 0, g_stream>>>(m.tok_emb.p, bs.tokens.p, m.pf_x.p, H);
     ++g_launches;
     for (size_t l = 0; l < m.layers.size(); ++l) {
         Layer& ly = m.layers[l];
+        const int Il = ly.down->L.K;   // this rank's share of the intermediate width
         TRY(batch_digits(m, m.pf_x.p, nullptr, ly.attn_norm.p, B, H, m_pad, ly.qkv->k_pad));
         TRY(pf_gemm(m, *ly.qkv, B, m_pad, m.pf_qkv.p, nullptr));
-        rope_kv_batch_kernel<<<B, 256, 0, g_stream>>>(m.pf_qkv.p, H, rope_dim, m.inv_freq.p, bs.pos_step.p, bs.k[l].p, bs.v[l].p, bs.tables.p,
+        rope_kv_batch_kernel<<<B, 256, 0, g_stream>>>(m.pf_qkv.p, Hl, rope_dim, m.inv_freq.p, bs.pos_step.p, bs.k[l].p, bs.v[l].p, bs.tables.p,
                                                        bs.pages_per_seq, m.page_tokens);
         AttnArgs a{};
         a.q = m.pf_qkv.p;
@@ -1169,7 +1184,7 @@ int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
         a.page_tokens = m.page_tokens;
         a.pos_ptr = bs.pos_step.p;
         a.t_bias = 1;
-        a.H = H;
+        a.H = Hl;
         a.D = m.attn_dim;
         a.heads = m.attn_heads;
         a.max_splits = bs.max_splits;
@@ -1178,26 +1193,36 @@ int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
         a.part_o = bs.part_o.p;
         a.part_ml = bs.part_ml.p;
         a.out = m.pf_attn.p;
-        a.zq = 3 * H;
-        a.zout = H;
+        a.zq = 3 * Hl;
+        a.zout = Hl;
         a.ztable = bs.pages_per_seq;
         a.zpart_o = (size_t)m.attn_heads * bs.max_splits * m.attn_dim;
         a.zpart_ml = (size_t)m.attn_heads * bs.max_splits * 2;
         attn_partial_kernel<<<dim3(m.attn_heads, bs.max_splits, B), kAttnThreads, m.attn_smem, g_stream>>>(a);
         attn_combine_kernel<<<dim3(m.attn_heads, 1, B), 256, 0, g_stream>>>(a);
         g_launches += 3;
-        TRY(batch_digits(m, m.pf_attn.p, nullptr, nullptr, B, H, m_pad, ly.o->k_pad));
-        TRY(pf_gemm(m, *ly.o, B, m_pad, m.pf_x.p, m.pf_x.p));
+        TRY(batch_digits(m, m.pf_attn.p, nullptr, nullptr, B, Hl, m_pad, ly.o->k_pad));
+        if (tp) {   // row-parallel: partial sums of all ranks, then the residual
+            TRY(pf_gemm(m, *ly.o, B, m_pad, bs.ar.p, nullptr));
+            TRY(batch_allreduce_add(m, bs, B));
+        } else {
+            TRY(pf_gemm(m, *ly.o, B, m_pad, m.pf_x.p, m.pf_x.p));
+        }
         TRY(batch_digits(m, m.pf_x.p, nullptr, ly.ffn_norm.p, B, H, m_pad, ly.gateup->k_pad));
         TRY(pf_gemm(m, *ly.gateup, B, m_pad, m.pf_gu.p, nullptr));
         if (ly.has_gate) {
-            TRY(batch_digits(m, nullptr, m.pf_gu.p, nullptr, B, I, m_pad, ly.down->k_pad));   // SwiGLU fused into the conversion
+            TRY(batch_digits(m, nullptr, m.pf_gu.p, nullptr, B, Il, m_pad, ly.down->k_pad));   // SwiGLU fused into the conversion
         } else {
-            relu_rows_kernel<<<grid_for((size_t)B * I), 256, 0, g_stream>>>(m.pf_gu.p, m.pf_act.p, (size_t)B * I);
+            relu_rows_kernel<<<grid_for((size_t)B * Il), 256, 0, g_stream>>>(m.pf_gu.p, m.pf_act.p, (size_t)B * Il);
             ++g_launches;
-            TRY(batch_digits(m, m.pf_act.p, nullptr, nullptr, B, I, m_pad, ly.down->k_pad));
+            TRY(batch_digits(m, m.pf_act.p, nullptr, nullptr, B, Il, m_pad, ly.down->k_pad));
         }
-        TRY(pf_gemm(m, *ly.down, B, m_pad, m.pf_x.p, m.pf_x.p));
+        if (tp) {
+            TRY(pf_gemm(m, *ly.down, B, m_pad, bs.ar.p, nullptr));
+            TRY(batch_allreduce_add(m, bs, B));
+        } else {
+            TRY(pf_gemm(m, *ly.down, B, m_pad, m.pf_x.p, m.pf_x.p));
+        }
     }
     if (sample) {
         TRY(batch_digits(m, m.pf_x.p, nullptr, m.out_norm.p, B, H, m_pad, m.lm_head->k_pad));
@@ -1966,7 +1991,7 @@ int ti_b200_generate_batch_greedy(ti_model_t h, const int32_t* prompts, int32_t 
     if (batch <= 0) return fail("batch must be >= 1");
     if (n_prompt <= 0) return fail("Input tokens cannot be empty");  // validate_input_tokens (:1409)
     if (n_new <= 0) return fail("n_new must be >= 1");
-    if (!batch_eligible(m)) return fail("generate_batch needs a complete, non-literal, single-GPU model (q/k/v/o, up/down, lm_head; rope per head or off)");
+    if (!batch_eligible(m)) return fail("generate_batch needs a complete, non-literal model (q/k/v/o, up/down, lm_head; rope per head or off)");
     const int B = batch, V = m.cfg.vocab, H = m.cfg.hidden;
     for (int i = 0; i < B * n_prompt; ++i)
         if (prompts[i] < 0 || prompts[i] >= V) return fail("token id %d out of range", prompts[i]);
@@ -1999,7 +2024,8 @@ int ti_b200_generate_batch_greedy(ti_model_t h, const int32_t* prompts, int32_t 
         bs.max_splits = std::max(1, std::min(m.max_splits, (2 * g_num_sms) / std::max(1, B * m.attn_heads)));
         bs.k.resize(m.layers.size());
         bs.v.resize(m.layers.size());
-        const size_t pool = (size_t)B * pages * m.page_tokens * H;
+        const size_t pool = (size_t)B * pages * m.page_tokens * (H / m.tp);   // a rank keeps the K / V rows of its own heads
+        if (m.tp > 1) TRY(bs.ar.alloc((size_t)B * H));
         for (size_t l = 0; l < m.layers.size(); ++l) { TRY(bs.k[l].alloc(pool)); TRY(bs.v[l].alloc(pool)); }
         std::vector<int> tab((size_t)B * pages);
         for (int b = 0; b < B; ++b)
