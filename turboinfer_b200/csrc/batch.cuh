@@ -19,7 +19,7 @@ __global__ void rope_kv_batch_kernel(float* qkv, int H, int rope_dim, const floa
     float* row = qkv + (size_t)b * 3 * H;
     const int page = tables[(size_t)b * pages_per_seq + pos / page_tokens];
     const size_t kvoff = ((size_t)page * page_tokens + (pos % page_tokens)) * H;
-    for (int p = threadIdx.x; p < H / 2; p += blockDim.x) {
+    for (int p = blockIdx.y * blockDim.x + threadIdx.x; p < H / 2; p += gridDim.y * blockDim.x) {   // grid (B, slices of the row)
         const int d = 2 * p;
         float q0 = row[d], q1 = row[d + 1], k0 = row[H + d], k1 = row[H + d + 1];
         if (rope_dim > 0) {

@@ -1174,7 +1174,7 @@ int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
         const int Il = ly.down->L.K;   // this rank's share of the intermediate width
         TRY(batch_digits(m, m.pf_x.p, nullptr, ly.attn_norm.p, B, H, m_pad, ly.qkv->k_pad));
         TRY(pf_gemm(m, *ly.qkv, B, m_pad, m.pf_qkv.p, nullptr));
-        rope_kv_batch_kernel<<<B, 256, 0, g_stream>>>(m.pf_qkv.p, Hl, rope_dim, m.inv_freq.p, bs.pos_step.p, bs.k[l].p, bs.v[l].p, bs.tables.p,
+        rope_kv_batch_kernel<<<dim3(B, std::max(1, Hl / 512)), 256, 0, g_stream>>>(m.pf_qkv.p, Hl, rope_dim, m.inv_freq.p, bs.pos_step.p, bs.k[l].p, bs.v[l].p, bs.tables.p,
                                                        bs.pages_per_seq, m.page_tokens);
         AttnArgs a{};
         a.q = m.pf_qkv.p;
@@ -1227,7 +1227,7 @@ int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
     if (sample) {
         TRY(batch_digits(m, m.pf_x.p, nullptr, m.out_norm.p, B, H, m_pad, m.lm_head->k_pad));
         TRY(pf_gemm(m, *m.lm_head, B, m_pad, bs.logits.p, nullptr));
-        argmax_rows_kernel<<<B, 256, 0, g_stream>>>(bs.logits.p, V, bs.tokens.p, bs.out.p, out_stride, bs.pos_step.p + 1);
+        argmax_rows_kernel<<<B, 1024, 0, g_stream>>>(bs.logits.p, V, bs.tokens.p, bs.out.p, out_stride, bs.pos_step.p + 1);
         ++g_launches;
     }
     batch_advance_kernel<<<1, 1, 0, g_stream>>>(bs.pos_step.p, sample ? 1 : 0);
