@@ -327,7 +327,8 @@ struct Model {
     bool tp_fused = false;
     void* xchg = nullptr;
     void* peer_base[kMaxTp] = {};
-    size_t xchg_part_off = 0, xchg_part_bytes = 0;
+    size_t xchg_flag_off = 0, xchg_part_off = 0, xchg_part_bytes = 0;
+    bool tp_p2p = false;   // point-to-point exchange per column slice instead of the barrier across the GPUs + reduce phase
     DevBuf<MegaPhase> phases;
     DevBuf<ProdRec> prod;
     int nphases = 0;
@@ -655,7 +656,8 @@ int tp_exchange_setup(Model& m) {
     const int H = m.cfg.hidden, P = m.tp;
     if (P > kMaxTp) return fail("fused tensor parallelism supports up to %d ranks", kMaxTp);
     const size_t bar_bytes = (size_t)kBarWords * kBarStride * sizeof(unsigned int) + 256;   // + the barrier sequence number
-    m.xchg_part_off = (bar_bytes + 255) & ~size_t(255);
+    m.xchg_flag_off = (bar_bytes + 255) & ~size_t(255);                                     // flags [2 buffers][P][256 CTAs]
+    m.xchg_part_off = m.xchg_flag_off + (size_t)2 * kMaxTp * 256 * sizeof(unsigned int);
     m.xchg_part_bytes = ((size_t)P * H * sizeof(float) + 255) & ~size_t(255);
     const size_t total = m.xchg_part_off + 2 * m.xchg_part_bytes;
     CK(cudaMalloc(&m.xchg, total));
@@ -759,7 +761,15 @@ int build_mega(Model& m) {
         ph.push_back(at);
         GemvArgs o{};
         o.x = m.attn_out.p;
-        if (tp) {   // row-parallel: partial output to every rank, barrier across the GPUs, then the reduce phase
+        if (tp && m.tp_p2p) {   // row-parallel: partial output to every rank, the P CTAs of a column slice meet and reduce it
+            o.epi = EPI_STORE;
+            o.resid = m.x.p;
+            o.out = m.x.p;
+            o.next_norm_w = ly.ffn_norm.p;
+            gemv_phase(*ly.o, o, SRC_PTR, src0, 0);
+            ph.back().mgpu = 2;
+            ph.back().part_sel = 0;
+        } else if (tp) {   // row-parallel: partial output to every rank, barrier across the GPUs, then the reduce phase
             o.epi = EPI_STORE;
             o.out = part[0];
             gemv_phase(*ly.o, o, SRC_PTR, SRC_PTR, 0);
@@ -783,7 +793,15 @@ int build_mega(Model& m) {
         GemvArgs d{};
         d.x = m.act.p;
         const float* norm_after = l + 1 < m.layers.size() ? m.layers[l + 1].attn_norm.p : m.out_norm.p;
-        if (tp) {
+        if (tp && m.tp_p2p) {
+            d.epi = EPI_STORE;
+            d.resid = m.x.p;
+            d.out = m.x.p;
+            d.next_norm_w = norm_after;
+            gemv_phase(*ly.down, d, SRC_PTR, SRC_PTR, 0);
+            ph.back().mgpu = 2;
+            ph.back().part_sel = 1;
+        } else if (tp) {
             d.epi = EPI_STORE;
             d.out = part[1];
             gemv_phase(*ly.down, d, SRC_PTR, SRC_PTR, 0);
@@ -884,7 +902,10 @@ int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
             a.peer_bar[r] = reinterpret_cast<unsigned int*>(b);
             a.peer_part[0][r] = reinterpret_cast<float*>(b + m.xchg_part_off);
             a.peer_part[1][r] = reinterpret_cast<float*>(b + m.xchg_part_off + m.xchg_part_bytes);
+            a.peer_flag[0][r] = reinterpret_cast<unsigned int*>(b + m.xchg_flag_off);
+            a.peer_flag[1][r] = reinterpret_cast<unsigned int*>(b + m.xchg_flag_off) + (size_t)kMaxTp * 256;
         }
+        a.tp_p2p = m.tp_p2p ? 1 : 0;
         a.mg_seq = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(m.xchg) + (size_t)kBarWords * kBarStride * sizeof(unsigned int));
     }
     void* args[] = {&a};
@@ -1808,7 +1829,11 @@ int ti_b200_model_finalize(ti_model_t h) {
                  H <= kConsumerThreads * g_num_sms;
     m.use_mega = complete && !want_graph && vec_ok && (m.tp == 1 || m.tp_fused);   // the persistent kernel's prologue uses 128-bit loads only
     if (m.tp > 1) TRY(m.ar_tmp.alloc(H));
-    if (m.tp_fused) TRY(tp_exchange_setup(m));
+    if (m.tp_fused) {
+        const char* red = getenv("TURBOINFER_B200_TP_REDUCE");   // "p2p" (per column slice) or "barrier" (all GPUs + reduce phase)
+        m.tp_p2p = (red ? std::string(red) == "p2p" : false) && g_num_sms <= 256;
+        TRY(tp_exchange_setup(m));
+    }
     TRY(m.prompt.alloc(16));
     if (m.use_mega) TRY(build_mega(m));
     // tensor-parallel steps hold NCCL all-reduces: NCCL supports stream capture, so they are replayed from a graph as

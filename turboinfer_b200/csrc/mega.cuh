@@ -31,7 +31,9 @@ struct MegaPhase {
     // tensor parallel: a row-parallel GEMV phase (mgpu = 1) stores its partial output into EVERY rank's
     // partial buffer `part_sel` and ends with a barrier across all GPUs; the PH_REDUCE phase after it sums the partials in
     // rank order on top of the residual (g.x = this rank's partial buffer [tp][H], g.resid / g.out = the residual stream,
-    // g.L.N = H, g.next_norm_w as in a residual epilogue)
+    // g.L.N = H, g.next_norm_w as in a residual epilogue).  mgpu = 2: point-to-point variant -- no barrier across the GPUs
+    // and no PH_REDUCE phase: the CTA waits for the flags of its own column slice from every rank and reduces the slice
+    // in the tail of the GEMV phase (g.resid / g.out / g.next_norm_w as in the single-GPU residual epilogue)
     int mgpu, part_sel;
     GemvArgs g;
     AttnArgs at;
@@ -71,7 +73,11 @@ struct MegaArgs {
     int tp, tp_rank;
     float* peer_part[2][kMaxTp];       // [buffer][rank] -> that rank's partial buffer, layout [source rank][H]
     unsigned int* peer_bar[kMaxTp];    // [rank] -> that rank's multi-GPU barrier words (kBarWords x kBarStride)
-    unsigned int* mg_seq;              // device scalar: multi-GPU barriers passed so far (carried across launches)
+    unsigned int* mg_seq;              // device scalar: multi-GPU barriers / exchanges passed so far (carried across launches)
+    // point-to-point variant (tp_p2p): CTA b of every rank owns the same column slice, so only the P CTAs "b" have to meet:
+    // flags [source rank][CTA] per partial buffer, written by the source with a system-scope release
+    unsigned int* peer_flag[2][kMaxTp];
+    int tp_p2p;
     const XStats* emb_stats;  // [V]: statistics of every embedding row (against the first norm weight)
 };
 
@@ -530,7 +536,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                         nnorm = __ldg(reinterpret_cast<const unsigned long long*>(&np->g.norm_w)) != 0ull;
                         neps = __ldg(&np->g.rms_eps);
                     }
-                    const bool mgpu = m.tp > 1 && __ldg(&m.phases[ph].mgpu) != 0;
+                    const bool mgpu = m.tp > 1 && __ldg(&m.phases[ph].mgpu) == 1;
                     bar_sync(2, kConsumerThreads + 32);   // every consumer thread has stored its outputs and partials
                     if (mgpu) {
                         // barrier across all GPUs: the partial outputs this CTA wrote into the peers' buffers become visible
@@ -619,6 +625,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
     };
 
     unsigned int phase_seq = 0;   // phases executed so far: selects the descriptor slot
+    unsigned int ex_seq = (m.tp > 1 && m.tp_p2p) ? *m.mg_seq : 0u;   // point-to-point exchanges since the group was formed
     int token = m.st->token;  // decode-only launches continue from the token the previous launch picked
     for (int s = 0; s < m.n_steps; ++s) {
         const bool sample = s >= m.first_sample;
@@ -689,6 +696,42 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                     if (stamp) ts[3] = clock64();
                     out_st = gemv_epilogue(g, slab, sm, s_x, resid, ctx, pre, tid, lane);
                 }
+                if (m.tp > 1 && P.mgpu == 2) {
+                    // Point-to-point all-reduce of this CTA's column slice.  CTA b of every rank computes the same columns, so
+                    // only those P CTAs meet: the partials went to every rank's buffer in the epilogue; one flag per (source
+                    // rank, CTA) says "slice written" (system-scope release after the CTA-wide barrier), the CTA waits for
+                    // its P flags and sums residual + partials in rank order -- every rank reads the same stored values, so
+                    // the replicated residual stream stays bit-identical.
+                    ++ex_seq;
+                    bar_sync(1, kConsumerThreads);   // every thread's peer stores are ordered before the flags
+                    if (warp == 0) {
+                        if (lane < m.tp) {
+                            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(m.peer_flag[P.part_sel][lane] + (size_t)m.tp_rank * gridDim.x + blockIdx.x), "r"(ex_seq)
+                                         : "memory");
+                            const unsigned int* fl = m.peer_flag[P.part_sel][m.tp_rank] + (size_t)lane * gridDim.x + blockIdx.x;
+                            const long long t0 = clock64();
+                            while ((int)(bar_poll_sys(fl) - ex_seq) < 0) {
+                                if (clock64() - t0 > 120000000000LL) __trap();
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    bar_sync(1, kConsumerThreads);
+                    out_st = XStats{0.f, 0.f};
+                    if (gemv_here) {
+                        const float* part = m.peer_part[P.part_sel][m.tp_rank];
+                        const int Hn = P.g.L.N;
+                        for (int c = tid; c < slab.ncols; c += kConsumerThreads) {
+                            const int n = slab.col0 + c;
+                            if (n >= Hn) continue;
+                            float v = ld_act(resid + n, P.resid_src != SRC_EMB);
+                            for (int r = 0; r < m.tp; ++r) v += __ldcg(part + (size_t)r * Hn + n);
+                            P.g.out[n] = v;
+                            out_st.ss = fmaf(v, v, out_st.ss);
+                            out_st.am = fmaxf(out_st.am, fabsf(P.g.next_norm_w ? v * P.g.next_norm_w[n] : v));
+                        }
+                    }
+                }
             } else if (P.type == PH_REDUCE) {
                 // all-reduce, second half: every rank's partial of the row-parallel GEMV is in this rank's buffer (the
                 // barrier across the GPUs has been passed); x <- residual + partials in rank order -- the same sums on
@@ -720,6 +763,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
         publish(last, token);
     }
     if (blockIdx.x == 0 && tid == 0) {
+        if (m.tp > 1 && m.tp_p2p) *m.mg_seq = ex_seq;
         m.st->pos = pos0 + m.n_steps;
         m.st->token = token;
         const int sampled = m.n_steps - m.first_sample;
