@@ -18,16 +18,19 @@ def _gpu_count():
 
 
 @pytest.mark.skipif(_gpu_count() < 2, reason="tensor parallelism needs at least two GPUs")
-@pytest.mark.parametrize("engine", ["fused", "nccl"])
+@pytest.mark.parametrize("engine", ["fused", "fused-p2p", "nccl"])
 def test_tp2_tokens_equal_single_gpu(engine):
     """fused: the persistent kernel with peer stores over NVLink + the barrier across the GPUs (default);
+    fused-p2p: the same kernel with the point-to-point exchange per column slice (opt-in);
     nccl: the per-op engine with ncclAllReduce after every row-parallel GEMV (the baseline of SURVEY.md 8e)."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533" if engine == "fused" else "29534", os.path.join(ROOT, "scripts", "tp_check.py")]
+           "--master-port", {"fused": "29533", "fused-p2p": "29535", "nccl": "29534"}[engine], os.path.join(ROOT, "scripts", "tp_check.py")]
     env = dict(os.environ)
+    env.pop("TURBOINFER_B200_TP_ENGINE", None)
+    env.pop("TURBOINFER_B200_TP_REDUCE", None)
     if engine == "nccl":
         env["TURBOINFER_B200_TP_ENGINE"] = "nccl"
-    else:
-        env.pop("TURBOINFER_B200_TP_ENGINE", None)
+    if engine == "fused-p2p":
+        env["TURBOINFER_B200_TP_REDUCE"] = "p2p"
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert r.returncode == 0 and "TP CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
