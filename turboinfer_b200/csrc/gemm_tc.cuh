@@ -3,12 +3,13 @@
 //
 // Replaces simd_gemm_float (src/core/tensor_engine.cpp:191-255, the M,N,K >= 32 branch of TensorEngine::matmul) on
 // quantized weights.  Same arithmetic contract as the streaming GEMV (gemv.cuh), so a row of the GEMM is bit-identical
-// to the GEMV of that row: each activation row is converted to 24-bit block fixed point and split into three 8-bit
-// digit planes; the tensor cores multiply the INT8 planes with the INT8 / unpacked-INT4 weights (kind::i8, exact
+// to the GEMV of that row: each activation row is converted to 24-bit block fixed point and split into three signed
+// 8-bit digit planes; the tensor cores multiply the INT8 planes with the INT8 / unpacked-INT4 weights (kind::i8, exact
 // int32 accumulation in TMEM, one accumulator per digit); the epilogue recombines the digits in int64 and scales once.
 //
 //   CTA tile      128 tokens x 128 columns, K in steps of 128 bytes; 3 accumulators x 128 columns of TMEM
-//   warp 0        TMA producer: per stage 3 digit tiles of A (128 x 128 B) + 1 tile of B (128 x 128 B), SWIZZLE_128B
+//   warp 0        producer: per stage 3 digit tiles of A (TMA boxes of 128 x 128 B, SWIZZLE_128B) + 1 weight tile of B
+//                 (16 KiB, stored in HBM as its swizzled image: one 1-D bulk copy)
 //   warp 1        TMEM allocation; one elected lane issues tcgen05.mma (M 128, N 128, K 32): 4 k-steps x 3 digits per stage,
 //                 tcgen05.commit releases the stage / publishes the accumulators
 //   warps 2..5    epilogue: tcgen05.ld 32x32b (lane = token row), digit recombination, scale, store
