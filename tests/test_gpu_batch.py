@@ -57,3 +57,18 @@ def test_generate_batch_rejects_bad_arguments(tb):
             m.generate_batch_greedy(np.full((2, 3), meta["vocab"], np.int32), 2)   # token id out of range
     finally:
         m.free()
+
+
+def test_generate_batch_survives_scratch_reallocation(tb):
+    """The step graphs hold pointers into the scratch buffers; a long prompt in between reallocates them."""
+    meta = SHAPES["bench-small"]
+    w = make_model(meta, norm_jitter=0.1)
+    prompts = np.array([prompt_tokens(5, meta["vocab"], offset=b) for b in range(4)], dtype=np.int32)
+    m = tb.Model(meta, oracle.QINT4, attn_mode=1, rope_mode=1, max_seq=256).load(w)
+    try:
+        first, _, _ = m.generate_batch_greedy(prompts, 7)
+        m.generate_greedy(prompt_tokens(120, meta["vocab"]), 3)      # batched prefill with M = 119 rows: scratch grows
+        again, _, _ = m.generate_batch_greedy(prompts, 7)
+    finally:
+        m.free()
+    assert np.array_equal(first, again)

@@ -283,7 +283,7 @@ struct BatchState {
     DevBuf<float> part_o, part_ml, logits;
     DevBuf<float> ar;                    // tensor parallel: [B][H] partial output of a row-parallel GEMM, all-reduced in place
     cudaGraphExec_t graph[2] = {nullptr, nullptr};   // [0] step without sampling, [1] with lm_head + argmax
-    const void* cap_scratch = nullptr;               // what the captured graphs were built against: the scratch buffers
+    unsigned int cap_scratch = 0xFFFFFFFFu;          // what the captured graphs were built against: the scratch generation
     int cap_stride = 0;                              // ... and the row stride of `out`
     void drop_graphs() { for (auto& g : graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; } }
     ~BatchState() { drop_graphs(); }
@@ -317,6 +317,7 @@ struct Model {
     DevBuf<long long> pf_sxf;
     DevBuf<unsigned long long> pf_ws;   // split-K workspace of the 32-row GEMM: [n_pad][32] integer partial sums, zero between GEMMs
     DevBuf<unsigned int> pf_cnt;        // ... and its per-tile arrival counters
+    unsigned int pf_gen = 0;            // bumped whenever the scratch buffers are (re)allocated: captured graphs hold their pointers
     bool pf_small_layout = false;       // pf_planes currently holds the 32-row GEMM's tile images (batch.cuh) rather than [3][m_pad][k_pad]
     DevBuf<int> pf_tokens;
     std::unique_ptr<struct BatchState> batch;   // batched decode (generate_batch): per-sequence KV pages, step graphs
@@ -1131,6 +1132,7 @@ int ensure_pf_scratch(Model& m, int M) {
         TRY(m.pf_sxf.alloc(M));
         TRY(m.pf_planes.alloc((size_t)3 * m_pad * kmax));
         m.pf_cap = M;
+        ++m.pf_gen;
     }
     size_t nmax = 0;
     auto updn = [&](QWeight* w) { if (w) nmax = std::max(nmax, (size_t)(4 * w->L.U + kGemmBN - 1) / kGemmBN * kGemmBN); };
@@ -1142,6 +1144,7 @@ int ensure_pf_scratch(Model& m, int M) {
         TRY(m.pf_cnt.alloc(nmax / kGemmBN));
         CK(cudaMemsetAsync(m.pf_ws.p, 0, nmax * kSmallRows * sizeof(unsigned long long), g_stream));
         CK(cudaMemsetAsync(m.pf_cnt.p, 0, nmax / kGemmBN * sizeof(unsigned int), g_stream));
+        ++m.pf_gen;
     }
     return 0;
 }
@@ -2069,9 +2072,9 @@ int ti_b200_generate_batch_greedy(ti_model_t h, const int32_t* prompts, int32_t 
         TRY(bs.out.alloc((size_t)B * n_new));
         bs.drop_graphs();   // the graphs hold the old pointer
     }
-    if (bs.cap_scratch != m.pf_planes.p || bs.cap_stride != n_new) {   // kernel parameters of the captured graphs
+    if (bs.cap_scratch != m.pf_gen || bs.cap_stride != n_new) {   // kernel parameters of the captured graphs
         bs.drop_graphs();
-        bs.cap_scratch = m.pf_planes.p;
+        bs.cap_scratch = m.pf_gen;
         bs.cap_stride = n_new;
     }
     std::vector<int> cols((size_t)n_prompt * B);
