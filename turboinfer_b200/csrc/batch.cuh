@@ -41,8 +41,10 @@ __global__ void rope_kv_batch_kernel(float* qkv, int H, int rope_dim, const floa
 // computed on the fly as up * silu(gate) from the interleaved (gate_i, up_i) columns of gu[M][2K] (SwiGLU fused in front
 // of the down projection, :918, :1729).  Same expressions as rmsnorm_digits_kernel (prefill.cuh).
 constexpr int kDigitsThreads = 1024, kDigitsVecs = 4;   // 4 float4 per thread
+// tile_layout = 1: planes in the 32-row GEMM's tile images (xtile_offset); 0: [3][m_pad][k_pad] row-major for the 128-row GEMM
 __global__ void __launch_bounds__(kDigitsThreads) rmsnorm_digits_small_kernel(const float* x, const float* gu, const float* w, float eps, int K,
-                                                                               int m_pad, int k_pad, int8_t* planes, float* sx_out, long long* sxf_out) {
+                                                                               int m_pad, int k_pad, int8_t* planes, float* sx_out, long long* sxf_out,
+                                                                               int tile_layout) {
     __shared__ float red[32];
     __shared__ long long redl[32];
     const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -104,10 +106,17 @@ __global__ void __launch_bounds__(kDigitsThreads) rmsnorm_digits_small_kernel(co
             const int u0 = f0 + 0x808080, u1 = f1 + 0x808080, u2 = f2 + 0x808080, u3 = f3 + 0x808080;
             const uint32_t lo01 = __byte_perm(u0, u1, 0x5140), lo23 = __byte_perm(u2, u3, 0x5140);
             const uint32_t hi01 = __byte_perm(u0, u1, 0x0062), hi23 = __byte_perm(u2, u3, 0x0062);
-            // stored as the swizzled tile images the 32-row GEMM copies in bulk (gemm_tc.cuh xtile_offset)
-            *reinterpret_cast<uint32_t*>(planes + xtile_offset(0, row, k)) = __byte_perm(lo01, lo23, 0x5410) ^ 0x80808080u;
-            *reinterpret_cast<uint32_t*>(planes + xtile_offset(1, row, k)) = __byte_perm(lo01, lo23, 0x7632) ^ 0x80808080u;
-            *reinterpret_cast<uint32_t*>(planes + xtile_offset(2, row, k)) = __byte_perm(hi01, hi23, 0x5410) ^ 0x80808080u;
+            const uint32_t d0 = __byte_perm(lo01, lo23, 0x5410) ^ 0x80808080u, d1 = __byte_perm(lo01, lo23, 0x7632) ^ 0x80808080u,
+                           d2 = __byte_perm(hi01, hi23, 0x5410) ^ 0x80808080u;
+            if (tile_layout) {   // the swizzled tile images the 32-row GEMM copies in bulk (gemm_tc.cuh xtile_offset)
+                *reinterpret_cast<uint32_t*>(planes + xtile_offset(0, row, k)) = d0;
+                *reinterpret_cast<uint32_t*>(planes + xtile_offset(1, row, k)) = d1;
+                *reinterpret_cast<uint32_t*>(planes + xtile_offset(2, row, k)) = d2;
+            } else {
+                *reinterpret_cast<uint32_t*>(planes + ((size_t)0 * m_pad + row) * k_pad + k) = d0;
+                *reinterpret_cast<uint32_t*>(planes + ((size_t)1 * m_pad + row) * k_pad + k) = d1;
+                *reinterpret_cast<uint32_t*>(planes + ((size_t)2 * m_pad + row) * k_pad + k) = d2;
+            }
         }
     }
 #pragma unroll

@@ -1051,11 +1051,20 @@ int pf_gemm(Model& m, QWeight& w, int M, int m_pad, float* y, const float* resid
     CK(cudaGetLastError());
     return 0;
 }
-int pf_digits(Model& m, const float* x, const float* norm_w, int M, int K, int m_pad, int k_pad) {
-    // planes of rows >= M and columns >= K stay zero: the buffer is cleared when it is (re)allocated and only rows < M,
-    // columns < k_pad are written -- k_pad differs per weight, so clear the tail columns explicitly
-    // (the 32-row GEMM of the batched decode never reads rows it does not also ignore: nothing to clear there)
+// gu != nullptr: x is computed on the fly as up * silu(gate) from gu[M][2K] (needs the fast path; callers check pf_digits_fast)
+bool pf_digits_fast(int K, int k_pad) { return K % 4 == 0 && k_pad <= 4 * kDigitsThreads * kDigitsVecs; }
+int pf_digits(Model& m, const float* x, const float* norm_w, int M, int K, int m_pad, int k_pad, const float* gu = nullptr) {
     m.pf_small_layout = false;
+    if (pf_digits_fast(K, k_pad)) {
+        // register-resident conversion, 4-byte stores; it writes every column < k_pad of the rows < M, and rows >= M only
+        // produce output rows nobody stores: nothing to clear
+        rmsnorm_digits_small_kernel<<<M, kDigitsThreads, 0, g_stream>>>(x, gu, norm_w, m.cfg.rms_eps, K, m_pad, k_pad, m.pf_planes.p, m.pf_sx.p, m.pf_sxf.p, 0);
+        ++g_launches;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    // planes of rows >= M and columns >= K stay zero: only rows < M, columns < k_pad are written -- k_pad differs per
+    // weight, so clear explicitly
     CK(cudaMemsetAsync(m.pf_planes.p, 0, (size_t)3 * m_pad * k_pad, g_stream));
     rmsnorm_digits_kernel<<<M, 256, (size_t)K * sizeof(float), g_stream>>>(x, norm_w, m.cfg.rms_eps, M, K, m_pad, k_pad, m.pf_planes.p, m.pf_sx.p, m.pf_sxf.p);
     ++g_launches;
@@ -1102,11 +1111,15 @@ int prefill_gemm(Model& m, const int* prompt_dev, int M) {
         TRY(ensure_kmajor(*ly.gateup));
         TRY(pf_digits(m, m.pf_x.p, ly.ffn_norm.p, M, H, m_pad, ly.gateup->k_pad));
         TRY(pf_gemm(m, *ly.gateup, M, m_pad, m.pf_gu.p, nullptr));
-        if (ly.has_gate) swiglu_rows_kernel<<<grid_for((size_t)M * I), 256, 0, g_stream>>>(m.pf_gu.p, m.pf_act.p, (size_t)M, (size_t)I);
-        else relu_rows_kernel<<<grid_for((size_t)M * I), 256, 0, g_stream>>>(m.pf_gu.p, m.pf_act.p, (size_t)M * I);
-        ++g_launches;
         TRY(ensure_kmajor(*ly.down));
-        TRY(pf_digits(m, m.pf_act.p, nullptr, M, I, m_pad, ly.down->k_pad));
+        if (ly.has_gate && pf_digits_fast(I, ly.down->k_pad)) {
+            TRY(pf_digits(m, nullptr, nullptr, M, I, m_pad, ly.down->k_pad, m.pf_gu.p));   // SwiGLU fused into the conversion
+        } else {
+            if (ly.has_gate) swiglu_rows_kernel<<<grid_for((size_t)M * I), 256, 0, g_stream>>>(m.pf_gu.p, m.pf_act.p, (size_t)M, (size_t)I);
+            else relu_rows_kernel<<<grid_for((size_t)M * I), 256, 0, g_stream>>>(m.pf_gu.p, m.pf_act.p, (size_t)M * I);
+            ++g_launches;
+            TRY(pf_digits(m, m.pf_act.p, nullptr, M, I, m_pad, ly.down->k_pad));
+        }
         TRY(pf_gemm(m, *ly.down, M, m_pad, m.pf_x.p, m.pf_x.p));
     }
     CK(cudaGetLastError());
@@ -1159,7 +1172,7 @@ bool batch_eligible(const Model& m) {
 int batch_digits(Model& m, const float* x, const float* gu, const float* norm_w, int B, int K, int m_pad, int k_pad) {
     const bool small = K % 4 == 0 && k_pad <= 4 * kDigitsThreads * kDigitsVecs;
     if (small && B <= kSmallRows) {
-        rmsnorm_digits_small_kernel<<<B, kDigitsThreads, 0, g_stream>>>(x, gu, norm_w, m.cfg.rms_eps, K, m_pad, k_pad, m.pf_planes.p, m.pf_sx.p, m.pf_sxf.p);
+        rmsnorm_digits_small_kernel<<<B, kDigitsThreads, 0, g_stream>>>(x, gu, norm_w, m.cfg.rms_eps, K, m_pad, k_pad, m.pf_planes.p, m.pf_sx.p, m.pf_sxf.p, 1);
         m.pf_small_layout = true;
         ++g_launches;
         CK(cudaGetLastError());
