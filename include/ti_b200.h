@@ -148,6 +148,9 @@ int ti_b200_model_free(ti_model_t m);
 /* KVCache::reset (:60-69): frees the page list, length = 0 */
 int ti_b200_model_reset(ti_model_t m);
 int ti_b200_model_kv_length(ti_model_t m, int32_t* length);
+/* which engine decodes this (finalized) model: 1 = the persistent decode kernel (one cooperative launch per generation), 0 =
+ * the per-op graph engine (models with absent tensors -- the reference's null-weight fall-backs -- and the NCCL baseline) */
+int ti_b200_model_engine(ti_model_t m, int32_t* persistent);
 /* bytes one decode step must move at cache length t: packed weights + scales + KV read/write */
 int ti_b200_model_step_bytes(ti_model_t m, int32_t t, double* weight_bytes, double* kv_bytes);
 /* forward_pass_incremental for one token: appends to the KV cache; logits_host may be NULL */
@@ -186,6 +189,9 @@ int ti_b200_bench_gemm(ti_qweight_t w, size_t rows, size_t reps, float* ms, doub
 /* debug: one decode step on the persistent-kernel engine with CTA 0 recording 6 SM-clock stamps per phase
  * (phase start, barrier passed, x staged, weights consumed, epilogue done, barrier arrived) */
 int ti_b200_debug_timeline(ti_model_t m, int32_t token, int64_t* stamps, size_t cap, size_t* n_phases);
+/* the same with EVERY CTA recording: stamps[cta][phase][32]; slots 25 / 26 = SM clock when the CTA finished the phase / when it
+ * passed the grid barrier, 27 / 28 = the same on the global nanosecond timer (comparable across CTAs) */
+int ti_b200_debug_timeline_all(ti_model_t m, int32_t token, int64_t* stamps, size_t cap, size_t* n_phases, size_t* n_ctas);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,9 @@ class Oracle:
         L.tio_decode_greedy.restype = C.c_int
         L.tio_decode_greedy.argtypes = [C.POINTER(TioModel), C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int,
                                         C.POINTER(C.c_int32), _f]
+        L.tio_decode_greedy_timed.restype = C.c_int
+        L.tio_decode_greedy_timed.argtypes = [C.POINTER(TioModel), C.POINTER(C.c_int32), C.c_int, C.c_int, C.POINTER(C.c_int32),
+                                              C.POINTER(C.c_double), C.c_int]
         L.tio_generate_literal.restype = C.c_int
         L.tio_generate_literal.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int,
                                            C.c_int, C.POINTER(C.c_int32), _f]
@@ -215,9 +218,7 @@ class Oracle:
         return out
 
     # ---- level B ----
-    def decode_greedy(self, weights: dict, meta: dict, prompt: Sequence[int], n_new: int, *,
-                      attn_mode: int = 1, rope_mode: int = 0, stop_on_eos: bool = False,
-                      want_logits: bool = True):
+    def _marshal(self, weights: dict, meta: dict, attn_mode: int, rope_mode: int):
         """weights: name -> fp32 array using the reference tensor names of
         InferenceEngineImpl::initialize_model (src/model/inference_engine.cpp:483-563), all [in, out]."""
         L = meta["layers"]
@@ -257,15 +258,37 @@ class Oracle:
         m.w_up = per_layer("layers.{}.mlp.up_proj.weight")
         m.w_gate = per_layer("layers.{}.mlp.gate_proj.weight")
         m.w_down = per_layer("layers.{}.mlp.down_proj.weight")
+        return m, keep
+
+    def decode_greedy(self, weights: dict, meta: dict, prompt: Sequence[int], n_new: int, *,
+                      attn_mode: int = 1, rope_mode: int = 0, stop_on_eos: bool = False,
+                      want_logits: bool = True):
+        m, keep = self._marshal(weights, meta, attn_mode, rope_mode)
         p = np.ascontiguousarray(prompt, dtype=np.int32)
         out = np.zeros(max(n_new, 1), dtype=np.int32)
         logits = np.zeros((max(n_new, 1), meta["vocab"]), dtype=np.float32) if want_logits else None
         n = self.lib.tio_decode_greedy(C.byref(m), p.ctypes.data_as(C.POINTER(C.c_int32)), p.size, n_new,
                                        int(stop_on_eos), out.ctypes.data_as(C.POINTER(C.c_int32)),
                                        _fp(logits) if logits is not None else C.cast(None, _f))
+        del keep
         if n < 0:
             raise RuntimeError(f"tio_decode_greedy failed ({n})")
         return out[:n].copy(), (logits[:n].copy() if logits is not None else None)
+
+    def decode_greedy_timed(self, weights: dict, meta: dict, prompt: Sequence[int], n_new: int, *,
+                            attn_mode: int = 1, rope_mode: int = 0):
+        """(tokens, seconds of each of the n_prompt + n_new - 1 forward passes) -- bench.py's CPU arm."""
+        m, keep = self._marshal(weights, meta, attn_mode, rope_mode)
+        p = np.ascontiguousarray(prompt, dtype=np.int32)
+        out = np.zeros(max(n_new, 1), dtype=np.int32)
+        cap = p.size + max(n_new, 1)
+        secs = np.zeros(cap, dtype=np.float64)
+        n = self.lib.tio_decode_greedy_timed(C.byref(m), p.ctypes.data_as(C.POINTER(C.c_int32)), p.size, n_new,
+                                             out.ctypes.data_as(C.POINTER(C.c_int32)), secs.ctypes.data_as(C.POINTER(C.c_double)), cap)
+        del keep
+        if n < 0:
+            raise RuntimeError(f"tio_decode_greedy_timed failed ({n})")
+        return out[:max(n_new, 0)].copy(), secs[:n].copy()
 
     # ---- level C ----
     def generate_literal(self, vocab: int, hidden: int, layers: int, qtype: int, prompt: Sequence[int], n_new: int):

@@ -8,6 +8,7 @@
 // R2/R4 defects of SURVEY.md section 0 removed (2-D activations, real embedding lookup).
 #include "ti_oracle.h"
 
+#include <chrono>
 #include <turboinfer/core/tensor.hpp>
 #include <turboinfer/core/tensor_engine.hpp>
 #include <turboinfer/model/inference_engine.hpp>
@@ -123,6 +124,10 @@ void tio_multi_head_attention(const float* q, const float* k, const float* v, fl
     put(engine().multi_head_attention(make({B, 1, H}, q), make({B, t, H}, k), make({B, t, H}, v), nh), out);
 }
 
+// bench.py's CPU arm: per-pass wall-clock times of the next tio_decode_greedy call (set by tio_decode_greedy_timed)
+static double* g_step_times = nullptr;
+static int g_step_cap = 0, g_step_n = 0;
+
 int tio_decode_greedy(const tio_model* m, const int32_t* prompt, int n_prompt, int n_new,
                       int stop_on_eos, int32_t* out_tokens, float* logits_out) {
     if (!m || n_prompt <= 0 || n_new < 0) return -1;
@@ -155,7 +160,7 @@ int tio_decode_greedy(const tio_model* m, const int32_t* prompt, int n_prompt, i
     std::vector<std::vector<float>> kc(L), vc(L);  // flat [t, H] caches
     size_t t = 0;
 
-    auto step = [&](int token, float* logits) {
+    auto step_untimed = [&](int token, float* logits) {
         Tensor x = make({1, H}, m->tok_emb + static_cast<size_t>(token) * H);
         const float posf = static_cast<float>(t);
         for (size_t l = 0; l < L; ++l) {
@@ -200,6 +205,12 @@ int tio_decode_greedy(const tio_model* m, const int32_t* prompt, int n_prompt, i
         Tensor hn = out_norm ? te.rms_norm(x, *out_norm, m->rms_eps) : x;
         put(te.matmul(hn, *lm_head), logits);
     };
+    auto step = [&](int token, float* logits) {
+        const auto c0 = std::chrono::steady_clock::now();
+        step_untimed(token, logits);
+        if (g_step_times && g_step_n < g_step_cap)
+            g_step_times[g_step_n++] = std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count();
+    };
 
     std::vector<float> logits(V);
     for (int i = 0; i < n_prompt; ++i) step(prompt[i], i == n_prompt - 1 ? logits.data() : nullptr);
@@ -214,6 +225,16 @@ int tio_decode_greedy(const tio_model* m, const int32_t* prompt, int n_prompt, i
         if (i + 1 < n_new) step(best, logits.data());
     }
     return produced;
+}
+
+int tio_decode_greedy_timed(const tio_model* m, const int32_t* prompt, int n_prompt, int n_new,
+                            int32_t* out_tokens, double* step_seconds, int cap) {
+    g_step_times = step_seconds;
+    g_step_cap = cap;
+    g_step_n = 0;
+    const int rc = tio_decode_greedy(m, prompt, n_prompt, n_new, 0, out_tokens, nullptr);
+    g_step_times = nullptr;
+    return rc < 0 ? rc : g_step_n;
 }
 
 // benchmarks/benchmark_inference.cpp:145-225 builds this model inside the benchmark executable (not in

@@ -13,11 +13,13 @@
  * = fused, `p = a*b; s = s + p` = un-fused), and this file is compiled with -ffp-contract=off so the
  * rounding does not depend on compiler flags.
  */
+#define _POSIX_C_SOURCE 200809L
 #include "ti_oracle.h"
 
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 int tio_kind(void) { return 0; }
 
@@ -391,6 +393,17 @@ static int argmax_first(const float* x, size_t n) {
     return (int)best;
 }
 
+/* bench.py's CPU arm: per-pass wall-clock times of the next tio_decode_greedy call (set by tio_decode_greedy_timed) */
+static double* g_step_times = NULL;
+static int g_step_cap = 0, g_step_n = 0;
+static void step_B_timed(const tio_model* m, tio_scratch* s, size_t t, int token, float* logits) {
+    struct timespec a, b;
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    step_B(m, s, t, token, logits);
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    if (g_step_times && g_step_n < g_step_cap) g_step_times[g_step_n++] = (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec);
+}
+
 int tio_decode_greedy(const tio_model* m, const int32_t* prompt, int n_prompt, int n_new,
                       int stop_on_eos, int32_t* out_tokens, float* logits_out) {
     if (!m || !m->lm_head || !m->tok_emb || n_prompt <= 0 || n_new < 0) return -1;
@@ -411,20 +424,30 @@ int tio_decode_greedy(const tio_model* m, const int32_t* prompt, int n_prompt, i
     }
     float* logits = (float*)calloc(V, sizeof(float));
     size_t t = 0;
-    for (int i = 0; i < n_prompt; ++i, ++t) step_B(m, &s, t, prompt[i], i == n_prompt - 1 ? logits : NULL);
+    for (int i = 0; i < n_prompt; ++i, ++t) step_B_timed(m, &s, t, prompt[i], i == n_prompt - 1 ? logits : NULL);
     int produced = 0;
     for (int i = 0; i < n_new; ++i) {
         int best = argmax_first(logits, V); /* top_k = 1: :1585-1598 */
         if (logits_out) memcpy(logits_out + (size_t)i * V, logits, V * sizeof(float));
         out_tokens[produced++] = best;
         if (stop_on_eos && best == 2) break; /* :760 */
-        if (i + 1 < n_new) { step_B(m, &s, t, best, logits); ++t; }
+        if (i + 1 < n_new) { step_B_timed(m, &s, t, best, logits); ++t; }
     }
     for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); ++i) free(*bufs[i]);
     free(s.up); free(s.gate); free(s.act);
     for (size_t l = 0; l < L; ++l) { free(s.kc[l]); free(s.vc[l]); }
     free(s.kc); free(s.vc); free(logits);
     return produced;
+}
+
+int tio_decode_greedy_timed(const tio_model* m, const int32_t* prompt, int n_prompt, int n_new,
+                            int32_t* out_tokens, double* step_seconds, int cap) {
+    g_step_times = step_seconds;
+    g_step_cap = cap;
+    g_step_n = 0;
+    const int rc = tio_decode_greedy(m, prompt, n_prompt, n_new, 0, out_tokens, NULL);
+    g_step_times = NULL;
+    return rc < 0 ? rc : g_step_n;
 }
 
 /* ------------------------------------------------------------------------------------------

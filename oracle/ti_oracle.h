@@ -99,6 +99,12 @@ typedef struct tio_model {
 int tio_decode_greedy(const tio_model* m, const int32_t* prompt, int n_prompt, int n_new,
                       int stop_on_eos, int32_t* out_tokens, float* logits_out);
 
+/* Same generation, with the wall-clock time of every forward pass (steady clock around one step: n_prompt + n_new - 1
+ * passes) written to step_seconds[0 .. cap) -- what bench.py's CPU arm reports; weight set-up (the deep copies of
+ * initialize_model) stays outside the timed passes.  Returns the number of passes timed, < 0 on error. */
+int tio_decode_greedy_timed(const tio_model* m, const int32_t* prompt, int n_prompt, int n_new,
+                            int32_t* out_tokens, double* step_seconds, int cap);
+
 /* ---- level C: the literal path of benchmarks/benchmark_inference (SURVEY 8c oracle-C) --- */
 /* create_test_model(vocab, hidden, layers) (benchmarks/benchmark_inference.cpp:145-225) run through
  * InferenceEngine::generate with top_k = 1; qtype TIO_QNONE / TIO_QINT8 / TIO_QINT4 goes through

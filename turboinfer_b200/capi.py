@@ -69,6 +69,7 @@ SYMBOLS = {
     "ti_b200_model_free": (C.c_int, [C.c_uint64]),
     "ti_b200_model_reset": (C.c_int, [C.c_uint64]),
     "ti_b200_model_kv_length": (C.c_int, [C.c_uint64, _i32]),
+    "ti_b200_model_engine": (C.c_int, [C.c_uint64, _i32]),
     "ti_b200_model_step_bytes": (C.c_int, [C.c_uint64, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ti_b200_decode_step": (C.c_int, [C.c_uint64, C.c_int32, _f, _i32]),
     "ti_b200_generate_greedy": (C.c_int, [C.c_uint64, _i32, C.c_int32, C.c_int32, C.c_int32, _i32, _i32, _f, _f]),
@@ -78,6 +79,7 @@ SYMBOLS = {
     "ti_b200_bench_gemv": (C.c_int, [C.POINTER(C.c_uint64), C.c_size_t, C.c_size_t, _f]),
     "ti_b200_model_bench_gemv": (C.c_int, [C.c_uint64, C.c_int, C.c_size_t, _f, C.POINTER(C.c_double)]),
     "ti_b200_debug_timeline": (C.c_int, [C.c_uint64, C.c_int32, C.POINTER(C.c_int64), C.c_size_t, C.POINTER(C.c_size_t)]),
+    "ti_b200_debug_timeline_all": (C.c_int, [C.c_uint64, C.c_int32, C.POINTER(C.c_int64), C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -371,6 +373,13 @@ class Model:
         _ck(lib().ti_b200_debug_timeline(self.handle, token, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size, C.byref(n)))
         return buf[: 32 * n.value].reshape(n.value, 32).copy()
 
+    def debug_timeline_all(self, token: int = 1) -> np.ndarray:
+        """[ctas, phases, 32]: the same stamps from thread 0 of EVERY CTA, plus the barrier warp's [25..28]."""
+        buf = np.zeros(32 * 4096 * 160, dtype=np.int64)
+        n, c = C.c_size_t(), C.c_size_t()
+        _ck(lib().ti_b200_debug_timeline_all(self.handle, token, buf.ctypes.data_as(C.POINTER(C.c_int64)), buf.size, C.byref(n), C.byref(c)))
+        return buf[: 32 * n.value * c.value].reshape(c.value, n.value, 32).copy()
+
     def last_prefill_ms(self) -> float:
         ms = C.c_float()
         _ck(lib().ti_b200_model_last_prefill_ms(self.handle, C.byref(ms)))
@@ -393,6 +402,13 @@ class Model:
         n = C.c_int32()
         _ck(lib().ti_b200_model_kv_length(self.handle, C.byref(n)))
         return n.value
+
+    @property
+    def persistent_engine(self) -> bool:
+        """True: the persistent decode kernel runs this model; False: the per-op graph engine (null-weight fall-backs)."""
+        k = C.c_int32()
+        _ck(lib().ti_b200_model_engine(self.handle, C.byref(k)))
+        return bool(k.value)
 
     def step_bytes(self, t: int):
         w, k = C.c_double(), C.c_double()

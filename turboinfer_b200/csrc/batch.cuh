@@ -140,7 +140,9 @@ __global__ void argmax_rows_kernel(const float* logits, int V, int* tokens, int*
     const float* row = logits + (size_t)b * V;
     unsigned long long key = 0ull;
     for (int i = threadIdx.x; i < V; i += blockDim.x) {
-        const unsigned long long k = argmax_pack(row[i], i);
+        // NaN never wins and -inf never beats "nothing yet" (key 0 -> token 0): the policy of the GEMV epilogue (`y > best`)
+        const float v = row[i];
+        const unsigned long long k = v > -INFINITY ? argmax_pack(v, i) : 0ull;
         key = k > key ? k : key;
     }
 #pragma unroll
@@ -152,7 +154,8 @@ __global__ void argmax_rows_kernel(const float* logits, int V, int* tokens, int*
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int i = 1; i < (int)(blockDim.x >> 5); ++i) key = best[i] > key ? best[i] : key;
-        const int tok = 0x7FFFFFFF - (int)(uint32_t)(key & 0xFFFFFFFFull);
+        int tok = key == 0ull ? 0 : 0x7FFFFFFF - (int)(uint32_t)(key & 0xFFFFFFFFull);
+        tok = min(max(tok, 0), V - 1);
         tokens[b] = tok;
         const int step = *step_ptr;
         if (out && step < out_stride) out[(size_t)b * out_stride + step] = tok;

@@ -33,6 +33,7 @@ cudaStream_t g_stream = nullptr;
 uint64_t g_launches = 0;
 bool g_use_pdl = false;
 bool g_attr_done = false;
+bool g_batch_carveout_done = false;   // the batched step's uniform carve-out preference (reset by shutdown, like g_attr_done)
 
 // ---- tensor parallelism: NCCL is loaded at run time (dlopen), so the library has no link-time dependency on it ----
 struct NcclApi {
@@ -137,12 +138,18 @@ int pick_stages(const QLayout& L, int* stages, size_t* smem) {
 }
 
 int set_kernel_attrs() {
+    // every cudaFuncSetAttribute of the library in one place, behind one flag that ti_b200_shutdown resets: attributes
+    // belong to the device context, so a fresh init (same or another device) must set them again
     if (g_attr_done) return 0;
     CK(cudaFuncSetAttribute(gemv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(gemv_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(attn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CK(cudaFuncSetAttribute(mega_decode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(mega_decode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
+    CK(cudaFuncSetAttribute(gemm_i8_tc_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmemBytes));
+    CK(cudaFuncSetAttribute(rmsnorm_digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CK(cudaFuncSetAttribute(causal_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPfSmemBytes));
     g_attr_done = true;
     return 0;
 }
@@ -337,7 +344,7 @@ struct Model {
     DevBuf<unsigned int> head_cnt;
     int mega_stages = 0, mega_max_kpad = 0, mega_max_units = 0, mega_attn_floats = 0;
     DevBuf<long long> dbg;
-    bool dbg_on = false;
+    bool dbg_on = false, dbg_all = false;
     DevBuf<XStats> emb_stats;
     size_t mega_smem = 0;
     int host_pos = 0;  // mirror of state.pos
@@ -895,6 +902,7 @@ int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
     a.dbg = m.dbg_on ? m.dbg.p : nullptr;
     a.emb_stats = m.emb_stats.p;
     a.dbg_flags = getenv("TURBOINFER_B200_DBG_FLAGS") ? atoi(getenv("TURBOINFER_B200_DBG_FLAGS")) : 0;
+    if (m.dbg_on && m.dbg_all) a.dbg_flags |= 4;   // every CTA stamps
     a.tp = m.tp_fused ? m.tp : 1;
     a.tp_rank = m.tp_rank;
     if (m.tp_fused) {
@@ -952,11 +960,6 @@ int ensure_kmajor(QWeight& w) {
 
 // x_dev [M][K] fp32 -> y_dev [M][N] fp32; scratch buffers are allocated per call (this entry point is not the decode path)
 int gemm_q_dev(QWeight& w, const float* x_dev, float* y_dev, int M, float* kernel_ms, int reps) {
-    static bool attr = false;
-    if (!attr) {
-        CK(cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
-        attr = true;
-    }
     TRY(ensure_kmajor(w));
     const int K = w.L.K, N = w.L.N;
     const int m_pad = (M + kGemmBM - 1) / kGemmBM * kGemmBM;
@@ -1011,11 +1014,6 @@ int small_gemm_splits(int tiles, int ksteps) {
     return std::max(1, std::min(s, 8));
 }
 int launch_small_gemm(Model& m, QWeight& w, int m_pad, const GemmArgs& g) {
-    static bool attr = false;
-    if (!attr) {
-        CK(cudaFuncSetAttribute(gemm_i8_tc_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmemBytes));
-        attr = true;
-    }
     const int tiles = (w.L.N + kGemmBN - 1) / kGemmBN;
     if (m.pf_ws.n < (size_t)w.n_pad * kSmallRows || m.pf_cnt.n < (size_t)tiles) return fail("internal: split-K workspace too small");
     SplitKArgs sk{reinterpret_cast<const uint8_t*>(m.pf_planes.p), m.pf_ws.p, m.pf_cnt.p, w.n_pad, nullptr};
@@ -1083,13 +1081,6 @@ bool prefill_gemm_eligible(const Model& m, int M) {
 // The hidden states stay in pf_x; the caller runs the last prompt token through the decode engine for the logits.
 int ensure_pf_scratch(Model& m, int M);
 int prefill_gemm(Model& m, const int* prompt_dev, int M) {
-    static bool attr = false;
-    if (!attr) {
-        CK(cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
-        CK(cudaFuncSetAttribute(rmsnorm_digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        CK(cudaFuncSetAttribute(causal_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPfSmemBytes));
-        attr = true;
-    }
     const int H = m.cfg.hidden, I = std::max(m.cfg.inter, 1);
     const int m_pad = (M + kGemmBM - 1) / kGemmBM * kGemmBM;
     TRY(ensure_pf_scratch(m, M));
@@ -1299,6 +1290,9 @@ int ti_b200_init(int device) {
         return fail("ti_b200_init: no CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
     if (device < 0 || device >= count) return fail("ti_b200_init: device %d out of range [0,%d)", device, count);
     if (g_device == device) return 0;
+    // one device per process (one process per GPU): the stream, the models and the kernel attributes belong
+    // to the device of the first init; switching needs ti_b200_shutdown first
+    if (g_device >= 0) return fail("ti_b200_init: already initialised on device %d; call ti_b200_shutdown before selecting device %d", g_device, device);
     CK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
@@ -1317,10 +1311,17 @@ int ti_b200_shutdown(void) {
     cudaStreamSynchronize(g_stream);
     g_models.clear();
     g_qweights.clear();
+    if (g_comm) {   // the tensor-parallel group dies with the library state: a fresh init may form a new one
+        g_nccl.CommDestroy(g_comm);
+        g_comm = nullptr;
+        g_tp_size = 1;
+        g_tp_rank = 0;
+    }
     cudaStreamDestroy(g_stream);
     g_stream = nullptr;
     g_device = -1;
     g_attr_done = false;
+    g_batch_carveout_done = false;
     return 0;
 }
 
@@ -1888,6 +1889,13 @@ int ti_b200_model_kv_length(ti_model_t h, int32_t* length) {
     return 0;
 }
 
+int ti_b200_model_engine(ti_model_t h, int32_t* persistent) {
+    Model* m = get_model(h);
+    if (!m || !m->finalized) return fail("invalid or unfinalized model handle");
+    *persistent = m->use_mega ? 1 : 0;
+    return 0;
+}
+
 int ti_b200_model_step_bytes(ti_model_t h, int32_t t, double* weight_bytes, double* kv_bytes) {
     Model* m = get_model(h);
     if (!m || !m->finalized) return fail("invalid or unfinalized model handle");
@@ -2038,10 +2046,7 @@ int ti_b200_generate_batch_greedy(ti_model_t h, const int32_t* prompts, int32_t 
         if (prompts[i] < 0 || prompts[i] >= V) return fail("token id %d out of range", prompts[i]);
     const int total = n_prompt + n_new - 1;
     if (total > m.cfg.max_seq) return fail("KV cache overflow: sequence too long");  // :100-102
-    static bool attr = false;
-    if (!attr) {
-        CK(cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
-        CK(cudaFuncSetAttribute(rmsnorm_digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    if (!g_batch_carveout_done) {
         // every kernel of the step asks for the same L1 / shared-memory split as the GEMM (which needs nearly all of it):
         // a kernel that wants a different carve-out than its predecessor makes the SMs reconfigure before it can start
         const void* fns[] = {(const void*)gemm_i8_tc_small_kernel, (const void*)gemm_i8_tc_kernel, (const void*)rmsnorm_digits_small_kernel,
@@ -2049,7 +2054,7 @@ int ti_b200_generate_batch_greedy(ti_model_t h, const int32_t* prompts, int32_t 
                              (const void*)attn_combine_kernel, (const void*)argmax_rows_kernel, (const void*)batch_advance_kernel,
                              (const void*)embed_rows_kernel, (const void*)swiglu_rows_kernel, (const void*)relu_rows_kernel};
         for (const void* f : fns) CK(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr = true;
+        g_batch_carveout_done = true;
     }
     // everything that allocates or launches set-up kernels happens before the step graphs are captured
     for (auto& ly : m.layers)
@@ -2139,27 +2144,38 @@ int ti_b200_model_last_prefill_ms(ti_model_t h, float* ms) {
     return 0;
 }
 
-int ti_b200_debug_timeline(ti_model_t h, int32_t token, int64_t* stamps, size_t cap, size_t* n_phases) {
+static int debug_timeline_run(ti_model_t h, int32_t token, int64_t* stamps, size_t cap, size_t* n_phases, size_t* n_ctas, bool all) {
     TRY(need_init());
     Model* m = get_model(h);
     if (!m || !m->finalized || !m->use_mega) return fail("timeline needs a finalized model on the persistent-kernel engine");
     TRY(check_capacity(*m, 1));
-    const size_t n = (size_t)m->nphases * kStampsPerPhase;
-    if (cap < n) return fail("stamp buffer too small: need %zu", n);
+    const size_t per_cta = (size_t)m->nphases * kStampsPerPhase;
+    const size_t n = per_cta * (size_t)g_num_sms;
+    const size_t want = all ? n : per_cta;
+    if (cap < want) return fail("stamp buffer too small: need %zu", want);
     TRY(m->dbg.alloc(n));
     CK(cudaMemsetAsync(m->dbg.p, 0, n * sizeof(long long), g_stream));
     StepIO io{};
     CK(cudaMemcpyAsync(m->io.p, &io, sizeof(io), cudaMemcpyHostToDevice, g_stream));
     CK(cudaMemcpyAsync(&m->state.p->token, &token, sizeof(int), cudaMemcpyHostToDevice, g_stream));
     m->dbg_on = true;
+    m->dbg_all = all;
     int rc = run_mega(*m, 0, 1, 0);
     m->dbg_on = false;
+    m->dbg_all = false;
     TRY(rc);
     m->host_pos += 1;
-    CK(cudaMemcpyAsync(stamps, m->dbg.p, n * sizeof(long long), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaMemcpyAsync(stamps, m->dbg.p, want * sizeof(long long), cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
     *n_phases = m->nphases;
+    if (n_ctas) *n_ctas = g_num_sms;
     return 0;
+}
+int ti_b200_debug_timeline(ti_model_t h, int32_t token, int64_t* stamps, size_t cap, size_t* n_phases) {
+    return debug_timeline_run(h, token, stamps, cap, n_phases, nullptr, false);
+}
+int ti_b200_debug_timeline_all(ti_model_t h, int32_t token, int64_t* stamps, size_t cap, size_t* n_phases, size_t* n_ctas) {
+    return debug_timeline_run(h, token, stamps, cap, n_phases, n_ctas, true);
 }
 
 int ti_b200_bench_gemv(const ti_qweight_t* ws, size_t n_w, size_t reps, float* ms) {

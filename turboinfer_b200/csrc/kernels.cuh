@@ -406,7 +406,9 @@ __global__ void step_finish_kernel(StepState* st, const StepIO* io, const float*
     __syncthreads();
     if (threadIdx.x == 0) {
         if (sample) {
-            const int tok = 0x7FFFFFFF - (int)(uint32_t)(st->argmax_key & 0xFFFFFFFFull);
+            // key 0 = no logit compared greater than -inf (all NaN / -inf): defined as token 0, like the persistent kernel
+            int tok = st->argmax_key == 0ull ? 0 : 0x7FFFFFFF - (int)(uint32_t)(st->argmax_key & 0xFFFFFFFFull);
+            tok = min(max(tok, 0), V - 1);
             st->token = tok;
             if (io->out_tokens && step < io->out_cap) io->out_tokens[step] = tok;
             st->step = step + 1;

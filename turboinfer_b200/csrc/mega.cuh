@@ -85,6 +85,11 @@ TIB_HD size_t mega_smem_bytes(int stages, int max_kpad, int max_units, int attn_
     return gemv_smem_bytes_for(stages, max_kpad, max_units) + 16 + (size_t)attn_floats * 4 + 16 + 2 * ((sizeof(MegaPhase) + 15) & ~size_t(15));
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -103,6 +108,7 @@ __device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v)
 // rotation, each in its own 128-byte line; CTA 0 clears word (k-1) & 3 after passing barrier k (every CTA arrived at
 // k, so every CTA has finished reading k-1), three barriers before its next use.
 constexpr int kBarWords = 4, kBarStride = 32;   // in 32-bit units
+constexpr long long kBarWatchdog = 120000000000LL;   // ~60 s of SM clocks: a protocol bug traps instead of hanging the box; long enough for profiler replay and time slicing
 constexpr float kSsScale = 268435456.0f;         // 2^28: resolution 3.7e-9, range 6.9e10
 __device__ __forceinline__ void bar_arrive_stats(unsigned int* w, float ss, float am) {
     const unsigned long long q = __float2ull_rn(fminf(ss, 6.0e10f) * kSsScale);
@@ -473,6 +479,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
     __syncthreads();
 
     const int pos0 = m.st->pos;
+    const int step0 = m.st->step;   // read once: thread 0 bumps st->step at the end of the launch while other warps may still publish
     RingPos it;
 
     if (warp >= kConsumerWarps) {
@@ -538,6 +545,11 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                     }
                     const bool mgpu = m.tp > 1 && __ldg(&m.phases[ph].mgpu) == 1;
                     bar_sync(2, kConsumerThreads + 32);   // every consumer thread has stored its outputs and partials
+                    // debug timeline ([25] CTA done, [26] barrier passed: SM clock; [27], [28] the same on the global timer,
+                    // comparable across CTAs): how long each CTA waits for the slowest one
+                    long long* bts = (m.dbg != nullptr && s == 0 && lane == 0 && (blockIdx.x == 0 || (m.dbg_flags & 4)))
+                                         ? m.dbg + ((size_t)blockIdx.x * m.nphases + ph) * kStampsPerPhase : nullptr;
+                    if (bts) { bts[25] = clock64(); bts[27] = (long long)globaltimer_ns(); }
                     if (mgpu) {
                         // barrier across all GPUs: the partial outputs this CTA wrote into the peers' buffers become visible
                         // (system-scope release) before its arrival is counted on every rank's word
@@ -565,7 +577,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                         const long long t0 = clock64();
                         uint4 v = bar_poll(w);
                         while (v.x < gridDim.x) {
-                            if (clock64() - t0 > 8000000000LL) __trap();
+                            if (clock64() - t0 > kBarWatchdog) __trap();
                             v = bar_poll(w);
                         }
                         XStats st;
@@ -577,13 +589,16 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                         sm.red[2] = sc.s_x;
                         if (blockIdx.x == 0)
                             *reinterpret_cast<uint4*>(m.grid_bar + ((k + kBarWords - 1) & (kBarWords - 1)) * kBarStride) = make_uint4(0u, 0u, 0u, 0u);
+                        if (bts) { bts[26] = clock64(); bts[28] = (long long)globaltimer_ns(); }
                     }
                     ++k;
                     __syncwarp();
                     bar_arrive(3, kConsumerThreads + 32);  // barrier passed, scalars in sm.red[0..2]
                 }
             }
-            if (m.tp > 1 && blockIdx.x == 0 && lane == 0) *m.mg_seq = kk;
+            // the point-to-point variant keeps its own exchange count in the same word (written by consumer thread 0 at the
+            // end of the launch); this warp passes no barrier across the GPUs in that mode and must not write a stale value back
+            if (m.tp > 1 && !m.tp_p2p && blockIdx.x == 0 && lane == 0) *m.mg_seq = kk;
         }
         return;
     }
@@ -610,12 +625,15 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
     };
     auto decode_key = [&](int s) -> int {
         const unsigned long long key = __ldcg(&m.keys[s & 1]);
-        return 0x7FFFFFFF - (int)(uint32_t)(key & 0xFFFFFFFFull);
+        // key 0: no logit compared greater than -inf (all NaN / -inf): defined as token 0; the clamp keeps the embedding
+        // lookup of the next step inside the table whatever the key holds
+        const int tok = key == 0ull ? 0 : 0x7FFFFFFF - (int)(uint32_t)(key & 0xFFFFFFFFull);
+        return min(max(tok, 0), m.V - 1);
     };
     // CTA 0 publishes the token picked in step s (called by all its consumer threads, after that step's barrier)
     auto publish = [&](int s, int tok) {
         if (blockIdx.x != 0) return;
-        const int k = m.st->step + (s - m.first_sample);
+        const int k = step0 + (s - m.first_sample);
         if (m.io->hist && k < m.io->hist_cap)
             for (int i = tid; i < m.V; i += kConsumerThreads) m.io->hist[(size_t)k * m.V + i] = __ldcg(m.logits + i);
         if (tid == 0) {
@@ -639,8 +657,9 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
         for (int ph = 0; ph < m.nphases; ++ph) {
             const bool is_head = ph == m.nphases - 1;  // the lm_head is always the last phase
             if (is_head && !sample) continue;
-            const bool stamp = m.dbg != nullptr && s == 0 && blockIdx.x == 0 && tid == 0;
-            long long* ts = m.dbg + (size_t)ph * kStampsPerPhase;
+            // debug timeline: thread 0 of CTA 0 (dbg_flags & 4: of every CTA) stamps the SM clock along the phase
+            const bool stamp = m.dbg != nullptr && s == 0 && tid == 0 && (blockIdx.x == 0 || (m.dbg_flags & 4));
+            long long* ts = m.dbg + ((size_t)blockIdx.x * m.nphases + ph) * kStampsPerPhase;
             if (stamp) ts[0] = clock64();
             // Everything that does not depend on the previous phase's output happens BEFORE the grid barrier:
             // stage the phase descriptor in shared memory, fetch the epilogue's per-column constants.
