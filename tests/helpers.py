@@ -72,3 +72,25 @@ def rel_err_inf(got: np.ndarray, ref: np.ndarray) -> float:
     ref = np.asarray(ref, dtype=np.float64)
     denom = max(float(np.max(np.abs(ref))) if ref.size else 0.0, 1e-30)
     return float(np.max(np.abs(got - ref))) / denom if ref.size else 0.0
+
+
+def make_literal_model(vocab: int, hidden: int, layers: int) -> dict:
+    """create_test_model of benchmarks/benchmark_inference.cpp:145-225, fp32 arithmetic as written there:
+    (float(i % m) / float(m) - 0.5f) * amp.  q/k/v are present, o_proj is not (the attention fall-back), no gate, no norms."""
+    f = np.float32
+
+    def ramp(n, shift, mod, amp):
+        i = (np.arange(n, dtype=np.int64) + shift) % mod
+        return ((i.astype(np.float32) / f(mod) - f(0.5)) * f(amp)).astype(np.float32)
+
+    H, I = hidden, hidden * 4
+    w = {"token_embeddings.weight": ramp(vocab * H, 0, 1000, 0.1).reshape(vocab, H),
+         "lm_head.weight": ramp(H * vocab, 0, 500, 0.01).reshape(H, vocab)}
+    for l in range(layers):
+        p = f"layers.{l}."
+        w[p + "attention.q_proj.weight"] = ramp(H * H, 0, 100, 0.05).reshape(H, H)
+        w[p + "attention.k_proj.weight"] = ramp(H * H, 1, 100, 0.05).reshape(H, H)
+        w[p + "attention.v_proj.weight"] = ramp(H * H, 2, 100, 0.05).reshape(H, H)
+        w[p + "mlp.up_proj.weight"] = ramp(H * I, 0, 200, 0.02).reshape(H, I)
+        w[p + "mlp.down_proj.weight"] = ramp(I * H, 0, 200, 0.02).reshape(I, H)
+    return w

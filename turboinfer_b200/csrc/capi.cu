@@ -275,7 +275,7 @@ struct Layer {
     DevBuf<float> k_pool, v_pool;
     bool has_gate = false;
     // compat_literal: reference-layout fp32 (or integer-valued fp32) matrices
-    DevBuf<float> lit_up, lit_down;
+    DevBuf<float> lit_up, lit_down, lit_gate;
 };
 
 // Batched decode: B sequences in lockstep, each with its own pages of every layer's KV pools.
@@ -303,6 +303,8 @@ struct Model {
     RawTensor raw_lm;
     std::unique_ptr<QWeight> lm_head;
     DevBuf<float> lit_lm;
+    DevBuf<float> lit_x, lit_pa, lit_n, lit_u, lit_g, lit_f;   // compat_literal activations, sized for lit_rows rows
+    int lit_rows = 0;
     bool finalized = false;
     int page_tokens = 64, num_pages = 0;
     DevBuf<int> page_table;
@@ -1264,6 +1266,145 @@ int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
     return 0;
 }
 
+// ---- compat_literal: BASELINE.json configs[0], the path benchmarks/benchmark_inference runs today --------------------
+// The unmodified InferenceEngine::generate on create_test_model (benchmarks/benchmark_inference.cpp:145-225): placeholder
+// embeddings 0.1f*(i%100) over the flattened [1,T,H] index (token ids never reach the arithmetic), the
+// attention fall-back (a projection is missing: compute_attention returns its input, x <- x + n, :293-296), the FFN
+// x <- x + down(relu(up(n))) (or SwiGLU with a gate, :376-401), logits = x . lm_head; after quantize_model the integer
+// weights are cast to fp32 WITHOUT their scale.  Everything is fp32 in the reference build's order of
+// roundings (matmul_f32_exact_kernel), so the logits -- ties between identical lm_head columns included -- are the
+// reference's bit for bit, and the greedy pick can apply the reference's own rule to them (literal_pick).
+int literal_quantize(DevBuf<float>& w, int qtype) {
+    if (!w.p || (qtype != TI_Q_INT8 && qtype != TI_Q_INT4)) return 0;
+    DevBuf<float> sz;
+    DevBuf<uint32_t> mm;
+    TRY(sz.alloc(2));
+    TRY(mm.alloc(2));
+    TRY(device_quant_params(w.p, w.n, qtype, 1, sz.p, mm.p, g_stream));
+    literal_quant_kernel<<<grid_for(w.n), 256, 0, g_stream>>>(w.p, w.n, qtype, sz.p);
+    ++g_launches;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+int literal_finalize(Model& m) {
+    const int H = m.cfg.hidden, V = m.cfg.vocab;
+    if (!m.raw_lm.present()) return fail("lm_head.weight missing");
+    auto move = [](RawTensor& r, DevBuf<float>& d) { d = std::move(r.data); };
+    move(m.raw_lm, m.lit_lm);
+    TRY(literal_quantize(m.lit_lm, m.cfg.qtype));
+    for (auto& ly : m.layers) {
+        if (ly.raw_q.present() && ly.raw_k.present() && ly.raw_v.present() && ly.raw_o.present())
+            return fail("compat_literal reproduces benchmark_inference's model (no o_proj: the attention fall-back); a layer with a complete attention block needs the normal engine");
+        ly.raw_q.data.release(); ly.raw_k.data.release(); ly.raw_v.data.release(); ly.raw_o.data.release();   // unused by the reference too
+        if (ly.raw_up.present() && ly.raw_down.present()) {
+            move(ly.raw_up, ly.lit_up);
+            move(ly.raw_down, ly.lit_down);
+            if (ly.raw_gate.present()) move(ly.raw_gate, ly.lit_gate);
+            TRY(literal_quantize(ly.lit_up, m.cfg.qtype));
+            TRY(literal_quantize(ly.lit_down, m.cfg.qtype));
+            TRY(literal_quantize(ly.lit_gate, m.cfg.qtype));
+        }
+        ly.raw_up.data.release(); ly.raw_down.data.release(); ly.raw_gate.data.release();
+    }
+    TRY(m.logits.alloc(V));
+    TRY(m.state.alloc(1));
+    CK(cudaMemsetAsync(m.state.p, 0, sizeof(StepState), g_stream));
+    (void)H;
+    m.use_mega = false;
+    m.finalized = true;
+    m.host_pos = 0;
+    return 0;
+}
+// forward_pass over T rows (:1429-1491); only the last row's logits are sampled (:1571-1576)
+int literal_forward(Model& m, int T) {
+    const size_t H = m.cfg.hidden, I = std::max(m.cfg.inter, 1), V = m.cfg.vocab;
+    if (T > m.lit_rows) {
+        for (DevBuf<float>* b : {&m.lit_x, &m.lit_pa, &m.lit_n, &m.lit_f}) TRY(b->alloc((size_t)T * H));
+        for (DevBuf<float>* b : {&m.lit_u, &m.lit_g}) TRY(b->alloc((size_t)T * I));
+        m.lit_rows = T;
+    }
+    auto mm = [&](const float* a, const float* b, float* c, size_t M, size_t K, size_t N) {
+        matmul_f32_exact_kernel<<<dim3((unsigned)((N + 127) / 128), (unsigned)M), 128, 0, g_stream>>>(a, b, c, (int)M, (int)K, (int)N, 0);
+        ++g_launches;
+    };
+    auto ew = [&](const float* a, const float* b, float* y, size_t n, int op) {
+        elementwise_kernel<<<grid_for(n), 256, 0, g_stream>>>(a, b, y, n, op);
+        ++g_launches;
+    };
+    auto norm = [&](const float* x, const DevBuf<float>& w) -> const float* {
+        if (!w.p) return x;
+        rms_norm_kernel<<<(unsigned)T, 256, 0, g_stream>>>(x, w.p, m.lit_n.p, (int)H, m.cfg.rms_eps);
+        ++g_launches;
+        return m.lit_n.p;
+    };
+    literal_embed_kernel<<<grid_for((size_t)T * H), 256, 0, g_stream>>>(m.lit_x.p, (size_t)T * H);
+    ++g_launches;
+    for (auto& ly : m.layers) {
+        ew(m.lit_x.p, norm(m.lit_x.p, ly.attn_norm), m.lit_pa.p, (size_t)T * H, EW_ADD);           // x + attention fall-back (:264, :293-296)
+        const float* f = norm(m.lit_pa.p, ly.ffn_norm);
+        const float* ffn = f;                                                                        // compute_ffn returns its input (:377-380)
+        if (ly.lit_up.p && ly.lit_down.p) {
+            mm(f, ly.lit_up.p, m.lit_u.p, T, H, I);
+            if (ly.lit_gate.p) {
+                mm(f, ly.lit_gate.p, m.lit_g.p, T, H, I);
+                ew(m.lit_g.p, m.lit_u.p, m.lit_u.p, (size_t)T * I, EW_SILU_MUL);                     // multiply(up, silu(gate))
+            } else {
+                ew(m.lit_u.p, nullptr, m.lit_u.p, (size_t)T * I, EW_RELU);                           // :392-395
+            }
+            mm(m.lit_u.p, ly.lit_down.p, m.lit_f.p, T, I, H);
+            ffn = m.lit_f.p;
+        }
+        ew(m.lit_pa.p, ffn, m.lit_x.p, (size_t)T * H, EW_ADD);
+    }
+    // final norm over all rows (the fall-back norm buffer is free again), then the last row against lm_head
+    const float* hn = norm(m.lit_x.p, m.out_norm);
+    mm(hn + (size_t)(T - 1) * H, m.lit_lm.p, m.logits.p, 1, H, V);
+    CK(cudaGetLastError());
+    return 0;
+}
+// greedy = the top_k 1 branch of sample_next_token (:1585-1598): (logit, index) pairs, std::sort descending by logit,
+// element 0 survives.  The benchmark model's lm_head has identical columns (v and v + 500), so WHICH of the tied maxima
+// comes first is decided by the sort itself: apply the same std::sort to the same values.
+int literal_pick(const std::vector<float>& logits) {
+    std::vector<std::pair<float, int>> p;
+    p.reserve(logits.size());
+    for (size_t i = 0; i < logits.size(); ++i) p.emplace_back(logits[i], static_cast<int>(i));
+    std::sort(p.begin(), p.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+    return p[0].second;
+}
+int literal_generate(Model& m, int n_prompt, int n_new, int stop_on_eos, int32_t* out_tokens, int32_t* n_out, float* logits_host, float* decode_ms) {
+    const int V = m.cfg.vocab;
+    std::vector<float> logits(V);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    TRY(literal_forward(m, n_prompt));   // prefill (:749)
+    CK(cudaEventRecord(e0, g_stream));
+    int produced = 0, total = n_prompt;
+    for (int i = 0; i < n_new; ++i) {
+        CK(cudaMemcpyAsync(logits.data(), m.logits.p, (size_t)V * 4, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        if (logits_host) memcpy(logits_host + (size_t)i * V, logits.data(), (size_t)V * 4);
+        const int best = literal_pick(logits);
+        out_tokens[produced++] = best;
+        ++total;
+        if (stop_on_eos && best == 2) break;        // :760
+        if (total >= m.cfg.max_seq) break;          // max_sequence_length (:767)
+        if (i + 1 < n_new) TRY(literal_forward(m, 1));   // decode (:774): one row, position-independent
+    }
+    CK(cudaEventRecord(e1, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (decode_ms) *decode_ms = ms;
+    if (n_out) *n_out = produced;
+    m.host_pos = std::min(total, m.cfg.max_seq);
+    return 0;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -1788,7 +1929,10 @@ int ti_b200_model_finalize(ti_model_t h) {
     if (!mp) return fail("invalid model handle");
     Model& m = *mp;
     if (m.finalized) return 0;
-    if (m.cfg.compat_literal) return fail("compat_literal decode is not available in this build");
+    if (m.cfg.compat_literal) {
+        if (m.tp > 1) return fail("compat_literal is a single-GPU path");
+        return literal_finalize(m);
+    }
     const int H = m.cfg.hidden, V = m.cfg.vocab, I = m.cfg.inter;
     if (!m.tok_emb.p) return fail("token_embeddings.weight missing");
     if (!m.lm_head) return fail("lm_head.weight missing");  // the reference draws random logits here (:1544-1549); refuse instead
@@ -1927,6 +2071,16 @@ int ti_b200_decode_step(ti_model_t h, int32_t token, float* logits_host, int32_t
     if (!m || !m->finalized) return fail("invalid or unfinalized model handle");
     if (token < 0 || token >= m->cfg.vocab) return fail("token id %d out of range", token);
     TRY(check_capacity(*m, 1));
+    if (m->cfg.compat_literal) {   // one row, independent of the token and of the position
+        TRY(literal_forward(*m, 1));
+        std::vector<float> lg(m->cfg.vocab);
+        CK(cudaMemcpyAsync(lg.data(), m->logits.p, lg.size() * 4, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        if (logits_host) memcpy(logits_host, lg.data(), lg.size() * 4);
+        if (argmax) *argmax = literal_pick(lg);
+        m->host_pos += 1;
+        return 0;
+    }
     StepIO io{};
     CK(cudaMemcpyAsync(m->io.p, &io, sizeof(io), cudaMemcpyHostToDevice, g_stream));
     CK(cudaMemcpyAsync(&m->state.p->token, &token, sizeof(int), cudaMemcpyHostToDevice, g_stream));
@@ -1957,6 +2111,7 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
     for (int i = 0; i < n_prompt; ++i)
         if (prompt[i] < 0 || prompt[i] >= m.cfg.vocab) return fail("token id %d out of range", prompt[i]);
     TRY(ti_b200_model_reset(h));  // generate() resets the KV cache first (:746)
+    if (m.cfg.compat_literal) return literal_generate(m, n_prompt, n_new, stop_on_eos, out_tokens, n_out, logits_host, decode_ms);
     TRY(check_capacity(m, n_prompt + std::max(0, n_new - 1)));
     const int V = m.cfg.vocab;
     if ((int)m.prompt.n < n_prompt) TRY(m.prompt.alloc(n_prompt));

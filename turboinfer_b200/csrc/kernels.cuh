@@ -367,6 +367,19 @@ __global__ void embed_kernel(const float* emb, const StepState* st, float* x, in
         x[i] = literal ? 0.1f * (float)(i % 100) : emb[(size_t)tok * H + i];
 }
 
+// compat_literal (BASELINE.json configs[0], the literal benchmark_inference path):
+//   placeholder embeddings over the flattened [1,T,H] index (inference_engine.cpp:1444-1448, :1508-1512)
+__global__ void literal_embed_kernel(float* x, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = 0.1f * (float)(i % 100);
+}
+//   Quantizer::quantize_model (:89-118) followed by convert_dtype's cast WITHOUT the scale (tensor_engine.cpp:2218-2253,
+//   SURVEY R8): w <- float(q(w)), in place; sz = {scale, zero_point} of the whole tensor
+__global__ void literal_quant_kernel(float* w, size_t n, int qtype, const float* sz) {
+    const float scale = sz[0], zp = sz[1];
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        w[i] = (float)quantize_one(w[i], qtype, scale, zp);
+}
+
 // XStats of every embedding row against the norm weight of the first GEMV (gemv.cuh XStats): one block per row
 __global__ void emb_stats_kernel(const float* emb, const float* norm_w, XStats* out, int H) {
     __shared__ float red[64];

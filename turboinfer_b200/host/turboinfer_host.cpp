@@ -381,7 +381,11 @@ InferenceEngine::InferenceEngine(const ModelData& model_data, const InferenceCon
     cfg.inter = (int32_t)md.intermediate_size;
     cfg.rope_theta = md.rope_theta;
     cfg.rms_eps = 1e-5f;
-    cfg.qtype = param("b200.quantization", "int8") == "int4" ? TI_Q_INT4 : TI_Q_INT8;
+    const std::string quant = param("b200.quantization", "int8");
+    cfg.qtype = quant == "int4" ? TI_Q_INT4 : (quant == "none" ? TI_Q_NONE : TI_Q_INT8);
+    // "literal": the path benchmarks/benchmark_inference runs on the reference today (placeholder embeddings, attention
+    // fall-back, unscaled integer weights; quantization "none" = its FP32 variant) -- BASELINE.json configs[0]
+    cfg.compat_literal = param("b200.compat", "") == "literal" ? 1 : 0;
     cfg.attn_mode = param("b200.attention", "multi_head") == "single_head" ? 0 : 1;
     const std::string rope = param("b200.rope", "per_head");
     cfg.rope_mode = rope == "none" ? 0 : (rope == "hidden" ? 2 : 1);
