@@ -146,6 +146,7 @@ int set_kernel_attrs() {
     CK(cudaFuncSetAttribute(attn_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CK(cudaFuncSetAttribute(mega_decode_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(mega_decode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(mega_decode_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(gemm_i8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmemBytes));
     CK(cudaFuncSetAttribute(gemm_i8_tc_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmemBytes));
     CK(cudaFuncSetAttribute(rmsnorm_digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -921,6 +922,10 @@ int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
     }
     void* args[] = {&a};
     const void* fn = m.cfg.qtype == TI_Q_INT4 ? (const void*)mega_decode_kernel<4> : (const void*)mega_decode_kernel<8>;
+    if (m.dbg_on) {   // the timeline instance exists for INT4 only (compile time)
+        if (m.cfg.qtype != TI_Q_INT4) return fail("the debug timeline is compiled for INT4 models only");
+        fn = (const void*)mega_decode_kernel<4, true>;
+    }
     CK(cudaLaunchCooperativeKernel(fn, dim3(g_num_sms), dim3(kMegaThreads), args, m.mega_smem, g_stream));
     ++g_launches;
     return 0;

@@ -161,46 +161,45 @@ __device__ __forceinline__ unsigned long long argmax_pack(float v, int idx) {
 }
 
 // ---- shared-memory carve-up ------------------------------------------------------------------------
+// The block starts at the kernel's dynamic shared memory (declared 128-byte aligned) and is carved with plain pointer
+// arithmetic on that array: the compiler then knows every pointer is a shared-memory one and emits LDS / STS / ATOMS and
+// constant shared-window addresses.  (Carving through uintptr_t, as the first version did, loses the address space: every
+// access became a generic LD / ST / ATOM, several times slower, and every barrier address a ~10-instruction conversion.)
+// The mbarriers and the ring come first so that their addresses are compile-time offsets from the base.
+constexpr int kBarBlockBytes = 128;   // full[kMaxStages], empty[kMaxStages], padding
 struct GemvSmem {
+    uint64_t* full;     // [stages]
+    uint64_t* empty;    // [stages]
     uint8_t* ring;      // stages * 32 KiB
     uint8_t* xd;        // digit planes of x: 3 * kpad bytes
     int* acc;           // [ncols][3] integer column sums
     float* red;         // 128 floats of reduction scratch
     long long* sxf;     // [16] per-warp partial sums of xf over k
     unsigned int* spare;         // 128 spare bytes
-    uint64_t* full;     // [stages]
-    uint64_t* empty;    // [stages]
 };
 
 TIB_HD size_t gemv_smem_bytes_for(int stages, int kpad, int max_units) {
-    size_t b = (size_t)stages * kStageBytes;
+    size_t b = kBarBlockBytes;
+    b += (size_t)stages * kStageBytes;
     b += (size_t)3 * kpad;
     b += (size_t)max_units * 4 * 3 * 4;
     b += 128 * 4 + 32 * 8;
-    b += (size_t)2 * kMaxStages * 8;
     return b + 128;
 }
 TIB_HD size_t gemv_smem_bytes(const QLayout& L, int stages) { return gemv_smem_bytes_for(stages, layout_kpad(L), slab_max_units(L)); }
 
+// `base` must be the (128-byte aligned) dynamic shared memory array itself
 __device__ __forceinline__ GemvSmem gemv_carve_for(uint8_t* base, int stages, int kpad, int max_units, uint8_t** end = nullptr) {
     GemvSmem s;
-    uintptr_t p = (reinterpret_cast<uintptr_t>(base) + 127) & ~uintptr_t(127);
-    s.ring = reinterpret_cast<uint8_t*>(p);
-    p += (size_t)stages * kStageBytes;
-    s.xd = reinterpret_cast<uint8_t*>(p);
-    p += (size_t)3 * kpad;   // kpad is a multiple of 128: stays 16-byte aligned
-    s.acc = reinterpret_cast<int*>(p);
-    p += (size_t)max_units * 4 * 3 * 4;
-    s.red = reinterpret_cast<float*>(p);
-    p += 128 * 4;
-    s.sxf = reinterpret_cast<long long*>(p);
-    p += 16 * 8;
-    s.spare = reinterpret_cast<unsigned int*>(p);
-    p += 16 * 8;
-    s.full = reinterpret_cast<uint64_t*>(p);
+    s.full = reinterpret_cast<uint64_t*>(base);
     s.empty = s.full + kMaxStages;
-    p += (size_t)2 * kMaxStages * 8;
-    if (end) *end = reinterpret_cast<uint8_t*>(p);
+    s.ring = base + kBarBlockBytes;
+    s.xd = s.ring + (size_t)stages * kStageBytes;
+    s.acc = reinterpret_cast<int*>(s.xd + (size_t)3 * kpad);   // kpad is a multiple of 128: stays 16-byte aligned
+    s.red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(s.acc) + (size_t)max_units * 4 * 3 * 4);
+    s.sxf = reinterpret_cast<long long*>(s.red + 128);
+    s.spare = reinterpret_cast<unsigned int*>(s.sxf + 16);
+    if (end) *end = reinterpret_cast<uint8_t*>(s.spare + 32);
     return s;
 }
 __device__ __forceinline__ GemvSmem gemv_carve(uint8_t* base, const QLayout& L, int stages) {
@@ -481,26 +480,45 @@ __device__ __forceinline__ ConsumePlan make_consume_plan(const QLayout& L, const
     p.l_fq = warp_first_quad(slab, lane & 15);
     return p;
 }
+// DBG: 0 production; 1 = no MMAs, 2 = no barrier waits (stand-alone kernel experiments); 3 = timeline stamps through `dbg`
+// (the persistent kernel's debug instance; `xskip` then also takes the timing switches 8 = no MMAs, 16 = no digit loads).
+//
+// The loop is written for the instruction issue slots: a round is only 4 k-items per warp (4 LDS.128 of weights, 4 of
+// digits, 8 IMMA and -- INT4 -- 32 mask LOP3), so every instruction of bookkeeping around them shows: the first version of
+// this loop ran ~170 instructions per round and warp and was issue-bound at 0.8 us per stage with the whole ring already in
+// shared memory (profiles/r02_timeline_*: `rounds`).  Hence: barrier and stage addresses as 32-bit shared-window values
+// advanced incrementally, the per-round offset sum (REDUX) only on rounds that can be ragged -- a warp whose quad is not in
+// the slab's last group has only full quads before it, so its offset is 4 * warp items -- and no debug code in the
+// production instance.
 template <int BITS, int DBG = 0>
 __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab, const GemvSmem& sm, RingPos& it, const ConsumePlan& pl,
-                                             int warp, int lane, long long* dbg = nullptr, bool ready0 = false) {
-    const QLayout& L = a.L;
-    const int S = a.stages;
-    const int C = L.nchunks, nrounds = slab.rounds;
+                                             int warp, int lane, long long* dbg = nullptr, bool ready0 = false, int xskip = 0) {
+    const uint32_t S = (uint32_t)a.stages;
+    const int C = a.L.nchunks, nrounds = slab.rounds;
     constexpr int kChunkBytes = BITS == 4 ? 768 : 384;   // digits of one chunk: 4 k-items x 3 planes x 4 t x 16 / 8 B
     constexpr int kXItem = kChunkBytes / 4;
     const int my_nq = pl.my_nq;
     int grp = pl.grp, chunk = pl.chunk;   // group / chunk of the warp's next quad
     const int g = lane >> 2, t = lane & 3;
     const uint32_t xlane = smem_u32(sm.xd) + ((g < 3 ? g : 0) * 4 + t) * (BITS == 4 ? 16 : 8);   // B column g = digit plane g
-    const uint32_t ring_base = smem_u32(sm.ring);
-    // lane l < 16 stands for warp l when the stage offsets are summed with one REDUX per round
+    const uint32_t ring0 = smem_u32(sm.ring), full0 = smem_u32(sm.full), empty0 = smem_u32(sm.empty);
+    // lane l < 16 stands for warp l when the stage offsets are summed with one REDUX (ragged rounds only)
     const int l_nq = pl.l_nq, l_fq = pl.l_fq;
     const bool l_before = lane < warp;  // warp < 16
+    const int last_grp = slab.nlast == 4 ? -1 : slab.ngroups - 1;   // the only group whose quads are smaller than 4 items
     QuadAcc<BITS> acc;
     acc.clear();
     bool dirty = false;
-    if (dbg) dbg[6] = clock64();
+    if (DBG == 3 && dbg != nullptr) {
+        dbg[6] = clock64();
+        // how many ring stages have landed when the loop starts (the producer runs ahead during the hand-over), and how many
+        // rounds the slab has; dbg[-10 .. -6] below = completion time of rounds 0..4
+        int nready = 0;
+        RingPos probe = it;
+        for (int i = 0; i < (int)S && i < nrounds; ++i, probe.advance(S)) nready += mbar_test_wait(&sm.full[probe.st], probe.par) ? 1 : 0;
+        dbg[-1] = nready;
+        dbg[5] = nrounds;
+    }
     auto flush = [&]() {
         // C fragment: c0, c1 = (row g, B columns 2t, 2t+1), c2, c3 = (row g + 8, same columns); B column = digit plane
         const int rows = grp == slab.ngroups - 1 ? 4 * slab.nlast : 16;
@@ -518,67 +536,84 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
         acc.clear();
         dirty = false;
     };
+    auto one = [&](int i, const uint4& wv, const uint4& xv) {
+        if (DBG == 1 || (DBG == 3 && (xskip & 8))) acc.lo[0][0] += (int)(wv.x ^ wv.y ^ wv.z ^ wv.w);
+        else kitem_mma<BITS>(acc, i & 1, wv, xv);
+    };
+    // ring position as addresses: the warp's slot of the current stage, its two barriers, the parity of the current use
+    uint32_t st = it.st, par = it.par;
+    uint32_t stage = ring0 + st * kStageBytes, fullb = full0 + st * 8, emptyb = empty0 + st * 8;
+    uint32_t xq = xlane + chunk * kChunkBytes;
+    const uint32_t wfast = (uint32_t)(warp * 4 * kItemBytes + lane * 16);   // offset in the stage when every warp before has a full quad
     // the NEXT stage's barrier is probed while this stage is being multiplied; the first one may have been probed by the
     // caller during its prologue (polling an mbarrier costs 0.1-0.2 us even when its phase is long complete)
     bool ready = ready0;
-    for (int r = 0; r < nrounds; ++r, it.advance(S)) {
-        const uint32_t st = it.st, par = it.par;
+    for (int r = 0; r < nrounds; ++r) {
         const bool have = r < my_nq;
-        // 512-byte items of the warps before this one in the stage
-        const int l_items = (l_before && r < l_nq) ? (l_fq + r >= slab.qfull ? slab.nlast : 4) : 0;
-        const int woff = __reduce_add_sync(0xffffffffu, l_items);
-        const uint32_t xq = xlane + chunk * kChunkBytes;
-        uint4 xa, xb;
-        if (have) {   // digits of the first two k-items: they do not depend on the stage, so before the wait
-            xa = load_xfrag<BITS>(xq);
-            xb = load_xfrag<BITS>(xq + kXItem);
-        }
-        if (dbg && r == 0) dbg[7] = clock64();
-        if (DBG != 2 && !ready) mbar_wait(&sm.full[st], par);
-        if (dbg && r == 0) dbg[0] = clock64();
-        ready = false;
-        RingPos nx = it;
-        nx.advance(S);
-        if (have) {
-            const int nl = grp == slab.ngroups - 1 ? slab.nlast : 4;
-            const uint32_t qbase = ring_base + st * kStageBytes + woff * kItemBytes;
-            auto one = [&](int i, const uint4& wv, const uint4& xv) {
-                if (DBG != 1) kitem_mma<BITS>(acc, i & 1, wv, xv);
-                else acc.lo[0][0] += (int)(wv.x ^ wv.y ^ wv.z ^ wv.w);
-            };
-            if (nl == 4) {  // the common case, straight-line, two k-items at a time (register budget)
-                const uint32_t wbase = qbase + lane * 16;
-                const uint4 w0 = lds128s(wbase), w1 = lds128s(wbase + 512);
-                one(0, w0, xa); one(1, w1, xb);
-                const uint4 w2 = lds128s(wbase + 1024), w3 = lds128s(wbase + 1536);
+        uint32_t nstage = stage + kStageBytes, nfull = fullb + 8, nempty = emptyb + 8, npar = par;
+        if (++st == S) { st = 0; npar ^= 1u; nstage = ring0; nfull = full0; nempty = empty0; }
+        if (have && grp != last_grp) {
+            // ---- fast path: a full quad, and only full quads before it in the stage ----
+            uint4 xa, xb;
+            if (!(DBG == 3 && (xskip & 16))) {   // digits of the first two k-items: they do not depend on the stage, so before the wait
+                xa = load_xfrag<BITS>(xq);
+                xb = load_xfrag<BITS>(xq + kXItem);
+            } else {
+                xa = xb = make_uint4(1u, 2u, 3u, 4u);
+            }
+            if constexpr (DBG == 3) { if (dbg && r == 0) dbg[7] = clock64(); }
+            if (DBG != 2 && !ready) mbar_wait_s(fullb, par);
+            if constexpr (DBG == 3) { if (dbg && r == 0) dbg[0] = clock64(); }
+            const uint32_t wbase = stage + wfast;
+            const uint4 w0 = lds128s(wbase), w1 = lds128s(wbase + 512);
+            one(0, w0, xa); one(1, w1, xb);
+            const uint4 w2 = lds128s(wbase + 1024), w3 = lds128s(wbase + 1536);
+            if (!(DBG == 3 && (xskip & 16))) {
                 xa = load_xfrag<BITS>(xq + 2 * kXItem);
                 xb = load_xfrag<BITS>(xq + 3 * kXItem);
-                if (DBG != 2 && r + 1 < nrounds) ready = mbar_test_wait(&sm.full[nx.st], nx.par);
-                one(2, w2, xa); one(3, w3, xb);
-            } else {        // ragged last group of the slab: rows 0..7 in part A, rows 8..11 (nl = 3) in part B
+            }
+            ready = (DBG != 2 && r + 1 < nrounds) ? mbar_test_wait_s(nfull, npar) : false;
+            one(2, w2, xa); one(3, w3, xb);
+            dirty = true;
+            xq += kChunkBytes;
+            if (++chunk == C) { flush(); chunk = 0; ++grp; xq = xlane; }
+        } else {
+            // ---- generic path: ragged last group (quads of nlast items), or no quad for this warp in the last round ----
+            const int l_items = (l_before && r < l_nq) ? (l_fq + r >= slab.qfull ? slab.nlast : 4) : 0;
+            const int woff = __reduce_add_sync(0xffffffffu, l_items);   // 512-byte items of the warps before this one in the stage
+            if constexpr (DBG == 3) { if (dbg && r == 0) dbg[7] = clock64(); }
+            if (DBG != 2 && !ready) mbar_wait_s(fullb, par);
+            if constexpr (DBG == 3) { if (dbg && r == 0) dbg[0] = clock64(); }
+            ready = (DBG != 2 && r + 1 < nrounds) ? mbar_test_wait_s(nfull, npar) : false;
+            if (have) {
+                const int nl = slab.nlast;   // rows 0..7 in part A, rows 8..11 (nl = 3) in part B
                 const bool in_a = nl > 1 || lane < 16, in_b = nl == 3 && lane < 16;
-                const uint32_t wbase = qbase + lane * 8;
+                const uint32_t wbase = stage + woff * kItemBytes + lane * 8;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     uint2 pa = make_uint2(0u, 0u), pb = make_uint2(0u, 0u);
                     if (in_a) pa = lds64s(wbase + i * nl * 128);
                     if (in_b) pb = lds64s(wbase + i * nl * 128 + 256);
-                    if (i == 2) xa = load_xfrag<BITS>(xq + 2 * kXItem);
-                    if (i == 3) xb = load_xfrag<BITS>(xq + 3 * kXItem);
-                    one(i, make_uint4(pa.x, pb.x, pa.y, pb.y), (i & 1) ? xb : xa);
+                    const uint4 xv = load_xfrag<BITS>(xq + i * kXItem);
+                    one(i, make_uint4(pa.x, pb.x, pa.y, pb.y), xv);
                 }
+                dirty = true;
+                xq += kChunkBytes;
+                if (++chunk == C) { flush(); chunk = 0; ++grp; xq = xlane; }
             }
-            dirty = true;
-            if (++chunk == C) { flush(); chunk = 0; ++grp; }
         }
         __syncwarp();
-        if (DBG != 2 && lane == 0) mbar_arrive(&sm.empty[st]);  // this warp is done reading the stage
+        if (DBG != 2 && lane == 0) mbar_arrive_s(emptyb);  // this warp is done reading the stage
+        if constexpr (DBG == 3) { if (dbg && r < 5) dbg[r - 10] = clock64(); }
+        stage = nstage; fullb = nfull; emptyb = nempty; par = npar;
     }
-    if (dbg) dbg[1] = clock64();
+    it.st = st;
+    it.par = par;
+    if constexpr (DBG == 3) { if (dbg) dbg[1] = clock64(); }
     if (dirty) flush();
-    if (dbg) dbg[2] = clock64();
+    if constexpr (DBG == 3) { if (dbg) dbg[2] = clock64(); }
     bar_sync(1, kConsumerThreads);
-    if (dbg) dbg[3] = clock64();
+    if constexpr (DBG == 3) { if (dbg) dbg[3] = clock64(); }
 }
 
 // Values the epilogue needs that do not depend on this phase's arithmetic; loaded early (before the grid barrier
@@ -722,7 +757,7 @@ __device__ __forceinline__ void gemv_init_barriers(const GemvSmem& sm, int stage
 // ---- the stand-alone kernel: one GEMV per launch -----------------------------------------------------------
 template <int BITS, int DBG = 0>
 __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const __grid_constant__ GemvArgs a) {
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const Slab slab = make_slab(a.L, blockIdx.x);
     const GemvSmem sm = gemv_carve(smem_raw, a.L, a.stages);

@@ -460,21 +460,21 @@ __device__ __forceinline__ float mega_attention(const AttnArgs& a, int t, unsign
 // warpgroup-wide instruction, so the producer warp comes with three idle siblings (warps 17..19) that only execute
 // the shrink and exit: the CTA has 20 warps.
 constexpr int kMegaThreads = (kConsumerWarps + 4) * 32;  // 640
-template <int BITS>
+// TL: the debug-timeline instance (SM-clock stamps along every phase, m.dbg); the production instance carries none of it
+template <int BITS, bool TL = false>
 __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaArgs m) {
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // carve: ring | x digits | column sums | reduction scratch | mbarriers | attention scratch | phase descriptor
+    // carve: mbarriers | ring | x digits | column sums | reduction scratch | attention scratch | phase descriptors -- plain
+    // pointer arithmetic on the shared array (every block is a multiple of 16 bytes), so that the accesses stay LDS / STS
     uint8_t* tail = nullptr;
     const GemvSmem sm = gemv_carve_for(smem_raw, m.stages, m.max_kpad, m.max_units, &tail);
-    uintptr_t p = (reinterpret_cast<uintptr_t>(tail) + 15) & ~uintptr_t(15);
-    float* attn_sm = reinterpret_cast<float*>(p);
-    p += (size_t)m.attn_floats * 4;
-    p = (p + 15) & ~uintptr_t(15);
+    float* attn_sm = reinterpret_cast<float*>(tail);
+    uint8_t* const ptail = tail + (((size_t)m.attn_floats * 4 + 15) & ~size_t(15));
     // the phase descriptors, staged by the consumers; two slots: a warp may already stage the next phase's while another
     // still reads this phase's in its epilogue (nobody is more than one barrier ahead)
-    MegaPhase* const sph0 = reinterpret_cast<MegaPhase*>(p);
-    MegaPhase* const sph1 = reinterpret_cast<MegaPhase*>(p + ((sizeof(MegaPhase) + 15) & ~size_t(15)));
+    MegaPhase* const sph0 = reinterpret_cast<MegaPhase*>(ptail);
+    MegaPhase* const sph1 = reinterpret_cast<MegaPhase*>(ptail + ((sizeof(MegaPhase) + 15) & ~size_t(15)));
     if (tid == 0) gemv_init_barriers(sm, m.stages);
     __syncthreads();
 
@@ -547,7 +547,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                     bar_sync(2, kConsumerThreads + 32);   // every consumer thread has stored its outputs and partials
                     // debug timeline ([25] CTA done, [26] barrier passed: SM clock; [27], [28] the same on the global timer,
                     // comparable across CTAs): how long each CTA waits for the slowest one
-                    long long* bts = (m.dbg != nullptr && s == 0 && lane == 0 && (blockIdx.x == 0 || (m.dbg_flags & 4)))
+                    long long* bts = (TL && m.dbg != nullptr && s == 0 && lane == 0 && (blockIdx.x == 0 || (m.dbg_flags & 4)))
                                          ? m.dbg + ((size_t)blockIdx.x * m.nphases + ph) * kStampsPerPhase : nullptr;
                     if (bts) { bts[25] = clock64(); bts[27] = (long long)globaltimer_ns(); }
                     if (mgpu) {
@@ -614,7 +614,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
         if (lane == 0) { sm.red[32 + warp] = st.ss; sm.red[48 + warp] = st.am; }
         __syncwarp();
         bar_arrive(2, kConsumerThreads + 32);   // does not wait: on to the next phase's pre-barrier work
-        if (ts) ts[21] = clock64();
+        if (TL && ts) ts[21] = clock64();
         need_wait = true;
     };
     // waits until every CTA has finished the phase last arrived on; the next prologue's scalars are then in sm.red[0..2]
@@ -658,7 +658,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
             const bool is_head = ph == m.nphases - 1;  // the lm_head is always the last phase
             if (is_head && !sample) continue;
             // debug timeline: thread 0 of CTA 0 (dbg_flags & 4: of every CTA) stamps the SM clock along the phase
-            const bool stamp = m.dbg != nullptr && s == 0 && tid == 0 && (blockIdx.x == 0 || (m.dbg_flags & 4));
+            const bool stamp = TL && m.dbg != nullptr && s == 0 && tid == 0 && (blockIdx.x == 0 || (m.dbg_flags & 4));
             long long* ts = m.dbg + ((size_t)blockIdx.x * m.nphases + ph) * kStampsPerPhase;
             if (stamp) ts[0] = clock64();
             // Everything that does not depend on the previous phase's output happens BEFORE the grid barrier:
@@ -711,7 +711,11 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                     const bool ready0 = slab.rounds > 0 && mbar_test_wait(&sm.full[it.st], it.par);
                     const float s_x = gemv_stage_x_lean<BITS>(g, x, sm, slab, !from_emb, xsc, xpre, (m.dbg_flags & 1) != 0, tid, lane, stamp ? ts + 13 : nullptr);
                     if (stamp) ts[2] = clock64();
-                    gemv_consume<BITS>(g, slab, sm, it, plan, warp, lane, stamp ? ts + 17 : nullptr, ready0);
+                    if constexpr (TL) {   // every thread runs the same instance (the loop holds warp-collective instructions)
+                        gemv_consume<BITS, 3>(g, slab, sm, it, plan, warp, lane, stamp ? ts + 17 : nullptr, ready0, m.dbg_flags & 24);
+                    } else {
+                        gemv_consume<BITS, 0>(g, slab, sm, it, plan, warp, lane, nullptr, ready0);
+                    }
                     if (stamp) ts[3] = clock64();
                     out_st = gemv_epilogue(g, slab, sm, s_x, resid, ctx, pre, tid, lane);
                 }
