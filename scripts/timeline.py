@@ -26,7 +26,7 @@ for i, r in enumerate(ts):
     nm = names[i % 5] if i < len(ts) - 1 else "lm_head"
     u = lambda a, b: (r[b] - r[a]) * f if r[a] > 0 and r[b] > 0 else 0.0
     if nm == "attn":
-        line = f"{i:3d} {nm:7s} | {u(0,12):5.2f} {u(12,1):5.2f} | {'':29s} | {'':29s} | {u(1,4):4.2f} | {u(4,21):4.2f}  0.00 0.00 ={u(4,5):5.2f} | {u(0,5):6.2f}"
+        line = f"{i:3d} {nm:7s} | {u(0,12):5.2f} {u(12,1):5.2f} | {'':29s} | {'':29s} | {u(1,4):4.2f} | {u(4,21):4.2f}  0.00 0.00 ={u(4,5):5.2f} | {u(0,5):6.2f}   attn: entry {u(1,11):.2f} issue {u(11,16):.2f} loads+dot {u(16,22):.2f} softmax+rest {u(22,7):.2f} | kv+softmax {u(1,7):.2f} warp-merge+store {u(7,8):.2f} atomic {u(8,9):.2f} head-merge {u(9,10):.2f}"
     else:
         line = (f"{i:3d} {nm:7s} | {u(0,12):5.2f} {u(12,1):5.2f} | {u(6,13):5.2f} {u(13,14):5.2f} {u(14,15):4.2f} {u(15,2):4.2f} ={u(1,2):5.2f} | "
                 f"{u(2,23):4.2f}+{u(23,24):4.2f}+{u(24,17):4.2f} {u(17,18):5.2f} {u(18,19):5.2f} {u(19,3):4.2f} ={u(2,3):6.2f} | {u(3,4):4.2f} | {u(4,21):4.2f}  0.00 0.00 ={u(4,5):5.2f} | {u(0,5):6.2f}  "

@@ -87,7 +87,8 @@ _inited = False
 
 
 def library_path() -> str:
-    return os.path.join(HERE, "libturboinfer_b200.so")
+    # TURBOINFER_B200_LIB: an alternative build of the same library (A/B experiments with compile-time switches)
+    return os.environ.get("TURBOINFER_B200_LIB") or os.path.join(HERE, "libturboinfer_b200.so")
 
 
 def lib() -> C.CDLL:
@@ -96,7 +97,7 @@ def lib() -> C.CDLL:
     if _lib is None:
         path = library_path()
         srcdir = os.path.join(HERE, "csrc")
-        if os.path.isdir(srcdir) and os.path.exists("/usr/local/cuda/bin/nvcc"):
+        if os.path.isdir(srcdir) and os.path.exists("/usr/local/cuda/bin/nvcc") and not os.environ.get("TURBOINFER_B200_LIB"):
             from . import build as _build
             _build.build()
         if not os.path.exists(path):

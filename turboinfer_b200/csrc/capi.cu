@@ -500,6 +500,7 @@ int enqueue_attention(Model& m, Layer& ly, cudaStream_t st) {
     a.v_pool = ly.v_pool.p;
     a.page_table = m.page_table.p;
     a.page_tokens = m.page_tokens;
+    a.page_shift = log2_if_pow2(m.page_tokens);
     a.pos_ptr = &m.state.p->pos;
     a.t_bias = 1;
     a.H = m.cfg.hidden / m.tp;
@@ -714,6 +715,8 @@ int build_mega(Model& m) {
         ph.push_back(p);
     };
     const int mega_splits = std::max(1, std::min(g_num_sms / m.attn_heads, m.max_splits));
+    bool lean_attn = m.attn_dim <= 128 && log2_if_pow2(m.page_tokens) >= 0;   // mega.cuh attn_item_lean + deferred merge
+    if (const char* e = getenv("TURBOINFER_B200_LEAN_ATTN")) lean_attn = lean_attn && atoi(e) != 0;   // A/B experiments
     const bool tp = m.tp > 1;
     const int Hl = H / m.tp;   // this rank's share of the attention width (its heads)
     float* part[2] = {nullptr, nullptr};
@@ -758,18 +761,20 @@ int build_mega(Model& m) {
         at.at.v_pool = ly.v_pool.p;
         at.at.page_table = m.page_table.p;
         at.at.page_tokens = m.page_tokens;
+        at.at.page_shift = lean_attn ? log2_if_pow2(m.page_tokens) : -1;   // -1: the in-phase merge of mega_attention
         at.at.pos_ptr = &m.state.p->pos;
         at.at.t_bias = 1;
         at.at.H = Hl;
         at.at.D = m.attn_dim;
         at.at.heads = m.attn_heads;
         at.at.max_splits = mega_splits;
-        at.at.min_chunk = 64;
+        at.at.min_chunk = lean_attn ? 320 : 64;   // lean item: 16 warps x 5 tokens in flight = one round trip per 80 tokens; up to 4 round trips before a split pays
         at.at.scale = 1.0f / sqrtf((float)m.attn_dim);
         at.at.part_o = m.part_o.p;
         at.at.part_ml = m.part_ml.p;
         at.at.out = m.attn_out.p;
         ph.push_back(at);
+        const int o_src = SRC_PTR;
         GemvArgs o{};
         o.x = m.attn_out.p;
         if (tp && m.tp_p2p) {   // row-parallel: partial output to every rank, the P CTAs of a column slice meet and reduce it
@@ -777,13 +782,15 @@ int build_mega(Model& m) {
             o.resid = m.x.p;
             o.out = m.x.p;
             o.next_norm_w = ly.ffn_norm.p;
-            gemv_phase(*ly.o, o, SRC_PTR, src0, 0);
+            gemv_phase(*ly.o, o, o_src, src0, 0);
+            ph.back().at = at.at;
             ph.back().mgpu = 2;
             ph.back().part_sel = 0;
         } else if (tp) {   // row-parallel: partial output to every rank, barrier across the GPUs, then the reduce phase
             o.epi = EPI_STORE;
             o.out = part[0];
-            gemv_phase(*ly.o, o, SRC_PTR, SRC_PTR, 0);
+            gemv_phase(*ly.o, o, o_src, SRC_PTR, 0);
+            ph.back().at = at.at;
             ph.back().mgpu = 1;
             ph.back().part_sel = 0;
             reduce_phase(0, src0, ly.ffn_norm.p);
@@ -792,7 +799,8 @@ int build_mega(Model& m) {
             o.resid = m.x.p;
             o.out = m.x.p;
             o.next_norm_w = ly.ffn_norm.p;
-            gemv_phase(*ly.o, o, SRC_PTR, src0, 0);
+            gemv_phase(*ly.o, o, o_src, src0, 0);
+            ph.back().at = at.at;
         }
         GemvArgs g{};
         g.x = m.x.p;
@@ -842,9 +850,9 @@ int build_mega(Model& m) {
     int max_stages = kMaxStages;
     if (const char* e = getenv("TURBOINFER_B200_STAGES")) max_stages = std::max(2, std::min(kMaxStages, atoi(e)));   // experiments
     for (int s = max_stages; s >= 2; --s)
-        if (mega_smem_bytes(s, max_kpad, max_units, m.mega_attn_floats) <= 227 * 1024) { m.mega_stages = s; break; }
+        if (mega_smem_bytes(s, max_kpad, max_units, m.mega_attn_floats, m.num_pages) <= 227 * 1024) { m.mega_stages = s; break; }
     if (m.mega_stages == 0) return fail("persistent kernel does not fit shared memory");
-    m.mega_smem = mega_smem_bytes(m.mega_stages, max_kpad, max_units, m.mega_attn_floats);
+    m.mega_smem = mega_smem_bytes(m.mega_stages, max_kpad, max_units, m.mega_attn_floats, m.num_pages);
     for (auto& p : ph) p.g.stages = m.mega_stages;
     m.nphases = (int)ph.size();
     TRY(m.phases.alloc(ph.size()));
@@ -904,6 +912,8 @@ int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
     a.attn_floats = m.mega_attn_floats;
     a.dbg = m.dbg_on ? m.dbg.p : nullptr;
     a.emb_stats = m.emb_stats.p;
+    a.kv_page_table = m.page_table.p;
+    a.kv_pages = m.num_pages;
     a.dbg_flags = getenv("TURBOINFER_B200_DBG_FLAGS") ? atoi(getenv("TURBOINFER_B200_DBG_FLAGS")) : 0;
     if (m.dbg_on && m.dbg_all) a.dbg_flags |= 4;   // every CTA stamps
     a.tp = m.tp_fused ? m.tp : 1;
@@ -1217,6 +1227,7 @@ int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
         a.v_pool = bs.v[l].p;
         a.page_table = bs.tables.p;
         a.page_tokens = m.page_tokens;
+    a.page_shift = log2_if_pow2(m.page_tokens);
         a.pos_ptr = bs.pos_step.p;
         a.t_bias = 1;
         a.H = Hl;
@@ -1856,6 +1867,7 @@ int ti_b200_attention_decode(const float* q_host, const float* k_host, const flo
         a.v_pool = v.p + b * t * H;
         a.page_table = table.p;
         a.page_tokens = page_tokens;
+        a.page_shift = log2_if_pow2(page_tokens);
         a.pos_ptr = pos.p;
         a.t_bias = 0;
         a.H = (int)H;

@@ -115,24 +115,32 @@ __device__ __forceinline__ void imma_s8s8(int (&d)[4], uint32_t a0, uint32_t a1,
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// Accumulators of one warp for the group it is working on.  INT4: lo[] collects the low-nibble MMAs, hi[] the
-// high-nibble ones (operands 16x too large: total = lo + (hi >> 4), exact); two sets each so that consecutive
-// k-items do not wait on one another.  INT8: lo[] only.
+// Accumulators of one warp for the group it is working on.  INT4: lo collects the low-nibble MMAs, hi the high-nibble ones
+// (operands 16x too large: total = lo + (hi >> 4), exact) -- two independent dependency chains per warp; INT8: lo only.
+// (A second set per parity was dropped: four warps per scheduler hide the MMA latency, and the eight registers it cost
+// pushed loop-carried values of the persistent kernel into local memory.)
+#ifndef TIB_ACC_SETS
+#define TIB_ACC_SETS 1
+#endif
+#ifndef TIB_ZERO_IN_EPI
+#define TIB_ZERO_IN_EPI 1
+#endif
 template <int BITS>
 struct QuadAcc {
-    int lo[2][4];
-    int hi[BITS == 4 ? 2 : 1][4];
+    int lo[TIB_ACC_SETS][4];
+    int hi[TIB_ACC_SETS][4];
     __device__ __forceinline__ void clear() {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            lo[0][i] = lo[1][i] = 0;
-            hi[0][i] = 0;
-            if (BITS == 4) hi[BITS == 4 ? 1 : 0][i] = 0;
-        }
+        for (int s = 0; s < TIB_ACC_SETS; ++s)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { lo[s][i] = 0; hi[s][i] = 0; }
     }
     __device__ __forceinline__ int total(int i) const {
-        if constexpr (BITS == 4) return (lo[0][i] + lo[1][i]) + ((hi[0][i] + hi[1][i]) >> 4);
-        else return lo[0][i] + lo[1][i];
+        int l = 0, h = 0;
+#pragma unroll
+        for (int s = 0; s < TIB_ACC_SETS; ++s) { l += lo[s][i]; h += hi[s][i]; }
+        if constexpr (BITS == 4) return l + (h >> 4);
+        else return l;
     }
 };
 
@@ -147,8 +155,13 @@ __device__ __forceinline__ void kitem_mma(QuadAcc<BITS>& acc, int par, const uin
         imma_s8s8(acc.lo[par], w.x, w.y, w.z, w.w, xv.x, xv.y);
     }
 }
+// B fragment of one k-item.  Only B columns 0..2 carry digit planes (lanes g = lane >> 2 < 3); the other lanes read plane 0
+// again (their product columns are never used).  Predicating those lanes off would halve the wavefronts of this load, but
+// costs four register clears per load pair in a loop that is bound by issue slots, not by shared-memory bandwidth: measured
+// slower (profiles/r02_*), so every lane loads.
 template <int BITS>
-__device__ __forceinline__ uint4 load_xfrag(uint32_t addr) {
+__device__ __forceinline__ uint4 load_xfrag(uint32_t addr, bool on) {
+    (void)on;
     if constexpr (BITS == 4) return lds128s(addr);
     else { const uint2 v = lds64s(addr); return make_uint4(v.x, v.y, 0u, 0u); }
 }
@@ -428,7 +441,10 @@ __device__ __forceinline__ float gemv_stage_x_lean(const GemvArgs& a, const floa
     };
     issue(tid, load_w);
     if (ts) ts[0] = clock64();
+    // (the column accumulators are zero already: every epilogue clears what it has read)
+#if !TIB_ZERO_IN_EPI
     for (int i = tid; i < slab.ncols * 3; i += kConsumerThreads) sm.acc[i] = 0;
+#endif
     const float inv_rms = sc.inv_rms, inv_s = sc.inv_s, s_x = sc.s_x;
     if (ts) ts[1] = clock64();
     long long sxf = 0;
@@ -501,6 +517,7 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
     int grp = pl.grp, chunk = pl.chunk;   // group / chunk of the warp's next quad
     const int g = lane >> 2, t = lane & 3;
     const uint32_t xlane = smem_u32(sm.xd) + ((g < 3 ? g : 0) * 4 + t) * (BITS == 4 ? 16 : 8);   // B column g = digit plane g
+    const bool xon = g < 3;
     const uint32_t ring0 = smem_u32(sm.ring), full0 = smem_u32(sm.full), empty0 = smem_u32(sm.empty);
     // lane l < 16 stands for warp l when the stage offsets are summed with one REDUX (ragged rounds only)
     const int l_nq = pl.l_nq, l_fq = pl.l_fq;
@@ -538,7 +555,7 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
     };
     auto one = [&](int i, const uint4& wv, const uint4& xv) {
         if (DBG == 1 || (DBG == 3 && (xskip & 8))) acc.lo[0][0] += (int)(wv.x ^ wv.y ^ wv.z ^ wv.w);
-        else kitem_mma<BITS>(acc, i & 1, wv, xv);
+        else kitem_mma<BITS>(acc, i % TIB_ACC_SETS, wv, xv);
     };
     // ring position as addresses: the warp's slot of the current stage, its two barriers, the parity of the current use
     uint32_t st = it.st, par = it.par;
@@ -556,8 +573,8 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
             // ---- fast path: a full quad, and only full quads before it in the stage ----
             uint4 xa, xb;
             if (!(DBG == 3 && (xskip & 16))) {   // digits of the first two k-items: they do not depend on the stage, so before the wait
-                xa = load_xfrag<BITS>(xq);
-                xb = load_xfrag<BITS>(xq + kXItem);
+                xa = load_xfrag<BITS>(xq, xon);
+                xb = load_xfrag<BITS>(xq + kXItem, xon);
             } else {
                 xa = xb = make_uint4(1u, 2u, 3u, 4u);
             }
@@ -569,8 +586,8 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
             one(0, w0, xa); one(1, w1, xb);
             const uint4 w2 = lds128s(wbase + 1024), w3 = lds128s(wbase + 1536);
             if (!(DBG == 3 && (xskip & 16))) {
-                xa = load_xfrag<BITS>(xq + 2 * kXItem);
-                xb = load_xfrag<BITS>(xq + 3 * kXItem);
+                xa = load_xfrag<BITS>(xq + 2 * kXItem, xon);
+                xb = load_xfrag<BITS>(xq + 3 * kXItem, xon);
             }
             ready = (DBG != 2 && r + 1 < nrounds) ? mbar_test_wait_s(nfull, npar) : false;
             one(2, w2, xa); one(3, w3, xb);
@@ -594,7 +611,7 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
                     uint2 pa = make_uint2(0u, 0u), pb = make_uint2(0u, 0u);
                     if (in_a) pa = lds64s(wbase + i * nl * 128);
                     if (in_b) pb = lds64s(wbase + i * nl * 128 + 256);
-                    const uint4 xv = load_xfrag<BITS>(xq + i * kXItem);
+                    const uint4 xv = load_xfrag<BITS>(xq + i * kXItem, xon);
                     one(i, make_uint4(pa.x, pb.x, pa.y, pb.y), xv);
                 }
                 dirty = true;
@@ -665,9 +682,15 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
     const long long offterm = (long long)a.woff * sxf;
     const float fsxf = (float)sxf;
     // y = cs * s_x * (sum_k u_k xf_k - off * sum xf + zt * sum xf)
+    // reads the three digit sums of column c and leaves them zero for the next GEMV that uses this shared memory (the
+    // persistent kernel's prologue no longer spends a pass on clearing them)
     auto colval = [&](int c, float cs, float zt) -> float {
-        const int* p = sm.acc + c * 3;
-        const long long t = ((long long)p[2] << 16) + ((long long)p[1] << 8) + (long long)p[0] - offterm;
+        int* p = sm.acc + c * 3;
+        const int a0 = p[0], a1 = p[1], a2 = p[2];
+#if TIB_ZERO_IN_EPI
+        p[0] = 0; p[1] = 0; p[2] = 0;
+#endif
+        const long long t = ((long long)a2 << 16) + ((long long)a1 << 8) + (long long)a0 - offterm;
         // |t| < 2^47: hi * 2^23 + lo with both parts exact in fp32, so tf is the correctly rounded t (no fp64 needed)
         const int hi = (int)(t >> 23), lo = (int)(t & 0x7FFFFF);
         const float tf = fmaf((float)hi, 8388608.0f, (float)lo);
@@ -676,7 +699,10 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
     if (a.epi == EPI_SWIGLU || a.epi == EPI_QKV) {
         for (int pc = tid; pc < ncols / 2; pc += kConsumerThreads) {  // column pairs
             const int n0 = slab.col0 + 2 * pc;
-            if (n0 >= L.N) continue;
+            if (n0 >= L.N) {   // padding columns of the last slab: nothing to store, but their sums must not survive
+                for (int i = 0; i < 6; ++i) sm.acc[6 * pc + i] = 0;
+                continue;
+            }
             const bool first = pc == tid;
             const float cs0 = first ? pre.cs0 : a.colscale[n0], cs1 = first ? pre.cs1 : a.colscale[n0 + 1];
             const float zt0 = first ? pre.zt0 : (a.colzterm ? a.colzterm[n0] : 0.f);
@@ -714,7 +740,10 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
         int besti = 0x7FFFFFFF;
         for (int c = tid; c < ncols; c += kConsumerThreads) {
             const int n = slab.col0 + c;
-            if (n >= L.N) continue;
+            if (n >= L.N) {
+                for (int i = 0; i < 3; ++i) sm.acc[3 * c + i] = 0;
+                continue;
+            }
             const bool first = c == tid;
             const float cs = first ? pre.cs0 : a.colscale[n];
             const float zt = first ? pre.zt0 : (a.colzterm ? a.colzterm[n] : 0.f);

@@ -332,7 +332,14 @@ struct AttnArgs {
     // table / the partial buffers (0 for a single sequence)
     int zq, zout, ztable;
     size_t zpart_o, zpart_ml;
+    int page_shift;          // log2(page_tokens) when it is a power of two (the fast item then needs no division), else -1
 };
+TIB_HD int log2_if_pow2(int v) {
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int s = 0;
+    while ((1 << s) < v) ++s;
+    return s;
+}
 
 __device__ __forceinline__ const float* kv_row(const float* pool, const int* table, int page_tokens, int H, int t) {
     const int page = table[t / page_tokens];

@@ -79,10 +79,15 @@ struct MegaArgs {
     unsigned int* peer_flag[2][kMaxTp];
     int tp_p2p;
     const XStats* emb_stats;  // [V]: statistics of every embedding row (against the first norm weight)
+    // the sequence's KV page table (static for the launch), copied to shared memory once: kv_pages entries (0: none)
+    const int* kv_page_table;
+    int kv_pages;
 };
+constexpr int kMaxSmemPages = 1024;   // 64 k tokens at 64 tokens per page; longer tables are read from global memory
 
-TIB_HD size_t mega_smem_bytes(int stages, int max_kpad, int max_units, int attn_floats) {
-    return gemv_smem_bytes_for(stages, max_kpad, max_units) + 16 + (size_t)attn_floats * 4 + 16 + 2 * ((sizeof(MegaPhase) + 15) & ~size_t(15));
+TIB_HD size_t mega_smem_bytes(int stages, int max_kpad, int max_units, int attn_floats, int kv_pages = 0) {
+    const size_t table = kv_pages <= kMaxSmemPages ? (((size_t)kv_pages * 4 + 15) & ~size_t(15)) : 0;
+    return gemv_smem_bytes_for(stages, max_kpad, max_units) + 16 + (size_t)attn_floats * 4 + 16 + 2 * ((sizeof(MegaPhase) + 15) & ~size_t(15)) + table;
 }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -159,10 +164,12 @@ __device__ __forceinline__ float nt_max(float v, float* red) {
 }
 
 TIB_HD int attn_fast_scratch_floats(int nt);
+TIB_HD int attn_lean_scratch_floats(int nt);
 TIB_HD int attn_scratch_floats(int D, int nt) {
     const int groups = D < nt ? nt / D : 1;
     const int generic = D + kAttnTokBlock + 32 + groups * D + 4;
-    const int fast = D <= 128 ? attn_fast_scratch_floats(nt) + 4 : 0;   // + the merge flag of mega_attention
+    int fast = D <= 128 ? attn_fast_scratch_floats(nt) + 4 : 0;   // + the merge flag of mega_attention
+    if (D <= 128 && attn_lean_scratch_floats(nt) > fast) fast = attn_lean_scratch_floats(nt);
     return generic > fast ? generic : fast;
 }
 
@@ -273,8 +280,8 @@ __device__ __forceinline__ float attn_item(const AttnArgs& a, int h, int j, int 
 // attention_fast_incremental (:1254-1388) up to the order of the fp32 sums; expf is the full-precision one.
 TIB_HD int attn_fast_scratch_floats(int nt) { return (nt / 32) * (128 + 2); }
 template <int NT>
-__device__ __forceinline__ float attn_item_fast(const AttnArgs& a, int h, int j, int t0, int t1, float* sm, bool direct) {
-    constexpr int NW = NT / 32, G = 4;
+__device__ __forceinline__ float attn_item_fast(const AttnArgs& a, int h, int j, int t0, int t1, float* sm, bool direct, long long* ts = nullptr) {
+    constexpr int NW = NT / 32, G = 5;   // 5 tokens in flight per warp: a 320-token item (4 splits of a 1280-token context) is one round trip
     float* wm = sm;                 // [NW]
     float* wl = wm + NW;            // [NW]
     float* wo = wl + NW;            // [NW][128]
@@ -282,24 +289,43 @@ __device__ __forceinline__ float attn_item_fast(const AttnArgs& a, int h, int j,
     const int D = a.D, hoff = h * D;
     const bool lane_on = 4 * lane < D;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // the item's page ids, one per lane (an item of up to 32 pages): the K / V addresses then need no dependent global load
+    const int ps = a.page_shift;
+    const int p0 = ps >= 0 ? (t0 >> ps) : 0;
+    const bool hoisted = ps >= 0 && ((t1 - 1) >> ps) - p0 < 32;
+    int pg = 0;
+    if (hoisted && p0 + lane <= ((t1 - 1) >> ps)) pg = a.page_table[p0 + lane];
+    const int pmask = a.page_tokens - 1;
+    auto row_of = [&](const float* pool, int t) -> const float* {
+        if (hoisted) {
+            const int page = __shfl_sync(0xffffffffu, pg, (t >> ps) - p0);
+            return pool + ((size_t)page * a.page_tokens + (t & pmask)) * a.H;
+        }
+        return kv_row(pool, a.page_table, a.page_tokens, a.H, t);
+    };
     // the first group's K / V loads go out before q is needed
     float4 kv[G], vv[G];
     auto issue = [&](int tbase) {
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             const int t = tbase + g * NW;
+            const int tc = t < t1 ? t : t1 - 1;   // the shuffle inside row_of is warp-wide: every lane computes an in-range row
+            const size_t row = (size_t)hoff + 4 * lane;
+            const float* kr = row_of(a.k_pool, tc);
+            const float* vr = row_of(a.v_pool, tc);
             if (t < t1 && lane_on) {
-                const size_t row = (size_t)hoff + 4 * lane;
-                kv[g] = __ldcg(reinterpret_cast<const float4*>(kv_row(a.k_pool, a.page_table, a.page_tokens, a.H, t) + row));
-                vv[g] = __ldcg(reinterpret_cast<const float4*>(kv_row(a.v_pool, a.page_table, a.page_tokens, a.H, t) + row));
+                kv[g] = __ldcg(reinterpret_cast<const float4*>(kr + row));
+                vv[g] = __ldcg(reinterpret_cast<const float4*>(vr + row));
             } else {
                 kv[g] = zero4;
                 vv[g] = zero4;
             }
         }
     };
+    if (ts) ts[11] = clock64();
     issue(t0 + warp);
     const float4 q = lane_on ? __ldcg(reinterpret_cast<const float4*>(a.q + hoff + 4 * lane)) : zero4;
+    if (ts) ts[16] = clock64();
     float m_run = -INFINITY, l_run = 0.f;
     float4 o = zero4;
     for (int tbase = t0 + warp; tbase < t1; tbase += G * NW) {
@@ -324,6 +350,7 @@ __device__ __forceinline__ float attn_item_fast(const AttnArgs& a, int h, int j,
             s[g] = tbase + g * NW < t1 ? s[g] * a.scale : -INFINITY;
             mx = fmaxf(mx, s[g]);
         }
+        if (ts && tbase == t0 + warp) ts[22] = clock64() + (long long)(mx == 12345.678f);   // depends on the scores: after loads + shuffles
         const float corr = expf(m_run - mx);   // first group: exp(-inf) = 0
         l_run *= corr;
         o.x *= corr; o.y *= corr; o.z *= corr; o.w *= corr;
@@ -338,6 +365,7 @@ __device__ __forceinline__ float attn_item_fast(const AttnArgs& a, int h, int j,
         }
         m_run = mx;
     }
+    if (ts) ts[7] = clock64();
     // merge the warps (a warp without tokens has m = -inf, l = 0, o = 0)
     if (lane == 0) { wm[warp] = m_run; wl[warp] = l_run; }
     *reinterpret_cast<float4*>(wo + warp * 128 + 4 * lane) = o;
@@ -366,7 +394,134 @@ __device__ __forceinline__ float attn_item_fast(const AttnArgs& a, int h, int j,
             }
         }
     }
-    bar_sync(1, NT);   // the scratch is reused by the next item
+    bar_sync(1, NT);   // the scratch is reused by the next item; every thread's partial stores are issued
+    if (ts) ts[8] = clock64();
+    return out_am;
+}
+
+// ---- the attention phase of the persistent kernel for head dims <= 128: lean item ----------------------------------
+// Same arithmetic as attn_item_fast, written for latency: the page table lives in shared memory (copied once per launch), the
+// split geometry is computed once per step, and the 16 warps' (m, l, o) are merged with 16 exponentials instead of 16 per
+// output element.  Contexts of up to min_chunk tokens (4 round trips of 80 tokens) are ONE item per head that writes the
+// normalised output directly: at these lengths a split's counter + last-arriver merge (~2 us, and the merging CTA finishes
+// after all others) costs more than the extra round trips.  (Deferring the merge to the o-projection's prologue was tried:
+// 148 CTAs re-reading nsplit partial vectors from L2 at the same moment cost more than the merge it saved.)
+// Returns the thread's max |output| (direct items only).
+struct AttnStep {
+    int nsplit, chunk;
+};
+__device__ __forceinline__ AttnStep attn_step_geometry(const AttnArgs& a, int t) {
+    AttnStep g;
+    attn_split_range(t, a.max_splits, a.min_chunk, g.nsplit, g.chunk);
+    return g;
+}
+TIB_HD int attn_lean_scratch_floats(int nt) { return (nt / 32) * (128 + 3) + 4 + 4; }   // + the merge flag
+template <int NT>
+__device__ __forceinline__ float attn_item_lean(const AttnArgs& a, const int* spt, int h, int j, int t0, int t1, float* sm, bool direct, long long* ts) {
+    constexpr int NW = NT / 32, G = 5;   // 5 tokens in flight per warp: an item of up to 80 tokens is one round trip.  (Two rounds in
+                                         // flight -- double-buffered K / V registers -- was tried: the 48-64 extra registers spill.)
+    float* wm = sm;                 // [NW] running max of each warp
+    float* wl = wm + NW;            // [NW] its sum of exponentials
+    float* wf = wl + NW;            // [NW] e^(m_w - M), then [NW] = M, [NW + 1] = L
+    float* wo = wf + NW + 4;        // [NW][128]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int D = a.D, hoff = h * D;
+    const bool lane_on = 4 * lane < D;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ps = a.page_shift, pmask = a.page_tokens - 1;
+    const size_t lane_off = (size_t)hoff + 4 * lane;
+    const int* table = spt != nullptr ? spt : a.page_table;
+    float4 kv[G], vv[G];
+    auto issue = [&](int tbase) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int t = tbase + g * NW;
+            if (t < t1 && lane_on) {
+                const size_t row = ((size_t)table[t >> ps] * a.page_tokens + (t & pmask)) * a.H + lane_off;
+                kv[g] = __ldcg(reinterpret_cast<const float4*>(a.k_pool + row));
+                vv[g] = __ldcg(reinterpret_cast<const float4*>(a.v_pool + row));
+            } else {
+                kv[g] = zero4;
+                vv[g] = zero4;
+            }
+        }
+    };
+    if (ts) ts[11] = clock64();
+    issue(t0 + warp);   // the first group's K / V loads go out before q is needed
+    const float4 q = lane_on ? __ldcg(reinterpret_cast<const float4*>(a.q + hoff + 4 * lane)) : zero4;
+    if (ts) ts[16] = clock64();
+    float m_run = -INFINITY, l_run = 0.f;
+    float4 o = zero4;
+    for (int tbase = t0 + warp; tbase < t1; tbase += G * NW) {
+        if (tbase != t0 + warp) issue(tbase);
+        float s[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            float d = q.x * kv[g].x;
+            d = fmaf(q.y, kv[g].y, d);
+            d = fmaf(q.z, kv[g].z, d);
+            d = fmaf(q.w, kv[g].w, d);
+            s[g] = d;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) s[g] += __shfl_xor_sync(0xffffffffu, s[g], off);
+        }
+        float mx = m_run;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            s[g] = tbase + g * NW < t1 ? s[g] * a.scale : -INFINITY;
+            mx = fmaxf(mx, s[g]);
+        }
+        if (ts && tbase == t0 + warp) ts[22] = clock64() + (long long)(mx == 12345.678f);   // depends on the scores: after loads + shuffles
+        const float corr = expf(m_run - mx);   // first group: exp(-inf) = 0
+        l_run *= corr;
+        o.x *= corr; o.y *= corr; o.z *= corr; o.w *= corr;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const float p = expf(s[g] - mx);     // masked tokens: exp(-inf) = 0
+            l_run += p;
+            o.x = fmaf(p, vv[g].x, o.x);
+            o.y = fmaf(p, vv[g].y, o.y);
+            o.z = fmaf(p, vv[g].z, o.z);
+            o.w = fmaf(p, vv[g].w, o.w);
+        }
+        m_run = mx;
+    }
+    if (ts) ts[7] = clock64();
+    // merge the warps (a warp without tokens has m = -inf, l = 0, o = 0): warp 0 turns the 16 maxima into 16 factors
+    if (lane == 0) { wm[warp] = m_run; wl[warp] = l_run; }
+    *reinterpret_cast<float4*>(wo + warp * 128 + 4 * lane) = o;
+    bar_sync(1, NT);
+    if (warp == 0) {
+        const float mw = lane < NW ? wm[lane] : -INFINITY;
+        const float M = warp_max(mw);
+        const float f = mw == -INFINITY ? 0.f : expf(mw - M);
+        float L = lane < NW ? wl[lane] * f : 0.f;
+        L = warp_sum(L);
+        if (lane < NW) wf[lane] = f;
+        if (lane == 0) { wf[NW] = M; wf[NW + 1] = L; }
+    }
+    bar_sync(1, NT);
+    float out_am = 0.f;
+    if (tid < D) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) acc = fmaf(wo[w * 128 + tid], wf[w], acc);
+        if (direct) {
+            const float r = acc / wf[NW + 1];
+            a.out[hoff + tid] = r;
+            out_am = fabsf(r);
+        } else {
+            a.part_o[((size_t)h * a.max_splits + j) * D + tid] = acc;
+            if (tid == 0) {
+                a.part_ml[((size_t)h * a.max_splits + j) * 2 + 0] = wf[NW];
+                a.part_ml[((size_t)h * a.max_splits + j) * 2 + 1] = wf[NW + 1];
+            }
+        }
+    }
+    if (ts) ts[8] = clock64();
     return out_am;
 }
 
@@ -386,6 +541,38 @@ __device__ __forceinline__ float attn_merge_head(const AttnArgs& a, int h, int n
         const float o = acc / Lsum;
         a.out[h * a.D + d] = o;
         out_am = fmaxf(out_am, fabsf(o));
+    }
+    return out_am;
+}
+
+template <int NT>
+__device__ __forceinline__ float mega_attention_lean(const AttnArgs& a, const AttnStep g, const int* spt, int t, unsigned int* head_cnt, float* sm, long long* ts) {
+    float out_am = 0.f;
+    const int items = a.heads * g.nsplit;
+    int* flag = reinterpret_cast<int*>(sm + attn_lean_scratch_floats(NT) - 4);
+    for (int i = blockIdx.x; i < items; i += gridDim.x) {
+        const int h = g.nsplit == 1 ? i : i / g.nsplit, j = i - h * g.nsplit;
+        const int t0 = j * g.chunk, t1 = min(t, t0 + g.chunk);
+        if (i != (int)blockIdx.x) bar_sync(1, NT);   // the scratch is reused
+        if (g.nsplit == 1) {   // one item per head: normalised output, no partials / counter / merge
+            out_am = fmaxf(out_am, attn_item_lean<NT>(a, spt, h, 0, 0, t, sm, true, ts));
+            continue;
+        }
+        (void)attn_item_lean<NT>(a, spt, h, j, t0, t1, sm, false, ts);
+        // Every thread's partial stores precede this CTA barrier; ONE acquire-release atomic by thread 0 then publishes them
+        // (release, cumulative over what the barrier ordered before it) and, for the CTA that arrives last on the head's
+        // counter, makes the other splits' partials visible (acquire) -- no separate fences.
+        bar_sync(1, NT);
+        if (threadIdx.x == 0) {
+            unsigned int prev;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&head_cnt[h]) : "memory");
+            *flag = (prev == (unsigned int)(g.nsplit - 1)) ? 1 : 0;
+            if (*flag) head_cnt[h] = 0u;  // ready for the next layer (a grid barrier away)
+        }
+        bar_sync(1, NT);
+        if (ts) ts[9] = clock64();
+        if (*flag) out_am = fmaxf(out_am, attn_merge_head<NT>(a, h, g.nsplit));
+        if (ts) ts[10] = clock64();
     }
     return out_am;
 }
@@ -421,7 +608,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_combine_kernel(const AttnAr
 
 // the attention phase of the persistent kernel: (head, split) items dealt round-robin to the CTAs; the CTA that
 // completes the last split of a head merges that head's partials (no extra grid barrier, deterministic result)
-__device__ __forceinline__ float mega_attention(const AttnArgs& a, int t, unsigned int* head_cnt, float* sm) {
+__device__ __forceinline__ float mega_attention(const AttnArgs& a, int t, unsigned int* head_cnt, float* sm, long long* ts = nullptr) {
     constexpr int NT = kConsumerThreads;
     float out_am = 0.f;
     int nsplit, chunk;
@@ -433,33 +620,40 @@ __device__ __forceinline__ float mega_attention(const AttnArgs& a, int t, unsign
         const int t0 = j * chunk, t1 = min(t, t0 + chunk);
         const bool fast = a.D <= 128;
         if (nsplit == 1) {  // short context: one CTA per head does everything, no partials / counters / merge
-            out_am = fmaxf(out_am, fast ? attn_item_fast<NT>(a, h, 0, 0, t, sm, true) : attn_item<NT>(a, h, 0, 0, t, sm, true));
+            out_am = fmaxf(out_am, fast ? attn_item_fast<NT>(a, h, 0, 0, t, sm, true, ts) : attn_item<NT>(a, h, 0, 0, t, sm, true));
             bar_sync(1, NT);
             continue;
         }
-        if (fast) (void)attn_item_fast<NT>(a, h, j, t0, t1, sm, false);
-        else (void)attn_item<NT>(a, h, j, t0, t1, sm);
-        __threadfence();
-        bar_sync(1, NT);
+        if (fast) (void)attn_item_fast<NT>(a, h, j, t0, t1, sm, false, ts);
+        else { (void)attn_item<NT>(a, h, j, t0, t1, sm); bar_sync(1, NT); }
+        // Every thread's partial stores precede the CTA barrier that ended the item; ONE acquire-release atomic by thread 0
+        // then publishes them (release, cumulative over what the barrier ordered before it) and, for the CTA that arrives last on the
+        // head's counter, makes the other splits' partials visible (acquire) -- no separate fences.
         if (threadIdx.x == 0) {
-            const unsigned int prev = atomicAdd(&head_cnt[h], 1u);
+            unsigned int prev;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(&head_cnt[h]) : "memory");
             *flag = (prev == (unsigned int)(nsplit - 1)) ? 1 : 0;
-            if (*flag) head_cnt[h] = 0u;  // ready for the next layer
-            __threadfence();
+            if (*flag) head_cnt[h] = 0u;  // ready for the next layer (a grid barrier away)
         }
         bar_sync(1, NT);
+        if (ts) ts[9] = clock64();
         if (*flag) out_am = fmaxf(out_am, attn_merge_head<NT>(a, h, nsplit));
         bar_sync(1, NT);
+        if (ts) ts[10] = clock64();
     }
     return out_am;
 }
 
-// Registers: more than 16 warps put 5 on an SM sub-partition, which caps a uniform allocation at 96 per thread.  The
-// kernel is compiled for 96 (__maxnreg__); the producer warpgroup then shrinks to 56 and the four consumer warpgroups
-// grow to 104 (the pool is the CTA's launch allocation: 640 x 96 >= 512 x 104 + 128 x 56).  setmaxnreg is a
-// warpgroup-wide instruction, so the producer warp comes with three idle siblings (warps 17..19) that only execute
-// the shrink and exit: the CTA has 20 warps.
+// Registers: more than 16 warps put 5 on an SM sub-partition (16 K registers each), which caps a uniform allocation at 96
+// per thread -- 18 warps at 112 do not fit, measured.  The kernel is compiled for 96 (__maxnreg__); the producer warpgroup then
+// shrinks to 40 and the four consumer warpgroups grow to 104 (the pool is the CTA's launch allocation: 640 x 96 >= 512 x 104
+// + 128 x 40).  setmaxnreg is a warpgroup-wide instruction, so the producer warp comes with three siblings: warp 17 is the
+// grid-barrier warp, warps 18 and 19 only execute the shrink and exit: the CTA has 20 warps.
 constexpr int kMegaThreads = (kConsumerWarps + 4) * 32;  // 640
+#ifndef TIB_PROD_REGS
+#define TIB_PROD_REGS 32
+#define TIB_CONS_REGS 112
+#endif
 // TL: the debug-timeline instance (SM-clock stamps along every phase, m.dbg); the production instance carries none of it
 template <int BITS, bool TL = false>
 __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaArgs m) {
@@ -475,6 +669,8 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
     // still reads this phase's in its epilogue (nobody is more than one barrier ahead)
     MegaPhase* const sph0 = reinterpret_cast<MegaPhase*>(ptail);
     MegaPhase* const sph1 = reinterpret_cast<MegaPhase*>(ptail + ((sizeof(MegaPhase) + 15) & ~size_t(15)));
+    // the KV page table of the sequence, copied once: a page lookup in the attention phase is then an LDS
+    int* const spt = (m.kv_pages > 0 && m.kv_pages <= kMaxSmemPages) ? reinterpret_cast<int*>(ptail + 2 * ((sizeof(MegaPhase) + 15) & ~size_t(15))) : nullptr;
     if (tid == 0) gemv_init_barriers(sm, m.stages);
     __syncthreads();
 
@@ -484,7 +680,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
 
     if (warp >= kConsumerWarps) {
         // ===== producer warpgroup: warp 16 streams every GEMV phase of every step, back to back =====
-        reg_dealloc<40>();
+        reg_dealloc<TIB_PROD_REGS>();
         if (warp == kConsumerWarps) {
             // lane l holds the record of phase base + l: one latency per 32 phases, then register shuffles only
             for (int s = 0; s < m.n_steps; ++s) {
@@ -604,7 +800,10 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
     }
 
     // ===== consumers =====
-    reg_alloc<104>();
+    reg_alloc<TIB_CONS_REGS>();
+    for (int i = tid; i < m.max_units * 4 * 3; i += kConsumerThreads) sm.acc[i] = 0;   // from here on every epilogue re-zeroes what it reads
+    if (spt != nullptr)
+        for (int i = tid; i < m.kv_pages; i += kConsumerThreads) spt[i] = m.kv_page_table[i];
     // ends a phase: publishes this CTA's partial statistics of the phase's output, then arrives on the grid barrier
     bool need_wait = false;
     // ends a phase: leaves this CTA's partial statistics of the phase's output for the barrier warp and signals it
@@ -648,6 +847,8 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
     for (int s = 0; s < m.n_steps; ++s) {
         const bool sample = s >= m.first_sample;
         const int pos = pos0 + s;
+        AttnStep ageo{1, 1};        // split geometry of this step's attention phases (the same in every layer)
+        bool ageo_set = false;
         if (s > 0 && s - 1 >= m.first_sample) {
             grid_wait();
             token = decode_key(s - 1);
@@ -771,7 +972,12 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                     out_st.am = fabsf(P.g.next_norm_w ? v * P.g.next_norm_w[i] : v);
                 }
             } else {
-                out_st.am = mega_attention(P.at, pos + 1, m.head_cnt, attn_sm);
+                if (P.at.D <= 128 && P.at.page_shift >= 0) {   // lean item
+                    if (!ageo_set) { ageo = attn_step_geometry(P.at, pos + 1); ageo_set = true; }
+                    out_st.am = mega_attention_lean<kConsumerThreads>(P.at, ageo, spt, pos + 1, m.head_cnt, attn_sm, stamp ? ts : nullptr);
+                } else {
+                    out_st.am = mega_attention(P.at, pos + 1, m.head_cnt, attn_sm, stamp ? ts : nullptr);
+                }
             }
             if (stamp) ts[4] = clock64();
             grid_arrive(out_st, stamp ? ts : nullptr);
