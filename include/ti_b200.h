@@ -169,6 +169,22 @@ int ti_b200_generate_greedy(ti_model_t m, const int32_t* prompt, int32_t n_promp
 int ti_b200_generate_batch_greedy(ti_model_t m, const int32_t* prompts, int32_t batch, int32_t n_prompt, int32_t n_new,
                                   int32_t* out_tokens, float* logits_last, float* decode_ms);
 
+/* ---- sampling -----------------------------------------------------------------
+ * ti_b200_sample_logits    <- InferenceEngine::sample_next_token (src/model/inference_engine.cpp:1554-1673) on host logits
+ *                             [rows, vocab]: temperature -> top-k -> softmax -> top-p -> inverse CDF, and the log-probability
+ *                             of the pick.  The reference's RNG is a time-seeded std::mt19937; here the uniform of a pick is
+ *                             a counter-based hash of (seed, step), so generations are reproducible.
+ * ti_b200_generate_sampled <- generate() (:734-802) with that sampler ON THE DEVICE: the picked token feeds the next forward
+ *                             pass without a logits download or a host sort; logprobs_out (optional) as include_logprobs.
+ * ti_b200_compute_logprobs <- compute_logprobs (:873-954): out[pos] = log softmax(logits[pos])[tokens[pos]], -20 for an id
+ *                             outside the vocabulary. */
+int ti_b200_sample_logits(const float* logits_host, size_t rows, size_t vocab, float temperature, int32_t top_k, float top_p,
+                          uint64_t seed, int32_t step, int32_t* tokens_out, float* logprobs_out);
+int ti_b200_generate_sampled(ti_model_t m, const int32_t* prompt, int32_t n_prompt, int32_t n_new, float temperature,
+                             int32_t top_k, float top_p, uint64_t seed, int32_t stop_on_eos, int32_t* out_tokens,
+                             int32_t* n_out, float* logprobs_out, float* decode_ms);
+int ti_b200_compute_logprobs(ti_model_t m, const int32_t* tokens, int32_t n, float* out);
+
 /* CUDA-event time of the prompt phase (prefill) of the last ti_b200_generate_greedy call on this model, in ms */
 int ti_b200_model_last_prefill_ms(ti_model_t m, float* ms);
 

@@ -1,7 +1,8 @@
 // turboinfer/model/inference_engine.hpp -- InferenceEngine of the B200 build (reference include/turboinfer/model/
 // inference_engine.hpp:25-372): weights are quantized, packed and uploaded once at construction; generate() runs the
-// persistent decode kernel.  Greedy (top_k = 1) is sampled on the device; other settings sample on the host from
-// downloaded logits (temperature -> top-k -> softmax -> top-p -> inverse CDF, like sample_next_token :1554-1673).
+// persistent decode kernel.  Sampling runs on the device for every setting: greedy (top_k = 1) as an arg-max inside the
+// decode kernel, everything else through the on-device sampler (temperature -> top-k -> softmax -> top-p -> inverse CDF,
+// sample_next_token :1554-1673) with a seeded counter-based RNG (set_seed; the reference seeds from the clock, :472).
 #pragma once
 #include <cstdint>
 #include <memory>
@@ -51,6 +52,10 @@ public:
     GenerationResult generate(const std::vector<int>& input_tokens, size_t max_new_tokens, bool include_logprobs = false);
     std::vector<GenerationResult> generate_batch(const std::vector<std::vector<int>>& input_tokens_batch, size_t max_new_tokens,
                                                  bool include_logprobs = false);
+    /// compute_logprobs (:873-954): log softmax(logits[pos])[tokens[pos]] per position; the reference's sentinels on failure
+    std::vector<float> compute_logprobs(const std::vector<int>& tokens);
+    /// seed of the sampler's counter-based RNG (a generation with the same seed reproduces its tokens); default: from the clock
+    void set_seed(uint64_t seed);
     void reset_state();
     size_t memory_usage() const;
     std::string performance_stats() const;
@@ -60,7 +65,6 @@ public:
 
 private:
     void validate_input_tokens(const std::vector<int>& tokens) const;
-    int sample_next_token(const float* logits, std::vector<float>* logprobs);
 
     ModelMetadata model_metadata_;
     InferenceConfig config_;

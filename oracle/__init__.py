@@ -90,6 +90,12 @@ class Oracle:
         L.tio_decode_greedy_timed.restype = C.c_int
         L.tio_decode_greedy_timed.argtypes = [C.POINTER(TioModel), C.POINTER(C.c_int32), C.c_int, C.c_int, C.POINTER(C.c_int32),
                                               C.POINTER(C.c_double), C.c_int]
+        if hasattr(L, "tio_sample"):   # the C restatement only (the reference's RNG is time-seeded, see ti_oracle.h)
+            L.tio_sample.restype = C.c_int
+            L.tio_sample.argtypes = [_f, C.c_size_t, C.c_float, C.c_int, C.c_float, C.c_float, _f]
+            L.tio_uniform.restype = C.c_float
+            L.tio_uniform.argtypes = [C.c_uint64, C.c_uint64]
+            L.tio_logprobs.argtypes = [_f, C.c_size_t, C.c_size_t, C.POINTER(C.c_int32), _f]
         L.tio_generate_literal.restype = C.c_int
         L.tio_generate_literal.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int,
                                            C.c_int, C.POINTER(C.c_int32), _f]
@@ -289,6 +295,24 @@ class Oracle:
         if n < 0:
             raise RuntimeError(f"tio_decode_greedy_timed failed ({n})")
         return out[:max(n_new, 0)].copy(), secs[:n].copy()
+
+    # ---- sampling ----
+    def uniform(self, seed: int, step: int) -> float:
+        return float(self.lib.tio_uniform(seed, step))
+
+    def sample(self, logits: np.ndarray, temperature: float, top_k: int, top_p: float, u: float):
+        """(token, logprob) of sample_next_token on one row of logits with the uniform u."""
+        lg = np.ascontiguousarray(logits, dtype=np.float32).ravel()
+        lp = C.c_float()
+        tok = self.lib.tio_sample(_fp(lg), lg.size, temperature, top_k, top_p, u, C.byref(lp))
+        return int(tok), float(lp.value)
+
+    def logprobs(self, logits: np.ndarray, tokens) -> np.ndarray:
+        lg = np.ascontiguousarray(logits, dtype=np.float32)
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        out = np.zeros(t.size, dtype=np.float32)
+        self.lib.tio_logprobs(_fp(lg.reshape(-1)), t.size, lg.shape[-1], t.ctypes.data_as(C.POINTER(C.c_int32)), _fp(out))
+        return out
 
     # ---- level C ----
     def generate_literal(self, vocab: int, hidden: int, layers: int, qtype: int, prompt: Sequence[int], n_new: int):

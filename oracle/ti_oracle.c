@@ -451,6 +451,87 @@ int tio_decode_greedy_timed(const tio_model* m, const int32_t* prompt, int n_pro
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Sampling: sample_next_token (src/model/inference_engine.cpp:1554-1673) with the uniform passed in.
+ * ---------------------------------------------------------------------------------------- */
+static uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+/* the engine's counter-based uniform (turboinfer_b200/csrc/sampling.cuh sample_uniform): 24 bits in [0, 1) */
+float tio_uniform(uint64_t seed, uint64_t step) {
+    const uint64_t h = splitmix64(splitmix64(seed) ^ (step * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull));
+    return (float)(uint32_t)(h >> 40) * (1.0f / 16777216.0f);
+}
+
+typedef struct { float v; int idx; } spair;
+static int spair_desc(const void* a, const void* b) {   /* value descending, index ascending (see ti_oracle.h) */
+    const spair* x = (const spair*)a;
+    const spair* y = (const spair*)b;
+    if (x->v > y->v) return -1;
+    if (x->v < y->v) return 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);
+}
+
+int tio_sample(const float* logits, size_t vocab, float temperature, int top_k, float top_p, float u, float* logprob) {
+    const size_t V = vocab;
+    float* l = (float*)malloc(V * sizeof(float));
+    float* p = (float*)malloc(V * sizeof(float));
+    spair* pairs = (spair*)malloc(V * sizeof(spair));
+    memcpy(l, logits, V * sizeof(float));
+    if (temperature != 1.0f && temperature > 0.0f)                       /* :1577-1582 */
+        for (size_t i = 0; i < V; ++i) l[i] = l[i] / temperature;
+    if (top_k > 0 && (size_t)top_k < V) {                                /* :1584-1598 */
+        for (size_t i = 0; i < V; ++i) { pairs[i].v = l[i]; pairs[i].idx = (int)i; }
+        qsort(pairs, V, sizeof(spair), spair_desc);
+        for (size_t i = (size_t)top_k; i < V; ++i) l[pairs[i].idx] = -INFINITY;
+    }
+    float mx = l[0];                                                     /* :1600-1612 */
+    for (size_t i = 1; i < V; ++i) if (l[i] > mx) mx = l[i];
+    float sum = 0.0f;
+    for (size_t i = 0; i < V; ++i) { p[i] = expf(l[i] - mx); sum += p[i]; }
+    for (size_t i = 0; i < V; ++i) p[i] = p[i] / sum;
+    if (top_p < 1.0f) {                                                  /* :1614-1648 */
+        for (size_t i = 0; i < V; ++i) { pairs[i].v = p[i]; pairs[i].idx = (int)i; }
+        qsort(pairs, V, sizeof(spair), spair_desc);
+        float cum = 0.0f;
+        size_t cutoff = V;
+        for (size_t i = 0; i < V; ++i) {
+            cum += pairs[i].v;
+            if (cum >= top_p) { cutoff = i + 1; break; }
+        }
+        for (size_t i = cutoff; i < V; ++i) p[pairs[i].idx] = 0.0f;
+        float ns = 0.0f;
+        for (size_t i = 0; i < V; ++i) ns += p[i];
+        if (ns > 0.0f) for (size_t i = 0; i < V; ++i) p[i] = p[i] / ns;
+    }
+    float cum = 0.0f;                                                    /* :1650-1672 */
+    int tok = (int)V - 1;
+    int found = 0;
+    for (size_t i = 0; i < V; ++i) {
+        cum += p[i];
+        if (u <= cum) { tok = (int)i; found = 1; break; }
+    }
+    (void)found;
+    if (logprob) *logprob = logf(p[tok]);
+    free(l); free(p); free(pairs);
+    return tok;
+}
+
+void tio_logprobs(const float* logits, size_t n, size_t vocab, const int32_t* tokens, float* out) {   /* :919-944 */
+    for (size_t pos = 0; pos < n; ++pos) {
+        const float* row = logits + pos * vocab;
+        float mx = row[0];
+        for (size_t v = 1; v < vocab; ++v) mx = row[v] > mx ? row[v] : mx;
+        float se = 0.0f;
+        for (size_t v = 0; v < vocab; ++v) se += expf(row[v] - mx);
+        const int tok = tokens[pos];
+        out[pos] = (tok < 0 || (size_t)tok >= vocab) ? -20.0f : row[tok] - mx - logf(se);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * Level C: the literal path that benchmarks/benchmark_inference runs (SURVEY 8c oracle-C).
  *   model      create_test_model, benchmarks/benchmark_inference.cpp:145-225 (no o_proj, no gate, no norms)
  *   quantize   Quantizer::quantize_model :89-118 -> integer tensors; matmul casts them WITHOUT scale

@@ -105,6 +105,20 @@ int tio_decode_greedy(const tio_model* m, const int32_t* prompt, int n_prompt, i
 int tio_decode_greedy_timed(const tio_model* m, const int32_t* prompt, int n_prompt, int n_new,
                             int32_t* out_tokens, double* step_seconds, int cap);
 
+/* ---- sampling ----------------------------------------------------------------
+ * InferenceEngine::sample_next_token (src/model/inference_engine.cpp:1554-1673) on one row of logits: temperature
+ * (:1577-1582), top-k (:1584-1598), softmax (:1600-1612), top-p (:1614-1648), inverse CDF (:1650-1672), every sum
+ * sequential in the reference's order.  The reference draws its uniform from a time-seeded std::mt19937 (:472), which
+ * cannot be reproduced: the uniform is an ARGUMENT here (tio_uniform = the counter-based generator the GPU engine uses),
+ * so this part of the oracle is pinned against the compiled reference only where no randomness enters (top_k = 1).
+ * std::sort is unstable: among equal logits / probabilities the reference's order is unspecified; restated as value
+ * descending, index ascending.  Returns the token; *logprob (may be NULL) = log of its final probability. */
+int tio_sample(const float* logits, size_t vocab, float temperature, int top_k, float top_p, float u, float* logprob);
+float tio_uniform(uint64_t seed, uint64_t step);
+/* compute_logprobs (:873-954) on precomputed logits [n, vocab]: out[pos] = logit[token] - max - log(sum exp(logit - max)),
+ * -20 for a token id outside the vocabulary */
+void tio_logprobs(const float* logits, size_t n, size_t vocab, const int32_t* tokens, float* out);
+
 /* ---- level C: the literal path of benchmarks/benchmark_inference (SURVEY 8c oracle-C) --- */
 /* create_test_model(vocab, hidden, layers) (benchmarks/benchmark_inference.cpp:145-225) run through
  * InferenceEngine::generate with top_k = 1; qtype TIO_QNONE / TIO_QINT8 / TIO_QINT4 goes through

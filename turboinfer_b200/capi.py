@@ -74,6 +74,9 @@ SYMBOLS = {
     "ti_b200_decode_step": (C.c_int, [C.c_uint64, C.c_int32, _f, _i32]),
     "ti_b200_generate_greedy": (C.c_int, [C.c_uint64, _i32, C.c_int32, C.c_int32, C.c_int32, _i32, _i32, _f, _f]),
     "ti_b200_generate_batch_greedy": (C.c_int, [C.c_uint64, _i32, C.c_int32, C.c_int32, C.c_int32, _i32, _f, _f]),
+    "ti_b200_sample_logits": (C.c_int, [_f, C.c_size_t, C.c_size_t, C.c_float, C.c_int32, C.c_float, C.c_uint64, C.c_int32, _i32, _f]),
+    "ti_b200_generate_sampled": (C.c_int, [C.c_uint64, _i32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_uint64, C.c_int32, _i32, _i32, _f, _f]),
+    "ti_b200_compute_logprobs": (C.c_int, [C.c_uint64, _i32, C.c_int32, _f]),
     "ti_b200_model_last_prefill_ms": (C.c_int, [C.c_uint64, _f]),
     "ti_b200_launch_count": (C.c_int, [C.POINTER(C.c_uint64)]),
     "ti_b200_bench_gemv": (C.c_int, [C.POINTER(C.c_uint64), C.c_size_t, C.c_size_t, _f]),
@@ -295,6 +298,16 @@ class _Ops:
         _ck(_need().ti_b200_softmax(_fp(x), _fp(y), x.size // n, n, temperature))
         return y
 
+    def sample(self, logits, temperature: float = 1.0, top_k: int = 50, top_p: float = 0.9, seed: int = 0, step: int = 0):
+        """sample_next_token on [rows, vocab] logits -> (tokens [rows], logprobs [rows])."""
+        lg = _c(logits)
+        lg = lg.reshape(-1, lg.shape[-1])
+        tok = np.zeros(lg.shape[0], dtype=np.int32)
+        lp = np.zeros(lg.shape[0], dtype=np.float32)
+        _ck(_need().ti_b200_sample_logits(_fp(lg.reshape(-1)), lg.shape[0], lg.shape[1], temperature, top_k, top_p, seed, step,
+                                          tok.ctypes.data_as(_i32), _fp(lp)))
+        return tok, lp
+
     def attention_decode(self, q, k, v, num_heads: int = 1) -> np.ndarray:
         q, k, v = _c(q), _c(k), _c(v)
         B, _, H = q.shape
@@ -433,6 +446,23 @@ class Model:
                                           _fp(logits) if want_logits else C.cast(None, _f), C.byref(ms)))
         n = n_out.value
         return out[:n].copy(), (logits[:n].copy() if want_logits else None), ms.value
+
+    def generate_sampled(self, prompt: Sequence[int], n_new: int, *, temperature: float = 1.0, top_k: int = 50, top_p: float = 0.9,
+                         seed: int = 0, stop_on_eos: bool = False):
+        """generate() with the on-device sampler -> (tokens, logprobs of the picks, decode ms)."""
+        p = _c(prompt, np.int32)
+        out = np.zeros(max(n_new, 1), dtype=np.int32)
+        lp = np.zeros(max(n_new, 1), dtype=np.float32)
+        n_out, ms = C.c_int32(), C.c_float()
+        _ck(lib().ti_b200_generate_sampled(self.handle, p.ctypes.data_as(_i32), p.size, n_new, temperature, top_k, top_p, seed,
+                                           int(stop_on_eos), out.ctypes.data_as(_i32), C.byref(n_out), _fp(lp), C.byref(ms)))
+        return out[: n_out.value].copy(), lp[: n_out.value].copy(), ms.value
+
+    def compute_logprobs(self, tokens: Sequence[int]) -> np.ndarray:
+        t = _c(tokens, np.int32)
+        out = np.zeros(t.size, dtype=np.float32)
+        _ck(lib().ti_b200_compute_logprobs(self.handle, t.ctypes.data_as(_i32), t.size, _fp(out)))
+        return out
 
     def generate_batch_greedy(self, prompts, n_new: int, *, want_logits: bool = False):
         """generate_batch: prompts [B][n_prompt] (equal lengths) -> tokens [B][n_new], logits of the last step, decode ms."""

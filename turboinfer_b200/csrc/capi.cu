@@ -21,6 +21,7 @@
 #include "gemm_tc.cuh"
 #include "prefill.cuh"
 #include "batch.cuh"
+#include "sampling.cuh"
 
 using namespace tib;
 
@@ -303,6 +304,9 @@ struct Model {
     DevBuf<float> tok_emb, out_norm;
     RawTensor raw_lm;
     std::unique_ptr<QWeight> lm_head;
+    std::unique_ptr<QWeight> lm_head_shard;   // tensor parallel: this rank's V / tp columns (fused engine; the full copy serves the other engines)
+    bool lm_sharded = false;
+    size_t xchg_key_off = 0;
     DevBuf<float> lit_lm;
     DevBuf<float> lit_x, lit_pa, lit_n, lit_u, lit_g, lit_f;   // compat_literal activations, sized for lit_rows rows
     int lit_rows = 0;
@@ -312,6 +316,8 @@ struct Model {
     DevBuf<StepState> state;
     DevBuf<float> x, nrm, q, attn_out, act, logits, part_o, part_ml, inv_freq, hist;
     DevBuf<int> out_tokens, prompt;
+    DevBuf<int> smp_tokens, smp_count;      // sampled generation: token history [n_new], the step counter of the RNG
+    DevBuf<float> smp_logprobs;             // ... and the log-probability of every pick
     int attn_heads = 1, attn_dim = 0, max_splits = 1;
     size_t attn_smem = 0;
     cudaGraphExec_t graph_decode = nullptr, graph_prefill = nullptr;
@@ -472,7 +478,13 @@ int store_tensor(Model& m, const std::string& name, DevBuf<float>&& dev, size_t 
     if (s == S_LM) {
         TRY(expect(H, V));
         take(m.raw_lm);
-        if (!m.cfg.compat_literal) TRY(pack_single(m.raw_lm, m.cfg.qtype, &m.lm_head));
+        if (!m.cfg.compat_literal) {
+            if (m.tp > 1 && V % m.tp == 0) {   // column-parallel slice of the vocabulary, same whole-tensor quantization parameters
+                const SrcView v = shard_view(m.raw_lm, SH_COLS, m.tp, m.tp_rank);
+                TRY(build_qweight_views(&v, 1, 0, (int)H, m.cfg.qtype, 1, false, &m.lm_head_shard));
+            }
+            TRY(pack_single(m.raw_lm, m.cfg.qtype, &m.lm_head));
+        }
         return 0;
     }
     if (li < 0 || li >= (int)m.layers.size()) return fail("layer index out of range in '%s'", name.c_str());
@@ -669,7 +681,8 @@ int tp_exchange_setup(Model& m) {
     if (P > kMaxTp) return fail("fused tensor parallelism supports up to %d ranks", kMaxTp);
     const size_t bar_bytes = (size_t)kBarWords * kBarStride * sizeof(unsigned int) + 256;   // + the barrier sequence number
     m.xchg_flag_off = (bar_bytes + 255) & ~size_t(255);                                     // flags [2 buffers][P][256 CTAs]
-    m.xchg_part_off = m.xchg_flag_off + (size_t)2 * kMaxTp * 256 * sizeof(unsigned int);
+    m.xchg_key_off = m.xchg_flag_off + (size_t)2 * kMaxTp * 256 * sizeof(unsigned int);      // arg-max keys [2][kMaxTp]
+    m.xchg_part_off = m.xchg_key_off + 256;
     m.xchg_part_bytes = ((size_t)P * H * sizeof(float) + 255) & ~size_t(255);
     const size_t total = m.xchg_part_off + 2 * m.xchg_part_bytes;
     CK(cudaMalloc(&m.xchg, total));
@@ -841,7 +854,24 @@ int build_mega(Model& m) {
     lm.rms_eps = m.cfg.rms_eps;
     lm.epi = EPI_LOGITS;
     lm.out = m.logits.p;
-    gemv_phase(*m.lm_head, lm, m.layers.empty() ? SRC_EMB : SRC_PTR, SRC_PTR, 1);
+    m.lm_sharded = tp && !m.tp_p2p && m.lm_head_shard != nullptr;
+    if (const char* e = getenv("TURBOINFER_B200_TP_LMHEAD")) if (std::string(e) == "replicated") m.lm_sharded = false;   // A/B
+    if (m.lm_sharded) {
+        // column-parallel lm_head: every rank computes the logits of its V / tp columns (stored at their
+        // global position of m.logits, the rest stays zero) and a local arg-max key with GLOBAL indices; the PH_KEYX phase
+        // exchanges the P keys over NVLink
+        const int Vl = m.cfg.vocab / m.tp;
+        lm.out = m.logits.p + (size_t)m.tp_rank * Vl;
+        lm.col_off = m.tp_rank * Vl;
+        gemv_phase(*m.lm_head_shard, lm, m.layers.empty() ? SRC_EMB : SRC_PTR, SRC_PTR, 1);
+        MegaPhase kx{};
+        kx.type = PH_KEYX;
+        kx.is_head = 1;
+        kx.mgpu = 1;
+        ph.push_back(kx);
+    } else {
+        gemv_phase(*m.lm_head, lm, m.layers.empty() ? SRC_EMB : SRC_PTR, SRC_PTR, 1);
+    }
 
     m.mega_max_kpad = max_kpad;
     m.mega_max_units = max_units;
@@ -914,6 +944,7 @@ int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
     a.emb_stats = m.emb_stats.p;
     a.kv_page_table = m.page_table.p;
     a.kv_pages = m.num_pages;
+    a.n_head = m.lm_sharded ? 2 : 1;
     a.dbg_flags = getenv("TURBOINFER_B200_DBG_FLAGS") ? atoi(getenv("TURBOINFER_B200_DBG_FLAGS")) : 0;
     if (m.dbg_on && m.dbg_all) a.dbg_flags |= 4;   // every CTA stamps
     a.tp = m.tp_fused ? m.tp : 1;
@@ -926,6 +957,7 @@ int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
             a.peer_part[1][r] = reinterpret_cast<float*>(b + m.xchg_part_off + m.xchg_part_bytes);
             a.peer_flag[0][r] = reinterpret_cast<unsigned int*>(b + m.xchg_flag_off);
             a.peer_flag[1][r] = reinterpret_cast<unsigned int*>(b + m.xchg_flag_off) + (size_t)kMaxTp * 256;
+            a.peer_keys[r] = reinterpret_cast<unsigned long long*>(b + m.xchg_key_off);
         }
         a.tp_p2p = m.tp_p2p ? 1 : 0;
         a.mg_seq = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(m.xchg) + (size_t)kBarWords * kBarStride * sizeof(unsigned int));
@@ -1277,6 +1309,61 @@ int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
         ++g_launches;
     }
     batch_advance_kernel<<<1, 1, 0, g_stream>>>(bs.pos_step.p, sample ? 1 : 0);
+    ++g_launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Tensor parallel with the lm_head sharded over the vocabulary: a rank holds the logits of its own columns (zero elsewhere), so
+// the full rows -- needed only when the caller asks for logits, samples, or scores log-probabilities -- are one all-reduce (sum
+// with exact zeros) away.
+int gather_sharded_logits(Model& m, float* buf, size_t count) {
+    if (!m.lm_sharded) return 0;
+    const ncclResult_t r = g_nccl.AllReduce(buf, buf, count, ncclFloat32, ncclSum, g_comm, g_stream);
+    if (r != ncclSuccess) return fail("ncclAllReduce (logits) failed: %s", g_nccl.GetErrorString(r));
+    return 0;
+}
+
+// ---- the prompt of a generation (forward_pass, :749): fills the KV cache; the last prompt token's logits are left in
+// m.logits (steps < n_prompt - 1 skip the lm_head).  Long prompts go through the tensor-core GEMM path (all tokens but the
+// last in one batched forward pass), short ones through the decode engine token by token.  m.prompt holds the prompt.
+int prompt_pass(Model& m, const int32_t* prompt_host, int n_prompt) {
+    if (m.use_mega) {
+        if (prefill_gemm_eligible(m, n_prompt - 1)) {
+            const int M = n_prompt - 1;
+            TRY(prefill_gemm(m, m.prompt.p, M));
+            CK(cudaMemcpyAsync(&m.state.p->pos, &M, sizeof(int), cudaMemcpyHostToDevice, g_stream));
+            CK(cudaMemcpyAsync(m.prompt.p, prompt_host + M, sizeof(int), cudaMemcpyHostToDevice, g_stream));
+            TRY(run_mega(m, 1, 1, 0));
+        } else {
+            TRY(run_mega(m, n_prompt, n_prompt, n_prompt - 1));
+        }
+        return 0;
+    }
+    for (int i = 0; i < n_prompt; ++i) {
+        set_token_kernel<<<1, 1, 0, g_stream>>>(m.state.p, m.prompt.p, i);
+        ++g_launches;
+        TRY(run_step(m, i == n_prompt - 1));
+    }
+    return 0;
+}
+
+// one more forward pass from the token in state.token (decode), logits in m.logits
+int decode_pass(Model& m) {
+    if (m.use_mega) return run_mega(m, 0, 1, 0);
+    return run_step(m, true);
+}
+
+int launch_sample(const float* logits, int rows, int V, int ld, float temperature, int top_k, float top_p, uint64_t seed, const int* step_ptr, int step,
+                  int* token_out, float* logprob_out, int* hist_tokens, float* hist_logprobs, int hist_stride, int* feed_token) {
+    SampleArgs a{};
+    a.logits = logits; a.V = V; a.ld = ld;
+    a.temperature = temperature; a.top_k = top_k; a.top_p = top_p;
+    a.seed = seed; a.step_ptr = step_ptr; a.step = step;
+    a.token_out = token_out; a.logprob_out = logprob_out;
+    a.hist_tokens = hist_tokens; a.hist_logprobs = hist_logprobs; a.hist_stride = hist_stride;
+    a.feed_token = feed_token;
+    sample_kernel<<<rows, kSampleThreads, 0, g_stream>>>(a);
     ++g_launches;
     CK(cudaGetLastError());
     return 0;
@@ -1986,6 +2073,7 @@ int ti_b200_model_finalize(ti_model_t h) {
     TRY(m.attn_out.alloc(H));
     TRY(m.act.alloc(std::max(I, 1)));
     TRY(m.logits.alloc(V));
+    CK(cudaMemsetAsync(m.logits.p, 0, (size_t)V * sizeof(float), g_stream));   // a sharded lm_head writes its own columns only: the rest stays 0
     TRY(m.part_o.alloc((size_t)m.attn_heads * m.max_splits * m.attn_dim));
     TRY(m.part_ml.alloc((size_t)m.attn_heads * m.max_splits * 2));
     const int rope_dim = m.cfg.rope_mode == 1 ? H / m.cfg.heads : H;
@@ -2070,7 +2158,7 @@ int ti_b200_model_step_bytes(ti_model_t h, int32_t t, double* weight_bytes, doub
         add(ly.qkv); add(ly.o); add(ly.gateup); add(ly.down);
         if (ly.qkv && ly.o) kb += 2.0 * t * H * 4.0 + 2.0 * H * 4.0;  // K,V read over t tokens + one row written
     }
-    add(m->lm_head);
+    add(m->lm_sharded ? m->lm_head_shard : m->lm_head);
     wb += H * 4.0;  // embedding row
     if (weight_bytes) *weight_bytes = wb;
     if (kv_bytes) *kv_bytes = kb;
@@ -2109,7 +2197,16 @@ int ti_b200_decode_step(ti_model_t h, int32_t token, float* logits_host, int32_t
         TRY(run_step(*m, true));
     }
     m->host_pos += 1;
-    if (logits_host) CK(cudaMemcpyAsync(logits_host, m->logits.p, (size_t)m->cfg.vocab * 4, cudaMemcpyDeviceToHost, g_stream));
+    if (logits_host) {
+        if (m->lm_sharded) {   // into a scratch copy: m->logits must keep its zeros outside this rank's columns
+            if (m->hist.n < (size_t)m->cfg.vocab) TRY(m->hist.alloc((size_t)m->cfg.vocab));
+            CK(cudaMemcpyAsync(m->hist.p, m->logits.p, (size_t)m->cfg.vocab * 4, cudaMemcpyDeviceToDevice, g_stream));
+            TRY(gather_sharded_logits(*m, m->hist.p, (size_t)m->cfg.vocab));
+            CK(cudaMemcpyAsync(logits_host, m->hist.p, (size_t)m->cfg.vocab * 4, cudaMemcpyDeviceToHost, g_stream));
+        } else {
+            CK(cudaMemcpyAsync(logits_host, m->logits.p, (size_t)m->cfg.vocab * 4, cudaMemcpyDeviceToHost, g_stream));
+        }
+    }
     int tok = 0;
     CK(cudaMemcpyAsync(&tok, &m->state.p->token, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
@@ -2181,7 +2278,10 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
     m.host_pos = n_prompt + std::max(0, n_new - 1);
     std::vector<int> toks(std::max(n_new, 1));
     if (n_new > 0) CK(cudaMemcpyAsync(toks.data(), m.out_tokens.p, n_new * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
-    if (logits_host && n_new > 0) CK(cudaMemcpyAsync(logits_host, m.hist.p, (size_t)n_new * V * 4, cudaMemcpyDeviceToHost, g_stream));
+    if (logits_host && n_new > 0) {
+        TRY(gather_sharded_logits(m, m.hist.p, (size_t)n_new * V));
+        CK(cudaMemcpyAsync(logits_host, m.hist.p, (size_t)n_new * V * 4, cudaMemcpyDeviceToHost, g_stream));
+    }
     CK(cudaStreamSynchronize(g_stream));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -2306,6 +2406,136 @@ int ti_b200_generate_batch_greedy(ti_model_t h, const int32_t* prompts, int32_t 
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (decode_ms) *decode_ms = ms;
+    return 0;
+}
+
+// sample_next_token on host logits (op-level entry, tests): rows independent rows of `vocab` logits
+int ti_b200_sample_logits(const float* logits_host, size_t rows, size_t vocab, float temperature, int32_t top_k, float top_p, uint64_t seed,
+                          int32_t step, int32_t* tokens_out, float* logprobs_out) {
+    TRY(need_init());
+    if (rows == 0 || vocab == 0) return fail("Cannot sample from empty logits");   // :1555-1557
+    if (temperature <= 0.0f) return fail("Temperature must be positive");          // apply_temperature (:1676-1678)
+    DevBuf<float> lg, lp;
+    DevBuf<int> tok;
+    TRY(upload(lg, logits_host, rows * vocab));
+    TRY(tok.alloc(rows));
+    TRY(lp.alloc(rows));
+    TRY(launch_sample(lg.p, (int)rows, (int)vocab, (int)vocab, temperature, top_k, top_p, seed, nullptr, step, tok.p, lp.p, nullptr, nullptr, 0, nullptr));
+    CK(cudaMemcpyAsync(tokens_out, tok.p, rows * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    if (logprobs_out) CK(cudaMemcpyAsync(logprobs_out, lp.p, rows * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+// generate() with sampling (:734-802 + :1554-1673): the token is picked ON THE DEVICE from the logits of every step
+// (sample_kernel) and fed to the next forward pass without touching the host; one launch of the decode engine per token.
+int ti_b200_generate_sampled(ti_model_t h, const int32_t* prompt, int32_t n_prompt, int32_t n_new, float temperature, int32_t top_k, float top_p,
+                             uint64_t seed, int32_t stop_on_eos, int32_t* out_tokens, int32_t* n_out, float* logprobs_out, float* decode_ms) {
+    TRY(need_init());
+    Model* mp = get_model(h);
+    if (!mp || !mp->finalized) return fail("invalid or unfinalized model handle");
+    Model& m = *mp;
+    if (m.cfg.compat_literal) return fail("sampling is not part of the literal benchmark path (top_k = 1 there)");
+    if (n_prompt <= 0) return fail("Input tokens cannot be empty");
+    if (n_new < 0) return fail("n_new must be >= 0");
+    if (temperature <= 0.0f) return fail("Temperature must be positive");
+    for (int i = 0; i < n_prompt; ++i)
+        if (prompt[i] < 0 || prompt[i] >= m.cfg.vocab) return fail("token id %d out of range", prompt[i]);
+    TRY(ti_b200_model_reset(h));
+    TRY(check_capacity(m, n_prompt + std::max(0, n_new - 1)));
+    const int V = m.cfg.vocab;
+    if ((int)m.prompt.n < n_prompt) TRY(m.prompt.alloc(n_prompt));
+    CK(cudaMemcpyAsync(m.prompt.p, prompt, n_prompt * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    const int cap = std::max(n_new, 1);
+    if ((int)m.smp_tokens.n < cap) { TRY(m.smp_tokens.alloc(cap)); TRY(m.smp_logprobs.alloc(cap)); }
+    if (!m.smp_count.p) TRY(m.smp_count.alloc(1));
+    StepIO io{};   // the engines' own greedy bookkeeping stays off: the sampler owns the token history
+    CK(cudaMemcpyAsync(m.io.p, &io, sizeof(io), cudaMemcpyHostToDevice, g_stream));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    TRY(prompt_pass(m, prompt, n_prompt));
+    CK(cudaEventRecord(e0, g_stream));
+    if (m.lm_sharded && m.hist.n < (size_t)V) TRY(m.hist.alloc((size_t)V));
+    for (int i = 0; i < n_new; ++i) {
+        const float* row = m.logits.p;
+        if (m.lm_sharded) {   // every rank samples the same full row with the same uniform: identical tokens on all ranks
+            CK(cudaMemcpyAsync(m.hist.p, m.logits.p, (size_t)V * 4, cudaMemcpyDeviceToDevice, g_stream));
+            TRY(gather_sharded_logits(m, m.hist.p, (size_t)V));
+            row = m.hist.p;
+        }
+        TRY(launch_sample(row, 1, V, V, temperature, top_k, top_p, seed, nullptr, i, m.smp_tokens.p + i, m.smp_logprobs.p + i, nullptr, nullptr, 0,
+                          &m.state.p->token));
+        if (i + 1 < n_new) TRY(decode_pass(m));
+    }
+    CK(cudaEventRecord(e1, g_stream));
+    m.host_pos = n_prompt + std::max(0, n_new - 1);
+    std::vector<int> toks(cap);
+    std::vector<float> lps(cap);
+    if (n_new > 0) {
+        CK(cudaMemcpyAsync(toks.data(), m.smp_tokens.p, n_new * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaMemcpyAsync(lps.data(), m.smp_logprobs.p, n_new * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
+    }
+    CK(cudaStreamSynchronize(g_stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (decode_ms) *decode_ms = ms;
+    int produced = n_new;
+    if (stop_on_eos)
+        for (int i = 0; i < n_new; ++i)
+            if (toks[i] == 2) { produced = i + 1; break; }  // :760
+    for (int i = 0; i < produced; ++i) {
+        out_tokens[i] = toks[i];
+        if (logprobs_out) logprobs_out[i] = lps[i];
+    }
+    if (n_out) *n_out = produced;
+    return 0;
+}
+
+// compute_logprobs (:873-954): forward pass over `tokens`, out[pos] = log softmax(logits[pos])[tokens[pos]] (the reference
+// scores a token under the logits of ITS OWN position); -20 for an id outside the vocabulary.
+int ti_b200_compute_logprobs(ti_model_t h, const int32_t* tokens, int32_t n, float* out) {
+    TRY(need_init());
+    Model* mp = get_model(h);
+    if (!mp || !mp->finalized) return fail("invalid or unfinalized model handle");
+    Model& m = *mp;
+    if (m.cfg.compat_literal) return fail("compute_logprobs is not available on the literal benchmark path");
+    if (n <= 0) return fail("Input tokens cannot be empty");
+    const int V = m.cfg.vocab;
+    TRY(ti_b200_model_reset(h));
+    TRY(check_capacity(m, n));
+    std::vector<int> fed(n);
+    for (int i = 0; i < n; ++i) fed[i] = (tokens[i] < 0 || tokens[i] >= V) ? 0 : tokens[i];   // an invalid id is scored -20; it still needs a row to feed
+    if ((int)m.prompt.n < n) TRY(m.prompt.alloc(n));
+    CK(cudaMemcpyAsync(m.prompt.p, fed.data(), n * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    if (m.hist.n < (size_t)n * V) TRY(m.hist.alloc((size_t)n * V));
+    DevBuf<int> tok;
+    DevBuf<float> lp;
+    TRY(tok.alloc(n));
+    TRY(lp.alloc(n));
+    CK(cudaMemcpyAsync(tok.p, tokens, n * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    StepIO io{};
+    io.hist = m.hist.p;
+    io.hist_cap = n;
+    CK(cudaMemcpyAsync(m.io.p, &io, sizeof(io), cudaMemcpyHostToDevice, g_stream));
+    if (m.use_mega) {
+        TRY(run_mega(m, n, n, 0));   // every step runs the lm_head and keeps its logits
+    } else {
+        for (int i = 0; i < n; ++i) {
+            set_token_kernel<<<1, 1, 0, g_stream>>>(m.state.p, m.prompt.p, i);
+            ++g_launches;
+            TRY(run_step(m, true));
+        }
+    }
+    TRY(gather_sharded_logits(m, m.hist.p, (size_t)n * V));
+    logprob_rows_kernel<<<n, 256, 0, g_stream>>>(m.hist.p, V, tok.p, lp.p);
+    ++g_launches;
+    CK(cudaGetLastError());
+    m.host_pos = n;
+    CK(cudaMemcpyAsync(out, lp.p, n * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
     return 0;
 }
 

@@ -79,6 +79,7 @@ struct GemvArgs {
     int page_tokens;
     // EPI_LOGITS
     unsigned long long* argmax_key;
+    int col_off;            // added to the column index in the arg-max key (tensor parallel: this rank's slice of the vocabulary)
     // persistent kernel: the RMSNorm weight the NEXT GEMV applies to this one's output (nullptr: none); used to hand
     // the next prologue its sum of squares and max|x * w| bound (see XStats)
     const float* next_norm_w;
@@ -756,7 +757,7 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
                 a.out[n] = y;
             }
             if (a.epi == EPI_LOGITS) {
-                if (y > best) { best = y; besti = n; }
+                if (y > best) { best = y; besti = n + a.col_off; }
             } else {
                 out_st.ss = fmaf(y, y, out_st.ss);
                 out_st.am = fmaxf(out_st.am, fabsf(y * (first ? pre.nw0 : (a.next_norm_w ? a.next_norm_w[n] : 1.f))));

@@ -17,7 +17,7 @@
 
 namespace tib {
 
-enum MegaPhaseType : int { PH_GEMV = 0, PH_ATTN = 1, PH_REDUCE = 2 };
+enum MegaPhaseType : int { PH_GEMV = 0, PH_ATTN = 1, PH_REDUCE = 2, PH_KEYX = 3 };
 constexpr int kMaxTp = 8;
 struct MegaArgs;
 constexpr int kStampsPerPhase = 32;  // debug timeline: 6 phase-level stamps, [11] ring stages ready, [12..] finer stamps
@@ -78,6 +78,11 @@ struct MegaArgs {
     // flags [source rank][CTA] per partial buffer, written by the source with a system-scope release
     unsigned int* peer_flag[2][kMaxTp];
     int tp_p2p;
+    // tensor parallel with the lm_head sharded over the vocabulary: every rank's local (max, index) key of a
+    // sampling step goes to slot [step & 1][rank] of every rank's exchange block (PH_KEYX phase), the barrier across the GPUs
+    // follows, and the token is the maximum of the P keys -- n_head = 2 phases run on sampling steps only (lm_head, PH_KEYX)
+    unsigned long long* peer_keys[kMaxTp];
+    int n_head;
     const XStats* emb_stats;  // [V]: statistics of every embedding row (against the first norm weight)
     // the sequence's KV page table (static for the launch), copied to shared memory once: kv_pages entries (0: none)
     const int* kv_page_table;
@@ -726,7 +731,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
             unsigned int k = 0;                                  // local barriers of this launch
             unsigned int kk = m.tp > 1 ? *m.mg_seq : 0u;         // multi-GPU barriers since the group was formed
             for (int s = 0; s < m.n_steps; ++s) {
-                const int nph = m.nphases - (s >= m.first_sample ? 0 : 1);   // the lm_head runs on sampling steps only
+                const int nph = m.nphases - (s >= m.first_sample ? 0 : m.n_head);   // the lm_head (and the key exchange) run on sampling steps only
                 for (int ph = 0; ph < nph; ++ph) {
                     // what the NEXT phase's prologue needs to turn the statistics into its conversion scalars (fetched
                     // while the consumers are still working on this phase)
@@ -823,7 +828,14 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
         need_wait = false;
     };
     auto decode_key = [&](int s) -> int {
-        const unsigned long long key = __ldcg(&m.keys[s & 1]);
+        unsigned long long key = __ldcg(&m.keys[s & 1]);
+        if (m.n_head == 2) {   // vocabulary sharded over the tensor-parallel ranks: the maximum of every rank's key
+            key = 0ull;
+            for (int r = 0; r < m.tp; ++r) {
+                const unsigned long long kr = __ldcg(m.peer_keys[m.tp_rank] + (size_t)(s & 1) * kMaxTp + r);
+                key = kr > key ? kr : key;
+            }
+        }
         // key 0: no logit compared greater than -inf (all NaN / -inf): defined as token 0; the clamp keeps the embedding
         // lookup of the next step inside the table whatever the key holds
         const int tok = key == 0ull ? 0 : 0x7FFFFFFF - (int)(uint32_t)(key & 0xFFFFFFFFull);
@@ -856,8 +868,8 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
         }
         if (s < m.n_prompt) token = m.prompt[s];
         for (int ph = 0; ph < m.nphases; ++ph) {
-            const bool is_head = ph == m.nphases - 1;  // the lm_head is always the last phase
-            if (is_head && !sample) continue;
+            const bool is_head = ph == m.nphases - m.n_head;  // the lm_head is the first of the n_head phases at the end of the list
+            if (ph >= m.nphases - m.n_head && !sample) continue;
             // debug timeline: thread 0 of CTA 0 (dbg_flags & 4: of every CTA) stamps the SM clock along the phase
             const bool stamp = TL && m.dbg != nullptr && s == 0 && tid == 0 && (blockIdx.x == 0 || (m.dbg_flags & 4));
             long long* ts = m.dbg + ((size_t)blockIdx.x * m.nphases + ph) * kStampsPerPhase;
@@ -955,6 +967,14 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                             out_st.am = fmaxf(out_st.am, fabsf(P.g.next_norm_w ? v * P.g.next_norm_w[n] : v));
                         }
                     }
+                }
+            } else if (P.type == PH_KEYX) {
+                // the lm_head's grid barrier has been passed: this rank's key is final; hand it to every rank (the barrier
+                // across the GPUs that ends this phase orders the stores before anybody reads them)
+                if (blockIdx.x == 0 && tid == 0) {
+                    const unsigned long long key = __ldcg(&m.keys[s & 1]);
+                    for (int r = 0; r < m.tp; ++r)
+                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(m.peer_keys[r] + (size_t)(s & 1) * kMaxTp + m.tp_rank), "l"(key) : "memory");
                 }
             } else if (P.type == PH_REDUCE) {
                 // all-reduce, second half: every rank's partial of the row-parallel GEMV is in this rank's buffer (the

@@ -1,0 +1,418 @@
+// sampling.cuh -- on-device sample_next_token (src/model/inference_engine.cpp:1554-1673): temperature -> top-k -> softmax ->
+// top-p -> inverse CDF, plus the log-probabilities of compute_logprobs (:873-954).  The reference does this on the host
+// with two std::sort calls over the vocabulary per token; here one CTA per sequence does it next to the logits, and the
+// token never leaves the device between steps.
+//
+// Randomness: the reference draws from a time-seeded std::mt19937 (:472), so its stream cannot be reproduced.  Here the
+// uniform of step s is a counter-based hash of (seed, s) (sample_uniform below; the test-side restatement of the reference algorithm takes the same uniform), which
+// makes a generation reproducible and testable.
+//
+// Arithmetic contract (what tests/test_gpu_sampling.py checks against the CPU restatement of the reference algorithm on the same logits):
+//   * top_k in [1, 1024] (the reference default is 50): the survivors are gathered in index order into shared memory and
+//     every sum the reference computes sequentially over the vocabulary (softmax denominator, top-p cumulative sum in sorted
+//     order, renormalisation, inverse CDF) is computed sequentially over the survivors in the same order -- adding the
+//     exact zeros of the filtered entries changes nothing, so the result equals the reference's arithmetic up to the last
+//     bit of expf (CUDA's expf vs glibc's).  Equal logits / probabilities: std::sort is unstable, i.e. the reference's
+//     order among ties is unspecified; here (and in the test-side restatement) ties go by ascending index.
+//   * top_k = 0 or > 1024 (no top-k filter, or a very wide one): the same pipeline with block-wide parallel sums and a
+//     radix search for the top-p cut -- the same distribution, sums in a different order (~1e-6 relative), ties at the
+//     top-p cut kept as a group.
+#pragma once
+#include "kernels.cuh"
+
+namespace tib {
+
+constexpr int kSampleThreads = 1024;
+constexpr int kTopKMax = 1024;
+
+// uniform in [0, 1) with 24 bits, from (seed, step); the same function on the host side of the tests
+TIB_HD float sample_uniform(uint64_t seed, uint64_t step) {
+    const uint64_t h = splitmix64(splitmix64(seed) ^ (step * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull));
+    return (float)(uint32_t)(h >> 40) * (1.0f / 16777216.0f);
+}
+
+struct SampleArgs {
+    const float* logits;   // [V] of this sequence (blockIdx.x selects the row: logits + row * ld)
+    int V, ld;
+    float temperature;
+    int top_k;
+    float top_p;
+    uint64_t seed;
+    const int* step_ptr;   // device scalar: index of the token being sampled (the counter of the RNG); may be null -> step
+    int step;
+    int* token_out;        // [rows]
+    float* logprob_out;    // [rows] or null
+    int* hist_tokens;      // optional history: hist_tokens[row * hist_stride + step]
+    float* hist_logprobs;
+    int hist_stride;
+    int* feed_token;       // optional: where the next decode step reads its input token (StepState::token)
+};
+
+__device__ __forceinline__ uint32_t desc_key(float v) {   // larger value -> larger key
+    uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// block-wide exclusive scan of one int per thread (1024 threads); returns the exclusive prefix, total in *total
+__device__ __forceinline__ int block_exscan(int v, int* wsum, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        wsum[lane] = winc - w;
+        if (lane == 31) *total = winc;
+    }
+    __syncthreads();
+    const int r = wsum[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ float block_exscan_f(float v, float* wsum, float* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        float w = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0.f;
+        float winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        wsum[lane] = winc - w;
+        if (lane == 31) *total = winc;
+    }
+    __syncthreads();
+    const float r = wsum[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs a) {
+    __shared__ int hist[256];
+    __shared__ float fhist[256];
+    __shared__ int wsum[32];
+    __shared__ float wsumf[32];
+    __shared__ int s_tot, s_sel, s_need, s_token;
+    __shared__ float s_ftot, s_max, s_sum, s_lp;
+    __shared__ uint32_t s_prefix;
+    __shared__ int sidx[kTopKMax];
+    __shared__ float sval[kTopKMax];      // scaled logit, then probability
+    __shared__ int sord[kTopKMax];        // positions sorted by (probability desc, index asc)
+    const int tid = threadIdx.x, V = a.V;
+    const float* lg = a.logits + (size_t)blockIdx.x * a.ld;
+    const int step = a.step_ptr ? *a.step_ptr : a.step;
+    const float u = sample_uniform(a.seed + (uint64_t)blockIdx.x * 0x51ED27ull, (uint64_t)step);
+    const bool scale = a.temperature != 1.0f && a.temperature > 0.0f;                      // :1578-1582
+    auto val = [&](int i) -> float { const float x = lg[i]; return scale ? x / a.temperature : x; };
+    // indices in blocked order: thread t owns [t * per, (t + 1) * per) -- a compaction by thread order is then in index order
+    const int per = (V + kSampleThreads - 1) / kSampleThreads;
+    const int i0 = min(tid * per, V), i1 = min(i0 + per, V);
+    const bool use_topk = a.top_k > 0 && a.top_k < V;                                        // :1585
+    const bool exact = use_topk && a.top_k <= kTopKMax;
+
+    if (exact) {
+        // ---- radix select of the k-th largest key (4 passes of 8 bits, most significant first) ----
+        const int k = a.top_k;
+        uint32_t prefix = 0, mask = 0;
+        int need = k;   // how many of the elements matching the prefix are still to be taken from the top
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            for (int b = tid; b < 256; b += kSampleThreads) hist[b] = 0;
+            __syncthreads();
+            for (int i = i0; i < i1; ++i) {
+                const uint32_t key = desc_key(val(i));
+                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int acc = 0, b = 255;
+                for (; b > 0; --b) {
+                    if (acc + hist[b] >= need) break;
+                    acc += hist[b];
+                }
+                s_sel = b;
+                s_need = need - acc;
+            }
+            __syncthreads();
+            prefix |= (uint32_t)s_sel << shift;
+            mask |= 255u << shift;
+            need = s_need;
+            __syncthreads();
+        }
+        const uint32_t tau = prefix;   // key of the k-th largest value; `need` of the elements equal to it survive (lowest indices)
+        // ---- gather the survivors in index order ----
+        int cgt = 0, ceq = 0;
+        for (int i = i0; i < i1; ++i) {
+            const uint32_t key = desc_key(val(i));
+            cgt += key > tau ? 1 : 0;
+            ceq += key == tau ? 1 : 0;
+        }
+        const int eq_before = block_exscan(ceq, wsum, &s_tot);
+        int keep = cgt, eqr = eq_before;
+        for (int i = i0; i < i1; ++i)
+            if (desc_key(val(i)) == tau) { keep += eqr < need ? 1 : 0; ++eqr; }
+        int off = block_exscan(keep, wsum, &s_tot);   // the total lands in shared memory: every thread reads it
+        eqr = eq_before;
+        for (int i = i0; i < i1; ++i) {
+            const float x = val(i);
+            const uint32_t key = desc_key(x);
+            bool take = key > tau;
+            if (key == tau) { take = eqr < need; ++eqr; }
+            if (take) { sidx[off] = i; sval[off] = x; ++off; }
+        }
+        __syncthreads();
+        const int n = s_tot;   // == k
+        // ---- softmax over the survivors (:1600-1612): exp in parallel, the sum sequentially in index order ----
+        if (tid == 0) {
+            float mx = sval[0];
+            for (int i = 1; i < n; ++i) mx = fmaxf(mx, sval[i]);
+            s_max = mx;
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += kSampleThreads) sval[i] = expf(sval[i] - s_max);
+        __syncthreads();
+        if (tid == 0) {
+            float s = 0.f;
+            for (int i = 0; i < n; ++i) s += sval[i];
+            s_sum = s;
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += kSampleThreads) sval[i] = sval[i] / s_sum;
+        __syncthreads();
+        // ---- top-p (:1614-1648): rank by (probability desc, index asc), sequential cumulative sum in that order ----
+        if (a.top_p < 1.0f) {
+            for (int i = tid; i < n; i += kSampleThreads) {
+                const float p = sval[i];
+                int rank = 0;
+                for (int j = 0; j < n; ++j) {
+                    const float q = sval[j];
+                    rank += (q > p || (q == p && j < i)) ? 1 : 0;   // survivors are in index order: j < i <=> smaller index
+                }
+                sord[rank] = i;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float c = 0.f;
+                int cutoff = n;
+                for (int r = 0; r < n; ++r) {
+                    c += sval[sord[r]];
+                    if (c >= a.top_p) { cutoff = r + 1; break; }
+                }
+                s_sel = cutoff;
+            }
+            __syncthreads();
+            for (int r = s_sel + tid; r < n; r += kSampleThreads) sval[sord[r]] = 0.0f;
+            __syncthreads();
+            if (tid == 0) {
+                float s = 0.f;
+                for (int i = 0; i < n; ++i) s += sval[i];
+                s_sum = s;
+            }
+            __syncthreads();
+            if (s_sum > 0.0f)
+                for (int i = tid; i < n; i += kSampleThreads) sval[i] = sval[i] / s_sum;
+            __syncthreads();
+        }
+        // ---- inverse CDF in index order (:1650-1666) ----
+        if (tid == 0) {
+            float c = 0.f;
+            int tok = V - 1;
+            float lp = -INFINITY;   // the fall-back of :1668-1672: last token, log of ITS probability (0 unless it survived)
+            bool found = false;
+            if (u <= 0.0f) {   // the reference loop's `random_value <= cumsum` holds at index 0 for a uniform of exactly 0
+                tok = 0;
+                lp = (n > 0 && sidx[0] == 0) ? logf(sval[0]) : -INFINITY;
+                found = true;
+            }
+            for (int i = 0; i < n && !found; ++i) {
+                c += sval[i];
+                if (u <= c) { tok = sidx[i]; lp = logf(sval[i]); found = true; break; }
+            }
+            if (!found && n > 0 && sidx[n - 1] == V - 1) lp = logf(sval[n - 1]);
+            s_token = tok;
+            s_lp = lp;
+        }
+        __syncthreads();
+    } else {
+        // ---- no top-k filter (or a wider one than the exact path holds): block-wide sums ----
+        // (a top_k > 1024 is applied as a key threshold first, found with the same radix select on counts)
+        uint32_t kth = 0;   // survivors: key >= kth
+        if (use_topk) {
+            uint32_t prefix = 0, mask = 0;
+            int need = a.top_k;
+            for (int pass = 0; pass < 4; ++pass) {
+                const int shift = 24 - 8 * pass;
+                for (int b = tid; b < 256; b += kSampleThreads) hist[b] = 0;
+                __syncthreads();
+                for (int i = i0; i < i1; ++i) {
+                    const uint32_t key = desc_key(val(i));
+                    if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    int acc = 0, b = 255;
+                    for (; b > 0; --b) {
+                        if (acc + hist[b] >= need) break;
+                        acc += hist[b];
+                    }
+                    s_sel = b;
+                    s_need = need - acc;
+                }
+                __syncthreads();
+                prefix |= (uint32_t)s_sel << shift;
+                mask |= 255u << shift;
+                need = s_need;
+                __syncthreads();
+            }
+            kth = prefix;
+        }
+        float mx = -INFINITY;
+        for (int i = i0; i < i1; ++i) {
+            const float x = val(i);
+            if (desc_key(x) >= kth) mx = fmaxf(mx, x);
+        }
+        mx = warp_max(mx);
+        if ((tid & 31) == 0) wsumf[tid >> 5] = mx;
+        __syncthreads();
+        if (tid == 0) {
+            float m2 = -INFINITY;
+            for (int w = 0; w < kSampleThreads / 32; ++w) m2 = fmaxf(m2, wsumf[w]);
+            s_max = m2;
+        }
+        __syncthreads();
+        auto prob_un = [&](int i) -> float {   // unnormalised probability of a survivor, 0 otherwise
+            const float x = val(i);
+            return desc_key(x) >= kth ? expf(x - s_max) : 0.f;
+        };
+        float part = 0.f;
+        for (int i = i0; i < i1; ++i) part += prob_un(i);
+        float Z;
+        (void)block_exscan_f(part, wsumf, &s_ftot);
+        Z = s_ftot;
+        uint32_t pth = kth;   // top-p: survivors are the keys >= pth
+        if (a.top_p < 1.0f) {
+            // radix search over the key: the largest threshold whose mass from the top reaches top_p * Z
+            const float target = a.top_p * Z;
+            uint32_t prefix = 0, mask = 0;
+            float above = 0.f;   // mass of the keys above the current prefix range
+            for (int pass = 0; pass < 4; ++pass) {
+                const int shift = 24 - 8 * pass;
+                for (int b = tid; b < 256; b += kSampleThreads) fhist[b] = 0.f;
+                __syncthreads();
+                for (int i = i0; i < i1; ++i) {
+                    const uint32_t key = desc_key(val(i));
+                    if (key >= kth && (key & mask) == prefix) atomicAdd(&fhist[(key >> shift) & 255u], expf(val(i) - s_max));
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    float acc = above;
+                    int b = 255;
+                    for (; b > 0; --b) {
+                        if (acc + fhist[b] >= target) break;
+                        acc += fhist[b];
+                    }
+                    s_sel = b;
+                    s_ftot = acc;
+                }
+                __syncthreads();
+                prefix |= (uint32_t)s_sel << shift;
+                mask |= 255u << shift;
+                above = s_ftot;
+                __syncthreads();
+            }
+            pth = prefix > kth ? prefix : kth;
+        }
+        // renormalise over the final survivors and walk the CDF: per-thread sequential, block-wide exclusive scan between
+        float mine = 0.f;
+        for (int i = i0; i < i1; ++i) {
+            const float x = val(i);
+            if (desc_key(x) >= pth) mine += expf(x - s_max);
+        }
+        float Z2;
+        const float before = block_exscan_f(mine, wsumf, &s_ftot);
+        Z2 = s_ftot;
+        if (tid == 0) { s_token = -1; s_lp = -INFINITY; }
+        __syncthreads();
+        const float target = u * Z2;
+        // the owner of the target: the first thread (in index order) whose inclusive prefix reaches it
+        if (mine > 0.f && before < target && target <= before + mine) {
+            float c = before;
+            int tok = -1;
+            float pr = 0.f;
+            for (int i = i0; i < i1; ++i) {
+                const float x = val(i);
+                if (desc_key(x) >= pth) {
+                    const float p = expf(x - s_max);
+                    c += p;
+                    tok = i;
+                    pr = p;
+                    if (target <= c) break;
+                }
+            }
+            s_token = tok;
+            s_lp = logf(pr / Z2);
+        }
+        __syncthreads();
+        if (tid == 0 && s_token < 0) {
+            // u == 0 exactly (target 0: the first survivor), or rounding left the target just above the total: the reference
+            // takes the first entry with u <= cumsum / falls back to the last token (:1668-1672)
+            int tok = V - 1;
+            float lp = -INFINITY;
+            if (target <= 0.f) {   // uniform of exactly 0: index 0 (see the exact path)
+                tok = 0;
+                lp = desc_key(val(0)) >= pth ? logf(expf(val(0) - s_max) / Z2) : -INFINITY;
+            } else if (desc_key(val(V - 1)) >= pth) {
+                lp = logf(expf(val(V - 1) - s_max) / Z2);
+            }
+            s_token = tok;
+            s_lp = lp;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        a.token_out[blockIdx.x] = s_token;
+        if (a.logprob_out) a.logprob_out[blockIdx.x] = s_lp;
+        if (a.hist_tokens && step < a.hist_stride) a.hist_tokens[(size_t)blockIdx.x * a.hist_stride + step] = s_token;
+        if (a.hist_logprobs && step < a.hist_stride) a.hist_logprobs[(size_t)blockIdx.x * a.hist_stride + step] = s_lp;
+        if (a.feed_token) a.feed_token[blockIdx.x] = s_token;
+    }
+}
+
+// compute_logprobs (:919-944): one block per position, logprob of tokens[pos] under logits[pos]:
+//   logit - max - log(sum exp(logit - max)); the -20 of an out-of-vocabulary token id (:933-936)
+__global__ void logprob_rows_kernel(const float* logits, int V, const int* tokens, float* out) {
+    __shared__ float red[32];
+    const float* row = logits + (size_t)blockIdx.x * V;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) mx = fmaxf(mx, row[i]);
+    mx = block_max_256(mx, red);
+    float s = 0.f;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) s += expf(row[i] - mx);
+    const float tot = block_sum_256(s, red);
+    if (threadIdx.x == 0) {
+        const int tok = tokens[blockIdx.x];
+        out[blockIdx.x] = (tok < 0 || tok >= V) ? -20.0f : row[tok] - mx - logf(tot);
+    }
+}
+
+}  // namespace tib

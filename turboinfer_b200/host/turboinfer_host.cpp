@@ -361,6 +361,8 @@ struct InferenceEngine::Stats {
     size_t generations = 0, tokens = 0;
     double time_ms = 0.0, peak_tps = 0.0;
     std::mt19937 rng{(uint32_t)std::chrono::steady_clock::now().time_since_epoch().count()};  // time-seeded like the reference (:472)
+    bool seed_set = false;
+    uint64_t seed = 0;
 };
 
 InferenceEngine::InferenceEngine(const ModelData& model_data, const InferenceConfig& config)
@@ -439,6 +441,15 @@ void InferenceEngine::validate_input_tokens(const std::vector<int>& tokens) cons
     if (tokens.size() > config_.max_sequence_length) throw std::runtime_error("Input sequence length exceeds maximum allowed length");
 }
 void InferenceEngine::reset_state() { ck(ti_b200_model_reset(handle_)); }
+void InferenceEngine::set_seed(uint64_t seed) { stats_->seed_set = true; stats_->seed = seed; }
+
+std::vector<float> InferenceEngine::compute_logprobs(const std::vector<int>& tokens) {
+    validate_input_tokens(tokens);
+    std::vector<float> out(tokens.size());
+    // the reference swallows failures and answers with a sentinel (-18: computation error, :947-952)
+    if (ti_b200_compute_logprobs(handle_, tokens.data(), (int32_t)tokens.size(), out.data()) != 0) return std::vector<float>(tokens.size(), -18.0f);
+    return out;
+}
 
 core::Tensor InferenceEngine::forward_pass_incremental(const std::vector<int>& tokens) {
     if (tokens.empty()) throw std::runtime_error("Cannot perform incremental forward pass with empty token sequence");
@@ -447,39 +458,6 @@ core::Tensor InferenceEngine::forward_pass_incremental(const std::vector<int>& t
     for (size_t i = 0; i < tokens.size(); ++i)
         ck(ti_b200_decode_step(handle_, tokens[i], logits.data_ptr<float>() + i * V, nullptr));
     return logits;
-}
-
-// host-side sampling for the non-greedy settings: temperature -> top-k -> softmax -> top-p -> inverse CDF
-int InferenceEngine::sample_next_token(const float* logits, std::vector<float>* logprobs) {
-    const size_t V = model_metadata_.vocab_size;
-    if (config_.temperature <= 0.0f) throw std::runtime_error("Temperature must be positive");
-    std::vector<int> order(V);
-    std::iota(order.begin(), order.end(), 0);
-    const size_t k = config_.top_k > 0 && config_.top_k < V ? config_.top_k : V;
-    std::partial_sort(order.begin(), order.begin() + k, order.end(), [&](int a, int b) { return logits[a] > logits[b] || (logits[a] == logits[b] && a < b); });
-    std::vector<double> p(k);
-    const double mx = logits[order[0]] / config_.temperature;
-    double sum = 0.0;
-    for (size_t i = 0; i < k; ++i) sum += (p[i] = std::exp(logits[order[i]] / config_.temperature - mx));
-    for (double& v : p) v /= sum;
-    size_t keep = k;
-    if (config_.top_p > 0.0f && config_.top_p < 1.0f) {
-        double c = 0.0;
-        for (size_t i = 0; i < k; ++i) {
-            c += p[i];
-            if (c >= config_.top_p) { keep = i + 1; break; }
-        }
-    }
-    double kept = 0.0;
-    for (size_t i = 0; i < keep; ++i) kept += p[i];
-    double u = std::uniform_real_distribution<double>(0.0, 1.0)(stats_->rng) * kept, c = 0.0;
-    size_t pick = keep - 1;
-    for (size_t i = 0; i < keep; ++i) {
-        c += p[i];
-        if (u <= c) { pick = i; break; }
-    }
-    if (logprobs) logprobs->push_back((float)std::log(p[pick] / kept));
-    return order[pick];
 }
 
 GenerationResult InferenceEngine::generate(const std::vector<int>& input_tokens, size_t max_new_tokens, bool include_logprobs) {
@@ -513,17 +491,21 @@ GenerationResult InferenceEngine::generate(const std::vector<int>& input_tokens,
         if (n_out > 0 && out[n_out - 1] == 2) { result.finished = true; result.stop_reason = "eos_token"; }
         else if (result.tokens.size() >= config_.max_sequence_length) { result.finished = true; result.stop_reason = "max_length"; }
     } else if (budget > 0) {
-        reset_state();
-        std::vector<float> logits(V);
-        for (size_t i = 0; i < input_tokens.size(); ++i)
-            ck(ti_b200_decode_step(handle_, input_tokens[i], i + 1 == input_tokens.size() ? logits.data() : nullptr, nullptr));
-        for (size_t i = 0; i < budget; ++i) {
-            const int next = sample_next_token(logits.data(), include_logprobs ? &result.logprobs : nullptr);
-            result.tokens.push_back(next);
-            if (next == 2) { result.finished = true; result.stop_reason = "eos_token"; break; }
-            if (result.tokens.size() >= config_.max_sequence_length) { result.finished = true; result.stop_reason = "max_length"; break; }
-            if (i + 1 < budget) ck(ti_b200_decode_step(handle_, next, logits.data(), nullptr));
+        // sampling: the token is picked on the device from every step's logits and fed to the next forward pass there
+        if (config_.temperature <= 0.0f) throw std::runtime_error("Temperature must be positive");
+        std::vector<int32_t> out(budget);
+        std::vector<float> lps(budget);
+        int32_t n_out = 0;
+        const uint64_t seed = stats_->seed_set ? stats_->seed + stats_->generations : stats_->rng();
+        ck(ti_b200_generate_sampled(handle_, input_tokens.data(), (int32_t)input_tokens.size(), (int32_t)budget, config_.temperature,
+                                    (int32_t)std::min<size_t>(config_.top_k, 0x7fffffff), config_.top_p, seed, 1, out.data(), &n_out,
+                                    include_logprobs ? lps.data() : nullptr, nullptr));
+        for (int32_t i = 0; i < n_out; ++i) {
+            result.tokens.push_back(out[i]);
+            if (include_logprobs) result.logprobs.push_back(lps[i]);
         }
+        if (n_out > 0 && out[n_out - 1] == 2) { result.finished = true; result.stop_reason = "eos_token"; }
+        else if (result.tokens.size() >= config_.max_sequence_length) { result.finished = true; result.stop_reason = "max_length"; }
     }
     const auto t1 = std::chrono::high_resolution_clock::now();
     result.total_time_ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
