@@ -35,6 +35,7 @@ enum { TI_Q_INT8 = 0, TI_Q_INT4 = 1, TI_Q_NONE = 3 };
 
 typedef uint64_t ti_qweight_t; /* packed INT4/INT8 weight resident in HBM */
 typedef uint64_t ti_model_t;   /* device-resident decoder (weights + paged KV cache + decode graph) */
+typedef uint64_t ti_kv_t;      /* stand-alone paged KV cache (the reference's KVCache as an object of its own) */
 
 /* ---- lifecycle / errors ---------------------------------------------------------------------
  * replaces TensorEngine::TensorEngine(ComputeDevice) / initialize / gpu_available / device_info
@@ -114,6 +115,39 @@ int ti_b200_softmax(const float* x_host, float* y_host, size_t rows, size_t n, f
 int ti_b200_attention_decode(const float* q_host, const float* k_host, const float* v_host, float* out_host,
                              size_t B, size_t t, size_t H, size_t num_heads);
 
+/* ---- fused GEMV (north_star item 4) -----------------------------------------------------------------
+ * ti_b200_quantize_pack_fused: up to three [K, n_i] matrices sharing x packed as ONE streaming weight, each keeping its own
+ *                           per-tensor scale: concatenated (q | k | v) or, interleave = 1, two sources column-interleaved
+ *                           (gate_i, up_i) for the SwiGLU epilogue -- what initialize_model's separate tensors become here.
+ * ti_b200_gemv_q_ex:        the decode GEMV with its fused prologue / epilogues: norm_w_host != NULL applies rms_norm(x, norm_w, eps)
+ *                           (tensor_engine.cpp:1452-1508) in front; epilogue = TI_EPI_STORE, TI_EPI_RESIDUAL (y + resid, :1626-1678),
+ *                           TI_EPI_SWIGLU (up_i * silu(gate_i), N / 2 outputs, :900-923 + :1680-1743) or TI_EPI_RELU (:828-869). */
+enum { TI_EPI_STORE = 0, TI_EPI_RESIDUAL = 1, TI_EPI_SWIGLU = 2, TI_EPI_RELU = 3 };
+int ti_b200_quantize_pack_fused(const float* const* w_host, const size_t* n_cols, int32_t n_src, int32_t interleave, size_t K,
+                                int qtype, ti_qweight_t* out);
+int ti_b200_gemv_q_ex(ti_qweight_t w, const float* x_host, float* y_host, int32_t epilogue, const float* resid_host,
+                      const float* norm_w_host, float eps);
+
+/* ---- KV cache manager ---------------------------------------------------------------------------------
+ * The reference's KVCache (src/model/inference_engine.cpp:25-172) as a device-resident, paged object: per layer two pools
+ * [page][page_tokens][heads * head_dim] fp32 behind one page table.
+ *   ti_b200_kv_create    <- KVCache::initialize (:40-55), batch 1
+ *   ti_b200_kv_reset     <- KVCache::reset (:57-69): lengths to 0 (no zero-fill needed: nothing reads beyond the length)
+ *   ti_b200_kv_append    <- update_incremental / update (:78-172): k_new / v_new [heads, new_tokens, head_dim] appended at the
+ *                           layer's length; "Layer index out of bounds for KV cache" and "KV cache overflow: sequence too long"
+ *                           are the reference's errors.  Each layer has its OWN length (the reference advances one shared counter
+ *                           on every layer's update, which overflows a model of L layers after max/L tokens).
+ *   ti_b200_kv_read      <- the (full_keys, full_values) pair update_incremental returns: [heads, length, head_dim]
+ *   ti_b200_kv_attention <- attention over the cached tokens read in place (no copy-out): multi_head_attention with q_len 1
+ *                           (tensor_engine.cpp:1149-1252); heads = 1 is attention_fast_incremental (:1254-1388) */
+int ti_b200_kv_create(int32_t layers, int32_t heads, int32_t head_dim, int32_t max_seq, int32_t page_tokens, ti_kv_t* out);
+int ti_b200_kv_destroy(ti_kv_t kv);
+int ti_b200_kv_reset(ti_kv_t kv);
+int ti_b200_kv_length(ti_kv_t kv, int32_t layer, int32_t* current_length, int32_t* max_length);
+int ti_b200_kv_append(ti_kv_t kv, int32_t layer, const float* k_new_host, const float* v_new_host, int32_t new_tokens);
+int ti_b200_kv_read(ti_kv_t kv, int32_t layer, float* k_out_host, float* v_out_host);
+int ti_b200_kv_attention(ti_kv_t kv, int32_t layer, const float* q_host, float* out_host);
+
 /* device-pointer variant of the GEMV used by the bench (inputs already resident in HBM) */
 int ti_b200_gemv_q_dev(ti_qweight_t w, const float* x_dev, float* y_dev);
 
@@ -160,6 +194,11 @@ int ti_b200_decode_step(ti_model_t m, int32_t token, float* logits_host, int32_t
  * [n_new, vocab]; decode_ms (optional) is the CUDA-event time of the decode loop only. */
 int ti_b200_generate_greedy(ti_model_t m, const int32_t* prompt, int32_t n_prompt, int32_t n_new, int32_t stop_on_eos,
                             int32_t* out_tokens, int32_t* n_out, float* logits_host, float* decode_ms);
+
+/* forward_pass (:1429-1491) over a prompt: resets the model's KV cache, fills it with the n tokens (tensor-core GEMM path for
+ * prompts of >= 33 tokens, the decode engine otherwise) and returns the logits of the last position (last_logits_host may be NULL).
+ * ti_b200_decode_step continues from there. */
+int ti_b200_prefill(ti_model_t m, const int32_t* tokens, int32_t n, float* last_logits_host);
 
 /* generate_batch() (src/model/inference_engine.cpp:804-828, a sequential loop of generate() in the reference): `batch`
  * prompts of equal length n_prompt ([batch][n_prompt]), n_new >= 1 greedy tokens each, advanced in lockstep so that the

@@ -28,15 +28,19 @@ for shape, layers, qt, n_new in cases:
     ref = tb.Model(meta, qt, attn_mode=1, rope_mode=1, max_seq=128).load(w)
     rt, rl, _ = ref.generate_greedy(prompt, n_new, want_logits=True)
     rbt, rbl, _ = ref.generate_batch_greedy(prompts, 6, want_logits=True)
+    rs, rsl, _ = ref.generate_sampled(prompt, 10, temperature=0.9, top_k=40, top_p=0.9, seed=5)   # on-device sampling
+    rlp = ref.compute_logprobs(prompt + [int(x) for x in rt[:4]])
     ref.free()
     m = tb.Model(meta, qt, attn_mode=1, rope_mode=1, max_seq=128, tp=world).load(w)
     t0 = time.perf_counter()
     tt, tl, ms = m.generate_greedy(prompt, n_new, want_logits=True)
     dt = time.perf_counter() - t0
     tbt, tbl, _ = m.generate_batch_greedy(prompts, 6, want_logits=True)
+    ts_, tsl, _ = m.generate_sampled(prompt, 10, temperature=0.9, top_k=40, top_p=0.9, seed=5)
+    tlp = m.compute_logprobs(prompt + [int(x) for x in rt[:4]])
     m.free()
-    same = bool(np.array_equal(rt, tt)) and bool(np.array_equal(rbt, tbt))
-    err = max(float(rel_err_inf(tl, rl)), float(rel_err_inf(tbl, rbl)))
+    same = bool(np.array_equal(rt, tt)) and bool(np.array_equal(rbt, tbt)) and bool(np.array_equal(rs, ts_))
+    err = max(float(rel_err_inf(tl, rl)), float(rel_err_inf(tbl, rbl)), float(np.max(np.abs(tlp - rlp))), float(np.max(np.abs(tsl - rsl))))
     ok &= same and err <= 1e-4
     print(json.dumps({"rank": rank, "case": f"{shape}/L{meta['layers']}/q{qt}", "tokens_equal": same, "logits_rel_err": err,
                       "tp_decode_ms_per_token": ms / max(1, n_new - 1)}), flush=True)

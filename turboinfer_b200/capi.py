@@ -61,6 +61,16 @@ SYMBOLS = {
     "ti_b200_silu_mul": (C.c_int, [_f, _f, _f, C.c_size_t]),
     "ti_b200_softmax": (C.c_int, [_f, _f, C.c_size_t, C.c_size_t, C.c_float]),
     "ti_b200_attention_decode": (C.c_int, [_f, _f, _f, _f, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]),
+    "ti_b200_quantize_pack_fused": (C.c_int, [C.POINTER(_f), C.POINTER(C.c_size_t), C.c_int32, C.c_int32, C.c_size_t, C.c_int, C.POINTER(C.c_uint64)]),
+    "ti_b200_gemv_q_ex": (C.c_int, [C.c_uint64, _f, _f, C.c_int32, _f, _f, C.c_float]),
+    "ti_b200_kv_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
+    "ti_b200_kv_destroy": (C.c_int, [C.c_uint64]),
+    "ti_b200_kv_reset": (C.c_int, [C.c_uint64]),
+    "ti_b200_kv_length": (C.c_int, [C.c_uint64, C.c_int32, _i32, _i32]),
+    "ti_b200_kv_append": (C.c_int, [C.c_uint64, C.c_int32, _f, _f, C.c_int32]),
+    "ti_b200_kv_read": (C.c_int, [C.c_uint64, C.c_int32, _f, _f]),
+    "ti_b200_kv_attention": (C.c_int, [C.c_uint64, C.c_int32, _f, _f]),
+    "ti_b200_prefill": (C.c_int, [C.c_uint64, _i32, C.c_int32, _f]),
     "ti_b200_gemv_q_dev": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p]),
     "ti_b200_model_new": (C.c_int, [C.POINTER(ModelConfig), C.POINTER(C.c_uint64)]),
     "ti_b200_model_set_tensor": (C.c_int, [C.c_uint64, C.c_char_p, _f, C.c_size_t, C.c_size_t]),
@@ -214,6 +224,72 @@ class QWeight:
     def free(self) -> None:
         if self.handle:
             _ck(lib().ti_b200_qweight_free(self.handle))
+            self.handle = 0
+
+
+EPI_STORE, EPI_RESIDUAL, EPI_SWIGLU, EPI_RELU = 0, 1, 2, 3
+
+
+class FusedQWeight(QWeight):
+    """Several [K, n_i] matrices that share x, packed as one streaming weight (q | k | v, or gate / up interleaved)."""
+
+    def __init__(self, mats, qtype: int, interleave: bool = False):
+        mats = [_c(m) for m in mats]
+        K = mats[0].shape[0]
+        ptrs = (_f * len(mats))(*[_fp(m) for m in mats])
+        ncols = (C.c_size_t * len(mats))(*[m.shape[1] for m in mats])
+        h = C.c_uint64()
+        _ck(_need().ti_b200_quantize_pack_fused(ptrs, ncols, len(mats), int(interleave), K, qtype, C.byref(h)))
+        self.handle = h.value
+        self.K, self.N, self.qtype = K, sum(m.shape[1] for m in mats), qtype
+
+    def gemv_ex(self, x, epilogue: int = EPI_STORE, resid=None, norm_w=None, eps: float = 1e-5) -> np.ndarray:
+        x = _c(x).ravel()
+        n_out = self.N // 2 if epilogue == EPI_SWIGLU else self.N
+        y = np.empty(n_out, dtype=np.float32)
+        r = _c(resid).ravel() if resid is not None else None
+        nw = _c(norm_w).ravel() if norm_w is not None else None
+        _ck(lib().ti_b200_gemv_q_ex(self.handle, _fp(x), _fp(y), epilogue, _fp(r) if r is not None else C.cast(None, _f),
+                                    _fp(nw) if nw is not None else C.cast(None, _f), eps))
+        return y
+
+
+class KVCache:
+    """Stand-alone paged KV cache (reference KVCache, src/model/inference_engine.cpp:25-172), device resident."""
+
+    def __init__(self, layers: int, heads: int, head_dim: int, max_seq: int, page_tokens: int = 0):
+        h = C.c_uint64()
+        _ck(_need().ti_b200_kv_create(layers, heads, head_dim, max_seq, page_tokens, C.byref(h)))
+        self.handle, self.layers, self.heads, self.head_dim = h.value, layers, heads, head_dim
+
+    def append(self, layer: int, k_new, v_new) -> None:
+        k, v = _c(k_new), _c(v_new)           # [heads, new_tokens, head_dim]
+        _ck(lib().ti_b200_kv_append(self.handle, layer, _fp(k.reshape(-1)), _fp(v.reshape(-1)), k.shape[1]))
+
+    def length(self, layer: int = 0):
+        cur, mx = C.c_int32(), C.c_int32()
+        _ck(lib().ti_b200_kv_length(self.handle, layer, C.byref(cur), C.byref(mx)))
+        return cur.value, mx.value
+
+    def read(self, layer: int):
+        n = self.length(layer)[0]
+        k = np.zeros((self.heads, n, self.head_dim), dtype=np.float32)
+        v = np.zeros_like(k)
+        _ck(lib().ti_b200_kv_read(self.handle, layer, _fp(k.reshape(-1)), _fp(v.reshape(-1))))
+        return k, v
+
+    def attention(self, layer: int, q) -> np.ndarray:
+        q = _c(q).ravel()
+        out = np.empty_like(q)
+        _ck(lib().ti_b200_kv_attention(self.handle, layer, _fp(q), _fp(out)))
+        return out
+
+    def reset(self) -> None:
+        _ck(lib().ti_b200_kv_reset(self.handle))
+
+    def free(self) -> None:
+        if self.handle:
+            _ck(lib().ti_b200_kv_destroy(self.handle))
             self.handle = 0
 
 
@@ -428,6 +504,13 @@ class Model:
         w, k = C.c_double(), C.c_double()
         _ck(lib().ti_b200_model_step_bytes(self.handle, t, C.byref(w), C.byref(k)))
         return w.value, k.value
+
+    def prefill(self, tokens: Sequence[int], want_logits: bool = True):
+        """forward_pass over a prompt (KV cache reset first); logits of the last position."""
+        t = _c(tokens, np.int32)
+        logits = np.empty(self.meta["vocab"], dtype=np.float32) if want_logits else None
+        _ck(lib().ti_b200_prefill(self.handle, t.ctypes.data_as(_i32), t.size, _fp(logits) if want_logits else C.cast(None, _f)))
+        return logits
 
     def decode_step(self, token: int, want_logits: bool = True):
         V = self.meta["vocab"]

@@ -370,6 +370,23 @@ std::mutex g_mu;
 std::vector<std::unique_ptr<QWeight>> g_qweights;
 std::vector<std::unique_ptr<Model>> g_models;
 
+// stand-alone paged KV cache (ti_b200_kv_*): the reference's KVCache (src/model/inference_engine.cpp:25-172) as an object of
+// its own -- per layer two pools [page][page_tokens][heads * head_dim] fp32 and one page table; append is a scatter, the
+// attention reads the pages in place (no copy-out), reset() forgets the lengths
+struct KvCache {
+    int layers = 0, heads = 0, head_dim = 0, max_seq = 0, page_tokens = 64, num_pages = 0;
+    std::vector<DevBuf<float>> k, v;
+    std::vector<int> len;            // tokens cached per layer
+    DevBuf<int> page_table, pos;
+    DevBuf<float> part_o, part_ml;
+    int max_splits = 1;
+};
+std::vector<std::unique_ptr<KvCache>> g_kvs;
+KvCache* get_kv(uint64_t h) {
+    if (h == 0 || h > g_kvs.size()) return nullptr;
+    return g_kvs[h - 1].get();
+}
+
 QWeight* get_qw(ti_qweight_t h) {
     if (h == 0 || h > g_qweights.size()) return nullptr;
     return g_qweights[h - 1].get();
@@ -1555,6 +1572,7 @@ int ti_b200_shutdown(void) {
     cudaStreamSynchronize(g_stream);
     g_models.clear();
     g_qweights.clear();
+    g_kvs.clear();
     if (g_comm) {   // the tensor-parallel group dies with the library state: a fresh init may form a new one
         g_nccl.CommDestroy(g_comm);
         g_comm = nullptr;
@@ -1972,6 +1990,227 @@ int ti_b200_attention_decode(const float* q_host, const float* k_host, const flo
         CK(cudaGetLastError());
     }
     CK(cudaMemcpyAsync(out_host, out.p, B * H * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+static int check_capacity(Model& m, int extra);
+
+// ---- KV cache manager (reference KVCache, src/model/inference_engine.cpp:25-172) --------------------------
+int ti_b200_kv_create(int32_t layers, int32_t heads, int32_t head_dim, int32_t max_seq, int32_t page_tokens, ti_kv_t* out) {
+    TRY(need_init());
+    if (!out || layers <= 0 || heads <= 0 || head_dim <= 0 || max_seq <= 0) return fail("invalid KV cache geometry");
+    if (head_dim % 4 != 0) return fail("attention head dimension %d must be a multiple of 4", head_dim);
+    auto kv = std::make_unique<KvCache>();
+    kv->layers = layers; kv->heads = heads; kv->head_dim = head_dim; kv->max_seq = max_seq;
+    kv->page_tokens = page_tokens > 0 ? page_tokens : 64;
+    kv->num_pages = (max_seq + kv->page_tokens - 1) / kv->page_tokens;
+    const size_t H = (size_t)heads * head_dim;
+    kv->k.resize(layers);
+    kv->v.resize(layers);
+    for (int l = 0; l < layers; ++l) {
+        TRY(kv->k[l].alloc((size_t)kv->num_pages * kv->page_tokens * H));
+        TRY(kv->v[l].alloc((size_t)kv->num_pages * kv->page_tokens * H));
+    }
+    kv->len.assign(layers, 0);
+    std::vector<int> tab(kv->num_pages);
+    for (int i = 0; i < kv->num_pages; ++i) tab[i] = kv->num_pages - 1 - i;   // physical order deliberately not the identity
+    TRY(kv->page_table.alloc(kv->num_pages));
+    CK(cudaMemcpyAsync(kv->page_table.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    TRY(kv->pos.alloc(1));
+    kv->max_splits = std::max(1, std::min((2 * g_num_sms + heads - 1) / heads, 512));
+    TRY(kv->part_o.alloc((size_t)heads * kv->max_splits * head_dim));
+    TRY(kv->part_ml.alloc((size_t)heads * kv->max_splits * 2));
+    CK(cudaStreamSynchronize(g_stream));
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_kvs.push_back(std::move(kv));
+    *out = g_kvs.size();
+    return 0;
+}
+int ti_b200_kv_destroy(ti_kv_t h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (h == 0 || h > g_kvs.size() || !g_kvs[h - 1]) return fail("invalid KV cache handle");
+    cudaStreamSynchronize(g_stream);
+    g_kvs[h - 1].reset();
+    return 0;
+}
+int ti_b200_kv_reset(ti_kv_t h) {   // KVCache::reset (:57-69): length 0; the pages need no clearing, nothing reads beyond the length
+    KvCache* kv = get_kv(h);
+    if (!kv) return fail("invalid KV cache handle");
+    std::fill(kv->len.begin(), kv->len.end(), 0);
+    return 0;
+}
+int ti_b200_kv_length(ti_kv_t h, int32_t layer, int32_t* current_length, int32_t* max_length) {
+    KvCache* kv = get_kv(h);
+    if (!kv) return fail("invalid KV cache handle");
+    if (layer < 0 || layer >= kv->layers) return fail("Layer index out of bounds for KV cache");
+    if (current_length) *current_length = kv->len[layer];
+    if (max_length) *max_length = kv->max_seq;
+    return 0;
+}
+// update_incremental (:78-160): k_new / v_new [heads, new_tokens, head_dim] appended at the layer's current length
+int ti_b200_kv_append(ti_kv_t h, int32_t layer, const float* k_new_host, const float* v_new_host, int32_t new_tokens) {
+    TRY(need_init());
+    KvCache* kv = get_kv(h);
+    if (!kv) return fail("invalid KV cache handle");
+    if (layer < 0 || layer >= kv->layers) return fail("Layer index out of bounds for KV cache");       // :82-84
+    if (new_tokens <= 0) return fail("new_tokens must be >= 1");
+    if (kv->len[layer] + new_tokens > kv->max_seq) return fail("KV cache overflow: sequence too long");   // :100-102
+    const size_t n = (size_t)kv->heads * new_tokens * kv->head_dim;
+    DevBuf<float> kn, vn;
+    TRY(upload(kn, k_new_host, n));
+    TRY(upload(vn, v_new_host, n));
+    kv_append_kernel<<<grid_for(n), 256, 0, g_stream>>>(kn.p, vn.p, kv->heads, new_tokens, kv->head_dim, kv->len[layer], kv->k[layer].p, kv->v[layer].p,
+                                                       kv->page_table.p, kv->page_tokens);
+    ++g_launches;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(g_stream));
+    kv->len[layer] += new_tokens;
+    return 0;
+}
+// the (full_keys, full_values) update_incremental returns (:132-157): [heads, length, head_dim]
+int ti_b200_kv_read(ti_kv_t h, int32_t layer, float* k_out_host, float* v_out_host) {
+    TRY(need_init());
+    KvCache* kv = get_kv(h);
+    if (!kv) return fail("invalid KV cache handle");
+    if (layer < 0 || layer >= kv->layers) return fail("Layer index out of bounds for KV cache");
+    const int len = kv->len[layer];
+    if (len == 0) return 0;
+    const size_t n = (size_t)kv->heads * len * kv->head_dim;
+    DevBuf<float> ko, vo;
+    TRY(ko.alloc(n));
+    TRY(vo.alloc(n));
+    kv_read_kernel<<<grid_for(n), 256, 0, g_stream>>>(kv->k[layer].p, kv->v[layer].p, kv->page_table.p, kv->page_tokens, kv->heads, len, kv->head_dim, ko.p, vo.p);
+    ++g_launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(k_out_host, ko.p, n * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaMemcpyAsync(v_out_host, vo.p, n * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+// attention of one query token over the layer's cached tokens, read in place (flash-decoding, split over the context):
+// multi_head_attention with q_len 1 (tensor_engine.cpp:1149-1252); heads = 1: attention_fast_incremental (:1254-1388)
+int ti_b200_kv_attention(ti_kv_t h, int32_t layer, const float* q_host, float* out_host) {
+    TRY(need_init());
+    KvCache* kv = get_kv(h);
+    if (!kv) return fail("invalid KV cache handle");
+    if (layer < 0 || layer >= kv->layers) return fail("Layer index out of bounds for KV cache");
+    const int len = kv->len[layer];
+    if (len == 0) return fail("Cannot compute attention with empty tensors");
+    const int H = kv->heads * kv->head_dim;
+    DevBuf<float> q, out;
+    TRY(upload(q, q_host, H));
+    TRY(out.alloc(H));
+    CK(cudaMemcpyAsync(kv->pos.p, &len, sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    AttnArgs a{};
+    a.q = q.p;
+    a.k_pool = kv->k[layer].p;
+    a.v_pool = kv->v[layer].p;
+    a.page_table = kv->page_table.p;
+    a.page_tokens = kv->page_tokens;
+    a.page_shift = log2_if_pow2(kv->page_tokens);
+    a.pos_ptr = kv->pos.p;
+    a.t_bias = 0;
+    a.H = H;
+    a.D = kv->head_dim;
+    a.heads = kv->heads;
+    a.max_splits = kv->max_splits;
+    a.min_chunk = 64;
+    a.scale = 1.0f / sqrtf((float)kv->head_dim);
+    a.part_o = kv->part_o.p;
+    a.part_ml = kv->part_ml.p;
+    a.out = out.p;
+    attn_partial_kernel<<<dim3(kv->heads, kv->max_splits), kAttnThreads, sizeof(float) * (size_t)attn_scratch_floats(kv->head_dim, kAttnThreads), g_stream>>>(a);
+    attn_combine_kernel<<<kv->heads, 256, 0, g_stream>>>(a);
+    g_launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_host, out.p, (size_t)H * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+// ---- fused GEMV entry (north_star item 4: RMSNorm prologue, residual / ReLU / SwiGLU epilogues) --------------------------
+int ti_b200_quantize_pack_fused(const float* const* w_host, const size_t* n_cols, int32_t n_src, int32_t interleave, size_t K, int qtype, ti_qweight_t* out) {
+    TRY(need_init());
+    if (n_src < 1 || n_src > 3 || K == 0) return fail("1 to 3 source matrices with K >= 1 rows");
+    if (interleave && n_src != 2) return fail("interleaving takes exactly two sources (gate, up)");
+    if (qtype != TI_Q_INT8 && qtype != TI_Q_INT4) return fail("Unsupported quantization type");
+    DevBuf<float> w[3];
+    const float* src[3] = {nullptr, nullptr, nullptr};
+    int n[3] = {0, 0, 0};
+    for (int i = 0; i < n_src; ++i) {
+        if (n_cols[i] == 0) return fail("Cannot quantize an empty tensor");
+        if (interleave && n_cols[i] != n_cols[0]) return fail("interleaved sources need equal widths");
+        TRY(upload(w[i], w_host[i], K * n_cols[i]));
+        src[i] = w[i].p;
+        n[i] = (int)n_cols[i];
+    }
+    std::unique_ptr<QWeight> q;
+    TRY(build_qweight(src, n, n_src, interleave ? 1 : 0, (int)K, qtype, 1, false, &q));
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_qweights.push_back(std::move(q));
+    *out = g_qweights.size();
+    return 0;
+}
+// y = epilogue(dequant(W)^T . prologue(x)): norm_w_host != NULL fuses rms_norm(x, norm_w, eps) in front (:1452-1508);
+// epilogue TI_EPI_STORE / TI_EPI_RESIDUAL (y += resid, :1626) / TI_EPI_SWIGLU (interleaved gate/up weight: y[i] = up_i * silu(gate_i),
+// N / 2 outputs, :900-923 + :1680) / TI_EPI_RELU (:828)
+int ti_b200_gemv_q_ex(ti_qweight_t h, const float* x_host, float* y_host, int32_t epilogue, const float* resid_host, const float* norm_w_host, float eps) {
+    TRY(need_init());
+    QWeight* w = get_qw(h);
+    if (!w) return fail("invalid qweight handle");
+    if (epilogue != EPI_STORE && epilogue != EPI_RESIDUAL && epilogue != EPI_SWIGLU && epilogue != EPI_RELU) return fail("unsupported epilogue %d", epilogue);
+    if (epilogue == EPI_RESIDUAL && !resid_host) return fail("the residual epilogue needs a residual vector");
+    if (epilogue == EPI_SWIGLU && (w->L.N & 1)) return fail("the SwiGLU epilogue needs an interleaved (gate, up) weight with an even number of columns");
+    const size_t K = w->L.K, N = w->L.N, n_out = epilogue == EPI_SWIGLU ? N / 2 : N;
+    DevBuf<float> x, y, r, nw;
+    TRY(upload(x, x_host, K));
+    TRY(y.alloc(n_out));
+    if (resid_host) TRY(upload(r, resid_host, N));
+    if (norm_w_host) TRY(upload(nw, norm_w_host, K));
+    GemvArgs a{};
+    a.x = x.p;
+    a.norm_w = norm_w_host ? nw.p : nullptr;
+    a.rms_eps = eps;
+    a.epi = epilogue;
+    a.out = y.p;
+    a.resid = r.p;
+    TRY(launch_gemv(*w, a, g_stream));
+    CK(cudaMemcpyAsync(y_host, y.p, n_out * 4, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+// forward_pass (:1429-1491) over a prompt: resets the model's KV cache, fills it with the n tokens (tensor-core GEMM path for
+// long prompts) and returns the logits of the last position (optional)
+int ti_b200_prefill(ti_model_t h, const int32_t* tokens, int32_t n, float* last_logits_host) {
+    TRY(need_init());
+    Model* mp = get_model(h);
+    if (!mp || !mp->finalized) return fail("invalid or unfinalized model handle");
+    Model& m = *mp;
+    if (m.cfg.compat_literal) return fail("ti_b200_prefill is not available on the literal benchmark path");
+    if (n <= 0) return fail("Input tokens cannot be empty");
+    for (int i = 0; i < n; ++i)
+        if (tokens[i] < 0 || tokens[i] >= m.cfg.vocab) return fail("token id %d out of range", tokens[i]);
+    TRY(ti_b200_model_reset(h));
+    TRY(check_capacity(m, n));
+    if ((int)m.prompt.n < n) TRY(m.prompt.alloc(n));
+    CK(cudaMemcpyAsync(m.prompt.p, tokens, n * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    StepIO io{};
+    CK(cudaMemcpyAsync(m.io.p, &io, sizeof(io), cudaMemcpyHostToDevice, g_stream));
+    TRY(prompt_pass(m, tokens, n));
+    m.host_pos = n;
+    if (last_logits_host) {
+        const size_t V = m.cfg.vocab;
+        if (m.lm_sharded) {
+            if (m.hist.n < V) TRY(m.hist.alloc(V));
+            CK(cudaMemcpyAsync(m.hist.p, m.logits.p, V * 4, cudaMemcpyDeviceToDevice, g_stream));
+            TRY(gather_sharded_logits(m, m.hist.p, V));
+            CK(cudaMemcpyAsync(last_logits_host, m.hist.p, V * 4, cudaMemcpyDeviceToHost, g_stream));
+        } else {
+            CK(cudaMemcpyAsync(last_logits_host, m.logits.p, V * 4, cudaMemcpyDeviceToHost, g_stream));
+        }
+    }
     CK(cudaStreamSynchronize(g_stream));
     return 0;
 }

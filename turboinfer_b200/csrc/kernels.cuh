@@ -353,6 +353,36 @@ __device__ __forceinline__ void attn_split_range(int t, int max_splits, int min_
     chunk = (t + nsplit - 1) / nsplit;
 }
 
+// KVCache::update_incremental (inference_engine.cpp:78-160) on the paged pools: new keys / values arrive in the reference's
+// [heads, new_tokens, head_dim] order and are appended at token positions pos0 .. pos0 + new_tokens - 1 (one pool row per
+// token, heads side by side: the layout the attention kernels read)
+__global__ void kv_append_kernel(const float* k_new, const float* v_new, int heads, int new_tokens, int head_dim, int pos0, float* k_pool,
+                                 float* v_pool, const int* page_table, int page_tokens) {
+    const int H = heads * head_dim;
+    const size_t n = (size_t)new_tokens * H;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i / H), c = (int)(i - (size_t)t * H), h = c / head_dim, d = c - h * head_dim;
+        const size_t src = ((size_t)h * new_tokens + t) * head_dim + d;
+        const int pos = pos0 + t;
+        const size_t dst = ((size_t)page_table[pos / page_tokens] * page_tokens + (pos % page_tokens)) * H + c;
+        k_pool[dst] = k_new[src];
+        v_pool[dst] = v_new[src];
+    }
+}
+// the copy-out of update_incremental (:132-157): the first `len` tokens as [heads, len, head_dim]
+__global__ void kv_read_kernel(const float* k_pool, const float* v_pool, const int* page_table, int page_tokens, int heads, int len, int head_dim,
+                               float* k_out, float* v_out) {
+    const int H = heads * head_dim;
+    const size_t n = (size_t)len * H;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i / H), c = (int)(i - (size_t)t * H), h = c / head_dim, d = c - h * head_dim;
+        const size_t src = ((size_t)page_table[t / page_tokens] * page_tokens + (t % page_tokens)) * H + c;
+        const size_t dst = ((size_t)h * len + t) * head_dim + d;
+        k_out[dst] = k_pool[src];
+        v_out[dst] = v_pool[src];
+    }
+}
+
 // (attn_partial_kernel / attn_combine_kernel are defined in mega.cuh on top of attn_item / attn_merge_head)
 
 // ---------------------------------------------------------------------------------------------------
