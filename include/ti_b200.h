@@ -224,6 +224,12 @@ int ti_b200_generate_sampled(ti_model_t m, const int32_t* prompt, int32_t n_prom
                              int32_t* n_out, float* logprobs_out, float* decode_ms);
 int ti_b200_compute_logprobs(ti_model_t m, const int32_t* tokens, int32_t n, float* out);
 
+/* the same for prompts of DIFFERENT lengths: prompts [batch][max_len] (row b: lens[b] tokens, the rest ignored).  Sequences are
+ * left-aligned and advance in lockstep; one whose prompt has ended feeds its own picks while longer prompts are still being
+ * read, so every sequence produces exactly what generate() would for it alone. */
+int ti_b200_generate_batch_ragged(ti_model_t m, const int32_t* prompts, const int32_t* lens, int32_t batch, int32_t max_len,
+                                  int32_t n_new, int32_t* out_tokens, float* decode_ms);
+
 /* CUDA-event time of the prompt phase (prefill) of the last ti_b200_generate_greedy call on this model, in ms */
 int ti_b200_model_last_prefill_ms(ti_model_t m, float* ms);
 

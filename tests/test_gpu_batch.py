@@ -72,3 +72,30 @@ def test_generate_batch_survives_scratch_reallocation(tb):
     finally:
         m.free()
     assert np.array_equal(first, again)
+
+
+@pytest.mark.parametrize("qt", [oracle.QINT8, oracle.QINT4])
+def test_generate_batch_ragged_prompts(tb, port, qt):
+    """Prompts of different lengths (the reference's generate_batch loops over generate(), :804-828, so any lengths go):
+    left-aligned lockstep on the device; every sequence's tokens equal the single-sequence engine's and the oracle's."""
+    meta = SHAPES["bench-small"]
+    w = make_model(meta, norm_jitter=0.1)
+    lens = [3, 9, 1, 40, 6, 17]          # 40 > 32: that sequence alone would take the tensor-core prefill; here all go step by step
+    prompts = [prompt_tokens(n, meta["vocab"], offset=5 * b) for b, n in enumerate(lens)]
+    n_new = 7
+    m = tb.Model(meta, qt, attn_mode=1, rope_mode=1, max_seq=128).load(w)
+    try:
+        toks, _ = m.generate_batch_ragged(prompts, n_new)
+        toks2, _ = m.generate_batch_ragged(prompts, n_new)        # graph replay
+        singles = [m.generate_greedy(p, n_new)[0] for p in prompts]
+        eq, _, _ = m.generate_batch_greedy(np.array([prompts[1], prompts[1]], dtype=np.int32), n_new)   # the equal-length entry still works
+    finally:
+        m.free()
+    assert np.array_equal(toks, toks2)
+    for b in range(len(lens)):
+        assert np.array_equal(toks[b], singles[b]), (b, toks[b], singles[b])
+    assert np.array_equal(eq[0], singles[1]) and np.array_equal(eq[1], singles[1])
+    fq = fake_quant_model(port, w, qt)
+    for b in (0, 3):
+        rt, _ = port.decode_greedy(fq, meta, prompts[b], n_new, attn_mode=1, rope_mode=1)
+        assert np.array_equal(toks[b], rt)

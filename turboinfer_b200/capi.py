@@ -87,6 +87,7 @@ SYMBOLS = {
     "ti_b200_sample_logits": (C.c_int, [_f, C.c_size_t, C.c_size_t, C.c_float, C.c_int32, C.c_float, C.c_uint64, C.c_int32, _i32, _f]),
     "ti_b200_generate_sampled": (C.c_int, [C.c_uint64, _i32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_uint64, C.c_int32, _i32, _i32, _f, _f]),
     "ti_b200_compute_logprobs": (C.c_int, [C.c_uint64, _i32, C.c_int32, _f]),
+    "ti_b200_generate_batch_ragged": (C.c_int, [C.c_uint64, _i32, _i32, C.c_int32, C.c_int32, C.c_int32, _i32, _f]),
     "ti_b200_model_last_prefill_ms": (C.c_int, [C.c_uint64, _f]),
     "ti_b200_launch_count": (C.c_int, [C.POINTER(C.c_uint64)]),
     "ti_b200_bench_gemv": (C.c_int, [C.POINTER(C.c_uint64), C.c_size_t, C.c_size_t, _f]),
@@ -558,6 +559,19 @@ class Model:
         _ck(lib().ti_b200_generate_batch_greedy(self.handle, p.ctypes.data_as(_i32), B, n_prompt, n_new, out.ctypes.data_as(_i32),
                                                 _fp(logits) if want_logits else C.cast(None, _f), C.byref(ms)))
         return out, logits, ms.value
+
+    def generate_batch_ragged(self, prompts, n_new: int):
+        """generate_batch for prompts of different lengths (list of token lists) -> tokens [B][n_new], decode ms."""
+        lens = np.array([len(p) for p in prompts], dtype=np.int32)
+        B, mx = len(prompts), int(lens.max())
+        flat = np.zeros((B, mx), dtype=np.int32)
+        for b, p in enumerate(prompts):
+            flat[b, : len(p)] = p
+        out = np.zeros((B, n_new), dtype=np.int32)
+        ms = C.c_float()
+        _ck(lib().ti_b200_generate_batch_ragged(self.handle, flat.ctypes.data_as(_i32), lens.ctypes.data_as(_i32), B, mx, n_new,
+                                                out.ctypes.data_as(_i32), C.byref(ms)))
+        return out, ms.value
 
     def free(self) -> None:
         if self.handle:

@@ -133,8 +133,11 @@ __global__ void __launch_bounds__(kDigitsThreads) rmsnorm_digits_small_kernel(co
 
 // One block per row: the FIRST maximum of logits[b][0..V) (std::sort descending + [0] of the reference keeps the first of
 // equal values only by accident of its sort; the oracle and every engine here define greedy as "first maximum").
-// tokens[b] feeds the next step's embedding lookup; out[b * out_stride + *step_ptr] is the history the host reads.
-__global__ void argmax_rows_kernel(const float* logits, int V, int* tokens, int* out, int out_stride, const int* step_ptr) {
+// tokens[b] feeds the next step's embedding lookup.  Ragged batches: sequence b's prompt has lens[b] tokens, all sequences
+// are left-aligned and advance in lockstep, so at step s (= tokens already in every cache, *pos_ptr) sequence b has produced
+// its output number s - (lens[b] - 1): that is the column of out[b][...] the pick goes to (nothing is written before the
+// sequence's prompt has ended or after its n_new-th token).
+__global__ void argmax_rows_kernel(const float* logits, int V, int* tokens, int* out, int out_stride, const int* pos_ptr, const int* lens) {
     __shared__ unsigned long long best[32];
     const int b = blockIdx.x;
     const float* row = logits + (size_t)b * V;
@@ -156,10 +159,19 @@ __global__ void argmax_rows_kernel(const float* logits, int V, int* tokens, int*
         for (int i = 1; i < (int)(blockDim.x >> 5); ++i) key = best[i] > key ? best[i] : key;
         int tok = key == 0ull ? 0 : 0x7FFFFFFF - (int)(uint32_t)(key & 0xFFFFFFFFull);
         tok = min(max(tok, 0), V - 1);
-        tokens[b] = tok;
-        const int step = *step_ptr;
-        if (out && step < out_stride) out[(size_t)b * out_stride + step] = tok;
+        const int s = *pos_ptr, col = s - (lens[b] - 1);
+        if (col >= 0) tokens[b] = tok;   // still inside the prompt: the next token comes from the prompt (batch_feed_kernel)
+        if (out && col >= 0 && col < out_stride) out[(size_t)b * out_stride + col] = tok;
     }
+}
+
+// start of a batched step: sequence b is fed its prompt token of this position while its prompt lasts, its own last pick after
+// that (prompts: [max_len][B], column b = sequence b, padded)
+__global__ void batch_feed_kernel(const int* prompts, const int* lens, const int* pos_ptr, int B, int* tokens) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int s = *pos_ptr;
+    if (s < lens[b]) tokens[b] = prompts[(size_t)s * B + b];
 }
 
 // end of a batched step: every sequence is one token longer; `sampled` steps also advance the output column

@@ -286,7 +286,8 @@ struct BatchState {
     std::vector<DevBuf<float>> k, v;     // per layer: [B * pages_per_seq][page_tokens][H]
     DevBuf<int> tables;                  // [B][pages_per_seq] physical page of each logical page
     DevBuf<int> tokens;                  // [B] tokens of the current step
-    DevBuf<int> prompts;                 // [n_prompt][B] (column p = the tokens of prompt step p)
+    DevBuf<int> prompts;                 // [max prompt length][B] (row p = the tokens of prompt position p, padded)
+    DevBuf<int> lens;                    // [B] prompt length of every sequence
     DevBuf<int> out;                     // [B][n_new]
     DevBuf<int> pos_step;                // [0] tokens in every cache, [1] output column
     DevBuf<float> part_o, part_ml, logits;
@@ -1261,8 +1262,9 @@ int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
     const int m_pad = (B + kGemmBM - 1) / kGemmBM * kGemmBM;
     const int rope_dim = m.cfg.rope_mode == 1 ? H / m.cfg.heads : 0;
     const bool tp = m.tp > 1;
+    batch_feed_kernel<<<(B + 127) / 128, 128, 0, g_stream>>>(bs.prompts.p, bs.lens.p, bs.pos_step.p, B, bs.tokens.p);
     embed_rows_kernel<<<B, 256, 0, g_stream>>>(m.tok_emb.p, bs.tokens.p, m.pf_x.p, H);
-    ++g_launches;
+    g_launches += 2;
     for (size_t l = 0; l < m.layers.size(); ++l) {
         Layer& ly = m.layers[l];
         const int Il = ly.down->L.K;   // this rank's share of the intermediate width
@@ -1322,7 +1324,7 @@ int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
     if (sample) {
         TRY(batch_digits(m, m.pf_x.p, nullptr, m.out_norm.p, B, H, m_pad, m.lm_head->k_pad));
         TRY(pf_gemm(m, *m.lm_head, B, m_pad, bs.logits.p, nullptr));
-        argmax_rows_kernel<<<B, 1024, 0, g_stream>>>(bs.logits.p, V, bs.tokens.p, bs.out.p, out_stride, bs.pos_step.p + 1);
+        argmax_rows_kernel<<<B, 1024, 0, g_stream>>>(bs.logits.p, V, bs.tokens.p, bs.out.p, out_stride, bs.pos_step.p, bs.lens.p);
         ++g_launches;
     }
     batch_advance_kernel<<<1, 1, 0, g_stream>>>(bs.pos_step.p, sample ? 1 : 0);
@@ -2542,20 +2544,25 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
 // tokens each.  The reference loops over generate(); here the sequences advance in lockstep so that the weights are read
 // once per step for all of them (tensor-core GEMM path).  out_tokens: [batch][n_new]; logits_last (optional): [batch][vocab]
 // of the last step; decode_ms (optional): CUDA-event time of the n_new - 1 decode steps after the prompt.
-int ti_b200_generate_batch_greedy(ti_model_t h, const int32_t* prompts, int32_t batch, int32_t n_prompt, int32_t n_new, int32_t* out_tokens,
-                                  float* logits_last, float* decode_ms) {
+static int generate_batch_impl(ti_model_t h, const int32_t* prompts, const int32_t* lens, int32_t batch, int32_t max_len, int32_t n_new,
+                               int32_t* out_tokens, float* logits_last, float* decode_ms) {
     TRY(need_init());
     Model* mp = get_model(h);
     if (!mp || !mp->finalized) return fail("invalid or unfinalized model handle");
     Model& m = *mp;
     if (batch <= 0) return fail("batch must be >= 1");
-    if (n_prompt <= 0) return fail("Input tokens cannot be empty");  // validate_input_tokens (:1409)
+    if (max_len <= 0) return fail("Input tokens cannot be empty");  // validate_input_tokens (:1409)
     if (n_new <= 0) return fail("n_new must be >= 1");
     if (!batch_eligible(m)) return fail("generate_batch needs a complete, non-literal model (q/k/v/o, up/down, lm_head; rope per head or off)");
     const int B = batch, V = m.cfg.vocab, H = m.cfg.hidden;
-    for (int i = 0; i < B * n_prompt; ++i)
-        if (prompts[i] < 0 || prompts[i] >= V) return fail("token id %d out of range", prompts[i]);
-    const int total = n_prompt + n_new - 1;
+    int min_len = max_len;
+    for (int b = 0; b < B; ++b) {
+        if (lens[b] <= 0 || lens[b] > max_len) return fail("Input tokens cannot be empty");
+        min_len = std::min(min_len, (int)lens[b]);
+        for (int p = 0; p < lens[b]; ++p)
+            if (prompts[(size_t)b * max_len + p] < 0 || prompts[(size_t)b * max_len + p] >= V) return fail("token id %d out of range", prompts[(size_t)b * max_len + p]);
+    }
+    const int total = max_len + n_new - 1;   // the longest prompt decides how many lockstep steps run
     if (total > m.cfg.max_seq) return fail("KV cache overflow: sequence too long");  // :100-102
     if (!g_batch_carveout_done) {
         // every kernel of the step asks for the same L1 / shared-memory split as the GEMM (which needs nearly all of it):
@@ -2563,7 +2570,7 @@ int ti_b200_generate_batch_greedy(ti_model_t h, const int32_t* prompts, int32_t 
         const void* fns[] = {(const void*)gemm_i8_tc_small_kernel, (const void*)gemm_i8_tc_kernel, (const void*)rmsnorm_digits_small_kernel,
                              (const void*)rmsnorm_digits_kernel, (const void*)rope_kv_batch_kernel, (const void*)attn_partial_kernel,
                              (const void*)attn_combine_kernel, (const void*)argmax_rows_kernel, (const void*)batch_advance_kernel,
-                             (const void*)embed_rows_kernel, (const void*)swiglu_rows_kernel, (const void*)relu_rows_kernel};
+                             (const void*)embed_rows_kernel, (const void*)swiglu_rows_kernel, (const void*)relu_rows_kernel, (const void*)batch_feed_kernel};
         for (const void* f : fns) CK(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         g_batch_carveout_done = true;
     }
@@ -2591,27 +2598,34 @@ int ti_b200_generate_batch_greedy(ti_model_t h, const int32_t* prompts, int32_t 
         CK(cudaMemcpyAsync(bs.tables.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, g_stream));
         CK(cudaStreamSynchronize(g_stream));
         TRY(bs.tokens.alloc(B));
+        TRY(bs.lens.alloc(B));
         TRY(bs.pos_step.alloc(2));
         TRY(bs.part_o.alloc((size_t)B * m.attn_heads * bs.max_splits * m.attn_dim));
         TRY(bs.part_ml.alloc((size_t)B * m.attn_heads * bs.max_splits * 2));
         TRY(bs.logits.alloc((size_t)B * V));
     }
     BatchState& bs = *m.batch;
+    bool regraph = false;
     if (bs.out.n < (size_t)B * n_new) {
         TRY(bs.out.alloc((size_t)B * n_new));
-        bs.drop_graphs();   // the graphs hold the old pointer
+        regraph = true;   // the graphs hold the old pointer
     }
-    if (bs.cap_scratch != m.pf_gen || bs.cap_stride != n_new) {   // kernel parameters of the captured graphs
+    std::vector<int> cols((size_t)max_len * B, 0);
+    for (int b = 0; b < B; ++b)
+        for (int p = 0; p < lens[b]; ++p) cols[(size_t)p * B + b] = prompts[(size_t)b * max_len + p];
+    if (bs.prompts.n < cols.size()) {
+        TRY(bs.prompts.alloc(cols.size()));
+        regraph = true;
+    }
+    if (regraph || bs.cap_scratch != m.pf_gen || bs.cap_stride != n_new) {   // kernel parameters of the captured graphs
         bs.drop_graphs();
         bs.cap_scratch = m.pf_gen;
         bs.cap_stride = n_new;
     }
-    std::vector<int> cols((size_t)n_prompt * B);
-    for (int b = 0; b < B; ++b)
-        for (int p = 0; p < n_prompt; ++p) cols[(size_t)p * B + b] = prompts[(size_t)b * n_prompt + p];
-    if (bs.prompts.n < cols.size()) TRY(bs.prompts.alloc(cols.size()));
     CK(cudaMemcpyAsync(bs.prompts.p, cols.data(), cols.size() * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpyAsync(bs.lens.p, lens, B * sizeof(int), cudaMemcpyHostToDevice, g_stream));
     CK(cudaMemsetAsync(bs.pos_step.p, 0, 2 * sizeof(int), g_stream));   // reset(): every cache is empty again
+    CK(cudaMemsetAsync(bs.out.p, 0, (size_t)B * n_new * sizeof(int), g_stream));
     auto run = [&](bool sample) -> int {
         cudaGraphExec_t& ge = bs.graph[sample ? 1 : 0];
         if (!ge) {
@@ -2630,10 +2644,8 @@ int ti_b200_generate_batch_greedy(ti_model_t h, const int32_t* prompts, int32_t 
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    for (int p = 0; p < n_prompt; ++p) {
-        CK(cudaMemcpyAsync(bs.tokens.p, bs.prompts.p + (size_t)p * B, B * sizeof(int), cudaMemcpyDeviceToDevice, g_stream));
-        TRY(run(p == n_prompt - 1));
-    }
+    // steps 0 .. min_len - 2 are prompt-only for every sequence (no lm_head); from step min_len - 1 on some sequence samples
+    for (int s = 0; s < max_len; ++s) TRY(run(s >= min_len - 1));
     CK(cudaEventRecord(e0, g_stream));
     for (int i = 1; i < n_new; ++i) TRY(run(true));
     CK(cudaEventRecord(e1, g_stream));
@@ -2648,7 +2660,23 @@ int ti_b200_generate_batch_greedy(ti_model_t h, const int32_t* prompts, int32_t 
     return 0;
 }
 
-// sample_next_token on host logits (op-level entry, tests): rows independent rows of `vocab` logits
+int ti_b200_generate_batch_greedy(ti_model_t h, const int32_t* prompts, int32_t batch, int32_t n_prompt, int32_t n_new, int32_t* out_tokens,
+                                  float* logits_last, float* decode_ms) {
+    if (batch <= 0) return fail("batch must be >= 1");
+    std::vector<int32_t> lens(batch, n_prompt);
+    return generate_batch_impl(h, prompts, lens.data(), batch, n_prompt, n_new, out_tokens, logits_last, decode_ms);
+}
+
+// generate_batch with prompts of DIFFERENT lengths (the reference loops over generate(), :804-828, so any lengths go): prompts is
+// [batch][max_len] (row b holds lens[b] tokens, the rest is ignored).  The sequences are left-aligned and advance in lockstep;
+// a sequence whose prompt has ended feeds its own picks while longer prompts are still being read.  out_tokens [batch][n_new].
+// (logits_last of the equal-length entry has no ragged counterpart: the sequences' last steps differ.)
+int ti_b200_generate_batch_ragged(ti_model_t h, const int32_t* prompts, const int32_t* lens, int32_t batch, int32_t max_len, int32_t n_new,
+                                  int32_t* out_tokens, float* decode_ms) {
+    if (batch <= 0 || !lens) return fail("batch must be >= 1");
+    return generate_batch_impl(h, prompts, lens, batch, max_len, n_new, out_tokens, nullptr, decode_ms);
+}
+
 int ti_b200_sample_logits(const float* logits_host, size_t rows, size_t vocab, float temperature, int32_t top_k, float top_p, uint64_t seed,
                           int32_t step, int32_t* tokens_out, float* logprobs_out) {
     TRY(need_init());

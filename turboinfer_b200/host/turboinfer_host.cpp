@@ -524,21 +524,25 @@ std::vector<GenerationResult> InferenceEngine::generate_batch(const std::vector<
     if (batch.empty()) throw std::runtime_error("Batch size cannot be zero");
     if (batch.size() > config_.max_batch_size) throw std::runtime_error("Batch size exceeds maximum allowed batch size");
     std::vector<GenerationResult> out;
-    // Greedy, equal-length prompts, no log-probabilities: the sequences advance in lockstep on the device, the weights
+    // Greedy, no log-probabilities (prompts of any lengths): the sequences advance in lockstep on the device, the weights
     // are read once per step for the whole batch (ti_b200_generate_batch_greedy).  Tokens after a sequence's first EOS
     // are dropped here, which is where the reference's per-sequence loop would have stopped (:760).
     bool lockstep = config_.top_k == 1 && !include_logprobs && batch.size() > 1 && max_new_tokens > 0;
+    size_t P = 0;
     for (const auto& tokens : batch) {
         validate_input_tokens(tokens);
-        lockstep = lockstep && tokens.size() == batch[0].size();
+        P = std::max(P, tokens.size());   // prompts may differ in length: the sequences are left-aligned on the device
     }
-    lockstep = lockstep && batch[0].size() + max_new_tokens - 1 <= config_.max_sequence_length;
+    lockstep = lockstep && P + max_new_tokens - 1 <= config_.max_sequence_length;
     if (lockstep) {
         const auto t0 = std::chrono::high_resolution_clock::now();
-        const size_t B = batch.size(), P = batch[0].size();
-        std::vector<int32_t> prompts(B * P), toks(B * max_new_tokens);
-        for (size_t b = 0; b < B; ++b) std::copy(batch[b].begin(), batch[b].end(), prompts.begin() + b * P);
-        const int rc = ti_b200_generate_batch_greedy(handle_, prompts.data(), (int32_t)B, (int32_t)P, (int32_t)max_new_tokens, toks.data(), nullptr, nullptr);
+        const size_t B = batch.size();
+        std::vector<int32_t> prompts(B * P, 0), lens(B), toks(B * max_new_tokens);
+        for (size_t b = 0; b < B; ++b) {
+            std::copy(batch[b].begin(), batch[b].end(), prompts.begin() + b * P);
+            lens[b] = (int32_t)batch[b].size();
+        }
+        const int rc = ti_b200_generate_batch_ragged(handle_, prompts.data(), lens.data(), (int32_t)B, (int32_t)P, (int32_t)max_new_tokens, toks.data(), nullptr);
         if (rc == 0) {
             const auto t1 = std::chrono::high_resolution_clock::now();
             const float ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
@@ -552,7 +556,7 @@ std::vector<GenerationResult> InferenceEngine::generate_batch(const std::vector<
                 if (!r.finished && r.tokens.size() >= config_.max_sequence_length) { r.finished = true; r.stop_reason = "max_length"; }
                 if (!r.finished) r.stop_reason = "max_new_tokens";
                 r.total_time_ms = ms;
-                const size_t generated = r.tokens.size() - P;
+                const size_t generated = r.tokens.size() - batch[b].size();
                 r.tokens_per_second = ms > 0.f ? generated / (ms / 1000.0f) : 0.f;
                 stats_->generations++;
                 stats_->tokens += generated;
