@@ -241,8 +241,29 @@ static void test_engine_gpu() {
         cfg.top_k = 5;
         cfg.temperature = 0.8f;
         eng.set_config(cfg);
-        model::GenerationResult smp = eng.generate(prompt, 6, true);       // host-side sampling path
+        model::GenerationResult smp = eng.generate(prompt, 6, true);       // on-device sampler (temperature, top-k, top-p)
         CHECK(smp.tokens.size() > prompt.size() && smp.logprobs.size() == smp.tokens.size() - prompt.size());
+        for (float lp : smp.logprobs) CHECK(lp <= 0.f);
+        {   // a seeded sampler reproduces its generation; compute_logprobs scores a sequence position by position
+            model::InferenceEngine e1(small_model(quant), cfg), e2(small_model(quant), cfg);
+            e1.set_seed(99);
+            e2.set_seed(99);
+            CHECK(e1.generate(prompt, 10).tokens == e2.generate(prompt, 10).tokens);
+            std::vector<float> lps = e1.compute_logprobs(prompt);
+            CHECK(lps.size() == prompt.size());
+            for (float lp : lps) CHECK(lp <= 0.f && lp > -30.f);
+            std::vector<int> bad_tok = prompt;
+            bad_tok[1] = 1000000;                                          // out of vocabulary: the reference's -20 sentinel (:933-936)
+            CHECK(e1.compute_logprobs(bad_tok)[1] == -20.0f);
+        }
+        cfg.top_k = 1;
+        eng.set_config(cfg);
+        {   // greedy batches with prompts of DIFFERENT lengths also run in lockstep on the device
+            const std::vector<std::vector<int>> ragged = {prompt, {3, 4}, {9, 8, 7, 6, 5, 4, 3}};
+            auto rb = eng.generate_batch(ragged, 4);
+            CHECK(rb.size() == 3);
+            for (size_t b = 0; b < ragged.size(); ++b) CHECK(rb[b].tokens == eng.generate(ragged[b], 4).tokens);
+        }
         auto batch = eng.generate_batch({prompt, {3, 4}}, 3);
         CHECK(batch.size() == 2);
         CHECK(eng.memory_usage() > 0 && !eng.performance_stats().empty());

@@ -92,7 +92,7 @@ constexpr int kMaxSmemPages = 1024;   // 64 k tokens at 64 tokens per page; long
 
 TIB_HD size_t mega_smem_bytes(int stages, int max_kpad, int max_units, int attn_floats, int kv_pages = 0) {
     const size_t table = kv_pages <= kMaxSmemPages ? (((size_t)kv_pages * 4 + 15) & ~size_t(15)) : 0;
-    return gemv_smem_bytes_for(stages, max_kpad, max_units) + 16 + (size_t)attn_floats * 4 + 16 + 2 * ((sizeof(MegaPhase) + 15) & ~size_t(15)) + table;
+    return gemv_smem_bytes_for(stages, max_kpad, max_units) + 16 + (size_t)attn_floats * 4 + 16 + 3 * ((sizeof(MegaPhase) + 15) & ~size_t(15)) + table;
 }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -670,12 +670,14 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
     const GemvSmem sm = gemv_carve_for(smem_raw, m.stages, m.max_kpad, m.max_units, &tail);
     float* attn_sm = reinterpret_cast<float*>(tail);
     uint8_t* const ptail = tail + (((size_t)m.attn_floats * 4 + 15) & ~size_t(15));
-    // the phase descriptors, staged by the consumers; two slots: a warp may already stage the next phase's while another
-    // still reads this phase's in its epilogue (nobody is more than one barrier ahead)
-    MegaPhase* const sph0 = reinterpret_cast<MegaPhase*>(ptail);
-    MegaPhase* const sph1 = reinterpret_cast<MegaPhase*>(ptail + ((sizeof(MegaPhase) + 15) & ~size_t(15)));
+    // the phase descriptors, staged by the consumers ONE PHASE AHEAD (three slots): while a phase runs out of slot i, the next
+    // one is copied into slot i + 1 before the grid barrier, so that a phase's own header -- slab geometry, epilogue constants,
+    // norm weights, all of it on the barrier's critical path -- reads its descriptor from shared memory instead of starting
+    // with a chain of global loads; slot i + 2 may still be read by a warp finishing the previous phase's epilogue
+    constexpr size_t kPhaseSlot = (sizeof(MegaPhase) + 15) & ~size_t(15);
+    uint8_t* const sph_base = ptail;
     // the KV page table of the sequence, copied once: a page lookup in the attention phase is then an LDS
-    int* const spt = (m.kv_pages > 0 && m.kv_pages <= kMaxSmemPages) ? reinterpret_cast<int*>(ptail + 2 * ((sizeof(MegaPhase) + 15) & ~size_t(15))) : nullptr;
+    int* const spt = (m.kv_pages > 0 && m.kv_pages <= kMaxSmemPages) ? reinterpret_cast<int*>(ptail + 3 * kPhaseSlot) : nullptr;
     if (tid == 0) gemv_init_barriers(sm, m.stages);
     __syncthreads();
 
@@ -854,6 +856,13 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
     };
 
     unsigned int phase_seq = 0;   // phases executed so far: selects the descriptor slot
+    auto stage_descriptor = [&](int ph, unsigned int slot) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(m.phases + ph);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(sph_base + (size_t)slot * kPhaseSlot);
+        for (int i = tid; i < (int)(sizeof(MegaPhase) / 4); i += kConsumerThreads) dst[i] = src[i];
+    };
+    stage_descriptor(0, 0);   // the first phase's descriptor; every later one is staged during its predecessor
+    bar_sync(1, kConsumerThreads);
     unsigned int ex_seq = (m.tp > 1 && m.tp_p2p) ? *m.mg_seq : 0u;   // point-to-point exchanges since the group was formed
     int token = m.st->token;  // decode-only launches continue from the token the previous launch picked
     for (int s = 0; s < m.n_steps; ++s) {
@@ -876,17 +885,15 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
             if (stamp) ts[0] = clock64();
             // Everything that does not depend on the previous phase's output happens BEFORE the grid barrier:
             // stage the phase descriptor in shared memory, fetch the epilogue's per-column constants.
-            const MegaPhase& PG = m.phases[ph];
-            // the NEXT phase's descriptor: pull it into L1 now, so that its header does not start with a round trip to L2
-            if (tid * 128 < (int)sizeof(MegaPhase) && !(m.dbg_flags & 2)) {
-                const int nx = ph + 1 < m.nphases ? ph + 1 : 0;
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(m.phases + nx) + tid * 128));
-            }
-            MegaPhase* const sph = (phase_seq++ & 1u) ? sph1 : sph0;
-            {
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(&PG);
-                uint32_t* dst = reinterpret_cast<uint32_t*>(sph);
-                for (int i = tid; i < (int)(sizeof(MegaPhase) / 4); i += kConsumerThreads) dst[i] = src[i];
+            const unsigned int slot = phase_seq % 3u;
+            ++phase_seq;
+            MegaPhase* const sph = reinterpret_cast<MegaPhase*>(sph_base + (size_t)slot * kPhaseSlot);
+            const MegaPhase& PG = *sph;   // staged during the previous phase (or before the loop)
+            {   // the phase that will execute next (the head phases only on sampling steps; after the last one: phase 0 of the next step)
+                int nx = ph + 1;
+                if (nx >= m.nphases - m.n_head && !sample) nx = m.nphases;
+                if (nx >= m.nphases) nx = 0;
+                stage_descriptor(nx, phase_seq % 3u);
             }
             const bool gemv_here = PG.type == PH_GEMV && (int)blockIdx.x < PG.g.L.P;
             const bool to_peers = m.tp > 1 && PG.type == PH_GEMV && PG.mgpu != 0;
