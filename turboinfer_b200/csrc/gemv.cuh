@@ -126,20 +126,28 @@ __device__ __forceinline__ void imma_s8s8(int (&d)[4], uint32_t a0, uint32_t a1,
 #ifndef TIB_ZERO_IN_EPI
 #define TIB_ZERO_IN_EPI 1
 #endif
+#ifndef TIB_LOOP_SYNC
+#define TIB_LOOP_SYNC 0   // 0: every warp waits / probes / arrives on the ring's mbarriers itself; 1: no probe of the next stage;
+                          // 2: the 16 consumer warps meet at named barriers and ONE thread talks to the mbarriers
+#endif
+#ifndef TIB_MASK_FREE_HI
+#define TIB_MASK_FREE_HI 1
+#endif
 template <int BITS>
 struct QuadAcc {
     int lo[TIB_ACC_SETS][4];
     int hi[TIB_ACC_SETS][4];
+    int lb[TIB_MASK_FREE_HI ? TIB_ACC_SETS : 1][4];   // INT4, mask-free high nibbles: low nibbles x the digits of the SECOND 32 k (see kitem_mma)
     __device__ __forceinline__ void clear() {
 #pragma unroll
         for (int s = 0; s < TIB_ACC_SETS; ++s)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { lo[s][i] = 0; hi[s][i] = 0; }
+            for (int i = 0; i < 4; ++i) { lo[s][i] = 0; hi[s][i] = 0; lb[TIB_MASK_FREE_HI ? s : 0][i] = 0; }
     }
     __device__ __forceinline__ int total(int i) const {
         int l = 0, h = 0;
 #pragma unroll
-        for (int s = 0; s < TIB_ACC_SETS; ++s) { l += lo[s][i]; h += hi[s][i]; }
+        for (int s = 0; s < TIB_ACC_SETS; ++s) { l += lo[s][i]; h += hi[s][i] - (TIB_MASK_FREE_HI ? lb[s][i] : 0); }
         if constexpr (BITS == 4) return l + (h >> 4);
         else return l;
     }
@@ -147,11 +155,21 @@ struct QuadAcc {
 
 // One k-item: the lane's A fragment registers (w.x .. w.w = registers 0..3) against the digits of the item's k range
 // (INT4: xv = {b0, b1 of the first 32 k, b0, b1 of the next 32 k}; INT8: xv.x, xv.y).
+// INT4: a byte b = lo + 16 hi holds the nibbles of k and k + 32.  The low nibbles need their mask (4 LOP3); the high nibbles
+// are taken WITHOUT masking: b . x2 = lo . x2 + 16 hi . x2, and lo . x2 is one more MMA on the already masked registers, kept
+// in its own accumulator and subtracted when the group's sums are flushed -- exact, since everything is an integer.  One
+// extra IMMA (the tensor pipe is ~20 % busy in this loop) replaces four LOP3 on the ALU pipe.
 template <int BITS>
 __device__ __forceinline__ void kitem_mma(QuadAcc<BITS>& acc, int par, const uint4& w, const uint4& xv) {
     if constexpr (BITS == 4) {
-        imma_u8s8(acc.lo[par], w.x & 0x0F0F0F0Fu, w.y & 0x0F0F0F0Fu, w.z & 0x0F0F0F0Fu, w.w & 0x0F0F0F0Fu, xv.x, xv.y);
+        const uint32_t l0 = w.x & 0x0F0F0F0Fu, l1 = w.y & 0x0F0F0F0Fu, l2 = w.z & 0x0F0F0F0Fu, l3 = w.w & 0x0F0F0F0Fu;
+        imma_u8s8(acc.lo[par], l0, l1, l2, l3, xv.x, xv.y);
+#if TIB_MASK_FREE_HI
+        imma_u8s8(acc.hi[par], w.x, w.y, w.z, w.w, xv.z, xv.w);
+        imma_u8s8(acc.lb[par], l0, l1, l2, l3, xv.z, xv.w);
+#else
         imma_u8s8(acc.hi[par], w.x & 0xF0F0F0F0u, w.y & 0xF0F0F0F0u, w.z & 0xF0F0F0F0u, w.w & 0xF0F0F0F0u, xv.z, xv.w);
+#endif
     } else {
         imma_s8s8(acc.lo[par], w.x, w.y, w.z, w.w, xv.x, xv.y);
     }
@@ -517,9 +535,12 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
     const int my_nq = pl.my_nq;
     int grp = pl.grp, chunk = pl.chunk;   // group / chunk of the warp's next quad
     const int g = lane >> 2, t = lane & 3;
-    const uint32_t xlane = smem_u32(sm.xd) + ((g < 3 ? g : 0) * 4 + t) * (BITS == 4 ? 16 : 8);   // B column g = digit plane g
+    // B column g = digit plane g.  Columns 3..7 of the product are never read; their lanes duplicate a plane that is read in
+    // the SAME quarter-warp (g = 3 -> plane 2, g >= 4 -> plane 0), so that the extra lanes are pure broadcasts: pointing all of
+    // them at plane 0 put planes 0 and 2 -- the same banks -- into one quarter-warp of the LDS.128, a 2-way bank conflict on
+    // every digit load (15 % of the kernel's shared-memory load wavefronts in the ncu capture of profiles/r02_*)
+    const uint32_t xlane = smem_u32(sm.xd) + ((g < 3 ? g : (g == 3 ? 2 : 0)) * 4 + t) * (BITS == 4 ? 16 : 8);
     const bool xon = g < 3;
-    const uint32_t ring0 = smem_u32(sm.ring), full0 = smem_u32(sm.full), empty0 = smem_u32(sm.empty);
     // lane l < 16 stands for warp l when the stage offsets are summed with one REDUX (ragged rounds only)
     const int l_nq = pl.l_nq, l_fq = pl.l_fq;
     const bool l_before = lane < warp;  // warp < 16
@@ -558,18 +579,27 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
         if (DBG == 1 || (DBG == 3 && (xskip & 8))) acc.lo[0][0] += (int)(wv.x ^ wv.y ^ wv.z ^ wv.w);
         else kitem_mma<BITS>(acc, i % TIB_ACC_SETS, wv, xv);
     };
-    // ring position as addresses: the warp's slot of the current stage, its two barriers, the parity of the current use
+    // Ring position: stage index and parity; every address of a round is a constant offset from ONE register holding the
+    // block's shared-window base (mbarriers at +0 / +48, ring at +128).  The base, the lane's offset and the digit address are
+    // made opaque to the compiler once: left to itself it re-derives them from %tid and the CTA id (S2R + several ALU
+    // instructions) in every round.
     uint32_t st = it.st, par = it.par;
-    uint32_t stage = ring0 + st * kStageBytes, fullb = full0 + st * 8, emptyb = empty0 + st * 8;
+    uint32_t sbase = smem_u32(sm.full);
+    uint32_t wfast = (uint32_t)(kBarBlockBytes + warp * 4 * kItemBytes + lane * 16);   // the warp's slot in a stage when every warp before has a full quad
     uint32_t xq = xlane + chunk * kChunkBytes;
-    const uint32_t wfast = (uint32_t)(warp * 4 * kItemBytes + lane * 16);   // offset in the stage when every warp before has a full quad
+    asm volatile("" : "+r"(sbase), "+r"(wfast), "+r"(xq));
     // the NEXT stage's barrier is probed while this stage is being multiplied; the first one may have been probed by the
     // caller during its prologue (polling an mbarrier costs 0.1-0.2 us even when its phase is long complete)
     bool ready = ready0;
     for (int r = 0; r < nrounds; ++r) {
         const bool have = r < my_nq;
-        uint32_t nstage = stage + kStageBytes, nfull = fullb + 8, nempty = emptyb + 8, npar = par;
-        if (++st == S) { st = 0; npar ^= 1u; nstage = ring0; nfull = full0; nempty = empty0; }
+        const uint32_t stage = sbase + st * kStageBytes, fullb = sbase + st * 8, emptyb = fullb + kMaxStages * 8;
+        const uint32_t nst = st + 1 == S ? 0u : st + 1, npar = par ^ (nst == 0u ? 1u : 0u);
+        // wait until the stage has landed
+#if TIB_LOOP_SYNC == 2
+        if (warp == 0 && lane == 0 && !ready) mbar_wait_s(fullb, par);
+        bar_sync(4, kConsumerThreads);
+#endif
         if (have && grp != last_grp) {
             // ---- fast path: a full quad, and only full quads before it in the stage ----
             uint4 xa, xb;
@@ -580,7 +610,9 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
                 xa = xb = make_uint4(1u, 2u, 3u, 4u);
             }
             if constexpr (DBG == 3) { if (dbg && r == 0) dbg[7] = clock64(); }
+#if TIB_LOOP_SYNC != 2
             if (DBG != 2 && !ready) mbar_wait_s(fullb, par);
+#endif
             if constexpr (DBG == 3) { if (dbg && r == 0) dbg[0] = clock64(); }
             const uint32_t wbase = stage + wfast;
             const uint4 w0 = lds128s(wbase), w1 = lds128s(wbase + 512);
@@ -590,7 +622,11 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
                 xa = load_xfrag<BITS>(xq + 2 * kXItem, xon);
                 xb = load_xfrag<BITS>(xq + 3 * kXItem, xon);
             }
-            ready = (DBG != 2 && r + 1 < nrounds) ? mbar_test_wait_s(nfull, npar) : false;
+#if TIB_LOOP_SYNC == 0
+            ready = (DBG != 2 && r + 1 < nrounds) ? mbar_test_wait_s(sbase + nst * 8, npar) : false;
+#else
+            ready = false;
+#endif
             one(2, w2, xa); one(3, w3, xb);
             dirty = true;
             xq += kChunkBytes;
@@ -600,13 +636,19 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
             const int l_items = (l_before && r < l_nq) ? (l_fq + r >= slab.qfull ? slab.nlast : 4) : 0;
             const int woff = __reduce_add_sync(0xffffffffu, l_items);   // 512-byte items of the warps before this one in the stage
             if constexpr (DBG == 3) { if (dbg && r == 0) dbg[7] = clock64(); }
+#if TIB_LOOP_SYNC != 2
             if (DBG != 2 && !ready) mbar_wait_s(fullb, par);
+#endif
             if constexpr (DBG == 3) { if (dbg && r == 0) dbg[0] = clock64(); }
-            ready = (DBG != 2 && r + 1 < nrounds) ? mbar_test_wait_s(nfull, npar) : false;
+#if TIB_LOOP_SYNC == 0
+            ready = (DBG != 2 && r + 1 < nrounds) ? mbar_test_wait_s(sbase + nst * 8, npar) : false;
+#else
+            ready = false;
+#endif
             if (have) {
                 const int nl = slab.nlast;   // rows 0..7 in part A, rows 8..11 (nl = 3) in part B
                 const bool in_a = nl > 1 || lane < 16, in_b = nl == 3 && lane < 16;
-                const uint32_t wbase = stage + woff * kItemBytes + lane * 8;
+                const uint32_t wbase = stage + kBarBlockBytes + woff * kItemBytes + lane * 8;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     uint2 pa = make_uint2(0u, 0u), pb = make_uint2(0u, 0u);
@@ -620,10 +662,16 @@ __device__ __forceinline__ void gemv_consume(const GemvArgs& a, const Slab& slab
                 if (++chunk == C) { flush(); chunk = 0; ++grp; xq = xlane; }
             }
         }
+#if TIB_LOOP_SYNC == 2
+        bar_sync(5, kConsumerThreads);
+        if (warp == 0 && lane == 0) mbar_arrive_s(emptyb);   // every warp is done reading the stage (the empty barriers count 1 arrival)
+#else
         __syncwarp();
         if (DBG != 2 && lane == 0) mbar_arrive_s(emptyb);  // this warp is done reading the stage
+#endif
         if constexpr (DBG == 3) { if (dbg && r < 5) dbg[r - 10] = clock64(); }
-        stage = nstage; fullb = nfull; emptyb = nempty; par = npar;
+        st = nst;
+        par = npar;
     }
     it.st = st;
     it.par = par;
@@ -779,7 +827,7 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
 __device__ __forceinline__ void gemv_init_barriers(const GemvSmem& sm, int stages) {
     for (int i = 0; i < stages; ++i) {
         mbar_init(&sm.full[i], 1);
-        mbar_init(&sm.empty[i], kConsumerWarps);
+        mbar_init(&sm.empty[i], TIB_LOOP_SYNC == 2 ? 1 : kConsumerWarps);
     }
     fence_mbar_init();
 }
