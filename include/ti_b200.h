@@ -174,6 +174,13 @@ int ti_b200_model_new(const ti_model_config* cfg, ti_model_t* out);
  * "layers.3.attention.q_proj.weight"; data is fp32 [rows, cols] ([in, out] for projections, [H] for norms:
  * rows = 1).  Absent tensors trigger the reference's null-weight fall-backs (:293-296, :377-380, :392-395). */
 int ti_b200_model_set_tensor(ti_model_t m, const char* name, const float* data_host, size_t rows, size_t cols);
+/* An ALREADY QUANTIZED projection / lm_head tensor -- the output of Quantizer::quantize_model (src/optimize/quantization.cpp:67-87) or
+ * a tensor of a .tinq file (load_quantized_model, :208-333): int8 elements for TI_Q_INT8, int32 elements for TI_Q_INT4 (the
+ * reference's storage, :683-693), row-major [rows, cols], with the (scale, zero_point) they were quantized with.  The integers are
+ * packed into the streaming layout as they are (no re-quantization); qtype must equal the model's.  INT4 integers lie in [-7, 7]
+ * (zero_point 0) or [0, 15] (asymmetric).  Embedding rows and norm weights stay float32 (ti_b200_model_set_tensor). */
+int ti_b200_model_set_tensor_q(ti_model_t m, const char* name, const void* q_host, size_t rows, size_t cols, int qtype, float scale,
+                               float zero_point);
 /* same, but the fp32 source is generated on the device: uniform(-amp, amp) from a counter-based hash of
  * (seed, element index) -- for benchmark-size models whose fp32 weights would not fit host RAM. */
 int ti_b200_model_set_tensor_synthetic(ti_model_t m, const char* name, size_t rows, size_t cols, uint64_t seed, float amp);

@@ -47,9 +47,21 @@ public:
     bool has_tensor(const std::string& name) const { return tensors_.count(name) != 0; }
     size_t num_tensors() const noexcept { return tensors_.size(); }
 
+    // B200 build: the REAL (scale, zero_point) of a quantized (int8 / int32) tensor, as Quantizer::quantize_model computed
+    // them.  The reference drops them (its engine multiplies by the bare integers, SURVEY R8, and its .tinq writer re-invents
+    // scales from the integer range, quantization.cpp:737-816); keeping them is what lets a quantized model -- in memory or
+    // loaded from a .tinq file -- go to the device as integers, packed once, without re-quantizing.
+    struct QuantParams { float scale = 0.f, zero_point = 0.f; int type = 0; };   // type: optimize::QuantizationType as int
+    void set_quant_params(const std::string& name, QuantParams q) { qparams_[name] = q; }
+    const QuantParams* quant_params(const std::string& name) const {
+        auto it = qparams_.find(name);
+        return it == qparams_.end() ? nullptr : &it->second;
+    }
+
 private:
     ModelMetadata metadata_;
     std::unordered_map<std::string, core::Tensor> tensors_;
+    std::unordered_map<std::string, QuantParams> qparams_;
 };
 
 }  // namespace model

@@ -41,6 +41,12 @@ public:
     core::Tensor dequantize_tensor(const core::Tensor& quantized, const QuantizationInfo& info);
     model::ModelData quantize_model(const model::ModelData& model_data);
     QuantizationInfo calculate_quantization_info(const core::Tensor& input);
+    // .tinq files (reference quantization.cpp:120-333): the same byte layout -- magic "TINQ", version 1, config, metadata,
+    // tensors with their (scales, zero_points, sizes) trailer -- so files travel both ways between the two implementations.
+    // The trailer holds the tensor's REAL scale / zero-point (ModelData::quant_params) where the reference writes values
+    // re-derived from the integer range (:737-816); a file without usable parameters loads as plain integer tensors.
+    void save_quantized_model(const model::ModelData& quantized_model, const std::string& output_path);
+    static model::ModelData load_quantized_model(const std::string& model_path);
 
 private:
     QuantizationConfig config_;

@@ -337,6 +337,26 @@ def port() -> Oracle:
     return _cache["port"]
 
 
+def tinq_write_sample(path: str, qtype: int) -> None:
+    """reference-only: quantize the model of tests/test_quantization_persistence.cpp with the reference and save it as .tinq"""
+    lib = ref().lib
+    lib.tio_tinq_write_sample.restype = C.c_int
+    lib.tio_tinq_write_sample.argtypes = [C.c_char_p, C.c_int]
+    if lib.tio_tinq_write_sample(path.encode(), qtype) != 0:
+        raise RuntimeError("reference save_quantized_model failed")
+
+
+def tinq_resave(src: str, dst: str, qtype: int) -> int:
+    """reference-only: load_quantized_model(src) then save_quantized_model(dst); returns the tensor count"""
+    lib = ref().lib
+    lib.tio_tinq_resave.restype = C.c_int
+    lib.tio_tinq_resave.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    n = lib.tio_tinq_resave(src.encode(), dst.encode(), qtype)
+    if n < 0:
+        raise RuntimeError("the reference could not load " + src)
+    return n
+
+
 def ref_available() -> bool:
     return os.path.exists(REF_SO)
 

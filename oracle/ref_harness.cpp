@@ -299,4 +299,52 @@ int tio_generate_literal(int vocab, int hidden, int layers, int qtype, const int
     }
 }
 
+// ---- .tinq files through the reference's own writer / reader (quantization.cpp:120-333); harness only, the port has no file IO ----
+// Writes the model of tests/test_quantization_persistence.cpp:33-77 (three float tensors, ramps), quantized by the reference.
+int tio_tinq_write_sample(const char* path, int qtype) {
+    try {
+        mdl::ModelData md;
+        auto& meta = md.metadata();
+        meta.name = "test_model";
+        meta.architecture = "transformer";
+        meta.version = "1.0";
+        meta.vocab_size = 1000;
+        meta.hidden_size = 128;
+        meta.num_layers = 2;
+        meta.num_heads = 8;
+        meta.intermediate_size = 512;
+        meta.rope_theta = 10000.0f;
+        auto ramp = [](std::vector<size_t> dims, int mod) {
+            Tensor t(TensorShape(dims), DataType::kFloat32);
+            float* d = t.data_ptr<float>();
+            for (size_t i = 0; i < t.shape().total_size(); ++i) d[i] = static_cast<float>(i % mod) / static_cast<float>(mod) - 0.5f;
+            return t;
+        };
+        md.add_tensor("weight1", ramp({128, 256}, 255));
+        md.add_tensor("weight2", ramp({256, 512}, 127));
+        md.add_tensor("bias", ramp({256}, 64));
+        opt::QuantizationConfig qc;
+        qc.type = static_cast<opt::QuantizationType>(qtype);
+        qc.symmetric = true;
+        opt::Quantizer qz(qc);
+        qz.save_quantized_model(qz.quantize_model(md), path);
+        return 0;
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
+// reference reader -> reference writer: proves a file written elsewhere is one the reference accepts, and what it keeps of it
+int tio_tinq_resave(const char* in_path, const char* out_path, int qtype) {
+    try {
+        mdl::ModelData md = opt::Quantizer::load_quantized_model(in_path);
+        opt::QuantizationConfig qc;
+        qc.type = static_cast<opt::QuantizationType>(qtype);
+        qc.symmetric = true;
+        opt::Quantizer(qc).save_quantized_model(md, out_path);
+        return static_cast<int>(md.tensor_names().size());
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
+
 }  // extern "C"

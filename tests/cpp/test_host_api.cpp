@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <string>
 
 #include "turboinfer/core/tensor_engine.hpp"
@@ -273,7 +274,155 @@ static void test_engine_gpu() {
     CHECK_THROWS(model::InferenceEngine(bad), std::runtime_error);
 }
 
+// ---- .tinq persistence (reference tests/test_quantization_persistence.cpp) -------------------------------------------------
+// A quantized model made on the host alone (no device): fixed integers + parameters, one float tensor, one int tensor without
+// parameters.
+static model::ModelData tinq_fixture(bool int4) {
+    model::ModelData md;
+    auto& m = md.metadata();
+    m.name = "tinq-fixture"; m.architecture = "llama"; m.version = "7"; m.vocab_size = 321; m.hidden_size = 48; m.num_layers = 3;
+    m.num_heads = 6; m.intermediate_size = 100; m.rope_theta = 12345.5f;
+    const int type = int4 ? (int)optimize::QuantizationType::kInt4 : (int)optimize::QuantizationType::kInt8;
+    auto qmat = [&](size_t r, size_t c, int salt) {
+        Tensor t{TensorShape({r, c}), int4 ? DataType::kInt32 : DataType::kInt8};
+        for (size_t i = 0; i < r * c; ++i) {
+            const int v = (int)((i * 37 + salt * 11) % (int4 ? 15 : 255)) - (int4 ? 7 : 127);
+            if (int4) t.data_ptr<int32_t>()[i] = v; else t.data_ptr<int8_t>()[i] = (int8_t)v;
+        }
+        return t;
+    };
+    md.add_tensor("layers.0.attention.q_proj.weight", qmat(48, 48, 1));
+    md.set_quant_params("layers.0.attention.q_proj.weight", {0.00123f, 0.f, type});
+    md.add_tensor("lm_head.weight", qmat(48, 321, 2));
+    md.set_quant_params("lm_head.weight", {0.0456f, int4 ? 0.f : 3.f, type});
+    md.add_tensor("plain.integers", qmat(5, 7, 3));                       // no parameters: stays a plain integer tensor
+    md.add_tensor("norm.weight", ramp({48}, 0.01f, 1.f));                 // float32 tensors travel untouched
+    return md;
+}
+static bool same_tensor(const Tensor& a, const Tensor& b) {
+    if (a.dtype() != b.dtype() || a.shape().ndim() != b.shape().ndim() || a.byte_size() != b.byte_size()) return false;
+    for (size_t i = 0; i < a.shape().ndim(); ++i) if (a.shape().size(i) != b.shape().size(i)) return false;
+    return std::memcmp(a.data(), b.data(), a.byte_size()) == 0;
+}
+static void check_same_model(const model::ModelData& a, const model::ModelData& b, bool params) {
+    const auto &ma = a.metadata(), &mb = b.metadata();
+    CHECK(ma.name == mb.name && ma.architecture == mb.architecture && ma.version == mb.version);
+    CHECK(ma.vocab_size == mb.vocab_size && ma.hidden_size == mb.hidden_size && ma.num_layers == mb.num_layers);
+    CHECK(ma.num_heads == mb.num_heads && ma.intermediate_size == mb.intermediate_size && ma.rope_theta == mb.rope_theta);
+    CHECK(a.num_tensors() == b.num_tensors());
+    for (const std::string& n : a.tensor_names()) {
+        const Tensor* tb = b.get_tensor(n);
+        CHECK(tb != nullptr);
+        if (!tb) continue;
+        CHECK(same_tensor(*a.get_tensor(n), *tb));
+        const auto *qa = a.quant_params(n), *qb = b.quant_params(n);
+        if (params) {
+            CHECK((qa == nullptr) == (qb == nullptr));
+            if (qa && qb) CHECK(qa->scale == qb->scale && qa->zero_point == qb->zero_point && qa->type == qb->type);
+        } else {
+            CHECK(qb == nullptr);   // a trailer derived from the integers (the reference's writer) is not taken for parameters
+        }
+    }
+}
+static optimize::Quantizer tinq_quantizer(bool int4) {
+    optimize::QuantizationConfig qc;
+    qc.type = int4 ? optimize::QuantizationType::kInt4 : optimize::QuantizationType::kInt8;
+    qc.symmetric = true;
+    return optimize::Quantizer(qc);
+}
+// tinq-write <int8|int4> <path> | tinq-check <int8|int4> <path> <ours|resaved> | tinq-dump <path> <dir> | tinq-errors <dir>
+static int tinq_tool(int argc, char** argv) {
+    const std::string mode = argv[1];
+    if (mode == "tinq-write") {
+        tinq_quantizer(std::strcmp(argv[2], "int4") == 0).save_quantized_model(tinq_fixture(std::strcmp(argv[2], "int4") == 0), argv[3]);
+    } else if (mode == "tinq-check") {
+        const bool int4 = std::strcmp(argv[2], "int4") == 0;
+        check_same_model(tinq_fixture(int4), optimize::Quantizer::load_quantized_model(argv[3]), std::strcmp(argv[4], "ours") == 0);
+    } else if (mode == "tinq-dump") {   // every tensor's raw bytes + one line of metadata, for a comparison made outside
+        model::ModelData md = optimize::Quantizer::load_quantized_model(argv[2]);
+        std::ofstream idx(std::string(argv[3]) + "/index.txt");
+        const auto& m = md.metadata();
+        idx << "meta " << m.name << " " << m.architecture << " " << m.version << " " << m.vocab_size << " " << m.hidden_size << " "
+            << m.num_layers << " " << m.num_heads << " " << m.intermediate_size << " " << m.rope_theta << "\n";
+        for (const std::string& n : md.tensor_names()) {
+            const Tensor* t = md.get_tensor(n);
+            idx << "tensor " << n << " " << (int)t->dtype() << " " << (md.quant_params(n) ? 1 : 0);
+            for (size_t i = 0; i < t->shape().ndim(); ++i) idx << " " << t->shape().size(i);
+            idx << "\n";
+            std::ofstream(std::string(argv[3]) + "/" + n + ".bin", std::ios::binary).write(static_cast<const char*>(t->data()), (std::streamsize)t->byte_size());
+        }
+    } else if (mode == "tinq-errors") {   // the reader's error paths (quantization.cpp:216-231, :289-291, :329-331)
+        const std::string dir = argv[2];
+        CHECK_THROWS(optimize::Quantizer::load_quantized_model(dir + "/does-not-exist.tinq"), std::runtime_error);
+        { std::ofstream f(dir + "/bad-magic.tinq", std::ios::binary); const uint32_t w[2] = {0x12345678u, 1u}; f.write((const char*)w, 8); }
+        CHECK_THROWS(optimize::Quantizer::load_quantized_model(dir + "/bad-magic.tinq"), std::runtime_error);
+        { std::ofstream f(dir + "/bad-version.tinq", std::ios::binary); const uint32_t w[2] = {0x54494E51u, 2u}; f.write((const char*)w, 8); }
+        CHECK_THROWS(optimize::Quantizer::load_quantized_model(dir + "/bad-version.tinq"), std::runtime_error);
+        tinq_quantizer(false).save_quantized_model(tinq_fixture(false), dir + "/whole.tinq");
+        std::ifstream in(dir + "/whole.tinq", std::ios::binary);
+        std::string bytes((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+        for (size_t cut : {bytes.size() - 1, bytes.size() / 2, (size_t)40, (size_t)9}) {   // truncated anywhere: an error, never a partial model
+            std::ofstream(dir + "/cut.tinq", std::ios::binary).write(bytes.data(), (std::streamsize)cut);
+            CHECK_THROWS(optimize::Quantizer::load_quantized_model(dir + "/cut.tinq"), std::runtime_error);
+        }
+        CHECK_THROWS(tinq_quantizer(false).save_quantized_model(tinq_fixture(false), dir + "/no/such/dir/x.tinq"), std::runtime_error);
+    } else {
+        std::printf("unknown mode %s\n", mode.c_str());
+        return 2;
+    }
+    std::printf("%s: %d check(s) failed\n", mode.c_str(), g_failed);
+    return g_failed == 0 ? 0 : 1;
+}
+
+// quantize on the device -> save -> load -> engine: the loaded integers reach the device as they are, so the tokens equal those of
+// the engine that quantizes the same float32 projections itself (and the embedding / norm rows, which the engine reads as float32,
+// are dequantized from the file)
+static void test_tinq_engine_gpu(const char* dir) {
+    for (const char* quant : {"int8", "int4"}) {
+        const bool int4 = std::strcmp(quant, "int4") == 0;
+        model::ModelData fp = small_model(quant);
+        optimize::Quantizer qz = tinq_quantizer(int4);
+        model::ModelData qm = qz.quantize_model(fp);
+        for (const std::string& n : fp.tensor_names()) CHECK(qm.quant_params(n) != nullptr && qm.quant_params(n)->scale > 0.f);
+        const std::string path = std::string(dir) + "/small-" + quant + ".tinq";
+        qz.save_quantized_model(qm, path);
+        model::ModelData back = optimize::Quantizer::load_quantized_model(path);
+        check_same_model(qm, back, true);
+        // reference engine for the comparison: float32 projections (quantized on the device with the same formulas) over the SAME
+        // dequantized embedding / norm rows the file holds
+        model::ModelData mixed = small_model(quant);
+        for (const std::string& n : fp.tensor_names()) {
+            if (n.find("embed") == std::string::npos && n.find("norm") == std::string::npos) continue;
+            optimize::QuantizationInfo info;
+            info.type = int4 ? optimize::QuantizationType::kInt4 : optimize::QuantizationType::kInt8;
+            info.scales = {qm.quant_params(n)->scale};
+            info.zero_points = {qm.quant_params(n)->zero_point};
+            mixed.add_tensor(n, qz.dequantize_tensor(*qm.get_tensor(n), info));
+        }
+        model::InferenceConfig cfg;
+        cfg.top_k = 1;
+        cfg.max_sequence_length = 64;
+        model::InferenceEngine from_file(back, cfg), from_float(mixed, cfg);
+        const std::vector<int> prompt = {1, 15, 25, 35};
+        const auto a = from_file.generate(prompt, 16), b = from_float.generate(prompt, 16);
+        CHECK(a.tokens.size() > prompt.size() && a.tokens == b.tokens);
+        Tensor la = from_file.forward_pass_incremental({7}), lb = from_float.forward_pass_incremental({7});
+        CHECK(same_tensor(la, lb));                                        // same packed integers, same arithmetic: bit-identical logits
+        // a file written by the reference carries no usable parameters: refused with a message, not run on bare integers
+        model::ModelData no_params;
+        no_params.metadata() = back.metadata();
+        for (const std::string& n : back.tensor_names()) no_params.add_tensor(n, *back.get_tensor(n));
+        CHECK_THROWS(model::InferenceEngine(no_params, cfg), std::runtime_error);
+    }
+}
+
 int main(int argc, char** argv) {
+    if (argc > 2 && std::strncmp(argv[1], "tinq-", 5) == 0) return tinq_tool(argc, argv);
+    if (argc > 2 && std::strcmp(argv[1], "gpu-tinq") == 0) {
+        test_tinq_engine_gpu(argv[2]);
+        std::printf("gpu-tinq: %d check(s) failed\n", g_failed);
+        return g_failed == 0 ? 0 : 1;
+    }
     const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
     test_host_types();
     test_no_cpu_fallback(gpu);

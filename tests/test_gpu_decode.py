@@ -135,3 +135,81 @@ def test_full_width_truncated_depth(tb, port, shape, qt, n_new):
     print(f"{shape} q{qt}: logits rel err {err:.3e}, min top-2 margin {margin.min():.3e}")
     assert err <= 1e-2
     assert np.array_equal(toks, rt)
+
+
+def _quantized_tensors(port, w, qt):
+    """Quantizer::quantize_model on the CPU oracle: integers + (scale, zero_point) per projection / lm_head tensor"""
+    out = {}
+    for name, v in w.items():
+        if v.ndim == 2 and "embeddings" not in name:
+            scale, zp = port.quant_info(v, qt, True)
+            out[name] = (port.quantize(v, qt, scale, zp), float(scale), float(zp))
+    return out
+
+
+@pytest.mark.parametrize("qt", [oracle.QINT8, oracle.QINT4])
+def test_model_from_quantized_integers(tb, port, qt):
+    """ti_b200_model_set_tensor_q (the .tinq path): integers quantized elsewhere are packed as they are -- the model
+    is bit-identical to the one the device quantizes from the same float32 tensors"""
+    meta = SHAPES["tiny-test"]
+    w = make_model(meta, norm_jitter=0.1)
+    prompt = prompt_tokens(5, meta["vocab"])
+    a = tb.Model(meta, qt, max_seq=64).load(w)
+    b = tb.Model(meta, qt, max_seq=64)
+    try:
+        qs = _quantized_tensors(port, w, qt)
+        for name, v in w.items():
+            if name in qs:
+                q, scale, zp = qs[name]
+                b.set_tensor_q(name, q, qt, scale, zp)
+            else:
+                b.set_tensor(name, v)
+        b.finalize()
+        ta, la, _ = a.generate_greedy(prompt, 12, want_logits=True)
+        tb_, lb, _ = b.generate_greedy(prompt, 12, want_logits=True)
+        assert list(ta) == list(tb_)
+        np.testing.assert_array_equal(la, lb)
+        # wrong element type / wrong quantization type / non-positive scale / float-only slots are refused
+        c = tb.Model(meta, qt, max_seq=64)
+        name = "layers.0.attention.q_proj.weight"
+        q, scale, zp = qs[name]
+        with pytest.raises(TypeError):
+            c.set_tensor_q(name, q.astype(np.int16), qt, scale, zp)
+        other = oracle.QINT4 if qt == oracle.QINT8 else oracle.QINT8
+        with pytest.raises(RuntimeError):
+            c.set_tensor_q(name, q.astype(np.int32 if other == oracle.QINT4 else np.int8), other, scale, zp)
+        with pytest.raises(RuntimeError):
+            c.set_tensor_q(name, q, qt, 0.0, zp)
+        with pytest.raises(RuntimeError):
+            c.set_tensor_q("norm.weight", q[:1], qt, scale, zp)
+        c.free()
+    finally:
+        a.free()
+        b.free()
+
+
+def test_model_from_asymmetric_int4_integers(tb, port):
+    """INT4 integers made WITH a zero-point live in [0, 15] (quantize_to_int4, quantization.cpp:683-693).  Re-coding a symmetric
+    tensor as (q + 8, zero_point - 8) describes the same real values, so the logits agree to rounding of the zero-point term."""
+    meta = SHAPES["tiny-test"]
+    w = make_model(meta, norm_jitter=0.1)
+    prompt = prompt_tokens(5, meta["vocab"])
+    a = tb.Model(meta, oracle.QINT4, max_seq=64).load(w)
+    b = tb.Model(meta, oracle.QINT4, max_seq=64)
+    try:
+        qs = _quantized_tensors(port, w, oracle.QINT4)
+        for name, v in w.items():
+            if name in qs:
+                q, scale, zp = qs[name]
+                assert zp == 0.0 and q.min() >= -7 and q.max() <= 7
+                b.set_tensor_q(name, (q + 8).astype(np.int32), oracle.QINT4, scale, -8.0)
+            else:
+                b.set_tensor(name, v)
+        b.finalize()
+        ta, la, _ = a.generate_greedy(prompt, 8, want_logits=True)
+        tb_, lb, _ = b.generate_greedy(prompt, 8, want_logits=True)
+        assert rel_err_inf(lb, la) <= 1e-4     # the same real weights through the zero-point term: fp32 rounding only
+        assert list(ta) == list(tb_)
+    finally:
+        a.free()
+        b.free()

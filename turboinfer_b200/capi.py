@@ -74,6 +74,7 @@ SYMBOLS = {
     "ti_b200_gemv_q_dev": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p]),
     "ti_b200_model_new": (C.c_int, [C.POINTER(ModelConfig), C.POINTER(C.c_uint64)]),
     "ti_b200_model_set_tensor": (C.c_int, [C.c_uint64, C.c_char_p, _f, C.c_size_t, C.c_size_t]),
+    "ti_b200_model_set_tensor_q": (C.c_int, [C.c_uint64, C.c_char_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_float, C.c_float]),
     "ti_b200_model_set_tensor_synthetic": (C.c_int, [C.c_uint64, C.c_char_p, C.c_size_t, C.c_size_t, C.c_uint64, C.c_float]),
     "ti_b200_model_finalize": (C.c_int, [C.c_uint64]),
     "ti_b200_model_free": (C.c_int, [C.c_uint64]),
@@ -420,6 +421,16 @@ class Model:
         data = _c(data)
         rows, cols = (1, data.size) if data.ndim == 1 else data.shape
         _ck(lib().ti_b200_model_set_tensor(self.handle, name.encode(), _fp(data), rows, cols))
+
+    def set_tensor_q(self, name: str, q: np.ndarray, qtype: int, scale: float, zero_point: float = 0.0) -> None:
+        """An already quantized tensor (Quantizer::quantize_model / a .tinq file): int8 for INT8, int32 for INT4."""
+        want = np.int8 if qtype == Q_INT8 else np.int32
+        if q.dtype != want:
+            raise TypeError(f"quantized tensor '{name}' must be {np.dtype(want).name}")
+        q = np.ascontiguousarray(q)
+        rows, cols = (1, q.size) if q.ndim == 1 else q.shape
+        _ck(lib().ti_b200_model_set_tensor_q(self.handle, name.encode(), q.ctypes.data_as(C.c_void_p), rows, cols, qtype,
+                                             float(scale), float(zero_point)))
 
     def set_tensor_synthetic(self, name: str, rows: int, cols: int, seed: int, amp: float) -> None:
         _ck(lib().ti_b200_model_set_tensor_synthetic(self.handle, name.encode(), rows, cols, seed, amp))

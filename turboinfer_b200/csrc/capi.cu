@@ -183,11 +183,16 @@ int launch_gemv(const QWeight& w, GemvArgs a, cudaStream_t st) {
     return 0;
 }
 
-// source fp32 matrix on the device awaiting quantization
+// source matrix on the device awaiting packing: fp32 (quantized while packing), or the int8 / int32 integers of an already
+// quantized tensor with the (scale, zero_point) they were made with (ti_b200_model_set_tensor_q, the .tinq path)
 struct RawTensor {
     DevBuf<float> data;
+    DevBuf<uint8_t> qdata;
+    int kind = 0;   // 0 fp32, 1 int8, 2 int32
+    float scale = 0.f, zp = 0.f;
     size_t rows = 0, cols = 0;
-    bool present() const { return data.p != nullptr; }
+    bool present() const { return data.p != nullptr || qdata.p != nullptr; }
+    void release() { data.release(); qdata.release(); }
 };
 
 // min/max -> (scale, zero_point) on the device; sz = 2 floats
@@ -204,10 +209,12 @@ int device_quant_params(const float* x, size_t n, int qtype, int symmetric, floa
 // A source of a packed weight: a view (rows [row0, row0 + K), columns [col0, col0 + n)) of a whole fp32 tensor
 // [rows][cols] on the device.  The quantization parameters always come from the WHOLE tensor.
 struct SrcView {
-    const float* full;
+    const void* full;
     size_t rows, cols;
     size_t row0, col0;
     int n;
+    int kind = 0;                  // as RawTensor::kind
+    float scale = 0.f, zp = 0.f;   // kind != 0: the given parameters
 };
 
 int build_qweight_views(const SrcView* v, int nsrc, int mode, int K, int qtype, int symmetric, bool unit_scale, std::unique_ptr<QWeight>* out);
@@ -216,14 +223,19 @@ int build_qweight_views(const SrcView* v, int nsrc, int mode, int K, int qtype, 
 int build_qweight(const float* const* src, const int* src_n, int nsrc, int mode, int K, int qtype, int symmetric, bool unit_scale,
                   std::unique_ptr<QWeight>* out) {
     SrcView v[3];
-    for (int i = 0; i < nsrc; ++i) v[i] = SrcView{src[i], (size_t)K, (size_t)src_n[i], 0, 0, src_n[i]};
+    for (int i = 0; i < nsrc; ++i) v[i] = SrcView{src[i], (size_t)K, (size_t)src_n[i], 0, 0, src_n[i], 0, 0.f, 0.f};
     return build_qweight_views(v, nsrc, mode, K, qtype, symmetric, unit_scale, out);
 }
 
 int build_qweight_views(const SrcView* v, int nsrc, int mode, int K, int qtype, int symmetric, bool unit_scale, std::unique_ptr<QWeight>* out) {
-    const float* src[3];
+    const void* src[3];
     int src_n[3];
-    for (int i = 0; i < nsrc; ++i) { src[i] = v[i].full + v[i].row0 * v[i].cols + v[i].col0; src_n[i] = v[i].n; }
+    for (int i = 0; i < nsrc; ++i) {
+        const size_t esz = v[i].kind == 1 ? 1 : 4;
+        src[i] = static_cast<const char*>(v[i].full) + (v[i].row0 * v[i].cols + v[i].col0) * esz;
+        src_n[i] = v[i].n;
+        if (v[i].kind != 0 && v[i].kind != (qtype == TI_Q_INT8 ? 1 : 2)) return fail("quantized tensor type does not match the weight's quantization type");
+    }
     auto w = std::make_unique<QWeight>();
     int N = 0;
     for (int i = 0; i < nsrc; ++i) N += src_n[i];
@@ -248,7 +260,16 @@ int build_qweight_views(const SrcView* v, int nsrc, int mode, int K, int qtype, 
     pa.colscale = w->colscale.p;
     pa.colzterm = w->colzterm.p;
     for (int i = 0; i < nsrc; ++i) {
-        TRY(device_quant_params(v[i].full, v[i].rows * v[i].cols, qtype, symmetric, sz.p + 2 * i, mm.p, g_stream));
+        if (v[i].kind == 0) {
+            TRY(device_quant_params(static_cast<const float*>(v[i].full), v[i].rows * v[i].cols, qtype, symmetric, sz.p + 2 * i, mm.p, g_stream));
+        } else {
+            const float given[2] = {v[i].scale, v[i].zp};
+            CK(cudaMemcpyAsync(sz.p + 2 * i, given, sizeof(given), cudaMemcpyHostToDevice, g_stream));
+            // INT4 integers made with a zero-point live in [0, 15] (quantize_to_int4, quantization.cpp:683-693); under the signed
+            // nibble code they are stored as q - 8
+            pa.src[i].shift4 = (qtype == TI_Q_INT4 && pa.off4 == 8 && v[i].zp != 0.0f) ? 8 : 0;
+        }
+        pa.src[i].kind = v[i].kind;
         pa.src[i].w = src[i];
         pa.src[i].n = src_n[i];
         pa.src[i].ld = (int)v[i].cols;
@@ -263,7 +284,7 @@ int build_qweight_views(const SrcView* v, int nsrc, int mode, int K, int qtype, 
     w->scale = h[0];
     w->zp = h[1];
     w->has_zterm = false;
-    for (int i = 0; i < nsrc; ++i) w->has_zterm |= (h[2 * i + 1] != 0.0f);
+    for (int i = 0; i < nsrc; ++i) w->has_zterm |= (h[2 * i + 1] != 0.0f);   // (a shifted source has a zero-point by definition)
     w->offset4 = symmetric ? 8 : 0;
     *out = std::move(w);
     return 0;
@@ -434,7 +455,7 @@ Slot parse_name(const std::string& name, int* layer) {
 
 enum ShardKind { SH_NONE, SH_COLS, SH_ROWS };   // column-parallel (split N) / row-parallel (split K)
 SrcView shard_view(const RawTensor& raw, ShardKind kind, int tp, int rank) {
-    SrcView v{raw.data.p, raw.rows, raw.cols, 0, 0, (int)raw.cols};
+    SrcView v{raw.kind ? (const void*)raw.qdata.p : (const void*)raw.data.p, raw.rows, raw.cols, 0, 0, (int)raw.cols, raw.kind, raw.scale, raw.zp};
     if (tp > 1 && kind == SH_COLS) { v.n = (int)(raw.cols / tp); v.col0 = (size_t)rank * v.n; }
     if (tp > 1 && kind == SH_ROWS) v.row0 = (size_t)rank * (raw.rows / tp);
     return v;
@@ -443,7 +464,7 @@ int pack_single(RawTensor& raw, int qtype, std::unique_ptr<QWeight>* out, ShardK
     const SrcView v = shard_view(raw, kind, tp, rank);
     const int K = (tp > 1 && kind == SH_ROWS) ? (int)(raw.rows / tp) : (int)raw.rows;
     TRY(build_qweight_views(&v, 1, 0, K, qtype, 1, false, out));
-    raw.data.release();
+    raw.release();
     return 0;
 }
 
@@ -456,7 +477,7 @@ int pack_ready(Model& m, Layer& ly, bool final_pass) {
         const SrcView v[3] = {shard_view(ly.raw_q, SH_COLS, m.tp, m.tp_rank), shard_view(ly.raw_k, SH_COLS, m.tp, m.tp_rank),
                               shard_view(ly.raw_v, SH_COLS, m.tp, m.tp_rank)};
         TRY(build_qweight_views(v, 3, 0, (int)ly.raw_q.rows, qt, 1, false, &ly.qkv));
-        ly.raw_q.data.release(); ly.raw_k.data.release(); ly.raw_v.data.release();
+        ly.raw_q.release(); ly.raw_k.release(); ly.raw_v.release();
     }
     if (!ly.o && ly.raw_o.present()) TRY(pack_single(ly.raw_o, qt, &ly.o, SH_ROWS, m.tp, m.tp_rank));          // row-parallel
     if (!ly.down && ly.raw_down.present()) TRY(pack_single(ly.raw_down, qt, &ly.down, SH_ROWS, m.tp, m.tp_rank));
@@ -464,7 +485,7 @@ int pack_ready(Model& m, Layer& ly, bool final_pass) {
         const SrcView v[2] = {shard_view(ly.raw_gate, SH_COLS, m.tp, m.tp_rank), shard_view(ly.raw_up, SH_COLS, m.tp, m.tp_rank)};  // even columns = gate, odd = up
         TRY(build_qweight_views(v, 2, 1, (int)ly.raw_up.rows, qt, 1, false, &ly.gateup));
         ly.has_gate = true;
-        ly.raw_up.data.release(); ly.raw_gate.data.release();
+        ly.raw_up.release(); ly.raw_gate.release();
     }
     if (final_pass && !ly.gateup && ly.raw_up.present()) {  // no gate: relu(up) (:392-395)
         TRY(pack_single(ly.raw_up, qt, &ly.gateup, SH_COLS, m.tp, m.tp_rank));
@@ -473,18 +494,27 @@ int pack_ready(Model& m, Layer& ly, bool final_pass) {
     return 0;
 }
 
-int store_tensor(Model& m, const std::string& name, DevBuf<float>&& dev, size_t rows, size_t cols) {
+int store_tensor(Model& m, const std::string& name, DevBuf<float>&& dev, size_t rows, size_t cols, RawTensor* quantized = nullptr) {
     int li = -1;
     Slot s = parse_name(name, &li);
     if (s == S_NONE) return fail("unknown tensor name '%s'", name.c_str());
+    if (quantized && (s == S_EMB || s == S_NORM || s == S_AN || s == S_FN))
+        return fail("tensor '%s' is read as float32 (embedding rows and norm weights are not quantized on this path)", name.c_str());
+    if (quantized && m.cfg.compat_literal) return fail("the literal benchmark path takes float32 tensors");
     const size_t H = m.cfg.hidden, V = m.cfg.vocab, I = m.cfg.inter;
     auto expect = [&](size_t r, size_t c) -> int {
         if (rows != r || cols != c) return fail("tensor '%s' has shape [%zu,%zu], expected [%zu,%zu]", name.c_str(), rows, cols, r, c);
         return 0;
     };
     auto take = [&](RawTensor& t) {
-        t.data.release();
-        t.data.p = dev.p; t.data.n = dev.n; dev.p = nullptr; dev.n = 0;
+        t.release();
+        if (quantized) {
+            t.qdata = std::move(quantized->qdata);
+            t.kind = quantized->kind; t.scale = quantized->scale; t.zp = quantized->zp;
+        } else {
+            t.data.p = dev.p; t.data.n = dev.n; dev.p = nullptr; dev.n = 0;
+            t.kind = 0;
+        }
         t.rows = rows; t.cols = cols;
     };
     auto take_vec = [&](DevBuf<float>& t) {
@@ -1418,7 +1448,7 @@ int literal_finalize(Model& m) {
     for (auto& ly : m.layers) {
         if (ly.raw_q.present() && ly.raw_k.present() && ly.raw_v.present() && ly.raw_o.present())
             return fail("compat_literal reproduces benchmark_inference's model (no o_proj: the attention fall-back); a layer with a complete attention block needs the normal engine");
-        ly.raw_q.data.release(); ly.raw_k.data.release(); ly.raw_v.data.release(); ly.raw_o.data.release();   // unused by the reference too
+        ly.raw_q.release(); ly.raw_k.release(); ly.raw_v.release(); ly.raw_o.release();   // unused by the reference too
         if (ly.raw_up.present() && ly.raw_down.present()) {
             move(ly.raw_up, ly.lit_up);
             move(ly.raw_down, ly.lit_down);
@@ -1427,7 +1457,7 @@ int literal_finalize(Model& m) {
             TRY(literal_quantize(ly.lit_down, m.cfg.qtype));
             TRY(literal_quantize(ly.lit_gate, m.cfg.qtype));
         }
-        ly.raw_up.data.release(); ly.raw_down.data.release(); ly.raw_gate.data.release();
+        ly.raw_up.release(); ly.raw_down.release(); ly.raw_gate.release();
     }
     TRY(m.logits.alloc(V));
     TRY(m.state.alloc(1));
@@ -1564,7 +1594,7 @@ int ti_b200_init(int device) {
     if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     g_device = device;
     const char* pdl = getenv("TURBOINFER_B200_PDL");
-    g_use_pdl = pdl ? atoi(pdl) != 0 : false;
+    g_use_pdl = pdl ? atoi(pdl) != 0 : true;   // programmatic dependent launch of the stand-alone GEMV: on unless TURBOINFER_B200_PDL=0
     return set_kernel_attrs();
 }
 
@@ -2255,6 +2285,29 @@ int ti_b200_model_set_tensor(ti_model_t h, const char* name, const float* data_h
     return store_tensor(*m, name, std::move(dev), rows, cols);
 }
 
+// An already quantized tensor (Quantizer::quantize_model output, or a tensor of a .tinq file, quantization.cpp:208-333): the
+// integers are packed into the streaming layout as they are, with the (scale, zero_point) they were made with.
+int ti_b200_model_set_tensor_q(ti_model_t h, const char* name, const void* q_host, size_t rows, size_t cols, int qtype, float scale, float zero_point) {
+    TRY(need_init());
+    Model* m = get_model(h);
+    if (!m) return fail("invalid model handle");
+    if (m->finalized) return fail("model already finalized");
+    if (!q_host || rows * cols == 0) return fail("tensor '%s' is empty", name);
+    if (qtype != TI_Q_INT4 && qtype != TI_Q_INT8) return fail("qtype must be TI_Q_INT4 (int32 elements) or TI_Q_INT8 (int8 elements)");
+    if (qtype != m->cfg.qtype) return fail("tensor '%s' is %s but the model was created for %s weights", name, qtype == TI_Q_INT4 ? "INT4" : "INT8",
+                                           m->cfg.qtype == TI_Q_INT4 ? "INT4" : "INT8");
+    if (!(scale > 0.f) || !std::isfinite(scale) || !std::isfinite(zero_point)) return fail("tensor '%s': scale must be positive and finite", name);
+    RawTensor q;
+    q.kind = qtype == TI_Q_INT8 ? 1 : 2;
+    q.scale = scale;
+    q.zp = zero_point;
+    const size_t bytes = rows * cols * (qtype == TI_Q_INT8 ? 1 : 4);
+    TRY(q.qdata.alloc(bytes));
+    CK(cudaMemcpyAsync(q.qdata.p, q_host, bytes, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return store_tensor(*m, name, DevBuf<float>(), rows, cols, &q);
+}
+
 int ti_b200_model_set_tensor_synthetic(ti_model_t h, const char* name, size_t rows, size_t cols, uint64_t seed, float amp) {
     TRY(need_init());
     Model* m = get_model(h);
@@ -2296,8 +2349,8 @@ int ti_b200_model_finalize(ti_model_t h) {
             TRY(ly.v_pool.alloc((size_t)m.num_pages * m.page_tokens * Hl));
         }
         // sources that cannot be used (e.g. q/k/v without o_proj) are dropped, like the reference ignores them
-        ly.raw_q.data.release(); ly.raw_k.data.release(); ly.raw_v.data.release(); ly.raw_o.data.release();
-        ly.raw_up.data.release(); ly.raw_gate.data.release(); ly.raw_down.data.release();
+        ly.raw_q.release(); ly.raw_k.release(); ly.raw_v.release(); ly.raw_o.release();
+        ly.raw_up.release(); ly.raw_gate.release(); ly.raw_down.release();
     }
     // page table: pages are handed out in order by reset(); physical order is deliberately not the identity
     std::vector<int> tab(m.num_pages);

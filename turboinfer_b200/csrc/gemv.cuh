@@ -841,6 +841,9 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const __grid_cons
     const GemvSmem sm = gemv_carve(smem_raw, a.L, a.stages);
     if (tid == 0) gemv_init_barriers(sm, a.stages);
     __syncthreads();
+    // programmatic dependent launch: the NEXT kernel of the stream may be scheduled as soon as this CTA's resources free up --
+    // its producer then streams weights and its consumers park at griddepcontrol.wait until this grid has completed
+    pdl_launch_dependents();
     RingPos it;
     if (warp == kConsumerWarps) {
         // the weights do not depend on the previous kernel: start streaming at once

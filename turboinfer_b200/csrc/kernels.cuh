@@ -105,9 +105,12 @@ __global__ void dequantize_flat_kernel(const int8_t* q8, const int32_t* q32, siz
 // Each source keeps its own per-tensor scale / zero-point (written per column into colscale / colzterm).
 // ---------------------------------------------------------------------------------------------------
 struct PackSrc {
-    const float* w;   // fp32 on the device: element (k, c) at w[k * ld + c] -- a whole tensor or a tensor-parallel shard view
+    const void* w;    // on the device: element (k, c) at w[k * ld + c] -- a whole tensor or a tensor-parallel shard view
     int n;            // columns of the view
     int ld;           // row stride of the underlying tensor (= n when the view is the whole tensor)
+    int kind;         // 0: fp32, quantized here; 1 / 2: int8 / int32 integers of an already quantized tensor (.tinq), stored as they are
+    int shift4;       // INT4 integers in the asymmetric range [0, 15] under the signed nibble code (off4 = 8): stored as q - 8, and
+                      // 8 joins the zero-point term
     const float* sz;  // device: scale, zero_point (of the WHOLE tensor: quantize first, then shard -- SURVEY.md 8e)
 };
 struct PackArgs {
@@ -144,7 +147,11 @@ __global__ void pack_kernel(const PackArgs a) {
             if (live) {
                 int si, sc;
                 pack_locate(a, n, si, sc);
-                qv = quantize_one(a.src[si].w[(size_t)k * a.src[si].ld + sc], a.qtype, a.src[si].sz[0], a.src[si].sz[1]);
+                const PackSrc& ps = a.src[si];
+                const size_t e = (size_t)k * ps.ld + sc;
+                if (ps.kind == 0) qv = quantize_one(static_cast<const float*>(ps.w)[e], a.qtype, ps.sz[0], ps.sz[1]);
+                else if (ps.kind == 1) qv = static_cast<const int8_t*>(ps.w)[e];
+                else qv = static_cast<const int32_t*>(ps.w)[e] - ps.shift4;
             }
             if (L.bits == 4) word |= ((uint32_t)(live ? qv + a.off4 : a.off4) & 0xFu) << (4 * i);   // padding stores q = 0
             else word |= ((uint32_t)qv & 0xFFu) << (8 * i);
@@ -162,7 +169,7 @@ __global__ void pack_kernel(const PackArgs a) {
             int si, sc;
             pack_locate(a, n, si, sc);
             scale = a.src[si].sz[0];
-            zp = a.src[si].sz[1];
+            zp = a.src[si].sz[1] + (float)a.src[si].shift4;
         }
         a.colscale[n] = (col_live && !a.unit_scale) ? scale : (col_live ? 1.0f : 0.0f);
         float zt = 0.f;

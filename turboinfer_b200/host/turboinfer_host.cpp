@@ -4,6 +4,7 @@
 // model resident on the device.  A non-zero C status becomes std::runtime_error carrying ti_b200_last_error(),
 // which is the exception type the reference throws for shape / dtype / empty-input errors
 // (src/core/tensor_engine.cpp:492-494, src/model/inference_engine.cpp:1409-1417).
+#include <fstream>
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -293,10 +294,169 @@ model::ModelData Quantizer::quantize_model(const model::ModelData& model_data) {
     out.metadata() = model_data.metadata();
     for (const std::string& name : model_data.tensor_names()) {
         const core::Tensor* t = model_data.get_tensor(name);
-        if (t->dtype() == core::DataType::kFloat32 && !t->empty()) out.add_tensor(name, quantize_tensor(*t));  // :89-118
-        else out.add_tensor(name, *t);
+        if (t->dtype() == core::DataType::kFloat32 && !t->empty()) {   // :89-118
+            const QuantizationInfo info = calculate_quantization_info(*t);
+            out.add_tensor(name, quantize_tensor(*t));
+            out.set_quant_params(name, {info.scales[0], info.zero_points[0], (int)config_.type});   // kept (the reference drops them, R8)
+        } else {
+            out.add_tensor(name, *t);
+        }
     }
     return out;
+}
+
+namespace {
+// little-endian scalar IO with the reference's field widths (quantization.cpp:120-333 writes raw object bytes on x86-64:
+// enum = 4, bool = 1, size_t = 8, float = 4; strings = u32 length + bytes, :714-735)
+template <typename T> void put(std::ofstream& f, T v) { f.write(reinterpret_cast<const char*>(&v), sizeof(T)); }
+template <typename T> T get(std::ifstream& f) {
+    T v{};
+    f.read(reinterpret_cast<char*>(&v), sizeof(T));
+    if (!f) throw std::runtime_error("unexpected end of file");
+    return v;
+}
+void put_string(std::ofstream& f, const std::string& s) {
+    put<uint32_t>(f, (uint32_t)s.size());
+    if (!s.empty()) f.write(s.data(), (std::streamsize)s.size());
+}
+std::string get_string(std::ifstream& f) {
+    const uint32_t n = get<uint32_t>(f);
+    if (n > (1u << 20)) throw std::runtime_error("implausible string length");
+    std::string s(n, '\0');
+    if (n) f.read(&s[0], n);
+    if (!f) throw std::runtime_error("unexpected end of file");
+    return s;
+}
+// true when (scale, zp) is what the reference's writer computes from the stored integers alone (quantization.cpp:737-816)
+bool derived_from_integers(const core::Tensor& t, float scale, float zp) {
+    const size_t n = t.shape().total_size();
+    if (n == 0) return true;
+    long lo, hi;
+    float full, fallback;
+    if (t.dtype() == core::DataType::kInt8) {
+        const int8_t* d = static_cast<const int8_t*>(t.data());
+        lo = hi = d[0];
+        for (size_t i = 1; i < n; ++i) { lo = std::min<long>(lo, d[i]); hi = std::max<long>(hi, d[i]); }
+        full = 255.0f; fallback = 1.0f / 127.0f;
+    } else {
+        const int32_t* d = static_cast<const int32_t*>(t.data());
+        lo = hi = d[0];
+        for (size_t i = 1; i < n; ++i) { lo = std::min<long>(lo, d[i]); hi = std::max<long>(hi, d[i]); }
+        lo = std::max(lo, -8L); hi = std::min(hi, 7L);
+        full = 15.0f; fallback = 1.0f / 7.0f;
+    }
+    const float range = (float)(hi - lo);
+    if (range > 0) return scale == range / full && zp == (float)(-lo);
+    return scale == fallback && zp == 0.0f;
+}
+size_t dtype_bytes(core::DataType d) {
+    switch (d) {
+        case core::DataType::kFloat32: case core::DataType::kInt32: return 4;
+        case core::DataType::kFloat16: case core::DataType::kInt16: return 2;
+        default: return 1;
+    }
+}
+}  // namespace
+
+void Quantizer::save_quantized_model(const model::ModelData& qm, const std::string& output_path) {
+    std::ofstream f(output_path, std::ios::binary);
+    if (!f.is_open()) throw std::runtime_error("Failed to open file for writing: " + output_path);
+    put<uint32_t>(f, 0x54494E51u);                       // "TINQ" (:128)
+    put<uint32_t>(f, 1u);                                // version (:132)
+    put<int32_t>(f, (int32_t)config_.type);              // :136-138
+    put<uint8_t>(f, config_.symmetric ? 1 : 0);
+    put<uint8_t>(f, config_.per_channel ? 1 : 0);
+    const model::ModelMetadata& md = qm.metadata();      // :141-150
+    put_string(f, md.name);
+    put_string(f, md.architecture);
+    put_string(f, md.version);
+    put<uint64_t>(f, md.vocab_size);
+    put<uint64_t>(f, md.hidden_size);
+    put<uint64_t>(f, md.num_layers);
+    put<uint64_t>(f, md.num_heads);
+    put<uint64_t>(f, md.intermediate_size);
+    put<float>(f, md.rope_theta);
+    const std::vector<std::string> names = qm.tensor_names();
+    put<uint32_t>(f, (uint32_t)names.size());            // :153-155
+    for (const std::string& name : names) {
+        const core::Tensor* t = qm.get_tensor(name);
+        put_string(f, name);                             // :163-181
+        put<uint32_t>(f, (uint32_t)t->dtype());
+        put<uint32_t>(f, (uint32_t)t->shape().ndim());
+        for (size_t i = 0; i < t->shape().ndim(); ++i) put<uint64_t>(f, t->shape().size(i));
+        put<uint64_t>(f, t->byte_size());
+        f.write(static_cast<const char*>(t->data()), (std::streamsize)t->byte_size());
+        if (t->dtype() == core::DataType::kInt8 || t->dtype() == core::DataType::kInt32) {   // the trailer (:184-205)
+            const model::ModelData::QuantParams* q = qm.quant_params(name);
+            put<uint32_t>(f, q ? 1u : 0u);
+            if (q) put<float>(f, q->scale);
+            put<uint32_t>(f, q ? 1u : 0u);
+            if (q) put<float>(f, q->zero_point);
+            const uint64_t orig = t->shape().total_size() * sizeof(float);
+            put<uint64_t>(f, orig);
+            put<uint64_t>(f, t->byte_size());
+            put<float>(f, (float)orig / (float)t->byte_size());
+        }
+    }
+    if (!f) throw std::runtime_error("Failed to save quantized model: write error");
+}
+
+model::ModelData Quantizer::load_quantized_model(const std::string& model_path) {
+    std::ifstream f(model_path, std::ios::binary);
+    if (!f.is_open()) throw std::runtime_error("Failed to open file for reading: " + model_path);
+    try {
+        if (get<uint32_t>(f) != 0x54494E51u) throw std::runtime_error("Invalid file format - not a TurboInfer quantized model");   // :222-224
+        const uint32_t version = get<uint32_t>(f);
+        if (version != 1) throw std::runtime_error("Unsupported quantized model version: " + std::to_string(version));          // :229-231
+        const int32_t type = get<int32_t>(f);
+        (void)get<uint8_t>(f);   // symmetric
+        (void)get<uint8_t>(f);   // per_channel
+        model::ModelData md;
+        model::ModelMetadata& m = md.metadata();
+        m.name = get_string(f);
+        m.architecture = get_string(f);
+        m.version = get_string(f);
+        m.vocab_size = get<uint64_t>(f);
+        m.hidden_size = get<uint64_t>(f);
+        m.num_layers = get<uint64_t>(f);
+        m.num_heads = get<uint64_t>(f);
+        m.intermediate_size = get<uint64_t>(f);
+        m.rope_theta = get<float>(f);
+        const uint32_t count = get<uint32_t>(f);
+        for (uint32_t i = 0; i < count; ++i) {
+            const std::string name = get_string(f);
+            const uint32_t dt = get<uint32_t>(f);
+            if (dt > (uint32_t)core::DataType::kUInt8) throw std::runtime_error("unknown tensor data type in '" + name + "'");
+            const core::DataType dtype = (core::DataType)dt;
+            const uint32_t ndim = get<uint32_t>(f);
+            if (ndim == 0 || ndim > 8) throw std::runtime_error("implausible tensor rank in '" + name + "'");
+            std::vector<size_t> dims;
+            size_t total = 1;
+            for (uint32_t d = 0; d < ndim; ++d) { dims.push_back(get<uint64_t>(f)); total *= dims.back(); }
+            const uint64_t bytes = get<uint64_t>(f);
+            if (bytes != total * dtype_bytes(dtype)) throw std::runtime_error("Tensor size mismatch for: " + name);                // :289-291
+            core::Tensor t(core::TensorShape(dims), dtype);
+            f.read(static_cast<char*>(t.data()), (std::streamsize)bytes);
+            if (!f) throw std::runtime_error("unexpected end of file");
+            if (dtype == core::DataType::kInt8 || dtype == core::DataType::kInt32) {
+                std::vector<float> scales(get<uint32_t>(f));
+                for (float& v : scales) v = get<float>(f);
+                std::vector<float> zps(get<uint32_t>(f));
+                for (float& v : zps) v = get<float>(f);
+                (void)get<uint64_t>(f);
+                (void)get<uint64_t>(f);
+                (void)get<float>(f);
+                // The reference's writer re-derives (scale, zero_point) from the INTEGER range (:737-816): such a trailer carries no
+                // information about the original values, so the tensor then loads as plain integers, without parameters.
+                if (scales.size() == 1 && zps.size() == 1 && !derived_from_integers(t, scales[0], zps[0]))
+                    md.set_quant_params(name, {scales[0], zps[0], type});
+            }
+            md.add_tensor(name, std::move(t));
+        }
+        return md;
+    } catch (const std::exception& e) {
+        throw std::runtime_error("Failed to load quantized model: " + std::string(e.what()));   // :329-331
+    }
 }
 
 const char* quantization_type_to_string(QuantizationType type) {
@@ -383,7 +543,14 @@ InferenceEngine::InferenceEngine(const ModelData& model_data, const InferenceCon
     cfg.inter = (int32_t)md.intermediate_size;
     cfg.rope_theta = md.rope_theta;
     cfg.rms_eps = 1e-5f;
-    const std::string quant = param("b200.quantization", "int8");
+    // a quantized ModelData (Quantizer::quantize_model, a .tinq file) names its own type; otherwise the extra_params key decides
+    std::string quant_default = "int8";
+    for (const std::string& name : model_data.tensor_names())
+        if (const ModelData::QuantParams* q = model_data.quant_params(name)) {
+            quant_default = q->type == (int)optimize::QuantizationType::kInt4 ? "int4" : "int8";
+            break;
+        }
+    const std::string quant = param("b200.quantization", quant_default.c_str());
     cfg.qtype = quant == "int4" ? TI_Q_INT4 : (quant == "none" ? TI_Q_NONE : TI_Q_INT8);
     // "literal": the path benchmarks/benchmark_inference runs on the reference today (placeholder embeddings, attention
     // fall-back, unscaled integer weights; quantization "none" = its FP32 variant) -- BASELINE.json configs[0]
@@ -399,12 +566,32 @@ InferenceEngine::InferenceEngine(const ModelData& model_data, const InferenceCon
         for (const std::string& name : model_data.tensor_names()) {
             const core::Tensor* t = model_data.get_tensor(name);
             if (t->empty()) continue;
-            if (t->dtype() != core::DataType::kFloat32)
-                throw std::runtime_error("tensor '" + name + "': the B200 engine takes float32 weights and quantizes them on the device "
-                                         "(metadata extra_params[\"b200.quantization\"])");
             const size_t nd = t->shape().ndim();
             const size_t cols = t->shape().size(nd - 1), rows = t->shape().total_size() / cols;
-            if (ti_b200_model_set_tensor(h, name.c_str(), static_cast<const float*>(t->data()), rows, cols) != 0) {
+            int rc;
+            if (t->dtype() == core::DataType::kFloat32) {
+                rc = ti_b200_model_set_tensor(h, name.c_str(), static_cast<const float*>(t->data()), rows, cols);
+            } else if ((t->dtype() == core::DataType::kInt8 || t->dtype() == core::DataType::kInt32) && model_data.quant_params(name)) {
+                // an already quantized tensor (Quantizer::quantize_model, or a .tinq file): its integers go to the device as they are
+                const ModelData::QuantParams* q = model_data.quant_params(name);
+                const bool i8 = t->dtype() == core::DataType::kInt8;
+                const bool row_data = name.find("embed") != std::string::npos || name.find("norm") != std::string::npos;
+                if (row_data) {
+                    // embedding rows and norm weights are read as float32 by the engine: dequantize them here with the reference's
+                    // formulas (dequantize_from_int8 / _int4, quantization.cpp:695-713)
+                    std::vector<float> x(rows * cols);
+                    for (size_t i = 0; i < x.size(); ++i)
+                        x[i] = i8 ? q->scale * ((float)static_cast<const int8_t*>(t->data())[i] - q->zero_point)
+                                  : q->scale * ((float)static_cast<const int32_t*>(t->data())[i] + q->zero_point);
+                    rc = ti_b200_model_set_tensor(h, name.c_str(), x.data(), rows, cols);
+                } else {
+                    rc = ti_b200_model_set_tensor_q(h, name.c_str(), t->data(), rows, cols, i8 ? TI_Q_INT8 : TI_Q_INT4, q->scale, q->zero_point);
+                }
+            } else {
+                throw std::runtime_error("tensor '" + name + "': the B200 engine takes float32 weights (quantized on the device, metadata "
+                                         "extra_params[\"b200.quantization\"]) or int8 / int32 tensors with their quantization parameters");
+            }
+            if (rc != 0) {
                 const std::string err = ti_b200_last_error();
                 if (err.rfind("unknown tensor name", 0) == 0) continue;   // the reference ignores tensors it has no slot for
                 throw std::runtime_error(err);
