@@ -237,6 +237,22 @@ int ti_b200_compute_logprobs(ti_model_t m, const int32_t* tokens, int32_t n, flo
 int ti_b200_generate_batch_ragged(ti_model_t m, const int32_t* prompts, const int32_t* lens, int32_t batch, int32_t max_len,
                                   int32_t n_new, int32_t* out_tokens, float* decode_ms);
 
+/* InferenceEngine::generate_beam_search (src/model/inference_engine.cpp:830-871) / beam_search_decode (:1912-2069) on the cached
+ * engine: beams are rows of the lockstep step, a beam's KV cache is a page table into one shared pool (a fork copies the table and
+ * bumps page reference counts; the prompt is cached once), the expansion (softmax(logits / temperature), top-k and top-p on the
+ * probabilities, the beam_size most probable tokens) runs on the device.  Bookkeeping as the reference's: cumulative
+ * log-probability, score = log_prob / (prompt + new tokens)^length_penalty, keep the beam_size best, a candidate finishes on
+ * eos_token or at max_new tokens, stop when beam_size candidates have finished.  Results best score first:
+ * out_tokens [beam_size][max_new] (new tokens only), out_lens / out_logprob / out_score / out_finished [beam_size] (the last three
+ * optional), *n_results <= beam_size.  beam_size <= 64.  Ties (which std::sort leaves unspecified in the reference) go to the
+ * earlier candidate / the lower token id. */
+int ti_b200_beam_search(ti_model_t m, const int32_t* prompt, int32_t n_prompt, int32_t max_new, int32_t beam_size, float temperature,
+                        int32_t top_k, float top_p, float length_penalty, int32_t eos_token, int32_t* out_tokens, int32_t* out_lens,
+                        float* out_logprob, float* out_score, int32_t* out_finished, int32_t* n_results);
+/* the expansion step alone, on host logits [rows][vocab]: probs / tokens [rows][beam_size], counts [rows] */
+int ti_b200_beam_expand(const float* logits_host, size_t rows, size_t vocab, float temperature, int32_t top_k, float top_p, int32_t beam_size,
+                        float* probs_out, int32_t* tokens_out, int32_t* counts_out);
+
 /* CUDA-event time of the prompt phase (prefill) of the last ti_b200_generate_greedy call on this model, in ms */
 int ti_b200_model_last_prefill_ms(ti_model_t m, float* ms);
 

@@ -52,6 +52,11 @@ public:
     GenerationResult generate(const std::vector<int>& input_tokens, size_t max_new_tokens, bool include_logprobs = false);
     std::vector<GenerationResult> generate_batch(const std::vector<std::vector<int>>& input_tokens_batch, size_t max_new_tokens,
                                                  bool include_logprobs = false);
+    /// generate_beam_search (:830-871): one result per beam, best normalised score first; tokens = the NEW tokens only (:853-857),
+    /// logprobs (when asked) = the average log-probability repeated per token (:862-865).  On the device the beams share the
+    /// prompt's KV pages and fork by page table (ti_b200_beam_search).  throws std::runtime_error for beam_size == 0.
+    std::vector<GenerationResult> generate_beam_search(const std::vector<int>& input_tokens, size_t max_new_tokens, size_t beam_size = 4,
+                                                       bool include_logprobs = false);
     /// compute_logprobs (:873-954): log softmax(logits[pos])[tokens[pos]] per position; the reference's sentinels on failure
     std::vector<float> compute_logprobs(const std::vector<int>& tokens);
     /// seed of the sampler's counter-based RNG (a generation with the same seed reproduces its tokens); default: from the clock

@@ -96,6 +96,12 @@ class Oracle:
             L.tio_uniform.restype = C.c_float
             L.tio_uniform.argtypes = [C.c_uint64, C.c_uint64]
             L.tio_logprobs.argtypes = [_f, C.c_size_t, C.c_size_t, C.POINTER(C.c_int32), _f]
+            i32p = C.POINTER(C.c_int32)
+            L.tio_beam_expand.restype = C.c_int
+            L.tio_beam_expand.argtypes = [_f, C.c_size_t, C.c_float, C.c_int, C.c_float, C.c_int, _f, i32p]
+            L.tio_beam_search.restype = C.c_int
+            L.tio_beam_search.argtypes = [C.c_void_p, i32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int,
+                                          i32p, i32p, _f, _f, i32p]
         L.tio_generate_literal.restype = C.c_int
         L.tio_generate_literal.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int,
                                            C.c_int, C.POINTER(C.c_int32), _f]
@@ -313,6 +319,55 @@ class Oracle:
         out = np.zeros(t.size, dtype=np.float32)
         self.lib.tio_logprobs(_fp(lg.reshape(-1)), t.size, lg.shape[-1], t.ctypes.data_as(C.POINTER(C.c_int32)), _fp(out))
         return out
+
+    # ---- beam search (port only) ----
+    def beam_expand(self, logits: np.ndarray, beam_size: int, temperature: float, top_k: int, top_p: float):
+        """[(probability, token)] best first: the expansion of one candidate, beam_search_decode :1964-2005"""
+        lg = np.ascontiguousarray(logits, dtype=np.float32).ravel()
+        pr = np.zeros(beam_size, dtype=np.float32)
+        tk = np.zeros(beam_size, dtype=np.int32)
+        n = self.lib.tio_beam_expand(_fp(lg), lg.size, temperature, top_k, top_p, beam_size, _fp(pr), tk.ctypes.data_as(C.POINTER(C.c_int32)))
+        return [(float(pr[i]), int(tk[i])) for i in range(n)]
+
+    def beam_search(self, weights: dict, meta: dict, prompt: Sequence[int], max_new: int, beam_size: int, *, temperature: float = 1.0,
+                    top_k: int = 50, top_p: float = 0.9, length_penalty: float = 1.0, eos_token: int = 2,
+                    attn_mode: int = 1, rope_mode: int = 0):
+        """generate_beam_search (:830-871) -> [dict(tokens (new only), log_prob, score, finished)], best score first"""
+        m, keep = self._marshal(weights, meta, attn_mode, rope_mode)
+        p = np.ascontiguousarray(prompt, dtype=np.int32)
+        i32p = C.POINTER(C.c_int32)
+        out = np.zeros((beam_size, max(max_new, 1)), dtype=np.int32)
+        lens = np.zeros(beam_size, dtype=np.int32)
+        lp = np.zeros(beam_size, dtype=np.float32)
+        sc = np.zeros(beam_size, dtype=np.float32)
+        fin = np.zeros(beam_size, dtype=np.int32)
+        n = self.lib.tio_beam_search(C.cast(C.byref(m), C.c_void_p), p.ctypes.data_as(i32p), p.size, max_new, beam_size, temperature, top_k, top_p,
+                                     length_penalty, eos_token, out.ctypes.data_as(i32p), lens.ctypes.data_as(i32p), _fp(lp), _fp(sc),
+                                     fin.ctypes.data_as(i32p))
+        del keep
+        if n < 0:
+            raise RuntimeError("tio_beam_search failed")
+        return [dict(tokens=[int(t) for t in out[i, : lens[i]]], log_prob=float(lp[i]), score=float(sc[i]), finished=bool(fin[i]))
+                for i in range(n)]
+
+    def beam_search_literal(self, vocab: int, hidden: int, layers: int, qtype: int, prompt: Sequence[int], max_new: int, beam_size: int, *,
+                            temperature: float = 1.0, top_k: int = 50, top_p: float = 0.9, length_penalty: float = 1.0):
+        """generate_beam_search on the literal benchmark model (both oracles) -> [dict(tokens, avg_logprob, finished)]"""
+        L = self.lib
+        i32p = C.POINTER(C.c_int32)
+        L.tio_beam_search_literal.restype = C.c_int
+        L.tio_beam_search_literal.argtypes = [C.c_int] * 4 + [i32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float,
+                                              i32p, i32p, _f, i32p]
+        p = np.ascontiguousarray(prompt, dtype=np.int32)
+        out = np.zeros((beam_size, max(max_new, 1)), dtype=np.int32)
+        lens = np.zeros(beam_size, dtype=np.int32)
+        lp = np.zeros(beam_size, dtype=np.float32)
+        fin = np.zeros(beam_size, dtype=np.int32)
+        n = L.tio_beam_search_literal(vocab, hidden, layers, qtype, p.ctypes.data_as(i32p), p.size, max_new, beam_size, temperature, top_k, top_p,
+                                      length_penalty, out.ctypes.data_as(i32p), lens.ctypes.data_as(i32p), _fp(lp), fin.ctypes.data_as(i32p))
+        if n < 0:
+            raise RuntimeError("tio_beam_search_literal failed")
+        return [dict(tokens=[int(t) for t in out[i, : lens[i]]], avg_logprob=float(lp[i]), finished=bool(fin[i])) for i in range(n)]
 
     # ---- level C ----
     def generate_literal(self, vocab: int, hidden: int, layers: int, qtype: int, prompt: Sequence[int], n_new: int):

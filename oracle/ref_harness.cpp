@@ -299,6 +299,38 @@ int tio_generate_literal(int vocab, int hidden, int layers, int qtype, const int
     }
 }
 
+int tio_beam_search_literal(int vocab, int hidden, int layers, int qtype, const int32_t* prompt, int n_prompt, int max_new, int beam_size,
+                            float temperature, int top_k, float top_p, float length_penalty, int32_t* out_tokens, int32_t* out_lens,
+                            float* out_avg_logprob, int32_t* out_finished) {
+    try {
+        mdl::ModelData md = literal_model(vocab, hidden, layers);
+        if (qtype == TIO_QINT8 || qtype == TIO_QINT4) {
+            opt::QuantizationConfig qc;
+            qc.type = static_cast<opt::QuantizationType>(qtype);
+            qc.symmetric = true;
+            md = opt::Quantizer(qc).quantize_model(md);
+        }
+        mdl::InferenceConfig cfg;
+        cfg.temperature = temperature;
+        cfg.top_k = static_cast<size_t>(top_k);
+        cfg.top_p = top_p;
+        cfg.length_penalty = length_penalty;
+        mdl::InferenceEngine eng(md, cfg);
+        std::vector<int> in(prompt, prompt + n_prompt);
+        auto res = eng.generate_beam_search(in, static_cast<size_t>(max_new), static_cast<size_t>(beam_size), true);
+        const size_t cap = max_new > 0 ? max_new : 1;
+        for (size_t i = 0; i < res.size(); ++i) {
+            out_lens[i] = static_cast<int32_t>(res[i].tokens.size());
+            for (size_t t = 0; t < res[i].tokens.size(); ++t) out_tokens[i * cap + t] = res[i].tokens[t];
+            out_avg_logprob[i] = res[i].logprobs.empty() ? 0.0f : res[i].logprobs[0];
+            out_finished[i] = res[i].finished ? 1 : 0;
+        }
+        return static_cast<int>(res.size());
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
+
 // ---- .tinq files through the reference's own writer / reader (quantization.cpp:120-333); harness only, the port has no file IO ----
 // Writes the model of tests/test_quantization_persistence.cpp:33-77 (three float tensors, ramps), quantized by the reference.
 int tio_tinq_write_sample(const char* path, int qtype) {

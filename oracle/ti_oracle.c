@@ -519,6 +519,172 @@ int tio_sample(const float* logits, size_t vocab, float temperature, int top_k, 
     return tok;
 }
 
+/* ---- beam search: the expansion of one candidate (:1964-2005) ---- */
+int tio_beam_expand(const float* logits, size_t vocab, float temperature, int top_k, float top_p, int beam_size, float* probs, int32_t* tokens) {
+    const size_t V = vocab;
+    float* p = (float*)malloc(V * sizeof(float));
+    spair* pairs = (spair*)malloc(V * sizeof(spair));
+    for (size_t i = 0; i < V; ++i) p[i] = temperature != 1.0f ? logits[i] / temperature : logits[i];   /* :1972-1976 */
+    float mx = p[0];                                                                                  /* softmax, :1798-1819 */
+    for (size_t i = 1; i < V; ++i) if (p[i] > mx) mx = p[i];
+    float sum = 0.0f;
+    for (size_t i = 0; i < V; ++i) { p[i] = expf(p[i] - mx); sum += p[i]; }
+    if (sum > 0.0f) for (size_t i = 0; i < V; ++i) p[i] = p[i] / sum;
+    if (top_k > 0 && (size_t)top_k < V) {                                                             /* :1982-1984, :1821-1856 */
+        for (size_t i = 0; i < V; ++i) { pairs[i].v = p[i]; pairs[i].idx = (int)i; }
+        qsort(pairs, V, sizeof(spair), spair_desc);
+        for (size_t i = (size_t)top_k; i < V; ++i) p[pairs[i].idx] = 0.0f;
+        float s = 0.0f;
+        for (size_t i = 0; i < V; ++i) s += p[i];
+        if (s > 0.0f) for (size_t i = 0; i < V; ++i) p[i] = p[i] / s;
+    }
+    if (top_p < 1.0f) {                                                                               /* :1987-1989, :1858-1909 */
+        for (size_t i = 0; i < V; ++i) { pairs[i].v = p[i]; pairs[i].idx = (int)i; }
+        qsort(pairs, V, sizeof(spair), spair_desc);
+        float cum = 0.0f;
+        size_t cutoff = V;
+        for (size_t i = 0; i < V; ++i) {
+            cum += pairs[i].v;
+            if (cum >= top_p) { cutoff = i + 1; break; }
+        }
+        for (size_t i = cutoff; i < V; ++i) p[pairs[i].idx] = 0.0f;
+        float s = 0.0f;
+        for (size_t i = 0; i < V; ++i) s += p[i];
+        if (s > 0.0f) for (size_t i = 0; i < V; ++i) p[i] = p[i] / s;
+    }
+    size_t n = 0;                                                                                     /* :1990-2005 */
+    for (size_t i = 0; i < V; ++i) if (p[i] > 0.0f) { pairs[n].v = p[i]; pairs[n].idx = (int)i; ++n; }
+    qsort(pairs, n, sizeof(spair), spair_desc);
+    int cnt = 0;
+    for (size_t i = 0; i < n && cnt < beam_size; ++i) { probs[cnt] = pairs[i].v; tokens[cnt] = pairs[i].idx; ++cnt; }
+    free(p); free(pairs);
+    return cnt;
+}
+
+typedef struct { int32_t* toks; int n; float log_prob, score; int finished; long order; } bcand;
+static int bcand_by_score(const void* a, const void* b) {      /* normalised score descending; stable through `order` */
+    const bcand* x = (const bcand*)a;
+    const bcand* y = (const bcand*)b;
+    if (x->score > y->score) return -1;
+    if (x->score < y->score) return 1;
+    return x->order < y->order ? -1 : (x->order > y->order ? 1 : 0);
+}
+static int bcand_by_logprob(const void* a, const void* b) {    /* the heap of :1921-1925: most probable first */
+    const bcand* x = (const bcand*)a;
+    const bcand* y = (const bcand*)b;
+    if (x->log_prob > y->log_prob) return -1;
+    if (x->log_prob < y->log_prob) return 1;
+    return x->order < y->order ? -1 : (x->order > y->order ? 1 : 0);
+}
+static void scratch_init(const tio_model* m, tio_scratch* s, size_t cap) {
+    const size_t H = m->hidden, I = m->inter, L = m->layers;
+    memset(s, 0, sizeof(*s));
+    s->cap = cap;
+    float** bufs[] = {&s->x, &s->n, &s->q, &s->k, &s->v, &s->a, &s->o, &s->pa, &s->f, &s->ffn, &s->tmp};
+    for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); ++i) *bufs[i] = (float*)calloc(H, sizeof(float));
+    s->up = (float*)calloc(I ? I : 1, sizeof(float));
+    s->gate = (float*)calloc(I ? I : 1, sizeof(float));
+    s->act = (float*)calloc(I ? I : 1, sizeof(float));
+    s->kc = (float**)calloc(L ? L : 1, sizeof(float*));
+    s->vc = (float**)calloc(L ? L : 1, sizeof(float*));
+    for (size_t l = 0; l < L; ++l) {
+        s->kc[l] = (float*)calloc(cap * H, sizeof(float));
+        s->vc[l] = (float*)calloc(cap * H, sizeof(float));
+    }
+}
+static void scratch_free(const tio_model* m, tio_scratch* s) {
+    float** bufs[] = {&s->x, &s->n, &s->q, &s->k, &s->v, &s->a, &s->o, &s->pa, &s->f, &s->ffn, &s->tmp};
+    for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); ++i) free(*bufs[i]);
+    free(s->up); free(s->gate); free(s->act);
+    for (size_t l = 0; l < (size_t)m->layers; ++l) { free(s->kc[l]); free(s->vc[l]); }
+    free(s->kc); free(s->vc);
+}
+
+/* logits of the last position of a whole sequence (what forward_pass(candidate.tokens) returns, :1961) */
+/* returns how many logits it wrote: the vocabulary -- or, on the literal path, what the reference TAKES for the vocabulary (below) */
+typedef size_t (*seq_logits_fn)(void* ctx, const int32_t* prompt, int n_prompt, const int32_t* toks, int n, float* logits);
+
+static int beam_search_core(seq_logits_fn fwd, void* ctx, size_t max_logits, const int32_t* prompt, int n_prompt, int max_new, int beam_size,
+                            float temperature, int top_k, float top_p, float length_penalty, int eos_token, int32_t* out_tokens,
+                            int32_t* out_lens, float* out_logprob, float* out_score, int32_t* out_finished) {
+    const int cap_tok = max_new > 0 ? max_new : 1;
+    float* logits = (float*)calloc(max_logits, sizeof(float));
+    float* eprob = (float*)malloc((size_t)beam_size * sizeof(float));
+    int32_t* etok = (int32_t*)malloc((size_t)beam_size * sizeof(int32_t));
+    const size_t maxc = (size_t)beam_size * (size_t)beam_size + 1;
+    bcand* beam = (bcand*)calloc(maxc, sizeof(bcand));
+    bcand* next = (bcand*)calloc(maxc, sizeof(bcand));
+    bcand* done = (bcand*)calloc(maxc * (size_t)(cap_tok + 1), sizeof(bcand));
+    size_t nbeam = 0, ndone = 0;
+    long order = 0;
+    beam[0].toks = (int32_t*)calloc((size_t)cap_tok, sizeof(int32_t));
+    beam[0].order = order++;
+    nbeam = 1;
+    for (int step = 0; step < max_new && nbeam > 0; ++step) {
+        qsort(beam, nbeam, sizeof(bcand), bcand_by_logprob);
+        size_t nnext = 0;
+        for (size_t c = 0; c < nbeam; ++c) {
+            const size_t V = fwd(ctx, prompt, n_prompt, beam[c].toks, beam[c].n, logits);
+            const int cnt = tio_beam_expand(logits, V, temperature, top_k, top_p, beam_size, eprob, etok);
+            for (int i = 0; i < cnt; ++i) {
+                bcand* nc = &next[nnext++];
+                *nc = beam[c];
+                nc->toks = (int32_t*)calloc((size_t)cap_tok, sizeof(int32_t));
+                memcpy(nc->toks, beam[c].toks, (size_t)beam[c].n * sizeof(int32_t));
+                nc->toks[nc->n++] = etok[i];
+                nc->log_prob = beam[c].log_prob + logf(eprob[i]);
+                nc->finished = etok[i] == eos_token || nc->n >= max_new;                                      /* :2015-2016 */
+                nc->score = nc->log_prob / powf((float)(n_prompt + nc->n), length_penalty);                  /* :2024-2026 */
+                nc->order = order++;
+            }
+        }
+        for (size_t c = 0; c < nbeam; ++c) free(beam[c].toks);
+        qsort(next, nnext, sizeof(bcand), bcand_by_score);                                                   /* :2030-2033 */
+        nbeam = 0;
+        for (size_t i = 0; i < nnext; ++i) {
+            if (i >= (size_t)beam_size) { free(next[i].toks); continue; }
+            next[i].order = order++;   /* ties from here on: the order of insertion (what a stable sort keeps) */
+            if (next[i].finished) done[ndone++] = next[i];
+            else beam[nbeam++] = next[i];
+        }
+        if (ndone >= (size_t)beam_size) break;                                                               /* :2046-2048 */
+    }
+    qsort(beam, nbeam, sizeof(bcand), bcand_by_logprob);
+    for (size_t c = 0; c < nbeam; ++c) { beam[c].finished = 1; beam[c].order = order++; done[ndone++] = beam[c]; }   /* :2051-2057 */
+    qsort(done, ndone, sizeof(bcand), bcand_by_score);                                                       /* :2060-2063 */
+    const int nres = (int)(ndone < (size_t)beam_size ? ndone : (size_t)beam_size);
+    for (int i = 0; i < nres; ++i) {
+        out_lens[i] = done[i].n;
+        for (int t = 0; t < done[i].n; ++t) out_tokens[(size_t)i * (size_t)cap_tok + (size_t)t] = done[i].toks[t];
+        if (out_logprob) out_logprob[i] = done[i].log_prob;
+        if (out_score) out_score[i] = done[i].score;
+        if (out_finished) out_finished[i] = done[i].finished;
+    }
+    for (size_t i = 0; i < ndone; ++i) free(done[i].toks);
+    free(beam); free(next); free(done); free(logits); free(eprob); free(etok);
+    return nres;
+}
+
+typedef struct { const tio_model* m; tio_scratch* s; } levelB_ctx;
+static size_t levelB_seq_logits(void* ctx, const int32_t* prompt, int n_prompt, const int32_t* toks, int n, float* logits) {
+    levelB_ctx* c = (levelB_ctx*)ctx;   /* the whole sequence again, from an empty cache */
+    const int len = n_prompt + n;
+    for (int i = 0; i < len; ++i) step_B(c->m, c->s, (size_t)i, i < n_prompt ? prompt[i] : toks[i - n_prompt], i == len - 1 ? logits : NULL);
+    return c->m->vocab;
+}
+int tio_beam_search(const tio_model* m, const int32_t* prompt, int n_prompt, int max_new, int beam_size, float temperature, int top_k,
+                    float top_p, float length_penalty, int eos_token, int32_t* out_tokens, int32_t* out_lens, float* out_logprob,
+                    float* out_score, int32_t* out_finished) {
+    if (!m || !m->lm_head || !m->tok_emb || n_prompt <= 0 || max_new < 0 || beam_size <= 0) return -1;
+    tio_scratch s;
+    scratch_init(m, &s, (size_t)n_prompt + (size_t)(max_new > 0 ? max_new : 1));
+    levelB_ctx ctx = {m, &s};
+    const int n = beam_search_core(levelB_seq_logits, &ctx, m->vocab, prompt, n_prompt, max_new, beam_size, temperature, top_k, top_p,
+                                   length_penalty, eos_token, out_tokens, out_lens, out_logprob, out_score, out_finished);
+    scratch_free(m, &s);
+    return n;
+}
+
 void tio_logprobs(const float* logits, size_t n, size_t vocab, const int32_t* tokens, float* out) {   /* :919-944 */
     for (size_t pos = 0; pos < n; ++pos) {
         const float* row = logits + pos * vocab;
@@ -688,8 +854,8 @@ static void literal_quant_inplace(float* w, size_t n, int qtype) {
     }
 }
 
-static void literal_forward(size_t T, size_t H, size_t I, size_t V, size_t L, const float* up, const float* down,
-                            const float* lm, float* last_logits) {
+static void literal_forward_rows(size_t T, size_t H, size_t I, size_t V, size_t L, const float* up, const float* down,
+                                 const float* lm, float* logits, int all_rows) {
     float* x = (float*)malloc(T * H * sizeof(float));
     float* pa = (float*)malloc(T * H * sizeof(float));
     float* u = (float*)malloc(T * I * sizeof(float));
@@ -702,8 +868,13 @@ static void literal_forward(size_t T, size_t H, size_t I, size_t V, size_t L, co
         tio_matmul(u, down, f, T, I, H);
         tio_add(pa, f, x, T * H);
     }
-    tio_matmul(x + (T - 1) * H, lm, last_logits, 1, H, V); /* only the last row is sampled, :1571-1576 */
+    if (all_rows) tio_matmul(x, lm, logits, T, H, V);      /* forward_pass returns [1, T, V] */
+    else tio_matmul(x + (T - 1) * H, lm, logits, 1, H, V); /* only the last row is sampled, :1571-1576 */
     free(x); free(pa); free(u); free(f);
+}
+static void literal_forward(size_t T, size_t H, size_t I, size_t V, size_t L, const float* up, const float* down,
+                            const float* lm, float* last_logits) {
+    literal_forward_rows(T, H, I, V, L, up, down, lm, last_logits, 0);
 }
 
 int tio_generate_literal(int vocab, int hidden, int layers, int qtype, const int32_t* prompt, int n_prompt,
@@ -734,4 +905,37 @@ int tio_generate_literal(int vocab, int hidden, int layers, int qtype, const int
     if (last_logits) memcpy(last_logits, logits, V * sizeof(float));
     free(up); free(down); free(lm); free(logits);
     return produced;
+}
+
+/* generate_beam_search on the literal benchmark model (level C): forward_pass over the whole candidate, whose logits depend on
+ * the sequence LENGTH only (token ids never reach the arithmetic).  QUIRK restated here and nowhere else:
+ * beam_search_decode takes `total_size / shape[0]` for the vocabulary (:1964-1968); forward_pass returns [1, T, V], so the
+ * reference soft-maxes over the T * V logits of ALL positions and can emit "token ids" up to T * V - 1.  The level-B
+ * restatement (tio_beam_search) and the GPU engine use the last position's V logits, which is what the comment at :1963 intends. */
+typedef struct { size_t H, I, V, L; const float *up, *down, *lm; } literal_ctx;
+static size_t literal_seq_logits(void* ctx, const int32_t* prompt, int n_prompt, const int32_t* toks, int n, float* logits) {
+    (void)prompt; (void)toks;
+    const literal_ctx* c = (const literal_ctx*)ctx;
+    const size_t T = (size_t)(n_prompt + n);
+    literal_forward_rows(T, c->H, c->I, c->V, c->L, c->up, c->down, c->lm, logits, 1);
+    return T * c->V;
+}
+int tio_beam_search_literal(int vocab, int hidden, int layers, int qtype, const int32_t* prompt, int n_prompt, int max_new, int beam_size,
+                            float temperature, int top_k, float top_p, float length_penalty, int32_t* out_tokens, int32_t* out_lens,
+                            float* out_avg_logprob, int32_t* out_finished) {
+    if (n_prompt <= 0 || max_new < 0 || beam_size <= 0) return -1;
+    const size_t V = vocab, H = hidden, L = layers, I = H * 4;
+    float* up = ramp(H * I, 0, 200, 0.02f);
+    float* down = ramp(I * H, 0, 200, 0.02f);
+    float* lm = ramp(H * V, 0, 500, 0.01f);
+    literal_quant_inplace(up, H * I, qtype);
+    literal_quant_inplace(down, I * H, qtype);
+    literal_quant_inplace(lm, H * V, qtype);
+    literal_ctx ctx = {H, I, V, L, up, down, lm};
+    float* lp = (float*)calloc((size_t)beam_size, sizeof(float));
+    const int n = beam_search_core(literal_seq_logits, &ctx, (size_t)(n_prompt + (max_new > 0 ? max_new : 1)) * V, prompt, n_prompt, max_new, beam_size, temperature, top_k, top_p, length_penalty,
+                                   2 /* InferenceConfig::eos_token_id default */, out_tokens, out_lens, lp, NULL, out_finished);
+    for (int i = 0; i < n; ++i) out_avg_logprob[i] = lp[i] / (float)out_lens[i];   /* what GenerationResult::logprobs holds, :862-865 */
+    free(lp); free(up); free(down); free(lm);
+    return n;
 }

@@ -115,6 +115,25 @@ int tio_decode_greedy_timed(const tio_model* m, const int32_t* prompt, int n_pro
  * descending, index ascending.  Returns the token; *logprob (may be NULL) = log of its final probability. */
 int tio_sample(const float* logits, size_t vocab, float temperature, int top_k, float top_p, float u, float* logprob);
 float tio_uniform(uint64_t seed, uint64_t step);
+/* ---- beam search ---------------------------------------------------------------
+ * beam_search_decode's expansion of one candidate (:1964-2005) on one row of logits: logits / temperature (:1972-1976), softmax
+ * over the vocabulary (:1798-1819), top-k on the probabilities + renormalise (:1821-1856), top-p + renormalise (:1858-1909), the
+ * beam_size most probable tokens with probability > 0 (:1990-2005); every sum sequential in the reference's order, ties restated
+ * as value descending, index ascending.  Returns the count; probs / tokens [beam_size].  (Port only.) */
+int tio_beam_expand(const float* logits, size_t vocab, float temperature, int top_k, float top_p, int beam_size, float* probs, int32_t* tokens);
+/* beam_search_decode (:1912-2069) + the result conversion of generate_beam_search (:849-857) over the level-B forward pass: every
+ * candidate's whole sequence is run through the model at every step, as the reference does (:1961).  The candidates leave the heap
+ * most probable first (:1941-1944; ties: earlier candidate), the sorts by normalised score are stable.  out_tokens
+ * [beam_size][max_new] (new tokens only), best first; returns the number of results.  (Port only.) */
+int tio_beam_search(const tio_model* m, const int32_t* prompt, int n_prompt, int max_new, int beam_size, float temperature, int top_k,
+                    float top_p, float length_penalty, int eos_token, int32_t* out_tokens, int32_t* out_lens, float* out_logprob,
+                    float* out_score, int32_t* out_finished);
+/* generate_beam_search on the literal benchmark model (level C, as tio_generate_literal): in the compiled reference this is
+ * InferenceEngine::generate_beam_search itself, which pins the expansion arithmetic and the bookkeeping of the restatement.
+ * out_avg_logprob = cumulative log-probability / new tokens (GenerationResult::logprobs, :862-865).  Both oracles. */
+int tio_beam_search_literal(int vocab, int hidden, int layers, int qtype, const int32_t* prompt, int n_prompt, int max_new, int beam_size,
+                            float temperature, int top_k, float top_p, float length_penalty, int32_t* out_tokens, int32_t* out_lens,
+                            float* out_avg_logprob, int32_t* out_finished);
 /* compute_logprobs (:873-954) on precomputed logits [n, vocab]: out[pos] = logit[token] - max - log(sum exp(logit - max)),
  * -20 for a token id outside the vocabulary */
 void tio_logprobs(const float* logits, size_t n, size_t vocab, const int32_t* tokens, float* out);

@@ -265,6 +265,29 @@ static void test_engine_gpu() {
             CHECK(rb.size() == 3);
             for (size_t b = 0; b < ragged.size(); ++b) CHECK(rb[b].tokens == eng.generate(ragged[b], 4).tokens);
         }
+        {   // beam search (generate_beam_search :830-871): new tokens only, best first; beam 1 with top_k 1 walks the greedy path
+            CHECK_THROWS(eng.generate_beam_search(prompt, 4, 0), std::runtime_error);
+            model::InferenceConfig bc = cfg;
+            bc.top_k = 1;
+            bc.eos_token_id = -1;
+            eng.set_config(bc);
+            auto one = eng.generate_beam_search(prompt, 6, 1, true);
+            model::GenerationResult greedy = eng.generate(prompt, 6);
+            CHECK(one.size() == 1 && one[0].tokens.size() == 6 && one[0].finished);
+            if (greedy.tokens.size() == prompt.size() + 6)   // (generate() itself still stops on token 2)
+                CHECK(std::equal(one[0].tokens.begin(), one[0].tokens.end(), greedy.tokens.begin() + prompt.size()));
+            CHECK(one[0].logprobs.size() == 6 && one[0].logprobs[0] == 0.0f);   // the only survivor of top_k = 1 has probability 1
+            bc.top_k = 50;
+            bc.top_p = 0.95f;
+            eng.set_config(bc);
+            auto beams = eng.generate_beam_search(prompt, 6, 4, true);
+            CHECK(beams.size() == 4);
+            for (const auto& r : beams) {
+                CHECK(r.tokens.size() == 6 && r.finished && r.logprobs.size() == 6);
+                for (float lp : r.logprobs) CHECK(lp <= 0.f && lp == r.logprobs[0]);
+            }
+            eng.set_config(cfg);
+        }
         auto batch = eng.generate_batch({prompt, {3, 4}}, 3);
         CHECK(batch.size() == 2);
         CHECK(eng.memory_usage() > 0 && !eng.performance_stats().empty());

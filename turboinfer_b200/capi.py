@@ -89,6 +89,9 @@ SYMBOLS = {
     "ti_b200_generate_sampled": (C.c_int, [C.c_uint64, _i32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_uint64, C.c_int32, _i32, _i32, _f, _f]),
     "ti_b200_compute_logprobs": (C.c_int, [C.c_uint64, _i32, C.c_int32, _f]),
     "ti_b200_generate_batch_ragged": (C.c_int, [C.c_uint64, _i32, _i32, C.c_int32, C.c_int32, C.c_int32, _i32, _f]),
+    "ti_b200_beam_search": (C.c_int, [C.c_uint64, _i32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_int32,
+                                      _i32, _i32, _f, _f, _i32, _i32]),
+    "ti_b200_beam_expand": (C.c_int, [_f, C.c_size_t, C.c_size_t, C.c_float, C.c_int32, C.c_float, C.c_int32, _f, _i32, _i32]),
     "ti_b200_model_last_prefill_ms": (C.c_int, [C.c_uint64, _f]),
     "ti_b200_launch_count": (C.c_int, [C.POINTER(C.c_uint64)]),
     "ti_b200_bench_gemv": (C.c_int, [C.POINTER(C.c_uint64), C.c_size_t, C.c_size_t, _f]),
@@ -386,6 +389,18 @@ class _Ops:
                                           tok.ctypes.data_as(_i32), _fp(lp)))
         return tok, lp
 
+    def beam_expand(self, logits, beam_size: int, temperature: float = 1.0, top_k: int = 50, top_p: float = 0.9):
+        """beam_search_decode's expansion (:1964-2005) on [rows, vocab] logits -> per row a list of (probability, token), best first."""
+        lg = _c(logits)
+        lg = lg.reshape(-1, lg.shape[-1])
+        rows = lg.shape[0]
+        pr = np.zeros((rows, beam_size), dtype=np.float32)
+        tk = np.zeros((rows, beam_size), dtype=np.int32)
+        cn = np.zeros(rows, dtype=np.int32)
+        _ck(_need().ti_b200_beam_expand(_fp(lg.reshape(-1)), rows, lg.shape[1], temperature, top_k, top_p, beam_size, _fp(pr.reshape(-1)),
+                                        tk.ctypes.data_as(_i32), cn.ctypes.data_as(_i32)))
+        return [[(float(pr[r, i]), int(tk[r, i])) for i in range(cn[r])] for r in range(rows)]
+
     def attention_decode(self, q, k, v, num_heads: int = 1) -> np.ndarray:
         q, k, v = _c(q), _c(k), _c(v)
         B, _, H = q.shape
@@ -583,6 +598,24 @@ class Model:
         _ck(lib().ti_b200_generate_batch_ragged(self.handle, flat.ctypes.data_as(_i32), lens.ctypes.data_as(_i32), B, mx, n_new,
                                                 out.ctypes.data_as(_i32), C.byref(ms)))
         return out, ms.value
+
+    def beam_search(self, prompt, max_new: int, beam_size: int = 4, *, temperature: float = 1.0, top_k: int = 50, top_p: float = 0.9,
+                    length_penalty: float = 1.0, eos_token: int = 2):
+        """generate_beam_search (:830-871): list of dicts {tokens (new only), log_prob, score, finished}, best score first."""
+        p = np.ascontiguousarray(prompt, dtype=np.int32)
+        out = np.zeros((beam_size, max(max_new, 1)), dtype=np.int32)
+        lens = np.zeros(beam_size, dtype=np.int32)
+        lp = np.zeros(beam_size, dtype=np.float32)
+        sc = np.zeros(beam_size, dtype=np.float32)
+        fin = np.zeros(beam_size, dtype=np.int32)
+        n = C.c_int32()
+        _ck(lib().ti_b200_beam_search(self.handle, p.ctypes.data_as(_i32), p.size, max_new, beam_size, temperature, top_k, top_p, length_penalty,
+                                      eos_token, out.ctypes.data_as(_i32), lens.ctypes.data_as(_i32), _fp(lp), _fp(sc), fin.ctypes.data_as(_i32),
+                                      C.byref(n)))
+        if max_new > 0:
+            out = out.reshape(beam_size, max_new)
+        return [dict(tokens=[int(t) for t in out[i, : lens[i]]], log_prob=float(lp[i]), score=float(sc[i]), finished=bool(fin[i]))
+                for i in range(n.value)]
 
     def free(self) -> None:
         if self.handle:

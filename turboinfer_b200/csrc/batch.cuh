@@ -174,6 +174,16 @@ __global__ void batch_feed_kernel(const int* prompts, const int* lens, const int
     if (s < lens[b]) tokens[b] = prompts[(size_t)s * B + b];
 }
 
+// Beam search forks a sequence by copying its page TABLE; only the last, partly filled page of a shared prefix has to be copied
+// before two beams append to it.  pairs[2 * i] = source page, pairs[2 * i + 1] = destination page; grid (pairs, layers, 2: K / V),
+// `elems` = the filled part of the page (tokens * row width), a multiple of 4.
+__global__ void kv_pages_copy_kernel(float* const* k_pools, float* const* v_pools, const int* pairs, size_t page_elems, size_t elems) {
+    float* pool = (blockIdx.z == 0 ? k_pools : v_pools)[blockIdx.y];
+    const float4* src = reinterpret_cast<const float4*>(pool + (size_t)pairs[2 * blockIdx.x] * page_elems);
+    float4* dst = reinterpret_cast<float4*>(pool + (size_t)pairs[2 * blockIdx.x + 1] * page_elems);
+    for (size_t i = threadIdx.x; i < elems / 4; i += blockDim.x) dst[i] = src[i];
+}
+
 // end of a batched step: every sequence is one token longer; `sampled` steps also advance the output column
 __global__ void batch_advance_kernel(int* pos_step, int sampled) {
     pos_step[0] += 1;

@@ -320,6 +320,23 @@ struct BatchState {
     ~BatchState() { drop_graphs(); }
 };
 
+// beam search (generate_beam_search, :830-871 / :1912-2069) on the lockstep engine: a beam is a row of the batch, its KV cache a
+// page table into one shared pool -- forking a beam copies the table (reference counts per page), not the cache
+struct BeamState {
+    BatchState bs;                       // rows = beams; bs.k / bs.v hold `pool_pages` pages per layer
+    int beam = 0, pool_pages = 0;
+    DevBuf<float> cand_prob;             // [beam][beam] expansion of every row
+    DevBuf<int> cand_tok, cand_cnt;
+    DevBuf<float*> k_ptrs, v_ptrs;       // per-layer pool addresses for the page copy
+    DevBuf<int> copy_pairs;              // [beam][2]
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};   // forward without / with lm_head + expansion
+    unsigned int cap_scratch = 0xFFFFFFFFu;
+    float cap_temperature = 0.f, cap_top_p = 0.f;
+    int cap_top_k = -1;
+    void drop_graphs() { for (auto& g : graph) if (g) { cudaGraphExecDestroy(g); g = nullptr; } }
+    ~BeamState() { drop_graphs(); }
+};
+
 struct Model {
     ti_model_config cfg{};
     std::vector<Layer> layers;
@@ -359,6 +376,7 @@ struct Model {
     bool pf_small_layout = false;       // pf_planes currently holds the 32-row GEMM's tile images (batch.cuh) rather than [3][m_pad][k_pad]
     DevBuf<int> pf_tokens;
     std::unique_ptr<struct BatchState> batch;   // batched decode (generate_batch): per-sequence KV pages, step graphs
+    std::unique_ptr<struct BeamState> beams;    // beam search: rows of the lockstep engine over a shared, reference-counted page pool
     int tp = 1, tp_rank = 0;   // tensor-parallel degree / rank of this model
     DevBuf<float> ar_tmp;      // [H] partial output of a row-parallel GEMV, all-reduced in place
     // fused tensor-parallel engine: this rank's exchange block {barrier words, partial buffers 0 / 1 [tp][H]} and the
@@ -1286,15 +1304,15 @@ int batch_allreduce_add(Model& m, BatchState& bs, int B) {
     return 0;
 }
 
-int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
-    const int B = bs.B, H = m.cfg.hidden, V = m.cfg.vocab;
+// one lockstep forward pass of B sequences: bs.tokens at position bs.pos_step[0] -> (lm_head) bs.logits
+int batch_forward(Model& m, BatchState& bs, bool lm_head) {
+    const int B = bs.B, H = m.cfg.hidden;
     const int Hl = H / m.tp;   // tensor parallel: this rank's heads (q / k / v / attention width) -- SURVEY.md 8e
     const int m_pad = (B + kGemmBM - 1) / kGemmBM * kGemmBM;
     const int rope_dim = m.cfg.rope_mode == 1 ? H / m.cfg.heads : 0;
     const bool tp = m.tp > 1;
-    batch_feed_kernel<<<(B + 127) / 128, 128, 0, g_stream>>>(bs.prompts.p, bs.lens.p, bs.pos_step.p, B, bs.tokens.p);
     embed_rows_kernel<<<B, 256, 0, g_stream>>>(m.tok_emb.p, bs.tokens.p, m.pf_x.p, H);
-    g_launches += 2;
+    ++g_launches;
     for (size_t l = 0; l < m.layers.size(); ++l) {
         Layer& ly = m.layers[l];
         const int Il = ly.down->L.K;   // this rank's share of the intermediate width
@@ -1351,9 +1369,20 @@ int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
             TRY(pf_gemm(m, *ly.down, B, m_pad, m.pf_x.p, m.pf_x.p));
         }
     }
-    if (sample) {
+    if (lm_head) {
         TRY(batch_digits(m, m.pf_x.p, nullptr, m.out_norm.p, B, H, m_pad, m.lm_head->k_pad));
         TRY(pf_gemm(m, *m.lm_head, B, m_pad, bs.logits.p, nullptr));
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
+    const int B = bs.B, V = m.cfg.vocab;
+    batch_feed_kernel<<<(B + 127) / 128, 128, 0, g_stream>>>(bs.prompts.p, bs.lens.p, bs.pos_step.p, B, bs.tokens.p);
+    ++g_launches;
+    TRY(batch_forward(m, bs, sample));
+    if (sample) {
         argmax_rows_kernel<<<B, 1024, 0, g_stream>>>(bs.logits.p, V, bs.tokens.p, bs.out.p, out_stride, bs.pos_step.p, bs.lens.p);
         ++g_launches;
     }
@@ -2597,6 +2626,20 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
 // tokens each.  The reference loops over generate(); here the sequences advance in lockstep so that the weights are read
 // once per step for all of them (tensor-core GEMM path).  out_tokens: [batch][n_new]; logits_last (optional): [batch][vocab]
 // of the last step; decode_ms (optional): CUDA-event time of the n_new - 1 decode steps after the prompt.
+// every kernel of the lockstep step asks for the same L1 / shared-memory split as the GEMM (which needs nearly all of it): a
+// kernel that wants a different carve-out than its predecessor makes the SMs reconfigure before it can start
+static int batch_carveout() {
+    if (g_batch_carveout_done) return 0;
+    const void* fns[] = {(const void*)gemm_i8_tc_small_kernel, (const void*)gemm_i8_tc_kernel, (const void*)rmsnorm_digits_small_kernel,
+                         (const void*)rmsnorm_digits_kernel, (const void*)rope_kv_batch_kernel, (const void*)attn_partial_kernel,
+                         (const void*)attn_combine_kernel, (const void*)argmax_rows_kernel, (const void*)batch_advance_kernel,
+                         (const void*)embed_rows_kernel, (const void*)swiglu_rows_kernel, (const void*)relu_rows_kernel, (const void*)batch_feed_kernel,
+                         (const void*)beam_expand_kernel, (const void*)kv_pages_copy_kernel};
+    for (const void* f : fns) CK(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    g_batch_carveout_done = true;
+    return 0;
+}
+
 static int generate_batch_impl(ti_model_t h, const int32_t* prompts, const int32_t* lens, int32_t batch, int32_t max_len, int32_t n_new,
                                int32_t* out_tokens, float* logits_last, float* decode_ms) {
     TRY(need_init());
@@ -2617,16 +2660,7 @@ static int generate_batch_impl(ti_model_t h, const int32_t* prompts, const int32
     }
     const int total = max_len + n_new - 1;   // the longest prompt decides how many lockstep steps run
     if (total > m.cfg.max_seq) return fail("KV cache overflow: sequence too long");  // :100-102
-    if (!g_batch_carveout_done) {
-        // every kernel of the step asks for the same L1 / shared-memory split as the GEMM (which needs nearly all of it):
-        // a kernel that wants a different carve-out than its predecessor makes the SMs reconfigure before it can start
-        const void* fns[] = {(const void*)gemm_i8_tc_small_kernel, (const void*)gemm_i8_tc_kernel, (const void*)rmsnorm_digits_small_kernel,
-                             (const void*)rmsnorm_digits_kernel, (const void*)rope_kv_batch_kernel, (const void*)attn_partial_kernel,
-                             (const void*)attn_combine_kernel, (const void*)argmax_rows_kernel, (const void*)batch_advance_kernel,
-                             (const void*)embed_rows_kernel, (const void*)swiglu_rows_kernel, (const void*)relu_rows_kernel, (const void*)batch_feed_kernel};
-        for (const void* f : fns) CK(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        g_batch_carveout_done = true;
-    }
+    TRY(batch_carveout());
     // everything that allocates or launches set-up kernels happens before the step graphs are captured
     for (auto& ly : m.layers)
         for (QWeight* w : {ly.qkv.get(), ly.o.get(), ly.gateup.get(), ly.down.get()}) TRY(ensure_kmajor(*w));
@@ -2728,6 +2762,279 @@ int ti_b200_generate_batch_ragged(ti_model_t h, const int32_t* prompts, const in
                                   int32_t* out_tokens, float* decode_ms) {
     if (batch <= 0 || !lens) return fail("batch must be >= 1");
     return generate_batch_impl(h, prompts, lens, batch, max_len, n_new, out_tokens, nullptr, decode_ms);
+}
+
+// generate_beam_search (:830-871) / beam_search_decode (:1912-2069) on the cached, lockstep engine.  The reference runs a full
+// forward_pass over every candidate's whole sequence at every step (:1961, no cache); here a candidate is a row of the batched
+// step and owns a page TABLE into one shared K/V pool: the prompt is cached once, a fork copies the table and bumps the pages'
+// reference counts, and only a partly filled last page is copied when two beams are about to append to it.  The expansion
+// (softmax, top-k / top-p on probabilities, the beam best tokens) runs on the device next to the logits; the host keeps the
+// reference's bookkeeping (cumulative log-probability, length-normalised score, keep the beam best, early stop) on
+// beam * beam pairs per step.  Where the reference's order is unspecified (ties in std::sort / the heap) the earlier candidate wins.
+// out_tokens [beam_size][max_new] (new tokens only, like GenerationResult of :849-857), results best first.
+int ti_b200_beam_search(ti_model_t h, const int32_t* prompt, int32_t n_prompt, int32_t max_new, int32_t beam_size, float temperature, int32_t top_k,
+                        float top_p, float length_penalty, int32_t eos_token, int32_t* out_tokens, int32_t* out_lens, float* out_logprob,
+                        float* out_score, int32_t* out_finished, int32_t* n_results) {
+    TRY(need_init());
+    Model* mp = get_model(h);
+    if (!mp || !mp->finalized) return fail("invalid or unfinalized model handle");
+    Model& m = *mp;
+    if (beam_size <= 0) return fail("Beam size must be greater than 0");   // :836-838
+    if (beam_size > kBeamMax) return fail("beam_size above %d is not supported", kBeamMax);
+    if (n_prompt <= 0) return fail("Input tokens cannot be empty");
+    if (max_new < 0) return fail("max_new must be >= 0");
+    if (!(temperature > 0.0f)) return fail("Temperature must be positive");
+    if (!out_tokens || !out_lens || !n_results) return fail("null argument");
+    if (m.tp > 1) return fail("beam search runs on a single-GPU model");
+    if (!batch_eligible(m)) return fail("beam search needs a complete, non-literal model (q/k/v/o, up/down, lm_head; rope per head or off)");
+    const int B = beam_size, V = m.cfg.vocab, H = m.cfg.hidden, pt = m.page_tokens;
+    for (int i = 0; i < n_prompt; ++i)
+        if (prompt[i] < 0 || prompt[i] >= V) return fail("token id %d out of range", prompt[i]);
+    struct Cand { std::vector<int> toks; float log_prob = 0.f, score = 0.f; bool finished = false; int row = -1; };
+    auto emit = [&](std::vector<Cand>& done) {
+        std::stable_sort(done.begin(), done.end(), [](const Cand& a, const Cand& b) { return a.score > b.score; });   // :2060-2063
+        const int n = (int)std::min<size_t>(done.size(), (size_t)B);
+        for (int i = 0; i < n; ++i) {
+            out_lens[i] = (int)done[i].toks.size();
+            for (size_t t = 0; t < done[i].toks.size(); ++t) out_tokens[(size_t)i * max_new + t] = done[i].toks[t];
+            if (out_logprob) out_logprob[i] = done[i].log_prob;
+            if (out_score) out_score[i] = done[i].score;
+            if (out_finished) out_finished[i] = done[i].finished ? 1 : 0;
+        }
+        *n_results = n;
+    };
+    if (max_new == 0) {   // the loop of :1938 does not run: the initial candidate comes back as the only result
+        std::vector<Cand> done(1);
+        done[0].finished = true;
+        emit(done);
+        return 0;
+    }
+    const int total = n_prompt + max_new - 1;   // the last token of a sequence is never fed back
+    if (total > m.cfg.max_seq) return fail("KV cache overflow: sequence too long");
+    TRY(batch_carveout());
+    for (auto& ly : m.layers)
+        for (QWeight* w : {ly.qkv.get(), ly.o.get(), ly.gateup.get(), ly.down.get()}) TRY(ensure_kmajor(*w));
+    TRY(ensure_kmajor(*m.lm_head));
+    TRY(ensure_pf_scratch(m, B));
+    const int pages = (total + pt - 1) / pt;
+    const size_t page_elems = (size_t)pt * H;
+    if (!m.beams || m.beams->beam != B || m.beams->bs.pages_per_seq < pages) {
+        m.beams.reset(new BeamState());
+        BeamState& st = *m.beams;
+        BatchState& bs = st.bs;
+        st.beam = B;
+        st.pool_pages = B * pages + B;   // worst case every beam owns all its pages; + one scratch page per idle row
+        bs.B = B;
+        bs.pages_per_seq = pages;
+        bs.max_splits = std::max(1, std::min(m.max_splits, (2 * g_num_sms) / std::max(1, B * m.attn_heads)));
+        bs.k.resize(m.layers.size());
+        bs.v.resize(m.layers.size());
+        std::vector<float*> kp(m.layers.size()), vp(m.layers.size());
+        for (size_t l = 0; l < m.layers.size(); ++l) {
+            TRY(bs.k[l].alloc((size_t)st.pool_pages * page_elems));
+            TRY(bs.v[l].alloc((size_t)st.pool_pages * page_elems));
+            // idle rows read their scratch page through the attention: keep it finite
+            CK(cudaMemsetAsync(bs.k[l].p + (size_t)B * pages * page_elems, 0, (size_t)B * page_elems * sizeof(float), g_stream));
+            CK(cudaMemsetAsync(bs.v[l].p + (size_t)B * pages * page_elems, 0, (size_t)B * page_elems * sizeof(float), g_stream));
+            kp[l] = bs.k[l].p;
+            vp[l] = bs.v[l].p;
+        }
+        TRY(st.k_ptrs.alloc(std::max<size_t>(kp.size(), 1)));
+        TRY(st.v_ptrs.alloc(std::max<size_t>(vp.size(), 1)));
+        CK(cudaMemcpyAsync(st.k_ptrs.p, kp.data(), kp.size() * sizeof(float*), cudaMemcpyHostToDevice, g_stream));
+        CK(cudaMemcpyAsync(st.v_ptrs.p, vp.data(), vp.size() * sizeof(float*), cudaMemcpyHostToDevice, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        TRY(bs.tables.alloc((size_t)B * pages));
+        TRY(bs.tokens.alloc(B));
+        TRY(bs.pos_step.alloc(2));
+        TRY(bs.part_o.alloc((size_t)B * m.attn_heads * bs.max_splits * m.attn_dim));
+        TRY(bs.part_ml.alloc((size_t)B * m.attn_heads * bs.max_splits * 2));
+        TRY(bs.logits.alloc((size_t)B * V));
+        TRY(st.cand_prob.alloc((size_t)B * B));
+        TRY(st.cand_tok.alloc((size_t)B * B));
+        TRY(st.cand_cnt.alloc(B));
+        TRY(st.copy_pairs.alloc((size_t)2 * B));
+    }
+    BeamState& st = *m.beams;
+    BatchState& bs = st.bs;
+    const int ppr = bs.pages_per_seq;   // row stride of the page tables
+    if (st.cap_scratch != m.pf_gen || st.cap_temperature != temperature || st.cap_top_k != top_k || st.cap_top_p != top_p) {
+        st.drop_graphs();
+        st.cap_scratch = m.pf_gen;
+        st.cap_temperature = temperature;
+        st.cap_top_k = top_k;
+        st.cap_top_p = top_p;
+    }
+    CK(cudaMemsetAsync(bs.pos_step.p, 0, 2 * sizeof(int), g_stream));
+    auto run = [&](bool expand) -> int {
+        cudaGraphExec_t& ge = st.graph[expand ? 1 : 0];
+        if (!ge) {
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+            int rc = batch_forward(m, bs, expand);
+            if (rc == 0 && expand) {
+                BeamExpandArgs ea{};
+                ea.logits = bs.logits.p;
+                ea.V = V;
+                ea.ld = V;
+                ea.temperature = temperature;
+                ea.top_k = top_k;
+                ea.top_p = top_p;
+                ea.beam = B;
+                ea.cand_prob = st.cand_prob.p;
+                ea.cand_tok = st.cand_tok.p;
+                ea.cand_cnt = st.cand_cnt.p;
+                beam_expand_kernel<<<B, kSampleThreads, 0, g_stream>>>(ea);
+                ++g_launches;
+            }
+            batch_advance_kernel<<<1, 1, 0, g_stream>>>(bs.pos_step.p, 0);
+            ++g_launches;
+            const cudaError_t e = cudaStreamEndCapture(g_stream, &graph);
+            if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess) return fail("cudaStreamEndCapture: %s", cudaGetErrorString(e));
+            CK(cudaGraphInstantiate(&ge, graph, 0));
+            cudaGraphDestroy(graph);
+        }
+        CK(cudaGraphLaunch(ge, g_stream));
+        return 0;
+    };
+    // ---- page bookkeeping (host): reference counts, a free list, one table per row ----
+    const int data_pages = B * pages;
+    std::vector<int> ref(data_pages, 0), free_pages;
+    for (int p = data_pages - 1; p >= 0; --p) free_pages.push_back(p);
+    std::vector<int> tab((size_t)B * ppr);
+    for (int r = 0; r < B; ++r)
+        for (int j = 0; j < ppr; ++j) tab[(size_t)r * ppr + j] = data_pages + r;   // idle: everything on the row's scratch page
+    std::vector<int> pairs;
+    auto alloc_page = [&]() { const int p = free_pages.back(); free_pages.pop_back(); ref[p] = 1; return p; };
+    auto unref = [&](int p) { if (p < data_pages && --ref[p] == 0) free_pages.push_back(p); };
+    // every active row must own the page position t falls into before the step appends to it
+    auto prepare_append = [&](int nrows, int t) {
+        const int j = t / pt;
+        for (int r = 0; r < nrows; ++r) {
+            int& e = tab[(size_t)r * ppr + j];
+            if (t % pt == 0) {
+                e = alloc_page();
+            } else if (ref[e] > 1) {   // shared with another beam: copy the filled part, then append privately
+                const int fresh = alloc_page();
+                pairs.push_back(e);
+                pairs.push_back(fresh);
+                --ref[e];
+                e = fresh;
+            }
+        }
+    };
+    auto push_step = [&](const std::vector<int>& feed, int t, bool expand) -> int {
+        CK(cudaMemcpyAsync(bs.tables.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+        if (!pairs.empty()) {
+            CK(cudaMemcpyAsync(st.copy_pairs.p, pairs.data(), pairs.size() * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+            kv_pages_copy_kernel<<<dim3((unsigned)(pairs.size() / 2), (unsigned)std::max<size_t>(m.layers.size(), 1), 2), 256, 0, g_stream>>>(
+                st.k_ptrs.p, st.v_ptrs.p, st.copy_pairs.p, page_elems, (size_t)(t % pt) * H);
+            ++g_launches;
+            CK(cudaGetLastError());
+        }
+        CK(cudaMemcpyAsync(bs.tokens.p, feed.data(), B * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+        TRY(run(expand));
+        CK(cudaStreamSynchronize(g_stream));   // tab / pairs / feed are reused by the next step
+        pairs.clear();
+        return 0;
+    };
+    // ---- the prompt: cached ONCE, by row 0 (the other rows idle on their scratch pages) ----
+    std::vector<int> feed(B, 0);
+    for (int t = 0; t < n_prompt; ++t) {
+        prepare_append(1, t);
+        std::fill(feed.begin(), feed.end(), prompt[t]);
+        TRY(push_step(feed, t, t == n_prompt - 1));
+    }
+    std::vector<Cand> active(1), done;
+    active[0].row = 0;
+    std::vector<float> cprob((size_t)B * B);
+    std::vector<int> ctok((size_t)B * B), ccnt(B);
+    for (int step = 0; step < max_new && !active.empty(); ++step) {
+        CK(cudaMemcpyAsync(cprob.data(), st.cand_prob.p, cprob.size() * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaMemcpyAsync(ctok.data(), st.cand_tok.p, ctok.size() * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaMemcpyAsync(ccnt.data(), st.cand_cnt.p, B * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        std::vector<Cand> next;
+        for (const Cand& c : active) {   // most probable candidate first (the heap order of :1941-1944)
+            const int cnt = std::min(ccnt[c.row], B);
+            for (int i = 0; i < cnt; ++i) {
+                const float p = cprob[(size_t)c.row * B + i];
+                if (!(p > 0.0f)) continue;
+                Cand nc = c;
+                nc.toks.push_back(ctok[(size_t)c.row * B + i]);
+                nc.log_prob = c.log_prob + std::log(p);
+                nc.finished = nc.toks.back() == eos_token || (int)nc.toks.size() >= max_new;   // :2015-2016
+                const float penalty = std::pow((float)(n_prompt + (int)nc.toks.size()), length_penalty);   // :2024-2026
+                nc.score = nc.log_prob / penalty;
+                next.push_back(std::move(nc));
+            }
+        }
+        std::stable_sort(next.begin(), next.end(), [](const Cand& a, const Cand& b) { return a.score > b.score; });   // :2030-2033
+        std::vector<Cand> kept;
+        for (size_t i = 0; i < next.size() && i < (size_t)B; ++i) {
+            if (next[i].finished) done.push_back(std::move(next[i]));
+            else kept.push_back(std::move(next[i]));
+        }
+        std::stable_sort(kept.begin(), kept.end(), [](const Cand& a, const Cand& b) { return a.log_prob > b.log_prob; });
+        if (done.size() >= (size_t)B || kept.empty()) { active = std::move(kept); break; }   // :2046-2048
+        // ---- fork: row r of the next step continues kept[r]; its table is its parent's ----
+        const int t = n_prompt + step;   // tokens in every active cache; the step below appends position t
+        const int used = (t + pt - 1) / pt;
+        std::vector<int> ntab(tab.size());
+        for (int r = 0; r < B; ++r)
+            for (int j = 0; j < ppr; ++j) ntab[(size_t)r * ppr + j] = data_pages + r;
+        for (size_t r = 0; r < kept.size(); ++r)
+            for (int j = 0; j < used; ++j) {
+                const int p = tab[(size_t)kept[r].row * ppr + j];
+                ntab[r * ppr + j] = p;
+                ++ref[p];
+            }
+        for (const Cand& c : active)
+            for (int j = 0; j < used; ++j) unref(tab[(size_t)c.row * ppr + j]);
+        tab.swap(ntab);
+        std::fill(feed.begin(), feed.end(), 0);
+        for (size_t r = 0; r < kept.size(); ++r) { kept[r].row = (int)r; feed[r] = kept[r].toks.back(); }
+        active = std::move(kept);
+        prepare_append((int)active.size(), t);
+        TRY(push_step(feed, t, true));
+    }
+    for (Cand& c : active) { c.finished = true; done.push_back(std::move(c)); }   // :2051-2057
+    emit(done);
+    return 0;
+}
+
+int ti_b200_beam_expand(const float* logits_host, size_t rows, size_t vocab, float temperature, int32_t top_k, float top_p, int32_t beam_size,
+                        float* probs_out, int32_t* tokens_out, int32_t* counts_out) {
+    TRY(need_init());
+    if (rows == 0 || vocab == 0) return fail("empty logits");
+    if (beam_size <= 0 || beam_size > kBeamMax) return fail("beam_size must be in [1, %d]", kBeamMax);
+    if (!(temperature > 0.0f)) return fail("Temperature must be positive");
+    DevBuf<float> lg, pr;
+    DevBuf<int> tk, cn;
+    TRY(upload(lg, logits_host, rows * vocab));
+    TRY(pr.alloc(rows * beam_size));
+    TRY(tk.alloc(rows * beam_size));
+    TRY(cn.alloc(rows));
+    BeamExpandArgs ea{};
+    ea.logits = lg.p;
+    ea.V = (int)vocab;
+    ea.ld = (int)vocab;
+    ea.temperature = temperature;
+    ea.top_k = top_k;
+    ea.top_p = top_p;
+    ea.beam = beam_size;
+    ea.cand_prob = pr.p;
+    ea.cand_tok = tk.p;
+    ea.cand_cnt = cn.p;
+    beam_expand_kernel<<<(unsigned)rows, kSampleThreads, 0, g_stream>>>(ea);
+    ++g_launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(probs_out, pr.p, rows * beam_size * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaMemcpyAsync(tokens_out, tk.p, rows * beam_size * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaMemcpyAsync(counts_out, cn.p, rows * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
 }
 
 int ti_b200_sample_logits(const float* logits_host, size_t rows, size_t vocab, float temperature, int32_t top_k, float top_p, uint64_t seed,

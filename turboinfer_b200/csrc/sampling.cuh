@@ -107,6 +107,40 @@ __device__ __forceinline__ float block_exscan_f(float v, float* wsum, float* tot
     return r;
 }
 
+// Radix select over the keys of the block's elements (thread t owns [i0, i1)): key of the `need`-th largest value, 4 passes of 8
+// bits from the top.  Returns the key; *need_eq = how many of the elements EQUAL to it belong to the top `need` (the lowest indices).
+template <typename KeyFn>
+__device__ __forceinline__ uint32_t radix_select_key(KeyFn key_of, int i0, int i1, int need, int* hist, int* s_sel, int* s_need, int* need_eq) {
+    const int tid = threadIdx.x;
+    uint32_t prefix = 0, mask = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int b = tid; b < 256; b += kSampleThreads) hist[b] = 0;
+        __syncthreads();
+        for (int i = i0; i < i1; ++i) {
+            const uint32_t key = key_of(i);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0, b = 255;
+            for (; b > 0; --b) {
+                if (acc + hist[b] >= need) break;
+                acc += hist[b];
+            }
+            *s_sel = b;
+            *s_need = need - acc;
+        }
+        __syncthreads();
+        prefix |= (uint32_t)*s_sel << shift;
+        mask |= 255u << shift;
+        need = *s_need;
+        __syncthreads();
+    }
+    *need_eq = need;
+    return prefix;
+}
+
 __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs a) {
     __shared__ int hist[256];
     __shared__ float fhist[256];
@@ -114,7 +148,6 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs
     __shared__ float wsumf[32];
     __shared__ int s_tot, s_sel, s_need, s_token;
     __shared__ float s_ftot, s_max, s_sum, s_lp;
-    __shared__ uint32_t s_prefix;
     __shared__ int sidx[kTopKMax];
     __shared__ float sval[kTopKMax];      // scaled logit, then probability
     __shared__ int sord[kTopKMax];        // positions sorted by (probability desc, index asc)
@@ -131,35 +164,9 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs
     const bool exact = use_topk && a.top_k <= kTopKMax;
 
     if (exact) {
-        // ---- radix select of the k-th largest key (4 passes of 8 bits, most significant first) ----
-        const int k = a.top_k;
-        uint32_t prefix = 0, mask = 0;
-        int need = k;   // how many of the elements matching the prefix are still to be taken from the top
-        for (int pass = 0; pass < 4; ++pass) {
-            const int shift = 24 - 8 * pass;
-            for (int b = tid; b < 256; b += kSampleThreads) hist[b] = 0;
-            __syncthreads();
-            for (int i = i0; i < i1; ++i) {
-                const uint32_t key = desc_key(val(i));
-                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int acc = 0, b = 255;
-                for (; b > 0; --b) {
-                    if (acc + hist[b] >= need) break;
-                    acc += hist[b];
-                }
-                s_sel = b;
-                s_need = need - acc;
-            }
-            __syncthreads();
-            prefix |= (uint32_t)s_sel << shift;
-            mask |= 255u << shift;
-            need = s_need;
-            __syncthreads();
-        }
-        const uint32_t tau = prefix;   // key of the k-th largest value; `need` of the elements equal to it survive (lowest indices)
+        // ---- radix select of the k-th largest key ----
+        int need = 0;   // how many of the elements equal to that key survive (lowest indices)
+        const uint32_t tau = radix_select_key([&](int i) { return desc_key(val(i)); }, i0, i1, a.top_k, hist, &s_sel, &s_need, &need);
         // ---- gather the survivors in index order ----
         int cgt = 0, ceq = 0;
         for (int i = i0; i < i1; ++i) {
@@ -258,33 +265,8 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs
         // (a top_k > 1024 is applied as a key threshold first, found with the same radix select on counts)
         uint32_t kth = 0;   // survivors: key >= kth
         if (use_topk) {
-            uint32_t prefix = 0, mask = 0;
-            int need = a.top_k;
-            for (int pass = 0; pass < 4; ++pass) {
-                const int shift = 24 - 8 * pass;
-                for (int b = tid; b < 256; b += kSampleThreads) hist[b] = 0;
-                __syncthreads();
-                for (int i = i0; i < i1; ++i) {
-                    const uint32_t key = desc_key(val(i));
-                    if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    int acc = 0, b = 255;
-                    for (; b > 0; --b) {
-                        if (acc + hist[b] >= need) break;
-                        acc += hist[b];
-                    }
-                    s_sel = b;
-                    s_need = need - acc;
-                }
-                __syncthreads();
-                prefix |= (uint32_t)s_sel << shift;
-                mask |= 255u << shift;
-                need = s_need;
-                __syncthreads();
-            }
-            kth = prefix;
+            int need_eq = 0;
+            kth = radix_select_key([&](int i) { return desc_key(val(i)); }, i0, i1, a.top_k, hist, &s_sel, &s_need, &need_eq);
         }
         float mx = -INFINITY;
         for (int i = i0; i < i1; ++i) {
@@ -395,6 +377,238 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs
         if (a.hist_tokens && step < a.hist_stride) a.hist_tokens[(size_t)blockIdx.x * a.hist_stride + step] = s_token;
         if (a.hist_logprobs && step < a.hist_stride) a.hist_logprobs[(size_t)blockIdx.x * a.hist_stride + step] = s_lp;
         if (a.feed_token) a.feed_token[blockIdx.x] = s_token;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// beam_search_decode's expansion of one candidate (:1964-2018): probs = softmax(logits / T) over the vocabulary -> top-k filter
+// on the PROBABILITIES + renormalise (:1821-1856) -> top-p filter + renormalise (:1858-1909) -> the beam_size most probable
+// tokens with probability > 0, most probable first.  One CTA per candidate (row of the batched step's logits); the host
+// only receives [beam] (probability, token) pairs per row.
+//   * the softmax denominator over the whole vocabulary is a block-wide sum (the reference adds 32000 terms sequentially in
+//     fp32; with a top-k or top-p filter the denominator cancels in the renormalisation, without any filter the reference's
+//     own accumulated rounding shows: ~3e-5 relative at V = 32000);
+//   * top_k in [1, 1024]: every later sum runs sequentially over the survivors in index order, as the reference's loops do;
+//   * wider / no top-k: block-wide sums and a radix search for the nucleus, like sample_kernel's wide path;
+//   * equal probabilities: lower token id first (the reference's std::sort leaves the order of ties unspecified).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kBeamMax = 64;
+struct BeamExpandArgs {
+    const float* logits;   // [rows][ld]
+    int V, ld;
+    float temperature;
+    int top_k;
+    float top_p;
+    int beam;
+    float* cand_prob;      // [rows][beam]
+    int* cand_tok;         // [rows][beam]
+    int* cand_cnt;         // [rows]
+};
+__global__ void __launch_bounds__(kSampleThreads) beam_expand_kernel(const BeamExpandArgs a) {
+    __shared__ int hist[256];
+    __shared__ float fhist[256];
+    __shared__ int wsum[32];
+    __shared__ float wsumf[32];
+    __shared__ int s_tot, s_sel, s_need;
+    __shared__ float s_ftot, s_max, s_sum;
+    __shared__ int sidx[kTopKMax];
+    __shared__ float sval[kTopKMax];
+    __shared__ int sord[kTopKMax];
+    const int tid = threadIdx.x, V = a.V;
+    const float* lg = a.logits + (size_t)blockIdx.x * a.ld;
+    const bool scale = a.temperature != 1.0f;                                                 // :1972-1976
+    auto val = [&](int i) -> float { const float x = lg[i]; return scale ? x / a.temperature : x; };
+    auto key_of = [&](int i) -> uint32_t { return desc_key(val(i)); };
+    const int per = (V + kSampleThreads - 1) / kSampleThreads;
+    const int i0 = min(tid * per, V), i1 = min(i0 + per, V);
+    const bool use_topk = a.top_k > 0 && a.top_k < V;                                         // :1982
+    const bool exact = use_topk && a.top_k <= kTopKMax;
+    // ---- softmax over the vocabulary (:1798-1819) ----
+    float mx = -INFINITY;
+    for (int i = i0; i < i1; ++i) mx = fmaxf(mx, val(i));
+    mx = warp_max(mx);
+    if ((tid & 31) == 0) wsumf[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        float m2 = -INFINITY;
+        for (int w = 0; w < kSampleThreads / 32; ++w) m2 = fmaxf(m2, wsumf[w]);
+        s_max = m2;
+    }
+    __syncthreads();
+    float part = 0.f;
+    for (int i = i0; i < i1; ++i) part += expf(val(i) - s_max);
+    (void)block_exscan_f(part, wsumf, &s_ftot);
+    const float S = s_ftot;
+    auto prob = [&](int i) -> float { return expf(val(i) - s_max) / S; };
+    int n = 0;   // entries of the candidate list (sidx, sval), in index order
+    if (exact) {
+        int need = 0;
+        const uint32_t tau = radix_select_key(key_of, i0, i1, a.top_k, hist, &s_sel, &s_need, &need);
+        int cgt = 0, ceq = 0;
+        for (int i = i0; i < i1; ++i) {
+            const uint32_t key = key_of(i);
+            cgt += key > tau ? 1 : 0;
+            ceq += key == tau ? 1 : 0;
+        }
+        const int eq_before = block_exscan(ceq, wsum, &s_tot);
+        int keep = cgt, eqr = eq_before;
+        for (int i = i0; i < i1; ++i)
+            if (key_of(i) == tau) { keep += eqr < need ? 1 : 0; ++eqr; }
+        int off = block_exscan(keep, wsum, &s_tot);
+        eqr = eq_before;
+        for (int i = i0; i < i1; ++i) {
+            const uint32_t key = key_of(i);
+            bool take = key > tau;
+            if (key == tau) { take = eqr < need; ++eqr; }
+            if (take) { sidx[off] = i; sval[off] = prob(i); ++off; }
+        }
+        __syncthreads();
+        n = s_tot;
+        // renormalise over the top-k set (:1845-1854), sequentially in index order
+        if (tid == 0) {
+            float t = 0.f;
+            for (int i = 0; i < n; ++i) t += sval[i];
+            s_sum = t;
+        }
+        __syncthreads();
+        if (s_sum > 0.0f)
+            for (int i = tid; i < n; i += kSampleThreads) sval[i] = sval[i] / s_sum;
+        __syncthreads();
+        if (a.top_p < 1.0f) {   // (:1858-1909) nucleus in (probability desc, index asc) order, sequential cumulative sum
+            for (int i = tid; i < n; i += kSampleThreads) {
+                const float p = sval[i];
+                int rank = 0;
+                for (int j = 0; j < n; ++j) {
+                    const float q = sval[j];
+                    rank += (q > p || (q == p && j < i)) ? 1 : 0;
+                }
+                sord[rank] = i;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float c = 0.f;
+                int cutoff = n;
+                for (int r = 0; r < n; ++r) {
+                    c += sval[sord[r]];
+                    if (c >= a.top_p) { cutoff = r + 1; break; }
+                }
+                s_sel = cutoff;
+            }
+            __syncthreads();
+            for (int r = s_sel + tid; r < n; r += kSampleThreads) sval[sord[r]] = 0.0f;
+            __syncthreads();
+            if (tid == 0) {
+                float t = 0.f;
+                for (int i = 0; i < n; ++i) t += sval[i];
+                s_sum = t;
+            }
+            __syncthreads();
+            if (s_sum > 0.0f)
+                for (int i = tid; i < n; i += kSampleThreads) sval[i] = sval[i] / s_sum;
+            __syncthreads();
+        }
+    } else {
+        // ---- wide: thresholds on the key instead of a survivor list; only the `beam` best are gathered at the end ----
+        uint32_t kth = 0;
+        float Zk = 1.0f;   // mass of the top-k set (1: no top-k filter, nothing is renormalised, :1824-1826)
+        if (use_topk) {
+            int need_eq = 0;
+            kth = radix_select_key(key_of, i0, i1, a.top_k, hist, &s_sel, &s_need, &need_eq);
+            float mine = 0.f;
+            for (int i = i0; i < i1; ++i)
+                if (key_of(i) >= kth) mine += prob(i);
+            (void)block_exscan_f(mine, wsumf, &s_ftot);
+            Zk = s_ftot;
+        }
+        uint32_t pth = kth;
+        float Z2 = Zk;
+        if (a.top_p < 1.0f) {
+            const float target = a.top_p * Zk;   // cumulative RENORMALISED probability >= top_p
+            uint32_t prefix = 0, mask = 0;
+            float above = 0.f;
+            for (int pass = 0; pass < 4; ++pass) {
+                const int shift = 24 - 8 * pass;
+                for (int b = tid; b < 256; b += kSampleThreads) fhist[b] = 0.f;
+                __syncthreads();
+                for (int i = i0; i < i1; ++i) {
+                    const uint32_t key = key_of(i);
+                    if (key >= kth && (key & mask) == prefix) atomicAdd(&fhist[(key >> shift) & 255u], prob(i));
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    float acc = above;
+                    int b = 255;
+                    for (; b > 0; --b) {
+                        if (acc + fhist[b] >= target) break;
+                        acc += fhist[b];
+                    }
+                    s_sel = b;
+                    s_ftot = acc;
+                }
+                __syncthreads();
+                prefix |= (uint32_t)s_sel << shift;
+                mask |= 255u << shift;
+                above = s_ftot;
+                __syncthreads();
+            }
+            pth = prefix > kth ? prefix : kth;
+            float mine = 0.f;
+            for (int i = i0; i < i1; ++i)
+                if (key_of(i) >= pth) mine += prob(i);
+            (void)block_exscan_f(mine, wsumf, &s_ftot);
+            Z2 = s_ftot;
+        }
+        // the `beam` largest keys among the survivors (key >= pth), gathered in index order
+        int cs = 0;
+        for (int i = i0; i < i1; ++i) cs += key_of(i) >= pth ? 1 : 0;
+        (void)block_exscan(cs, wsum, &s_tot);
+        const int survivors = s_tot;
+        const int want = min(a.beam, survivors);
+        int need = 0;
+        const uint32_t tau = radix_select_key(key_of, i0, i1, want, hist, &s_sel, &s_need, &need);   // want <= survivors: tau >= pth
+        int cgt = 0, ceq = 0;
+        for (int i = i0; i < i1; ++i) {
+            const uint32_t key = key_of(i);
+            cgt += key > tau ? 1 : 0;
+            ceq += key == tau ? 1 : 0;
+        }
+        const int eq_before = block_exscan(ceq, wsum, &s_tot);
+        int keep = cgt, eqr = eq_before;
+        for (int i = i0; i < i1; ++i)
+            if (key_of(i) == tau) { keep += eqr < need ? 1 : 0; ++eqr; }
+        int off = block_exscan(keep, wsum, &s_tot);
+        eqr = eq_before;
+        const bool renorm = use_topk || a.top_p < 1.0f;
+        for (int i = i0; i < i1; ++i) {
+            const uint32_t key = key_of(i);
+            bool take = key > tau;
+            if (key == tau) { take = eqr < need; ++eqr; }
+            if (take) { sidx[off] = i; sval[off] = renorm ? prob(i) / Z2 : prob(i); ++off; }
+        }
+        __syncthreads();
+        n = s_tot;
+    }
+    // ---- the beam most probable entries with probability > 0, most probable first (:1990-2005) ----
+    for (int i = tid; i < n; i += kSampleThreads) {
+        const float p = sval[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const float q = sval[j];
+            rank += (q > p || (q == p && j < i)) ? 1 : 0;
+        }
+        sord[rank] = i;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int cnt = 0;
+        for (int r = 0; r < n && r < a.beam; ++r) {
+            const int i = sord[r];
+            if (!(sval[i] > 0.0f)) break;
+            a.cand_prob[(size_t)blockIdx.x * a.beam + cnt] = sval[i];
+            a.cand_tok[(size_t)blockIdx.x * a.beam + cnt] = sidx[i];
+            ++cnt;
+        }
+        a.cand_cnt[blockIdx.x] = cnt;
     }
 }
 

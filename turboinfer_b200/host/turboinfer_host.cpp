@@ -706,6 +706,33 @@ GenerationResult InferenceEngine::generate(const std::vector<int>& input_tokens,
     return result;
 }
 
+std::vector<GenerationResult> InferenceEngine::generate_beam_search(const std::vector<int>& input_tokens, size_t max_new_tokens, size_t beam_size,
+                                                                    bool include_logprobs) {
+    if (beam_size == 0) throw std::runtime_error("Beam size must be greater than 0");   // :836-838
+    validate_input_tokens(input_tokens);
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    const size_t cap = std::max<size_t>(max_new_tokens, 1);
+    std::vector<int32_t> toks(beam_size * cap), lens(beam_size), fin(beam_size);
+    std::vector<float> lp(beam_size), score(beam_size);
+    int32_t n = 0;
+    ck(ti_b200_beam_search(handle_, input_tokens.data(), (int32_t)input_tokens.size(), (int32_t)max_new_tokens, (int32_t)beam_size, config_.temperature,
+                           (int32_t)config_.top_k, config_.top_p, config_.length_penalty, config_.eos_token_id, toks.data(), lens.data(), lp.data(),
+                           score.data(), fin.data(), &n));
+    const float ms = std::chrono::duration<float, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+    std::vector<GenerationResult> out;
+    for (int32_t i = 0; i < n; ++i) {
+        GenerationResult r;
+        r.tokens.assign(toks.begin() + i * max_new_tokens, toks.begin() + i * max_new_tokens + lens[i]);
+        r.finished = fin[i] != 0;
+        if (include_logprobs) r.logprobs.assign(r.tokens.size(), lp[i] / (float)r.tokens.size());   // :862-865
+        r.total_time_ms = ms;
+        out.push_back(std::move(r));
+    }
+    stats_->generations++;
+    stats_->time_ms += ms;
+    return out;
+}
+
 std::vector<GenerationResult> InferenceEngine::generate_batch(const std::vector<std::vector<int>>& batch, size_t max_new_tokens,
                                                               bool include_logprobs) {
     if (batch.empty()) throw std::runtime_error("Batch size cannot be zero");
