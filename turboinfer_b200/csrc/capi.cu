@@ -847,7 +847,11 @@ int build_mega(Model& m) {
         at.at.D = m.attn_dim;
         at.at.heads = m.attn_heads;
         at.at.max_splits = mega_splits;
-        at.at.min_chunk = lean_attn ? 320 : 64;   // lean item: 16 warps x 5 tokens in flight = one round trip per 80 tokens; up to 4 round trips before a split pays
+        // lean item: 16 warps x 5 tokens in flight = one round trip per 80 tokens.  While a head is one item only `heads` of the 148 CTAs
+        // work, so a second round trip already costs more than the split's atomic + merge (measured, 7B decode-256: 843 -> 851 tok/s
+        // against a 320-token item; TinyLlama 1573 -> 1631)
+        at.at.min_chunk = lean_attn ? 80 : 64;
+        if (const char* e = getenv("TURBOINFER_B200_ATTN_CHUNK")) at.at.min_chunk = std::max(16, atoi(e));   // A/B experiments   // lean item: 16 warps x 5 tokens in flight = one round trip per 80 tokens; up to 4 round trips before a split pays
         at.at.scale = 1.0f / sqrtf((float)m.attn_dim);
         at.at.part_o = m.part_o.p;
         at.at.part_ml = m.part_ml.p;
@@ -1122,10 +1126,11 @@ int gemm_q_dev(QWeight& w, const float* x_dev, float* y_dev, int M, float* kerne
 // One GEMM of the prefill path: activations are already digit planes; no host synchronisation.
 // split factor of the 32-row GEMM: (N / 128) * S CTAs should fill the SMs in whole waves, with >= 6 k-steps per CTA
 int small_gemm_splits(int tiles, int ksteps) {
-    // One CTA per SM, and a CTA's time is its k-loop (a serial chain of TMA round trips) plus, when split, ~10 us of
-    // atomics + fix-up: splitting pays only for long k-loops on few tiles (the down projection).
-    if (ksteps <= 48 || tiles * 2 > g_num_sms) return 1;
-    int s = std::min(g_num_sms / tiles, ksteps / 24);
+    // One CTA per SM, and a CTA's time is its k-loop (a serial chain of TMA round trips) plus, when split, the atomics + fix-up:
+    // splitting pays for GEMMs with few column tiles (o and down projections: 32 tiles on 148 SMs).
+    static const int min_steps = getenv("TURBOINFER_B200_SPLIT_KSTEPS") ? std::max(2, atoi(getenv("TURBOINFER_B200_SPLIT_KSTEPS"))) : 8;   // A/B knob; 8 measured best (7B batch 32: 5.06 -> 4.96 ms per step)
+    if (ksteps <= 2 * min_steps || tiles * 2 > g_num_sms) return 1;
+    int s = std::min(g_num_sms / tiles, ksteps / min_steps);
     return std::max(1, std::min(s, 8));
 }
 int launch_small_gemm(Model& m, QWeight& w, int m_pad, const GemmArgs& g) {
