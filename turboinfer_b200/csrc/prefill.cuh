@@ -236,6 +236,160 @@ __global__ void __launch_bounds__(kPfThreads, 1) causal_attention_kernel(const f
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The same attention on the tensor cores (head dimension 64 or 128): S = Q K^T and O += P V as mma.sync m16n8k8 TF32 MMAs
+// with every fp32 operand split into two TF32 terms (x = hi + lo, hi = tf32(x), lo = tf32(x - hi)) and the three products
+// hi*hi + hi*lo + lo*hi accumulated in fp32 -- about 21 mantissa bits, i.e. the fp32 result to a few 1e-7 relative, at a
+// third of the TF32 rate instead of the CUDA cores' fp32 rate.  Softmax (max-subtracted, expf, running rescale) stays fp32.
+//   CTA = 8 warps = 128 queries of one head, a warp owns 16 query rows; per tile of 64 keys the CTA loads K and V once from the
+//   paged cache, splits them and keeps hi / lo images in shared memory ([key][D + 4]: conflict-free fragment reads);
+//   Q stays in shared memory as fp32 (A fragments read and split per k-step); P never leaves registers: the C fragment of S is used as the
+//   A fragment of P V with the keys of a k-step permuted (k slot t <-> key 2t, slot t + 4 <-> key 2t + 1), V rows read to match.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kTcQ = 128, kTcKT = 64, kTcThreads = 256;
+template <int DH> constexpr size_t attn_tc_smem_bytes() { return ((size_t)4 * kTcKT + kTcQ) * (DH + 4) * sizeof(uint32_t); }
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <int DH>
+__global__ void __launch_bounds__(kTcThreads, 1) causal_attention_tc_kernel(const float* qkv, int M, int H, float scale, int pos0, const float* k_pool,
+                                                                              const float* v_pool, const int* page_table, int page_tokens, float* out) {
+    constexpr int LD = DH + 4, KS = DH / 8;   // row stride of the shared tiles; k-steps of Q K^T = n-tiles of P V
+    extern __shared__ __align__(16) uint32_t tc_smem[];
+    uint32_t* Khi = tc_smem;
+    uint32_t* Klo = Khi + kTcKT * LD;
+    uint32_t* Vhi = Klo + kTcKT * LD;
+    uint32_t* Vlo = Vhi + kTcKT * LD;
+    float* Qs = reinterpret_cast<float*>(Vlo + kTcKT * LD);                    // [128 q][LD]
+    const int h = blockIdx.x, qb = (int)(gridDim.y - 1 - blockIdx.y) * kTcQ;   // latest queries (most key tiles) first
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int hoff = h * DH;
+    const int r0 = qb + 16 * warp + g, r1 = r0 + 8;   // this thread's two query rows (within the M prompt rows)
+    for (int i = tid; i < kTcQ * (DH / 4); i += kTcThreads) {
+        const int q = i / (DH / 4), d4 = (i % (DH / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (qb + q < M) v = *reinterpret_cast<const float4*>(qkv + (size_t)(qb + q) * 3 * H + hoff + d4);
+        *reinterpret_cast<float4*>(Qs + q * LD + d4) = v;
+    }
+    const float* qrow = Qs + (16 * warp + g) * LD + t;   // A fragment of k-step ks: rows g / g + 8, dims 8 ks + t / + 4
+    float o[KS][4];
+#pragma unroll
+    for (int n = 0; n < KS; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    const int last_pos = pos0 + min(qb + kTcQ, M) - 1;        // keys 0 .. last_pos can matter to this CTA
+    const int warp_last = pos0 + min(qb + 16 * warp + 15, M - 1);   // ... and to this warp
+    for (int t0 = 0; t0 <= last_pos; t0 += kTcKT) {
+        __syncthreads();   // the previous tile is no longer read
+        for (int i = tid; i < kTcKT * (DH / 4); i += kTcThreads) {
+            const int kk = i / (DH / 4), d4 = (i % (DH / 4)) * 4, tk = t0 + kk;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (tk <= last_pos) {
+                const size_t row = ((size_t)page_table[tk / page_tokens] * page_tokens + (tk % page_tokens)) * H + hoff + d4;
+                kv = *reinterpret_cast<const float4*>(k_pool + row);
+                vv = *reinterpret_cast<const float4*>(v_pool + row);
+            }
+            uint4 hi, lo;
+            split_tf32(kv.x, hi.x, lo.x); split_tf32(kv.y, hi.y, lo.y); split_tf32(kv.z, hi.z, lo.z); split_tf32(kv.w, hi.w, lo.w);
+            *reinterpret_cast<uint4*>(Khi + kk * LD + d4) = hi;
+            *reinterpret_cast<uint4*>(Klo + kk * LD + d4) = lo;
+            split_tf32(vv.x, hi.x, lo.x); split_tf32(vv.y, hi.y, lo.y); split_tf32(vv.z, hi.z, lo.z); split_tf32(vv.w, hi.w, lo.w);
+            *reinterpret_cast<uint4*>(Vhi + kk * LD + d4) = hi;
+            *reinterpret_cast<uint4*>(Vlo + kk * LD + d4) = lo;
+        }
+        __syncthreads();
+        if (t0 > warp_last) continue;   // every key of the tile lies in this warp's future (the barriers above stay CTA-wide)
+        // ---- S = Q K^T: 16 rows x 64 keys per warp ----
+        float sc[kTcKT / 8][4];
+#pragma unroll
+        for (int j = 0; j < kTcKT / 8; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            uint32_t ah[4], al[4];
+            split_tf32(qrow[8 * ks], ah[0], al[0]);
+            split_tf32(qrow[8 * LD + 8 * ks], ah[1], al[1]);
+            split_tf32(qrow[8 * ks + 4], ah[2], al[2]);
+            split_tf32(qrow[8 * LD + 8 * ks + 4], ah[3], al[3]);
+#pragma unroll
+            for (int j = 0; j < kTcKT / 8; ++j) {
+                const int off = (8 * j + g) * LD + 8 * ks + t;   // B fragment: (k = dim, n = key)
+                const uint32_t bh0 = Khi[off], bh1 = Khi[off + 4], bl0 = Klo[off], bl1 = Klo[off + 4];
+                mma_tf32(sc[j], al, bh0, bh1);
+                mma_tf32(sc[j], ah, bl0, bl1);
+                mma_tf32(sc[j], ah, bh0, bh1);
+            }
+        }
+        // ---- online softmax over the tile (rows r0, r1; this thread holds keys 8 j + 2 t, + 1 of every j) ----
+        const int qp0 = pos0 + r0, qp1 = pos0 + r1;
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kTcKT / 8; ++j) {
+            const int key = t0 + 8 * j + 2 * t;
+            sc[j][0] = (key <= qp0 && r0 < M) ? sc[j][0] * scale : -INFINITY;
+            sc[j][1] = (key + 1 <= qp0 && r0 < M) ? sc[j][1] * scale : -INFINITY;
+            sc[j][2] = (key <= qp1 && r1 < M) ? sc[j][2] * scale : -INFINITY;
+            sc[j][3] = (key + 1 <= qp1 && r1 < M) ? sc[j][3] * scale : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(sc[j][0], sc[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(sc[j][2], sc[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kTcKT / 8; ++j) {
+            sc[j][0] = mn0 == -INFINITY ? 0.f : expf(sc[j][0] - mn0);   // expf(-inf) = 0 for masked keys
+            sc[j][1] = mn0 == -INFINITY ? 0.f : expf(sc[j][1] - mn0);
+            sc[j][2] = mn1 == -INFINITY ? 0.f : expf(sc[j][2] - mn1);
+            sc[j][3] = mn1 == -INFINITY ? 0.f : expf(sc[j][3] - mn1);
+            rs0 += sc[j][0] + sc[j][1];
+            rs1 += sc[j][2] + sc[j][3];
+        }
+        rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+        rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+        const float c0 = mn0 == -INFINITY ? 1.f : expf(m0 - mn0), c1 = mn1 == -INFINITY ? 1.f : expf(m1 - mn1);
+        l0 = l0 * c0 + rs0;
+        l1 = l1 * c1 + rs1;
+        m0 = mn0;
+        m1 = mn1;
+#pragma unroll
+        for (int n = 0; n < KS; ++n) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
+        // ---- O += P V: k-step j = keys 8 j .. 8 j + 7, with k slot t <-> key 8 j + 2 t and slot t + 4 <-> key 8 j + 2 t + 1 ----
+#pragma unroll
+        for (int j = 0; j < kTcKT / 8; ++j) {
+            uint32_t ph[4], pl[4];
+            split_tf32(sc[j][0], ph[0], pl[0]);   // a0: (row g,     slot t)
+            split_tf32(sc[j][2], ph[1], pl[1]);   // a1: (row g + 8, slot t)
+            split_tf32(sc[j][1], ph[2], pl[2]);   // a2: (row g,     slot t + 4)
+            split_tf32(sc[j][3], ph[3], pl[3]);   // a3: (row g + 8, slot t + 4)
+            const int vrow = (8 * j + 2 * t) * LD + g;
+#pragma unroll
+            for (int n = 0; n < KS; ++n) {
+                const uint32_t bh0 = Vhi[vrow + 8 * n], bh1 = Vhi[vrow + LD + 8 * n], bl0 = Vlo[vrow + 8 * n], bl1 = Vlo[vrow + LD + 8 * n];
+                mma_tf32(o[n], pl, bh0, bh1);
+                mma_tf32(o[n], ph, bl0, bl1);
+                mma_tf32(o[n], ph, bh0, bh1);
+            }
+        }
+    }
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+    for (int n = 0; n < KS; ++n) {
+        if (r0 < M) *reinterpret_cast<float2*>(out + (size_t)r0 * H + hoff + 8 * n + 2 * t) = make_float2(o[n][0] * i0, o[n][1] * i0);
+        if (r1 < M) *reinterpret_cast<float2*>(out + (size_t)r1 * H + hoff + 8 * n + 2 * t) = make_float2(o[n][2] * i1, o[n][3] * i1);
+    }
+}
+
 // act[m][i] = up * silu(gate) from interleaved columns (gate_i, up_i) of gu[M][2I]
 __global__ void swiglu_rows_kernel(const float* gu, float* act, size_t M, size_t I) {
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < M * I; idx += (size_t)gridDim.x * blockDim.x) {
