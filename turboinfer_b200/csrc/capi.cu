@@ -154,6 +154,8 @@ int set_kernel_attrs() {
     CK(cudaFuncSetAttribute(causal_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPfSmemBytes));
     CK(cudaFuncSetAttribute(causal_attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_tc_smem_bytes<128>()));
     CK(cudaFuncSetAttribute(causal_attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_tc_smem_bytes<64>()));
+    CK(cudaFuncSetAttribute(causal_attention_h3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_h3_smem_bytes<128>()));
+    CK(cudaFuncSetAttribute(causal_attention_h3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_h3_smem_bytes<64>()));
     g_attr_done = true;
     return 0;
 }
@@ -1215,9 +1217,17 @@ int prefill_gemm(Model& m, const int* prompt_dev, int M) {
         TRY(pf_digits(m, m.pf_x.p, ly.attn_norm.p, M, H, m_pad, ly.qkv->k_pad));
         TRY(pf_gemm(m, *ly.qkv, M, m_pad, m.pf_qkv.p, nullptr));
         rope_kv_kernel<<<M, 256, 0, g_stream>>>(m.pf_qkv.p, M, H, rope_dim, m.inv_freq.p, pos0, ly.k_pool.p, ly.v_pool.p, m.page_table.p, m.page_tokens);
-        static const bool attn_fp32 = getenv("TURBOINFER_B200_PREFILL_ATTN") && std::string(getenv("TURBOINFER_B200_PREFILL_ATTN")) == "fp32";   // A/B
+        static const std::string attn_sel = getenv("TURBOINFER_B200_PREFILL_ATTN") ? getenv("TURBOINFER_B200_PREFILL_ATTN") : "";   // A/B: fp32 | tf32
+        const bool attn_fp32 = attn_sel == "fp32", attn_tf32 = attn_sel == "tf32";
         const float att_scale = 1.0f / sqrtf((float)m.attn_dim);
-        if (!attn_fp32 && m.attn_dim == 128) {          // tensor cores, split TF32 (prefill.cuh)
+        const dim3 tc_grid(m.attn_heads, (M + kTcQ - 1) / kTcQ);
+        if (!attn_fp32 && !attn_tf32 && m.attn_dim == 128) {          // tensor cores, split FP16 (prefill.cuh)
+            causal_attention_h3_kernel<128><<<tc_grid, kTcThreads, attn_h3_smem_bytes<128>(), g_stream>>>(
+                m.pf_qkv.p, M, H, att_scale, pos0, ly.k_pool.p, ly.v_pool.p, m.page_table.p, m.page_tokens, m.pf_attn.p);
+        } else if (!attn_fp32 && !attn_tf32 && m.attn_dim == 64) {
+            causal_attention_h3_kernel<64><<<tc_grid, kTcThreads, attn_h3_smem_bytes<64>(), g_stream>>>(
+                m.pf_qkv.p, M, H, att_scale, pos0, ly.k_pool.p, ly.v_pool.p, m.page_table.p, m.page_tokens, m.pf_attn.p);
+        } else if (!attn_fp32 && m.attn_dim == 128) {   // split TF32
             causal_attention_tc_kernel<128><<<dim3(m.attn_heads, (M + kTcQ - 1) / kTcQ), kTcThreads, attn_tc_smem_bytes<128>(), g_stream>>>(
                 m.pf_qkv.p, M, H, att_scale, pos0, ly.k_pool.p, ly.v_pool.p, m.page_table.p, m.page_tokens, m.pf_attn.p);
         } else if (!attn_fp32 && m.attn_dim == 64) {

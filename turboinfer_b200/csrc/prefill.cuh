@@ -7,6 +7,7 @@
 //   swiglu_rows_kernel      multiply(up, silu(gate)) on interleaved (gate, up) columns (:389-391)
 // All fp32, full-precision expf / division like the decode path.
 #pragma once
+#include <cuda_fp16.h>
 #include "gemm_tc.cuh"
 
 namespace tib {
@@ -258,7 +259,7 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
     lo = to_tf32(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -320,14 +321,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) causal_attention_tc_kernel(cons
             split_tf32(qrow[8 * LD + 8 * ks], ah[1], al[1]);
             split_tf32(qrow[8 * ks + 4], ah[2], al[2]);
             split_tf32(qrow[8 * LD + 8 * ks + 4], ah[3], al[3]);
+            // the three products of an accumulator are issued a whole pass apart (8 independent MMAs between dependent ones)
+            uint32_t bh0[kTcKT / 8], bh1[kTcKT / 8], bl0[kTcKT / 8], bl1[kTcKT / 8];
 #pragma unroll
             for (int j = 0; j < kTcKT / 8; ++j) {
                 const int off = (8 * j + g) * LD + 8 * ks + t;   // B fragment: (k = dim, n = key)
-                const uint32_t bh0 = Khi[off], bh1 = Khi[off + 4], bl0 = Klo[off], bl1 = Klo[off + 4];
-                mma_tf32(sc[j], al, bh0, bh1);
-                mma_tf32(sc[j], ah, bl0, bl1);
-                mma_tf32(sc[j], ah, bh0, bh1);
+                bh0[j] = Khi[off]; bh1[j] = Khi[off + 4]; bl0[j] = Klo[off]; bl1[j] = Klo[off + 4];
             }
+#pragma unroll
+            for (int j = 0; j < kTcKT / 8; ++j) mma_tf32(sc[j], al, bh0[j], bh1[j]);
+#pragma unroll
+            for (int j = 0; j < kTcKT / 8; ++j) mma_tf32(sc[j], ah, bl0[j], bl1[j]);
+#pragma unroll
+            for (int j = 0; j < kTcKT / 8; ++j) mma_tf32(sc[j], ah, bh0[j], bh1[j]);
         }
         // ---- online softmax over the tile (rows r0, r1; this thread holds keys 8 j + 2 t, + 1 of every j) ----
         const int qp0 = pos0 + r0, qp1 = pos0 + r1;
@@ -374,17 +380,201 @@ __global__ void __launch_bounds__(kTcThreads, 1) causal_attention_tc_kernel(cons
             split_tf32(sc[j][3], ph[3], pl[3]);   // a3: (row g + 8, slot t + 4)
             const int vrow = (8 * j + 2 * t) * LD + g;
 #pragma unroll
-            for (int n = 0; n < KS; ++n) {
-                const uint32_t bh0 = Vhi[vrow + 8 * n], bh1 = Vhi[vrow + LD + 8 * n], bl0 = Vlo[vrow + 8 * n], bl1 = Vlo[vrow + LD + 8 * n];
-                mma_tf32(o[n], pl, bh0, bh1);
-                mma_tf32(o[n], ph, bl0, bl1);
-                mma_tf32(o[n], ph, bh0, bh1);
+            for (int n0 = 0; n0 < KS; n0 += 8) {   // 8 output tiles at a time: dependent MMAs a pass apart, 32 fragment registers
+                uint32_t bh0[8], bh1[8], bl0[8], bl1[8];
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    const int off = vrow + 8 * (n0 + n);
+                    bh0[n] = Vhi[off]; bh1[n] = Vhi[off + LD]; bl0[n] = Vlo[off]; bl1[n] = Vlo[off + LD];
+                }
+#pragma unroll
+                for (int n = 0; n < 8; ++n) mma_tf32(o[n0 + n], pl, bh0[n], bh1[n]);
+#pragma unroll
+                for (int n = 0; n < 8; ++n) mma_tf32(o[n0 + n], ph, bl0[n], bl1[n]);
+#pragma unroll
+                for (int n = 0; n < 8; ++n) mma_tf32(o[n0 + n], ph, bh0[n], bh1[n]);
             }
         }
     }
     const float i0 = 1.0f / l0, i1 = 1.0f / l1;
 #pragma unroll
     for (int n = 0; n < KS; ++n) {
+        if (r0 < M) *reinterpret_cast<float2*>(out + (size_t)r0 * H + hoff + 8 * n + 2 * t) = make_float2(o[n][0] * i0, o[n][1] * i0);
+        if (r1 < M) *reinterpret_cast<float2*>(out + (size_t)r1 * H + hoff + 8 * n + 2 * t) = make_float2(o[n][2] * i1, o[n][3] * i1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The same attention with FP16 MMAs (mma.sync m16n8k16, twice the work per instruction of the TF32 form): every fp32 operand
+// is split into two halves, x = hi + lo (hi = fp16(x), lo = fp16(x - hi): 22 mantissa bits), and hi*hi + hi*lo + lo*hi is
+// accumulated in fp32 -- the accuracy of the split-TF32 kernel above at half its instruction count.  Values are activations
+// (|x| well inside fp16's range).  Q, K, V hi / lo images live in shared memory as halves ([row][D + 8]: conflict-free
+// ldmatrix / LDS.32); K fragments come from ldmatrix, V fragments from ldmatrix.trans (the k index of P V is the key), and the
+// C fragments of two adjacent S tiles ARE the A fragment of P V for 16 keys, so P never leaves registers.
+// ---------------------------------------------------------------------------------------------------
+template <int DH> constexpr size_t attn_h3_smem_bytes() { return ((size_t)2 * kTcQ + 4 * kTcKT) * (DH + 8) * sizeof(__half); }
+__device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn(x - __half2float(hi));
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+template <int DH>
+__global__ void __launch_bounds__(kTcThreads, 1) causal_attention_h3_kernel(const float* qkv, int M, int H, float scale, int pos0, const float* k_pool,
+                                                                              const float* v_pool, const int* page_table, int page_tokens, float* out) {
+    constexpr int LD = DH + 8, KS = DH / 16, NT = DH / 8;   // row stride in halves; k-steps of Q K^T; n-tiles of P V
+    extern __shared__ __align__(16) __half h3_smem[];
+    __half* Qh = h3_smem;                 // [128][LD]
+    __half* Ql = Qh + kTcQ * LD;
+    __half* Kh = Ql + kTcQ * LD;          // [64][LD]
+    __half* Kl = Kh + kTcKT * LD;
+    __half* Vh = Kl + kTcKT * LD;
+    __half* Vl = Vh + kTcKT * LD;
+    const int h = blockIdx.x, qb = (int)(gridDim.y - 1 - blockIdx.y) * kTcQ;   // latest queries (most key tiles) first
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int hoff = h * DH;
+    const int r0 = qb + 16 * warp + g, r1 = r0 + 8;
+    auto store_split4 = [](const float4& v, __half* hi, __half* lo) {
+        __half a[4], b[4];
+        split_h(v.x, a[0], b[0]); split_h(v.y, a[1], b[1]); split_h(v.z, a[2], b[2]); split_h(v.w, a[3], b[3]);
+        *reinterpret_cast<uint2*>(hi) = make_uint2(pack_h2(a[0], a[1]), pack_h2(a[2], a[3]));
+        *reinterpret_cast<uint2*>(lo) = make_uint2(pack_h2(b[0], b[1]), pack_h2(b[2], b[3]));
+    };
+    for (int i = tid; i < kTcQ * (DH / 4); i += kTcThreads) {
+        const int q = i / (DH / 4), d4 = (i % (DH / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (qb + q < M) v = *reinterpret_cast<const float4*>(qkv + (size_t)(qb + q) * 3 * H + hoff + d4);
+        store_split4(v, Qh + q * LD + d4, Ql + q * LD + d4);
+    }
+    float o[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    const int last_pos = pos0 + min(qb + kTcQ, M) - 1;
+    const int warp_last = pos0 + min(qb + 16 * warp + 15, M - 1);
+    // A fragments of Q: rows g / g + 8 of the warp's 16, halves (2t, 2t + 1) and (2t + 8, 2t + 9) of a 16-dim k-step
+    const uint32_t* qh_row = reinterpret_cast<const uint32_t*>(Qh + (16 * warp + g) * LD) + t;
+    const uint32_t* ql_row = reinterpret_cast<const uint32_t*>(Ql + (16 * warp + g) * LD) + t;
+    // ldmatrix row addresses: lane -> (matrix = lane / 8, row = lane % 8)
+    const int lm = lane >> 3, lr = lane & 7;
+    const uint32_t k_ld = (uint32_t)(((lr + 8 * (lm >> 1)) * LD + 8 * (lm & 1)) * 2);   // K: matrices (keys 0-7 | dims 0-7, 8-15), (keys 8-15 | ...)
+    const uint32_t v_ld = (uint32_t)(((lr + 8 * (lm & 1)) * LD + 8 * (lm >> 1)) * 2);   // V^T: matrices (keys 0-7, 8-15 | dims 0-7), (... | dims 8-15)
+    const uint32_t kh_s = smem_u32(Kh), kl_s = smem_u32(Kl), vh_s = smem_u32(Vh), vl_s = smem_u32(Vl);
+    for (int t0 = 0; t0 <= last_pos; t0 += kTcKT) {
+        __syncthreads();
+        for (int i = tid; i < kTcKT * (DH / 4); i += kTcThreads) {
+            const int kk = i / (DH / 4), d4 = (i % (DH / 4)) * 4, tk = t0 + kk;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (tk <= last_pos) {
+                const size_t row = ((size_t)page_table[tk / page_tokens] * page_tokens + (tk % page_tokens)) * H + hoff + d4;
+                kv = *reinterpret_cast<const float4*>(k_pool + row);
+                vv = *reinterpret_cast<const float4*>(v_pool + row);
+            }
+            store_split4(kv, Kh + kk * LD + d4, Kl + kk * LD + d4);
+            store_split4(vv, Vh + kk * LD + d4, Vl + kk * LD + d4);
+        }
+        __syncthreads();
+        if (t0 > warp_last) continue;
+        // ---- S = Q K^T ----
+        float sc[kTcKT / 8][4];
+#pragma unroll
+        for (int j = 0; j < kTcKT / 8; ++j) sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const uint32_t ah[4] = {qh_row[8 * ks], qh_row[8 * ks + 4 * LD], qh_row[8 * ks + 4], qh_row[8 * ks + 4 * LD + 4]};   // (LD halves = LD / 2 words; 8 rows = 4 LD words)
+            const uint32_t al[4] = {ql_row[8 * ks], ql_row[8 * ks + 4 * LD], ql_row[8 * ks + 4], ql_row[8 * ks + 4 * LD + 4]};
+#pragma unroll
+            for (int jp = 0; jp < kTcKT / 16; ++jp) {   // two key tiles per ldmatrix.x4: {b0, b1} of tile 2 jp, {b0, b1} of tile 2 jp + 1
+                uint32_t bh[4], bl[4];
+                const uint32_t off = (uint32_t)((16 * jp * LD + 16 * ks) * 2) + k_ld;
+                ldsm_x4(bh, kh_s + off);
+                ldsm_x4(bl, kl_s + off);
+                mma_f16(sc[2 * jp], al, bh[0], bh[1]);
+                mma_f16(sc[2 * jp + 1], al, bh[2], bh[3]);
+                mma_f16(sc[2 * jp], ah, bl[0], bl[1]);
+                mma_f16(sc[2 * jp + 1], ah, bl[2], bl[3]);
+                mma_f16(sc[2 * jp], ah, bh[0], bh[1]);
+                mma_f16(sc[2 * jp + 1], ah, bh[2], bh[3]);
+            }
+        }
+        // ---- online softmax (as in the TF32 kernel) ----
+        const int qp0 = pos0 + r0, qp1 = pos0 + r1;
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < kTcKT / 8; ++j) {
+            const int key = t0 + 8 * j + 2 * t;
+            sc[j][0] = (key <= qp0 && r0 < M) ? sc[j][0] * scale : -INFINITY;
+            sc[j][1] = (key + 1 <= qp0 && r0 < M) ? sc[j][1] * scale : -INFINITY;
+            sc[j][2] = (key <= qp1 && r1 < M) ? sc[j][2] * scale : -INFINITY;
+            sc[j][3] = (key + 1 <= qp1 && r1 < M) ? sc[j][3] * scale : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(sc[j][0], sc[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(sc[j][2], sc[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kTcKT / 8; ++j) {
+            sc[j][0] = mn0 == -INFINITY ? 0.f : expf(sc[j][0] - mn0);
+            sc[j][1] = mn0 == -INFINITY ? 0.f : expf(sc[j][1] - mn0);
+            sc[j][2] = mn1 == -INFINITY ? 0.f : expf(sc[j][2] - mn1);
+            sc[j][3] = mn1 == -INFINITY ? 0.f : expf(sc[j][3] - mn1);
+            rs0 += sc[j][0] + sc[j][1];
+            rs1 += sc[j][2] + sc[j][3];
+        }
+        rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+        rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+        const float c0 = mn0 == -INFINITY ? 1.f : expf(m0 - mn0), c1 = mn1 == -INFINITY ? 1.f : expf(m1 - mn1);
+        l0 = l0 * c0 + rs0;
+        l1 = l1 * c1 + rs1;
+        m0 = mn0;
+        m1 = mn1;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
+        // ---- O += P V: k-step jp = keys 16 jp .. 16 jp + 15 = S tiles 2 jp and 2 jp + 1 ----
+#pragma unroll
+        for (int jp = 0; jp < kTcKT / 16; ++jp) {
+            uint32_t ph[4], pl[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {   // a0: (row g, keys 2t, 2t+1) a1: (row g+8, ...) of tile 2 jp; a2, a3: the same of tile 2 jp + 1
+                const float x = sc[2 * jp + (i >> 1)][2 * (i & 1)], y = sc[2 * jp + (i >> 1)][2 * (i & 1) + 1];
+                __half xh, xl, yh, yl;
+                split_h(x, xh, xl);
+                split_h(y, yh, yl);
+                ph[i] = pack_h2(xh, yh);
+                pl[i] = pack_h2(xl, yl);
+            }
+#pragma unroll
+            for (int np = 0; np < NT / 2; ++np) {   // two dim tiles per ldmatrix.x4.trans
+                uint32_t bh[4], bl[4];
+                const uint32_t off = (uint32_t)((16 * jp * LD + 16 * np) * 2) + v_ld;
+                ldsm_x4_trans(bh, vh_s + off);
+                ldsm_x4_trans(bl, vl_s + off);
+                mma_f16(o[2 * np], pl, bh[0], bh[1]);
+                mma_f16(o[2 * np + 1], pl, bh[2], bh[3]);
+                mma_f16(o[2 * np], ph, bl[0], bl[1]);
+                mma_f16(o[2 * np + 1], ph, bl[2], bl[3]);
+                mma_f16(o[2 * np], ph, bh[0], bh[1]);
+                mma_f16(o[2 * np + 1], ph, bh[2], bh[3]);
+            }
+        }
+    }
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
         if (r0 < M) *reinterpret_cast<float2*>(out + (size_t)r0 * H + hoff + 8 * n + 2 * t) = make_float2(o[n][0] * i0, o[n][1] * i0);
         if (r1 < M) *reinterpret_cast<float2*>(out + (size_t)r1 * H + hoff + 8 * n + 2 * t) = make_float2(o[n][2] * i1, o[n][3] * i1);
     }
