@@ -29,8 +29,10 @@ def test_beam_expand_vs_oracle(tb, port, V, T, k, p):
         for r in range(3):
             want = port.beam_expand(lg[r], beam, T, k, p)
             assert [t for _, t in got[r]] == [t for _, t in want]
-            # the same pipeline; sums the reference adds sequentially over the vocabulary are block-wide sums here (1e-5: fp32 rounding)
-            np.testing.assert_allclose([q for q, _ in got[r]], [q for q, _ in want], rtol=2e-5)
+            # (rtol) The softmax denominator over the whole vocabulary is a block-wide sum here and a sequential fp32 sum in the
+            # reference, whose rounding error grows with V (~3e-5 at 32000 terms); a top-k / top-p filter renormalises over the
+            # survivors, where it cancels.
+            np.testing.assert_allclose([q for q, _ in got[r]], [q for q, _ in want], rtol=1e-4 if (k == 0 and p == 1.0) else 2e-5)
 
 
 def sharpen(w, f):

@@ -213,3 +213,49 @@ def test_model_from_asymmetric_int4_integers(tb, port):
     finally:
         a.free()
         b.free()
+
+
+def test_eos_stop_ends_the_device_loop_early(tb):
+    """stop_on_eos: the persistent launch is issued in chunks of 32 steps and the host stops issuing once token 2 has appeared, so
+    a generation that ends early does not decode all n_new tokens.  The EOS position is planted by relabelling: swapping vocabulary
+    entries T <-> 2 (embedding rows and lm_head columns) turns the first occurrence of T into the first EOS."""
+    meta = SHAPES["tiny-test"]
+    n_new = 120
+    found = None
+    for seed in range(12):
+        w = make_model(meta, norm_jitter=0.1)
+        w["lm_head.weight"] = (w["lm_head.weight"] * 6.0).astype(np.float32)
+        prompt = prompt_tokens(5, meta["vocab"], offset=17 * seed)
+        m = tb.Model(meta, oracle.QINT8, rope_mode=1, max_seq=160).load(w)
+        try:
+            full = [int(t) for t in m.generate_greedy(prompt, n_new)[0]]
+        finally:
+            m.free()
+        first = {}
+        for i, t in enumerate(full):
+            first.setdefault(t, i)
+        cands = [(i, t) for t, i in first.items() if 34 <= i <= 60 and t != 2 and 2 not in full[: i + 1] and t not in prompt and 2 not in prompt]
+        if cands:
+            found = (w, prompt, full, min(cands))
+            break
+    if found is None:
+        pytest.skip("no token with a first occurrence between steps 34 and 60 in these generations")
+    w, prompt, full, (idx, T) = found
+    w2 = dict(w)
+    emb, lm = w["token_embeddings.weight"].copy(), w["lm_head.weight"].copy()
+    emb[[2, T]] = emb[[T, 2]]
+    lm[:, [2, T]] = lm[:, [T, 2]]
+    w2["token_embeddings.weight"], w2["lm_head.weight"] = emb, lm
+    relabel = {2: T, T: 2}
+    m = tb.Model(meta, oracle.QINT8, rope_mode=1, max_seq=160).load(w2)
+    try:
+        whole = [int(t) for t in m.generate_greedy(prompt, n_new)[0]]
+        assert [relabel.get(t, t) for t in whole] == full          # the relabelled model walks the same path
+        l0 = tb.launch_count()
+        stopped = [int(t) for t in m.generate_greedy(prompt, n_new, stop_on_eos=True)[0]]
+        launches = tb.launch_count() - l0
+        assert stopped == whole[: idx + 1] and stopped[-1] == 2
+        # prompt launch + ceil(idx / 32) chunks instead of the 4 chunks of 119 steps
+        assert launches <= 1 + (idx + 31) // 32 + 1 < 1 + 4
+    finally:
+        m.free()

@@ -14,6 +14,8 @@ namespace tib {
 // page table is tables[b * pages_per_seq ..]
 __global__ void rope_kv_batch_kernel(float* qkv, int H, int rope_dim, const float* inv_freq, const int* pos_ptr, float* k_pool, float* v_pool,
                                      const int* tables, int pages_per_seq, int page_tokens) {
+    pdl_wait_prior_grid();       // (no-op unless launched with programmatic stream serialization: the lockstep step's graph)
+    pdl_launch_dependents();
     const int b = blockIdx.x;
     const int pos = *pos_ptr;
     float* row = qkv + (size_t)b * 3 * H;
@@ -45,6 +47,8 @@ constexpr int kDigitsThreads = 1024, kDigitsVecs = 4;   // 4 float4 per thread
 __global__ void __launch_bounds__(kDigitsThreads) rmsnorm_digits_small_kernel(const float* x, const float* gu, const float* w, float eps, int K,
                                                                                int m_pad, int k_pad, int8_t* planes, float* sx_out, long long* sxf_out,
                                                                                int tile_layout) {
+    pdl_wait_prior_grid();       // (no-op unless launched with programmatic stream serialization: the lockstep step's graph)
+    pdl_launch_dependents();
     __shared__ float red[32];
     __shared__ long long redl[32];
     const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -138,6 +142,8 @@ __global__ void __launch_bounds__(kDigitsThreads) rmsnorm_digits_small_kernel(co
 // its output number s - (lens[b] - 1): that is the column of out[b][...] the pick goes to (nothing is written before the
 // sequence's prompt has ended or after its n_new-th token).
 __global__ void argmax_rows_kernel(const float* logits, int V, int* tokens, int* out, int out_stride, const int* pos_ptr, const int* lens) {
+    pdl_wait_prior_grid();       // (no-op unless launched with programmatic stream serialization: the lockstep step's graph)
+    pdl_launch_dependents();
     __shared__ unsigned long long best[32];
     const int b = blockIdx.x;
     const float* row = logits + (size_t)b * V;
@@ -168,6 +174,8 @@ __global__ void argmax_rows_kernel(const float* logits, int V, int* tokens, int*
 // start of a batched step: sequence b is fed its prompt token of this position while its prompt lasts, its own last pick after
 // that (prompts: [max_len][B], column b = sequence b, padded)
 __global__ void batch_feed_kernel(const int* prompts, const int* lens, const int* pos_ptr, int B, int* tokens) {
+    pdl_wait_prior_grid();       // (no-op unless launched with programmatic stream serialization: the lockstep step's graph)
+    pdl_launch_dependents();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const int s = *pos_ptr;
@@ -186,6 +194,8 @@ __global__ void kv_pages_copy_kernel(float* const* k_pools, float* const* v_pool
 
 // end of a batched step: every sequence is one token longer; `sampled` steps also advance the output column
 __global__ void batch_advance_kernel(int* pos_step, int sampled) {
+    pdl_wait_prior_grid();       // (no-op unless launched with programmatic stream serialization: the lockstep step's graph)
+    pdl_launch_dependents();
     pos_step[0] += 1;
     if (sampled) pos_step[1] += 1;
 }

@@ -1126,6 +1126,27 @@ int gemm_q_dev(QWeight& w, const float* x_dev, float* y_dev, int M, float* kerne
     return 0;
 }
 
+// Launch of a kernel of the lockstep step with programmatic stream serialization: the kernel may start while its predecessor is
+// still running and blocks in griddepcontrol.wait (every kernel launched through here has one at its top, the 32-row GEMM after its
+// shared-memory / TMEM prologue) until the predecessor has completed.  Captured into the step graphs as programmatic edges.
+static bool g_batch_pdl = true;
+template <typename... KArgs, typename... Args>
+int launch_step(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = g_stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_batch_pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+    ++g_launches;
+    return 0;
+}
+
 // ---- batched prefill on the tensor cores --------------------------------------------------------------------------
 // One GEMM of the prefill path: activations are already digit planes; no host synchronisation.
 // split factor of the 32-row GEMM: (N / 128) * S CTAs should fill the SMs in whole waves, with >= 6 k-steps per CTA
@@ -1142,7 +1163,8 @@ int launch_small_gemm(Model& m, QWeight& w, int m_pad, const GemmArgs& g) {
     if (m.pf_ws.n < (size_t)w.n_pad * kSmallRows || m.pf_cnt.n < (size_t)tiles) return fail("internal: split-K workspace too small");
     SplitKArgs sk{reinterpret_cast<const uint8_t*>(m.pf_planes.p), m.pf_ws.p, m.pf_cnt.p, w.n_pad, nullptr};
     const int S = small_gemm_splits(tiles, w.k_pad / kGemmBK);
-    gemm_i8_tc_small_kernel<<<dim3(tiles, S), kSmallThreads, kSmallSmemBytes, g_stream>>>(g, sk);
+    TRY(launch_step(gemm_i8_tc_small_kernel, dim3(tiles, S), dim3(kSmallThreads), kSmallSmemBytes, g, sk));
+    --g_launches;   // (the caller counts this launch)
     return 0;
 }
 int pf_gemm(Model& m, QWeight& w, int M, int m_pad, float* y, const float* resid) {
@@ -1305,9 +1327,9 @@ bool batch_eligible(const Model& m) {
 int batch_digits(Model& m, const float* x, const float* gu, const float* norm_w, int B, int K, int m_pad, int k_pad) {
     const bool small = K % 4 == 0 && k_pad <= 4 * kDigitsThreads * kDigitsVecs;
     if (small && B <= kSmallRows) {
-        rmsnorm_digits_small_kernel<<<B, kDigitsThreads, 0, g_stream>>>(x, gu, norm_w, m.cfg.rms_eps, K, m_pad, k_pad, m.pf_planes.p, m.pf_sx.p, m.pf_sxf.p, 1);
+        TRY(launch_step(rmsnorm_digits_small_kernel, dim3(B), dim3(kDigitsThreads), 0, x, gu, norm_w, m.cfg.rms_eps, K, m_pad, k_pad, m.pf_planes.p, m.pf_sx.p,
+                        m.pf_sxf.p, 1));
         m.pf_small_layout = true;
-        ++g_launches;
         CK(cudaGetLastError());
         return 0;
     }
@@ -1338,15 +1360,14 @@ int batch_forward(Model& m, BatchState& bs, bool lm_head) {
     const int m_pad = (B + kGemmBM - 1) / kGemmBM * kGemmBM;
     const int rope_dim = m.cfg.rope_mode == 1 ? H / m.cfg.heads : 0;
     const bool tp = m.tp > 1;
-    embed_rows_kernel<<<B, 256, 0, g_stream>>>(m.tok_emb.p, bs.tokens.p, m.pf_x.p, H);
-    ++g_launches;
+    TRY(launch_step(embed_rows_kernel, dim3(B), dim3(256), 0, (const float*)m.tok_emb.p, (const int*)bs.tokens.p, m.pf_x.p, H));
     for (size_t l = 0; l < m.layers.size(); ++l) {
         Layer& ly = m.layers[l];
         const int Il = ly.down->L.K;   // this rank's share of the intermediate width
         TRY(batch_digits(m, m.pf_x.p, nullptr, ly.attn_norm.p, B, H, m_pad, ly.qkv->k_pad));
         TRY(pf_gemm(m, *ly.qkv, B, m_pad, m.pf_qkv.p, nullptr));
-        rope_kv_batch_kernel<<<dim3(B, std::max(1, Hl / 512)), 256, 0, g_stream>>>(m.pf_qkv.p, Hl, rope_dim, m.inv_freq.p, bs.pos_step.p, bs.k[l].p, bs.v[l].p, bs.tables.p,
-                                                       bs.pages_per_seq, m.page_tokens);
+        TRY(launch_step(rope_kv_batch_kernel, dim3(B, std::max(1, Hl / 512)), dim3(256), 0, m.pf_qkv.p, Hl, rope_dim, (const float*)m.inv_freq.p, (const int*)bs.pos_step.p,
+                        bs.k[l].p, bs.v[l].p, (const int*)bs.tables.p, bs.pages_per_seq, m.page_tokens));
         AttnArgs a{};
         a.q = m.pf_qkv.p;
         a.k_pool = bs.k[l].p;
@@ -1370,9 +1391,8 @@ int batch_forward(Model& m, BatchState& bs, bool lm_head) {
         a.ztable = bs.pages_per_seq;
         a.zpart_o = (size_t)m.attn_heads * bs.max_splits * m.attn_dim;
         a.zpart_ml = (size_t)m.attn_heads * bs.max_splits * 2;
-        attn_partial_kernel<<<dim3(m.attn_heads, bs.max_splits, B), kAttnThreads, m.attn_smem, g_stream>>>(a);
-        attn_combine_kernel<<<dim3(m.attn_heads, 1, B), 256, 0, g_stream>>>(a);
-        g_launches += 3;
+        TRY(launch_step(attn_partial_kernel, dim3(m.attn_heads, bs.max_splits, B), dim3(kAttnThreads), m.attn_smem, a));
+        TRY(launch_step(attn_combine_kernel, dim3(m.attn_heads, 1, B), dim3(256), 0, a));
         TRY(batch_digits(m, m.pf_attn.p, nullptr, nullptr, B, Hl, m_pad, ly.o->k_pad));
         if (tp) {   // row-parallel: partial sums of all ranks, then the residual
             TRY(pf_gemm(m, *ly.o, B, m_pad, bs.ar.p, nullptr));
@@ -1406,15 +1426,12 @@ int batch_forward(Model& m, BatchState& bs, bool lm_head) {
 
 int batch_step(Model& m, BatchState& bs, bool sample, int out_stride) {
     const int B = bs.B, V = m.cfg.vocab;
-    batch_feed_kernel<<<(B + 127) / 128, 128, 0, g_stream>>>(bs.prompts.p, bs.lens.p, bs.pos_step.p, B, bs.tokens.p);
-    ++g_launches;
+    TRY(launch_step(batch_feed_kernel, dim3((B + 127) / 128), dim3(128), 0, (const int*)bs.prompts.p, (const int*)bs.lens.p, (const int*)bs.pos_step.p, B, bs.tokens.p));
     TRY(batch_forward(m, bs, sample));
-    if (sample) {
-        argmax_rows_kernel<<<B, 1024, 0, g_stream>>>(bs.logits.p, V, bs.tokens.p, bs.out.p, out_stride, bs.pos_step.p, bs.lens.p);
-        ++g_launches;
-    }
-    batch_advance_kernel<<<1, 1, 0, g_stream>>>(bs.pos_step.p, sample ? 1 : 0);
-    ++g_launches;
+    if (sample)
+        TRY(launch_step(argmax_rows_kernel, dim3(B), dim3(1024), 0, (const float*)bs.logits.p, V, bs.tokens.p, bs.out.p, out_stride, (const int*)bs.pos_step.p,
+                        (const int*)bs.lens.p));
+    TRY(launch_step(batch_advance_kernel, dim3(1), dim3(1), 0, bs.pos_step.p, sample ? 1 : 0));
     CK(cudaGetLastError());
     return 0;
 }
@@ -1651,6 +1668,7 @@ int ti_b200_init(int device) {
     g_device = device;
     const char* pdl = getenv("TURBOINFER_B200_PDL");
     g_use_pdl = pdl ? atoi(pdl) != 0 : true;   // programmatic dependent launch of the stand-alone GEMV: on unless TURBOINFER_B200_PDL=0
+    if (const char* e = getenv("TURBOINFER_B200_BATCH_PDL")) g_batch_pdl = atoi(e) != 0;   // A/B: programmatic launches inside the lockstep step
     return set_kernel_attrs();
 }
 
@@ -2564,6 +2582,7 @@ int ti_b200_decode_step(ti_model_t h, int32_t token, float* logits_host, int32_t
     return 0;
 }
 
+constexpr int kEosChunk = 32;   // decode steps per launch when the generation may end early (stop_on_eos)
 int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_prompt, int32_t n_new, int32_t stop_on_eos,
                             int32_t* out_tokens, int32_t* n_out, float* logits_host, float* decode_ms) {
     TRY(need_init());
@@ -2595,6 +2614,7 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
     CK(cudaEventCreate(&e1));
     CK(cudaEventCreate(&ep));
     CK(cudaEventRecord(ep, g_stream));
+    int steps_done = 0;   // decode steps after the prompt
     if (m.use_mega) {
         // launch 1: the prompt (its last step picks token 0); launch 2: the decode loop, timed.
         // Long prompts (>= 32 tokens besides the last one, the reference's own GEMM threshold, tensor_engine.cpp:561) go
@@ -2610,7 +2630,24 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
             TRY(run_mega(m, n_prompt, n_prompt, n_new > 0 ? n_prompt - 1 : n_prompt));
         }
         CK(cudaEventRecord(e0, g_stream));
-        TRY(run_mega(m, 0, n_new - 1, 0));
+        if (stop_on_eos && n_new - 1 > kEosChunk) {
+            // generate() stops at the first EOS (:760).  The persistent launch cannot be cut short from inside (its producer warp
+            // runs ahead of the consumers), so with stop_on_eos it is issued in chunks and the host looks at the tokens in between:
+            // a generation that ends after 20 of 256 tokens costs one chunk, not 256 steps.
+            std::vector<int> seen(n_new);
+            while (steps_done < n_new - 1) {
+                const int c = std::min(kEosChunk, n_new - 1 - steps_done);
+                TRY(run_mega(m, 0, c, 0));
+                steps_done += c;
+                if (steps_done >= n_new - 1) break;
+                CK(cudaMemcpyAsync(seen.data(), m.out_tokens.p, (size_t)(1 + steps_done) * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+                CK(cudaStreamSynchronize(g_stream));
+                if (std::find(seen.begin(), seen.begin() + 1 + steps_done, 2) != seen.begin() + 1 + steps_done) break;
+            }
+        } else {
+            TRY(run_mega(m, 0, n_new - 1, 0));
+            steps_done = std::max(0, n_new - 1);
+        }
         CK(cudaEventRecord(e1, g_stream));
     } else {
     // prefill: the prompt goes through the same incremental step, one token at a time; only the last one needs logits
@@ -2623,14 +2660,16 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
     CK(cudaEventRecord(e0, g_stream));
     // the last prompt step already produced token 0; every further step feeds the token the previous one picked
     for (int i = 1; i < n_new; ++i) TRY(run_step(m, true));
+    steps_done = std::max(0, n_new - 1);
     CK(cudaEventRecord(e1, g_stream));
     }
-    m.host_pos = n_prompt + std::max(0, n_new - 1);
-    std::vector<int> toks(std::max(n_new, 1));
-    if (n_new > 0) CK(cudaMemcpyAsync(toks.data(), m.out_tokens.p, n_new * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
-    if (logits_host && n_new > 0) {
-        TRY(gather_sharded_logits(m, m.hist.p, (size_t)n_new * V));
-        CK(cudaMemcpyAsync(logits_host, m.hist.p, (size_t)n_new * V * 4, cudaMemcpyDeviceToHost, g_stream));
+    m.host_pos = n_prompt + steps_done;
+    const int have = n_new > 0 ? 1 + steps_done : 0;   // tokens on the device (fewer than n_new after an early EOS)
+    std::vector<int> toks(std::max(n_new, 1), 0);
+    if (have > 0) CK(cudaMemcpyAsync(toks.data(), m.out_tokens.p, have * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    if (logits_host && have > 0) {
+        TRY(gather_sharded_logits(m, m.hist.p, (size_t)have * V));
+        CK(cudaMemcpyAsync(logits_host, m.hist.p, (size_t)have * V * 4, cudaMemcpyDeviceToHost, g_stream));
     }
     CK(cudaStreamSynchronize(g_stream));
     float ms = 0.f;
@@ -2640,9 +2679,9 @@ int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_promp
     cudaEventDestroy(e1);
     cudaEventDestroy(ep);
     if (decode_ms) *decode_ms = ms;
-    int produced = n_new;
+    int produced = have;
     if (stop_on_eos)
-        for (int i = 0; i < n_new; ++i)
+        for (int i = 0; i < have; ++i)
             if (toks[i] == 2) { produced = i + 1; break; }  // hard-coded EOS id 2 (:760)
     for (int i = 0; i < produced; ++i) out_tokens[i] = toks[i];
     if (n_out) *n_out = produced;
@@ -3111,6 +3150,8 @@ int ti_b200_generate_sampled(ti_model_t h, const int32_t* prompt, int32_t n_prom
     TRY(prompt_pass(m, prompt, n_prompt));
     CK(cudaEventRecord(e0, g_stream));
     if (m.lm_sharded && m.hist.n < (size_t)V) TRY(m.hist.alloc((size_t)V));
+    int sampled = 0, passes = 0;   // tokens picked / decode passes run after the prompt
+    std::vector<int> seen;
     for (int i = 0; i < n_new; ++i) {
         const float* row = m.logits.p;
         if (m.lm_sharded) {   // every rank samples the same full row with the same uniform: identical tokens on all ranks
@@ -3120,15 +3161,22 @@ int ti_b200_generate_sampled(ti_model_t h, const int32_t* prompt, int32_t n_prom
         }
         TRY(launch_sample(row, 1, V, V, temperature, top_k, top_p, seed, nullptr, i, m.smp_tokens.p + i, m.smp_logprobs.p + i, nullptr, nullptr, 0,
                           &m.state.p->token));
-        if (i + 1 < n_new) TRY(decode_pass(m));
+        ++sampled;
+        if (stop_on_eos && sampled % kEosChunk == 0 && i + 1 < n_new) {   // look at the tokens so far: stop issuing steps after an EOS (:760)
+            seen.resize(sampled);
+            CK(cudaMemcpyAsync(seen.data(), m.smp_tokens.p, (size_t)sampled * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+            CK(cudaStreamSynchronize(g_stream));
+            if (std::find(seen.begin(), seen.end(), 2) != seen.end()) break;
+        }
+        if (i + 1 < n_new) { TRY(decode_pass(m)); ++passes; }
     }
     CK(cudaEventRecord(e1, g_stream));
-    m.host_pos = n_prompt + std::max(0, n_new - 1);
+    m.host_pos = n_prompt + passes;
     std::vector<int> toks(cap);
     std::vector<float> lps(cap);
-    if (n_new > 0) {
-        CK(cudaMemcpyAsync(toks.data(), m.smp_tokens.p, n_new * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
-        CK(cudaMemcpyAsync(lps.data(), m.smp_logprobs.p, n_new * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
+    if (sampled > 0) {
+        CK(cudaMemcpyAsync(toks.data(), m.smp_tokens.p, sampled * sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaMemcpyAsync(lps.data(), m.smp_logprobs.p, sampled * sizeof(float), cudaMemcpyDeviceToHost, g_stream));
     }
     CK(cudaStreamSynchronize(g_stream));
     float ms = 0.f;
@@ -3136,9 +3184,9 @@ int ti_b200_generate_sampled(ti_model_t h, const int32_t* prompt, int32_t n_prom
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (decode_ms) *decode_ms = ms;
-    int produced = n_new;
+    int produced = sampled;
     if (stop_on_eos)
-        for (int i = 0; i < n_new; ++i)
+        for (int i = 0; i < sampled; ++i)
             if (toks[i] == 2) { produced = i + 1; break; }  // :760
     for (int i = 0; i < produced; ++i) {
         out_tokens[i] = toks[i];

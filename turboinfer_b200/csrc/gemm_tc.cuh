@@ -337,14 +337,18 @@ gemm_i8_tc_small_kernel(const GemmArgs g, const SplitKArgs sk) {
         mbar_init(tmem_full, 1);
         fence_mbar_init();
     }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(kSmallTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // Everything above touches shared memory and TMEM only: under programmatic dependent launch (the lockstep step's graph) it
+    // overlaps the tail of the previous kernel; the activations, scales and split-K workspace are read after this point.
+    pdl_wait_prior_grid();
+    pdl_launch_dependents();
     if (threadIdx.x < kSmallRows) {
         const bool ok = (int)threadIdx.x < g.M;
         s_sx[threadIdx.x] = ok ? g.sx[threadIdx.x] : 0.f;
         s_off[threadIdx.x] = ok ? g.sxf[threadIdx.x] : 0;
-    }
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(kSmallTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();

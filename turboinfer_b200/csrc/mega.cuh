@@ -593,6 +593,8 @@ __device__ __forceinline__ AttnArgs attn_for_sequence(AttnArgs a, int z) {
 }
 __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnArgs a0) {
     extern __shared__ float attn_dyn_smem[];
+    pdl_wait_prior_grid();       // (no-op unless launched with programmatic stream serialization: the lockstep step's graph)
+    pdl_launch_dependents();
     const AttnArgs a = attn_for_sequence(a0, blockIdx.z);
     const int t = *a.pos_ptr + a.t_bias;
     int nsplit, chunk;
@@ -603,6 +605,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_partial_kernel(const AttnAr
     else (void)attn_item<kAttnThreads>(a, blockIdx.x, j, j * chunk, min(t, (j + 1) * chunk), attn_dyn_smem, nsplit == 1);
 }
 __global__ void __launch_bounds__(kAttnThreads) attn_combine_kernel(const AttnArgs a0) {
+    pdl_wait_prior_grid();       // (no-op unless launched with programmatic stream serialization: the lockstep step's graph)
+    pdl_launch_dependents();
     const AttnArgs a = attn_for_sequence(a0, blockIdx.z);
     const int t = *a.pos_ptr + a.t_bias;
     int nsplit, chunk;

@@ -593,6 +593,8 @@ __global__ void relu_rows_kernel(const float* up, float* act, size_t n) {
 }
 // x[m][:] = emb[token_m][:]
 __global__ void embed_rows_kernel(const float* emb, const int* tokens, float* x, int H) {
+    pdl_wait_prior_grid();       // (no-op unless launched with programmatic stream serialization: the lockstep step's graph)
+    pdl_launch_dependents();
     const int m = blockIdx.x;
     const float* e = emb + (size_t)tokens[m] * H;
     for (int i = threadIdx.x; i < H; i += blockDim.x) x[(size_t)m * H + i] = e[i];
