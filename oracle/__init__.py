@@ -350,6 +350,32 @@ class Oracle:
         return [dict(tokens=[int(t) for t in out[i, : lens[i]]], log_prob=float(lp[i]), score=float(sc[i]), finished=bool(fin[i]))
                 for i in range(n)]
 
+    def generate_literal_sampled(self, vocab: int, hidden: int, layers: int, qtype: int, prompt: Sequence[int], n_new: int, *,
+                                 temperature: float, top_k: int, top_p: float, u: float = 0.5) -> np.ndarray:
+        """generate() on the literal model through the sampling pipeline (both oracles; u matters only to the restatement)"""
+        L = self.lib
+        i32p = C.POINTER(C.c_int32)
+        L.tio_generate_literal_sampled.restype = C.c_int
+        L.tio_generate_literal_sampled.argtypes = [C.c_int] * 4 + [i32p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_float, i32p]
+        p = np.ascontiguousarray(prompt, dtype=np.int32)
+        out = np.zeros(max(n_new, 1), dtype=np.int32)
+        n = L.tio_generate_literal_sampled(vocab, hidden, layers, qtype, p.ctypes.data_as(i32p), p.size, n_new, temperature, top_k, top_p, u,
+                                           out.ctypes.data_as(i32p))
+        if n < 0:
+            raise RuntimeError("tio_generate_literal_sampled failed")
+        return out[:n].copy()
+
+    def logprobs_literal(self, vocab: int, hidden: int, layers: int, qtype: int, tokens: Sequence[int]) -> np.ndarray:
+        """compute_logprobs on the literal benchmark model (both oracles)"""
+        L = self.lib
+        L.tio_logprobs_literal.restype = C.c_int
+        L.tio_logprobs_literal.argtypes = [C.c_int] * 4 + [C.POINTER(C.c_int32), C.c_int, _f]
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        out = np.zeros(t.size, dtype=np.float32)
+        if L.tio_logprobs_literal(vocab, hidden, layers, qtype, t.ctypes.data_as(C.POINTER(C.c_int32)), t.size, _fp(out)) != t.size:
+            raise RuntimeError("tio_logprobs_literal failed")
+        return out
+
     def beam_search_literal(self, vocab: int, hidden: int, layers: int, qtype: int, prompt: Sequence[int], max_new: int, beam_size: int, *,
                             temperature: float = 1.0, top_k: int = 50, top_p: float = 0.9, length_penalty: float = 1.0):
         """generate_beam_search on the literal benchmark model (both oracles) -> [dict(tokens, avg_logprob, finished)]"""

@@ -299,6 +299,50 @@ int tio_generate_literal(int vocab, int hidden, int layers, int qtype, const int
     }
 }
 
+int tio_generate_literal_sampled(int vocab, int hidden, int layers, int qtype, const int32_t* prompt, int n_prompt, int n_new,
+                                 float temperature, int top_k, float top_p, float u, int32_t* out_tokens) {
+    (void)u;   // the reference draws from its own time-seeded generator (:472)
+    try {
+        mdl::ModelData md = literal_model(vocab, hidden, layers);
+        if (qtype == TIO_QINT8 || qtype == TIO_QINT4) {
+            opt::QuantizationConfig qc;
+            qc.type = static_cast<opt::QuantizationType>(qtype);
+            qc.symmetric = true;
+            md = opt::Quantizer(qc).quantize_model(md);
+        }
+        mdl::InferenceConfig cfg;
+        cfg.temperature = temperature;
+        cfg.top_k = static_cast<size_t>(top_k);
+        cfg.top_p = top_p;
+        mdl::InferenceEngine eng(md, cfg);
+        auto res = eng.generate(std::vector<int>(prompt, prompt + n_prompt), static_cast<size_t>(n_new), false);
+        const int produced = static_cast<int>(res.tokens.size()) - n_prompt;
+        for (int i = 0; i < produced; ++i) out_tokens[i] = res.tokens[n_prompt + i];
+        return produced;
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
+
+int tio_logprobs_literal(int vocab, int hidden, int layers, int qtype, const int32_t* tokens, int n, float* out) {
+    try {
+        mdl::ModelData md = literal_model(vocab, hidden, layers);
+        if (qtype == TIO_QINT8 || qtype == TIO_QINT4) {
+            opt::QuantizationConfig qc;
+            qc.type = static_cast<opt::QuantizationType>(qtype);
+            qc.symmetric = true;
+            md = opt::Quantizer(qc).quantize_model(md);
+        }
+        mdl::InferenceEngine eng(md, mdl::InferenceConfig{});
+        const std::vector<float> lp = eng.compute_logprobs(std::vector<int>(tokens, tokens + n));
+        if (static_cast<int>(lp.size()) != n) return -2;
+        std::memcpy(out, lp.data(), sizeof(float) * lp.size());
+        return n;
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
+
 int tio_beam_search_literal(int vocab, int hidden, int layers, int qtype, const int32_t* prompt, int n_prompt, int max_new, int beam_size,
                             float temperature, int top_k, float top_p, float length_penalty, int32_t* out_tokens, int32_t* out_lens,
                             float* out_avg_logprob, int32_t* out_finished) {

@@ -939,3 +939,51 @@ int tio_beam_search_literal(int vocab, int hidden, int layers, int qtype, const 
     free(lp); free(up); free(down); free(lm);
     return n;
 }
+
+/* compute_logprobs on the literal benchmark model (level C): forward_pass over the tokens ([1, T, V] logits, which depend on T
+ * only) and the log-softmax of every position (:919-944) -- in the compiled reference InferenceEngine::compute_logprobs itself */
+int tio_logprobs_literal(int vocab, int hidden, int layers, int qtype, const int32_t* tokens, int n, float* out) {
+    if (n <= 0) return -1;
+    const size_t V = vocab, H = hidden, L = layers, I = H * 4;
+    float* up = ramp(H * I, 0, 200, 0.02f);
+    float* down = ramp(I * H, 0, 200, 0.02f);
+    float* lm = ramp(H * V, 0, 500, 0.01f);
+    literal_quant_inplace(up, H * I, qtype);
+    literal_quant_inplace(down, I * H, qtype);
+    literal_quant_inplace(lm, H * V, qtype);
+    float* logits = (float*)malloc((size_t)n * V * sizeof(float));
+    literal_forward_rows((size_t)n, H, I, V, L, up, down, lm, logits, 1);
+    tio_logprobs(logits, (size_t)n, V, tokens, out);
+    free(logits); free(up); free(down); free(lm);
+    return n;
+}
+
+/* generate() on the literal benchmark model with the sampling pipeline switched on (temperature, top_k, top_p as given): every
+ * token goes through tio_sample with the uniform u.  With a top_p so small that the nucleus is ONE token the draw does not depend
+ * on the generator, which is how the temperature / top-k / softmax / top-p stages are pinned against the compiled reference
+ * (whose std::mt19937 is time-seeded, :472). */
+int tio_generate_literal_sampled(int vocab, int hidden, int layers, int qtype, const int32_t* prompt, int n_prompt, int n_new,
+                                 float temperature, int top_k, float top_p, float u, int32_t* out_tokens) {
+    (void)prompt;
+    if (n_prompt <= 0 || n_new < 0) return -1;
+    const size_t V = vocab, H = hidden, L = layers, I = H * 4;
+    float* up = ramp(H * I, 0, 200, 0.02f);
+    float* down = ramp(I * H, 0, 200, 0.02f);
+    float* lm = ramp(H * V, 0, 500, 0.01f);
+    literal_quant_inplace(up, H * I, qtype);
+    literal_quant_inplace(down, I * H, qtype);
+    literal_quant_inplace(lm, H * V, qtype);
+    float* logits = (float*)malloc(V * sizeof(float));
+    literal_forward((size_t)n_prompt, H, I, V, L, up, down, lm, logits);
+    int produced = 0;
+    size_t total = (size_t)n_prompt;
+    for (int i = 0; i < n_new; ++i) {
+        const int tok = tio_sample(logits, V, temperature, top_k, top_p, u, NULL);
+        out_tokens[produced++] = tok;
+        ++total;
+        if (tok == 2 || total >= 2048) break;
+        literal_forward(1, H, I, V, L, up, down, lm, logits);
+    }
+    free(up); free(down); free(lm); free(logits);
+    return produced;
+}

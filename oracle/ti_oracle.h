@@ -128,6 +128,14 @@ int tio_beam_expand(const float* logits, size_t vocab, float temperature, int to
 int tio_beam_search(const tio_model* m, const int32_t* prompt, int n_prompt, int max_new, int beam_size, float temperature, int top_k,
                     float top_p, float length_penalty, int eos_token, int32_t* out_tokens, int32_t* out_lens, float* out_logprob,
                     float* out_score, int32_t* out_finished);
+/* generate() on the literal benchmark model through the SAMPLING pipeline (both oracles; in the compiled reference the engine's
+ * own generate with these InferenceConfig values; u is ignored there).  Deterministic -- and therefore comparable -- when top_p
+ * leaves a one-token nucleus. */
+int tio_generate_literal_sampled(int vocab, int hidden, int layers, int qtype, const int32_t* prompt, int n_prompt, int n_new,
+                                 float temperature, int top_k, float top_p, float u, int32_t* out_tokens);
+/* compute_logprobs (:873-954) on the literal benchmark model (level C): pins tio_logprobs against the compiled reference's own
+ * InferenceEngine::compute_logprobs.  Returns n (or < 0).  Both oracles. */
+int tio_logprobs_literal(int vocab, int hidden, int layers, int qtype, const int32_t* tokens, int n, float* out);
 /* generate_beam_search on the literal benchmark model (level C, as tio_generate_literal): in the compiled reference this is
  * InferenceEngine::generate_beam_search itself, which pins the expansion arithmetic and the bookkeeping of the restatement.
  * out_avg_logprob = cumulative log-probability / new tokens (GenerationResult::logprobs, :862-865).  Both oracles. */

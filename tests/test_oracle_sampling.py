@@ -1,6 +1,7 @@
 """The oracle's restatement of sample_next_token / compute_logprobs (no GPU): invariants the reference algorithm has, and
 the one case where it can be pinned against the compiled reference's behaviour (top_k = 1 is an arg-max)."""
 import numpy as np
+import pytest
 
 import oracle
 
@@ -45,3 +46,33 @@ def test_logprobs_restatement():
             assert abs(got[i] - ref[i, t]) < 1e-5
         else:
             assert got[i] == -20.0                                   # LOGPROB_INVALID_TOKEN, inference_engine.cpp:933-936
+
+
+@pytest.mark.parametrize("qtype", [3, 0, 1])
+def test_logprobs_port_vs_reference_on_the_literal_model(qtype):
+    """tio_logprobs pinned: the compiled reference's own InferenceEngine::compute_logprobs (:873-954) on the literal benchmark
+    model, against the restatement (literal forward pass + tio_logprobs) -- bit for bit, including the -20 of an invalid id"""
+    if not oracle.ref_available():
+        pytest.skip("the compiled reference (oracle/_ref) is not present")
+    toks = [1, 15, 25, 35, 999, 0, 500]
+    a = oracle.port().logprobs_literal(1000, 256, 4, qtype, toks)
+    b = oracle.ref().logprobs_literal(1000, 256, 4, qtype, toks)
+    np.testing.assert_array_equal(a, b)
+    assert np.all(a <= 0) and np.all(np.isfinite(a))
+
+
+@pytest.mark.parametrize("kw", [dict(temperature=0.8, top_k=50, top_p=1e-6), dict(temperature=1.0, top_k=5, top_p=1e-4),
+                                dict(temperature=1.7, top_k=0, top_p=1e-6)])
+def test_sampling_pipeline_port_vs_reference_with_a_one_token_nucleus(kw):
+    """The reference's generator is time-seeded (:472), but with a top_p so small that the nucleus is a single token the draw
+    cannot matter: the compiled reference's own generate() with temperature / top-k / top-p switched on must then produce what
+    tio_sample produces for ANY uniform.  INT8 literal model (its winning logit is never tied; in the fp32 / INT4 variants the
+    ramp fills tie the maximum and std::sort's order among equals is unspecified)."""
+    if not oracle.ref_available():
+        pytest.skip("the compiled reference (oracle/_ref) is not present")
+    want = oracle.ref().generate_literal_sampled(1000, 256, 4, 0, [1, 15, 25, 35], 12, **kw)
+    for u in (0.0, 0.01, 0.5, 0.99):
+        got = oracle.port().generate_literal_sampled(1000, 256, 4, 0, [1, 15, 25, 35], 12, u=u, **kw)
+        if u == 0.0:
+            continue   # (u == 0 selects index 0 by the loop's `<=`, a case the reference's generator produces with probability 2^-24)
+        np.testing.assert_array_equal(got, want)
