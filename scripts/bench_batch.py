@@ -17,6 +17,8 @@ ap.add_argument("--prompt", type=int, default=4)
 ap.add_argument("--new", type=int, default=256)
 ap.add_argument("--layers", type=int, default=0)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--no-warmup", action="store_true", help="skip the untimed warm-up generation (long prompts: the step graphs are built during the prompt phase, outside the timed decode steps anyway)")
+ap.add_argument("--no-single", action="store_true", help="skip the single-sequence cross-check of row 0")
 ap.add_argument("--tp", action="store_true", help="under torchrun: the ranks form one tensor-parallel group (NCCL all-reduce after o / down)")
 args = ap.parse_args()
 rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -33,14 +35,15 @@ m = tb.Model(meta, tb.Q_INT4 if args.qtype == "int4" else tb.Q_INT8, attn_mode=1
 m.load_synthetic()
 prompts = np.array([prompt_tokens(args.prompt, meta["vocab"], offset=b) for b in range(args.batch)], dtype=np.int32)
 l0 = tb.launch_count()
-m.generate_batch_greedy(prompts, args.new)      # warm-up: builds the K-major weight copies and the step graphs
+if not args.no_warmup:
+    m.generate_batch_greedy(prompts, args.new)      # warm-up: builds the K-major weight copies and the step graphs
 dev, wall = [], []
 for _ in range(args.reps):
     t0 = time.perf_counter()
     toks, _, ms = m.generate_batch_greedy(prompts, args.new)
     wall.append(time.perf_counter() - t0)
     dev.append(ms)
-single, _, _ = m.generate_greedy(prompts[0], min(args.new, 16))
+single = toks[0][:0] if args.no_single else m.generate_greedy(prompts[0], min(args.new, 16))[0]
 H, L, I, V = meta["hidden"], meta["layers"], meta["inter"], meta["vocab"]
 w_elems = L * (4 * H * H + 3 * H * I) + H * V
 t_mid = args.prompt + args.new // 2
@@ -51,7 +54,9 @@ out = {"metric": "decode_tokens_per_s", "value": args.batch * steps / (ms * 1e-3
        "config": {"workload": f"{args.shape}-{args.qtype}-batch{args.batch}-decode{args.new}", "batch": args.batch, "prompt_tokens": args.prompt,
                   "new_tokens": args.new, "path": "tcgen05 INT8 GEMM (three digit planes) + flash-decoding attention per sequence, CUDA graph per step"},
        "ms_per_step": ms / steps, "e2e": {"value": args.batch * args.new / float(np.median(wall)), "unit": "tokens/s"},
-       "step_bytes": {"weights_as_read_by_the_gemm": w_elems, "kv_mid_run": kv, "GBps": (w_elems + kv) / (ms / steps * 1e-3) / 1e9},
+       "step_bytes": {"weights_as_read_by_the_gemm": w_elems, "kv_mid_run": kv, "GBps": (w_elems + kv) / (ms / steps * 1e-3) / 1e9,
+                      "per_gpu": {"weights_GB": w_elems / tp / 1e9, "kv_GB": kv / tp / 1e9, "weights_GBps": w_elems / tp / (ms / steps * 1e-3) / 1e9,
+                                  "kv_GBps": kv / tp / (ms / steps * 1e-3) / 1e9}},
        "row0_equals_single_sequence_engine": bool(np.array_equal(toks[0][: len(single)], single)),
        "gpu_launches": tb.launch_count() - l0, "tokens_tail_row0": [int(x) for x in toks[0][-4:]]}
 if rank == 0:
