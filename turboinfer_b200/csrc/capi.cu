@@ -33,6 +33,7 @@ int g_num_sms = 0;
 cudaStream_t g_stream = nullptr;
 uint64_t g_launches = 0;
 bool g_use_pdl = false;
+static int kEosChunk = 32;   // decode steps per launch when the generation may end early (stop_on_eos); TURBOINFER_B200_EOS_CHUNK for experiments
 bool g_attr_done = false;
 bool g_batch_carveout_done = false;   // the batched step's uniform carve-out preference (reset by shutdown, like g_attr_done)
 
@@ -156,6 +157,10 @@ int set_kernel_attrs() {
     CK(cudaFuncSetAttribute(causal_attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_tc_smem_bytes<64>()));
     CK(cudaFuncSetAttribute(causal_attention_h3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_h3_smem_bytes<128>()));
     CK(cudaFuncSetAttribute(causal_attention_h3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_h3_smem_bytes<64>()));
+    CK(cudaFuncSetAttribute(sample_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
+    CK(cudaFuncSetAttribute(sample_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
+    CK(cudaFuncSetAttribute(beam_expand_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
+    CK(cudaFuncSetAttribute(beam_expand_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 176 * 1024));
     g_attr_done = true;
     return 0;
 }
@@ -1485,7 +1490,10 @@ int launch_sample(const float* logits, int rows, int V, int ld, float temperatur
     a.token_out = token_out; a.logprob_out = logprob_out;
     a.hist_tokens = hist_tokens; a.hist_logprobs = hist_logprobs; a.hist_stride = hist_stride;
     a.feed_token = feed_token;
-    sample_kernel<<<rows, kSampleThreads, 0, g_stream>>>(a);
+    const size_t row_smem = sample_row_smem_bytes(V);
+    a.staged = row_smem ? 1 : 0;
+    if (sample_keys_in_registers(V)) sample_kernel<32><<<rows, kSampleThreads, row_smem, g_stream>>>(a);
+    else sample_kernel<0><<<rows, kSampleThreads, row_smem, g_stream>>>(a);
     ++g_launches;
     CK(cudaGetLastError());
     return 0;
@@ -1668,6 +1676,7 @@ int ti_b200_init(int device) {
     g_device = device;
     const char* pdl = getenv("TURBOINFER_B200_PDL");
     g_use_pdl = pdl ? atoi(pdl) != 0 : true;   // programmatic dependent launch of the stand-alone GEMV: on unless TURBOINFER_B200_PDL=0
+    if (const char* e = getenv("TURBOINFER_B200_EOS_CHUNK")) kEosChunk = std::max(1, atoi(e));
     if (const char* e = getenv("TURBOINFER_B200_BATCH_PDL")) g_batch_pdl = atoi(e) != 0;   // A/B: programmatic launches inside the lockstep step
     return set_kernel_attrs();
 }
@@ -2582,7 +2591,6 @@ int ti_b200_decode_step(ti_model_t h, int32_t token, float* logits_host, int32_t
     return 0;
 }
 
-constexpr int kEosChunk = 32;   // decode steps per launch when the generation may end early (stop_on_eos)
 int ti_b200_generate_greedy(ti_model_t h, const int32_t* prompt, int32_t n_prompt, int32_t n_new, int32_t stop_on_eos,
                             int32_t* out_tokens, int32_t* n_out, float* logits_host, float* decode_ms) {
     TRY(need_init());
@@ -2700,7 +2708,7 @@ static int batch_carveout() {
                          (const void*)rmsnorm_digits_kernel, (const void*)rope_kv_batch_kernel, (const void*)attn_partial_kernel,
                          (const void*)attn_combine_kernel, (const void*)argmax_rows_kernel, (const void*)batch_advance_kernel,
                          (const void*)embed_rows_kernel, (const void*)swiglu_rows_kernel, (const void*)relu_rows_kernel, (const void*)batch_feed_kernel,
-                         (const void*)beam_expand_kernel, (const void*)kv_pages_copy_kernel};
+                         (const void*)beam_expand_kernel<32>, (const void*)beam_expand_kernel<0>, (const void*)kv_pages_copy_kernel};
     for (const void* f : fns) CK(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     g_batch_carveout_done = true;
     return 0;
@@ -2950,7 +2958,9 @@ int ti_b200_beam_search(ti_model_t h, const int32_t* prompt, int32_t n_prompt, i
                 ea.cand_prob = st.cand_prob.p;
                 ea.cand_tok = st.cand_tok.p;
                 ea.cand_cnt = st.cand_cnt.p;
-                beam_expand_kernel<<<B, kSampleThreads, 0, g_stream>>>(ea);
+                ea.staged = sample_row_smem_bytes(V) ? 1 : 0;
+                if (sample_keys_in_registers(V)) beam_expand_kernel<32><<<B, kSampleThreads, sample_row_smem_bytes(V), g_stream>>>(ea);
+                else beam_expand_kernel<0><<<B, kSampleThreads, sample_row_smem_bytes(V), g_stream>>>(ea);
                 ++g_launches;
             }
             batch_advance_kernel<<<1, 1, 0, g_stream>>>(bs.pos_step.p, 0);
@@ -3093,7 +3103,9 @@ int ti_b200_beam_expand(const float* logits_host, size_t rows, size_t vocab, flo
     ea.cand_prob = pr.p;
     ea.cand_tok = tk.p;
     ea.cand_cnt = cn.p;
-    beam_expand_kernel<<<(unsigned)rows, kSampleThreads, 0, g_stream>>>(ea);
+    ea.staged = sample_row_smem_bytes((int)vocab) ? 1 : 0;
+    if (sample_keys_in_registers((int)vocab)) beam_expand_kernel<32><<<(unsigned)rows, kSampleThreads, sample_row_smem_bytes((int)vocab), g_stream>>>(ea);
+    else beam_expand_kernel<0><<<(unsigned)rows, kSampleThreads, sample_row_smem_bytes((int)vocab), g_stream>>>(ea);
     ++g_launches;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(probs_out, pr.p, rows * beam_size * sizeof(float), cudaMemcpyDeviceToHost, g_stream));

@@ -46,7 +46,16 @@ struct SampleArgs {
     float* hist_logprobs;
     int hist_stride;
     int* feed_token;       // optional: where the next decode step reads its input token (StepState::token)
+    int staged;            // 1: the launch carries sample_row_smem_bytes(V) of dynamic shared memory for the scaled row
 };
+// dynamic shared memory of sample_kernel / beam_expand_kernel for a row of V logits (0: too long, read from global memory)
+TIB_HD size_t sample_row_smem_bytes(int V) {
+    const int per = (V + kSampleThreads - 1) / kSampleThreads;
+    const size_t bytes = (size_t)kSampleThreads * (size_t)(per | 1) * sizeof(float);
+    return bytes <= (size_t)176 * 1024 ? bytes : 0;
+}
+// the <32> instances (a thread's keys in registers) serve staged rows of at most 32 logits per thread
+TIB_HD bool sample_keys_in_registers(int V) { return sample_row_smem_bytes(V) != 0 && (V + kSampleThreads - 1) / kSampleThreads <= 32; }
 
 __device__ __forceinline__ uint32_t desc_key(float v) {   // larger value -> larger key
     uint32_t b = __float_as_uint(v);
@@ -107,46 +116,81 @@ __device__ __forceinline__ float block_exscan_f(float v, float* wsum, float* tot
     return r;
 }
 
-// Radix select over the keys of the block's elements (thread t owns [i0, i1)): key of the `need`-th largest value, 4 passes of 8
-// bits from the top.  Returns the key; *need_eq = how many of the elements EQUAL to it belong to the top `need` (the lowest indices).
-template <typename KeyFn>
-__device__ __forceinline__ uint32_t radix_select_key(KeyFn key_of, int i0, int i1, int need, int* hist, int* s_sel, int* s_need, int* need_eq) {
-    const int tid = threadIdx.x;
-    uint32_t prefix = 0, mask = 0;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        for (int b = tid; b < 256; b += kSampleThreads) hist[b] = 0;
-        __syncthreads();
-        for (int i = i0; i < i1; ++i) {
-            const uint32_t key = key_of(i);
-            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int acc = 0, b = 255;
-            for (; b > 0; --b) {
-                if (acc + hist[b] >= need) break;
-                acc += hist[b];
-            }
-            *s_sel = b;
-            *s_need = need - acc;
-        }
-        __syncthreads();
-        prefix |= (uint32_t)*s_sel << shift;
-        mask |= 255u << shift;
-        need = *s_need;
-        __syncthreads();
-    }
-    *need_eq = need;
-    return prefix;
+// Block-wide sums that every thread receives (1 024 threads): warp reduction, one shared word per warp, every warp sums the 32
+// words.  `wbuf` holds two sets of 32 words used alternately (one __syncthreads per sum); the order of the additions is fixed,
+// so float sums are deterministic.
+__device__ __forceinline__ int block_sum_i(int v, int* wbuf, int& parity) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = __reduce_add_sync(0xffffffffu, v);
+    int* buf = wbuf + 32 * parity;
+    if (lane == 0) buf[warp] = v;
+    __syncthreads();
+    parity ^= 1;
+    return __reduce_add_sync(0xffffffffu, buf[lane]);
+}
+__device__ __forceinline__ float block_sum_f(float v, float* wbuf, int& parity) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    float* buf = wbuf + 32 * parity;
+    if (lane == 0) buf[warp] = v;
+    __syncthreads();
+    parity ^= 1;
+    float t = buf[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
 }
 
+// Key of the `need`-th largest element: a bit-by-bit search from the top, each step one block-wide count of the keys >= the
+// candidate (32 counts of register-held keys: ~5 us.  The first two versions used radix histograms -- 32 000 shared atomics on a
+// few hot buckets, then per-warp histograms with __match_any_sync -- and spent 140-200 us per token in them).
+// key_k(k) = key of the thread's k-th own element (0 beyond its range: never counted, a real value's key is never 0).
+// Returns the key; *need_eq = how many of the elements EQUAL to it belong to the top `need` (the lowest indices).
+template <int P, typename KeyK>
+__device__ __forceinline__ uint32_t select_kth_key(KeyK key_k, int per, int need, int* wbuf, int& parity, int* need_eq) {
+    uint32_t prefix = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = prefix | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int k = 0; k < (P ? P : per); ++k) c += key_k(k) >= cand ? 1 : 0;
+        if (block_sum_i(c, wbuf, parity) >= need) prefix = cand;
+    }
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < (P ? P : per); ++k) c += key_k(k) > prefix ? 1 : 0;
+    *need_eq = need - block_sum_i(c, wbuf, parity);
+    return prefix;
+}
+// The largest key T (>= floor_key) such that the mass of the elements with key >= T reaches `target` (0 when even all of them
+// do not, by rounding): the nucleus cut of the wide path.  mass_k(k) = the element's (unnormalised) probability.
+template <int P, typename KeyK, typename MassK>
+__device__ __forceinline__ uint32_t select_mass_key(KeyK key_k, MassK mass_k, int per, uint32_t floor_key, float target, float* wbuf, int& parity) {
+    uint32_t prefix = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = prefix | (1u << bit);
+        float mass = 0.f;
+#pragma unroll
+        for (int k = 0; k < (P ? P : per); ++k) {
+            const uint32_t key = key_k(k);
+            mass += (key >= cand && key >= floor_key) ? mass_k(k) : 0.f;
+        }
+        if (block_sum_f(mass, wbuf, parity) >= target) prefix = cand;
+    }
+    return prefix > floor_key ? prefix : floor_key;
+}
+
+// P = 32: rows of up to 32 768 logits staged in shared memory, every thread's 32 keys held in registers (fully unrolled loops);
+// P = 0: any row, keys recomputed from the row at every use.
+template <int P>
 __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs a) {
-    __shared__ int hist[256];
-    __shared__ float fhist[256];
+    __shared__ int wbuf_i[64];
+    __shared__ float wbuf_f[64];
+    int parity_i = 0, parity_f = 0;
     __shared__ int wsum[32];
     __shared__ float wsumf[32];
-    __shared__ int s_tot, s_sel, s_need, s_token;
+    __shared__ int s_tot, s_sel, s_token;
     __shared__ float s_ftot, s_max, s_sum, s_lp;
     __shared__ int sidx[kTopKMax];
     __shared__ float sval[kTopKMax];      // scaled logit, then probability
@@ -156,17 +200,50 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs
     const int step = a.step_ptr ? *a.step_ptr : a.step;
     const float u = sample_uniform(a.seed + (uint64_t)blockIdx.x * 0x51ED27ull, (uint64_t)step);
     const bool scale = a.temperature != 1.0f && a.temperature > 0.0f;                      // :1578-1582
-    auto val = [&](int i) -> float { const float x = lg[i]; return scale ? x / a.temperature : x; };
     // indices in blocked order: thread t owns [t * per, (t + 1) * per) -- a compaction by thread order is then in index order
     const int per = (V + kSampleThreads - 1) / kSampleThreads;
     const int i0 = min(tid * per, V), i1 = min(i0 + per, V);
+    // The row is read many times (4 radix passes, gathers, sums).  In the blocked order a warp's load touches 32 different cache
+    // lines -- 32 LSU transactions per instruction, ~16 us per pass over 32 000 logits, 144-200 us per token in the first version
+    // of this kernel -- so the scaled row is staged ONCE in shared memory (coalesced global reads), each thread's range at an odd
+    // stride (conflict-free).  Rows too long for shared memory are read from global memory as before.
+    extern __shared__ float s_row[];
+    const int stride = per | 1;
+    if (a.staged) {
+        for (int i = tid; i < V; i += kSampleThreads) {
+            const float x = lg[i];
+            s_row[(i / per) * stride + (i % per)] = scale ? x / a.temperature : x;
+        }
+        __syncthreads();
+    }
+    const float* const own = s_row + tid * stride - i0;   // own[i] for i in [i0, i1)
+    auto val = [&](int i) -> float {   // an element of this thread's own range
+        if (a.staged) return own[i];
+        const float x = lg[i];
+        return scale ? x / a.temperature : x;
+    };
+    auto val_any = [&](int i) -> float {   // any element
+        if (a.staged) return s_row[(i / per) * stride + (i % per)];
+        const float x = lg[i];
+        return scale ? x / a.temperature : x;
+    };
     const bool use_topk = a.top_k > 0 && a.top_k < V;                                        // :1585
     const bool exact = use_topk && a.top_k <= kTopKMax;
+    const int cnt = i1 - i0;
+    uint32_t kreg[P ? P : 1];
+    if (P) {
+#pragma unroll
+        for (int k = 0; k < (P ? P : 1); ++k) kreg[k] = k < cnt ? desc_key(own[i0 + k]) : 0u;
+    }
+    auto key_k = [&](int k) -> uint32_t {
+        if (P) return kreg[k];
+        return k < cnt ? desc_key(val(i0 + k)) : 0u;
+    };
 
     if (exact) {
-        // ---- radix select of the k-th largest key ----
+        // ---- the k-th largest key ----
         int need = 0;   // how many of the elements equal to that key survive (lowest indices)
-        const uint32_t tau = radix_select_key([&](int i) { return desc_key(val(i)); }, i0, i1, a.top_k, hist, &s_sel, &s_need, &need);
+        const uint32_t tau = select_kth_key<P>(key_k, per, a.top_k, wbuf_i, parity_i, &need);
         // ---- gather the survivors in index order ----
         int cgt = 0, ceq = 0;
         for (int i = i0; i < i1; ++i) {
@@ -266,7 +343,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs
         uint32_t kth = 0;   // survivors: key >= kth
         if (use_topk) {
             int need_eq = 0;
-            kth = radix_select_key([&](int i) { return desc_key(val(i)); }, i0, i1, a.top_k, hist, &s_sel, &s_need, &need_eq);
+            kth = select_kth_key<P>(key_k, per, a.top_k, wbuf_i, parity_i, &need_eq);
         }
         float mx = -INFINITY;
         for (int i = i0; i < i1; ++i) {
@@ -293,36 +370,17 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs
         Z = s_ftot;
         uint32_t pth = kth;   // top-p: survivors are the keys >= pth
         if (a.top_p < 1.0f) {
-            // radix search over the key: the largest threshold whose mass from the top reaches top_p * Z
-            const float target = a.top_p * Z;
-            uint32_t prefix = 0, mask = 0;
-            float above = 0.f;   // mass of the keys above the current prefix range
-            for (int pass = 0; pass < 4; ++pass) {
-                const int shift = 24 - 8 * pass;
-                for (int b = tid; b < 256; b += kSampleThreads) fhist[b] = 0.f;
-                __syncthreads();
-                for (int i = i0; i < i1; ++i) {
-                    const uint32_t key = desc_key(val(i));
-                    if (key >= kth && (key & mask) == prefix) atomicAdd(&fhist[(key >> shift) & 255u], expf(val(i) - s_max));
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    float acc = above;
-                    int b = 255;
-                    for (; b > 0; --b) {
-                        if (acc + fhist[b] >= target) break;
-                        acc += fhist[b];
-                    }
-                    s_sel = b;
-                    s_ftot = acc;
-                }
-                __syncthreads();
-                prefix |= (uint32_t)s_sel << shift;
-                mask |= 255u << shift;
-                above = s_ftot;
-                __syncthreads();
+            // the largest threshold whose mass from the top reaches top_p * Z (bit-by-bit search; the masses are held in registers)
+            float ereg[P ? P : 1];
+            if (P) {
+#pragma unroll
+                for (int k = 0; k < (P ? P : 1); ++k) ereg[k] = k < cnt ? expf(own[i0 + k] - s_max) : 0.f;
             }
-            pth = prefix > kth ? prefix : kth;
+            auto mass_k = [&](int k) -> float {
+                if (P) return ereg[k];
+                return k < cnt ? expf(val(i0 + k) - s_max) : 0.f;
+            };
+            pth = select_mass_key<P>(key_k, mass_k, per, kth, a.top_p * Z, wbuf_f, parity_f);
         }
         // renormalise over the final survivors and walk the CDF: per-thread sequential, block-wide exclusive scan between
         float mine = 0.f;
@@ -362,9 +420,9 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs
             float lp = -INFINITY;
             if (target <= 0.f) {   // uniform of exactly 0: index 0 (see the exact path)
                 tok = 0;
-                lp = desc_key(val(0)) >= pth ? logf(expf(val(0) - s_max) / Z2) : -INFINITY;
-            } else if (desc_key(val(V - 1)) >= pth) {
-                lp = logf(expf(val(V - 1) - s_max) / Z2);
+                lp = desc_key(val_any(0)) >= pth ? logf(expf(val_any(0) - s_max) / Z2) : -INFINITY;
+            } else if (desc_key(val_any(V - 1)) >= pth) {
+                lp = logf(expf(val_any(V - 1) - s_max) / Z2);
             }
             s_token = tok;
             s_lp = lp;
@@ -403,13 +461,16 @@ struct BeamExpandArgs {
     float* cand_prob;      // [rows][beam]
     int* cand_tok;         // [rows][beam]
     int* cand_cnt;         // [rows]
+    int staged;            // as SampleArgs::staged
 };
+template <int P>
 __global__ void __launch_bounds__(kSampleThreads) beam_expand_kernel(const BeamExpandArgs a) {
-    __shared__ int hist[256];
-    __shared__ float fhist[256];
+    __shared__ int wbuf_i[64];
+    __shared__ float wbuf_f[64];
+    int parity_i = 0, parity_f = 0;
     __shared__ int wsum[32];
     __shared__ float wsumf[32];
-    __shared__ int s_tot, s_sel, s_need;
+    __shared__ int s_tot, s_sel;
     __shared__ float s_ftot, s_max, s_sum;
     __shared__ int sidx[kTopKMax];
     __shared__ float sval[kTopKMax];
@@ -417,10 +478,34 @@ __global__ void __launch_bounds__(kSampleThreads) beam_expand_kernel(const BeamE
     const int tid = threadIdx.x, V = a.V;
     const float* lg = a.logits + (size_t)blockIdx.x * a.ld;
     const bool scale = a.temperature != 1.0f;                                                 // :1972-1976
-    auto val = [&](int i) -> float { const float x = lg[i]; return scale ? x / a.temperature : x; };
-    auto key_of = [&](int i) -> uint32_t { return desc_key(val(i)); };
     const int per = (V + kSampleThreads - 1) / kSampleThreads;
     const int i0 = min(tid * per, V), i1 = min(i0 + per, V);
+    extern __shared__ float s_row[];   // the scaled row, staged once (see sample_kernel)
+    const int stride = per | 1;
+    if (a.staged) {
+        for (int i = tid; i < V; i += kSampleThreads) {
+            const float x = lg[i];
+            s_row[(i / per) * stride + (i % per)] = scale ? x / a.temperature : x;
+        }
+        __syncthreads();
+    }
+    const float* const own = s_row + tid * stride - i0;
+    auto val = [&](int i) -> float {   // an element of this thread's own range
+        if (a.staged) return own[i];
+        const float x = lg[i];
+        return scale ? x / a.temperature : x;
+    };
+    auto key_of = [&](int i) -> uint32_t { return desc_key(val(i)); };
+    const int cnt = i1 - i0;
+    uint32_t kreg[P ? P : 1];
+    if (P) {
+#pragma unroll
+        for (int k = 0; k < (P ? P : 1); ++k) kreg[k] = k < cnt ? desc_key(own[i0 + k]) : 0u;
+    }
+    auto key_k = [&](int k) -> uint32_t {
+        if (P) return kreg[k];
+        return k < cnt ? desc_key(val(i0 + k)) : 0u;
+    };
     const bool use_topk = a.top_k > 0 && a.top_k < V;                                         // :1982
     const bool exact = use_topk && a.top_k <= kTopKMax;
     // ---- softmax over the vocabulary (:1798-1819) ----
@@ -443,7 +528,7 @@ __global__ void __launch_bounds__(kSampleThreads) beam_expand_kernel(const BeamE
     int n = 0;   // entries of the candidate list (sidx, sval), in index order
     if (exact) {
         int need = 0;
-        const uint32_t tau = radix_select_key(key_of, i0, i1, a.top_k, hist, &s_sel, &s_need, &need);
+        const uint32_t tau = select_kth_key<P>(key_k, per, a.top_k, wbuf_i, parity_i, &need);
         int cgt = 0, ceq = 0;
         for (int i = i0; i < i1; ++i) {
             const uint32_t key = key_of(i);
@@ -513,7 +598,7 @@ __global__ void __launch_bounds__(kSampleThreads) beam_expand_kernel(const BeamE
         float Zk = 1.0f;   // mass of the top-k set (1: no top-k filter, nothing is renormalised, :1824-1826)
         if (use_topk) {
             int need_eq = 0;
-            kth = radix_select_key(key_of, i0, i1, a.top_k, hist, &s_sel, &s_need, &need_eq);
+            kth = select_kth_key<P>(key_k, per, a.top_k, wbuf_i, parity_i, &need_eq);
             float mine = 0.f;
             for (int i = i0; i < i1; ++i)
                 if (key_of(i) >= kth) mine += prob(i);
@@ -523,35 +608,16 @@ __global__ void __launch_bounds__(kSampleThreads) beam_expand_kernel(const BeamE
         uint32_t pth = kth;
         float Z2 = Zk;
         if (a.top_p < 1.0f) {
-            const float target = a.top_p * Zk;   // cumulative RENORMALISED probability >= top_p
-            uint32_t prefix = 0, mask = 0;
-            float above = 0.f;
-            for (int pass = 0; pass < 4; ++pass) {
-                const int shift = 24 - 8 * pass;
-                for (int b = tid; b < 256; b += kSampleThreads) fhist[b] = 0.f;
-                __syncthreads();
-                for (int i = i0; i < i1; ++i) {
-                    const uint32_t key = key_of(i);
-                    if (key >= kth && (key & mask) == prefix) atomicAdd(&fhist[(key >> shift) & 255u], prob(i));
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    float acc = above;
-                    int b = 255;
-                    for (; b > 0; --b) {
-                        if (acc + fhist[b] >= target) break;
-                        acc += fhist[b];
-                    }
-                    s_sel = b;
-                    s_ftot = acc;
-                }
-                __syncthreads();
-                prefix |= (uint32_t)s_sel << shift;
-                mask |= 255u << shift;
-                above = s_ftot;
-                __syncthreads();
+            float ereg[P ? P : 1];   // cumulative RENORMALISED probability >= top_p, i.e. mass >= top_p * Zk
+            if (P) {
+#pragma unroll
+                for (int k = 0; k < (P ? P : 1); ++k) ereg[k] = k < cnt ? prob(i0 + k) : 0.f;
             }
-            pth = prefix > kth ? prefix : kth;
+            auto mass_k = [&](int k) -> float {
+                if (P) return ereg[k];
+                return k < cnt ? prob(i0 + k) : 0.f;
+            };
+            pth = select_mass_key<P>(key_k, mass_k, per, kth, a.top_p * Zk, wbuf_f, parity_f);
             float mine = 0.f;
             for (int i = i0; i < i1; ++i)
                 if (key_of(i) >= pth) mine += prob(i);
@@ -565,7 +631,7 @@ __global__ void __launch_bounds__(kSampleThreads) beam_expand_kernel(const BeamE
         const int survivors = s_tot;
         const int want = min(a.beam, survivors);
         int need = 0;
-        const uint32_t tau = radix_select_key(key_of, i0, i1, want, hist, &s_sel, &s_need, &need);   // want <= survivors: tau >= pth
+        const uint32_t tau = select_kth_key<P>(key_k, per, want, wbuf_i, parity_i, &need);   // want <= survivors: tau >= pth
         int cgt = 0, ceq = 0;
         for (int i = i0; i < i1; ++i) {
             const uint32_t key = key_of(i);
