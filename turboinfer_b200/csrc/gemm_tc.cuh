@@ -288,9 +288,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap map_a, const GemmArgs g) {
 //     S = 1); the CTA that arrives last on the tile's counter applies offset, scales and residual, stores the tile and
 //     leaves workspace and counter zeroed for the next GEMM.  S is chosen on the host for GEMMs with few column tiles.
 // warps 0..3: epilogue (TMEM lanes 32w.. = weight columns), warp 4: TMEM allocation + MMA issue, warp 5: TMA producer.
-constexpr int kSmallRows = 32, kSmallThreads = 192, kSmallStages = 7;   // 196 KiB in flight per CTA: a CTA's k-loop is a serial chain of TMA round trips
+#ifndef TIB_SMALL_TILES
+#define TIB_SMALL_TILES 1
+#endif
+// A pipeline stage holds kSmallTiles consecutive k-tiles (each: weights 16 KiB + digits 12 KiB, fetched as ready-made images).
+// Stages of two or three k-tiles (fewer mbarrier polls per byte at the same ~170-196 KiB in flight) were measured and are no
+// faster (7B, batch 32: 5.34 ms per step with 1 tile x 7 stages, 5.37 with 2 x 3, 5.48 with 3 x 2): the polls are not what paces
+// the k-loop.  Kept as a compile-time knob.
+constexpr int kSmallTiles = TIB_SMALL_TILES;
+constexpr int kSmallRows = 32, kSmallThreads = 192, kSmallStages = kSmallTiles == 1 ? 7 : (kSmallTiles == 2 ? 3 : 2);
 constexpr int kSmallPlaneBytes = kSmallRows * kGemmBK;                       // 4 KiB
-constexpr int kSmallStageBytes = kGemmTileBytes + 3 * kSmallPlaneBytes;      // weights 16 KiB + digits 12 KiB
+constexpr int kSmallTileBytes = kGemmTileBytes + 3 * kSmallPlaneBytes;       // one k-tile: weights 16 KiB + digits 12 KiB
+constexpr int kSmallStageBytes = kSmallTiles * kSmallTileBytes;
 constexpr int kSmallTmemCols = 512;                                          // four accumulator sets of 3 x 32 columns
 constexpr size_t kSmallSmemBytes = (size_t)kSmallStages * kSmallStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2 * kSmallRows * 8;
 
@@ -331,6 +340,7 @@ gemm_i8_tc_small_kernel(const GemmArgs g, const SplitKArgs sk) {
     // lines at the same moment (measured: ~1.2 us per k-step whatever the pipeline depth).  Each column tile therefore
     // starts its k-loop at a different offset and wraps around -- integer sums do not care about the order.
     const int nk = kb1 - kb0, rot = nk > 0 ? (int)((blockIdx.x * 7u) % (unsigned)nk) : 0;
+    const int ns = (nk + kSmallTiles - 1) / kSmallTiles;   // pipeline stages of this CTA: stage i = k-tiles [i * kSmallTiles, ...) of its (rotated) range
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kSmallStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -361,7 +371,7 @@ gemm_i8_tc_small_kernel(const GemmArgs g, const SplitKArgs sk) {
     auto probe4 = [&](uint64_t* bars, int i, int phase_flip) -> int {
         const int j = i + lane;
         bool ok = false;
-        if (lane < 4 && j < nk) {
+        if (lane < 4 && j < ns) {
             const int stj = j % kSmallStages;
             const uint32_t parj = (uint32_t)((j / kSmallStages) & 1) ^ (uint32_t)phase_flip;
             ok = lane == 0 ? mbar_try_wait(&bars[stj], parj) : mbar_test_wait(&bars[stj], parj);
@@ -371,17 +381,21 @@ gemm_i8_tc_small_kernel(const GemmArgs g, const SplitKArgs sk) {
     };
     if (warp == 5) {
         int i = 0;
-        while (i < nk) {
+        while (i < ns) {
             const int nready = probe4(empty, i, 1);   // a fresh mbarrier counts its "previous" phase as complete
             if (lane == 0) {
                 for (int q = 0; q < nready; ++q) {
                     const int ii = i + q, st = ii % kSmallStages;
-                    const int kb = kb0 + (ii + rot < nk ? ii + rot : ii + rot - nk);
+                    const int ntile = min(kSmallTiles, nk - ii * kSmallTiles);
                     if (sk.dbg && blockIdx.x == 0 && blockIdx.y == 0 && ii < 40) sk.dbg[64 + ii] = clock64();
-                    mbar_arrive_expect_tx(&full[st], kSmallStageBytes);
-                    uint8_t* sbase = tiles + (size_t)st * kSmallStageBytes;
-                    bulk_g2s(sbase, g.wt + ((size_t)nb * KB + kb) * kGemmTileBytes, kGemmTileBytes, &full[st]);
-                    bulk_g2s(sbase + kGemmTileBytes, sk.xt + (size_t)kb * 3 * kSmallPlaneBytes, 3 * kSmallPlaneBytes, &full[st]);
+                    mbar_arrive_expect_tx(&full[st], (uint32_t)(ntile * kSmallTileBytes));
+                    for (int j = 0; j < ntile; ++j) {
+                        const int tt = ii * kSmallTiles + j;
+                        const int kb = kb0 + (tt + rot < nk ? tt + rot : tt + rot - nk);
+                        uint8_t* sbase = tiles + (size_t)st * kSmallStageBytes + (size_t)j * kSmallTileBytes;
+                        bulk_g2s(sbase, g.wt + ((size_t)nb * KB + kb) * kGemmTileBytes, kGemmTileBytes, &full[st]);
+                        bulk_g2s(sbase + kGemmTileBytes, sk.xt + (size_t)kb * 3 * kSmallPlaneBytes, 3 * kSmallPlaneBytes, &full[st]);
+                    }
                 }
             }
             __syncwarp();
@@ -393,20 +407,23 @@ gemm_i8_tc_small_kernel(const GemmArgs g, const SplitKArgs sk) {
         // (columns 32 d + m) of the k4 step's accumulator set.
         const uint32_t id = umma_idesc_i8_mn(g.a_signed_b, 1, kGemmBN, 3 * kSmallRows);
         int i = 0;
-        while (i < nk) {
+        while (i < ns) {
             const int nready = probe4(full, i, 0);
             if (lane == 0 && nready > 0) {
                 tc_fence_after();
                 for (int q = 0; q < nready; ++q) {
                     const int ii = i + q, st = ii % kSmallStages;
+                    const int ntile = min(kSmallTiles, nk - ii * kSmallTiles);
                     if (sk.dbg && blockIdx.x == 0 && blockIdx.y == 0 && ii < 40) sk.dbg[128 + ii] = clock64();
-                    const uint32_t sbase = base + st * kSmallStageBytes;
+                    for (int j = 0; j < ntile; ++j) {
+                        const uint32_t sbase = base + st * kSmallStageBytes + j * kSmallTileBytes;
 #pragma unroll
-                    for (int k4 = 0; k4 < kGemmBK / 32; ++k4) {
-                        const uint64_t wdesc = umma_desc_sw128(sbase + k4 * 32);
-                        const uint64_t xdesc = umma_desc_sw128(sbase + kGemmTileBytes + k4 * 32);
-                        // one accumulator set per k4: four independent accumulation chains; the epilogue adds the sets
-                        tc_mma_i8(tmem + k4 * 3 * kSmallRows, wdesc, xdesc, id, ii != 0 ? 1u : 0u);
+                        for (int k4 = 0; k4 < kGemmBK / 32; ++k4) {
+                            const uint64_t wdesc = umma_desc_sw128(sbase + k4 * 32);
+                            const uint64_t xdesc = umma_desc_sw128(sbase + kGemmTileBytes + k4 * 32);
+                            // one accumulator set per k4: four independent accumulation chains; the epilogue adds the sets
+                            tc_mma_i8(tmem + k4 * 3 * kSmallRows, wdesc, xdesc, id, (ii | j) != 0 ? 1u : 0u);
+                        }
                     }
                     tc_commit(&empty[st]);   // the stage may be refilled once these MMAs have read it
                 }
