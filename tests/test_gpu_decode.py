@@ -122,10 +122,11 @@ def test_eos_stop(tb, port):
         assert np.array_equal(stopped, full)
 
 
-@pytest.mark.parametrize("shape,qt,n_new", [("tinyllama", oracle.QINT4, 6), ("llama7b", oracle.QINT4, 3), ("llama7b", oracle.QINT8, 3)])
-def test_full_width_truncated_depth(tb, port, shape, qt, n_new):
-    """Full-width, L = 2: the end-to-end parity case for the big shapes."""
-    meta = meta_with_layers(SHAPES[shape], 2)
+@pytest.mark.parametrize("shape,qt,n_new,layers", [("tinyllama", oracle.QINT4, 6, 2), ("llama7b", oracle.QINT4, 3, 2), ("llama7b", oracle.QINT8, 3, 2),
+                                                   ("llama13b", oracle.QINT8, 2, 1)])
+def test_full_width_truncated_depth(tb, port, shape, qt, n_new, layers):
+    """Full-width, truncated depth: the end-to-end parity case for the big shapes (13B: the widths of configs[3])."""
+    meta = meta_with_layers(SHAPES[shape], layers)
     w = make_model(meta)
     prompt = prompt_tokens(4, meta["vocab"])
     toks, logits, rt, rl = run_pair(tb, port, meta, w, qt, prompt, n_new, 1, 1, max_seq=64, engine=True)

@@ -18,13 +18,16 @@ def _gpu_count():
 
 
 @pytest.mark.skipif(_gpu_count() < 2, reason="tensor parallelism needs at least two GPUs")
-@pytest.mark.parametrize("engine", ["fused", "fused-p2p", "nccl"])
+@pytest.mark.parametrize("engine", ["fused", "fused-p2p", "fused-barrier", "nccl"])
 def test_tp2_tokens_equal_single_gpu(engine):
-    """fused: the persistent kernel with peer stores over NVLink + the barrier across the GPUs (default);
-    fused-p2p: the same kernel with the point-to-point exchange per column slice (opt-in);
+    """fused: the persistent kernel with peer stores over NVLink, the partials exchanged point to point per column slice as tagged
+    8-byte words the reader polls (default, "ll");
+    fused-p2p: the same exchange with separate flags behind a system-scope release;
+    fused-barrier: a barrier across the GPUs + a reduce phase instead (round 1's default);
     nccl: the per-op engine with ncclAllReduce after every row-parallel GEMV (the baseline of SURVEY.md 8e)."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", {"fused": "29533", "fused-p2p": "29535", "nccl": "29534"}[engine], os.path.join(ROOT, "scripts", "tp_check.py")]
+           "--master-port", {"fused": "29533", "fused-p2p": "29535", "fused-barrier": "29536", "nccl": "29534"}[engine],
+           os.path.join(ROOT, "scripts", "tp_check.py")]
     env = dict(os.environ)
     env.pop("TURBOINFER_B200_TP_ENGINE", None)
     env.pop("TURBOINFER_B200_TP_REDUCE", None)
@@ -32,5 +35,7 @@ def test_tp2_tokens_equal_single_gpu(engine):
         env["TURBOINFER_B200_TP_ENGINE"] = "nccl"
     if engine == "fused-p2p":
         env["TURBOINFER_B200_TP_REDUCE"] = "p2p"
+    if engine == "fused-barrier":
+        env["TURBOINFER_B200_TP_REDUCE"] = "barrier"
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert r.returncode == 0 and "TP CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

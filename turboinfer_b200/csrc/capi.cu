@@ -395,6 +395,7 @@ struct Model {
     void* peer_base[kMaxTp] = {};
     size_t xchg_flag_off = 0, xchg_part_off = 0, xchg_part_bytes = 0;
     bool tp_p2p = false;   // point-to-point exchange per column slice instead of the barrier across the GPUs + reduce phase
+    bool tp_ll = false;    // ... with the partials as tagged 8-byte words polled by the reader (one NVLink crossing per exchange)
     DevBuf<MegaPhase> phases;
     DevBuf<ProdRec> prod;
     int nphases = 0;
@@ -758,7 +759,7 @@ int tp_exchange_setup(Model& m) {
     m.xchg_flag_off = (bar_bytes + 255) & ~size_t(255);                                     // flags [2 buffers][P][256 CTAs]
     m.xchg_key_off = m.xchg_flag_off + (size_t)2 * kMaxTp * 256 * sizeof(unsigned int);      // arg-max keys [2][kMaxTp]
     m.xchg_part_off = m.xchg_key_off + 256;
-    m.xchg_part_bytes = ((size_t)P * H * sizeof(float) + 255) & ~size_t(255);
+    m.xchg_part_bytes = ((size_t)P * H * sizeof(unsigned long long) + 255) & ~size_t(255);   // sized for the tagged 8-byte words of the LL exchange
     const size_t total = m.xchg_part_off + 2 * m.xchg_part_bytes;
     CK(cudaMalloc(&m.xchg, total));
     CK(cudaMemset(m.xchg, 0, total));
@@ -933,7 +934,7 @@ int build_mega(Model& m) {
     lm.rms_eps = m.cfg.rms_eps;
     lm.epi = EPI_LOGITS;
     lm.out = m.logits.p;
-    m.lm_sharded = tp && !m.tp_p2p && m.lm_head_shard != nullptr;
+    m.lm_sharded = tp && m.lm_head_shard != nullptr;
     if (const char* e = getenv("TURBOINFER_B200_TP_LMHEAD")) if (std::string(e) == "replicated") m.lm_sharded = false;   // A/B
     if (m.lm_sharded) {
         // column-parallel lm_head: every rank computes the logits of its V / tp columns (stored at their
@@ -1039,6 +1040,7 @@ int run_mega(Model& m, int n_prompt, int n_steps, int first_sample) {
             a.peer_keys[r] = reinterpret_cast<unsigned long long*>(b + m.xchg_key_off);
         }
         a.tp_p2p = m.tp_p2p ? 1 : 0;
+        a.tp_ll = m.tp_ll ? 1 : 0;
         a.mg_seq = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(m.xchg) + (size_t)kBarWords * kBarStride * sizeof(unsigned int));
     }
     void* args[] = {&a};
@@ -2474,7 +2476,11 @@ int ti_b200_model_finalize(ti_model_t h) {
     if (m.tp > 1) TRY(m.ar_tmp.alloc(H));
     if (m.tp_fused) {
         const char* red = getenv("TURBOINFER_B200_TP_REDUCE");   // "p2p" (per column slice) or "barrier" (all GPUs + reduce phase)
-        m.tp_p2p = (red ? std::string(red) == "p2p" : false) && g_num_sms <= 256;
+        // how the row-parallel partials are reduced: "ll" (default) point-to-point with tagged words, "p2p" point-to-point with
+        // flags, "barrier" the barrier across the GPUs + reduce phase
+        const std::string mode = red ? std::string(red) : std::string("ll");
+        m.tp_p2p = (mode == "p2p" || mode == "ll") && g_num_sms <= 256;
+        m.tp_ll = m.tp_p2p && mode == "ll";
         TRY(tp_exchange_setup(m));
     }
     TRY(m.prompt.alloc(16));

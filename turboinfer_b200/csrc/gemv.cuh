@@ -252,6 +252,9 @@ struct PhaseCtx {
     float* const* peers;
     int npeers;
     size_t peer_off;
+    // != 0: the partial buffers hold 8-byte words {value, ll_seq} (one single-copy-atomic store per element: the reader polls the
+    // tag inside the word it needs, no fence and no flag; the element index is the same, the stride 8 bytes)
+    unsigned int ll_seq;
 };
 
 // Position in the ring, carried across the GEMVs of a launch (no divisions per phase): stage and the parity of its use.
@@ -800,7 +803,14 @@ __device__ __forceinline__ XStats gemv_epilogue(const GemvArgs& a, const Slab& s
             if (a.epi == EPI_RESIDUAL) y = (first ? pre.r0 : ld_act(resid + n, ctx.coherent)) + y;
             else if (a.epi == EPI_RELU) y = fmaxf(y, 0.f);
             if (ctx.npeers > 0) {
-                for (int r = 0; r < ctx.npeers; ++r) ctx.peers[r][ctx.peer_off + n] = y;   // NVLink stores (one local)
+                if (ctx.ll_seq != 0u) {
+                    const unsigned long long word = ((unsigned long long)ctx.ll_seq << 32) | (unsigned long long)__float_as_uint(y);
+                    for (int r = 0; r < ctx.npeers; ++r)
+                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(ctx.peers[r]) + ctx.peer_off + n), "l"(word)
+                                     : "memory");
+                } else {
+                    for (int r = 0; r < ctx.npeers; ++r) ctx.peers[r][ctx.peer_off + n] = y;   // NVLink stores (one local)
+                }
             } else {
                 a.out[n] = y;
             }
@@ -851,7 +861,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const __grid_cons
         return;
     }
     pdl_wait_prior_grid();  // x (and resid / pos) come from the previous kernel in the stream
-    const PhaseCtx ctx{false, -1, nullptr, nullptr, 0, 0};
+    const PhaseCtx ctx{false, -1, nullptr, nullptr, 0, 0, 0u};
     const EpiPre pre = gemv_epilogue_prefetch(a, slab, a.resid, ctx, tid);
     const float s_x = gemv_stage_x<BITS>(a, a.x, sm, slab, false, tid, warp, lane);
     gemv_consume<BITS, DBG>(a, slab, sm, it, make_consume_plan(a.L, slab, warp, lane), warp, lane);

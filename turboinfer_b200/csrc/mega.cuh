@@ -73,11 +73,14 @@ struct MegaArgs {
     int tp, tp_rank;
     float* peer_part[2][kMaxTp];       // [buffer][rank] -> that rank's partial buffer, layout [source rank][H]
     unsigned int* peer_bar[kMaxTp];    // [rank] -> that rank's multi-GPU barrier words (kBarWords x kBarStride)
-    unsigned int* mg_seq;              // device scalar: multi-GPU barriers / exchanges passed so far (carried across launches)
+    unsigned int* mg_seq;              // two device words carried across launches: [0] barriers across the GPUs passed so far, [1] point-to-point exchanges
     // point-to-point variant (tp_p2p): CTA b of every rank owns the same column slice, so only the P CTAs "b" have to meet:
     // flags [source rank][CTA] per partial buffer, written by the source with a system-scope release
     unsigned int* peer_flag[2][kMaxTp];
     int tp_p2p;
+    // tp_ll (with tp_p2p): the partials travel as 8-byte words {value, exchange number} -- a reader polls the words themselves, so an
+    // exchange costs ONE NVLink crossing (no release fence waiting for the stores' acknowledgements, no separate flag)
+    int tp_ll;
     // tensor parallel with the lm_head sharded over the vocabulary: every rank's local (max, index) key of a
     // sampling step goes to slot [step & 1][rank] of every rank's exchange block (PH_KEYX phase), the barrier across the GPUs
     // follows, and the token is the maximum of the P keys -- n_head = 2 phases run on sampling steps only (lm_head, PH_KEYX)
@@ -805,7 +808,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
             }
             // the point-to-point variant keeps its own exchange count in the same word (written by consumer thread 0 at the
             // end of the launch); this warp passes no barrier across the GPUs in that mode and must not write a stale value back
-            if (m.tp > 1 && !m.tp_p2p && blockIdx.x == 0 && lane == 0) *m.mg_seq = kk;
+            if (m.tp > 1 && blockIdx.x == 0 && lane == 0) m.mg_seq[0] = kk;   // (the exchange count lives in its own word, mg_seq[1])
         }
         return;
     }
@@ -867,7 +870,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
     };
     stage_descriptor(0, 0);   // the first phase's descriptor; every later one is staged during its predecessor
     bar_sync(1, kConsumerThreads);
-    unsigned int ex_seq = (m.tp > 1 && m.tp_p2p) ? *m.mg_seq : 0u;   // point-to-point exchanges since the group was formed
+    unsigned int ex_seq = (m.tp > 1 && m.tp_p2p) ? m.mg_seq[1] : 0u;   // point-to-point exchanges since the group was formed
     int token = m.st->token;  // decode-only launches continue from the token the previous launch picked
     for (int s = 0; s < m.n_steps; ++s) {
         const bool sample = s >= m.first_sample;
@@ -901,8 +904,9 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
             }
             const bool gemv_here = PG.type == PH_GEMV && (int)blockIdx.x < PG.g.L.P;
             const bool to_peers = m.tp > 1 && PG.type == PH_GEMV && PG.mgpu != 0;
+            // (a point-to-point phase bumps ex_seq in its tail, after the epilogue: the epilogue tags its stores with the NEXT number)
             const PhaseCtx ctx{true, pos, is_head ? &m.keys[s & 1] : nullptr, to_peers ? m.peer_part[PG.part_sel] : nullptr, to_peers ? m.tp : 0,
-                               (size_t)m.tp_rank * (size_t)m.H};
+                               (size_t)m.tp_rank * (size_t)m.H, (to_peers && m.tp_ll && PG.mgpu == 2) ? ex_seq + 1u : 0u};
             Slab slab{};
             EpiPre pre{};
             XPre xpre;
@@ -950,6 +954,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                     // its P flags and sums residual + partials in rank order -- every rank reads the same stored values, so
                     // the replicated residual stream stays bit-identical.
                     ++ex_seq;
+                    if (!m.tp_ll) {
                     bar_sync(1, kConsumerThreads);   // every thread's peer stores are ordered before the flags
                     if (warp == 0) {
                         if (lane < m.tp) {
@@ -964,6 +969,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                         __syncwarp();
                     }
                     bar_sync(1, kConsumerThreads);
+                    }
                     out_st = XStats{0.f, 0.f};
                     if (gemv_here) {
                         const float* part = m.peer_part[P.part_sel][m.tp_rank];
@@ -972,6 +978,22 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                             const int n = slab.col0 + c;
                             if (n >= Hn) continue;
                             float v = ld_act(resid + n, P.resid_src != SRC_EMB);
+                            if (m.tp_ll) {
+                                // the thread that stored column n on every rank tagged it with this exchange's number: wait for the P
+                                // words of the column (its own among them) and add them in rank order
+                                const unsigned long long* part8 = reinterpret_cast<const unsigned long long*>(part);
+                                for (int r = 0; r < m.tp; ++r) {
+                                    const unsigned long long* w = part8 + (size_t)r * Hn + n;
+                                    unsigned long long word;
+                                    const long long t0 = clock64();
+                                    while (true) {
+                                        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(word) : "l"(w) : "memory");
+                                        if ((unsigned int)(word >> 32) == ex_seq) break;
+                                        if (clock64() - t0 > 120000000000LL) __trap();
+                                    }
+                                    v += __uint_as_float((unsigned int)word);
+                                }
+                            } else
                             for (int r = 0; r < m.tp; ++r) v += __ldcg(part + (size_t)r * Hn + n);
                             P.g.out[n] = v;
                             out_st.ss = fmaf(v, v, out_st.ss);
@@ -1023,7 +1045,7 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
         publish(last, token);
     }
     if (blockIdx.x == 0 && tid == 0) {
-        if (m.tp > 1 && m.tp_p2p) *m.mg_seq = ex_seq;
+        if (m.tp > 1 && m.tp_p2p) m.mg_seq[1] = ex_seq;
         m.st->pos = pos0 + m.n_steps;
         m.st->token = token;
         const int sampled = m.n_steps - m.first_sample;
