@@ -956,6 +956,7 @@ int build_mega(Model& m) {
     m.mega_max_kpad = max_kpad;
     m.mega_max_units = max_units;
     m.mega_attn_floats = attn_scratch_floats(m.attn_dim, kConsumerThreads);
+    if (m.tp_ll) m.mega_attn_floats = std::max(m.mega_attn_floats, 4 * max_units * m.tp);   // the exchange hands (column, rank) values over through this scratch
     m.mega_stages = 0;
     int max_stages = kMaxStages;
     if (const char* e = getenv("TURBOINFER_B200_STAGES")) max_stages = std::max(2, std::min(kMaxStages, atoi(e)));   // experiments

@@ -974,15 +974,18 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                     if (gemv_here) {
                         const float* part = m.peer_part[P.part_sel][m.tp_rank];
                         const int Hn = P.g.L.N;
-                        for (int c = tid; c < slab.ncols; c += kConsumerThreads) {
-                            const int n = slab.col0 + c;
-                            if (n >= Hn) continue;
-                            float v = ld_act(resid + n, P.resid_src != SRC_EMB);
-                            if (m.tp_ll) {
-                                // the thread that stored column n on every rank tagged it with this exchange's number: wait for the P
-                                // words of the column (its own among them) and add them in rank order
-                                const unsigned long long* part8 = reinterpret_cast<const unsigned long long*>(part);
-                                for (int r = 0; r < m.tp; ++r) {
+                        if (m.tp_ll) {
+                            // Every (column, rank) word of this CTA's slice is polled by its OWN thread -- ncols * P <= 512 polls in
+                            // flight at once, one L2 round trip whatever P is (one thread walking the P words of a column pays P
+                            // round trips: 8 x 0.6 us at TP 8) -- and handed over through shared memory (the attention scratch, idle
+                            // in a GEMV phase).  The stores of the slice were tagged with this exchange's number by the thread that
+                            // owns the column on each rank.
+                            const unsigned long long* part8 = reinterpret_cast<const unsigned long long*>(part);
+                            const int nw = slab.ncols * m.tp;
+                            for (int idx = tid; idx < nw; idx += kConsumerThreads) {
+                                const int c = idx / m.tp, r = idx - c * m.tp, n = slab.col0 + c;
+                                float val = 0.f;
+                                if (n < Hn) {
                                     const unsigned long long* w = part8 + (size_t)r * Hn + n;
                                     unsigned long long word;
                                     const long long t0 = clock64();
@@ -991,14 +994,26 @@ __global__ void __maxnreg__(96) mega_decode_kernel(const __grid_constant__ MegaA
                                         if ((unsigned int)(word >> 32) == ex_seq) break;
                                         if (clock64() - t0 > 120000000000LL) __trap();
                                     }
-                                    v += __uint_as_float((unsigned int)word);
+                                    val = __uint_as_float((unsigned int)word);
                                 }
-                            } else
-                            for (int r = 0; r < m.tp; ++r) v += __ldcg(part + (size_t)r * Hn + n);
+                                attn_sm[idx] = val;
+                            }
+                            bar_sync(1, kConsumerThreads);
+                        }
+                        for (int c = tid; c < slab.ncols; c += kConsumerThreads) {
+                            const int n = slab.col0 + c;
+                            if (n >= Hn) continue;
+                            float v = ld_act(resid + n, P.resid_src != SRC_EMB);
+                            if (m.tp_ll) {
+                                for (int r = 0; r < m.tp; ++r) v += attn_sm[c * m.tp + r];   // in rank order: the same sums on every rank
+                            } else {
+                                for (int r = 0; r < m.tp; ++r) v += __ldcg(part + (size_t)r * Hn + n);
+                            }
                             P.g.out[n] = v;
                             out_st.ss = fmaf(v, v, out_st.ss);
                             out_st.am = fmaxf(out_st.am, fabsf(P.g.next_norm_w ? v * P.g.next_norm_w[n] : v));
                         }
+                        if (m.tp_ll) bar_sync(1, kConsumerThreads);   // the scratch is free again before anybody reuses it
                     }
                 }
             } else if (P.type == PH_KEYX) {
