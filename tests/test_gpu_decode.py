@@ -183,6 +183,11 @@ def test_model_from_quantized_integers(tb, port, qt):
             c.set_tensor_q(name, q, qt, 0.0, zp)
         with pytest.raises(RuntimeError):
             c.set_tensor_q("norm.weight", q[:1], qt, scale, zp)
+        if qt == oracle.QINT4:   # integers outside the nibble code are refused instead of wrapping
+            bad = q.copy()
+            bad[0, 0] = 9
+            with pytest.raises(RuntimeError, match="INT4 integers"):
+                c.set_tensor_q(name, bad, qt, scale, zp)
         c.free()
     finally:
         a.free()

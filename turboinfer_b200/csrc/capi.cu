@@ -2383,6 +2383,13 @@ int ti_b200_model_set_tensor_q(ti_model_t h, const char* name, const void* q_hos
     if (qtype != m->cfg.qtype) return fail("tensor '%s' is %s but the model was created for %s weights", name, qtype == TI_Q_INT4 ? "INT4" : "INT8",
                                            m->cfg.qtype == TI_Q_INT4 ? "INT4" : "INT8");
     if (!(scale > 0.f) || !std::isfinite(scale) || !std::isfinite(zero_point)) return fail("tensor '%s': scale must be positive and finite", name);
+    if (qtype == TI_Q_INT4) {   // the nibble code holds [-8, 7] (zero_point 0) or [0, 15]: anything else would wrap silently when packed
+        const int32_t* q4 = static_cast<const int32_t*>(q_host);
+        const int32_t lo = zero_point == 0.0f ? -8 : 0, hi = zero_point == 0.0f ? 7 : 15;
+        int32_t mn = q4[0], mx = q4[0];
+        for (size_t i = 1; i < rows * cols; ++i) { mn = std::min(mn, q4[i]); mx = std::max(mx, q4[i]); }
+        if (mn < lo || mx > hi) return fail("tensor '%s': INT4 integers must lie in [%d, %d] (found %d .. %d)", name, lo, hi, mn, mx);
+    }
     RawTensor q;
     q.kind = qtype == TI_Q_INT8 ? 1 : 2;
     q.scale = scale;
