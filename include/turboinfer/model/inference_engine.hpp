@@ -65,8 +65,11 @@ public:
     size_t memory_usage() const;
     std::string performance_stats() const;
 
-    // exposed for tests (private in the reference, :248-255): one incremental forward pass, logits [1, 1, vocab]
+    // exposed for tests (private in the reference, :248-255)
+    /// forward_pass_incremental (:1493-1552): appends the tokens to the cached sequence; logits [1, tokens, vocab]
     core::Tensor forward_pass_incremental(const std::vector<int>& tokens);
+    /// forward_pass (:1429-1491): the whole sequence from an empty cache; logits of every position, [1, tokens, vocab]
+    core::Tensor forward_pass(const std::vector<int>& tokens);
 
 private:
     void validate_input_tokens(const std::vector<int>& tokens) const;

@@ -228,6 +228,17 @@ static void test_engine_gpu() {
             seq.push_back(best);
             if (i + 1 < a.tokens.size()) lg = eng.forward_pass_incremental({best});
         }
+        {   // forward_pass: the whole sequence from an empty cache, logits of every position; its last row picks generate()'s first token
+            Tensor all = eng.forward_pass(prompt);
+            CHECK(all.shape().ndim() == 3 && all.shape().size(0) == 1 && all.shape().size(1) == prompt.size() && all.shape().size(2) == 96);
+            const float* row = all.data_ptr<float>() + (prompt.size() - 1) * 96;
+            int best = 0;
+            for (int v = 1; v < 96; ++v) if (row[v] > row[best]) best = v;
+            CHECK(best == a.tokens[prompt.size()]);
+            Tensor again = eng.forward_pass(prompt);                       // deterministic, and independent of what was cached before
+            CHECK(std::memcmp(all.data(), again.data(), all.byte_size()) == 0);
+            CHECK_THROWS(eng.forward_pass({}), std::runtime_error);
+        }
         CHECK_THROWS(eng.generate({}, 4), std::runtime_error);
         CHECK_THROWS(eng.generate(std::vector<int>(65, 1), 4), std::runtime_error);
         model::GenerationResult longrun = eng.generate(prompt, 1000);      // stops at max_sequence_length (or EOS)

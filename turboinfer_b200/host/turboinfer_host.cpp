@@ -647,6 +647,12 @@ core::Tensor InferenceEngine::forward_pass_incremental(const std::vector<int>& t
     return logits;
 }
 
+core::Tensor InferenceEngine::forward_pass(const std::vector<int>& tokens) {
+    validate_input_tokens(tokens);
+    reset_state();
+    return forward_pass_incremental(tokens);
+}
+
 GenerationResult InferenceEngine::generate(const std::vector<int>& input_tokens, size_t max_new_tokens, bool include_logprobs) {
     validate_input_tokens(input_tokens);
     const auto t0 = std::chrono::high_resolution_clock::now();
