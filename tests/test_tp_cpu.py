@@ -48,6 +48,30 @@ def _worker(rank, world, port_no, out):
             # a shard quantized on its own would NOT be the reference's integers (different min/max -> different scale)
             s_shard, _ = port.quant_info(np.ascontiguousarray(w[rows] * (0.5 if rank else 1.0)), qt, True)
             ok &= (s_shard != s) or rank == 0
+        # The exchange of the fused engine: every rank hands its fp32 partial of a row-parallel GEMV to every rank as words tagged
+        # with the exchange number, and every rank adds residual + partial_0 + ... + partial_{P-1} IN RANK ORDER from what was
+        # stored -- the same additions on every rank, so the replicated residual stream stays bit-identical (a tree or
+        # arrival-order sum would not guarantee that).  Restated with an all_gather of {value bits, tag} words.
+        resid = rng.standard_normal(N).astype(np.float32)
+        for seq in (1, 2, 3):
+            partial = np.random.default_rng(100 * seq + rank).standard_normal(N).astype(np.float32)
+            words = torch.from_numpy(((np.uint64(seq) << np.uint64(32)) | partial.view(np.uint32).astype(np.uint64)).view(np.int64))
+            got = [torch.empty_like(words) for _ in range(world)]
+            dist.all_gather(got, words)
+            acc = resid.copy()
+            for r in range(world):
+                w64 = got[r].numpy().view(np.uint64)
+                ok &= bool(np.all((w64 >> np.uint64(32)) == np.uint64(seq)))            # every word carries this exchange's number
+                acc = acc + (w64 & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32)
+            mine = torch.from_numpy(acc.view(np.int32).copy())
+            everyone = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(everyone, mine)
+            ok &= all(torch.equal(everyone[0], e) for e in everyone)                   # bit-identical on every rank
+            expect = resid.copy()
+            for r in range(world):
+                expect = expect + np.random.default_rng(100 * seq + r).standard_normal(N).astype(np.float32)
+            ok &= bool(np.array_equal(acc, expect))
+            resid = acc
         # rank plumbing of bench.py: id broadcast over a side channel, max over ranks of the timed region
         box = [b"\\x07" * 128 if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
